@@ -1,0 +1,59 @@
+// TEST INFRASTRUCTURE ONLY (oracle build).
+//
+// The eleven non-arithmetic symbols the reference's engine translation units reference but whose real
+// definitions live in files that need libsndfile / Vulkan / VST3 / leveldb / midi-parser, none of which is
+// on the mixing hot path. Everything that touches a sample VALUE is compiled from the
+// reference's own sources; these stubs only allocate memory or return "absent".
+#include <cstdlib>
+#include <cstring>
+#include <utility>
+
+#include "core/midi_file.h"
+#include "dsp/sample.h"
+#include "gfx/waveform_visual.h"
+#include "plughost/plugin_manager.h"
+
+namespace wb {
+
+// --- dsp/sample.cpp stand-ins (real file needs libsndfile/vorbis/dr_mp3 for decoding only) -------------
+Sample::Sample(AudioFormat format, uint32_t sample_rate) : format(format), sample_rate(sample_rate) {}
+
+Sample::Sample(Sample&& other) noexcept
+    : name(std::move(other.name)),
+      path(std::move(other.path)),
+      format(std::exchange(other.format, AudioFormat::Unknown)),
+      channels(std::exchange(other.channels, 0)),
+      sample_rate(std::exchange(other.sample_rate, 0)),
+      count(std::exchange(other.count, 0)),
+      sample_data(std::move(other.sample_data)) {}
+
+Sample::~Sample() {
+  for (auto p : sample_data)
+    std::free(p);
+}
+
+// Fresh zeroed channels of n frames + Sample::sample_padding zero frames — the shape load_file produces
+// (dsp/sample.cpp:127,140). The harness fills the first n frames afterwards.
+void Sample::resize(size_t n, uint32_t new_channels, bool) {
+  for (auto p : sample_data)
+    std::free(p);
+  sample_data.resize(new_channels);
+  size_t bytes = (n + sample_padding) * get_audio_format_size(format);
+  for (uint32_t c = 0; c < new_channels; c++)
+    sample_data[c] = (std::byte*)std::calloc(1, bytes);
+  channels = new_channels;
+  count = n;
+}
+
+std::optional<Sample> Sample::load_file(const std::filesystem::path&) noexcept { return {}; }
+
+// --- gfx/waveform_visual.cpp stand-ins (real file uploads min/max mip-maps to the Vulkan renderer) -----
+WaveformVisual::~WaveformVisual() {}
+WaveformVisual* WaveformVisual::create(Sample*, WaveformVisualQuality) { return new WaveformVisual{}; }
+
+// --- plughost / midi file stand-ins ----------------------------------------------------------------------
+PluginInterface* pm_open_plugin(PluginUID) { return nullptr; }
+void pm_close_plugin(PluginInterface*) {}
+bool load_notes_from_file(MidiNoteBuffer&, const std::filesystem::path&) { return false; }
+
+}  // namespace wb

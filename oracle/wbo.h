@@ -1,0 +1,77 @@
+/* TEST INFRASTRUCTURE ONLY — never linked into, imported by or executed from the product path.
+ *
+ * wbo.h — the scenario API shared by the two CPU checkers of the whitebox mixing hot path:
+ *
+ *   oracle/_ref/libwbref.so  the reference's OWN Engine::process, compiled unmodified from
+ *                            /root/reference/src (engine/engine.cpp:1576-1654, engine/track.cpp:587-736,
+ *                            dsp/sampler.cpp:88-210 ...) by oracle/Makefile, driven by ref_harness.cpp.
+ *   oracle/liboracle.so      a plain-C restatement of the same algorithm (wb_oracle.c), pinned against
+ *                            libwbref.so and against tests/golden/ vectors produced by libwbref.so.
+ *
+ * Both export exactly these symbols so one ctypes wrapper (tests/oracle_api.py) drives either.
+ * Calls mirror the reference's editing API (Engine::add_track / add_audio_clip / play / process,
+ * Track::set_volume / set_pan / set_mute) so a scenario reads like a reference session.
+ */
+#ifndef WBO_H
+#define WBO_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* wb::AudioFormat values (src/core/audio_format.h:7-20) used by Sample (src/dsp/sample.h:18-28). */
+enum { WBO_FMT_I16 = 3, WBO_FMT_I24 = 5, WBO_FMT_I32 = 7, WBO_FMT_F32 = 9 };
+
+typedef struct wbo_session wbo_session;
+
+/* Engine::set_audio_channel_config(0, out_channels, block, rate) + set_bpm(bpm). */
+wbo_session* wbo_create(uint32_t out_channels, uint32_t block_frames, uint32_t sample_rate, double bpm);
+void wbo_destroy(wbo_session*);
+const char* wbo_kind(void); /* "reference" or "port" */
+
+/* Engine::add_track + Track::set_volume/set_pan/set_mute. Returns the track index. */
+int wbo_add_track(wbo_session*, float volume_db, float pan, int mute);
+void wbo_set_volume(wbo_session*, int track, float db);
+void wbo_set_pan(wbo_session*, int track, float pan);
+void wbo_set_mute(wbo_session*, int track, int mute);
+
+/* A resident Sample (planar channels, `frames` elements each + 16 zero frames of padding,
+ * sample.cpp:127,140). I24 data is passed already widened to int32 (sample.cpp:20). Returns id. */
+int wbo_add_sample(wbo_session*, int format, uint32_t channels, uint64_t frames, uint32_t sample_rate,
+                   const void* const* planar);
+
+/* Engine::add_audio_clip(track, name, min_beat, max_beat, start_offset_frames, {asset, speed, gain}). */
+int wbo_add_clip(wbo_session*, int track, int sample, double min_beat, double max_beat, double start_offset,
+                 double speed, float gain);
+
+void wbo_set_playhead(wbo_session*, double beat); /* Engine::set_playhead_position */
+void wbo_play(wbo_session*);                      /* Engine::play */
+void wbo_stop(wbo_session*);                      /* Engine::stop */
+
+/* n_blocks consecutive Engine::process callbacks.
+ *   out   [n_blocks][out_channels][block_frames] f32 — the clamped master bus of each callback
+ *   peaks [n_blocks][n_tracks][2] f32 — VUMeter block peak of each track/channel, i.e. the value
+ *         push_samples (vu_meter.h:20-30) offers to `level` for that callback (may be NULL). */
+int wbo_process(wbo_session*, uint32_t n_blocks, float* out, float* peaks);
+
+double wbo_sampler_offset(wbo_session*, int track); /* Track::sampler.sample_offset_ */
+double wbo_sample_position(wbo_session*);           /* Engine::sample_position */
+double wbo_playhead(wbo_session*);                  /* Engine::playhead */
+
+/* Host-side scalar math feeding the kernel (core/panning_law.cpp:9-32, core/core_math.h:83-89). */
+void wbo_panning_coefs(float pan, float* left, float* right);
+float wbo_db_to_linear(float db);
+
+/* planar f32 -> interleaved device format (core/audio_format_conv.cpp:5-106). fmt: WBO_FMT_I16,
+ * WBO_FMT_I24 (packed 3 bytes), 6 = I24_X8, WBO_FMT_I32, WBO_FMT_F32. */
+void wbo_interleave(void* dst, const float* const* src, uint32_t offset, uint32_t frames, uint32_t channels,
+                    int fmt);
+
+/* CPU timing of the same loop (bench.py cpu_baseline / --impl reference only): runs n_blocks callbacks
+ * without copying results out and returns elapsed seconds (steady clock). */
+double wbo_time_process(wbo_session*, uint32_t n_blocks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

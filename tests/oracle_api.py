@@ -1,0 +1,159 @@
+"""ctypes wrapper over the CPU checkers (oracle/wbo.h). TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+Two libraries export the same wbo_* symbols:
+  oracle/_ref/libwbref.so  - the reference's own Engine::process (built from /root/reference/src)
+  oracle/liboracle.so      - the plain-C restatement (oracle/wb_oracle.c)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libwbref.so")
+PORT_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+
+FMT_I16, FMT_I24, FMT_I24_X8, FMT_I32, FMT_F32 = 3, 5, 6, 7, 9
+_NP = {FMT_I16: np.int16, FMT_I24: np.int32, FMT_I32: np.int32, FMT_F32: np.float32}
+
+_libs = {}
+
+
+def _load(path):
+    if path in _libs:
+        return _libs[path]
+    lib = C.CDLL(path)
+    vp, u32, u64, dbl, flt, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_double, C.c_float, C.c_int
+    lib.wbo_create.restype = vp
+    lib.wbo_create.argtypes = [u32, u32, u32, dbl]
+    lib.wbo_destroy.argtypes = [vp]
+    lib.wbo_kind.restype = C.c_char_p
+    lib.wbo_add_track.argtypes = [vp, flt, flt, i32]
+    lib.wbo_set_volume.argtypes = [vp, i32, flt]
+    lib.wbo_set_pan.argtypes = [vp, i32, flt]
+    lib.wbo_set_mute.argtypes = [vp, i32, i32]
+    lib.wbo_add_sample.argtypes = [vp, i32, u32, u64, u32, C.POINTER(vp)]
+    lib.wbo_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
+    lib.wbo_set_playhead.argtypes = [vp, dbl]
+    lib.wbo_play.argtypes = [vp]
+    lib.wbo_stop.argtypes = [vp]
+    lib.wbo_process.argtypes = [vp, u32, vp, vp]
+    lib.wbo_time_process.argtypes = [vp, u32]
+    lib.wbo_time_process.restype = dbl
+    for f in ("wbo_sampler_offset",):
+        getattr(lib, f).argtypes = [vp, i32]
+        getattr(lib, f).restype = dbl
+    for f in ("wbo_sample_position", "wbo_playhead"):
+        getattr(lib, f).argtypes = [vp]
+        getattr(lib, f).restype = dbl
+    lib.wbo_panning_coefs.argtypes = [flt, C.POINTER(flt), C.POINTER(flt)]
+    lib.wbo_db_to_linear.argtypes = [flt]
+    lib.wbo_db_to_linear.restype = flt
+    lib.wbo_interleave.argtypes = [vp, C.POINTER(vp), u32, u32, u32, i32]
+    _libs[path] = lib
+    return lib
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def have_port():
+    return os.path.exists(PORT_SO)
+
+
+def lib(kind):
+    return _load(REF_SO if kind == "reference" else PORT_SO)
+
+
+class Session:
+    """One engine session on a CPU checker; mirrors the reference's editing API."""
+
+    def __init__(self, kind, out_channels=2, block=512, rate=48000, bpm=120.0):
+        self.lib = lib(kind)
+        self.kind = kind
+        self.C, self.B, self.rate = out_channels, block, rate
+        self.h = self.lib.wbo_create(out_channels, block, rate, bpm)
+        self.n_tracks = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.wbo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def add_track(self, volume_db=0.0, pan=0.0, mute=False):
+        self.n_tracks += 1
+        return self.lib.wbo_add_track(self.h, volume_db, pan, int(mute))
+
+    def set_volume(self, t, db):
+        self.lib.wbo_set_volume(self.h, t, db)
+
+    def set_pan(self, t, pan):
+        self.lib.wbo_set_pan(self.h, t, pan)
+
+    def set_mute(self, t, m):
+        self.lib.wbo_set_mute(self.h, t, int(m))
+
+    def add_sample(self, data, rate, fmt=FMT_F32):
+        """data: [channels][frames] array of the format's dtype."""
+        data = np.ascontiguousarray(data, dtype=_NP[fmt])
+        ch, frames = data.shape
+        ptrs = (C.c_void_p * ch)(*[data[c].ctypes.data for c in range(ch)])
+        return self.lib.wbo_add_sample(self.h, fmt, ch, frames, rate, ptrs)
+
+    def add_clip(self, track, sample, min_beat, max_beat, start_offset=0.0, speed=1.0, gain=1.0):
+        return self.lib.wbo_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain)
+
+    def set_playhead(self, beat):
+        self.lib.wbo_set_playhead(self.h, beat)
+
+    def play(self):
+        self.lib.wbo_play(self.h)
+
+    def stop(self):
+        self.lib.wbo_stop(self.h)
+
+    def process(self, n_blocks):
+        out = np.zeros((n_blocks, self.C, self.B), np.float32)
+        peaks = np.zeros((n_blocks, self.n_tracks, 2), np.float32)
+        self.lib.wbo_process(self.h, n_blocks, out.ctypes.data, peaks.ctypes.data)
+        return out, peaks
+
+    def time_process(self, n_blocks):
+        return self.lib.wbo_time_process(self.h, n_blocks)
+
+    def sampler_offset(self, t):
+        return self.lib.wbo_sampler_offset(self.h, t)
+
+    def sample_position(self):
+        return self.lib.wbo_sample_position(self.h)
+
+    def playhead(self):
+        return self.lib.wbo_playhead(self.h)
+
+
+def panning_coefs(kind, pan):
+    l, r = C.c_float(), C.c_float()
+    lib(kind).wbo_panning_coefs(pan, C.byref(l), C.byref(r))
+    return np.float32(l.value), np.float32(r.value)
+
+
+def db_to_linear(kind, db):
+    return np.float32(lib(kind).wbo_db_to_linear(db))
+
+
+def interleave(kind, planar, fmt, offset=0, frames=None):
+    """planar: [channels][n] f32 -> interleaved bytes in device format `fmt`."""
+    planar = np.ascontiguousarray(planar, np.float32)
+    ch, n = planar.shape
+    frames = n - offset if frames is None else frames
+    size = {FMT_I16: 2, FMT_I24: 3, FMT_I24_X8: 4, FMT_I32: 4, FMT_F32: 4}[fmt]
+    dst = np.zeros(frames * ch * size, np.uint8)
+    ptrs = (C.c_void_p * ch)(*[planar[c].ctypes.data for c in range(ch)])
+    lib(kind).wbo_interleave(dst.ctypes.data, ptrs, offset, frames, ch, fmt)
+    return dst
