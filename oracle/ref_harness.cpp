@@ -69,7 +69,8 @@ int wbo_add_sample(wbo_session* s, int format, uint32_t channels, uint64_t frame
   smp.name = "s" + std::to_string(s->uid) + "_" + std::to_string(s->samples.size());
   smp.path = smp.name;
   smp.resize(frames, channels);
-  size_t bytes = frames * get_audio_format_size((AudioFormat)format);
+  size_t elem = (AudioFormat)format == AudioFormat::I24 ? 4 : get_audio_format_size((AudioFormat)format);
+  size_t bytes = frames * elem;  // I24 = int32 container, see ref_stubs.cpp Sample::resize
   for (uint32_t c = 0; c < channels; c++)
     std::memcpy(smp.sample_data[c], planar[c], bytes);
   SampleAsset* asset = g_sample_table.create_from_existing_sample(std::move(smp));

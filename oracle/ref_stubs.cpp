@@ -38,7 +38,10 @@ void Sample::resize(size_t n, uint32_t new_channels, bool) {
   for (auto p : sample_data)
     std::free(p);
   sample_data.resize(new_channels);
-  size_t bytes = (n + sample_padding) * get_audio_format_size(format);
+  // The sampler reads AudioFormat::I24 sources through int32_t pointers (dsp/sampler.cpp:121-132,171-181),
+  // i.e. 24-bit data widened to a 4-byte container (dsp/sample.cpp:20), so size I24 channels as 4 bytes.
+  size_t elem = format == AudioFormat::I24 ? 4 : get_audio_format_size(format);
+  size_t bytes = (n + sample_padding) * elem;
   for (uint32_t c = 0; c < new_channels; c++)
     sample_data[c] = (std::byte*)std::calloc(1, bytes);
   channels = new_channels;

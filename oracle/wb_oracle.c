@@ -1,0 +1,718 @@
+/* TEST INFRASTRUCTURE ONLY — never linked into, imported by or executed from the product path.
+ *
+ * wb_oracle.c — plain-C restatement ("port") of whitebox's mixing hot path, exporting the wbo.h scenario
+ * API. Each function cites the reference file:line (relative to /root/reference) it follows.
+ *
+ * Parity status: PINNED. This file is checked bit-for-bit against the reference's own Engine::process
+ * (oracle/_ref/libwbref.so, compiled unmodified from /root/reference/src) by tests/test_oracle.py on seeded
+ * scenarios whenever that library is present, and against the committed vectors under tests/golden/ that
+ * libwbref.so produced (tests/golden/make_golden.py) everywhere else. The reference's own tests hold no
+ * golden vectors for this path.
+ *
+ * Build: gcc -std=c11 -O3 -ffp-contract=off (no -march, no -ffast-math) so every f32/f64 operation is
+ * separately rounded exactly as in the reference's ISO-C++ x86-64 build.
+ *
+ * Scope notes (documented deviations, none reachable through wbo.h calls used by the tests):
+ *  - clips added through wbo_add_clip must not overlap an existing clip of the track (abutting is fine);
+ *    the reference would trim/split the old clip (Engine::reserve_track_region, engine.cpp:478-569) —
+ *    editing logic, out of scope. Overlap returns -1.
+ *  - the per-track message ring (capacity 64, track.cpp:23) is an unbounded list here.
+ *  - MIDI clips, plugins and recording are not restated.
+ */
+#define _POSIX_C_SOURCE 199309L
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "wbo.h"
+
+#define SAMPLE_PADDING 16 /* Sample::sample_padding, dsp/sample.h:19 */
+
+typedef struct {
+  int fmt;
+  uint32_t channels, rate;
+  size_t count;
+  void** data;
+} o_sample;
+
+typedef struct {
+  double min_time, max_time, start_offset; /* clip.h:68-70 */
+  double speed;                            /* AudioClip::speed clip.h:43 */
+  float gain;                              /* AudioClip::gain  clip.h:44 */
+  o_sample* sample;
+  int internal_state_changed; /* clip.h:62 — only UI edits set it */
+} o_clip;
+
+enum { EV_NONE, EV_STOP, EV_PLAY }; /* EventType, event.h:11-15 */
+
+typedef struct { /* AudioEvent, event.h:66-74 */
+  int type;
+  uint32_t buffer_offset;
+  double time, speed;
+  size_t sample_offset;
+  o_clip* clip;
+  o_sample* sample;
+} o_event;
+
+typedef struct {
+  uint32_t id; /* TrackParameter, track.h:29-34: 0 volume, 1 pan, 2 mute */
+  double value;
+} o_msg;
+
+typedef struct {
+  o_clip** clips;
+  uint32_t n_clips, cap_clips;
+  /* TrackEventState, track.h:36-44 */
+  int has_clip_idx;
+  uint32_t clip_idx;
+  int refresh_voice, partially_ended;
+  o_event* events;
+  uint32_t n_events, cap_events;
+  o_event current; /* Track::current_audio_event, track.h:118 */
+  /* dsp::Sampler, sampler.h:14-16 */
+  double playback_speed, sample_offset;
+  /* parameter_state, track.h:46-53 */
+  float volume, pan, pan_coeffs[2];
+  int mute;
+  o_msg* msgs;
+  uint32_t n_msgs, cap_msgs;
+  float level[2]; /* VUMeter::level, vu_meter.h:17 */
+} o_track;
+
+struct wbo_session {
+  uint32_t C, B, rate;
+  double beat_duration, ppq;
+  double playhead, playhead_start, sample_position;
+  int playing;
+  o_track** tracks;
+  uint32_t n_tracks, cap_tracks;
+  o_sample** samples;
+  uint32_t n_samples, cap_samples;
+  float** mixing; /* Engine::mixing_buffer, engine.h:57 */
+  float** out;
+};
+
+const char* wbo_kind(void) { return "port"; }
+
+static uint64_t g_ub_count = 0;
+/* port only: how many times a scenario drove the reference algorithm into undefined behaviour */
+uint64_t wbo_ub_count(void) { return g_ub_count; }
+
+/* ---- scalar math ------------------------------------------------------------------------------------- */
+
+/* core/core_math.h:209-212 */
+static double beat_to_samples(double beat, double sample_rate, double beat_duration) {
+  double sec = beat * beat_duration;
+  return sec * sample_rate;
+}
+
+/* core/core_math.h:83-89: db <= -72 -> 0, else powf(10, (float)((double)db * 0.05)) */
+float wbo_db_to_linear(float db) {
+  if (db <= -72.0f) return 0.0f;
+  return powf(10.0f, (float)((double)db * 0.05));
+}
+
+/* core/panning_law.cpp:9-32, ConstantPower_3db branch */
+void wbo_panning_coefs(float p, float* left, float* right) {
+  const double pi = 3.141592653589793238462643383279502884; /* std::numbers::pi */
+  double x = 0.5 * ((double)p + 1.0);
+  double l = sin(0.5 * pi * (1.0 - x));
+  double r = sin(0.5 * pi * x);
+  double boost = sqrt(2.0);
+  *left = (float)(l * boost);
+  *right = (float)(r * boost);
+}
+
+/* ---- session / editing API ------------------------------------------------------------------------- */
+
+static float** alloc_planar(uint32_t C, uint32_t B) {
+  float** p = (float**)calloc(C ? C : 1, sizeof(float*));
+  for (uint32_t c = 0; c < C; c++) p[c] = (float*)calloc(B ? B : 1, sizeof(float));
+  return p;
+}
+
+/* Engine::set_audio_channel_config (engine.cpp:43-57) + Engine::set_bpm (engine.cpp:24-30) */
+wbo_session* wbo_create(uint32_t out_channels, uint32_t block_frames, uint32_t sample_rate, double bpm) {
+  wbo_session* s = (wbo_session*)calloc(1, sizeof(*s));
+  s->C = out_channels;
+  s->B = block_frames;
+  s->rate = sample_rate;
+  s->beat_duration = 60.0 / bpm;
+  s->ppq = 96.0; /* engine.h:43 */
+  s->mixing = alloc_planar(out_channels, block_frames);
+  s->out = alloc_planar(out_channels, block_frames);
+  return s;
+}
+
+void wbo_destroy(wbo_session* s) {
+  if (!s) return;
+  for (uint32_t t = 0; t < s->n_tracks; t++) {
+    o_track* tr = s->tracks[t];
+    for (uint32_t i = 0; i < tr->n_clips; i++) free(tr->clips[i]);
+    free(tr->clips);
+    free(tr->events);
+    free(tr->msgs);
+    free(tr);
+  }
+  free(s->tracks);
+  for (uint32_t i = 0; i < s->n_samples; i++) {
+    for (uint32_t c = 0; c < s->samples[i]->channels; c++) free(s->samples[i]->data[c]);
+    free(s->samples[i]->data);
+    free(s->samples[i]);
+  }
+  free(s->samples);
+  for (uint32_t c = 0; c < s->C; c++) {
+    free(s->mixing[c]);
+    free(s->out[c]);
+  }
+  free(s->mixing);
+  free(s->out);
+  free(s);
+}
+
+static void push_msg(o_track* tr, uint32_t id, double value) {
+  if (tr->n_msgs == tr->cap_msgs) {
+    tr->cap_msgs = tr->cap_msgs ? tr->cap_msgs * 2 : 8;
+    tr->msgs = (o_msg*)realloc(tr->msgs, tr->cap_msgs * sizeof(o_msg));
+  }
+  tr->msgs[tr->n_msgs].id = id;
+  tr->msgs[tr->n_msgs].value = value;
+  tr->n_msgs++;
+}
+
+/* Track::set_volume / set_pan / set_mute (track.cpp:47-79): the UI thread converts dB -> linear in f32
+ * and queues the value as a double. */
+void wbo_set_volume(wbo_session* s, int t, float db) { push_msg(s->tracks[t], 0, (double)wbo_db_to_linear(db)); }
+void wbo_set_pan(wbo_session* s, int t, float pan) { push_msg(s->tracks[t], 1, (double)pan); }
+void wbo_set_mute(wbo_session* s, int t, int mute) { push_msg(s->tracks[t], 2, (double)(mute != 0)); }
+
+/* Engine::add_track (engine.cpp:199-207) + Track::Track() (track.cpp:22-27), which queues volume 0 dB,
+ * pan 0, mute off; the harness then applies the caller's values the same way. */
+int wbo_add_track(wbo_session* s, float volume_db, float pan, int mute) {
+  o_track* tr = (o_track*)calloc(1, sizeof(*tr));
+  if (s->n_tracks == s->cap_tracks) {
+    s->cap_tracks = s->cap_tracks ? s->cap_tracks * 2 : 16;
+    s->tracks = (o_track**)realloc(s->tracks, s->cap_tracks * sizeof(o_track*));
+  }
+  s->tracks[s->n_tracks++] = tr;
+  int t = (int)s->n_tracks - 1;
+  wbo_set_volume(s, t, 0.0f);
+  wbo_set_pan(s, t, 0.0f);
+  wbo_set_mute(s, t, 0);
+  wbo_set_volume(s, t, volume_db);
+  wbo_set_pan(s, t, pan);
+  wbo_set_mute(s, t, mute);
+  return t;
+}
+
+static size_t fmt_size(int fmt) { return fmt == WBO_FMT_I16 ? 2 : 4; }
+
+/* Sample layout (dsp/sample.h:18-28): one array per channel, `count` frames + 16 zero frames of padding
+ * (dsp/sample.cpp:127,140). */
+int wbo_add_sample(wbo_session* s, int format, uint32_t channels, uint64_t frames, uint32_t sample_rate,
+                   const void* const* planar) {
+  o_sample* sm = (o_sample*)calloc(1, sizeof(*sm));
+  sm->fmt = format;
+  sm->channels = channels;
+  sm->rate = sample_rate;
+  sm->count = (size_t)frames;
+  sm->data = (void**)calloc(channels, sizeof(void*));
+  for (uint32_t c = 0; c < channels; c++) {
+    sm->data[c] = calloc(frames + SAMPLE_PADDING, fmt_size(format));
+    memcpy(sm->data[c], planar[c], frames * fmt_size(format));
+  }
+  if (s->n_samples == s->cap_samples) {
+    s->cap_samples = s->cap_samples ? s->cap_samples * 2 : 16;
+    s->samples = (o_sample**)realloc(s->samples, s->cap_samples * sizeof(o_sample*));
+  }
+  s->samples[s->n_samples++] = sm;
+  return (int)s->n_samples - 1;
+}
+
+/* wb::find_lower_bound (core/algorithm.h:26-42) with the comparator of Track::find_next_clip
+ * (track.cpp:207): note `right` starts at n-1, so the result is never one-past-the-end. */
+static uint32_t lower_bound_max_time(o_clip** clips, uint32_t n, double time_pos) {
+  int64_t left = 0, right = (int64_t)n - 1;
+  while (left < right) {
+    int64_t middle = (left + right) >> 1;
+    if (clips[middle]->max_time <= time_pos)
+      left = middle + 1;
+    else
+      right = middle;
+  }
+  return (uint32_t)right;
+}
+
+/* Track::find_next_clip (track.cpp:182-213). Returns 1 and *idx when a clip is found. */
+static int find_next_clip(o_track* tr, double time_pos, uint32_t* idx) {
+  if (tr->n_clips == 0) return 0;
+  if (tr->clips[tr->n_clips - 1]->max_time < time_pos) return 0;
+  *idx = lower_bound_max_time(tr->clips, tr->n_clips, time_pos); /* ids == positions after ordering */
+  return 1;
+}
+
+/* Track::reset_playback_state (track.cpp:220-232) */
+static void reset_playback_state(o_track* tr, double time_pos, int refresh_voices) {
+  if (!refresh_voices) {
+    uint32_t idx = 0;
+    tr->has_clip_idx = find_next_clip(tr, time_pos, &idx);
+    tr->clip_idx = idx;
+    tr->partially_ended = 0;
+  }
+  tr->refresh_voice = refresh_voices;
+}
+
+/* Engine::add_audio_clip (engine.cpp:293-309) + add_to_cliplist (engine.cpp:409-461) for the
+ * non-overlapping cases: append / prepend / insert + sort by min_time, then
+ * reset_playback_state(playhead, true). */
+int wbo_add_clip(wbo_session* s, int track, int sample, double min_beat, double max_beat, double start_offset,
+                 double speed, float gain) {
+  o_track* tr = s->tracks[track];
+  for (uint32_t i = 0; i < tr->n_clips; i++) /* Track::query_clip_by_range (track.cpp:112-160) finds one */
+    if (min_beat < tr->clips[i]->max_time && max_beat > tr->clips[i]->min_time) return -1;
+  o_clip* c = (o_clip*)calloc(1, sizeof(*c));
+  c->min_time = min_beat;
+  c->max_time = max_beat;
+  c->start_offset = start_offset;
+  c->speed = speed;
+  c->gain = gain;
+  c->sample = s->samples[sample];
+  if (tr->n_clips == tr->cap_clips) {
+    tr->cap_clips = tr->cap_clips ? tr->cap_clips * 2 : 4;
+    tr->clips = (o_clip**)realloc(tr->clips, tr->cap_clips * sizeof(o_clip*));
+  }
+  uint32_t pos = tr->n_clips;
+  while (pos > 0 && tr->clips[pos - 1]->min_time > min_beat) {
+    tr->clips[pos] = tr->clips[pos - 1];
+    pos--;
+  }
+  tr->clips[pos] = c;
+  tr->n_clips++;
+  reset_playback_state(tr, s->playhead, 1);
+  return 0;
+}
+
+/* Engine::set_playhead_position (engine.cpp:32-41) */
+void wbo_set_playhead(wbo_session* s, double beat) {
+  s->playhead_start = beat;
+  s->playhead = beat;
+}
+
+/* Engine::play (engine.cpp:68-80) */
+void wbo_play(wbo_session* s) {
+  for (uint32_t t = 0; t < s->n_tracks; t++) reset_playback_state(s->tracks[t], s->playhead_start, 0);
+  s->sample_position = 0;
+  s->playing = 1;
+}
+
+/* Engine::stop (engine.cpp:82-92) + Track::stop (track.cpp:248-256) */
+void wbo_stop(wbo_session* s) {
+  s->playing = 0;
+  s->playhead = s->playhead_start;
+  for (uint32_t t = 0; t < s->n_tracks; t++) {
+    memset(&s->tracks[t]->current, 0, sizeof(o_event));
+    s->tracks[t]->n_events = 0;
+  }
+}
+
+/* ---- event scheduling ------------------------------------------------------------------------------ */
+
+static void push_event(o_track* tr, o_event e) {
+  if (tr->n_events == tr->cap_events) {
+    tr->cap_events = tr->cap_events ? tr->cap_events * 2 : 8;
+    tr->events = (o_event*)realloc(tr->events, tr->cap_events * sizeof(o_event));
+  }
+  tr->events[tr->n_events++] = e;
+}
+
+static void push_stop(o_track* tr, uint32_t buffer_offset, double time) {
+  o_event e;
+  memset(&e, 0, sizeof(e));
+  e.type = EV_STOP;
+  e.buffer_offset = buffer_offset;
+  e.time = time;
+  push_event(tr, e);
+}
+
+static void push_play(o_track* tr, uint32_t buffer_offset, double time, o_clip* clip, size_t sample_offset) {
+  o_event e;
+  memset(&e, 0, sizeof(e));
+  e.type = EV_PLAY;
+  e.buffer_offset = buffer_offset;
+  e.time = time;
+  e.speed = clip->speed;
+  e.sample_offset = sample_offset;
+  e.clip = clip;
+  e.sample = clip->sample;
+  push_event(tr, e);
+}
+
+/* Track::process_event (track.cpp:258-451), audio clips only. */
+static void process_event(o_track* tr, double start_time, double end_time, double sample_position,
+                          double beat_duration, double sample_rate, uint32_t buffer_size) {
+  if (tr->n_clips == 0) { /* :268-284 */
+    if (tr->refresh_voice) {
+      push_stop(tr, 0, start_time);
+      tr->has_clip_idx = 0;
+      tr->refresh_voice = 0;
+    }
+    return;
+  }
+
+  uint32_t num_clips = tr->n_clips;
+  if (tr->refresh_voice) { /* :287-340 */
+    uint32_t at = 0;
+    if (find_next_clip(tr, start_time, &at)) {
+      if (tr->has_clip_idx) {
+        uint32_t idx = tr->clip_idx;
+        if (idx < num_clips) {
+          o_clip* clip = tr->clips[at];
+          o_clip* current_clip = tr->clips[idx];
+          if (clip != current_clip && start_time >= clip->min_time && start_time <= clip->max_time) {
+            push_stop(tr, 0, start_time);
+            tr->clip_idx = at;
+            tr->partially_ended = 0;
+          } else if (clip == current_clip && (start_time < clip->min_time || start_time > clip->max_time)) {
+            push_stop(tr, 0, start_time);
+            tr->clip_idx = at;
+            tr->partially_ended = 0;
+          }
+        }
+      } else {
+        tr->has_clip_idx = 1;
+        tr->clip_idx = at;
+      }
+    } else {
+      push_stop(tr, 0, start_time);
+      tr->has_clip_idx = 0;
+    }
+    tr->refresh_voice = 0;
+  }
+
+  if (!tr->has_clip_idx) return; /* :342-346 */
+
+  uint32_t next_clip = tr->clip_idx;
+  while (next_clip < num_clips) { /* :348-446 */
+    o_clip* clip = tr->clips[next_clip];
+    double min_time = clip->min_time;
+    double max_time = clip->max_time;
+
+    if (min_time > end_time) break;
+
+    if (min_time >= start_time) { /* started from the beginning, :357-375 */
+      double offset_from_start = beat_to_samples(min_time - start_time, sample_rate, beat_duration);
+      double sample_offset = sample_position + offset_from_start;
+      uint32_t buffer_offset = (uint32_t)((uint64_t)sample_offset % (uint64_t)buffer_size);
+      push_play(tr, buffer_offset, min_time, clip, (size_t)clip->start_offset);
+      clip->internal_state_changed = 0;
+    } else if (start_time > min_time && !tr->partially_ended) { /* started in the middle, :376-395 */
+      double relative_start_time = start_time - min_time;
+      double sample_pos = beat_to_samples(relative_start_time, sample_rate, beat_duration);
+      size_t sample_offset = (size_t)(clip->start_offset + (sample_pos * clip->speed));
+      push_play(tr, 0, start_time, clip, sample_offset);
+      clip->internal_state_changed = 0;
+    } else if (clip->internal_state_changed && tr->partially_ended) { /* :396-421 */
+      double relative_start_time = start_time - min_time;
+      double sample_pos = beat_to_samples(relative_start_time, sample_rate, beat_duration);
+      size_t sample_offset = (size_t)(clip->start_offset + (sample_pos * clip->speed));
+      push_stop(tr, 0, start_time);
+      push_play(tr, 0, start_time, clip, sample_offset);
+      clip->internal_state_changed = 0;
+    }
+
+    if (max_time <= end_time) { /* reaching the end of the clip, :423-437 */
+      double offset_from_start = beat_to_samples(max_time - start_time, sample_rate, beat_duration);
+      double sample_offset = sample_position + offset_from_start;
+      uint32_t buffer_offset = (uint32_t)((uint64_t)sample_offset % (uint64_t)buffer_size);
+      push_stop(tr, buffer_offset, max_time);
+      tr->partially_ended = 0;
+    } else { /* :438-444 */
+      tr->partially_ended = 1;
+      break;
+    }
+    next_clip++;
+  }
+  tr->clip_idx = next_clip; /* :450 */
+}
+
+/* ---- sampler --------------------------------------------------------------------------------------- */
+
+static float clampf(float x, float lo, float hi) { /* math::clamp, core_math.h:34-38 */
+  float m = x < hi ? x : hi;
+  return m > lo ? m : lo;
+}
+static double clampd(double x, double lo, double hi) {
+  double m = x < hi ? x : hi;
+  return m > lo ? m : lo;
+}
+
+/* dsp::Sampler::reset_state (dsp/sampler.h:18-27) */
+static void sampler_reset(o_track* tr, double sample_offset, double speed, double src_rate, double dst_rate) {
+  tr->playback_speed = (src_rate / dst_rate) * speed;
+  tr->sample_offset = sample_offset;
+}
+
+/* dsp::Sampler::stream (dsp/sampler.cpp:88-210) incl. sample_linear<T,Fmt> (dsp/sampler.cpp:34-59). */
+static void sampler_stream(o_track* tr, o_sample* sm, uint32_t num_channels, uint32_t num_samples,
+                           uint32_t buffer_offset, float gain, float** dst) {
+  const float i16_norm = 1.0f / (float)INT16_MAX;              /* :95 */
+  const double i24_norm = 1.0 / (double)((1 << 23) - 1);       /* :96 */
+  const double i32_norm = 1.0 / (double)INT32_MAX;             /* :97 */
+  const float i16_norm_lin = (float)(1.0 / (double)INT16_MAX); /* get_pcm_sample_normalizer, :7-18 */
+
+  if (tr->sample_offset >= (double)sm->count) return; /* :99-100 */
+
+  double stream_max_length = ((double)sm->count - tr->sample_offset) / tr->playback_speed;
+  double next_sample_offset = tr->sample_offset + ((double)num_samples * tr->playback_speed);
+  uint32_t ceil_len = (uint32_t)ceil(stream_max_length);
+  uint32_t n = num_samples < ceil_len ? num_samples : ceil_len; /* :104 */
+
+  if (tr->playback_speed == 1.0) { /* :106-158 */
+    uint32_t off = (uint32_t)tr->sample_offset;
+    for (uint32_t i = 0; i < num_channels; i++) {
+      uint32_t c = i % sm->channels;
+      float* out = dst[i] + buffer_offset;
+      switch (sm->fmt) {
+        case WBO_FMT_I16: {
+          const int16_t* d = (const int16_t*)sm->data[c];
+          for (uint32_t j = 0; j < n; j++) {
+            float v = (float)d[off + j] * i16_norm;
+            out[j] += clampf(v, -1.0f, 1.0f) * gain;
+          }
+          break;
+        }
+        case WBO_FMT_I24: {
+          const int32_t* d = (const int32_t*)sm->data[c];
+          for (uint32_t j = 0; j < n; j++) {
+            double v = (double)d[off + j] * i24_norm;
+            out[j] += (float)clampd(v, -1.0, 1.0) * gain;
+          }
+          break;
+        }
+        case WBO_FMT_I32: {
+          const int32_t* d = (const int32_t*)sm->data[c];
+          for (uint32_t j = 0; j < n; j++) {
+            double v = (double)d[off + j] * i32_norm;
+            out[j] += (float)clampd(v, -1.0, 1.0) * gain;
+          }
+          break;
+        }
+        default: {
+          const float* d = (const float*)sm->data[c];
+          for (uint32_t j = 0; j < n; j++) out[j] += d[off + j] * gain;
+          break;
+        }
+      }
+    }
+  } else { /* sample_linear, :34-59. The reference indexes src_channels[i] without `% channels`
+              (:47, undefined for mono sources); fixtures never combine mono with speed != 1. */
+    for (uint32_t i = 0; i < num_channels; i++) {
+      uint32_t c = i % sm->channels;
+      float* out = dst[i] + buffer_offset;
+      for (uint32_t j = 0; j < n; j++) {
+        const double x = tr->sample_offset + ((double)j * tr->playback_speed);
+        const int64_t ix = (int64_t)x;
+        const float fx = (float)(x - (double)ix);
+        float a, b;
+        switch (sm->fmt) {
+          case WBO_FMT_I16:
+            a = (float)(i16_norm_lin * (float)((const int16_t*)sm->data[c])[ix]);
+            b = (float)(i16_norm_lin * (float)((const int16_t*)sm->data[c])[ix + 1]);
+            break;
+          case WBO_FMT_I24:
+            a = (float)(i24_norm * (double)((const int32_t*)sm->data[c])[ix]);
+            b = (float)(i24_norm * (double)((const int32_t*)sm->data[c])[ix + 1]);
+            break;
+          case WBO_FMT_I32:
+            a = (float)(i32_norm * (double)((const int32_t*)sm->data[c])[ix]);
+            b = (float)(i32_norm * (double)((const int32_t*)sm->data[c])[ix + 1]);
+            break;
+          default:
+            a = ((const float*)sm->data[c])[ix];
+            b = ((const float*)sm->data[c])[ix + 1];
+            break;
+        }
+        const float sv = a + fx * (b - a);
+        out[j] += sv * gain;
+      }
+    }
+  }
+  tr->sample_offset = next_sample_offset; /* :209 */
+}
+
+/* ---- Track::process (engine/track.cpp:587-736) ---------------------------------------------------------- */
+
+static void track_process(wbo_session* s, o_track* tr, float** out, double sample_rate, double beat_duration,
+                          double sample_position, double start_time, double end_time, int playing) {
+  const uint32_t B = s->B;
+
+  /* process_track_messages (:602, :773-779) + parameter application (:618-643) */
+  if (playing) process_event(tr, start_time, end_time, sample_position, beat_duration, sample_rate, B);
+  for (uint32_t i = 0; i < tr->n_msgs; i++) {
+    switch (tr->msgs[i].id) {
+      case 0: tr->volume = (float)tr->msgs[i].value; break;
+      case 1:
+        tr->pan = (float)tr->msgs[i].value;
+        wbo_panning_coefs(tr->pan, &tr->pan_coeffs[0], &tr->pan_coeffs[1]);
+        break;
+      case 2: tr->mute = tr->msgs[i].value > 0.0; break;
+    }
+  }
+  tr->n_msgs = 0;
+
+  if (playing) { /* :664-724 */
+    uint32_t next = 0;
+    uint32_t start_sample = 0;
+    while (start_sample < B) {
+      if (next != tr->n_events) {
+        o_event* ne = &tr->events[next];
+        uint32_t event_length = ne->buffer_offset - start_sample; /* unsigned, as in the reference (:670) */
+        if (ne->buffer_offset < start_sample || ne->buffer_offset > B) {
+          /* Reference UB: events out of offset order (e.g. a clip that ends EXACTLY on the block's end gets
+           * StopSample offset `B % B == 0`, track.cpp:425) make event_length wrap and Sampler::stream
+           * write past the mixing buffer. No defined answer exists; count it so fixtures can avoid it, and
+           * render nothing for this event instead of corrupting memory. */
+          g_ub_count++;
+          event_length = 0;
+          if (tr->current.type == EV_PLAY) tr->current.type = EV_NONE;
+        }
+        if (tr->current.type == EV_PLAY)
+          sampler_stream(tr, tr->current.sample, s->C, event_length, start_sample, tr->current.clip->gain, out);
+        if (ne->type == EV_PLAY)
+          sampler_reset(tr, (double)ne->sample_offset, ne->speed, (double)ne->sample->rate, sample_rate);
+        tr->current = *ne;
+        start_sample += event_length;
+        next++;
+      } else {
+        uint32_t event_length = B - start_sample;
+        if (tr->current.type == EV_PLAY)
+          sampler_stream(tr, tr->current.sample, s->C, event_length, start_sample, tr->current.clip->gain, out);
+        start_sample = B;
+      }
+    }
+  }
+
+  /* dsp::apply_gain (dsp/dsp_ops.h:27-31) + VUMeter::push_samples (engine/vu_meter.h:20-30), :728-733.
+   * pan_coeffs has two entries, so C <= 2 (track.h:50). */
+  float volume = tr->mute ? 0.0f : tr->volume;
+  for (uint32_t c = 0; c < s->C; c++) {
+    float* buf = out[c];
+    float g = volume * tr->pan_coeffs[c];
+    for (uint32_t j = 0; j < B; j++) buf[j] *= g;
+    float new_level = 0.0f;
+    for (uint32_t j = 0; j < B; j++) {
+      float v = buf[j];
+      float a = v < 0 ? -v : v;               /* math::abs, core_math.h:20-22 */
+      new_level = a < new_level ? new_level : a; /* math::max(new_level, a), core_math.h:29-32 */
+    }
+    if (tr->level[c] < new_level) tr->level[c] = new_level;
+  }
+}
+
+/* ---- Engine::process (engine/engine.cpp:1576-1654) ------------------------------------------------------ */
+
+static void engine_process(wbo_session* s) {
+  const uint32_t B = s->B, C = s->C;
+  const double sample_rate = (double)s->rate;
+  double buffer_duration = (double)B / sample_rate;
+  double current_beat_duration = s->beat_duration;
+  double current_playhead_position = s->playhead;
+  double buffer_duration_in_beats = buffer_duration / current_beat_duration;
+  double next_playhead_pos = s->playhead + buffer_duration_in_beats;
+  int currently_playing = s->playing;
+
+  for (uint32_t t = 0; t < s->n_tracks; t++) s->tracks[t]->n_events = 0; /* :1589-1596 */
+  for (uint32_t c = 0; c < C; c++) memset(s->out[c], 0, B * sizeof(float)); /* :1598 */
+
+  for (uint32_t t = 0; t < s->n_tracks; t++) { /* :1600-1617 */
+    for (uint32_t c = 0; c < C; c++) memset(s->mixing[c], 0, B * sizeof(float));
+    track_process(s, s->tracks[t], s->mixing, sample_rate, current_beat_duration, s->sample_position,
+                  current_playhead_position, next_playhead_pos, currently_playing);
+    for (uint32_t c = 0; c < C; c++) { /* AudioBuffer::mix, core/audio_buffer.h:73-82 */
+      const float* o = s->mixing[c];
+      float* b = s->out[c];
+      for (uint32_t j = 0; j < B; j++) b[j] += o[j];
+    }
+  }
+
+  if (currently_playing) { /* :1619-1623 */
+    s->sample_position += beat_to_samples(buffer_duration_in_beats, sample_rate, current_beat_duration);
+    s->playhead = next_playhead_pos;
+  }
+
+  for (uint32_t c = 0; c < C; c++) { /* :1627-1636 — NaN passes through */
+    float* ch = s->out[c];
+    for (uint32_t j = 0; j < B; j++) {
+      if (ch[j] > 1.0)
+        ch[j] = 1.0f;
+      else if (ch[j] < -1.0)
+        ch[j] = -1.0f;
+    }
+  }
+}
+
+int wbo_process(wbo_session* s, uint32_t n_blocks, float* out, float* peaks) {
+  for (uint32_t k = 0; k < n_blocks; k++) {
+    engine_process(s);
+    if (out)
+      for (uint32_t c = 0; c < s->C; c++)
+        memcpy(out + ((size_t)k * s->C + c) * s->B, s->out[c], s->B * sizeof(float));
+    for (uint32_t t = 0; t < s->n_tracks; t++)
+      for (uint32_t c = 0; c < 2; c++) {
+        if (peaks) peaks[((size_t)k * s->n_tracks + t) * 2 + c] = s->tracks[t]->level[c];
+        s->tracks[t]->level[c] = 0.0f; /* VUMeter::update's exchange(0), vu_meter.h:33 */
+      }
+  }
+  return 0;
+}
+
+double wbo_time_process(wbo_session* s, uint32_t n_blocks) {
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (uint32_t k = 0; k < n_blocks; k++) engine_process(s);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+double wbo_sampler_offset(wbo_session* s, int track) { return s->tracks[track]->sample_offset; }
+double wbo_sample_position(wbo_session* s) { return s->sample_position; }
+double wbo_playhead(wbo_session* s) { return s->playhead; }
+
+/* ---- core/audio_format_conv.cpp:5-106: planar f32 -> interleaved device format -------------------------- */
+
+void wbo_interleave(void* dst, const float* const* src, uint32_t offset, uint32_t frames, uint32_t channels,
+                    int fmt) {
+  for (uint32_t c = 0; c < channels; c++) {
+    const float* ch = src[c] + offset;
+    for (uint32_t i = 0; i < frames; i++) {
+      float v = ch[i];
+      size_t o = (size_t)i * channels + c;
+      switch (fmt) {
+        case WBO_FMT_I16: /* :5-20: positive * 32767, else * 32768, truncating cast */
+          ((int16_t*)dst)[o] = (int16_t)(v > 0.0f ? v * 32767.0f : v * 32768.0f);
+          break;
+        case WBO_FMT_I24: { /* :22-43 */
+          int32_t q = v > 0.0f ? (int32_t)(v * 8388607.0f) : (int32_t)(v * 8388608.0f);
+          /* the reference writes channel c's bytes at dst[3*i .. 3*i+2] for EVERY channel (no channel
+           * stride, :31-41): later channels overwrite earlier ones. Restated as written. */
+          uint8_t* p = (uint8_t*)dst + (size_t)i * 3;
+          p[0] = (uint8_t)q;
+          p[1] = (uint8_t)(q >> 8);
+          p[2] = (uint8_t)(q >> 16);
+          break;
+        }
+        case 6: { /* I24_X8, :45-59 */
+          int32_t q = v > 0.0f ? (int32_t)(v * 8388607.0f) : (int32_t)(v * 8388608.0f);
+          ((int32_t*)dst)[o] = q & 0xFFFFFF;
+          break;
+        }
+        case WBO_FMT_I32: /* :61-74, in double */
+          ((int32_t*)dst)[o] = (int32_t)(v > 0.0f ? (double)v * 2147483647.0 : (double)v * 2147483648.0);
+          break;
+        default: ((float*)dst)[o] = v; break; /* :76-88 */
+      }
+    }
+  }
+}

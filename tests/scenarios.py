@@ -1,0 +1,268 @@
+"""Seeded mixing scenarios shared by every implementation under test. TEST INFRASTRUCTURE ONLY.
+
+A scenario is a function `run(make_engine) -> dict[str, np.ndarray]`. `make_engine(out_channels, block, rate,
+bpm)` returns an object with the reference's editing API (tests/oracle_api.Session for the CPU checkers,
+whitebox_b200.Engine for the CUDA path): add_track / add_sample / add_clip / set_volume / set_pan / set_mute /
+set_playhead / play / stop / process(n_blocks) -> (out[K][C][B], peaks[K][N][2]) / sampler_offset /
+sample_position / playhead.
+
+Fixture values follow SURVEY.md §8(d): MT19937 seeds, sources uniform(-1,1)*0.5/sqrt(N), clip gain
+0.5+0.001*(t%512), volume dB -6-(t%7), pan -1+0.2*(t%11), one clip per track from beat 0, bpm 120.
+"""
+import numpy as np
+
+FMT_I16, FMT_I24, FMT_I32, FMT_F32 = 3, 5, 7, 9
+
+
+def _src(rng, channels, frames, n_tracks, fmt=FMT_F32):
+    x = (rng.uniform(-1.0, 1.0, size=(channels, frames)) * (0.5 / np.sqrt(n_tracks))).astype(np.float32)
+    if fmt == FMT_F32:
+        return x
+    if fmt == FMT_I16:
+        return np.clip(np.round(x.astype(np.float64) * 40000.0 * np.sqrt(n_tracks)), -32768, 32767).astype(np.int16)
+    if fmt == FMT_I24:  # 24-bit widened to int32 (dsp/sample.cpp:20); some values beyond full scale -> clamp path
+        return np.clip(np.round(x.astype(np.float64) * 1.2e7 * np.sqrt(n_tracks)), -(2**31), 2**31 - 1).astype(np.int32)
+    return np.clip(np.round(x.astype(np.float64) * 3.0e9 * np.sqrt(n_tracks)), -(2**31), 2**31 - 1).astype(np.int32)
+
+
+def _track_params(t):
+    return dict(volume_db=-6.0 - (t % 7), pan=-1.0 + 0.2 * (t % 11), gain=np.float32(0.5 + 0.001 * (t % 512)))
+
+
+def _collect(eng, outs, n_tracks):
+    out = np.concatenate([o for o, _ in outs], axis=0)
+    peaks = np.concatenate([p for _, p in outs], axis=0)
+    offs = np.array([eng.sampler_offset(t) for t in range(n_tracks)], np.float64)
+    pos = np.array([eng.sample_position(), eng.playhead()], np.float64)
+    return dict(out=out, peaks=peaks, sampler_offsets=offs, transport=pos)
+
+
+def standard(make_engine, n_tracks, src_channels, src_rate, n_blocks, block=512, rate=48000, seed=1234,
+             fmt=FMT_F32, out_channels=2, chunks=None):
+    """The SURVEY §8(d) fixture: one clip per track from beat 0 covering the whole render."""
+    rng = np.random.RandomState(seed)
+    eng = make_engine(out_channels, block, rate, 120.0)
+    frames = int((n_blocks + 4) * block * src_rate / rate) + 64
+    beats = (n_blocks + 2) * block / rate * 2.0  # bpm 120 -> 2 beats/s
+    for t in range(n_tracks):
+        p = _track_params(t)
+        eng.add_track(p["volume_db"], p["pan"], False)
+        sid = eng.add_sample(_src(rng, src_channels, frames, n_tracks, fmt), src_rate, fmt)
+        eng.add_clip(t, sid, 0.0, beats, 0.0, 1.0, float(p["gain"]))
+    eng.play()
+    outs = []
+    for n in (chunks or [n_blocks]):
+        outs.append(eng.process(n))
+    return _collect(eng, outs, n_tracks)
+
+
+def kat(make_engine):
+    """SURVEY §8(c) known answer: 1 track, ramp source @44.1k, block 16."""
+    eng = make_engine(2, 16, 48000, 120.0)
+    t = eng.add_track(-6.0, 0.25, False)
+    i = np.arange(4096, dtype=np.float32)
+    src = np.stack([(i + 1) * np.float32(1e-3), -(i + 1) * np.float32(1e-3)]).astype(np.float32)
+    sid = eng.add_sample(src, 44100, FMT_F32)
+    eng.add_clip(t, sid, 0.0, 1.0, 0.0, 1.0, 0.5)
+    eng.play()
+    return _collect(eng, [eng.process(1), eng.process(1)], 1)
+
+
+def cfg1(make_engine, n_blocks=8):
+    """BASELINE cfg 1: 16 mono tracks, 48 kHz f32, gain+pan only, 512-sample block."""
+    return standard(make_engine, 16, 1, 48000, n_blocks)
+
+
+def cfg2_small(make_engine, n_tracks=64, n_blocks=6):
+    """BASELINE cfg 2 shape (stereo 48k unity, gain/pan + bus sum), reduced N."""
+    return standard(make_engine, n_tracks, 2, 48000, n_blocks, chunks=[1, 2, n_blocks - 3])
+
+
+def cfg3_small(make_engine, n_tracks=32, n_blocks=6):
+    """BASELINE cfg 3 shape (stereo 44.1k -> 48k linear resample + mix), reduced N."""
+    return standard(make_engine, n_tracks, 2, 44100, n_blocks, chunks=[2, n_blocks - 2])
+
+
+def int_formats(make_engine, n_blocks=4):
+    """I16 / I24-in-I32 / I32 sources, unity and resampled (dsp/sampler.cpp:109-144,161-193)."""
+    rng = np.random.RandomState(77)
+    eng = make_engine(2, 256, 48000, 120.0)
+    n = 0
+    for fmt in (FMT_I16, FMT_I24, FMT_I32, FMT_F32):
+        for rate in (48000, 44100, 96000):
+            p = _track_params(n)
+            eng.add_track(p["volume_db"], p["pan"], False)
+            sid = eng.add_sample(_src(rng, 2, 4096, 12, fmt), rate, fmt)
+            eng.add_clip(n, sid, 0.0, 64.0, 3.0, 1.0, float(p["gain"]))
+            n += 1
+    eng.play()
+    return _collect(eng, [eng.process(n_blocks)], n)
+
+
+def event_split(make_engine):
+    """Clips that start / stop mid-block, abut, exhaust their sample, play at speeds != 1, start with an
+    offset; playback starting mid-clip (track.cpp:347-446, 664-724; sampler.cpp:99-104)."""
+    rng = np.random.RandomState(4321)
+    B, rate = 128, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    spb = rate * 0.5  # samples per beat at bpm 120
+    n = 0
+
+    def tr(vol=-3.0, pan=0.0):
+        nonlocal n
+        eng.add_track(vol, pan, False)
+        n += 1
+        return n - 1
+
+    def smp(frames, ch=2, r=48000):
+        return eng.add_sample(_src(rng, ch, frames, 8), r, FMT_F32)
+
+    # t0: clip starts mid-block (300 frames in) and ends mid-block
+    t = tr(-2.0, -0.3)
+    eng.add_clip(t, smp(5000), 300.0 / spb, 900.0 / spb, 0.0, 1.0, 0.8)
+    # t1: two abutting clips on one track, boundary mid-block, second with a start offset
+    t = tr(-4.0, 0.4)
+    eng.add_clip(t, smp(5000), 0.0, 333.0 / spb, 0.0, 1.0, 0.7)
+    eng.add_clip(t, smp(5000), 333.0 / spb, 1000.0 / spb, 17.0, 1.0, 0.9)
+    # t2: sample shorter than its clip (exhausts mid-block)
+    t = tr(0.0, 0.0)
+    eng.add_clip(t, smp(421), 0.0, 4.0, 0.0, 1.0, 1.0)
+    # t3: speed 0.5 / t4: speed 2.0 (sample exhausts) / t5: speed 1.25 on a 44.1k source
+    t = tr(-1.0, 0.1)
+    eng.add_clip(t, smp(3000), 10.0 / spb, 4.0, 5.0, 0.5, 0.6)
+    t = tr(-1.5, -0.8)
+    eng.add_clip(t, smp(900), 0.0, 4.0, 0.0, 2.0, 0.5)
+    t = tr(-7.0, 0.9)
+    eng.add_clip(t, smp(4000, 2, 44100), 64.0 / spb, 700.0 / spb, 11.0, 1.25, 1.1)
+    # t6: mono source at unity speed -> both channels (sampler.cpp:147 `i % channels`)
+    t = tr(-5.0, 0.5)
+    eng.add_clip(t, smp(2000, 1), 50.0 / spb, 1200.0 / spb, 0.0, 1.0, 0.75)
+    # t7: gap between two clips, second starts exactly on a block boundary
+    t = tr(-3.0, -1.0)
+    eng.add_clip(t, smp(1000), 0.0, 200.0 / spb, 0.0, 1.0, 0.5)
+    eng.add_clip(t, smp(1000), 512.0 / spb, 1100.0 / spb, 0.0, 1.0, 0.5)
+    # t8: muted / t9: no clips / t10: -inf dB
+    t = tr(-3.0, 0.0)
+    eng.set_mute(t, True)
+    eng.add_clip(t, smp(2000), 0.0, 4.0, 0.0, 1.0, 1.0)
+    tr(-3.0, 0.0)
+    t = tr(-80.0, 0.0)
+    eng.add_clip(t, smp(2000), 0.0, 4.0, 0.0, 1.0, 1.0)
+    eng.play()
+    outs = [eng.process(4), eng.process(1), eng.process(7)]
+    # stop, move the playhead into the middle of clips, play again (track.cpp:376-395 mid-clip start)
+    eng.stop()
+    eng.set_playhead(450.0 / spb)
+    eng.play()
+    outs.append(eng.process(6))
+    return _collect(eng, outs, n)
+
+
+def params(make_engine):
+    """Volume / pan / mute changes between callbacks, not-playing callbacks, stop/play (track.cpp:618-643)."""
+    rng = np.random.RandomState(99)
+    eng = make_engine(2, 64, 44100, 97.0)
+    for t in range(5):
+        eng.add_track(-3.0 * t, -0.5 + 0.25 * t, False)
+        sid = eng.add_sample(_src(rng, 2, 6000, 5), 44100 if t % 2 == 0 else 48000, FMT_F32)
+        eng.add_clip(t, sid, 0.0, 8.0, 0.0, 1.0, 0.9)
+    outs = [eng.process(2)]  # not playing: silence, params applied
+    eng.play()
+    outs.append(eng.process(3))
+    eng.set_volume(1, 2.5)
+    eng.set_pan(2, 1.0)
+    eng.set_mute(3, True)
+    outs.append(eng.process(2))
+    eng.set_mute(3, False)
+    eng.set_pan(0, -1.0)
+    eng.set_volume(4, -71.9)
+    outs.append(eng.process(2))
+    eng.stop()
+    outs.append(eng.process(1))
+    eng.play()
+    outs.append(eng.process(3))
+    return _collect(eng, outs, 5)
+
+
+def hot_clamp(make_engine):
+    """Deliberately hot mix so the +/-1 clamp (engine.cpp:1627-1636) is exercised on many samples."""
+    rng = np.random.RandomState(5)
+    eng = make_engine(2, 512, 48000, 120.0)
+    for t in range(12):
+        eng.add_track(6.0, 0.0, False)
+        sid = eng.add_sample((rng.uniform(-1, 1, size=(2, 4096))).astype(np.float32), 48000, FMT_F32)
+        eng.add_clip(t, sid, 0.0, 16.0, 0.0, 1.0, 1.0)
+    eng.play()
+    return _collect(eng, [eng.process(3)], 12)
+
+
+def ragged(make_engine):
+    """Odd block size, mono output bus, zero-track engine is covered by `empty`."""
+    rng = np.random.RandomState(31)
+    eng = make_engine(1, 100, 32000, 133.0)
+    for t in range(7):
+        eng.add_track(-2.0 * t, 0.3 * (t - 3), False)
+        sid = eng.add_sample(_src(rng, 1 + (t % 2), 3000, 7), 32000 if t % 3 else 22050, FMT_F32)
+        # mono bus: only src channel 0 is ever indexed, so mono + resample is well defined here
+        eng.add_clip(t, sid, 0.01 * t, 3.0, 2.0 * t, 1.0, 0.8)
+    eng.play()
+    return _collect(eng, [eng.process(9)], 7)
+
+
+def empty(make_engine):
+    """No tracks at all, then tracks without clips."""
+    eng = make_engine(2, 512, 48000, 120.0)
+    eng.play()
+    a = eng.process(2)
+    eng2 = make_engine(2, 512, 48000, 120.0)
+    for t in range(3):
+        eng2.add_track(0.0, 0.0, False)
+    eng2.play()
+    b = eng2.process(2)
+    return dict(out=np.concatenate([a[0], b[0]]), peaks=b[1])
+
+
+def fuzz(make_engine, seed):
+    """Random session: random rates / formats / speeds / clip layouts / block size, params changed mid-run."""
+    rng = np.random.RandomState(1000 + seed)
+    B = int(rng.choice([32, 64, 100, 128, 256, 512]))
+    rate = int(rng.choice([44100, 48000, 96000]))
+    bpm = float(rng.choice([90.0, 120.0, 133.3, 150.0]))
+    eng = make_engine(2, B, rate, bpm)
+    spb = rate * 60.0 / bpm
+    n_tracks = int(rng.randint(1, 12))
+    n_blocks = int(rng.randint(6, 14))
+    total = n_blocks * B
+    for t in range(n_tracks):
+        eng.add_track(float(rng.uniform(-30, 6)), float(rng.uniform(-1, 1)), bool(rng.rand() < 0.1))
+        pos = float(rng.randint(0, max(1, total // 3)))
+        for _ in range(int(rng.randint(0, 4))):
+            fmt = int(rng.choice([FMT_F32, FMT_F32, FMT_I16, FMT_I24, FMT_I32]))
+            srate = int(rng.choice([rate, rate, 44100, 22050, 96000]))
+            speed = float(rng.choice([1.0, 1.0, 0.5, 2.0, 0.91875, 1.3]))
+            frames = int(rng.randint(16, 3000))
+            length = float(rng.randint(1, total // 2 + 2))
+            sid = eng.add_sample(_src(rng, 2, frames, n_tracks, fmt), srate, fmt)
+            eng.add_clip(t, sid, pos / spb, (pos + length) / spb, float(rng.randint(0, 40)), speed,
+                         float(rng.uniform(0.1, 1.5)))
+            pos += length + float(rng.choice([0.0, 0.0, rng.randint(1, 200)]))
+    eng.play()
+    outs = []
+    done = 0
+    while done < n_blocks:
+        n = int(min(n_blocks - done, rng.randint(1, 5)))
+        outs.append(eng.process(n))
+        done += n
+        t = int(rng.randint(0, n_tracks))
+        which = rng.randint(0, 3)
+        if which == 0:
+            eng.set_volume(t, float(rng.uniform(-20, 3)))
+        elif which == 1:
+            eng.set_pan(t, float(rng.uniform(-1, 1)))
+        else:
+            eng.set_mute(t, bool(rng.rand() < 0.5))
+    return _collect(eng, outs, n_tracks)
+
+
+ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
+           event_split=event_split, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)
