@@ -1,0 +1,152 @@
+/*
+ * wbx.h — C ABI of the B200-native mixing hot path of native-m/whitebox.
+ *
+ * This is the drop-in boundary: everything in the reference from dsp::Sampler::stream down to the master
+ * bus clamp runs behind these calls as hand-written sm_100a CUDA; everything above it (transport, clip
+ * scheduling in doubles, parameter messages) stays host code. All file:line citations are relative to the
+ * reference tree (/root/reference/src).
+ *
+ *   reference                                                       this ABI
+ *   ---------------------------------------------------------------------------------------------------
+ *   Engine::set_audio_channel_config      engine/engine.cpp:43-57   wbx_configure
+ *   Sample (planar channels + 16 pad)     dsp/sample.h:18-28        wbx_sample_upload / wbx_sample_release
+ *   Engine::tracks.size()                 engine/engine.h:40        wbx_set_track_count
+ *   AudioEvent + dsp::Sampler state       engine/event.h:66-74,     wbx_segment (one per Sampler::stream call,
+ *                                         dsp/sampler.h:14-16       or one per run of identical calls)
+ *   volume * pan_coeffs[c]                engine/track.cpp:728-731  track_gains[n_tracks][2]
+ *   Sampler::stream                       dsp/sampler.cpp:88-210    \
+ *   dsp::apply_gain                       dsp/dsp_ops.h:27-31        |
+ *   VUMeter::push_samples                 engine/vu_meter.h:20-30    |  wbx_render (= wbx_submit + wbx_mix
+ *   AudioBuffer::clear / ::mix            core/audio_buffer.h:67-82  |              + wbx_fetch)
+ *   output clamp                          engine/engine.cpp:1627-36 /
+ *   convert_f32_to_interleaved_*          core/audio_format_conv.cpp wbx_fetch_interleaved
+ *
+ * Conventions: every function returns 0 (WBX_OK) or a negative wbx_status; nothing throws; one thread
+ * drives an engine at a time (the reference's audio thread); no allocation happens in steady state (device
+ * and pinned staging buffers grow on first use of a larger size and are then reused). There is NO CPU
+ * fallback: without a CUDA device wbx_create fails with WBX_ERR_NO_DEVICE.
+ */
+#ifndef WBX_H
+#define WBX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WBX_ABI_VERSION 1
+
+typedef struct wbx_engine wbx_engine;
+
+typedef enum wbx_status {
+  WBX_OK = 0,
+  WBX_ERR_INVALID = -1,     /* bad argument / call order */
+  WBX_ERR_CUDA = -2,        /* a CUDA runtime call failed; see wbx_last_error */
+  WBX_ERR_NOMEM = -3,       /* host or device allocation failed */
+  WBX_ERR_UNSUPPORTED = -4, /* e.g. more than 2 output channels (pan_coeffs[2], engine/track.h:50) */
+  WBX_ERR_NO_DEVICE = -5    /* no usable sm_100 device: there is no CPU path */
+} wbx_status;
+
+/* Source sample element types — numeric values of wb::AudioFormat (core/audio_format.h:7-20).
+ * I24 means 24-bit data widened to an int32 container, which is how the sampler reads it
+ * (dsp/sampler.cpp:121-132) and how the loader stores it (dsp/sample.cpp:20). */
+typedef enum wbx_format { WBX_FMT_I16 = 3, WBX_FMT_I24 = 5, WBX_FMT_I24_X8 = 6, WBX_FMT_I32 = 7, WBX_FMT_F32 = 9 } wbx_format;
+
+/* One dsp::Sampler::stream call (dsp/sampler.cpp:88-210) as Track::process issues it
+ * (engine/track.cpp:678,718), or `n_blocks` consecutive identical calls, one per callback.
+ *
+ * For block b in [block, block + n_blocks) the device renders
+ *     dst[c][dst_offset + j] += resample(sample, pos_b + j * speed) * gain        j < min(length, remaining)
+ * with pos_block = src_pos and pos_{b+1} = pos_b + (double)length * speed — the exact f64 recurrence of
+ * Sampler::sample_offset_ (sampler.cpp:103,209). speed == 1.0 takes the unity-copy branch
+ * (sampler.cpp:106-158; position truncated to an integer), anything else the 2-tap linear branch
+ * (sampler.cpp:34-59). Output channel c reads source channel c % sample_channels (sampler.cpp:111). */
+typedef struct wbx_segment {
+  uint32_t track;      /* index into Engine::tracks — also the bus summation order */
+  uint32_t block;      /* first callback (0-based within this render) the call belongs to */
+  uint32_t n_blocks;   /* run length in callbacks, >= 1 */
+  uint32_t dst_offset; /* `buffer_offset` argument: first frame written within the block */
+  uint32_t length;     /* `num_samples` argument (before clipping to the sample's end) */
+  uint32_t sample_id;  /* from wbx_sample_upload */
+  double src_pos;      /* Sampler::sample_offset_ at the first call */
+  double speed;        /* Sampler::playback_speed_ = src_rate / dst_rate * clip speed (sampler.h:24), > 0 */
+  float gain;          /* AudioClip::gain (engine/clip.h:44) */
+  uint32_t reserved;   /* must be 0 */
+} wbx_segment;
+
+/* Bus summation order (wbx_set_sum_mode). */
+typedef enum wbx_sum_mode {
+  WBX_SUM_AUTO = 0,  /* exact when the render is large enough to fill the GPU that way, else tree */
+  WBX_SUM_EXACT = 1, /* tracks added 0..N-1 sequentially in f32 per output sample: bit-identical to
+                        AudioBuffer::mix order (core/audio_buffer.h:73-82, engine.cpp:1600-1617) */
+  WBX_SUM_TREE = 2   /* track groups summed in parallel, group partials added in fixed group order:
+                        deterministic, re-associated (within 1e-5 of block peak of the reference) */
+} wbx_sum_mode;
+
+/* wbx_mix flags */
+#define WBX_MIX_NO_CLAMP 1u /* leave the bus unclamped (partial bus of a track shard, clamp after the reduce) */
+
+/* ---- lifetime / configuration ---------------------------------------------------------------------- */
+int wbx_abi_version(void);
+int wbx_create(wbx_engine** out, int device_ordinal);
+int wbx_destroy(wbx_engine* e);
+const char* wbx_last_error(const wbx_engine* e);
+/* Engine::set_audio_channel_config(_, out_channels, block_frames, sample_rate). May be called again at
+ * any time (device change, engine/config.cpp:198-232); resident samples survive. out_channels is 1 or 2. */
+int wbx_configure(wbx_engine* e, uint32_t out_channels, uint32_t block_frames, uint32_t sample_rate);
+int wbx_set_track_count(wbx_engine* e, uint32_t n_tracks);
+int wbx_set_sum_mode(wbx_engine* e, int mode);
+/* Run all work of this engine on an existing CUDA stream (cudaStream_t as void*); NULL = engine's own. */
+int wbx_set_stream(wbx_engine* e, void* cuda_stream);
+
+/* ---- resident samples (dsp/sample.h:18-28) -------------------------------------------------------- */
+/* planar[c] points to `frames` elements of `format` (host memory). The engine keeps a device copy with
+ * >= 16 zero frames of tail padding (dsp/sample.cpp:127,140). */
+int wbx_sample_upload(wbx_engine* e, int format, uint32_t channels, uint64_t frames, uint32_t sample_rate,
+                      const void* const* planar, uint32_t* out_id);
+int wbx_sample_release(wbx_engine* e, uint32_t id);
+
+/* ---- render ----------------------------------------------------------------------------------------- */
+/* One call = n_blocks consecutive Engine::process callbacks (n_blocks = 1 is the realtime callback).
+ *   track_gains  [n_tracks][2] f32: (mute ? 0 : volume) * pan_coeffs[c]            (track.cpp:728-731)
+ *   out_channels out_channels pointers, each to n_blocks*block_frames f32 (AudioBuffer layout, one
+ *                channel = one contiguous array, core/audio_buffer.h:19-23); callback b is frames
+ *                [b*block_frames, (b+1)*block_frames). Clamped to [-1, 1] (NaN passes, engine.cpp:1627-36).
+ *   peaks        [n_blocks][n_tracks][2] f32 block peak per track/channel = what VUMeter::push_samples
+ *                offers to `level` in that callback (vu_meter.h:20-30); may be NULL. */
+int wbx_render(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
+               uint32_t n_blocks, float* const* out_channels, float* peaks);
+
+/* The three stages of wbx_render, for callers that keep data on the device (sharded multi-GPU mixing,
+ * benchmarking the kernel alone):
+ *   wbx_submit  H2D of the segment table + gains, device-side schedule expansion (asynchronous)
+ *   wbx_mix     the fused sampler/gain/pan/peak/bus-sum/clamp kernel over the submitted schedule
+ *   wbx_fetch   D2H of bus and peaks into AudioBuffer-style host channels, then stream synchronise */
+int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
+               uint32_t n_blocks);
+int wbx_mix(wbx_engine* e, uint32_t flags);
+int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks);
+/* planar f32 bus -> interleaved device format (core/audio_format_conv.cpp:5-106) fused after the clamp;
+ * dst_format: WBX_FMT_I16 / I24 (3 packed bytes) / I24_X8 / I32 / F32. dst is host memory of
+ * n_blocks*block_frames*out_channels elements. */
+int wbx_fetch_interleaved(wbx_engine* e, void* dst, int dst_format);
+
+/* Device-side views of the last wbx_mix result (valid until the next wbx_submit):
+ * bus [out_channels][n_blocks*block_frames] f32, peaks [n_blocks][n_tracks][2] f32. */
+int wbx_device_bus(wbx_engine* e, float** d_bus, uint64_t* n_floats);
+int wbx_device_peaks(wbx_engine* e, float** d_peaks, uint64_t* n_floats);
+/* Clamp n floats at a device pointer to [-1, 1] on the engine's stream (engine.cpp:1627-1636) — the step
+ * that must follow the cross-GPU bus reduce when tracks are sharded. */
+int wbx_clamp_device(wbx_engine* e, float* d_bus, uint64_t n_floats);
+int wbx_synchronize(wbx_engine* e);
+
+/* ---- introspection --------------------------------------------------------------------------------- */
+/* Number of CUDA kernels this engine has launched since creation (bench.py's gpu_launches). */
+uint64_t wbx_launch_count(const wbx_engine* e);
+/* Name of the mix kernel variant the last wbx_mix used ("exact/vec16", "tree/g8", ...). */
+const char* wbx_last_kernel(const wbx_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WBX_H */

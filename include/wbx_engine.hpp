@@ -1,0 +1,152 @@
+// wbx_engine.hpp — C++ host side of the B200 mixing path: keeps the reference engine's call shape
+// (wb::Engine, engine/engine.h:26-271; wb::Track, engine/track.h:90-273) for everything the mix needs, does
+// the transport / clip scheduling / parameter bookkeeping on the host in doubles exactly as the reference
+// does (engine/track.cpp:258-451, 587-736), and hands the sample work to the CUDA engine through the C ABI
+// in wbx.h. It never touches a sample value itself and has no CPU render path.
+//
+// Drop-in use: where audio_io_* calls `engine->process(input_buffer_, output_buffer_, sample_rate)`
+// (engine/audio_io_pulseaudio.cpp:411, engine/audio_io_wasapi.cpp:708) a wbx::Engine can be called with the
+// same wb::AudioBuffer<float> objects: process() is a template over any buffer type that exposes
+// `n_samples`, `n_channels` and `channel_buffers` (core/audio_buffer.h:19-23).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "wbx.h"
+
+namespace wbx {
+
+// (mute ? 0 : volume) and pan law, engine/track.h:46-53
+struct TrackParameterState {
+  float volume_db = 0.0f;
+  float volume = 0.0f;
+  float pan = 0.0f;
+  float pan_coeffs[2] = {0.0f, 0.0f};
+  bool mute = false;
+};
+
+struct PanningCoefficient {
+  float left, right;
+};
+// core/panning_law.cpp:9-32 (ConstantPower_3db) and core/core_math.h:83-89 — host-only scalar math
+PanningCoefficient calculate_panning_coefs(float pan);
+float db_to_linear(float db);
+
+struct AudioClip {  // engine/clip.h:39-45 + Clip time placement (:68-70)
+  double min_time = 0, max_time = 0;  // beats
+  double start_offset = 0;            // source frames
+  double speed = 1.0;
+  float gain = 1.0f;
+  uint32_t sample_id = 0;
+  uint32_t sample_rate = 0;
+  bool internal_state_changed = false;
+};
+
+enum class EventType : uint8_t { None, StopSample, PlaySample };  // engine/event.h:11-15
+
+struct AudioEvent {  // engine/event.h:66-74
+  EventType type = EventType::None;
+  uint32_t buffer_offset = 0;
+  double time = 0, speed = 0;
+  uint64_t sample_offset = 0;
+  const AudioClip* clip = nullptr;
+};
+
+struct Track {
+  std::string name;
+  std::vector<AudioClip*> clips;  // sorted by min_time, never overlapping
+  // scheduler state (TrackEventState, engine/track.h:36-44)
+  bool has_clip_idx = false;
+  uint32_t clip_idx = 0;
+  bool refresh_voice = false;
+  bool partially_ended = false;
+  std::vector<AudioEvent> audio_event_buffer;
+  AudioEvent current_audio_event;
+  // dsp::Sampler state (dsp/sampler.h:14-16); the device replays the same recurrence
+  double playback_speed = 0, sample_offset = 0;
+  TrackParameterState ui_parameter_state, parameter_state;
+  struct Msg {
+    uint32_t id;
+    double value;
+  };
+  std::vector<Msg> track_msg_queue;  // UI -> audio parameter messages (engine/track.h:131)
+  float level[2] = {0, 0};           // VUMeter::level (engine/vu_meter.h:17): max since last read
+  int32_t open_run = -1;             // index of this track's extendable run in the segment list
+  ~Track();
+  void set_volume(float db);  // engine/track.cpp:47-57
+  void set_pan(float pan);    // :59-68
+  void set_mute(bool mute);   // :70-79
+};
+
+class Engine {
+ public:
+  // device_ordinal < 0 makes a scheduling-only engine (segment tables, no rendering: there is no CPU path).
+  explicit Engine(int device_ordinal = 0);
+  ~Engine();
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+  bool ok() const { return dev_ != nullptr; }
+  const char* last_error() const;
+
+  // engine/engine.cpp:43-57, :24-30, :32-41
+  int set_audio_channel_config(uint32_t input_channels, uint32_t output_channels, uint32_t buffer_size,
+                               uint32_t sample_rate);
+  void set_bpm(double bpm);
+  void set_playhead_position(double beat);
+
+  Track* add_track(const std::string& name);  // engine/engine.cpp:199-207
+  // Resident Sample (dsp/sample.h:18-28); returns the id clips refer to, or a negative wbx_status.
+  int add_sample(int format, uint32_t channels, uint64_t frames, uint32_t sample_rate, const void* const* planar);
+  // engine/engine.cpp:293-309 + add_to_cliplist (:409-461) for clips that do not overlap an existing one.
+  int add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
+                     double speed, float gain);
+  void play();  // engine/engine.cpp:68-80
+  void stop();  // :82-92
+
+  // One audio callback: Engine::process(input_buffer, output_buffer, sample_rate), engine.cpp:1576-1654.
+  template <class Buffer>
+  int process(const Buffer& /*input_buffer*/, Buffer& output_buffer, double sample_rate) {
+    if (output_buffer.n_samples != buffer_size_ || output_buffer.n_channels != out_channels_) return WBX_ERR_INVALID;
+    return render(1, output_buffer.channel_buffers, nullptr, sample_rate);
+  }
+
+  // n_blocks consecutive callbacks in one device launch (offline bounce / throughput mode). out_channels[c]
+  // receives n_blocks * buffer_size frames; peaks (optional) [n_blocks][n_tracks][2].
+  int render(uint32_t n_blocks, float* const* out_channels, float* peaks, double sample_rate = 0.0);
+
+  // Build the segment table for n_blocks callbacks and advance the transport, without touching the device
+  // (render = schedule + wbx_render). Exposed for tests, multi-GPU sharding and benchmarks.
+  int schedule(uint32_t n_blocks, double sample_rate = 0.0);
+  const std::vector<wbx_segment>& segments() const { return segs_; }
+  const std::vector<float>& track_gains() const { return gains_; }
+
+  wbx_engine* device() const { return dev_; }
+  std::vector<Track*> tracks;
+  double ppq = 96.0;
+  double playhead = 0, playhead_start = 0, sample_position = 0;
+  bool playing = false;
+  bool fast_forward = true;  // skip event-free callbacks in closed form while scheduling (same results)
+
+ private:
+  void process_event(Track& t, double start_time, double end_time, double sample_position_, double beat_duration,
+                     double sample_rate, uint32_t buffer_size);
+  void stream(Track& t, uint32_t track_index, uint32_t block, uint32_t num_samples, uint32_t buffer_offset);
+  void track_block(Track& t, uint32_t track_index, uint32_t block, double sample_rate, double beat_duration,
+                   double start_time, double end_time, bool currently_playing);
+  wbx_engine* dev_ = nullptr;
+  bool host_only_ = false;
+  uint32_t out_channels_ = 2, buffer_size_ = 512, sample_rate_ = 48000;
+  double beat_duration_ = 0.5;
+  struct SampleInfo {
+    uint64_t count;
+    uint32_t rate;
+  };
+  std::vector<SampleInfo> samples_;
+  std::vector<wbx_segment> segs_;
+  std::vector<float> gains_;
+  std::vector<float> peaks_;
+  std::string err_;
+};
+
+}  // namespace wbx

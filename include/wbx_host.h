@@ -1,0 +1,60 @@
+/*
+ * wbx_host.h — C exports of the host-side engine (include/wbx_engine.hpp) for FFI callers (ctypes, cgo-style
+ * bindings). Same call shape as the reference's editing / transport API:
+ *   Engine::add_track (engine/engine.cpp:199), Track::set_volume/set_pan/set_mute (engine/track.cpp:47-79),
+ *   Engine::add_audio_clip (engine.cpp:293), Engine::set_playhead_position (:32), play (:68), stop (:82),
+ *   Engine::process (:1576) — here wbxh_render(n_blocks = 1) — and the batched n_blocks > 1 form.
+ * All sample work runs in the CUDA engine (wbx.h); there is no CPU render path.
+ */
+#ifndef WBX_HOST_H
+#define WBX_HOST_H
+#include <stdint.h>
+
+#include "wbx.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wbxh_engine wbxh_engine;
+
+/* device_ordinal < 0: scheduling-only engine (wbxh_schedule works, wbxh_render returns WBX_ERR_NO_DEVICE). */
+int wbxh_create(wbxh_engine** out, int device_ordinal, uint32_t out_channels, uint32_t block_frames,
+                uint32_t sample_rate, double bpm);
+void wbxh_destroy(wbxh_engine* h);
+const char* wbxh_last_error(wbxh_engine* h);
+wbx_engine* wbxh_device(wbxh_engine* h); /* the underlying device engine (wbx.h) */
+
+int wbxh_add_track(wbxh_engine* h, float volume_db, float pan, int mute); /* returns the track index */
+void wbxh_set_volume(wbxh_engine* h, int track, float db);
+void wbxh_set_pan(wbxh_engine* h, int track, float pan);
+void wbxh_set_mute(wbxh_engine* h, int track, int mute);
+/* returns the sample id (>= 0) or a negative wbx_status */
+int wbxh_add_sample(wbxh_engine* h, int format, uint32_t channels, uint64_t frames, uint32_t sample_rate,
+                    const void* const* planar);
+int wbxh_add_clip(wbxh_engine* h, int track, int sample, double min_beat, double max_beat, double start_offset,
+                  double speed, float gain);
+void wbxh_set_playhead(wbxh_engine* h, double beat);
+void wbxh_play(wbxh_engine* h);
+void wbxh_stop(wbxh_engine* h);
+void wbxh_set_fast_forward(wbxh_engine* h, int on);
+
+/* n_blocks consecutive Engine::process callbacks: out_channels[c] -> n_blocks*block_frames f32 (clamped bus),
+ * peaks (optional) [n_blocks][n_tracks][2]. */
+int wbxh_render(wbxh_engine* h, uint32_t n_blocks, float* const* out_channels, float* peaks);
+/* host scheduling only: builds the wbx_segment table + track gains for n_blocks callbacks and advances the
+ * transport; pointers stay valid until the next call on this engine. */
+int wbxh_schedule(wbxh_engine* h, uint32_t n_blocks, const wbx_segment** segs, uint32_t* n_segs,
+                  const float** gains);
+
+double wbxh_sampler_offset(wbxh_engine* h, int track); /* Track::sampler.sample_offset_ */
+double wbxh_sample_position(wbxh_engine* h);           /* Engine::sample_position */
+double wbxh_playhead(wbxh_engine* h);                  /* Engine::playhead */
+float wbxh_level(wbxh_engine* h, int track, int channel, int reset); /* VUMeter::level (+ exchange(0)) */
+void wbxh_panning_coefs(float pan, float* left, float* right);
+float wbxh_db_to_linear(float db);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

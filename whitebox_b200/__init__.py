@@ -1,0 +1,371 @@
+"""whitebox_b200 — B200-native mixing hot path of native-m/whitebox.
+
+Python is only a thin ctypes binding over the C ABI in include/wbx.h (device engine) and include/wbx_host.h
+(host engine with the reference's editing/transport API). All sample work runs in hand-written sm_100a CUDA
+kernels inside whitebox_b200/libwbx.so; there is no CPU render path and importing this package fails loudly
+if the library has not been built (python whitebox_b200/build.py, or __graft_entry__.build()).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwbx.so")
+
+FMT_I16, FMT_I24, FMT_I24_X8, FMT_I32, FMT_F32 = 3, 5, 6, 7, 9
+SUM_AUTO, SUM_EXACT, SUM_TREE = 0, 1, 2
+MIX_NO_CLAMP = 1
+_NP = {FMT_I16: np.int16, FMT_I24: np.int32, FMT_I32: np.int32, FMT_F32: np.float32}
+
+
+class Segment(C.Structure):
+    """wbx_segment (include/wbx.h)."""
+    _fields_ = [("track", C.c_uint32), ("block", C.c_uint32), ("n_blocks", C.c_uint32), ("dst_offset", C.c_uint32),
+                ("length", C.c_uint32), ("sample_id", C.c_uint32), ("src_pos", C.c_double), ("speed", C.c_double),
+                ("gain", C.c_float), ("reserved", C.c_uint32)]
+
+
+SEGMENT_DTYPE = np.dtype([("track", "<u4"), ("block", "<u4"), ("n_blocks", "<u4"), ("dst_offset", "<u4"),
+                          ("length", "<u4"), ("sample_id", "<u4"), ("src_pos", "<f8"), ("speed", "<f8"),
+                          ("gain", "<f4"), ("reserved", "<u4")])
+assert SEGMENT_DTYPE.itemsize == C.sizeof(Segment) == 48
+
+# every symbol include/wbx.h and include/wbx_host.h declare
+WBX_SYMBOLS = [
+    "wbx_abi_version", "wbx_create", "wbx_destroy", "wbx_last_error", "wbx_configure", "wbx_set_track_count",
+    "wbx_set_sum_mode", "wbx_set_stream", "wbx_sample_upload", "wbx_sample_release", "wbx_render", "wbx_submit",
+    "wbx_mix", "wbx_fetch", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
+    "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel",
+]
+WBXH_SYMBOLS = [
+    "wbxh_create", "wbxh_destroy", "wbxh_last_error", "wbxh_device", "wbxh_add_track", "wbxh_set_volume",
+    "wbxh_set_pan", "wbxh_set_mute", "wbxh_add_sample", "wbxh_add_clip", "wbxh_set_playhead", "wbxh_play",
+    "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
+    "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
+]
+
+_lib = None
+
+
+class WbxError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libwbx.so (never falls back to anything else)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WbxError("whitebox_b200/libwbx.so is not built: run `python whitebox_b200/build.py` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, dbl, flt, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_double, C.c_float, C.c_int
+    pp = C.POINTER(vp)
+    L.wbx_abi_version.restype = i32
+    L.wbx_create.argtypes = [pp, i32]
+    L.wbx_destroy.argtypes = [vp]
+    L.wbx_last_error.argtypes = [vp]
+    L.wbx_last_error.restype = C.c_char_p
+    L.wbx_configure.argtypes = [vp, u32, u32, u32]
+    L.wbx_set_track_count.argtypes = [vp, u32]
+    L.wbx_set_sum_mode.argtypes = [vp, i32]
+    L.wbx_set_stream.argtypes = [vp, vp]
+    L.wbx_sample_upload.argtypes = [vp, i32, u32, u64, u32, pp, C.POINTER(u32)]
+    L.wbx_sample_release.argtypes = [vp, u32]
+    L.wbx_render.argtypes = [vp, vp, u32, vp, u32, pp, vp]
+    L.wbx_submit.argtypes = [vp, vp, u32, vp, u32]
+    L.wbx_mix.argtypes = [vp, u32]
+    L.wbx_fetch.argtypes = [vp, pp, vp]
+    L.wbx_fetch_interleaved.argtypes = [vp, vp, i32]
+    L.wbx_device_bus.argtypes = [vp, pp, C.POINTER(u64)]
+    L.wbx_device_peaks.argtypes = [vp, pp, C.POINTER(u64)]
+    L.wbx_clamp_device.argtypes = [vp, vp, u64]
+    L.wbx_synchronize.argtypes = [vp]
+    L.wbx_launch_count.argtypes = [vp]
+    L.wbx_launch_count.restype = u64
+    L.wbx_last_kernel.argtypes = [vp]
+    L.wbx_last_kernel.restype = C.c_char_p
+    L.wbxh_create.argtypes = [pp, i32, u32, u32, u32, dbl]
+    L.wbxh_destroy.argtypes = [vp]
+    L.wbxh_destroy.restype = None
+    L.wbxh_last_error.argtypes = [vp]
+    L.wbxh_last_error.restype = C.c_char_p
+    L.wbxh_device.argtypes = [vp]
+    L.wbxh_device.restype = vp
+    L.wbxh_add_track.argtypes = [vp, flt, flt, i32]
+    for f in ("wbxh_set_volume", "wbxh_set_pan"):
+        getattr(L, f).argtypes = [vp, i32, flt]
+        getattr(L, f).restype = None
+    L.wbxh_set_mute.argtypes = [vp, i32, i32]
+    L.wbxh_set_mute.restype = None
+    L.wbxh_add_sample.argtypes = [vp, i32, u32, u64, u32, pp]
+    L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
+    L.wbxh_set_playhead.argtypes = [vp, dbl]
+    L.wbxh_set_playhead.restype = None
+    for f in ("wbxh_play", "wbxh_stop"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = None
+    L.wbxh_set_fast_forward.argtypes = [vp, i32]
+    L.wbxh_set_fast_forward.restype = None
+    L.wbxh_render.argtypes = [vp, u32, pp, vp]
+    L.wbxh_schedule.argtypes = [vp, u32, pp, C.POINTER(u32), pp]
+    L.wbxh_sampler_offset.argtypes = [vp, i32]
+    L.wbxh_sampler_offset.restype = dbl
+    for f in ("wbxh_sample_position", "wbxh_playhead"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = dbl
+    L.wbxh_level.argtypes = [vp, i32, i32, i32]
+    L.wbxh_level.restype = flt
+    L.wbxh_panning_coefs.argtypes = [flt, C.POINTER(flt), C.POINTER(flt)]
+    L.wbxh_panning_coefs.restype = None
+    L.wbxh_db_to_linear.argtypes = [flt]
+    L.wbxh_db_to_linear.restype = flt
+    _lib = L
+    return L
+
+
+def _chan_ptrs(arr):
+    """arr: [channels][n] contiguous -> (void*[channels])"""
+    return (C.c_void_p * arr.shape[0])(*[arr[c].ctypes.data for c in range(arr.shape[0])])
+
+
+def panning_coefs(pan):
+    l, r = C.c_float(), C.c_float()
+    lib().wbxh_panning_coefs(pan, C.byref(l), C.byref(r))
+    return np.float32(l.value), np.float32(r.value)
+
+
+def db_to_linear(db):
+    return np.float32(lib().wbxh_db_to_linear(db))
+
+
+class DeviceEngine:
+    """The device engine of include/wbx.h: resident samples + segment table -> mixed bus."""
+
+    def __init__(self, device=0, handle=None):
+        self.L = lib()
+        self._own = handle is None
+        if handle is None:
+            h = C.c_void_p()
+            rc = self.L.wbx_create(C.byref(h), device)
+            if rc != 0:
+                raise WbxError("wbx_create(device=%d) failed with status %d: no sm_100 CUDA device "
+                               "(there is no CPU fallback)" % (device, rc))
+            handle = h
+        self.h = handle
+        self.C = self.B = self.n_tracks = 0
+        self.n_blocks = 0
+
+    def close(self):
+        if self.h and self._own:
+            self.L.wbx_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise WbxError("wbx status %d: %s" % (rc, (self.L.wbx_last_error(self.h) or b"").decode()))
+
+    def configure(self, out_channels, block, rate):
+        self._ck(self.L.wbx_configure(self.h, out_channels, block, rate))
+        self.C, self.B = out_channels, block
+
+    def set_track_count(self, n):
+        self._ck(self.L.wbx_set_track_count(self.h, n))
+        self.n_tracks = n
+
+    def set_sum_mode(self, mode):
+        self._ck(self.L.wbx_set_sum_mode(self.h, mode))
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.L.wbx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def sample_upload(self, data, rate, fmt=FMT_F32):
+        data = np.ascontiguousarray(data, dtype=_NP[fmt])
+        sid = C.c_uint32()
+        self._ck(self.L.wbx_sample_upload(self.h, fmt, data.shape[0], data.shape[1], rate, _chan_ptrs(data),
+                                          C.byref(sid)))
+        return sid.value
+
+    def sample_release(self, sid):
+        self._ck(self.L.wbx_sample_release(self.h, sid))
+
+    def submit(self, segs, gains, n_blocks):
+        segs = np.ascontiguousarray(segs, dtype=SEGMENT_DTYPE)
+        gains = np.ascontiguousarray(gains, dtype=np.float32)
+        self._ck(self.L.wbx_submit(self.h, segs.ctypes.data, len(segs), gains.ctypes.data, n_blocks))
+        self.n_blocks = n_blocks
+
+    def submit_raw(self, segs_ptr, n_segs, gains_ptr, n_blocks):
+        self._ck(self.L.wbx_submit(self.h, segs_ptr, n_segs, gains_ptr, n_blocks))
+        self.n_blocks = n_blocks
+
+    def mix(self, flags=0):
+        self._ck(self.L.wbx_mix(self.h, flags))
+
+    def fetch(self, want_peaks=True):
+        out = np.empty((self.C, self.n_blocks * self.B), np.float32)
+        peaks = np.empty((self.n_blocks, self.n_tracks, 2), np.float32) if want_peaks else None
+        self._ck(self.L.wbx_fetch(self.h, _chan_ptrs(out), peaks.ctypes.data if want_peaks else None))
+        return out, peaks
+
+    def fetch_interleaved(self, fmt):
+        frames = self.n_blocks * self.B
+        size = {FMT_I16: 2, FMT_I24: 3, FMT_I24_X8: 4, FMT_I32: 4, FMT_F32: 4}[fmt]
+        n = frames * 3 if fmt == FMT_I24 else frames * self.C * size
+        dst = np.zeros(n, np.uint8)
+        self._ck(self.L.wbx_fetch_interleaved(self.h, dst.ctypes.data, fmt))
+        return dst
+
+    def render(self, segs, gains, n_blocks, want_peaks=True):
+        self.submit(segs, gains, n_blocks)
+        self.mix()
+        return self.fetch(want_peaks)
+
+    def device_bus(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.wbx_device_bus(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def device_peaks(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.wbx_device_peaks(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def clamp_device(self, ptr, n):
+        self._ck(self.L.wbx_clamp_device(self.h, C.c_void_p(ptr), n))
+
+    def synchronize(self):
+        self._ck(self.L.wbx_synchronize(self.h))
+
+    def launch_count(self):
+        return self.L.wbx_launch_count(self.h)
+
+    def last_kernel(self):
+        return (self.L.wbx_last_kernel(self.h) or b"").decode()
+
+
+class Engine:
+    """Host engine (include/wbx_host.h): the reference's editing / transport API in front of the CUDA mix.
+
+    batched=True renders process(n_blocks) as ONE device launch over n_blocks callbacks (offline bounce /
+    throughput mode); batched=False issues one launch per callback like the realtime audio thread.
+    """
+
+    def __init__(self, out_channels=2, block=512, rate=48000, bpm=120.0, device=0, batched=True,
+                 sum_mode=SUM_AUTO):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.wbxh_create(C.byref(h), device, out_channels, block, rate, bpm)
+        if rc != 0:
+            raise WbxError("wbxh_create failed with status %d: no sm_100 CUDA device or bad config "
+                           "(there is no CPU fallback)" % rc)
+        self.h = h
+        self.C, self.B, self.rate = out_channels, block, rate
+        self.n_tracks = 0
+        self.batched = batched
+        self.dev = None
+        if device >= 0:  # device < 0: scheduling-only engine (host logic tests); render() then fails
+            self.dev = DeviceEngine(handle=C.c_void_p(self.L.wbxh_device(self.h)))
+            if sum_mode != SUM_AUTO:
+                self.dev.set_sum_mode(sum_mode)
+
+    def close(self):
+        if self.h:
+            self.L.wbxh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise WbxError("wbx status %d: %s" % (rc, (self.L.wbxh_last_error(self.h) or b"").decode()))
+        return rc
+
+    def add_track(self, volume_db=0.0, pan=0.0, mute=False):
+        self.n_tracks += 1
+        return self.L.wbxh_add_track(self.h, volume_db, pan, int(mute))
+
+    def set_volume(self, t, db):
+        self.L.wbxh_set_volume(self.h, t, db)
+
+    def set_pan(self, t, pan):
+        self.L.wbxh_set_pan(self.h, t, pan)
+
+    def set_mute(self, t, m):
+        self.L.wbxh_set_mute(self.h, t, int(m))
+
+    def add_sample(self, data, rate, fmt=FMT_F32):
+        data = np.ascontiguousarray(data, dtype=_NP[fmt])
+        return self._ck(self.L.wbxh_add_sample(self.h, fmt, data.shape[0], data.shape[1], rate, _chan_ptrs(data)))
+
+    def add_clip(self, track, sample, min_beat, max_beat, start_offset=0.0, speed=1.0, gain=1.0):
+        return self._ck(self.L.wbxh_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain))
+
+    def set_playhead(self, beat):
+        self.L.wbxh_set_playhead(self.h, beat)
+
+    def play(self):
+        self.L.wbxh_play(self.h)
+
+    def stop(self):
+        self.L.wbxh_stop(self.h)
+
+    def render(self, n_blocks, want_peaks=True):
+        """-> (bus [C][n_blocks*B], peaks [n_blocks][N][2]) from one device launch."""
+        out = np.empty((self.C, n_blocks * self.B), np.float32)
+        peaks = np.zeros((n_blocks, self.n_tracks, 2), np.float32)
+        self._ck(self.L.wbxh_render(self.h, n_blocks, _chan_ptrs(out),
+                                    peaks.ctypes.data if (want_peaks and self.n_tracks) else None))
+        return out, peaks
+
+    def process(self, n_blocks):
+        """Scenario API shared with the CPU checkers: -> (out [K][C][B], peaks [K][N][2])."""
+        if self.batched:
+            out, peaks = self.render(n_blocks)
+            return np.ascontiguousarray(out.reshape(self.C, n_blocks, self.B).transpose(1, 0, 2)), peaks
+        outs, pks = [], []
+        for _ in range(n_blocks):
+            o, p = self.render(1)
+            outs.append(o.reshape(1, self.C, self.B))
+            pks.append(p)
+        return np.concatenate(outs, axis=0), np.concatenate(pks, axis=0)
+
+    def schedule(self, n_blocks):
+        """Host scheduling only -> (segments structured array copy, gains [N][2] copy)."""
+        segs, n, gains = C.c_void_p(), C.c_uint32(), C.c_void_p()
+        self._ck(self.L.wbxh_schedule(self.h, n_blocks, C.byref(segs), C.byref(n), C.byref(gains)))
+        if n.value:
+            buf = (C.c_char * (n.value * SEGMENT_DTYPE.itemsize)).from_address(segs.value)
+            s = np.frombuffer(buf, dtype=SEGMENT_DTYPE).copy()
+        else:
+            s = np.zeros(0, SEGMENT_DTYPE)
+        if self.n_tracks:
+            gb = (C.c_float * (self.n_tracks * 2)).from_address(gains.value)
+            g = np.frombuffer(gb, dtype=np.float32).reshape(self.n_tracks, 2).copy()
+        else:
+            g = np.zeros((0, 2), np.float32)
+        return s, g
+
+    def sampler_offset(self, t):
+        return self.L.wbxh_sampler_offset(self.h, t)
+
+    def sample_position(self):
+        return self.L.wbxh_sample_position(self.h)
+
+    def playhead(self):
+        return self.L.wbxh_playhead(self.h)
+
+    def level(self, t, c, reset=False):
+        return self.L.wbxh_level(self.h, t, c, int(reset))

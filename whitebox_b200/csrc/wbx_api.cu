@@ -1,0 +1,525 @@
+// wbx_api.cu — the extern "C" ABI of include/wbx.h: engine object, resident samples, schedule upload,
+// kernel launches, result copies. No torch, no CPU fallback: every entry point fails loudly without a device.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/wbx.h"
+#include "wbx_device.cuh"
+
+namespace wbx {
+cudaError_t launch_mix(const MixParams& p, int fpl, int n_sm, cudaStream_t stream, int* ctas_out);
+cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, uint32_t n_tracks, uint32_t slots,
+                          cudaStream_t stream);
+cudaError_t launch_clamp(float* x, uint64_t n, int n_sm, cudaStream_t stream);
+cudaError_t launch_interleave(const float* bus, uint64_t frames, uint32_t channels, int fmt, void* dst, int n_sm,
+                              cudaStream_t stream);
+}  // namespace wbx
+
+using namespace wbx;
+
+namespace {
+
+struct SampleRec {
+  void* d_base = nullptr;
+  size_t stride_elems = 0;  // elements between channels
+  uint32_t channels = 0, rate = 0, fmt = 0, esize = 0;
+  uint64_t frames = 0;
+  bool live = false;
+};
+
+// grow-only device / pinned-host buffers: no allocation in steady state
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct wbx_engine {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  uint32_t C = 2, B = 512, rate = 48000, n_tracks = 0;
+  int sum_mode = WBX_SUM_AUTO;
+  std::vector<SampleRec> samples;
+  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv;
+  HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv;
+  std::vector<uint32_t> slot_busy;  // [track][slot] -> first free block
+  uint32_t slot_cap = 0;
+  // last submit
+  uint32_t n_blocks = 0, n_spans = 0, slots = 1;
+  bool submitted = false, mixed = false;
+  uint64_t launches = 0;
+  char err[256] = {0};
+  char kernel_name[64] = {0};
+};
+
+namespace {
+
+int fail(wbx_engine* e, int code, const char* fmt, ...) {
+  if (e) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(e->err, sizeof(e->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(e, call)                                                                            \
+  do {                                                                                         \
+    cudaError_t _err = (call);                                                                 \
+    if (_err != cudaSuccess)                                                                   \
+      return fail((e), WBX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_err), \
+                  __FILE__, __LINE__);                                                         \
+  } while (0)
+
+int dev_reserve(wbx_engine* e, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return WBX_OK;
+  if (b.p) {
+    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t cap = bytes + bytes / 4 + 256;
+  cudaError_t err = cudaMalloc(&b.p, cap);
+  if (err != cudaSuccess) return fail(e, WBX_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(err));
+  b.cap = cap;
+  return WBX_OK;
+}
+
+int host_reserve(wbx_engine* e, HostBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return WBX_OK;
+  if (b.p) {
+    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t cap = bytes + bytes / 4 + 256;
+  cudaError_t err = cudaMallocHost(&b.p, cap);
+  if (err != cudaSuccess)
+    return fail(e, WBX_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", cap, cudaGetErrorString(err));
+  b.cap = cap;
+  return WBX_OK;
+}
+
+uint32_t esize_of(int fmt) {
+  switch (fmt) {
+    case WBX_FMT_I16: return 2;
+    case WBX_FMT_I24:
+    case WBX_FMT_I32:
+    case WBX_FMT_F32: return 4;
+    default: return 0;
+  }
+}
+
+// frames per lane (tile = 32 * fpl frames) and track groups for a render of n_blocks callbacks
+void choose_shape(const wbx_engine* e, uint32_t n_blocks, int* fpl_out, uint32_t* groups_out) {
+  const uint32_t B = e->B, N = e->n_tracks;
+  // resident warps per SM for each variant (see launch_mix): fpl16: 2x5, fpl8: 2x8, fpl4: 2x8
+  const long sm = e->n_sm;
+  int fpl = 16;
+  if (B <= 128)
+    fpl = 4;
+  else if (B <= 256)
+    fpl = 8;
+  auto items_for = [&](int f) { return (long)n_blocks * ((B + 32 * f - 1) / (32 * f)); };
+  auto warps_for = [&](int f) { return sm * (f == 16 ? 10 : 16); };
+  const char* env = getenv("WBX_FPL");
+  if (env && (atoi(env) == 4 || atoi(env) == 8 || atoi(env) == 16)) {
+    fpl = atoi(env);
+  } else {
+    // prefer big tiles, but split tiles while the exact-order item count cannot fill the machine ~4x
+    while (fpl > 4 && items_for(fpl) < 4 * warps_for(fpl)) fpl >>= 1;
+  }
+  uint32_t groups = 1;
+  const long items = items_for(fpl), warps = warps_for(fpl);
+  bool tree = e->sum_mode == WBX_SUM_TREE || (e->sum_mode == WBX_SUM_AUTO && items < warps);
+  if (tree && N > 32) {
+    long want = (2 * warps + items - 1) / items;  // ~2 items per resident warp
+    long max_groups = (N + 31) / 32;              // at least 32 tracks per group
+    if (want > max_groups) want = max_groups;
+    if (want < 1) want = 1;
+    groups = (uint32_t)want;
+  }
+  const char* genv = getenv("WBX_GROUPS");
+  if (genv && atoi(genv) > 0 && e->sum_mode != WBX_SUM_EXACT) groups = (uint32_t)atoi(genv);
+  if (groups > N && N > 0) groups = N;
+  if (groups < 1) groups = 1;
+  *fpl_out = fpl;
+  *groups_out = groups;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wbx_abi_version(void) { return WBX_ABI_VERSION; }
+
+int wbx_create(wbx_engine** out, int device_ordinal) {
+  if (!out) return WBX_ERR_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return WBX_ERR_NO_DEVICE;
+  if (device_ordinal < 0 || device_ordinal >= n_dev) return WBX_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) return WBX_ERR_NO_DEVICE;
+  if (prop.major != 10) return WBX_ERR_NO_DEVICE;  // sm_100a code only
+  wbx_engine* e = new (std::nothrow) wbx_engine();
+  if (!e) return WBX_ERR_NOMEM;
+  e->device = device_ordinal;
+  e->n_sm = prop.multiProcessorCount;
+  if (cudaSetDevice(device_ordinal) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    return WBX_ERR_CUDA;
+  }
+  e->stream = e->own_stream;
+  *out = e;
+  return WBX_OK;
+}
+
+int wbx_destroy(wbx_engine* e) {
+  if (!e) return WBX_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (auto& s : e->samples)
+    if (s.live) cudaFree(s.d_base);
+  for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv})
+    if (b->p) cudaFree(b->p);
+  for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv})
+    if (b->p) cudaFreeHost(b->p);
+  cudaStreamDestroy(e->own_stream);
+  delete e;
+  return WBX_OK;
+}
+
+const char* wbx_last_error(const wbx_engine* e) { return e ? e->err : "null engine"; }
+
+int wbx_configure(wbx_engine* e, uint32_t out_channels, uint32_t block_frames, uint32_t sample_rate) {
+  if (!e) return WBX_ERR_INVALID;
+  if (out_channels < 1 || out_channels > 2)
+    return fail(e, WBX_ERR_UNSUPPORTED, "out_channels must be 1 or 2 (pan_coeffs[2], engine/track.h:50)");
+  if (block_frames == 0 || block_frames > 65535) return fail(e, WBX_ERR_INVALID, "block_frames out of range");
+  e->C = out_channels;
+  e->B = block_frames;
+  e->rate = sample_rate;
+  e->submitted = e->mixed = false;
+  return WBX_OK;
+}
+
+int wbx_set_track_count(wbx_engine* e, uint32_t n_tracks) {
+  if (!e) return WBX_ERR_INVALID;
+  e->n_tracks = n_tracks;
+  e->submitted = e->mixed = false;
+  return WBX_OK;
+}
+
+int wbx_set_sum_mode(wbx_engine* e, int mode) {
+  if (!e || mode < WBX_SUM_AUTO || mode > WBX_SUM_TREE) return WBX_ERR_INVALID;
+  e->sum_mode = mode;
+  return WBX_OK;
+}
+
+int wbx_set_stream(wbx_engine* e, void* cuda_stream) {
+  if (!e) return WBX_ERR_INVALID;
+  CU(e, cudaSetDevice(e->device));
+  CU(e, cudaStreamSynchronize(e->stream));
+  e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  return WBX_OK;
+}
+
+int wbx_sample_upload(wbx_engine* e, int format, uint32_t channels, uint64_t frames, uint32_t sample_rate,
+                      const void* const* planar, uint32_t* out_id) {
+  if (!e || !planar || !out_id || channels == 0) return fail(e, WBX_ERR_INVALID, "bad sample arguments");
+  const uint32_t es = esize_of(format);
+  if (!es) return fail(e, WBX_ERR_UNSUPPORTED, "sample format %d not supported by the sampler", format);
+  CU(e, cudaSetDevice(e->device));
+  SampleRec r;
+  r.fmt = (uint32_t)format;
+  r.esize = es;
+  r.channels = channels;
+  r.rate = sample_rate;
+  r.frames = frames;
+  // frames + 16 zero frames (dsp/sample.cpp:127,140) + slack for 16-B aligned windows, stride % 32 == 0
+  r.stride_elems = ((size_t)frames + 16 + 16 + 31) & ~(size_t)31;
+  const size_t bytes = r.stride_elems * es * channels;
+  cudaError_t err = cudaMalloc(&r.d_base, bytes);
+  if (err != cudaSuccess) return fail(e, WBX_ERR_NOMEM, "cudaMalloc(%zu) for sample failed", bytes);
+  CU(e, cudaMemsetAsync(r.d_base, 0, bytes, e->stream));
+  for (uint32_t c = 0; c < channels; c++)
+    CU(e, cudaMemcpyAsync((uint8_t*)r.d_base + (size_t)c * r.stride_elems * es, planar[c], (size_t)frames * es,
+                          cudaMemcpyHostToDevice, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));  // the caller's host arrays may go away after return
+  r.live = true;
+  uint32_t id = 0;
+  for (; id < e->samples.size(); id++)
+    if (!e->samples[id].live) break;
+  if (id == e->samples.size())
+    e->samples.push_back(r);
+  else
+    e->samples[id] = r;
+  *out_id = id;
+  return WBX_OK;
+}
+
+int wbx_sample_release(wbx_engine* e, uint32_t id) {
+  if (!e || id >= e->samples.size() || !e->samples[id].live) return fail(e, WBX_ERR_INVALID, "bad sample id");
+  CU(e, cudaSetDevice(e->device));
+  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, cudaFree(e->samples[id].d_base));
+  e->samples[id] = SampleRec();
+  return WBX_OK;
+}
+
+int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
+               uint32_t n_blocks) {
+  if (!e) return WBX_ERR_INVALID;
+  if (n_blocks == 0) return fail(e, WBX_ERR_INVALID, "n_blocks must be >= 1");
+  if (n_segs && !segs) return fail(e, WBX_ERR_INVALID, "segs is null");
+  if (e->n_tracks && !track_gains) return fail(e, WBX_ERR_INVALID, "track_gains is null");
+  CU(e, cudaSetDevice(e->device));
+  const uint32_t N = e->n_tracks, B = e->B, C = e->C;
+  int rc;
+
+  // ---- validate + resolve segments into spans (pinned staging), assign cell slots --------------------
+  if ((rc = host_reserve(e, e->h_spans, (size_t)(n_segs ? n_segs : 1) * sizeof(DSpan)))) return rc;
+  if ((rc = host_reserve(e, e->h_gains, (size_t)(N ? N : 1) * 2 * sizeof(float)))) return rc;
+  DSpan* hs = (DSpan*)e->h_spans.p;
+  uint32_t slots = 1;
+  if (e->slot_cap == 0) e->slot_cap = 2;
+  if (e->slot_busy.size() < (size_t)N * e->slot_cap) e->slot_busy.resize((size_t)N * e->slot_cap);
+  std::fill(e->slot_busy.begin(), e->slot_busy.end(), 0u);
+  for (uint32_t i = 0; i < n_segs; i++) {
+    const wbx_segment& sg = segs[i];
+    if (sg.track >= N) return fail(e, WBX_ERR_INVALID, "segment %u: track %u >= %u", i, sg.track, N);
+    if (sg.n_blocks == 0 || sg.block >= n_blocks || sg.n_blocks > n_blocks - sg.block)
+      return fail(e, WBX_ERR_INVALID, "segment %u: blocks [%u,+%u) outside render of %u", i, sg.block, sg.n_blocks,
+                  n_blocks);
+    if (sg.dst_offset > B || sg.length > B - sg.dst_offset)
+      return fail(e, WBX_ERR_INVALID, "segment %u: frames [%u,+%u) outside block of %u", i, sg.dst_offset, sg.length, B);
+    if (sg.sample_id >= e->samples.size() || !e->samples[sg.sample_id].live)
+      return fail(e, WBX_ERR_INVALID, "segment %u: unknown sample %u", i, sg.sample_id);
+    if (!(sg.speed > 0.0) || !(sg.src_pos >= 0.0) || !(sg.speed < 1e6))
+      return fail(e, WBX_ERR_INVALID, "segment %u: speed/src_pos must be positive and finite", i);
+    if (sg.reserved != 0) return fail(e, WBX_ERR_INVALID, "segment %u: reserved must be 0", i);
+    const SampleRec& sm = e->samples[sg.sample_id];
+    // slot = first one free at sg.block for this track (segments of a track arrive in block order)
+    uint32_t slot = 0;
+    for (;; slot++) {
+      if (slot == e->slot_cap) {  // grow the per-track slot table (rare: > 2 calls in one block)
+        const uint32_t nc = e->slot_cap * 2;
+        std::vector<uint32_t> nb((size_t)N * nc, 0u);
+        for (uint32_t t = 0; t < N; t++)
+          for (uint32_t s = 0; s < e->slot_cap; s++) nb[(size_t)t * nc + s] = e->slot_busy[(size_t)t * e->slot_cap + s];
+        e->slot_busy.swap(nb);
+        e->slot_cap = nc;
+      }
+      if (e->slot_busy[(size_t)sg.track * e->slot_cap + slot] <= sg.block) break;
+    }
+    e->slot_busy[(size_t)sg.track * e->slot_cap + slot] = sg.block + sg.n_blocks;
+    if (slot + 1 > slots) slots = slot + 1;
+    DSpan& d = hs[i];
+    const uint32_t c1 = (C > 1) ? (1 % sm.channels) : 0;  // i % sample->channels, sampler.cpp:111
+    d.ch[0] = sm.d_base;
+    d.ch[1] = (const uint8_t*)sm.d_base + (size_t)c1 * sm.stride_elems * sm.esize;
+    d.pos0 = sg.src_pos;
+    d.speed = sg.speed;
+    d.count = sm.frames;
+    d.gain = sg.gain;
+    d.track = sg.track;
+    d.block0 = sg.block;
+    d.n_blocks = sg.n_blocks;
+    d.dst_off = sg.dst_offset;
+    d.length = sg.length;
+    d.fmt = sm.fmt;
+    d.slot = slot;
+    d.mono = (c1 == 0 || C == 1) ? 1u : 0u;
+    d.pad = 0;
+  }
+  if (N) memcpy(e->h_gains.p, track_gains, (size_t)N * 2 * sizeof(float));
+
+  // ---- device buffers ------------------------------------------------------------------------------
+  const size_t n_cells = (size_t)n_blocks * N * slots;
+  const size_t bus_floats = (size_t)C * n_blocks * B;
+  const size_t peak_floats = (size_t)n_blocks * N * 2;
+  if ((rc = dev_reserve(e, e->d_spans, (size_t)(n_segs ? n_segs : 1) * sizeof(DSpan)))) return rc;
+  if ((rc = dev_reserve(e, e->d_gains, (size_t)(N ? N : 1) * 2 * sizeof(float)))) return rc;
+  if ((rc = dev_reserve(e, e->d_cells, (n_cells ? n_cells : 1) * sizeof(DCell)))) return rc;
+  if ((rc = dev_reserve(e, e->d_bus, bus_floats * sizeof(float)))) return rc;
+  if ((rc = dev_reserve(e, e->d_peaks, (peak_floats ? peak_floats : 1) * sizeof(float)))) return rc;
+
+  if (n_segs)
+    CU(e, cudaMemcpyAsync(e->d_spans.p, hs, (size_t)n_segs * sizeof(DSpan), cudaMemcpyHostToDevice, e->stream));
+  if (N) CU(e, cudaMemcpyAsync(e->d_gains.p, e->h_gains.p, (size_t)N * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  if (n_cells) CU(e, cudaMemsetAsync(e->d_cells.p, 0xFF, n_cells * sizeof(DCell), e->stream));  // span = kSilent
+  if (n_segs && N) {
+    CU(e, launch_expand((const DSpan*)e->d_spans.p, n_segs, (DCell*)e->d_cells.p, N, slots, e->stream));
+    e->launches++;
+  }
+  e->n_blocks = n_blocks;
+  e->n_spans = n_segs;
+  e->slots = slots;
+  e->submitted = true;
+  e->mixed = false;
+  return WBX_OK;
+}
+
+int wbx_mix(wbx_engine* e, uint32_t flags) {
+  if (!e) return WBX_ERR_INVALID;
+  if (!e->submitted) return fail(e, WBX_ERR_INVALID, "wbx_mix before wbx_submit");
+  CU(e, cudaSetDevice(e->device));
+  const uint32_t N = e->n_tracks, B = e->B, C = e->C, K = e->n_blocks;
+  const size_t bus_floats = (size_t)C * K * B;
+  const size_t peak_floats = (size_t)K * N * 2;
+  if (N == 0) {  // Engine::process with no tracks: output_buffer.clear() (engine.cpp:1598)
+    CU(e, cudaMemsetAsync(e->d_bus.p, 0, bus_floats * sizeof(float), e->stream));
+    snprintf(e->kernel_name, sizeof(e->kernel_name), "clear");
+    e->mixed = true;
+    return WBX_OK;
+  }
+  int fpl;
+  uint32_t groups;
+  choose_shape(e, K, &fpl, &groups);
+  const uint32_t T = 32u * fpl;
+  const uint32_t n_tiles = (B + T - 1) / T;
+  const uint32_t tpg = (N + groups - 1) / groups;
+  groups = (N + tpg - 1) / tpg;
+  int rc;
+  const size_t n_counters = 1 + (size_t)K * n_tiles;
+  if ((rc = dev_reserve(e, e->d_counters, n_counters * sizeof(uint32_t)))) return rc;
+  if (groups > 1)
+    if ((rc = dev_reserve(e, e->d_ws, (size_t)K * n_tiles * groups * 2 * T * sizeof(float)))) return rc;
+  CU(e, cudaMemsetAsync(e->d_counters.p, 0, n_counters * sizeof(uint32_t), e->stream));
+  CU(e, cudaMemsetAsync(e->d_peaks.p, 0, peak_floats * sizeof(float), e->stream));
+
+  MixParams p;
+  p.spans = (const DSpan*)e->d_spans.p;
+  p.cells = (const DCell*)e->d_cells.p;
+  p.gains = (const float*)e->d_gains.p;
+  p.bus = (float*)e->d_bus.p;
+  p.peaks = (float*)e->d_peaks.p;
+  p.ws = (float*)e->d_ws.p;
+  p.counters = (uint32_t*)e->d_counters.p;
+  p.n_tracks = N;
+  p.n_blocks = K;
+  p.slots = e->slots;
+  p.B = B;
+  p.C = C;
+  p.n_tiles = n_tiles;
+  p.groups = groups;
+  p.tracks_per_group = tpg;
+  p.n_items = K * n_tiles * groups;
+  p.clamp = (flags & WBX_MIX_NO_CLAMP) ? 0u : 1u;
+  int ctas = 0;
+  CU(e, launch_mix(p, fpl, e->n_sm, e->stream, &ctas));
+  e->launches++;
+  snprintf(e->kernel_name, sizeof(e->kernel_name), "%s/fpl%d/g%u/ctas%d", groups == 1 ? "exact" : "tree", fpl, groups, ctas);
+  e->mixed = true;
+  return WBX_OK;
+}
+
+int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks) {
+  if (!e) return WBX_ERR_INVALID;
+  if (!e->mixed) return fail(e, WBX_ERR_INVALID, "wbx_fetch before wbx_mix");
+  CU(e, cudaSetDevice(e->device));
+  const size_t chan_floats = (size_t)e->n_blocks * e->B;
+  const size_t bus_floats = chan_floats * e->C;
+  const size_t peak_floats = (size_t)e->n_blocks * e->n_tracks * 2;
+  int rc;
+  if (out_channels) {
+    if ((rc = host_reserve(e, e->h_bus, bus_floats * sizeof(float)))) return rc;
+    CU(e, cudaMemcpyAsync(e->h_bus.p, e->d_bus.p, bus_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  }
+  if (peaks && peak_floats) {
+    if ((rc = host_reserve(e, e->h_peaks, peak_floats * sizeof(float)))) return rc;
+    CU(e, cudaMemcpyAsync(e->h_peaks.p, e->d_peaks.p, peak_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CU(e, cudaStreamSynchronize(e->stream));
+  if (out_channels)
+    for (uint32_t c = 0; c < e->C; c++)
+      if (out_channels[c]) memcpy(out_channels[c], (const float*)e->h_bus.p + c * chan_floats, chan_floats * sizeof(float));
+  if (peaks && peak_floats) memcpy(peaks, e->h_peaks.p, peak_floats * sizeof(float));
+  return WBX_OK;
+}
+
+int wbx_fetch_interleaved(wbx_engine* e, void* dst, int dst_format) {
+  if (!e || !dst) return WBX_ERR_INVALID;
+  if (!e->mixed) return fail(e, WBX_ERR_INVALID, "wbx_fetch_interleaved before wbx_mix");
+  size_t es;
+  switch (dst_format) {
+    case WBX_FMT_I16: es = 2; break;
+    case WBX_FMT_I24: es = 3; break;
+    case WBX_FMT_I24_X8:
+    case WBX_FMT_I32:
+    case WBX_FMT_F32: es = 4; break;
+    default: return fail(e, WBX_ERR_UNSUPPORTED, "device format %d", dst_format);
+  }
+  CU(e, cudaSetDevice(e->device));
+  const uint64_t frames = (uint64_t)e->n_blocks * e->B;
+  // the reference's packed-I24 writer has no channel stride (audio_format_conv.cpp:31-41): frames*3 bytes
+  const size_t bytes = dst_format == WBX_FMT_I24 ? frames * 3 : frames * e->C * es;
+  int rc;
+  if ((rc = dev_reserve(e, e->d_conv, bytes))) return rc;
+  if ((rc = host_reserve(e, e->h_conv, bytes))) return rc;
+  CU(e, launch_interleave((const float*)e->d_bus.p, frames, e->C, dst_format, e->d_conv.p, e->n_sm, e->stream));
+  e->launches++;
+  CU(e, cudaMemcpyAsync(e->h_conv.p, e->d_conv.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  memcpy(dst, e->h_conv.p, bytes);
+  return WBX_OK;
+}
+
+int wbx_render(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
+               uint32_t n_blocks, float* const* out_channels, float* peaks) {
+  int rc = wbx_submit(e, segs, n_segs, track_gains, n_blocks);
+  if (rc) return rc;
+  if ((rc = wbx_mix(e, 0))) return rc;
+  return wbx_fetch(e, out_channels, peaks);
+}
+
+int wbx_device_bus(wbx_engine* e, float** d_bus, uint64_t* n_floats) {
+  if (!e || !e->submitted) return WBX_ERR_INVALID;
+  if (d_bus) *d_bus = (float*)e->d_bus.p;
+  if (n_floats) *n_floats = (uint64_t)e->C * e->n_blocks * e->B;
+  return WBX_OK;
+}
+
+int wbx_device_peaks(wbx_engine* e, float** d_peaks, uint64_t* n_floats) {
+  if (!e || !e->submitted) return WBX_ERR_INVALID;
+  if (d_peaks) *d_peaks = (float*)e->d_peaks.p;
+  if (n_floats) *n_floats = (uint64_t)e->n_blocks * e->n_tracks * 2;
+  return WBX_OK;
+}
+
+int wbx_clamp_device(wbx_engine* e, float* d_bus, uint64_t n_floats) {
+  if (!e || (!d_bus && n_floats)) return WBX_ERR_INVALID;
+  CU(e, cudaSetDevice(e->device));
+  CU(e, launch_clamp(d_bus, n_floats, e->n_sm, e->stream));
+  e->launches++;
+  return WBX_OK;
+}
+
+int wbx_synchronize(wbx_engine* e) {
+  if (!e) return WBX_ERR_INVALID;
+  CU(e, cudaSetDevice(e->device));
+  CU(e, cudaStreamSynchronize(e->stream));
+  return WBX_OK;
+}
+
+uint64_t wbx_launch_count(const wbx_engine* e) { return e ? e->launches : 0; }
+const char* wbx_last_kernel(const wbx_engine* e) { return e ? e->kernel_name : ""; }
+
+}  // extern "C"

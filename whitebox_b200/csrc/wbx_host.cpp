@@ -1,0 +1,526 @@
+// wbx_host.cpp — host side of the mixing path (see include/wbx_engine.hpp): transport, clip scheduling and
+// parameter bookkeeping in doubles, mirroring the reference's audio-thread host logic so that the segment
+// table handed to the device describes exactly the Sampler::stream calls the reference would make.
+// No sample value is read or written here.
+//
+// Built with -ffp-contract=off: every double operation below must round like the reference's x86-64 build,
+// because event offsets come from truncating those doubles (engine/track.cpp:359-361,378-379,423-425).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/wbx_engine.hpp"
+#include "../../include/wbx_host.h"
+
+namespace wbx {
+
+// ---- scalar math ------------------------------------------------------------------------------------------
+
+// core/core_math.h:209-212
+static inline double beat_to_samples(double beat, double sample_rate, double beat_duration) {
+  double sec = beat * beat_duration;
+  return sec * sample_rate;
+}
+
+// core/core_math.h:83-89
+float db_to_linear(float db) {
+  if (db <= -72.0f) return 0.0f;
+  return std::pow(10.0f, (float)((double)db * 0.05));
+}
+
+// core/panning_law.cpp:9-32, PanningLaw::ConstantPower_3db (the law Track::process hard-codes, track.cpp:627)
+PanningCoefficient calculate_panning_coefs(float p) {
+  constexpr double pi = 3.141592653589793238462643383279502884;
+  const double x = 0.5 * ((double)p + 1.0);
+  const double left = std::sin(0.5 * pi * (1.0 - x));
+  const double right = std::sin(0.5 * pi * x);
+  const double boost = std::sqrt(2.0);
+  return {(float)(left * boost), (float)(right * boost)};
+}
+
+// ---- Track ------------------------------------------------------------------------------------------------
+
+enum : uint32_t { kParamVolume = 0, kParamPan = 1, kParamMute = 2 };  // TrackParameter, engine/track.h:29-34
+
+Track::~Track() {
+  for (auto* c : clips) delete c;
+}
+void Track::set_volume(float db) {
+  ui_parameter_state.volume_db = db;
+  ui_parameter_state.volume = db_to_linear(db);
+  track_msg_queue.push_back({kParamVolume, (double)ui_parameter_state.volume});
+}
+void Track::set_pan(float pan) {
+  ui_parameter_state.pan = pan;
+  track_msg_queue.push_back({kParamPan, (double)pan});
+}
+void Track::set_mute(bool mute) {
+  ui_parameter_state.mute = mute;
+  track_msg_queue.push_back({kParamMute, (double)mute});
+}
+
+// ---- clip lookup (Track::find_next_clip, engine/track.cpp:182-213, incl. find_lower_bound's n-1 start) ----
+
+static bool find_next_clip(const Track& t, double time_pos, uint32_t* idx) {
+  const size_t n = t.clips.size();
+  if (n == 0) return false;
+  if (t.clips.back()->max_time < time_pos) return false;
+  int64_t left = 0, right = (int64_t)n - 1;
+  while (left < right) {
+    const int64_t middle = (left + right) >> 1;
+    if (t.clips[middle]->max_time <= time_pos)
+      left = middle + 1;
+    else
+      right = middle;
+  }
+  *idx = (uint32_t)right;
+  return true;
+}
+
+// Track::reset_playback_state, engine/track.cpp:220-232
+static void reset_playback_state(Track& t, double time_pos, bool refresh_voices) {
+  if (!refresh_voices) {
+    uint32_t idx = 0;
+    t.has_clip_idx = find_next_clip(t, time_pos, &idx);
+    t.clip_idx = idx;
+    t.partially_ended = false;
+  }
+  t.refresh_voice = refresh_voices;
+}
+
+// ---- Engine -----------------------------------------------------------------------------------------------
+
+Engine::Engine(int device_ordinal) {
+  if (device_ordinal < 0) {  // scheduling-only engine: builds segment tables, cannot render (no CPU path)
+    host_only_ = true;
+    return;
+  }
+  int rc = wbx_create(&dev_, device_ordinal);
+  if (rc != WBX_OK) {
+    dev_ = nullptr;
+    err_ = "wbx_create failed (no sm_100 CUDA device? there is no CPU path), status " + std::to_string(rc);
+  }
+}
+
+Engine::~Engine() {
+  for (auto* t : tracks) delete t;
+  if (dev_) wbx_destroy(dev_);
+}
+
+const char* Engine::last_error() const { return dev_ ? wbx_last_error(dev_) : err_.c_str(); }
+
+int Engine::set_audio_channel_config(uint32_t, uint32_t output_channels, uint32_t buffer_size, uint32_t sample_rate) {
+  if (!dev_ && !host_only_) return WBX_ERR_NO_DEVICE;
+  if (output_channels < 1 || output_channels > 2 || buffer_size == 0 || buffer_size > 65535) return WBX_ERR_INVALID;
+  if (dev_) {
+    int rc = wbx_configure(dev_, output_channels, buffer_size, sample_rate);
+    if (rc) return rc;
+  }
+  out_channels_ = output_channels;
+  buffer_size_ = buffer_size;
+  sample_rate_ = sample_rate;
+  return WBX_OK;
+}
+
+void Engine::set_bpm(double bpm) { beat_duration_ = 60.0 / bpm; }
+
+void Engine::set_playhead_position(double beat) {
+  playhead_start = beat;
+  playhead = beat;
+}
+
+Track* Engine::add_track(const std::string& name) {
+  Track* t = new Track();
+  t->name = name;
+  // Track::Track() queues the defaults first (engine/track.cpp:22-27)
+  t->set_volume(0.0f);
+  t->set_pan(0.0f);
+  t->set_mute(false);
+  tracks.push_back(t);
+  return t;
+}
+
+int Engine::add_sample(int format, uint32_t channels, uint64_t frames, uint32_t sample_rate, const void* const* planar) {
+  if (!dev_ && !host_only_) return WBX_ERR_NO_DEVICE;
+  uint32_t id = (uint32_t)samples_.size();
+  if (dev_) {
+    int rc = wbx_sample_upload(dev_, format, channels, frames, sample_rate, planar, &id);
+    if (rc) return rc;
+  }
+  if (samples_.size() <= id) samples_.resize(id + 1);
+  samples_[id] = {frames, sample_rate};
+  return (int)id;
+}
+
+int Engine::add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
+                           double speed, float gain) {
+  if (!track || sample_id >= samples_.size() || !(max_time >= min_time)) return WBX_ERR_INVALID;
+  for (auto* c : track->clips)  // the reference would trim/split here (Engine::reserve_track_region): out of scope
+    if (min_time < c->max_time && max_time > c->min_time) return WBX_ERR_UNSUPPORTED;
+  AudioClip* clip = new AudioClip();
+  clip->min_time = min_time;
+  clip->max_time = max_time;
+  clip->start_offset = start_offset;
+  clip->speed = speed;
+  clip->gain = gain;
+  clip->sample_id = sample_id;
+  clip->sample_rate = samples_[sample_id].rate;
+  auto pos = std::upper_bound(track->clips.begin(), track->clips.end(), clip,
+                              [](const AudioClip* a, const AudioClip* b) { return a->min_time < b->min_time; });
+  track->clips.insert(pos, clip);
+  reset_playback_state(*track, playhead, true);  // add_to_cliplist, engine.cpp:415,425,...
+  return WBX_OK;
+}
+
+void Engine::play() {
+  for (auto* t : tracks) reset_playback_state(*t, playhead_start, false);
+  sample_position = 0;
+  playing = true;
+}
+
+void Engine::stop() {
+  playing = false;
+  playhead = playhead_start;
+  for (auto* t : tracks) {  // Track::stop, engine/track.cpp:248-256
+    t->current_audio_event = AudioEvent();
+    t->audio_event_buffer.clear();
+  }
+}
+
+// Track::process_event (engine/track.cpp:258-451), audio clips.
+void Engine::process_event(Track& t, double start_time, double end_time, double sample_position_,
+                           double beat_duration, double sample_rate, uint32_t buffer_size) {
+  auto push_stop = [&](uint32_t off, double time) {
+    AudioEvent e;
+    e.type = EventType::StopSample;
+    e.buffer_offset = off;
+    e.time = time;
+    t.audio_event_buffer.push_back(e);
+  };
+  auto push_play = [&](uint32_t off, double time, const AudioClip* clip, uint64_t sample_offset) {
+    AudioEvent e;
+    e.type = EventType::PlaySample;
+    e.buffer_offset = off;
+    e.time = time;
+    e.speed = clip->speed;
+    e.sample_offset = sample_offset;
+    e.clip = clip;
+    t.audio_event_buffer.push_back(e);
+  };
+
+  if (t.clips.empty()) {
+    if (t.refresh_voice) {
+      push_stop(0, start_time);
+      t.has_clip_idx = false;
+      t.refresh_voice = false;
+    }
+    return;
+  }
+  const uint32_t num_clips = (uint32_t)t.clips.size();
+  if (t.refresh_voice) {
+    uint32_t at = 0;
+    if (find_next_clip(t, start_time, &at)) {
+      if (t.has_clip_idx) {
+        const uint32_t idx = t.clip_idx;
+        if (idx < num_clips) {
+          const AudioClip* clip = t.clips[at];
+          const AudioClip* current_clip = t.clips[idx];
+          const bool inside = start_time >= clip->min_time && start_time <= clip->max_time;
+          if ((clip != current_clip && inside) || (clip == current_clip && !inside)) {
+            push_stop(0, start_time);
+            t.clip_idx = at;
+            t.partially_ended = false;
+          }
+        }
+      } else {
+        t.has_clip_idx = true;
+        t.clip_idx = at;
+      }
+    } else {
+      push_stop(0, start_time);
+      t.has_clip_idx = false;
+    }
+    t.refresh_voice = false;
+  }
+  if (!t.has_clip_idx) return;
+
+  uint32_t next_clip = t.clip_idx;
+  while (next_clip < num_clips) {
+    AudioClip* clip = t.clips[next_clip];
+    const double min_time = clip->min_time, max_time = clip->max_time;
+    if (min_time > end_time) break;
+
+    if (min_time >= start_time) {  // the clip starts inside this callback
+      const double offset_from_start = beat_to_samples(min_time - start_time, sample_rate, beat_duration);
+      const double sample_offset = sample_position_ + offset_from_start;
+      const uint32_t buffer_offset = (uint32_t)((uint64_t)sample_offset % (uint64_t)buffer_size);
+      push_play(buffer_offset, min_time, clip, (uint64_t)clip->start_offset);
+      clip->internal_state_changed = false;
+    } else if (start_time > min_time && !t.partially_ended) {  // playback starts in the middle of the clip
+      const double sample_pos = beat_to_samples(start_time - min_time, sample_rate, beat_duration);
+      const uint64_t sample_offset = (uint64_t)(clip->start_offset + (sample_pos * clip->speed));
+      push_play(0, start_time, clip, sample_offset);
+      clip->internal_state_changed = false;
+    } else if (clip->internal_state_changed && t.partially_ended) {  // clip edited while it plays
+      const double sample_pos = beat_to_samples(start_time - min_time, sample_rate, beat_duration);
+      const uint64_t sample_offset = (uint64_t)(clip->start_offset + (sample_pos * clip->speed));
+      push_stop(0, start_time);
+      push_play(0, start_time, clip, sample_offset);
+      clip->internal_state_changed = false;
+    }
+
+    if (max_time <= end_time) {  // the clip ends inside this callback
+      const double offset_from_start = beat_to_samples(max_time - start_time, sample_rate, beat_duration);
+      const double sample_offset = sample_position_ + offset_from_start;
+      const uint32_t buffer_offset = (uint32_t)((uint64_t)sample_offset % (uint64_t)buffer_size);
+      push_stop(buffer_offset, max_time);
+      t.partially_ended = false;
+    } else {
+      t.partially_ended = true;
+      break;
+    }
+    next_clip++;
+  }
+  t.clip_idx = next_clip;
+}
+
+// One dsp::Sampler::stream call (dsp/sampler.cpp:88-210) becomes one wbx_segment — or extends the track's
+// open run when it is the whole-block continuation of the previous callback's call. Host keeps only the
+// position bookkeeping (sampler.cpp:99-103,209); the device clips to the sample's end itself.
+void Engine::stream(Track& t, uint32_t track_index, uint32_t block, uint32_t num_samples, uint32_t buffer_offset) {
+  const AudioClip* clip = t.current_audio_event.clip;
+  const double count = (double)samples_[clip->sample_id].count;
+  if (t.sample_offset >= count) return;  // has finished streaming: position no longer advances
+  if (num_samples != 0) {
+    bool extended = false;
+    if (t.open_run >= 0 && buffer_offset == 0 && num_samples == buffer_size_) {
+      wbx_segment& r = segs_[t.open_run];
+      if (r.block + r.n_blocks == block && r.length == buffer_size_ && r.dst_offset == 0) {
+        r.n_blocks++;
+        extended = true;
+      }
+    }
+    if (!extended) {
+      wbx_segment s;
+      s.track = track_index;
+      s.block = block;
+      s.n_blocks = 1;
+      s.dst_offset = buffer_offset;
+      s.length = num_samples;
+      s.sample_id = clip->sample_id;
+      s.src_pos = t.sample_offset;
+      s.speed = t.playback_speed;
+      s.gain = clip->gain;
+      s.reserved = 0;
+      segs_.push_back(s);
+      // only a whole-block call can be continued by the next callback's whole-block call
+      t.open_run = (buffer_offset == 0 && num_samples == buffer_size_) ? (int32_t)segs_.size() - 1 : -1;
+    }
+  }
+  t.sample_offset = t.sample_offset + ((double)num_samples * t.playback_speed);
+}
+
+// Track::process (engine/track.cpp:587-736) minus the sample loops.
+void Engine::track_block(Track& t, uint32_t track_index, uint32_t block, double sample_rate, double beat_duration,
+                         double start_time, double end_time, bool currently_playing) {
+  t.audio_event_buffer.clear();  // engine.cpp:1591
+  if (currently_playing)
+    process_event(t, start_time, end_time, sample_position, beat_duration, sample_rate, buffer_size_);
+
+  for (const auto& m : t.track_msg_queue) {  // process_track_messages + parameter application, :618-643
+    switch (m.id) {
+      case kParamVolume: t.parameter_state.volume = (float)m.value; break;
+      case kParamPan: {
+        t.parameter_state.pan = (float)m.value;
+        const PanningCoefficient pc = calculate_panning_coefs(t.parameter_state.pan);
+        t.parameter_state.pan_coeffs[0] = pc.left;
+        t.parameter_state.pan_coeffs[1] = pc.right;
+        break;
+      }
+      case kParamMute: t.parameter_state.mute = m.value > 0.0; break;
+    }
+  }
+  t.track_msg_queue.clear();
+
+  if (!currently_playing) {
+    t.open_run = -1;
+    return;
+  }
+  // walk the callback's events, splitting the block at each buffer_offset (:664-724)
+  const uint32_t B = buffer_size_;
+  size_t next = 0;
+  uint32_t start_sample = 0;
+  if (!t.audio_event_buffer.empty()) t.open_run = -1;  // any event ends the run this track was extending
+  while (start_sample < B) {
+    if (next != t.audio_event_buffer.size()) {
+      const AudioEvent& ne = t.audio_event_buffer[next];
+      uint32_t event_length = ne.buffer_offset - start_sample;
+      if (ne.buffer_offset < start_sample || ne.buffer_offset > B) {
+        // Events out of offset order: undefined behaviour in the reference (event_length wraps, :670, and
+        // Sampler::stream writes past the buffer; happens when a clip ends exactly on the callback's end,
+        // :423-425). Defined here as: render nothing for this event and silence the voice.
+        event_length = 0;
+        if (t.current_audio_event.type == EventType::PlaySample) t.current_audio_event.type = EventType::None;
+      }
+      if (t.current_audio_event.type == EventType::PlaySample)
+        stream(t, track_index, block, event_length, start_sample);
+      if (ne.type == EventType::PlaySample) {  // Sampler::reset_state, dsp/sampler.h:18-27
+        t.playback_speed = ((double)ne.clip->sample_rate / sample_rate) * ne.speed;
+        t.sample_offset = (double)ne.sample_offset;
+      }
+      t.current_audio_event = ne;
+      start_sample += event_length;
+      next++;
+    } else {
+      const uint32_t event_length = B - start_sample;
+      if (t.current_audio_event.type == EventType::PlaySample)
+        stream(t, track_index, block, event_length, start_sample);
+      start_sample = B;
+    }
+  }
+}
+
+int Engine::schedule(uint32_t n_blocks, double sample_rate) {
+  if (sample_rate == 0.0) sample_rate = (double)sample_rate_;
+  segs_.clear();
+  const uint32_t N = (uint32_t)tracks.size();
+  for (auto* t : tracks) t->open_run = -1;
+  for (uint32_t k = 0; k < n_blocks; k++) {
+    // transport arithmetic of Engine::process, engine.cpp:1578-1585
+    const double buffer_duration = (double)buffer_size_ / sample_rate;
+    const double current_beat_duration = beat_duration_;
+    const double current_playhead_position = playhead;
+    const double buffer_duration_in_beats = buffer_duration / current_beat_duration;
+    const double next_playhead_pos = playhead + buffer_duration_in_beats;
+    const bool currently_playing = playing;
+    for (uint32_t i = 0; i < N; i++)
+      track_block(*tracks[i], i, k, sample_rate, current_beat_duration, current_playhead_position, next_playhead_pos,
+                  currently_playing);
+    if (currently_playing) {  // :1619-1623
+      sample_position += beat_to_samples(buffer_duration_in_beats, sample_rate, current_beat_duration);
+      playhead = next_playhead_pos;
+    }
+  }
+  // gain used this render = (mute ? 0 : volume) * pan_coeffs[ch]   (track.cpp:728-731)
+  gains_.resize((size_t)N * 2);
+  for (uint32_t i = 0; i < N; i++) {
+    const TrackParameterState& ps = tracks[i]->parameter_state;
+    const float volume = ps.mute ? 0.0f : ps.volume;
+    gains_[2 * i + 0] = volume * ps.pan_coeffs[0];
+    gains_[2 * i + 1] = volume * ps.pan_coeffs[1];
+  }
+  return WBX_OK;
+}
+
+int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, double sample_rate) {
+  if (!dev_) return WBX_ERR_NO_DEVICE;
+  if (n_blocks == 0) return WBX_ERR_INVALID;
+  const uint32_t N = (uint32_t)tracks.size();
+  int rc = wbx_set_track_count(dev_, N);
+  if (rc) return rc;
+  schedule(n_blocks, sample_rate);
+  float* pk = peaks;
+  if (!pk && N) {
+    peaks_.resize((size_t)n_blocks * N * 2);
+    pk = peaks_.data();
+  }
+  rc = wbx_render(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n_blocks, out_channels, pk);
+  if (rc) return rc;
+  // VUMeter::push_samples: level only rises until the UI reads it (vu_meter.h:25-29)
+  for (uint32_t k = 0; k < n_blocks; k++)
+    for (uint32_t i = 0; i < N; i++)
+      for (uint32_t c = 0; c < 2; c++) {
+        const float v = pk[((size_t)k * N + i) * 2 + c];
+        if (tracks[i]->level[c] < v) tracks[i]->level[c] = v;
+      }
+  return WBX_OK;
+}
+
+}  // namespace wbx
+
+// ---- C exports of the host engine (include/wbx_host.h), for ctypes / other FFI -----------------------------
+
+using wbx::Engine;
+
+extern "C" {
+
+struct wbxh_engine {
+  Engine eng;
+  explicit wbxh_engine(int dev) : eng(dev) {}
+};
+
+int wbxh_create(wbxh_engine** out, int device_ordinal, uint32_t out_channels, uint32_t block_frames,
+                uint32_t sample_rate, double bpm) {
+  if (!out) return WBX_ERR_INVALID;
+  *out = nullptr;
+  wbxh_engine* h = new wbxh_engine(device_ordinal);
+  if (!h->eng.ok() && device_ordinal >= 0) {
+    delete h;
+    return WBX_ERR_NO_DEVICE;
+  }
+  int rc = h->eng.set_audio_channel_config(0, out_channels, block_frames, sample_rate);
+  if (rc) {
+    delete h;
+    return rc;
+  }
+  h->eng.set_bpm(bpm);
+  *out = h;
+  return WBX_OK;
+}
+void wbxh_destroy(wbxh_engine* h) { delete h; }
+const char* wbxh_last_error(wbxh_engine* h) { return h ? h->eng.last_error() : "null"; }
+wbx_engine* wbxh_device(wbxh_engine* h) { return h ? h->eng.device() : nullptr; }
+
+int wbxh_add_track(wbxh_engine* h, float volume_db, float pan, int mute) {
+  wbx::Track* t = h->eng.add_track("t" + std::to_string(h->eng.tracks.size()));
+  t->set_volume(volume_db);
+  t->set_pan(pan);
+  t->set_mute(mute != 0);
+  return (int)h->eng.tracks.size() - 1;
+}
+void wbxh_set_volume(wbxh_engine* h, int track, float db) { h->eng.tracks[track]->set_volume(db); }
+void wbxh_set_pan(wbxh_engine* h, int track, float pan) { h->eng.tracks[track]->set_pan(pan); }
+void wbxh_set_mute(wbxh_engine* h, int track, int mute) { h->eng.tracks[track]->set_mute(mute != 0); }
+int wbxh_add_sample(wbxh_engine* h, int format, uint32_t channels, uint64_t frames, uint32_t sample_rate,
+                    const void* const* planar) {
+  return h->eng.add_sample(format, channels, frames, sample_rate, planar);
+}
+int wbxh_add_clip(wbxh_engine* h, int track, int sample, double min_beat, double max_beat, double start_offset,
+                  double speed, float gain) {
+  if (track < 0 || (size_t)track >= h->eng.tracks.size() || sample < 0) return WBX_ERR_INVALID;
+  return h->eng.add_audio_clip(h->eng.tracks[track], min_beat, max_beat, start_offset, (uint32_t)sample, speed, gain);
+}
+void wbxh_set_playhead(wbxh_engine* h, double beat) { h->eng.set_playhead_position(beat); }
+void wbxh_play(wbxh_engine* h) { h->eng.play(); }
+void wbxh_stop(wbxh_engine* h) { h->eng.stop(); }
+void wbxh_set_fast_forward(wbxh_engine* h, int on) { h->eng.fast_forward = on != 0; }
+
+int wbxh_render(wbxh_engine* h, uint32_t n_blocks, float* const* out_channels, float* peaks) {
+  return h->eng.render(n_blocks, out_channels, peaks);
+}
+
+// Scheduling only (no device work): fills the engine's segment table for n_blocks callbacks.
+int wbxh_schedule(wbxh_engine* h, uint32_t n_blocks, const wbx_segment** segs, uint32_t* n_segs, const float** gains) {
+  int rc = h->eng.schedule(n_blocks);
+  if (segs) *segs = h->eng.segments().data();
+  if (n_segs) *n_segs = (uint32_t)h->eng.segments().size();
+  if (gains) *gains = h->eng.track_gains().data();
+  return rc;
+}
+
+double wbxh_sampler_offset(wbxh_engine* h, int track) { return h->eng.tracks[track]->sample_offset; }
+double wbxh_sample_position(wbxh_engine* h) { return h->eng.sample_position; }
+double wbxh_playhead(wbxh_engine* h) { return h->eng.playhead; }
+float wbxh_level(wbxh_engine* h, int track, int channel, int reset) {
+  float v = h->eng.tracks[track]->level[channel];
+  if (reset) h->eng.tracks[track]->level[channel] = 0.0f;
+  return v;
+}
+void wbxh_panning_coefs(float pan, float* left, float* right) {
+  wbx::PanningCoefficient c = wbx::calculate_panning_coefs(pan);
+  *left = c.left;
+  *right = c.right;
+}
+float wbxh_db_to_linear(float db) { return wbx::db_to_linear(db); }
+
+}  // extern "C"

@@ -1,0 +1,698 @@
+// wbx_kernels.cu — sm_100a kernels of the whitebox mixing hot path.
+//
+//   expand_schedule   one thread per wbx_segment: replays the f64 recurrence of Sampler::sample_offset_
+//                     (dsp/sampler.cpp:99-104,209) and writes one 16-B DCell per callback of the run.
+//   mix_kernel<FPL>   the fused render: Sampler::stream (unity + 2-tap linear, all source formats,
+//                     dsp/sampler.cpp:34-59,106-158) -> clip gain -> volume*pan (dsp/dsp_ops.h:27-31) -> VU
+//                     block peak (engine/vu_meter.h:20-30) -> bus sum (core/audio_buffer.h:73-82) -> clamp
+//                     (engine/engine.cpp:1627-1636). Persistent warps pull (block, frame-tile, track-group)
+//                     items from an atomic queue; each warp owns a private shared-memory ring that it fills
+//                     itself with cp.async.bulk (TMA 1-D bulk copies, SASS UBLKCP) completing on mbarriers,
+//                     so the only global loads in the loop are the 16-B cells / L2-resident span records.
+//                     A warp owns every output sample of its tile and adds tracks in index order, so with
+//                     one track group the f32 sum is bit-identical to the reference's sequential mix.
+//   clamp_kernel      engine.cpp:1627-1636 alone, for the bus after a cross-GPU reduce.
+//   interleave_kernel core/audio_format_conv.cpp:5-106, planar f32 bus -> interleaved device format.
+//
+// Built with -fmad=false: every f32/f64 multiply and add is separately rounded like the reference's ISO C++
+// x86-64 build (no FMA contraction); the arithmetic that decides parity also uses explicit _rn intrinsics.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "wbx_device.cuh"
+
+namespace wbx {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA) into shared memory
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// global -> shared bulk copy, 16-B aligned addresses, size a multiple of 16; completes `bytes` on `bar`.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// schedule expansion
+// ---------------------------------------------------------------------------------------------------------
+__global__ void expand_schedule(const DSpan* __restrict__ spans, uint32_t n_spans, DCell* __restrict__ cells,
+                                uint32_t n_tracks, uint32_t slots) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_spans) return;
+  const DSpan s = spans[i];
+  double pos = s.pos0;
+  const double cnt = (double)s.count;
+  const double adv = __dmul_rn((double)s.length, s.speed);           // (double)num_samples * playback_speed_
+  const double safe = __dmul_rn((double)s.length + 1.0, s.speed);    // rem >= safe  =>  ceil(rem/speed) >= length
+  for (uint32_t b = 0; b < s.n_blocks; b++) {
+    if (pos >= cnt) break;  // finished streaming; sample_offset_ no longer advances (sampler.cpp:99-100)
+    uint32_t n_act = s.length;
+    const double rem = __dsub_rn(cnt, pos);
+    if (rem < safe) {
+      // num_actual_samples = min(num_samples, (uint32_t)ceil((count - offset) / speed))   (sampler.cpp:102-104)
+      const double m = ceil(__ddiv_rn(rem, s.speed));
+      const uint32_t mm = m >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)m;
+      n_act = mm < n_act ? mm : n_act;
+    }
+    DCell c;
+    c.pos = pos;
+    c.span = i;
+    c.n_act = n_act;
+    cells[((size_t)(s.block0 + b) * n_tracks + s.track) * slots + s.slot] = c;
+    pos = __dadd_rn(pos, adv);  // next_sample_offset (sampler.cpp:103,209)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// element access with the reference's normalisation rules
+// ---------------------------------------------------------------------------------------------------------
+enum : uint32_t { F_I16 = 3, F_I24 = 5, F_I32 = 7, F_F32 = 9 };
+
+__device__ __forceinline__ float clampf_ref(float x, float lo, float hi) {  // math::clamp, core_math.h:34-38
+  float m = x < hi ? x : hi;
+  return m > lo ? m : lo;
+}
+__device__ __forceinline__ double clampd_ref(double x, double lo, double hi) {
+  double m = x < hi ? x : hi;
+  return m > lo ? m : lo;
+}
+
+// unity-speed branch: normalise + clamp to [-1, 1] (sampler.cpp:109-156)
+template <uint32_t FMT>
+__device__ __forceinline__ float load_unity(const void* row, int64_t idx) {
+  if (FMT == F_F32) {
+    return ((const float*)row)[idx];
+  } else if (FMT == F_I16) {
+    const float norm = 1.0f / 32767.0f;  // i16_pcm_normalizer, sampler.cpp:95
+    float v = __fmul_rn((float)((const int16_t*)row)[idx], norm);
+    return clampf_ref(v, -1.0f, 1.0f);
+  } else if (FMT == F_I24) {
+    const double norm = 1.0 / 8388607.0;  // sampler.cpp:96
+    double v = __dmul_rn((double)((const int32_t*)row)[idx], norm);
+    return (float)clampd_ref(v, -1.0, 1.0);
+  } else {
+    const double norm = 1.0 / 2147483647.0;  // sampler.cpp:97
+    double v = __dmul_rn((double)((const int32_t*)row)[idx], norm);
+    return (float)clampd_ref(v, -1.0, 1.0);
+  }
+}
+
+// linear branch: normalise, no clamp (sample_linear, sampler.cpp:53-54; get_pcm_sample_normalizer :7-18)
+template <uint32_t FMT>
+__device__ __forceinline__ float load_lin(const void* row, int64_t idx) {
+  if (FMT == F_F32) {
+    return ((const float*)row)[idx];
+  } else if (FMT == F_I16) {
+    const float norm = (float)(1.0 / 32767.0);
+    return __fmul_rn(norm, (float)((const int16_t*)row)[idx]);
+  } else if (FMT == F_I24) {
+    const double norm = 1.0 / 8388607.0;
+    return (float)__dmul_rn(norm, (double)((const int32_t*)row)[idx]);
+  } else {
+    const double norm = 1.0 / 2147483647.0;
+    return (float)__dmul_rn(norm, (double)((const int32_t*)row)[idx]);
+  }
+}
+
+// term = (sample * clip_gain) * track_gain, bus += term, peak = max(peak, |term|)
+__device__ __forceinline__ void accumulate(float s, float gain, float tg, float& acc, float& pk) {
+  const float term = __fmul_rn(__fmul_rn(s, gain), tg);  // sampler.cpp:154 then dsp_ops.h:29
+  acc = __fadd_rn(acc, term);                            // audio_buffer.h:79
+  pk = fmaxf(pk, fabsf(term));                           // vu_meter.h:24
+}
+
+// Generic per-frame path: any format, unity or linear, staged window (shared) or direct (global) rows.
+template <int FPL, uint32_t FMT, bool UNITY>
+__device__ __forceinline__ void consume_gen_t(const Desc& d, const void* rowL, const void* rowR,
+                                              float (&acc)[2][FPL], float& pkL, float& pkR, int lane, bool two) {
+  const int64_t ip = (int64_t)(uint32_t)(int64_t)d.pos;  // (uint32_t)sample_offset_, sampler.cpp:107
+#pragma unroll
+  for (int i = 0; i < FPL / 4; i++) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int fr = 4 * (lane + 32 * i) + e;
+      if (fr >= (int)d.lo && fr < (int)d.hi) {
+        const int32_t jj = fr + d.jrel0;
+        float sL, sR = 0.0f;
+        if (UNITY) {
+          const int64_t idx = ip + jj - d.base;
+          sL = load_unity<FMT>(rowL, idx);
+          if (two) sR = load_unity<FMT>(rowR, idx);
+        } else {
+          const double x = __dadd_rn(d.pos, __dmul_rn((double)jj, d.speed));  // sampler.cpp:50
+          const int64_t ix = __double2ll_rz(x);                                // :51
+          const float fx = __double2float_rn(__dsub_rn(x, __ll2double_rn(ix)));  // :52
+          const int64_t idx = ix - d.base;
+          const float a = load_lin<FMT>(rowL, idx), b = load_lin<FMT>(rowL, idx + 1);
+          sL = __fadd_rn(a, __fmul_rn(fx, __fsub_rn(b, a)));  // :55
+          if (two) {
+            const float a2 = load_lin<FMT>(rowR, idx), b2 = load_lin<FMT>(rowR, idx + 1);
+            sR = __fadd_rn(a2, __fmul_rn(fx, __fsub_rn(b2, a2)));
+          }
+        }
+        accumulate(sL, d.gain, d.tg[0], acc[0][i * 4 + e], pkL);
+        if (two) accumulate(sR, d.gain, d.tg[1], acc[1][i * 4 + e], pkR);
+      }
+    }
+  }
+}
+
+template <int FPL>
+__device__ __forceinline__ void consume_gen(const Desc& d, const void* rowL, const void* rowR, float (&acc)[2][FPL],
+                                         float& pkL, float& pkR, int lane, bool two) {
+  const uint32_t fmt = d.fmt & 0x7fu;
+  if (d.speed == 1.0) {  // playback_speed_ == 1.0, sampler.cpp:106
+    switch (fmt) {
+      case F_I16: consume_gen_t<FPL, F_I16, true>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+      case F_I24: consume_gen_t<FPL, F_I24, true>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+      case F_I32: consume_gen_t<FPL, F_I32, true>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+      default: consume_gen_t<FPL, F_F32, true>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+    }
+  } else {
+    switch (fmt) {
+      case F_I16: consume_gen_t<FPL, F_I16, false>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+      case F_I24: consume_gen_t<FPL, F_I24, false>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+      case F_I32: consume_gen_t<FPL, F_I32, false>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+      default: consume_gen_t<FPL, F_F32, false>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+    }
+  }
+}
+
+// Fast path: f32, unity speed, window 16-B aligned: 128-bit shared loads.
+template <int FPL>
+__device__ __forceinline__ void consume_vec(const Desc& d, const uint8_t* rowL, const uint8_t* rowR,
+                                            float (&acc)[2][FPL], float& pkL, float& pkR, int lane, bool two) {
+  const float4* rL = reinterpret_cast<const float4*>(rowL);
+  const float4* rR = reinterpret_cast<const float4*>(rowR);
+  const int lo = d.lo, hi = d.hi;
+  const float g = d.gain, tl = d.tg[0], tr = d.tg[1];
+#pragma unroll
+  for (int i = 0; i < FPL / 4; i++) {
+    const int fr = 4 * (lane + 32 * i);
+    if (fr >= lo && fr < hi) {
+      const int q = (fr - lo) >> 2;
+      const float4 vl = rL[q];
+      accumulate(vl.x, g, tl, acc[0][i * 4 + 0], pkL);
+      accumulate(vl.y, g, tl, acc[0][i * 4 + 1], pkL);
+      accumulate(vl.z, g, tl, acc[0][i * 4 + 2], pkL);
+      accumulate(vl.w, g, tl, acc[0][i * 4 + 3], pkL);
+      if (two) {
+        const float4 vr = rR[q];
+        accumulate(vr.x, g, tr, acc[1][i * 4 + 0], pkR);
+        accumulate(vr.y, g, tr, acc[1][i * 4 + 1], pkR);
+        accumulate(vr.z, g, tr, acc[1][i * 4 + 2], pkR);
+        accumulate(vr.w, g, tr, acc[1][i * 4 + 3], pkR);
+      }
+    }
+  }
+}
+
+// f32 unity, window not 16-B aligned relative to the output frames: scalar shared loads, conflict-free.
+template <int FPL>
+__device__ __forceinline__ void consume_uni(const Desc& d, const uint8_t* rowL, const uint8_t* rowR,
+                                            float (&acc)[2][FPL], float& pkL, float& pkR, int lane, bool two) {
+  const float* rL = reinterpret_cast<const float*>(rowL);
+  const float* rR = reinterpret_cast<const float*>(rowR);
+  const int lo = d.lo, hi = d.hi;
+  const int shift = (int)((int64_t)(uint32_t)(int64_t)d.pos + d.jrel0 - d.base);
+  const float g = d.gain, tl = d.tg[0], tr = d.tg[1];
+#pragma unroll
+  for (int i = 0; i < FPL / 4; i++) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int fr = 4 * (lane + 32 * i) + e;
+      if (fr >= lo && fr < hi) {
+        accumulate(rL[fr + shift], g, tl, acc[0][i * 4 + e], pkL);
+        if (two) accumulate(rR[fr + shift], g, tr, acc[1][i * 4 + e], pkR);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the mix kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int FPL, int STAGES>
+struct MixLayout {
+  static constexpr int T = 32 * FPL;                  // frames per tile
+  static constexpr int ROW_BYTES = (T + 32) * 4;      // staged window per channel (aligned superset + taps)
+  static constexpr int STAGE_BYTES = 2 * ROW_BYTES;
+  static constexpr int RING = 64;                     // descriptor ring entries (two batches of 32 cells)
+  static constexpr int OFF_DESC = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_DESC + RING * (int)sizeof(Desc);
+  static constexpr int WARP_BYTES = ((OFF_BAR + STAGES * 8) + 127) & ~127;
+};
+
+__device__ __forceinline__ DCell load_cell(const DCell* cells, uint32_t ci, uint32_t n_cells) {
+  DCell c;
+  c.pos = 0.0;
+  c.span = kSilent;
+  c.n_act = 0;
+  if (ci < n_cells) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(cells + ci));
+    c.pos = __hiloint2double(v.y, v.x);
+    c.span = (uint32_t)v.z;
+    c.n_act = (uint32_t)v.w;
+  }
+  return c;
+}
+
+__device__ __forceinline__ DSpan load_span(const DSpan* spans, const DCell& c) {
+  DSpan s;
+  if (c.span != kSilent) {
+    const int4* p = reinterpret_cast<const int4*>(spans + c.span);
+    int4* q = reinterpret_cast<int4*>(&s);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(DSpan) / 16); i++) q[i] = __ldg(p + i);
+  } else {
+    int4* q = reinterpret_cast<int4*>(&s);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(DSpan) / 16); i++) q[i] = make_int4(0, 0, 0, 0);
+  }
+  return s;
+}
+
+// Turn (cell, span) into the per-tile descriptor: which frames, which source window, which code path.
+template <int ROW_BYTES>
+__device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, const float* __restrict__ gains,
+                                              int f0, int tile_len, Desc* out) {
+  Desc d;
+  d.src[0] = nullptr;
+  d.src[1] = nullptr;
+  d.pos = c.pos;
+  d.speed = s.speed;
+  d.gain = s.gain;
+  d.tg[0] = 0.f;
+  d.tg[1] = 0.f;
+  d.track = s.track;
+  d.base = 0;
+  d.jrel0 = 0;
+  d.lo = 0;
+  d.hi = 0;
+  d.bytes = 0;
+  d.kind = K_SILENT;
+  d.fmt = (uint8_t)(s.fmt | (s.mono ? 0x80u : 0u));
+  if (c.span != kSilent) {
+    const int seg_lo = (int)s.dst_off, seg_hi = (int)(s.dst_off + c.n_act);
+    const int lo = (seg_lo > f0 ? seg_lo : f0) - f0;
+    const int hi = (seg_hi < f0 + tile_len ? seg_hi : f0 + tile_len) - f0;
+    if (hi > lo) {
+      d.tg[0] = __ldg(gains + 2 * s.track);
+      d.tg[1] = __ldg(gains + 2 * s.track + 1);
+      d.jrel0 = f0 - seg_lo;
+      d.lo = (uint16_t)lo;
+      d.hi = (uint16_t)hi;
+      const int esize = (s.fmt == F_I16) ? 2 : 4;
+      const int64_t jj_lo = lo + d.jrel0, jj_hi = hi - 1 + d.jrel0;
+      const bool unity = (s.speed == 1.0);
+      int64_t first, last;
+      if (unity) {
+        const int64_t ip = (int64_t)(uint32_t)(int64_t)c.pos;
+        first = ip + jj_lo;
+        last = ip + jj_hi;
+      } else {  // conservative superset of [floor(x_lo), floor(x_hi) + 1]
+        first = (int64_t)(c.pos + (double)jj_lo * s.speed) - 1;
+        last = (int64_t)(c.pos + (double)jj_hi * s.speed) + 2;
+      }
+      if (first < 0) first = 0;
+      const int64_t align = 16 / esize;
+      const int64_t a = first & ~(align - 1);
+      const int64_t end = (last + align) & ~(align - 1);
+      const int64_t bytes = (end - a) * esize;
+      if (bytes <= ROW_BYTES) {
+        d.src[0] = (const uint8_t*)s.ch[0] + a * esize;
+        d.src[1] = (const uint8_t*)s.ch[1] + a * esize;
+        d.base = (int32_t)a;
+        d.bytes = (uint16_t)bytes;
+        if (unity && s.fmt == F_F32) {
+          const bool vec = ((lo & 3) == 0) && ((hi & 3) == 0) && (first == a);
+          d.kind = vec ? K_VEC : K_UNI;
+        } else {
+          d.kind = K_GEN;
+        }
+      } else {  // window larger than a stage (speed well above 1): read the source straight from global
+        d.src[0] = s.ch[0];
+        d.src[1] = s.ch[1];
+        d.kind = K_DIRECT;
+      }
+    }
+  }
+  const int4* q = reinterpret_cast<const int4*>(&d);
+  int4* o = reinterpret_cast<int4*>(out);
+  o[0] = q[0];
+  o[1] = q[1];
+  o[2] = q[2];
+  o[3] = q[3];
+}
+
+template <int FPL, int STAGES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
+  using L = MixLayout<FPL, STAGES>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* wbase = smem + (size_t)warp * L::WARP_BYTES;
+  Desc* ring = reinterpret_cast<Desc*>(wbase + L::OFF_DESC);
+  const uint32_t rows_s = smem_u32(wbase);
+  const uint32_t bars_s = smem_u32(wbase + L::OFF_BAR);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) mbar_init(bars_s + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  const bool two = (p.C == 2);
+  const uint32_t N = p.n_tracks, S = p.slots;
+  uint32_t n_issued = 0, n_consumed = 0;  // staged items, monotonic over the kernel: stage = n % STAGES
+
+  for (;;) {
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(&p.counters[0], 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= p.n_items) break;
+    const uint32_t g = w % p.groups;
+    const uint32_t f = (w / p.groups) % p.n_tiles;
+    const uint32_t k = w / (p.groups * p.n_tiles);
+    const uint32_t tb = g * p.tracks_per_group;
+    const uint32_t te = (tb + p.tracks_per_group < N) ? tb + p.tracks_per_group : N;
+    const uint32_t n_cells = (te - tb) * S;
+    const DCell* cells = p.cells + ((size_t)k * N + tb) * S;
+    const int f0 = (int)(f * L::T);
+    const int tile_len = ((int)p.B - f0 < L::T) ? (int)p.B - f0 : L::T;
+
+    float acc[2][FPL];
+#pragma unroll
+    for (int i = 0; i < FPL; i++) {
+      acc[0][i] = 0.0f;
+      acc[1][i] = 0.0f;
+    }
+    float pkL = 0.0f, pkR = 0.0f;
+    bool active = false;
+    uint32_t cur_track = 0;
+
+    // descriptors of the first batch
+    {
+      const DCell c0 = load_cell(cells, lane, n_cells);
+      const DSpan s0 = load_span(p.spans, c0);
+      resolve_store<L::ROW_BYTES>(c0, s0, p.gains, f0, tile_len, &ring[lane]);
+      __syncwarp();
+    }
+    uint32_t limit = 32;  // cells [0, limit) have descriptors
+    uint32_t ip = 0;      // next cell to consider for staging
+    const uint32_t nb = (n_cells + 31) >> 5;
+    DCell cN;
+    DSpan sN;
+
+    for (uint32_t b = 0; b < nb; b++) {
+      const bool more = (b + 1 < nb);
+      if (more) cN = load_cell(cells, (b + 1) * 32 + lane, n_cells);
+      for (int i = 0; i < 32; i++) {
+        const uint32_t ci = b * 32 + i;
+        if (ci >= n_cells) break;
+        if (more && i == 8) sN = load_span(p.spans, cN);
+        if (more && i == 16) {
+          resolve_store<L::ROW_BYTES>(cN, sN, p.gains, f0, tile_len, &ring[((b + 1) & 1) * 32 + lane]);
+          __syncwarp();
+          limit += 32;
+        }
+        // ---- producer role: keep up to STAGES windows in flight -------------------------------------
+        {
+          const uint32_t lim = limit < n_cells ? limit : n_cells;
+          while (ip < lim && (n_issued - n_consumed) < (uint32_t)STAGES) {
+            const Desc* dd = &ring[ip & (L::RING - 1)];
+            const uint32_t kind = dd->kind;
+            if (kind == K_VEC || kind == K_UNI || kind == K_GEN) {
+              if (lane == 0) {
+                const uint32_t st = n_issued % STAGES;
+                const uint32_t bar = bars_s + 8 * st;
+                const uint32_t dst = rows_s + st * L::STAGE_BYTES;
+                const uint32_t bytes = dd->bytes;
+                const bool mono = (dd->fmt & 0x80u) != 0 || !two;
+                mbar_expect_tx(bar, mono ? bytes : 2 * bytes);
+                bulk_g2s(dst, dd->src[0], bytes, bar);
+                if (!mono) bulk_g2s(dst + L::ROW_BYTES, dd->src[1], bytes, bar);
+              }
+              n_issued++;
+            }
+            ip++;
+          }
+        }
+        // ---- consumer role ------------------------------------------------------------------------------
+        const Desc d = ring[ci & (L::RING - 1)];
+        if (d.kind != K_SILENT) {
+          active = true;
+          cur_track = d.track;
+          const bool staged = (d.kind != K_DIRECT);
+          const void* rowL = d.src[0];
+          const void* rowR = d.src[1];
+          if (staged) {
+            const uint32_t st = n_consumed % STAGES;
+            const uint32_t par = (n_consumed / STAGES) & 1u;
+            while (!mbar_try_wait(bars_s + 8 * st, par)) {
+            }
+            rowL = wbase + (size_t)st * L::STAGE_BYTES;
+            rowR = (d.fmt & 0x80u) ? rowL : (const void*)((const uint8_t*)rowL + L::ROW_BYTES);
+          }
+          if (d.kind == K_VEC)
+            consume_vec<FPL>(d, (const uint8_t*)rowL, (const uint8_t*)rowR, acc, pkL, pkR, lane, two);
+          else if (d.kind == K_UNI)
+            consume_uni<FPL>(d, (const uint8_t*)rowL, (const uint8_t*)rowR, acc, pkL, pkR, lane, two);
+          else
+            consume_gen<FPL>(d, rowL, rowR, acc, pkL, pkR, lane, two);
+          if (staged) {
+            __syncwarp();  // every lane is done reading the stage before lane 0 may refill it
+            n_consumed++;
+          }
+        }
+        // ---- VU block peak once the track's last slot is done (vu_meter.h:20-30) ----------------------
+        if (active && ((ci + 1) % S) == 0) {
+          // lanes 0-15 reduce L, lanes 16-31 reduce R: one exchange, then four butterfly steps
+          const float send = (lane < 16) ? pkR : pkL;
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+          float m = fmaxf((lane < 16) ? pkL : pkR, recv);
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          if ((lane == 0 || (lane == 16 && two)) && p.peaks) {
+            float* dst = p.peaks + ((size_t)k * N + cur_track) * 2 + (lane >> 4);
+            if (p.n_tiles == 1)
+              *dst = m;
+            else if (m > 0.0f)
+              atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(m));  // m >= 0: uint order == float order
+          }
+          pkL = 0.0f;
+          pkR = 0.0f;
+          active = false;
+        }
+      }
+    }
+
+    // ---- bus write ------------------------------------------------------------------------------------
+    const size_t chan_stride = (size_t)p.n_blocks * p.B;
+    const size_t out_off = (size_t)k * p.B + f0;
+    const bool vec_ok = (p.B & 3u) == 0;
+    if (p.groups == 1) {
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        if (c == 1 && !two) break;
+        float* out = p.bus + c * chan_stride + out_off;
+#pragma unroll
+        for (int i = 0; i < FPL / 4; i++) {
+          const int fr = 4 * (lane + 32 * i);
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            float x = acc[c][i * 4 + e];
+            if (p.clamp) x = x > 1.0f ? 1.0f : (x < -1.0f ? -1.0f : x);  // engine.cpp:1627-1636 (NaN passes)
+            v[e] = x;
+          }
+          if (vec_ok && fr + 3 < tile_len) {
+            *reinterpret_cast<float4*>(out + fr) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              if (fr + e < tile_len) out[fr + e] = v[e];
+          }
+        }
+      }
+    } else {
+      // tree mode: publish this group's partial, the last group to arrive adds them in group order
+      const uint32_t tile_id = k * p.n_tiles + f;
+      float* part = p.ws + ((size_t)tile_id * p.groups + g) * 2 * L::T;
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+#pragma unroll
+        for (int i = 0; i < FPL / 4; i++) {
+          const int fr = 4 * (lane + 32 * i);
+          *reinterpret_cast<float4*>(part + c * L::T + fr) =
+              make_float4(acc[c][i * 4 + 0], acc[c][i * 4 + 1], acc[c][i * 4 + 2], acc[c][i * 4 + 3]);
+        }
+      }
+      __threadfence();
+      __syncwarp();
+      uint32_t prev = 0;
+      if (lane == 0) prev = atomicAdd(&p.counters[1 + tile_id], 1u);
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (prev == p.groups - 1) {
+        __threadfence();
+        const float* base = p.ws + (size_t)tile_id * p.groups * 2 * L::T;
+        for (int c = 0; c < (two ? 2 : 1); c++) {
+          float* out = p.bus + c * chan_stride + out_off;
+          for (int i = 0; i < FPL / 4; i++) {
+            const int fr = 4 * (lane + 32 * i);
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint32_t gg = 0; gg < p.groups; gg++) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(base + ((size_t)gg * 2 + c) * L::T + fr));
+              sum.x = __fadd_rn(sum.x, v.x);
+              sum.y = __fadd_rn(sum.y, v.y);
+              sum.z = __fadd_rn(sum.z, v.z);
+              sum.w = __fadd_rn(sum.w, v.w);
+            }
+            float v[4] = {sum.x, sum.y, sum.z, sum.w};
+            for (int e = 0; e < 4; e++) {
+              float x = v[e];
+              if (p.clamp) x = x > 1.0f ? 1.0f : (x < -1.0f ? -1.0f : x);
+              if (fr + e < tile_len) out[fr + e] = x;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------------
+__global__ void clamp_kernel(float* __restrict__ x, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (v > 1.0f)
+      x[i] = 1.0f;
+    else if (v < -1.0f)
+      x[i] = -1.0f;
+  }
+}
+
+// core/audio_format_conv.cpp:5-106. One thread per (frame, channel).
+__global__ void interleave_kernel(const float* __restrict__ bus, uint64_t frames, uint32_t channels, int fmt,
+                                  void* __restrict__ dst) {
+  const uint64_t n = frames * channels;
+  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = o / channels;
+    const uint32_t c = (uint32_t)(o % channels);
+    const float v = bus[(uint64_t)c * frames + i];
+    switch (fmt) {
+      case 3:  // I16 (:5-20): positive * 32767, else * 32768, truncating cast
+        ((int16_t*)dst)[o] = (int16_t)__float2int_rz(v > 0.0f ? __fmul_rn(v, 32767.0f) : __fmul_rn(v, 32768.0f));
+        break;
+      case 5: {  // I24 packed (:22-43). The reference writes every channel at dst[3*i .. 3*i+2] (no channel
+                 // stride), so the last channel wins; reproduced as written: only the last channel stores.
+        if (c == channels - 1) {
+          const int32_t q = __float2int_rz(v > 0.0f ? __fmul_rn(v, 8388607.0f) : __fmul_rn(v, 8388608.0f));
+          uint8_t* p = (uint8_t*)dst + i * 3;
+          p[0] = (uint8_t)q;
+          p[1] = (uint8_t)(q >> 8);
+          p[2] = (uint8_t)(q >> 16);
+        }
+        break;
+      }
+      case 6: {  // I24_X8 (:45-59)
+        const int32_t q = __float2int_rz(v > 0.0f ? __fmul_rn(v, 8388607.0f) : __fmul_rn(v, 8388608.0f));
+        ((int32_t*)dst)[o] = q & 0xFFFFFF;
+        break;
+      }
+      case 7:  // I32 (:61-74), in double
+        ((int32_t*)dst)[o] =
+            __double2int_rz(v > 0.0f ? __dmul_rn((double)v, 2147483647.0) : __dmul_rn((double)v, 2147483648.0));
+        break;
+      default: ((float*)dst)[o] = v; break;  // F32 (:76-88)
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-callable launchers (used by wbx_api.cu)
+// ---------------------------------------------------------------------------------------------------------
+struct MixVariant {
+  int fpl, stages, warps;
+};
+
+template <int FPL, int STAGES, int WARPS>
+static cudaError_t launch_mix_t(const MixParams& p, int n_sm, cudaStream_t stream, int* ctas_out) {
+  using L = MixLayout<FPL, STAGES>;
+  auto kfn = mix_kernel<FPL, STAGES, WARPS>;
+  const int smem = L::WARP_BYTES * WARPS;
+  cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  int per_sm = 0;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, WARPS * 32, smem);
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) per_sm = 1;
+  long ctas = (long)n_sm * per_sm;
+  const long need = ((long)p.n_items + WARPS - 1) / WARPS;
+  if (ctas > need) ctas = need;
+  if (ctas < 1) ctas = 1;
+  if (ctas_out) *ctas_out = (int)ctas;
+  kfn<<<(unsigned)ctas, WARPS * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mix(const MixParams& p, int fpl, int n_sm, cudaStream_t stream, int* ctas_out) {
+  switch (fpl) {
+    case 16: return launch_mix_t<16, 4, 5>(p, n_sm, stream, ctas_out);
+    case 8: return launch_mix_t<8, 4, 8>(p, n_sm, stream, ctas_out);
+    default: return launch_mix_t<4, 6, 8>(p, n_sm, stream, ctas_out);
+  }
+}
+
+cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, uint32_t n_tracks, uint32_t slots,
+                          cudaStream_t stream) {
+  if (n_spans == 0) return cudaSuccess;
+  expand_schedule<<<(n_spans + 127) / 128, 128, 0, stream>>>(spans, n_spans, cells, n_tracks, slots);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_clamp(float* x, uint64_t n, int n_sm, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > (uint64_t)n_sm * 8) blocks = (uint64_t)n_sm * 8;
+  clamp_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_interleave(const float* bus, uint64_t frames, uint32_t channels, int fmt, void* dst, int n_sm,
+                              cudaStream_t stream) {
+  const uint64_t n = frames * channels;
+  if (n == 0) return cudaSuccess;
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > (uint64_t)n_sm * 8) blocks = (uint64_t)n_sm * 8;
+  interleave_kernel<<<(unsigned)blocks, 256, 0, stream>>>(bus, frames, channels, fmt, dst);
+  return cudaGetLastError();
+}
+
+}  // namespace wbx
