@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — the mixing hot path on B200 (BASELINE.json metric: mixed stereo samples/sec at N tracks; achieved
+HBM GB/s vs roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--blocks B] [--tracks T]
+
+A "step" renders `--blocks` consecutive Engine::process callbacks (512 frames each) of `--tracks` stereo 48 kHz
+f32 tracks per GPU (BASELINE cfg 2: gain/pan + bus sum; fade = 0, the reference has none) in one device launch.
+  value    whole-job stereo track-frames mixed per second, sources + schedule resident in HBM, timed with CUDA
+           events on the launching stream (max over ranks).
+  e2e      the same metric through the host engine API (wbx::Engine::render via the C ABI) with HOST buffers:
+           host clip scheduling, H2D of the segment table + gains, schedule expansion, mix, D2H of the clamped
+           bus and the per-callback VU peaks all inside the timed region. Source samples are resident engine
+           state (uploaded at load time, like wb::Sample objects in the reference); `e2e_cold` additionally
+           counts uploading every source sample from host memory each step.
+  roofline achieved = algorithmic bytes (8 B per stereo track-frame + cells) / mean mix-kernel duration.
+N > 1 (torchrun): tracks shard across ranks (weak scaling: --tracks per GPU), each rank mixes its shard
+unclamped, ONE NCCL all-reduce sums the partial buses, then the clamp runs (engine.cpp:1627 after the reduce).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 512
+RATE = 48000
+ALG_BYTES_PER_TRACK_FRAME = 8  # stereo f32 source frame read once (cfg 2)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks_json():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_sources(n_tracks, n_blocks, seed):
+    """SURVEY §8(d) fixture at bench size: uniform(-1,1) * 0.5/sqrt(N) stereo f32, (n_blocks+4)*512+64 frames."""
+    frames = (n_blocks + 4) * BLOCK + 64
+    rng = np.random.default_rng(seed)
+    scale = np.float32(0.5 / np.sqrt(n_tracks))
+    for t in range(n_tracks):
+        x = rng.random((2, frames), dtype=np.float32)
+        x *= 2.0
+        x -= 1.0
+        x *= scale
+        yield t, x
+
+
+def track_params(t):
+    return -6.0 - (t % 7), -1.0 + 0.2 * (t % 11), float(np.float32(0.5 + 0.001 * (t % 512)))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU engine (oracle/_ref) or the C port, on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_engine_run(kind, n_tracks, n_blocks, threads, seed=1234, total_tracks=None):
+    """Times Engine::process on the CPU. threads == 1 is the faithful single-threaded reference; threads > 1
+    runs that many independent engine instances, n_tracks/threads tracks each (the generous all-cores row).
+    Returns (track_frames_per_s, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as o
+    total_tracks = total_tracks or n_tracks
+    per = [n_tracks // threads + (1 if i < n_tracks % threads else 0) for i in range(threads)]
+    sessions = []
+    src = make_sources(n_tracks, n_blocks, seed)
+    for i in range(threads):
+        s = o.Session(kind, 2, BLOCK, RATE, 120.0)
+        for j in range(per[i]):
+            t, x = next(src)
+            x = x * np.float32(np.sqrt(n_tracks) / np.sqrt(total_tracks))
+            vol, pan, gain = track_params(t)
+            s.add_track(vol, pan, False)
+            sid = s.add_sample(x, RATE)
+            s.add_clip(j, sid, 0.0, 1e9, 0.0, 1.0, gain)
+        s.play()
+        s.time_process(1)  # warm-up callback (consumes the constructor's parameter messages)
+        sessions.append(s)
+    secs = [0.0] * threads
+
+    def run(i):
+        secs[i] = sessions[i].time_process(n_blocks)
+
+    ths = [threading.Thread(target=run, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    wall = time.perf_counter() - t0
+    for s in sessions:
+        s.close()
+    return n_tracks * n_blocks * BLOCK / wall, wall
+
+
+def oracle_kind():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as o
+    if o.have_ref():
+        return "reference"
+    if not o.have_port():
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
+    return "port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = oracle_kind()
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 32))
+    n_tracks = args.tracks * args.gpus
+    blocks = args.ref_blocks
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, secs = cpu_engine_run(kind, n_tracks, blocks, threads)
+        log("reference step %d: %.3e track-frames/s (%.2fs)" % (i, v, secs))
+        if i >= args.warmup:
+            vals.append((v, secs))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([s for _, s in vals])) * 1e3
+    one, _ = cpu_engine_run(kind, min(n_tracks, 1024), max(8, blocks // 4), 1)
+    out = {
+        "impl": "reference", "metric": "mixed stereo samples/sec at N tracks", "value": value,
+        "unit": "stereo track-frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "cfg2: %d stereo tracks, 48 kHz f32, gain/pan + bus sum (fade=0), 512-frame block" % n_tracks,
+                   "tracks": n_tracks, "block_frames": BLOCK, "blocks_per_step": blocks,
+                   "note": "reference CPU engine (Engine::process), %d independent engine instances, tracks split evenly" % threads},
+        "cpu_baseline": {"value": value, "unit": "stereo track-frames/s", "cores": threads, "kind": kind,
+                         "sample": "%d callbacks of %d tracks per step; single-thread (faithful) figure: %.3e" % (blocks, n_tracks, one),
+                         "single_thread_value": one},
+        "e2e": {"value": value, "unit": "stereo track-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+class DevPtr:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build_library()
+    import whitebox_b200 as wb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)" % (args.gpus, args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    N, K = args.tracks, args.blocks
+    hbm_peak, peak_src, sm_max = peaks_json()
+
+    # ---- session: N tracks on this rank (global track index rank*N + t) --------------------------------
+    t_setup = time.perf_counter()
+    eng = wb.Engine(2, BLOCK, RATE, 120.0, device=local, sum_mode=wb.SUM_EXACT if args.exact else wb.SUM_AUTO)
+    stream = torch.cuda.Stream()
+    eng.dev.set_stream(stream.cuda_stream)
+    host_sources = []
+    for t, x in make_sources(N, K, 1234 + rank):
+        x = x * np.float32(1.0 / np.sqrt(world))  # keep the N*world-track bus inside +/-1
+        vol, pan, gain = track_params(rank * N + t)
+        eng.add_track(vol, pan, False)
+        sid = eng.add_sample(x, RATE)
+        eng.add_clip(t, sid, 0.0, 1e9, 0.0, 1.0, gain)
+        if args.cold and rank == 0:
+            host_sources.append(x)
+    if rank == 0:
+        log("setup: %d tracks x %d blocks (%.2f GiB of sources per GPU) in %.1fs" %
+            (N, K, N * 2 * ((K + 4) * BLOCK + 64) * 4 / 2**30, time.perf_counter() - t_setup))
+
+    track_frames_per_step = N * K * BLOCK  # per rank
+    dev = eng.dev
+    dev.set_track_count(N)
+    flags = wb.MIX_NO_CLAMP if world > 1 else 0
+
+    def reduce_and_clamp():
+        if world > 1:
+            ptr, n = dev.device_bus()
+            bus = torch.as_tensor(DevPtr(ptr, n), device="cuda")
+            dist.all_reduce(bus)  # the single NCCL reduce of the partial buses (sum, f32)
+            dev.clamp_device(ptr, n)
+
+    # ---- (1) device-resident throughput: schedule submitted once, K launches of the mix kernel ---------
+    eng.play()
+    segs, gains = eng.schedule(K)
+    dev.submit(segs, gains, K)
+    dev.synchronize()
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, args.warmup)):
+            dev.mix(flags)
+            reduce_and_clamp()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = dev.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(args.steps):
+            ev[i][0].record(stream)
+            dev.mix(flags)
+            ev[i][1].record(stream)
+            reduce_and_clamp()
+        e1.record(stream)
+        barrier()
+        launches = dev.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+    total_ms = e0.elapsed_time(e1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    kernel_name = dev.last_kernel()
+    out_dev, peaks_dev = dev.fetch(True)
+
+    # ---- (2) end to end through the host engine API with host buffers --------------------------------
+    def e2e_step(cold):
+        if cold:  # upload every source sample again (host -> device), then render
+            for t, x in enumerate(host_sources):
+                dev.sample_release(t)
+                sid = dev.sample_upload(x, RATE)
+                assert sid == t
+        eng.stop()
+        eng.play()
+        if world == 1:
+            return eng.render(K)
+        segs2, gains2 = eng.schedule(K)
+        dev.submit(segs2, gains2, K)
+        dev.mix(flags)
+        reduce_and_clamp()
+        return dev.fetch(True) if rank == 0 else (dev.synchronize(), None)
+
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            e2e_step(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out_e2e, peaks_e2e = e2e_step(False)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_cold_s = None
+        if args.cold and world == 1:
+            e2e_step(True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(max(1, args.steps // 4)):
+                e2e_step(True)
+            barrier()
+            e2e_cold_s = (time.perf_counter() - t0) / max(1, args.steps // 4)
+    n_segs = len(segs)
+    h2d = n_segs * 48 + N * 8
+    d2h = 2 * K * BLOCK * 4 + K * N * 2 * 4
+
+    # max over ranks
+    t = torch.tensor([total_ms, kern_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms, e2e_s = [float(v) for v in t.tolist()]
+
+    if rank == 0:
+        same = bool(np.array_equal(out_dev.view(np.uint32), out_e2e.view(np.uint32))) if out_e2e is not None else None
+        ms_per_step = total_ms / args.steps
+        value = world * track_frames_per_step / (ms_per_step * 1e-3)
+        alg_bytes = track_frames_per_step * ALG_BYTES_PER_TRACK_FRAME
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        e2e_value = world * track_frames_per_step * args.steps / e2e_s
+        cpu_kind = oracle_kind()
+        cpu_blocks = args.cpu_blocks
+        cpu_val, cpu_secs = cpu_engine_run(cpu_kind, N, cpu_blocks, 1) if world == 1 else (None, None)
+        res = {
+            "metric": "mixed stereo samples/sec at N tracks", "value": value, "unit": "stereo track-frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "cfg2: %d stereo tracks/GPU, 48 kHz f32, gain/pan + bus sum (fade=0: the reference has none), 512-frame block" % N,
+                "tracks_per_gpu": N, "total_tracks": N * world, "block_frames": BLOCK, "blocks_per_step": K,
+                "out_frames_per_s": value / (N * world), "realtime_x": value / (N * world) / RATE,
+                "l2": "inputs larger than L2 (%.2f GiB streamed per step per GPU vs 126 MB)" % (alg_bytes / 2**30),
+                "kernel": kernel_name, "parallelism": "tracks sharded x%d, 1 NCCL all-reduce of the bus" % world if world > 1 else "1 GPU",
+                "e2e_equals_device_run": same,
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "e2e": {"value": e2e_value, "unit": "stereo track-frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "note": "host scheduling + H2D segment table + expand + mix + D2H bus and VU peaks; source samples resident (engine state, as wb::Sample in the reference)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if e2e_cold_s:
+            src_bytes = N * 2 * ((K + 4) * BLOCK + 64) * 4
+            res["e2e_cold"] = {"value": track_frames_per_step / e2e_cold_s, "unit": "stereo track-frames/s",
+                               "h2d_bytes_per_step": h2d + src_bytes, "d2h_bytes_per_step": d2h,
+                               "note": "as e2e, plus re-uploading every source sample from host memory each step"}
+        if cpu_val:
+            res["cpu_baseline"] = {"value": cpu_val, "unit": "stereo track-frames/s", "cores": 1, "kind": cpu_kind,
+                                   "sample": "%d callbacks of the same %d-track workload through Engine::process, 1 thread (the reference mix is single-threaded), %.1fs" % (cpu_blocks, N, cpu_secs)}
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tracks", type=int, default=1024, help="stereo tracks per GPU")
+    ap.add_argument("--blocks", type=int, default=1024, help="512-frame callbacks per step (our arm)")
+    ap.add_argument("--ref-blocks", type=int, default=96, help="callbacks per step of the reference arm")
+    ap.add_argument("--cpu-blocks", type=int, default=256, help="callbacks of the cpu_baseline sample")
+    ap.add_argument("--exact", type=int, default=1, help="1: bit-exact sequential track order, 0: auto")
+    ap.add_argument("--cold", type=int, default=1, help="also measure e2e_cold (N=1 only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
