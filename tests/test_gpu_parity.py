@@ -196,8 +196,8 @@ def big(wb):
         x = ((rng.random((2, frames), dtype=np.float32) * 2 - 1) * np.float32(0.5 / 32)).astype(np.float32)
         sid = dev.sample_upload(x, 48000)
         segs[t] = (t, 0, K, 0, B, sid, 0.0, 1.0, 0.5 + 0.001 * (t % 512), 0)
-    gains = np.stack([np.float32(0.3) + np.float32(0.001) * (np.arange(N) % 97),
-                      np.float32(0.9) - np.float32(0.0005) * (np.arange(N) % 89)], axis=1).astype(np.float32)
+    gains = np.stack([np.float32(0.15) + np.float32(0.001) * (np.arange(N) % 97),
+                      np.float32(0.3) - np.float32(0.0005) * (np.arange(N) % 89)], axis=1).astype(np.float32)
     return dict(dev=dev, segs=segs, gains=gains, N=N, K=K, B=B)
 
 
@@ -207,7 +207,7 @@ def test_full_size_properties(wb, big):
     out1, pk1 = dev.render(segs, gains, K)
     out1b, pk1b = dev.render(segs, gains, K)
     assert same_bits(out1, out1b) and same_bits(pk1, pk1b), "run-to-run determinism"
-    assert np.abs(out1).max() > 0.05 and np.all(np.isfinite(out1))
+    assert np.abs(out1).max() > 0.02 and np.all(np.isfinite(out1))
     # linearity: doubling every track gain doubles bus and peaks exactly (power-of-two scaling, no clamp hit)
     out2, pk2 = dev.render(segs, gains * 2, K)
     assert np.abs(out2).max() < 1.0
@@ -251,7 +251,7 @@ def test_single_track_solo_matches_peak(wb, big):
     g[777] = gains[777]
     out, pk = dev.render(segs, g, K)
     blockmax = np.abs(out.reshape(2, K, B)).max(axis=2).T
-    assert same_bits(blockmax, pk[:, 777, :])
+    assert same_bits(np.ascontiguousarray(blockmax), np.ascontiguousarray(pk[:, 777, :]))
     assert not pk[:, :777].any() and not pk[:, 778:].any()
 
 

@@ -328,6 +328,8 @@ class Engine:
         peaks = np.zeros((n_blocks, self.n_tracks, 2), np.float32)
         self._ck(self.L.wbxh_render(self.h, n_blocks, _chan_ptrs(out),
                                     peaks.ctypes.data if (want_peaks and self.n_tracks) else None))
+        if self.dev is not None:  # keep the device view's shape in step (fetch / fetch_interleaved after render)
+            self.dev.C, self.dev.B, self.dev.n_tracks, self.dev.n_blocks = self.C, self.B, self.n_tracks, n_blocks
         return out, peaks
 
     def process(self, n_blocks):

@@ -19,6 +19,9 @@ cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, ui
 cudaError_t launch_clamp(float* x, uint64_t n, int n_sm, cudaStream_t stream);
 cudaError_t launch_interleave(const float* bus, uint64_t frames, uint32_t channels, int fmt, void* dst, int n_sm,
                               cudaStream_t stream);
+cudaError_t launch_interleave_sample(const void* planar, size_t plane_bytes, uint64_t frames, uint32_t nch,
+                                     uint32_t esize, void* dst, int n_sm, cudaStream_t stream);
+int mix_warps_per_sm(int fpl);
 }  // namespace wbx
 
 using namespace wbx;
@@ -26,9 +29,10 @@ using namespace wbx;
 namespace {
 
 struct SampleRec {
-  void* d_base = nullptr;
-  size_t stride_elems = 0;  // elements between channels
-  uint32_t channels = 0, rate = 0, fmt = 0, esize = 0;
+  void* d_base = nullptr;   // frame-interleaved, nch channels
+  uint32_t channels = 0;    // channels of the Sample as uploaded
+  uint32_t nch = 0;         // channels kept on the device: min(channels, 2)
+  uint32_t rate = 0, fmt = 0, esize = 0;
   uint64_t frames = 0;
   bool live = false;
 };
@@ -52,7 +56,7 @@ struct wbx_engine {
   uint32_t C = 2, B = 512, rate = 48000, n_tracks = 0;
   int sum_mode = WBX_SUM_AUTO;
   std::vector<SampleRec> samples;
-  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv;
+  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload;
   HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv;
   std::vector<uint32_t> slot_busy;  // [track][slot] -> first free block
   uint32_t slot_cap = 0;
@@ -128,7 +132,6 @@ uint32_t esize_of(int fmt) {
 // frames per lane (tile = 32 * fpl frames) and track groups for a render of n_blocks callbacks
 void choose_shape(const wbx_engine* e, uint32_t n_blocks, int* fpl_out, uint32_t* groups_out) {
   const uint32_t B = e->B, N = e->n_tracks;
-  // resident warps per SM for each variant (see launch_mix): fpl16: 2x5, fpl8: 2x8, fpl4: 2x8
   const long sm = e->n_sm;
   int fpl = 16;
   if (B <= 128)
@@ -136,13 +139,13 @@ void choose_shape(const wbx_engine* e, uint32_t n_blocks, int* fpl_out, uint32_t
   else if (B <= 256)
     fpl = 8;
   auto items_for = [&](int f) { return (long)n_blocks * ((B + 32 * f - 1) / (32 * f)); };
-  auto warps_for = [&](int f) { return sm * (f == 16 ? 10 : 16); };
+  auto warps_for = [&](int f) { return sm * wbx::mix_warps_per_sm(f); };
   const char* env = getenv("WBX_FPL");
   if (env && (atoi(env) == 4 || atoi(env) == 8 || atoi(env) == 16)) {
     fpl = atoi(env);
   } else {
-    // prefer big tiles, but split tiles while the exact-order item count cannot fill the machine ~4x
-    while (fpl > 4 && items_for(fpl) < 4 * warps_for(fpl)) fpl >>= 1;
+    // prefer big tiles (4 KiB bulk copies); split tiles only while exact-order items cannot fill the machine
+    while (fpl > 4 && items_for(fpl) < warps_for(fpl)) fpl >>= 1;
   }
   uint32_t groups = 1;
   const long items = items_for(fpl), warps = warps_for(fpl);
@@ -197,7 +200,8 @@ int wbx_destroy(wbx_engine* e) {
   cudaStreamSynchronize(e->stream);
   for (auto& s : e->samples)
     if (s.live) cudaFree(s.d_base);
-  for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv})
+  for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv,
+                    &e->d_upload})
     if (b->p) cudaFree(b->p);
   for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv})
     if (b->p) cudaFreeHost(b->p);
@@ -253,15 +257,21 @@ int wbx_sample_upload(wbx_engine* e, int format, uint32_t channels, uint64_t fra
   r.channels = channels;
   r.rate = sample_rate;
   r.frames = frames;
-  // frames + 16 zero frames (dsp/sample.cpp:127,140) + slack for 16-B aligned windows, stride % 32 == 0
-  r.stride_elems = ((size_t)frames + 16 + 16 + 31) & ~(size_t)31;
-  const size_t bytes = r.stride_elems * es * channels;
+  r.nch = channels < 2 ? 1 : 2;  // output channel c reads source channel c % channels, c < 2 (sampler.cpp:111)
+  // frames + 16 zero frames (dsp/sample.cpp:127,140) + slack for 16-B aligned windows and the 2-tap reach
+  const size_t alloc_frames = ((size_t)frames + 16 + 32 + 31) & ~(size_t)31;
+  const size_t bytes = alloc_frames * es * r.nch;
+  const size_t plane_bytes = (((size_t)frames * es) + 255) & ~(size_t)255;
+  int rc = dev_reserve(e, e->d_upload, plane_bytes * r.nch);
+  if (rc) return rc;
   cudaError_t err = cudaMalloc(&r.d_base, bytes);
   if (err != cudaSuccess) return fail(e, WBX_ERR_NOMEM, "cudaMalloc(%zu) for sample failed", bytes);
   CU(e, cudaMemsetAsync(r.d_base, 0, bytes, e->stream));
-  for (uint32_t c = 0; c < channels; c++)
-    CU(e, cudaMemcpyAsync((uint8_t*)r.d_base + (size_t)c * r.stride_elems * es, planar[c], (size_t)frames * es,
+  for (uint32_t c = 0; c < r.nch; c++)
+    CU(e, cudaMemcpyAsync((uint8_t*)e->d_upload.p + c * plane_bytes, planar[c], (size_t)frames * es,
                           cudaMemcpyHostToDevice, e->stream));
+  CU(e, launch_interleave_sample(e->d_upload.p, plane_bytes, frames, r.nch, es, r.d_base, e->n_sm, e->stream));
+  e->launches++;
   CU(e, cudaStreamSynchronize(e->stream));  // the caller's host arrays may go away after return
   r.live = true;
   uint32_t id = 0;
@@ -332,9 +342,7 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     e->slot_busy[(size_t)sg.track * e->slot_cap + slot] = sg.block + sg.n_blocks;
     if (slot + 1 > slots) slots = slot + 1;
     DSpan& d = hs[i];
-    const uint32_t c1 = (C > 1) ? (1 % sm.channels) : 0;  // i % sample->channels, sampler.cpp:111
-    d.ch[0] = sm.d_base;
-    d.ch[1] = (const uint8_t*)sm.d_base + (size_t)c1 * sm.stride_elems * sm.esize;
+    d.base = sm.d_base;
     d.pos0 = sg.src_pos;
     d.speed = sg.speed;
     d.count = sm.frames;
@@ -346,7 +354,7 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     d.length = sg.length;
     d.fmt = sm.fmt;
     d.slot = slot;
-    d.mono = (c1 == 0 || C == 1) ? 1u : 0u;
+    d.nch = sm.nch;
     d.pad = 0;
   }
   if (N) memcpy(e->h_gains.p, track_gains, (size_t)N * 2 * sizeof(float));

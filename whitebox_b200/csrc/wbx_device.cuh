@@ -1,9 +1,14 @@
 // wbx_device.cuh — device-side data model of the mixing hot path (internal; the ABI is include/wbx.h).
 //
 // HBM layout
-//   samples   one allocation per Sample (dsp/sample.h:18-28): channels x stride elements, planar, channel
-//             base 256-B aligned, stride a multiple of 32 elements, >= 16 zero frames after `frames`
-//             (dsp/sample.cpp:127,140) plus slack so 16-B aligned bulk windows never leave the allocation.
+//   samples   one allocation per Sample (dsp/sample.h:18-28). The host hands planar channels over the ABI;
+//             on the device a sample is stored FRAME-INTERLEAVED (L0 R0 L1 R1 ...; mono stays as is) so that
+//             the window one callback needs from one stereo track (512 frames = 4 KiB of f32) is ONE
+//             contiguous, 16-byte-aligned run = one TMA bulk copy, and a 128-bit shared-memory load yields two
+//             (L, R) pairs for packed f32x2 math. Only the first min(channels, 2) source channels are kept
+//             (output channel c reads source channel c % channels and the bus has at most 2 channels,
+//             dsp/sampler.cpp:111, engine/track.h:50). Base 256-B aligned, >= 16 zero frames after `frames`
+//             (dsp/sample.cpp:127,140) plus slack so aligned windows never leave the allocation.
 //   spans     one DSpan per wbx_segment (L2-resident; reused by every block of a run).
 //   cells     [n_blocks][n_tracks][slots] DCell, 16 B each: the state of one Sampler::stream call
 //             (position in f64, clipped length) written by the schedule-expansion kernel. 0.4 % of the
@@ -18,7 +23,7 @@ namespace wbx {
 constexpr uint32_t kSilent = 0xFFFFFFFFu;
 
 struct __align__(16) DSpan {
-  const void* ch[2];  // source channel base for output channel 0 / 1 (c % sample_channels resolved)
+  const void* base;   // frame-interleaved sample data
   double pos0;        // Sampler::sample_offset_ at the first call
   double speed;       // Sampler::playback_speed_
   uint64_t count;     // Sample::count
@@ -28,7 +33,7 @@ struct __align__(16) DSpan {
   uint32_t dst_off, length;
   uint32_t fmt;   // wbx_format
   uint32_t slot;  // which of the `slots` cells of (block, track) this span writes
-  uint32_t mono;  // ch[1] == ch[0]
+  uint32_t nch;   // channels stored on the device (1 or 2)
   uint32_t pad;
 };
 static_assert(sizeof(DSpan) == 80, "DSpan layout");
@@ -41,22 +46,28 @@ struct __align__(16) DCell {
 static_assert(sizeof(DCell) == 16, "DCell layout");
 
 // item kinds after resolve (per cell and frame tile)
-enum : uint32_t { K_SILENT = 0, K_VEC = 1, K_UNI = 2, K_GEN = 3, K_DIRECT = 4 };
+enum : uint32_t {
+  K_SILENT = 0,
+  K_FAST = 1,    // stereo f32, unity speed, whole tile, 16-B aligned window: 128-bit loads + packed f32x2 math
+  K_GEN = 2,     // anything else whose window fits a stage: per-frame path on the staged window
+  K_DIRECT = 3   // window larger than a stage (speed well above 1): per-frame path straight from global
+};
 
 // Resolved per-(cell, tile) descriptor, lives in shared memory (64 B).
 struct __align__(16) Desc {
-  const void* src[2];  // staged kinds: 16-B aligned global address of the window; K_DIRECT: channel base
-  double pos;          // segment position (f64) of segment-relative frame 0
+  const void* src;   // staged kinds: 16-B aligned global address of the window; K_DIRECT: sample base
+  double pos;        // segment position (f64) of segment-relative frame 0
   double speed;
   float gain;
   float tg[2];     // (mute ? 0 : volume) * pan_coeffs[c]
   uint32_t track;
-  int32_t base;    // element index (relative to the channel base) of window element 0; 0 for K_DIRECT
+  int32_t base;    // frame index (relative to the sample start) of window frame 0; 0 for K_DIRECT
   int32_t jrel0;   // segment-relative index of tile frame 0 (jj = frame_in_tile + jrel0)
   uint16_t lo, hi; // tile-relative frame range [lo, hi) this item covers
-  uint16_t bytes;  // bytes per channel to stage (multiple of 16)
+  uint16_t bytes;  // bytes to stage (multiple of 16)
   uint8_t kind;
-  uint8_t fmt;     // wbx_format | 0x80 when both output channels read the same source channel (mono)
+  uint8_t fmt;     // wbx_format | 0x80 when the device copy has one channel (both outputs read it)
+  uint32_t pad[2];
 };
 static_assert(sizeof(Desc) == 64, "Desc layout");
 
@@ -66,7 +77,7 @@ struct MixParams {
   const float* gains;   // [n_tracks][2]
   float* bus;           // [C][n_blocks*B]
   float* peaks;         // [n_blocks][n_tracks][2], pre-zeroed
-  float* ws;            // tree mode: [items][C][tile] partial sums
+  float* ws;            // tree mode: [tiles][groups][2][T] partial sums
   uint32_t* counters;   // [0] = dynamic work counter, [1 + (k*n_tiles+f)] = arrivals per output tile
   uint32_t n_tracks, n_blocks, slots;
   uint32_t B, C;

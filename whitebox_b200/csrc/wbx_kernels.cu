@@ -142,111 +142,100 @@ __device__ __forceinline__ void accumulate(float s, float gain, float tg, float&
   pk = fmaxf(pk, fabsf(term));                           // vu_meter.h:24
 }
 
+// Lane <-> frame mapping of a tile of T = 32*FPL frames: lane owns frame pairs (2q, 2q+1), q = lane + 32*i,
+// i < FPL/2 — for an interleaved stereo f32 window that pair is exactly one 16-byte shared-memory word.
+// acc[i*2+e] is the (L, R) bus accumulator of frame 2*(lane+32*i)+e.
+
 // Generic per-frame path: any format, unity or linear, staged window (shared) or direct (global) rows.
-template <int FPL, uint32_t FMT, bool UNITY>
-__device__ __forceinline__ void consume_gen_t(const Desc& d, const void* rowL, const void* rowR,
-                                              float (&acc)[2][FPL], float& pkL, float& pkR, int lane, bool two) {
+// `row` points at window frame 0 (frame-interleaved, NCH channels); d.base is that frame's sample index.
+template <int FPL, uint32_t FMT, bool UNITY, int NCH>
+__device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
+                                              float& pkR, int lane, bool two) {
   const int64_t ip = (int64_t)(uint32_t)(int64_t)d.pos;  // (uint32_t)sample_offset_, sampler.cpp:107
 #pragma unroll
-  for (int i = 0; i < FPL / 4; i++) {
+  for (int i = 0; i < FPL / 2; i++) {
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int fr = 4 * (lane + 32 * i) + e;
+    for (int e = 0; e < 2; e++) {
+      const int fr = 2 * (lane + 32 * i) + e;
       if (fr >= (int)d.lo && fr < (int)d.hi) {
         const int32_t jj = fr + d.jrel0;
         float sL, sR = 0.0f;
         if (UNITY) {
-          const int64_t idx = ip + jj - d.base;
-          sL = load_unity<FMT>(rowL, idx);
-          if (two) sR = load_unity<FMT>(rowR, idx);
+          const int64_t idx = (ip + jj - d.base) * NCH;
+          sL = load_unity<FMT>(row, idx);
+          if (two) sR = (NCH == 2) ? load_unity<FMT>(row, idx + 1) : sL;
         } else {
           const double x = __dadd_rn(d.pos, __dmul_rn((double)jj, d.speed));  // sampler.cpp:50
           const int64_t ix = __double2ll_rz(x);                                // :51
           const float fx = __double2float_rn(__dsub_rn(x, __ll2double_rn(ix)));  // :52
-          const int64_t idx = ix - d.base;
-          const float a = load_lin<FMT>(rowL, idx), b = load_lin<FMT>(rowL, idx + 1);
+          const int64_t idx = (ix - d.base) * NCH;
+          const float a = load_lin<FMT>(row, idx), b = load_lin<FMT>(row, idx + NCH);
           sL = __fadd_rn(a, __fmul_rn(fx, __fsub_rn(b, a)));  // :55
           if (two) {
-            const float a2 = load_lin<FMT>(rowR, idx), b2 = load_lin<FMT>(rowR, idx + 1);
-            sR = __fadd_rn(a2, __fmul_rn(fx, __fsub_rn(b2, a2)));
+            if (NCH == 2) {
+              const float a2 = load_lin<FMT>(row, idx + 1), b2 = load_lin<FMT>(row, idx + 3);
+              sR = __fadd_rn(a2, __fmul_rn(fx, __fsub_rn(b2, a2)));
+            } else {
+              sR = sL;
+            }
           }
         }
-        accumulate(sL, d.gain, d.tg[0], acc[0][i * 4 + e], pkL);
-        if (two) accumulate(sR, d.gain, d.tg[1], acc[1][i * 4 + e], pkR);
+        accumulate(sL, d.gain, d.tg[0], acc[i * 2 + e].x, pkL);
+        if (two) accumulate(sR, d.gain, d.tg[1], acc[i * 2 + e].y, pkR);
       }
     }
   }
 }
 
+template <int FPL, uint32_t FMT, bool UNITY>
+__device__ __forceinline__ void consume_gen_n(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
+                                              float& pkR, int lane, bool two) {
+  if (d.fmt & 0x80u)
+    consume_gen_t<FPL, FMT, UNITY, 1>(d, row, acc, pkL, pkR, lane, two);
+  else
+    consume_gen_t<FPL, FMT, UNITY, 2>(d, row, acc, pkL, pkR, lane, two);
+}
+
 template <int FPL>
-__device__ __forceinline__ void consume_gen(const Desc& d, const void* rowL, const void* rowR, float (&acc)[2][FPL],
-                                         float& pkL, float& pkR, int lane, bool two) {
+__device__ __forceinline__ void consume_gen(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
+                                            float& pkR, int lane, bool two) {
   const uint32_t fmt = d.fmt & 0x7fu;
   if (d.speed == 1.0) {  // playback_speed_ == 1.0, sampler.cpp:106
     switch (fmt) {
-      case F_I16: consume_gen_t<FPL, F_I16, true>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
-      case F_I24: consume_gen_t<FPL, F_I24, true>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
-      case F_I32: consume_gen_t<FPL, F_I32, true>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
-      default: consume_gen_t<FPL, F_F32, true>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+      case F_I16: consume_gen_n<FPL, F_I16, true>(d, row, acc, pkL, pkR, lane, two); break;
+      case F_I24: consume_gen_n<FPL, F_I24, true>(d, row, acc, pkL, pkR, lane, two); break;
+      case F_I32: consume_gen_n<FPL, F_I32, true>(d, row, acc, pkL, pkR, lane, two); break;
+      default: consume_gen_n<FPL, F_F32, true>(d, row, acc, pkL, pkR, lane, two); break;
     }
   } else {
     switch (fmt) {
-      case F_I16: consume_gen_t<FPL, F_I16, false>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
-      case F_I24: consume_gen_t<FPL, F_I24, false>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
-      case F_I32: consume_gen_t<FPL, F_I32, false>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
-      default: consume_gen_t<FPL, F_F32, false>(d, rowL, rowR, acc, pkL, pkR, lane, two); break;
+      case F_I16: consume_gen_n<FPL, F_I16, false>(d, row, acc, pkL, pkR, lane, two); break;
+      case F_I24: consume_gen_n<FPL, F_I24, false>(d, row, acc, pkL, pkR, lane, two); break;
+      case F_I32: consume_gen_n<FPL, F_I32, false>(d, row, acc, pkL, pkR, lane, two); break;
+      default: consume_gen_n<FPL, F_F32, false>(d, row, acc, pkL, pkR, lane, two); break;
     }
   }
 }
 
-// Fast path: f32, unity speed, window 16-B aligned: 128-bit shared loads.
+// Fast path: stereo f32, unity speed, the whole tile, 16-B aligned window. One 128-bit shared load = two
+// (L, R) frames; gain, pan and the bus add run as packed f32x2 (each component separately rounded, rn).
 template <int FPL>
-__device__ __forceinline__ void consume_vec(const Desc& d, const uint8_t* rowL, const uint8_t* rowR,
-                                            float (&acc)[2][FPL], float& pkL, float& pkR, int lane, bool two) {
-  const float4* rL = reinterpret_cast<const float4*>(rowL);
-  const float4* rR = reinterpret_cast<const float4*>(rowR);
-  const int lo = d.lo, hi = d.hi;
-  const float g = d.gain, tl = d.tg[0], tr = d.tg[1];
+__device__ __forceinline__ void consume_fast(const uint8_t* row, float gain, float tgL, float tgR,
+                                             float2 (&acc)[FPL], float& pkL, float& pkR, int lane) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+  const float2 g2 = make_float2(gain, gain);
+  const float2 t2 = make_float2(tgL, tgR);
+  float4 v[FPL / 2];
 #pragma unroll
-  for (int i = 0; i < FPL / 4; i++) {
-    const int fr = 4 * (lane + 32 * i);
-    if (fr >= lo && fr < hi) {
-      const int q = (fr - lo) >> 2;
-      const float4 vl = rL[q];
-      accumulate(vl.x, g, tl, acc[0][i * 4 + 0], pkL);
-      accumulate(vl.y, g, tl, acc[0][i * 4 + 1], pkL);
-      accumulate(vl.z, g, tl, acc[0][i * 4 + 2], pkL);
-      accumulate(vl.w, g, tl, acc[0][i * 4 + 3], pkL);
-      if (two) {
-        const float4 vr = rR[q];
-        accumulate(vr.x, g, tr, acc[1][i * 4 + 0], pkR);
-        accumulate(vr.y, g, tr, acc[1][i * 4 + 1], pkR);
-        accumulate(vr.z, g, tr, acc[1][i * 4 + 2], pkR);
-        accumulate(vr.w, g, tr, acc[1][i * 4 + 3], pkR);
-      }
-    }
-  }
-}
-
-// f32 unity, window not 16-B aligned relative to the output frames: scalar shared loads, conflict-free.
-template <int FPL>
-__device__ __forceinline__ void consume_uni(const Desc& d, const uint8_t* rowL, const uint8_t* rowR,
-                                            float (&acc)[2][FPL], float& pkL, float& pkR, int lane, bool two) {
-  const float* rL = reinterpret_cast<const float*>(rowL);
-  const float* rR = reinterpret_cast<const float*>(rowR);
-  const int lo = d.lo, hi = d.hi;
-  const int shift = (int)((int64_t)(uint32_t)(int64_t)d.pos + d.jrel0 - d.base);
-  const float g = d.gain, tl = d.tg[0], tr = d.tg[1];
+  for (int i = 0; i < FPL / 2; i++) v[i] = r4[lane + 32 * i];
 #pragma unroll
-  for (int i = 0; i < FPL / 4; i++) {
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int fr = 4 * (lane + 32 * i) + e;
-      if (fr >= lo && fr < hi) {
-        accumulate(rL[fr + shift], g, tl, acc[0][i * 4 + e], pkL);
-        if (two) accumulate(rR[fr + shift], g, tr, acc[1][i * 4 + e], pkR);
-      }
-    }
+  for (int i = 0; i < FPL / 2; i++) {
+    const float2 a = __fmul2_rn(__fmul2_rn(make_float2(v[i].x, v[i].y), g2), t2);  // frame 2q:   (L, R)
+    const float2 b = __fmul2_rn(__fmul2_rn(make_float2(v[i].z, v[i].w), g2), t2);  // frame 2q+1: (L, R)
+    acc[i * 2 + 0] = __fadd2_rn(acc[i * 2 + 0], a);
+    acc[i * 2 + 1] = __fadd2_rn(acc[i * 2 + 1], b);
+    pkL = fmaxf(fmaxf(pkL, fabsf(a.x)), fabsf(b.x));
+    pkR = fmaxf(fmaxf(pkR, fabsf(a.y)), fabsf(b.y));
   }
 }
 
@@ -256,9 +245,9 @@ __device__ __forceinline__ void consume_uni(const Desc& d, const uint8_t* rowL, 
 template <int FPL, int STAGES>
 struct MixLayout {
   static constexpr int T = 32 * FPL;                  // frames per tile
-  static constexpr int ROW_BYTES = (T + 32) * 4;      // staged window per channel (aligned superset + taps)
-  static constexpr int STAGE_BYTES = 2 * ROW_BYTES;
-  static constexpr int RING = 64;                     // descriptor ring entries (two batches of 32 cells)
+  static constexpr int STAGE_BYTES = (T + 32) * 8;    // staged window: T frames of stereo f32 + taps/alignment
+  static constexpr int BATCH = 16;                    // cells resolved at a time
+  static constexpr int RING = 2 * BATCH;              // descriptor ring entries
   static constexpr int OFF_DESC = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_DESC + RING * (int)sizeof(Desc);
   static constexpr int WARP_BYTES = ((OFF_BAR + STAGES * 8) + 127) & ~127;
@@ -280,13 +269,12 @@ __device__ __forceinline__ DCell load_cell(const DCell* cells, uint32_t ci, uint
 
 __device__ __forceinline__ DSpan load_span(const DSpan* spans, const DCell& c) {
   DSpan s;
+  int4* q = reinterpret_cast<int4*>(&s);
   if (c.span != kSilent) {
     const int4* p = reinterpret_cast<const int4*>(spans + c.span);
-    int4* q = reinterpret_cast<int4*>(&s);
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(DSpan) / 16); i++) q[i] = __ldg(p + i);
   } else {
-    int4* q = reinterpret_cast<int4*>(&s);
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(DSpan) / 16); i++) q[i] = make_int4(0, 0, 0, 0);
   }
@@ -294,12 +282,11 @@ __device__ __forceinline__ DSpan load_span(const DSpan* spans, const DCell& c) {
 }
 
 // Turn (cell, span) into the per-tile descriptor: which frames, which source window, which code path.
-template <int ROW_BYTES>
+template <int STAGE_BYTES, int T>
 __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, const float* __restrict__ gains,
-                                              int f0, int tile_len, Desc* out) {
+                                              int f0, int tile_len, bool two, Desc* out) {
   Desc d;
-  d.src[0] = nullptr;
-  d.src[1] = nullptr;
+  d.src = nullptr;
   d.pos = c.pos;
   d.speed = s.speed;
   d.gain = s.gain;
@@ -312,7 +299,9 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
   d.hi = 0;
   d.bytes = 0;
   d.kind = K_SILENT;
-  d.fmt = (uint8_t)(s.fmt | (s.mono ? 0x80u : 0u));
+  d.fmt = (uint8_t)(s.fmt | (s.nch == 1 ? 0x80u : 0u));
+  d.pad[0] = 0;
+  d.pad[1] = 0;
   if (c.span != kSilent) {
     const int seg_lo = (int)s.dst_off, seg_hi = (int)(s.dst_off + c.n_act);
     const int lo = (seg_lo > f0 ? seg_lo : f0) - f0;
@@ -323,10 +312,10 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
       d.jrel0 = f0 - seg_lo;
       d.lo = (uint16_t)lo;
       d.hi = (uint16_t)hi;
-      const int esize = (s.fmt == F_I16) ? 2 : 4;
+      const int fbytes = (int)s.nch * ((s.fmt == F_I16) ? 2 : 4);  // bytes per frame on the device
       const int64_t jj_lo = lo + d.jrel0, jj_hi = hi - 1 + d.jrel0;
       const bool unity = (s.speed == 1.0);
-      int64_t first, last;
+      int64_t first, last;  // first / last source frame the item can touch
       if (unity) {
         const int64_t ip = (int64_t)(uint32_t)(int64_t)c.pos;
         first = ip + jj_lo;
@@ -336,24 +325,18 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
         last = (int64_t)(c.pos + (double)jj_hi * s.speed) + 2;
       }
       if (first < 0) first = 0;
-      const int64_t align = 16 / esize;
+      const int64_t align = 16 / fbytes;  // frames per 16 bytes: 2 (stereo f32), 4 (mono f32 / stereo i16), 8
       const int64_t a = first & ~(align - 1);
       const int64_t end = (last + align) & ~(align - 1);
-      const int64_t bytes = (end - a) * esize;
-      if (bytes <= ROW_BYTES) {
-        d.src[0] = (const uint8_t*)s.ch[0] + a * esize;
-        d.src[1] = (const uint8_t*)s.ch[1] + a * esize;
+      const int64_t bytes = (end - a) * fbytes;
+      if (bytes <= STAGE_BYTES) {
+        d.src = (const uint8_t*)s.base + a * fbytes;
         d.base = (int32_t)a;
         d.bytes = (uint16_t)bytes;
-        if (unity && s.fmt == F_F32) {
-          const bool vec = ((lo & 3) == 0) && ((hi & 3) == 0) && (first == a);
-          d.kind = vec ? K_VEC : K_UNI;
-        } else {
-          d.kind = K_GEN;
-        }
+        const bool fast = two && unity && s.fmt == F_F32 && s.nch == 2 && lo == 0 && hi == T && first == a;
+        d.kind = fast ? K_FAST : K_GEN;
       } else {  // window larger than a stage (speed well above 1): read the source straight from global
-        d.src[0] = s.ch[0];
-        d.src[1] = s.ch[1];
+        d.src = s.base;
         d.kind = K_DIRECT;
       }
     }
@@ -369,6 +352,7 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
 template <int FPL, int STAGES, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
   using L = MixLayout<FPL, STAGES>;
+  constexpr int BATCH = L::BATCH;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wbase = smem + (size_t)warp * L::WARP_BYTES;
@@ -402,111 +386,114 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
     const DCell* cells = p.cells + ((size_t)k * N + tb) * S;
     const int f0 = (int)(f * L::T);
     const int tile_len = ((int)p.B - f0 < L::T) ? (int)p.B - f0 : L::T;
+    float* peaks_k = p.peaks + (size_t)k * N * 2;
 
-    float acc[2][FPL];
+    float2 acc[FPL];
 #pragma unroll
-    for (int i = 0; i < FPL; i++) {
-      acc[0][i] = 0.0f;
-      acc[1][i] = 0.0f;
-    }
+    for (int i = 0; i < FPL; i++) acc[i] = make_float2(0.0f, 0.0f);
     float pkL = 0.0f, pkR = 0.0f;
     bool active = false;
     uint32_t cur_track = 0;
+    uint32_t slot_ctr = 0;  // position of the current cell within its track's `slots` cells
 
-    // descriptors of the first batch
-    {
+    // descriptors of the first batch (lanes >= BATCH idle)
+    if (lane < BATCH) {
       const DCell c0 = load_cell(cells, lane, n_cells);
       const DSpan s0 = load_span(p.spans, c0);
-      resolve_store<L::ROW_BYTES>(c0, s0, p.gains, f0, tile_len, &ring[lane]);
-      __syncwarp();
+      resolve_store<L::STAGE_BYTES, L::T>(c0, s0, p.gains, f0, tile_len, two, &ring[lane]);
     }
-    uint32_t limit = 32;  // cells [0, limit) have descriptors
-    uint32_t ip = 0;      // next cell to consider for staging
-    const uint32_t nb = (n_cells + 31) >> 5;
+    __syncwarp();
+    uint32_t limit = BATCH;  // cells [0, limit) have descriptors
+    uint32_t ip = 0;         // next cell to consider for staging
+    const uint32_t nb = (n_cells + BATCH - 1) / BATCH;
     DCell cN;
     DSpan sN;
+    cN.pos = 0.0;
+    cN.span = kSilent;
+    cN.n_act = 0;
+
+    // stage the window of cell `ip` if it needs one (lane 0 issues the bulk copy)
+    auto produce = [&]() {
+      const uint32_t lim = limit < n_cells ? limit : n_cells;
+      while (ip < lim && (n_issued - n_consumed) < (uint32_t)STAGES) {
+        const Desc* dd = &ring[ip & (L::RING - 1)];
+        const uint32_t kind = dd->kind;
+        if (kind == K_FAST || kind == K_GEN) {
+          if (lane == 0) {
+            const uint32_t st = n_issued % STAGES;
+            const uint32_t bar = bars_s + 8 * st;
+            const uint32_t bytes = dd->bytes;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(rows_s + st * L::STAGE_BYTES, dd->src, bytes, bar);
+          }
+          n_issued++;
+        }
+        ip++;
+      }
+    };
 
     for (uint32_t b = 0; b < nb; b++) {
       const bool more = (b + 1 < nb);
-      if (more) cN = load_cell(cells, (b + 1) * 32 + lane, n_cells);
-      for (int i = 0; i < 32; i++) {
-        const uint32_t ci = b * 32 + i;
+      if (more && lane < BATCH) cN = load_cell(cells, (b + 1) * BATCH + lane, n_cells);
+#pragma unroll 1
+      for (int i = 0; i < BATCH; i++) {
+        const uint32_t ci = b * BATCH + i;
         if (ci >= n_cells) break;
-        if (more && i == 8) sN = load_span(p.spans, cN);
-        if (more && i == 16) {
-          resolve_store<L::ROW_BYTES>(cN, sN, p.gains, f0, tile_len, &ring[((b + 1) & 1) * 32 + lane]);
+        if (more && i == BATCH / 4 && lane < BATCH) sN = load_span(p.spans, cN);
+        if (more && i == BATCH / 2) {
+          if (lane < BATCH)
+            resolve_store<L::STAGE_BYTES, L::T>(cN, sN, p.gains, f0, tile_len, two, &ring[((b + 1) & 1) * BATCH + lane]);
           __syncwarp();
-          limit += 32;
+          limit += BATCH;
         }
-        // ---- producer role: keep up to STAGES windows in flight -------------------------------------
-        {
-          const uint32_t lim = limit < n_cells ? limit : n_cells;
-          while (ip < lim && (n_issued - n_consumed) < (uint32_t)STAGES) {
-            const Desc* dd = &ring[ip & (L::RING - 1)];
-            const uint32_t kind = dd->kind;
-            if (kind == K_VEC || kind == K_UNI || kind == K_GEN) {
-              if (lane == 0) {
-                const uint32_t st = n_issued % STAGES;
-                const uint32_t bar = bars_s + 8 * st;
-                const uint32_t dst = rows_s + st * L::STAGE_BYTES;
-                const uint32_t bytes = dd->bytes;
-                const bool mono = (dd->fmt & 0x80u) != 0 || !two;
-                mbar_expect_tx(bar, mono ? bytes : 2 * bytes);
-                bulk_g2s(dst, dd->src[0], bytes, bar);
-                if (!mono) bulk_g2s(dst + L::ROW_BYTES, dd->src[1], bytes, bar);
-              }
-              n_issued++;
-            }
-            ip++;
-          }
-        }
+        produce();
         // ---- consumer role ------------------------------------------------------------------------------
-        const Desc d = ring[ci & (L::RING - 1)];
-        if (d.kind != K_SILENT) {
+        const Desc* dp = &ring[ci & (L::RING - 1)];
+        const uint32_t kind = dp->kind;
+        if (kind != K_SILENT) {
           active = true;
-          cur_track = d.track;
-          const bool staged = (d.kind != K_DIRECT);
-          const void* rowL = d.src[0];
-          const void* rowR = d.src[1];
-          if (staged) {
-            const uint32_t st = n_consumed % STAGES;
+          cur_track = dp->track;
+          const uint32_t st = n_consumed % STAGES;
+          if (kind != K_DIRECT) {
             const uint32_t par = (n_consumed / STAGES) & 1u;
             while (!mbar_try_wait(bars_s + 8 * st, par)) {
             }
-            rowL = wbase + (size_t)st * L::STAGE_BYTES;
-            rowR = (d.fmt & 0x80u) ? rowL : (const void*)((const uint8_t*)rowL + L::ROW_BYTES);
           }
-          if (d.kind == K_VEC)
-            consume_vec<FPL>(d, (const uint8_t*)rowL, (const uint8_t*)rowR, acc, pkL, pkR, lane, two);
-          else if (d.kind == K_UNI)
-            consume_uni<FPL>(d, (const uint8_t*)rowL, (const uint8_t*)rowR, acc, pkL, pkR, lane, two);
-          else
-            consume_gen<FPL>(d, rowL, rowR, acc, pkL, pkR, lane, two);
-          if (staged) {
+          const uint8_t* row = wbase + (size_t)st * L::STAGE_BYTES;
+          if (kind == K_FAST) {
+            consume_fast<FPL>(row, dp->gain, dp->tg[0], dp->tg[1], acc, pkL, pkR, lane);
+          } else {
+            const Desc d = *dp;
+            consume_gen<FPL>(d, kind == K_DIRECT ? d.src : (const void*)row, acc, pkL, pkR, lane, two);
+          }
+          if (kind != K_DIRECT) {
             __syncwarp();  // every lane is done reading the stage before lane 0 may refill it
             n_consumed++;
           }
         }
         // ---- VU block peak once the track's last slot is done (vu_meter.h:20-30) ----------------------
-        if (active && ((ci + 1) % S) == 0) {
-          // lanes 0-15 reduce L, lanes 16-31 reduce R: one exchange, then four butterfly steps
-          const float send = (lane < 16) ? pkR : pkL;
-          const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-          float m = fmaxf((lane < 16) ? pkL : pkR, recv);
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-          if ((lane == 0 || (lane == 16 && two)) && p.peaks) {
-            float* dst = p.peaks + ((size_t)k * N + cur_track) * 2 + (lane >> 4);
-            if (p.n_tiles == 1)
-              *dst = m;
-            else if (m > 0.0f)
-              atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(m));  // m >= 0: uint order == float order
+        if (++slot_ctr == S) {
+          slot_ctr = 0;
+          if (active) {
+            // lanes 0-15 reduce L, lanes 16-31 reduce R: one exchange, then four butterfly steps
+            const float send = (lane < 16) ? pkR : pkL;
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+            float m = fmaxf((lane < 16) ? pkL : pkR, recv);
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            if ((lane & 15) == 0 && (lane == 0 || two)) {
+              float* dst = peaks_k + (size_t)cur_track * 2 + (lane >> 4);
+              if (p.n_tiles == 1)
+                *dst = m;
+              else if (m > 0.0f)
+                atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(m));  // m >= 0: uint order == float order
+            }
+            pkL = 0.0f;
+            pkR = 0.0f;
+            active = false;
           }
-          pkL = 0.0f;
-          pkR = 0.0f;
-          active = false;
         }
       }
     }
@@ -514,43 +501,38 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
     // ---- bus write ------------------------------------------------------------------------------------
     const size_t chan_stride = (size_t)p.n_blocks * p.B;
     const size_t out_off = (size_t)k * p.B + f0;
-    const bool vec_ok = (p.B & 3u) == 0;
+    const bool vec_ok = (p.B & 1u) == 0;  // frame pairs are 8-byte aligned in the planar bus
     if (p.groups == 1) {
 #pragma unroll
-      for (int c = 0; c < 2; c++) {
-        if (c == 1 && !two) break;
-        float* out = p.bus + c * chan_stride + out_off;
+      for (int i = 0; i < FPL / 2; i++) {
+        const int fr = 2 * (lane + 32 * i);
+        float v[2][2] = {{acc[i * 2].x, acc[i * 2 + 1].x}, {acc[i * 2].y, acc[i * 2 + 1].y}};
 #pragma unroll
-        for (int i = 0; i < FPL / 4; i++) {
-          const int fr = 4 * (lane + 32 * i);
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            float x = acc[c][i * 4 + e];
-            if (p.clamp) x = x > 1.0f ? 1.0f : (x < -1.0f ? -1.0f : x);  // engine.cpp:1627-1636 (NaN passes)
-            v[e] = x;
+        for (int c = 0; c < 2; c++) {
+          if (c == 1 && !two) break;
+          float* out = p.bus + c * chan_stride + out_off;
+          float x0 = v[c][0], x1 = v[c][1];
+          if (p.clamp) {  // engine.cpp:1627-1636 (NaN passes)
+            x0 = x0 > 1.0f ? 1.0f : (x0 < -1.0f ? -1.0f : x0);
+            x1 = x1 > 1.0f ? 1.0f : (x1 < -1.0f ? -1.0f : x1);
           }
-          if (vec_ok && fr + 3 < tile_len) {
-            *reinterpret_cast<float4*>(out + fr) = make_float4(v[0], v[1], v[2], v[3]);
+          if (vec_ok && fr + 1 < tile_len) {
+            *reinterpret_cast<float2*>(out + fr) = make_float2(x0, x1);
           } else {
-#pragma unroll
-            for (int e = 0; e < 4; e++)
-              if (fr + e < tile_len) out[fr + e] = v[e];
+            if (fr < tile_len) out[fr] = x0;
+            if (fr + 1 < tile_len) out[fr + 1] = x1;
           }
         }
       }
     } else {
       // tree mode: publish this group's partial, the last group to arrive adds them in group order
       const uint32_t tile_id = k * p.n_tiles + f;
-      float* part = p.ws + ((size_t)tile_id * p.groups + g) * 2 * L::T;
+      float2* part = reinterpret_cast<float2*>(p.ws) + ((size_t)tile_id * p.groups + g) * 2 * (L::T / 2);
 #pragma unroll
-      for (int c = 0; c < 2; c++) {
-#pragma unroll
-        for (int i = 0; i < FPL / 4; i++) {
-          const int fr = 4 * (lane + 32 * i);
-          *reinterpret_cast<float4*>(part + c * L::T + fr) =
-              make_float4(acc[c][i * 4 + 0], acc[c][i * 4 + 1], acc[c][i * 4 + 2], acc[c][i * 4 + 3]);
-        }
+      for (int i = 0; i < FPL / 2; i++) {
+        const int q = lane + 32 * i;
+        part[q] = make_float2(acc[i * 2].x, acc[i * 2 + 1].x);               // channel 0, frames 2q, 2q+1
+        part[(L::T / 2) + q] = make_float2(acc[i * 2].y, acc[i * 2 + 1].y);  // channel 1
       }
       __threadfence();
       __syncwarp();
@@ -559,29 +541,42 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
       prev = __shfl_sync(0xffffffffu, prev, 0);
       if (prev == p.groups - 1) {
         __threadfence();
-        const float* base = p.ws + (size_t)tile_id * p.groups * 2 * L::T;
+        const float2* base = reinterpret_cast<const float2*>(p.ws) + (size_t)tile_id * p.groups * 2 * (L::T / 2);
         for (int c = 0; c < (two ? 2 : 1); c++) {
           float* out = p.bus + c * chan_stride + out_off;
-          for (int i = 0; i < FPL / 4; i++) {
-            const int fr = 4 * (lane + 32 * i);
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < FPL / 2; i++) {
+            const int q = lane + 32 * i;
+            const int fr = 2 * q;
+            float2 sum = make_float2(0.f, 0.f);
             for (uint32_t gg = 0; gg < p.groups; gg++) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(base + ((size_t)gg * 2 + c) * L::T + fr));
+              const float2 v = __ldcg(base + ((size_t)gg * 2 + c) * (L::T / 2) + q);
               sum.x = __fadd_rn(sum.x, v.x);
               sum.y = __fadd_rn(sum.y, v.y);
-              sum.z = __fadd_rn(sum.z, v.z);
-              sum.w = __fadd_rn(sum.w, v.w);
             }
-            float v[4] = {sum.x, sum.y, sum.z, sum.w};
-            for (int e = 0; e < 4; e++) {
-              float x = v[e];
-              if (p.clamp) x = x > 1.0f ? 1.0f : (x < -1.0f ? -1.0f : x);
-              if (fr + e < tile_len) out[fr + e] = x;
+            if (p.clamp) {
+              sum.x = sum.x > 1.0f ? 1.0f : (sum.x < -1.0f ? -1.0f : sum.x);
+              sum.y = sum.y > 1.0f ? 1.0f : (sum.y < -1.0f ? -1.0f : sum.y);
             }
+            if (fr < tile_len) out[fr] = sum.x;
+            if (fr + 1 < tile_len) out[fr + 1] = sum.y;
           }
         }
       }
     }
+  }
+}
+
+// (frames, channels) planar -> frame-interleaved device sample layout, keeping the first `nch` channels
+__global__ void interleave_sample_kernel(const uint8_t* __restrict__ planar, size_t plane_bytes, uint64_t frames,
+                                         uint32_t nch, uint32_t esize, uint8_t* __restrict__ dst) {
+  const uint64_t n = frames * nch;
+  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t f = o / nch;
+    const uint32_t c = (uint32_t)(o % nch);
+    if (esize == 4)
+      reinterpret_cast<uint32_t*>(dst)[o] = reinterpret_cast<const uint32_t*>(planar + c * plane_bytes)[f];
+    else
+      reinterpret_cast<uint16_t*>(dst)[o] = reinterpret_cast<const uint16_t*>(planar + c * plane_bytes)[f];
   }
 }
 
@@ -664,10 +659,34 @@ static cudaError_t launch_mix_t(const MixParams& p, int n_sm, cudaStream_t strea
 
 cudaError_t launch_mix(const MixParams& p, int fpl, int n_sm, cudaStream_t stream, int* ctas_out) {
   switch (fpl) {
-    case 16: return launch_mix_t<16, 4, 5>(p, n_sm, stream, ctas_out);
-    case 8: return launch_mix_t<8, 4, 8>(p, n_sm, stream, ctas_out);
-    default: return launch_mix_t<4, 6, 8>(p, n_sm, stream, ctas_out);
+    case 16: return launch_mix_t<16, 3, 7>(p, n_sm, stream, ctas_out);
+    case 8: return launch_mix_t<8, 3, 8>(p, n_sm, stream, ctas_out);
+    default: return launch_mix_t<4, 4, 8>(p, n_sm, stream, ctas_out);
   }
+}
+
+// resident warps per SM of each variant (shared-memory bound), for the host's work-shape heuristics
+int mix_warps_per_sm(int fpl) {
+  auto per_sm = [](int warp_bytes, int warps) {
+    int ctas = (227 * 1024) / (warp_bytes * warps + 1024);
+    return (ctas < 1 ? 1 : ctas) * warps;
+  };
+  switch (fpl) {
+    case 16: return per_sm(MixLayout<16, 3>::WARP_BYTES, 7);
+    case 8: return per_sm(MixLayout<8, 3>::WARP_BYTES, 8);
+    default: return per_sm(MixLayout<4, 4>::WARP_BYTES, 8);
+  }
+}
+
+cudaError_t launch_interleave_sample(const void* planar, size_t plane_bytes, uint64_t frames, uint32_t nch,
+                                     uint32_t esize, void* dst, int n_sm, cudaStream_t stream) {
+  const uint64_t n = frames * nch;
+  if (n == 0) return cudaSuccess;
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > (uint64_t)n_sm * 16) blocks = (uint64_t)n_sm * 16;
+  interleave_sample_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const uint8_t*)planar, plane_bytes, frames, nch, esize,
+                                                                 (uint8_t*)dst);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, uint32_t n_tracks, uint32_t slots,
