@@ -10,7 +10,8 @@ f32 tracks per GPU (BASELINE cfg 2: gain/pan + bus sum; fade = 0, the reference 
            events on the launching stream (max over ranks).
   e2e      the same metric through the host engine API (wbx::Engine::render via the C ABI) with HOST buffers:
            host clip scheduling, H2D of the segment table + gains, schedule expansion, mix, D2H of the clamped
-           bus and the per-callback VU peaks all inside the timed region. Source samples are resident engine
+           bus (into page-locked host channels) and of the per-track VU levels all inside the timed region.
+           Source samples are resident engine
            state (uploaded at load time, like wb::Sample objects in the reference); `e2e_cold` additionally
            counts uploading every source sample from host memory each step.
   roofline achieved = algorithmic bytes (8 B per stereo track-frame + cells) / mean mix-kernel duration.
@@ -98,17 +99,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_POOL = {}
+
+
 def make_sources(n_tracks, n_blocks, seed):
-    """SURVEY §8(d) fixture at bench size: uniform(-1,1) * 0.5/sqrt(N) stereo f32, (n_blocks+4)*512+64 frames."""
+    """SURVEY §8(d) fixture at bench size: stereo f32 sources of (n_blocks+4)*512+64 frames, uniform(-1,1) *
+    0.5/sqrt(N). Every track/channel is a different window of one 256 MiB MT-seeded random pool (generating
+    16 GiB of fresh random numbers per run would dominate the bench's wall time); yields (t, [L, R]) views."""
     frames = (n_blocks + 4) * BLOCK + 64
-    rng = np.random.default_rng(seed)
-    scale = np.float32(0.5 / np.sqrt(n_tracks))
+    pool_len = max(1 << 26, 2 * frames)
+    key = (seed, pool_len, n_tracks)
+    if key not in _POOL:
+        _POOL.clear()
+        rng = np.random.default_rng(seed)
+        pool = rng.random(pool_len, dtype=np.float32)
+        pool *= 2.0
+        pool -= 1.0
+        pool *= np.float32(0.5 / np.sqrt(n_tracks))
+        _POOL[key] = pool
+    pool = _POOL[key]
+    span = pool_len - frames
     for t in range(n_tracks):
-        x = rng.random((2, frames), dtype=np.float32)
-        x *= 2.0
-        x -= 1.0
-        x *= scale
-        yield t, x
+        offs = [((2 * t + c) * 7919 * 4099 + 12345 * c) % span for c in range(2)]
+        yield t, [pool[o:o + frames] for o in offs]
 
 
 def track_params(t):
@@ -132,10 +145,9 @@ def cpu_engine_run(kind, n_tracks, n_blocks, threads, seed=1234, total_tracks=No
         s = o.Session(kind, 2, BLOCK, RATE, 120.0)
         for j in range(per[i]):
             t, x = next(src)
-            x = x * np.float32(np.sqrt(n_tracks) / np.sqrt(total_tracks))
             vol, pan, gain = track_params(t)
             s.add_track(vol, pan, False)
-            sid = s.add_sample(x, RATE)
+            sid = s.add_sample(np.stack(x), RATE)
             s.add_clip(j, sid, 0.0, 1e9, 0.0, 1.0, gain)
         s.play()
         s.time_process(1)  # warm-up callback (consumes the constructor's parameter messages)
@@ -244,10 +256,9 @@ def run_ours(args):
     eng.dev.set_stream(stream.cuda_stream)
     host_sources = []
     for t, x in make_sources(N, K, 1234 + rank):
-        x = x * np.float32(1.0 / np.sqrt(world))  # keep the N*world-track bus inside +/-1
         vol, pan, gain = track_params(rank * N + t)
-        eng.add_track(vol, pan, False)
-        sid = eng.add_sample(x, RATE)
+        eng.add_track(vol - 3.0 * np.log2(world), pan, False)  # keep the N*world-track bus inside +/-1
+        sid = eng.add_sample_planar(x, RATE)
         eng.add_clip(t, sid, 0.0, 1e9, 0.0, 1.0, gain)
         if args.cold and rank == 0:
             host_sources.append(x)
@@ -297,25 +308,30 @@ def run_ours(args):
     total_ms = e0.elapsed_time(e1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     kernel_name = dev.last_kernel()
-    out_dev, peaks_dev = dev.fetch(True)
+    out_dev, _ = dev.fetch(False)
 
     # ---- (2) end to end through the host engine API with host buffers --------------------------------
     def e2e_step(cold):
         if cold:  # upload every source sample again (host -> device), then render
             for t, x in enumerate(host_sources):
                 dev.sample_release(t)
-                sid = dev.sample_upload(x, RATE)
+                sid = dev.sample_upload_planar(x, RATE)
                 assert sid == t
         eng.stop()
         eng.play()
-        if world == 1:
-            return eng.render(K)
+        if world == 1:  # the public call: host scheduling, H2D table, expand, mix, D2H bus + VU levels
+            return eng.render(K, want_peaks=False, out=pinned_out.array)
         segs2, gains2 = eng.schedule(K)
         dev.submit(segs2, gains2, K)
         dev.mix(flags)
         reduce_and_clamp()
-        return dev.fetch(True) if rank == 0 else (dev.synchronize(), None)
+        if rank == 0:
+            dev.L.wbx_fetch(dev.h, wb._chan_ptrs(pinned_out.array), None)
+            return pinned_out.array, dev.fetch_levels()
+        dev.synchronize()
+        return None, None
 
+    pinned_out = wb.PinnedArray((2, K * BLOCK))
     with torch.cuda.stream(stream):
         for _ in range(2):
             e2e_step(False)
@@ -336,7 +352,7 @@ def run_ours(args):
             e2e_cold_s = (time.perf_counter() - t0) / max(1, args.steps // 4)
     n_segs = len(segs)
     h2d = n_segs * 48 + N * 8
-    d2h = 2 * K * BLOCK * 4 + K * N * 2 * 4
+    d2h = 2 * K * BLOCK * 4 + N * 2 * 4  # clamped bus + per-track VU levels (reduced over callbacks on the device)
 
     # max over ranks
     t = torch.tensor([total_ms, kern_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -371,7 +387,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": e2e_value, "unit": "stereo track-frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "note": "host scheduling + H2D segment table + expand + mix + D2H bus and VU peaks; source samples resident (engine state, as wb::Sample in the reference)"},
+                    "note": "wbx::Engine::render through the C ABI: host clip scheduling + H2D segment table + schedule expansion + mix + D2H of the clamped bus into page-locked host channels and of the VU levels; source samples resident (engine state, as wb::Sample in the reference)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -395,7 +411,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tracks", type=int, default=1024, help="stereo tracks per GPU")
-    ap.add_argument("--blocks", type=int, default=1024, help="512-frame callbacks per step (our arm)")
+    ap.add_argument("--blocks", type=int, default=4096, help="512-frame callbacks per step (our arm)")
     ap.add_argument("--ref-blocks", type=int, default=96, help="callbacks per step of the reference arm")
     ap.add_argument("--cpu-blocks", type=int, default=256, help="callbacks of the cpu_baseline sample")
     ap.add_argument("--exact", type=int, default=1, help="1: bit-exact sequential track order, 0: auto")

@@ -28,6 +28,7 @@
  */
 #ifndef WBX_H
 #define WBX_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -126,6 +127,14 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
                uint32_t n_blocks);
 int wbx_mix(wbx_engine* e, uint32_t flags);
 int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks);
+/* VUMeter::level over the whole render: levels[n_tracks][2] = max over callbacks of the block peaks
+ * (level only rises until the UI reads it, engine/vu_meter.h:25-29). Reduced on the device: 8 bytes per
+ * track cross PCIe instead of the full peaks array. */
+int wbx_fetch_levels(wbx_engine* e, float* levels);
+/* Page-locked host memory: channel / peak buffers allocated here receive the device copy directly instead
+ * of through the engine's staging buffer (AudioBuffer allocations, core/audio_buffer.h:34, may use it). */
+void* wbx_host_alloc(size_t bytes);
+void wbx_host_free(void* p);
 /* planar f32 bus -> interleaved device format (core/audio_format_conv.cpp:5-106) fused after the clamp;
  * dst_format: WBX_FMT_I16 / I24 (3 packed bytes) / I24_X8 / I32 / F32. dst is host memory of
  * n_blocks*block_frames*out_channels elements. */

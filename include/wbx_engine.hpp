@@ -133,7 +133,10 @@ class Engine {
                      double sample_rate, uint32_t buffer_size);
   void stream(Track& t, uint32_t track_index, uint32_t block, uint32_t num_samples, uint32_t buffer_offset);
   void track_block(Track& t, uint32_t track_index, uint32_t block, double sample_rate, double beat_duration,
-                   double start_time, double end_time, bool currently_playing);
+                   double start_time, double end_time, double block_sample_position, bool currently_playing);
+  uint32_t quiet_blocks(const Track& t, uint32_t k, uint32_t K) const;
+  void stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t q);
+  std::vector<double> blk_start_, blk_end_, blk_spos_;  // per-callback transport of the current schedule()
   wbx_engine* dev_ = nullptr;
   bool host_only_ = false;
   uint32_t out_channels_ = 2, buffer_size_ = 512, sample_rate_ = 48000;
@@ -145,7 +148,7 @@ class Engine {
   std::vector<SampleInfo> samples_;
   std::vector<wbx_segment> segs_;
   std::vector<float> gains_;
-  std::vector<float> peaks_;
+  std::vector<float> levels_;
   std::string err_;
 };
 

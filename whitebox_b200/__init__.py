@@ -35,7 +35,7 @@ assert SEGMENT_DTYPE.itemsize == C.sizeof(Segment) == 48
 WBX_SYMBOLS = [
     "wbx_abi_version", "wbx_create", "wbx_destroy", "wbx_last_error", "wbx_configure", "wbx_set_track_count",
     "wbx_set_sum_mode", "wbx_set_stream", "wbx_sample_upload", "wbx_sample_release", "wbx_render", "wbx_submit",
-    "wbx_mix", "wbx_fetch", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
+    "wbx_mix", "wbx_fetch", "wbx_fetch_levels", "wbx_host_alloc", "wbx_host_free", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
     "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel",
 ]
 WBXH_SYMBOLS = [
@@ -79,6 +79,11 @@ def lib():
     L.wbx_mix.argtypes = [vp, u32]
     L.wbx_fetch.argtypes = [vp, pp, vp]
     L.wbx_fetch_interleaved.argtypes = [vp, vp, i32]
+    L.wbx_fetch_levels.argtypes = [vp, vp]
+    L.wbx_host_alloc.argtypes = [C.c_size_t]
+    L.wbx_host_alloc.restype = vp
+    L.wbx_host_free.argtypes = [vp]
+    L.wbx_host_free.restype = None
     L.wbx_device_bus.argtypes = [vp, pp, C.POINTER(u64)]
     L.wbx_device_peaks.argtypes = [vp, pp, C.POINTER(u64)]
     L.wbx_clamp_device.argtypes = [vp, vp, u64]
@@ -129,6 +134,25 @@ def lib():
 def _chan_ptrs(arr):
     """arr: [channels][n] contiguous -> (void*[channels])"""
     return (C.c_void_p * arr.shape[0])(*[arr[c].ctypes.data for c in range(arr.shape[0])])
+
+
+class PinnedArray:
+    """float32 numpy array in page-locked host memory (wbx_host_alloc): D2H copies land in it directly."""
+
+    def __init__(self, shape):
+        self.n = int(np.prod(shape))
+        self.ptr = lib().wbx_host_alloc(self.n * 4)
+        if not self.ptr:
+            raise WbxError("wbx_host_alloc failed")
+        self.array = np.frombuffer((C.c_float * self.n).from_address(self.ptr), dtype=np.float32).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().wbx_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
 
 
 def panning_coefs(pan):
@@ -194,6 +218,12 @@ class DeviceEngine:
                                           C.byref(sid)))
         return sid.value
 
+    def sample_upload_planar(self, channels, rate, fmt=FMT_F32):
+        ptrs = (C.c_void_p * len(channels))(*[c.ctypes.data for c in channels])
+        sid = C.c_uint32()
+        self._ck(self.L.wbx_sample_upload(self.h, fmt, len(channels), channels[0].size, rate, ptrs, C.byref(sid)))
+        return sid.value
+
     def sample_release(self, sid):
         self._ck(self.L.wbx_sample_release(self.h, sid))
 
@@ -215,6 +245,11 @@ class DeviceEngine:
         peaks = np.empty((self.n_blocks, self.n_tracks, 2), np.float32) if want_peaks else None
         self._ck(self.L.wbx_fetch(self.h, _chan_ptrs(out), peaks.ctypes.data if want_peaks else None))
         return out, peaks
+
+    def fetch_levels(self):
+        lv = np.zeros((self.n_tracks, 2), np.float32)
+        self._ck(self.L.wbx_fetch_levels(self.h, lv.ctypes.data))
+        return lv
 
     def fetch_interleaved(self, fmt):
         frames = self.n_blocks * self.B
@@ -274,6 +309,7 @@ class Engine:
         self.dev = None
         if device >= 0:  # device < 0: scheduling-only engine (host logic tests); render() then fails
             self.dev = DeviceEngine(handle=C.c_void_p(self.L.wbxh_device(self.h)))
+            self.dev.C, self.dev.B = out_channels, block
             if sum_mode != SUM_AUTO:
                 self.dev.set_sum_mode(sum_mode)
 
@@ -310,6 +346,12 @@ class Engine:
         data = np.ascontiguousarray(data, dtype=_NP[fmt])
         return self._ck(self.L.wbxh_add_sample(self.h, fmt, data.shape[0], data.shape[1], rate, _chan_ptrs(data)))
 
+    def add_sample_planar(self, channels, rate, fmt=FMT_F32):
+        """channels: list of 1-D contiguous arrays (one per channel, equal length) - no host-side copy."""
+        ptrs = (C.c_void_p * len(channels))(*[c.ctypes.data for c in channels])
+        assert all(c.flags["C_CONTIGUOUS"] and c.dtype == _NP[fmt] and c.size == channels[0].size for c in channels)
+        return self._ck(self.L.wbxh_add_sample(self.h, fmt, len(channels), channels[0].size, rate, ptrs))
+
     def add_clip(self, track, sample, min_beat, max_beat, start_offset=0.0, speed=1.0, gain=1.0):
         return self._ck(self.L.wbxh_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain))
 
@@ -322,12 +364,14 @@ class Engine:
     def stop(self):
         self.L.wbxh_stop(self.h)
 
-    def render(self, n_blocks, want_peaks=True):
-        """-> (bus [C][n_blocks*B], peaks [n_blocks][N][2]) from one device launch."""
-        out = np.empty((self.C, n_blocks * self.B), np.float32)
-        peaks = np.zeros((n_blocks, self.n_tracks, 2), np.float32)
+    def render(self, n_blocks, want_peaks=True, out=None):
+        """-> (bus [C][n_blocks*B], peaks [n_blocks][N][2]) from one device launch. `out` may be a
+        caller-owned [C][n_blocks*B] f32 array (e.g. PinnedArray(...).array)."""
+        if out is None:
+            out = np.empty((self.C, n_blocks * self.B), np.float32)
+        peaks = np.zeros((n_blocks, self.n_tracks, 2), np.float32) if want_peaks else None
         self._ck(self.L.wbxh_render(self.h, n_blocks, _chan_ptrs(out),
-                                    peaks.ctypes.data if (want_peaks and self.n_tracks) else None))
+                                    peaks.ctypes.data if (peaks is not None and self.n_tracks) else None))
         if self.dev is not None:  # keep the device view's shape in step (fetch / fetch_interleaved after render)
             self.dev.C, self.dev.B, self.dev.n_tracks, self.dev.n_blocks = self.C, self.B, self.n_tracks, n_blocks
         return out, peaks

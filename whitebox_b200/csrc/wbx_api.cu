@@ -17,6 +17,7 @@ cudaError_t launch_mix(const MixParams& p, int fpl, int n_sm, cudaStream_t strea
 cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, uint32_t n_tracks, uint32_t slots,
                           cudaStream_t stream);
 cudaError_t launch_clamp(float* x, uint64_t n, int n_sm, cudaStream_t stream);
+cudaError_t launch_levels(const float* peaks, uint32_t K, uint32_t NC, float* levels, cudaStream_t stream);
 cudaError_t launch_interleave(const float* bus, uint64_t frames, uint32_t channels, int fmt, void* dst, int n_sm,
                               cudaStream_t stream);
 cudaError_t launch_interleave_sample(const void* planar, size_t plane_bytes, uint64_t frames, uint32_t nch,
@@ -56,8 +57,8 @@ struct wbx_engine {
   uint32_t C = 2, B = 512, rate = 48000, n_tracks = 0;
   int sum_mode = WBX_SUM_AUTO;
   std::vector<SampleRec> samples;
-  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload;
-  HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv;
+  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels;
+  HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv, h_levels;
   std::vector<uint32_t> slot_busy;  // [track][slot] -> first free block
   uint32_t slot_cap = 0;
   // last submit
@@ -201,9 +202,9 @@ int wbx_destroy(wbx_engine* e) {
   for (auto& s : e->samples)
     if (s.live) cudaFree(s.d_base);
   for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv,
-                    &e->d_upload})
+                    &e->d_upload, &e->d_levels})
     if (b->p) cudaFree(b->p);
-  for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv})
+  for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels})
     if (b->p) cudaFreeHost(b->p);
   cudaStreamDestroy(e->own_stream);
   delete e;
@@ -439,6 +440,16 @@ int wbx_mix(wbx_engine* e, uint32_t flags) {
   return WBX_OK;
 }
 
+// true when p is page-locked host memory the device can copy to directly (cudaMallocHost / cudaHostRegister)
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks) {
   if (!e) return WBX_ERR_INVALID;
   if (!e->mixed) return fail(e, WBX_ERR_INVALID, "wbx_fetch before wbx_mix");
@@ -447,20 +458,66 @@ int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks) {
   const size_t bus_floats = chan_floats * e->C;
   const size_t peak_floats = (size_t)e->n_blocks * e->n_tracks * 2;
   int rc;
+  bool staged_bus = false, staged_peaks = false;
   if (out_channels) {
-    if ((rc = host_reserve(e, e->h_bus, bus_floats * sizeof(float)))) return rc;
-    CU(e, cudaMemcpyAsync(e->h_bus.p, e->d_bus.p, bus_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    bool direct = true;  // page-locked caller buffers (wbx_host_alloc) take the D2H copy directly
+    for (uint32_t c = 0; c < e->C; c++) direct = direct && out_channels[c] && is_pinned(out_channels[c]);
+    if (direct) {
+      for (uint32_t c = 0; c < e->C; c++)
+        CU(e, cudaMemcpyAsync(out_channels[c], (const float*)e->d_bus.p + c * chan_floats, chan_floats * sizeof(float),
+                              cudaMemcpyDeviceToHost, e->stream));
+    } else {
+      if ((rc = host_reserve(e, e->h_bus, bus_floats * sizeof(float)))) return rc;
+      CU(e, cudaMemcpyAsync(e->h_bus.p, e->d_bus.p, bus_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+      staged_bus = true;
+    }
   }
   if (peaks && peak_floats) {
-    if ((rc = host_reserve(e, e->h_peaks, peak_floats * sizeof(float)))) return rc;
-    CU(e, cudaMemcpyAsync(e->h_peaks.p, e->d_peaks.p, peak_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (is_pinned(peaks)) {
+      CU(e, cudaMemcpyAsync(peaks, e->d_peaks.p, peak_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    } else {
+      if ((rc = host_reserve(e, e->h_peaks, peak_floats * sizeof(float)))) return rc;
+      CU(e, cudaMemcpyAsync(e->h_peaks.p, e->d_peaks.p, peak_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+      staged_peaks = true;
+    }
   }
   CU(e, cudaStreamSynchronize(e->stream));
-  if (out_channels)
+  if (staged_bus)
     for (uint32_t c = 0; c < e->C; c++)
       if (out_channels[c]) memcpy(out_channels[c], (const float*)e->h_bus.p + c * chan_floats, chan_floats * sizeof(float));
-  if (peaks && peak_floats) memcpy(peaks, e->h_peaks.p, peak_floats * sizeof(float));
+  if (staged_peaks) memcpy(peaks, e->h_peaks.p, peak_floats * sizeof(float));
   return WBX_OK;
+}
+
+int wbx_fetch_levels(wbx_engine* e, float* levels) {
+  if (!e || !levels) return WBX_ERR_INVALID;
+  if (!e->mixed) return fail(e, WBX_ERR_INVALID, "wbx_fetch_levels before wbx_mix");
+  const uint32_t NC = e->n_tracks * 2;
+  if (NC == 0) return WBX_OK;
+  CU(e, cudaSetDevice(e->device));
+  int rc;
+  if ((rc = dev_reserve(e, e->d_levels, NC * sizeof(float)))) return rc;
+  if ((rc = host_reserve(e, e->h_levels, NC * sizeof(float)))) return rc;
+  CU(e, cudaMemsetAsync(e->d_levels.p, 0, NC * sizeof(float), e->stream));
+  CU(e, launch_levels((const float*)e->d_peaks.p, e->n_blocks, NC, (float*)e->d_levels.p, e->stream));
+  e->launches++;
+  CU(e, cudaMemcpyAsync(e->h_levels.p, e->d_levels.p, NC * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  memcpy(levels, e->h_levels.p, NC * sizeof(float));
+  return WBX_OK;
+}
+
+void* wbx_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void wbx_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 int wbx_fetch_interleaved(wbx_engine* e, void* dst, int dst_format) {

@@ -322,10 +322,10 @@ void Engine::stream(Track& t, uint32_t track_index, uint32_t block, uint32_t num
 
 // Track::process (engine/track.cpp:587-736) minus the sample loops.
 void Engine::track_block(Track& t, uint32_t track_index, uint32_t block, double sample_rate, double beat_duration,
-                         double start_time, double end_time, bool currently_playing) {
+                         double start_time, double end_time, double block_sample_position, bool currently_playing) {
   t.audio_event_buffer.clear();  // engine.cpp:1591
   if (currently_playing)
-    process_event(t, start_time, end_time, sample_position, beat_duration, sample_rate, buffer_size_);
+    process_event(t, start_time, end_time, block_sample_position, beat_duration, sample_rate, buffer_size_);
 
   for (const auto& m : t.track_msg_queue) {  // process_track_messages + parameter application, :618-643
     switch (m.id) {
@@ -380,25 +380,120 @@ void Engine::track_block(Track& t, uint32_t track_index, uint32_t block, double 
   }
 }
 
+// How many of the callbacks [k, K) are provably event-free for this track: Track::process_event would push
+// no event and leave its state untouched (engine/track.cpp:347-446), and no parameter message is pending.
+uint32_t Engine::quiet_blocks(const Track& t, uint32_t k, uint32_t K) const {
+  if (!t.track_msg_queue.empty()) return 0;
+  if (!playing) return K - k;
+  if (t.refresh_voice) return 0;
+  if (t.clips.empty() || !t.has_clip_idx || t.clip_idx >= t.clips.size()) return K - k;
+  const AudioClip* clip = t.clips[t.clip_idx];
+  if (clip->internal_state_changed) return 0;
+  double key;
+  if (t.partially_ended) {  // inside the clip: nothing happens until `max_time <= end_time` (:423)
+    if (!(blk_start_[k] > clip->min_time)) return 0;
+    key = clip->max_time;
+  } else {  // waiting for the clip: `min_time > end_time` breaks out immediately (:353)
+    key = clip->min_time;
+  }
+  // first callback whose end_time reaches `key` (end times are non-decreasing)
+  const double* first = blk_end_.data() + k;
+  const double* last = blk_end_.data() + K;
+  const double* it = std::lower_bound(first, last, key);  // first end_time >= key
+  return (uint32_t)(it - first);
+}
+
+// q consecutive event-free callbacks: each one is `stream(whole block)` when a sample is playing (:713-719).
+void Engine::stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t q) {
+  if (t.current_audio_event.type != EventType::PlaySample || q == 0) return;
+  const AudioClip* clip = t.current_audio_event.clip;
+  const double count = (double)samples_[clip->sample_id].count;
+  if (t.sample_offset >= count) return;
+  const uint32_t B = buffer_size_;
+  const double adv = (double)B * t.playback_speed;
+  double off = t.sample_offset;
+  uint32_t streamed = 0;
+  if (t.playback_speed == 1.0 && off + (double)q * (double)B < 4.0e15) {
+    // integers: the per-callback additions are exact, so the recurrence has a closed form
+    const double calls = std::ceil((count - off) / (double)B);  // calls made before the sample is exhausted
+    streamed = calls < (double)q ? (uint32_t)calls : q;
+    off = off + (double)streamed * (double)B;
+  } else {
+    while (streamed < q && off < count) {  // the reference's own recurrence, one rounding per callback
+      off = off + adv;
+      streamed++;
+    }
+  }
+  bool extended = false;
+  if (t.open_run >= 0) {
+    wbx_segment& r = segs_[t.open_run];
+    if (r.block + r.n_blocks == block && r.length == B && r.dst_offset == 0) {
+      r.n_blocks += streamed;
+      extended = true;
+    }
+  }
+  if (!extended) {
+    wbx_segment s;
+    s.track = track_index;
+    s.block = block;
+    s.n_blocks = streamed;
+    s.dst_offset = 0;
+    s.length = B;
+    s.sample_id = clip->sample_id;
+    s.src_pos = t.sample_offset;
+    s.speed = t.playback_speed;
+    s.gain = clip->gain;
+    s.reserved = 0;
+    segs_.push_back(s);
+    t.open_run = (int32_t)segs_.size() - 1;
+  }
+  t.sample_offset = off;
+}
+
 int Engine::schedule(uint32_t n_blocks, double sample_rate) {
   if (sample_rate == 0.0) sample_rate = (double)sample_rate_;
   segs_.clear();
   const uint32_t N = (uint32_t)tracks.size();
-  for (auto* t : tracks) t->open_run = -1;
-  for (uint32_t k = 0; k < n_blocks; k++) {
-    // transport arithmetic of Engine::process, engine.cpp:1578-1585
-    const double buffer_duration = (double)buffer_size_ / sample_rate;
-    const double current_beat_duration = beat_duration_;
-    const double current_playhead_position = playhead;
-    const double buffer_duration_in_beats = buffer_duration / current_beat_duration;
-    const double next_playhead_pos = playhead + buffer_duration_in_beats;
-    const bool currently_playing = playing;
-    for (uint32_t i = 0; i < N; i++)
-      track_block(*tracks[i], i, k, sample_rate, current_beat_duration, current_playhead_position, next_playhead_pos,
+  const uint32_t K = n_blocks;
+  // transport arithmetic of Engine::process (engine.cpp:1578-1585, 1619-1623), one entry per callback
+  blk_start_.resize(K);
+  blk_end_.resize(K);
+  blk_spos_.resize(K);
+  const bool currently_playing = playing;
+  const double current_beat_duration = beat_duration_;
+  {
+    double ph = playhead, sp = sample_position;
+    for (uint32_t k = 0; k < K; k++) {
+      const double buffer_duration = (double)buffer_size_ / sample_rate;
+      const double buffer_duration_in_beats = buffer_duration / current_beat_duration;
+      const double next_playhead_pos = ph + buffer_duration_in_beats;
+      blk_start_[k] = ph;
+      blk_end_[k] = next_playhead_pos;
+      blk_spos_[k] = sp;
+      if (currently_playing) {
+        sp += beat_to_samples(buffer_duration_in_beats, sample_rate, current_beat_duration);
+        ph = next_playhead_pos;
+      }
+    }
+    playhead = ph;
+    sample_position = sp;
+  }
+  // Tracks are independent until the bus sum, so walk each track through all callbacks in turn; callbacks
+  // that provably hold no event for the track are skipped in closed form (fast_forward).
+  for (uint32_t i = 0; i < N; i++) {
+    Track& t = *tracks[i];
+    t.open_run = -1;
+    uint32_t k = 0;
+    while (k < K) {
+      track_block(t, i, k, sample_rate, current_beat_duration, blk_start_[k], blk_end_[k], blk_spos_[k],
                   currently_playing);
-    if (currently_playing) {  // :1619-1623
-      sample_position += beat_to_samples(buffer_duration_in_beats, sample_rate, current_beat_duration);
-      playhead = next_playhead_pos;
+      k++;
+      if (!fast_forward || k >= K) continue;
+      const uint32_t q = quiet_blocks(t, k, K);
+      if (q) {
+        if (currently_playing) stream_run(t, i, k, q);
+        k += q;
+      }
     }
   }
   // gain used this render = (mute ? 0 : volume) * pan_coeffs[ch]   (track.cpp:728-731)
@@ -419,20 +514,18 @@ int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, 
   int rc = wbx_set_track_count(dev_, N);
   if (rc) return rc;
   schedule(n_blocks, sample_rate);
-  float* pk = peaks;
-  if (!pk && N) {
-    peaks_.resize((size_t)n_blocks * N * 2);
-    pk = peaks_.data();
-  }
-  rc = wbx_render(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n_blocks, out_channels, pk);
+  rc = wbx_submit(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n_blocks);
   if (rc) return rc;
+  if ((rc = wbx_mix(dev_, 0))) return rc;
+  if ((rc = wbx_fetch(dev_, out_channels, peaks))) return rc;
   // VUMeter::push_samples: level only rises until the UI reads it (vu_meter.h:25-29)
-  for (uint32_t k = 0; k < n_blocks; k++)
+  if (N) {
+    levels_.resize((size_t)N * 2);
+    if ((rc = wbx_fetch_levels(dev_, levels_.data()))) return rc;
     for (uint32_t i = 0; i < N; i++)
-      for (uint32_t c = 0; c < 2; c++) {
-        const float v = pk[((size_t)k * N + i) * 2 + c];
-        if (tracks[i]->level[c] < v) tracks[i]->level[c] = v;
-      }
+      for (uint32_t c = 0; c < 2; c++)
+        if (tracks[i]->level[c] < levels_[2 * i + c]) tracks[i]->level[c] = levels_[2 * i + c];
+  }
   return WBX_OK;
 }
 

@@ -593,6 +593,20 @@ __global__ void clamp_kernel(float* __restrict__ x, uint64_t n) {
   }
 }
 
+// VUMeter::level semantics over a whole render: max over callbacks of the block peaks (vu_meter.h:25-29).
+// peaks [K][NC] (NC = n_tracks*2, all >= 0), levels [NC] pre-zeroed; each thread folds `chunk` callbacks.
+__global__ void level_kernel(const float* __restrict__ peaks, uint32_t K, uint32_t NC, uint32_t chunk,
+                             float* __restrict__ levels) {
+  const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t tc = (uint32_t)(id % NC);
+  const uint32_t k0 = (uint32_t)(id / NC) * chunk;
+  if (k0 >= K) return;
+  const uint32_t k1 = (k0 + chunk < K) ? k0 + chunk : K;
+  float m = 0.0f;
+  for (uint32_t k = k0; k < k1; k++) m = fmaxf(m, __ldg(peaks + (size_t)k * NC + tc));
+  if (m > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(levels + tc), __float_as_uint(m));
+}
+
 // core/audio_format_conv.cpp:5-106. One thread per (frame, channel).
 __global__ void interleave_kernel(const float* __restrict__ bus, uint64_t frames, uint32_t channels, int fmt,
                                   void* __restrict__ dst) {
@@ -693,6 +707,14 @@ cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, ui
                           cudaStream_t stream) {
   if (n_spans == 0) return cudaSuccess;
   expand_schedule<<<(n_spans + 127) / 128, 128, 0, stream>>>(spans, n_spans, cells, n_tracks, slots);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_levels(const float* peaks, uint32_t K, uint32_t NC, float* levels, cudaStream_t stream) {
+  if (K == 0 || NC == 0) return cudaSuccess;
+  const uint32_t chunk = 32;
+  const uint64_t threads = (uint64_t)((K + chunk - 1) / chunk) * NC;
+  level_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(peaks, K, NC, chunk, levels);
   return cudaGetLastError();
 }
 
