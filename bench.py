@@ -217,19 +217,13 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-class DevPtr:
-    """Exposes a raw device pointer to torch through __cuda_array_interface__ (zero copy)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
     ge.build_library()
     import whitebox_b200 as wb
+    from whitebox_b200 import shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -274,8 +268,7 @@ def run_ours(args):
     def reduce_and_clamp():
         if world > 1:
             ptr, n = dev.device_bus()
-            bus = torch.as_tensor(DevPtr(ptr, n), device="cuda")
-            dist.all_reduce(bus)  # the single NCCL reduce of the partial buses (sum, f32)
+            dist.all_reduce(shard.bus_tensor(dev))  # the single NCCL reduce of the partial buses (sum, f32)
             dev.clamp_device(ptr, n)
 
     # ---- (1) device-resident throughput: schedule submitted once, K launches of the mix kernel ---------

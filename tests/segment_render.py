@@ -34,7 +34,7 @@ def _lin(data, fmt, idx):
     return (norm * v.astype(np.float64)).astype(f32)
 
 
-def render(segs, gains, samples, C, B, n_blocks, n_tracks):
+def render(segs, gains, samples, C, B, n_blocks, n_tracks, clamp=True):
     """samples: {id: (data[ch][frames], fmt)} -> (out [K][C][B], peaks [K][N][2])"""
     mix = np.zeros((n_blocks, n_tracks, C, B), f32)
     for s in segs:
@@ -71,7 +71,8 @@ def render(segs, gains, samples, C, B, n_blocks, n_tracks):
             term = (mix[:, t, c, :] * g[t, c]).astype(f32)
             peaks[:, t, c] = np.abs(term).max(axis=1) if B else 0
             out[:, c, :] = (out[:, c, :] + term).astype(f32)
-    out = np.where(out > f32(1.0), f32(1.0), np.where(out < f32(-1.0), f32(-1.0), out)).astype(f32)
+    if clamp:
+        out = np.where(out > f32(1.0), f32(1.0), np.where(out < f32(-1.0), f32(-1.0), out)).astype(f32)
     return out, peaks
 
 
@@ -79,10 +80,10 @@ class ScheduleOnlyEngine:
     """whitebox_b200's host engine without a device (scheduling only) + the numpy render above: exposes the
     scenario API so tests/scenarios.py can drive the product's host logic on a CPU-only box."""
 
-    def __init__(self, C, B, rate, bpm, batched=True):
+    def __init__(self, C, B, rate, bpm, batched=True, clamp=True):
         import whitebox_b200 as wb
         self.eng = wb.Engine(C, B, rate, bpm, device=-1)
-        self.C, self.B, self.batched = C, B, batched
+        self.C, self.B, self.batched, self.clamp = C, B, batched, clamp
         self.samples = {}
         self.n_tracks = 0
 
@@ -103,7 +104,7 @@ class ScheduleOnlyEngine:
         outs, pks = [], []
         for n in chunks:
             segs, gains = self.eng.schedule(n)
-            o, p = render(segs, gains, self.samples, self.C, self.B, n, self.n_tracks)
+            o, p = render(segs, gains, self.samples, self.C, self.B, n, self.n_tracks, self.clamp)
             outs.append(o)
             pks.append(p)
         return np.concatenate(outs), np.concatenate(pks)

@@ -1,0 +1,41 @@
+"""Track sharding across the GPUs of one box: tracks are independent until the bus sum
+(engine/engine.cpp:1600-1617), so each rank owns a contiguous track range and its samples, mixes its shard
+UNCLAMPED, one all-reduce (f32 sum) adds the partial buses, and the clamp (engine.cpp:1627-1636) runs after the
+reduce. torch.distributed supplies the communicator (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+import numpy as np
+
+
+def track_range(n_tracks, rank, world):
+    """Contiguous shard [lo, hi) of rank `rank`; earlier ranks take the remainder."""
+    per, rem = divmod(n_tracks, world)
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+class _DevPtr:
+    """Raw device pointer -> torch tensor without a copy (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def bus_tensor(dev):
+    """The engine's device bus [C * n_blocks * B] as a torch tensor aliasing the same memory."""
+    import torch
+    ptr, n = dev.device_bus()
+    return torch.as_tensor(_DevPtr(ptr, n), device="cuda")
+
+
+def mix_sharded(dev, dist, world):
+    """After dev.submit(...): mix this rank's shard, reduce the bus across ranks, clamp. All on dev's stream."""
+    from . import MIX_NO_CLAMP
+    dev.mix(MIX_NO_CLAMP if world > 1 else 0)
+    if world > 1:
+        ptr, n = dev.device_bus()
+        dist.all_reduce(bus_tensor(dev))  # the single exchange step: sum of the partial buses
+        dev.clamp_device(ptr, n)
+
+
+def clamp_bus(x):
+    """engine.cpp:1627-1636 on a host array (used by the CPU tests of the sharded path)."""
+    return np.where(x > np.float32(1.0), np.float32(1.0), np.where(x < np.float32(-1.0), np.float32(-1.0), x)).astype(np.float32)
