@@ -121,3 +121,31 @@ def test_runs_are_merged(wb):
     assert gains.shape == (3, 2)
     segs, _ = eng.schedule(4)  # continues where it left off
     assert len(segs) == 3 and all(segs["src_pos"] == 32 * 512.0)
+
+
+def test_no_fma_contraction_in_mix_kernels(wb):
+    """Parity depends on every multiply and add being separately rounded. nvcc -fmad=false covers scalar code,
+    but ptxas (12.9) still contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 when the product has a single use,
+    so lint the SASS: inside mix_kernel the only fused ops allowed are the intended `a * -1 + b` (= b - a)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", wb.LIB_PATH], capture_output=True, text=True).stdout
+    fn, bad, seen = None, [], 0
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+            continue
+        if fn and "mix_kernel" in fn:
+            seen += 1
+            body = line.split("/*")[1].split("*/")[-1] if line.count("/*") >= 2 else line
+            for op in ("FFMA2", "FFMA", "DFMA"):
+                if (" " + op + " ") in line or (" " + op + ".") in line:
+                    if op == "FFMA2" and ", -1, " in line:
+                        continue
+                    if op == "FFMA" and "FFMA2" not in line:
+                        continue  # integer-division helpers (work-item decode) use scalar FFMA on non-audio values
+                    bad.append((fn[:40], line.strip()[:90]))
+    assert seen > 1000, "mix_kernel SASS not found"
+    assert not bad, "fused multiply-adds on the audio path: %s" % bad[:5]

@@ -50,7 +50,9 @@ enum : uint32_t {
   K_SILENT = 0,
   K_FAST = 1,    // stereo f32, unity speed, whole tile, 16-B aligned window: 128-bit loads + packed f32x2 math
   K_GEN = 2,     // anything else whose window fits a stage: per-frame path on the staged window
-  K_DIRECT = 3   // window larger than a stage (speed well above 1): per-frame path straight from global
+  K_DIRECT = 3,  // window larger than a stage (speed well above 1): per-frame path straight from global
+  K_UNI = 4,     // stereo f32, unity speed, odd start frame or partial tile: 64-bit loads + packed math
+  K_LIN = 5      // stereo f32, 2-tap linear resample from the staged window, conversion-free position split
 };
 
 // Resolved per-(cell, tile) descriptor, lives in shared memory (64 B).

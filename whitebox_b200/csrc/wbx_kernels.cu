@@ -239,6 +239,79 @@ __device__ __forceinline__ void consume_fast(const uint8_t* row, float gain, flo
   }
 }
 
+// packed (L, R) version of `accumulate` for one frame
+__device__ __forceinline__ void accumulate2(float2 s, float2 g2, float2 t2, float2& acc, float& pkL, float& pkR) {
+  const float2 term = __fmul2_rn(__fmul2_rn(s, g2), t2);
+  acc = __fadd2_rn(acc, term);
+  pkL = fmaxf(pkL, fabsf(term.x));
+  pkR = fmaxf(pkR, fabsf(term.y));
+}
+
+// Stereo f32, unity speed, window not aligned to the tile (odd start frame, partial coverage): 64-bit shared
+// loads of (L, R) frames, packed math.
+template <int FPL>
+__device__ __forceinline__ void consume_uni(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
+                                            float& pkR, int lane) {
+  const float2* r2 = reinterpret_cast<const float2*>(row);
+  const int lo = d.lo, hi = d.hi;
+  const int shift = (int)((int64_t)(uint32_t)(int64_t)d.pos + d.jrel0 - d.base);  // window index of tile frame 0
+  const float2 g2 = make_float2(d.gain, d.gain);
+  const float2 t2 = make_float2(d.tg[0], d.tg[1]);
+#pragma unroll
+  for (int i = 0; i < FPL / 2; i++) {
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int fr = 2 * (lane + 32 * i) + e;
+      if (fr >= lo && fr < hi) accumulate2(r2[fr + shift], g2, t2, acc[i * 2 + e], pkL, pkR);
+    }
+  }
+}
+
+// Stereo f32, 2-tap linear resample (sample_linear<float, F32>, dsp/sampler.cpp:34-59) from the staged window.
+// The position split avoids the slow f64<->int conversions: for 0 <= x < 2^31, t = x + 2^52 rounded TOWARDS
+// -INF is exactly floor(x) + 2^52 (the ulp there is 1), so its low mantissa word is (int64_t)x and
+// x - (t - 2^52) is x - (double)ix — both subtractions exact — as in sampler.cpp:51-52.
+template <int FPL>
+__device__ __forceinline__ void consume_lin(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
+                                            float& pkR, int lane) {
+  const float2* r2 = reinterpret_cast<const float2*>(row);
+  const int lo = d.lo, hi = d.hi;
+  const float2* rb = r2 - d.base;
+  const double pos = d.pos, speed = d.speed;
+  const double M = 4503599627370496.0;  // 2^52
+  const double jj0 = (double)(d.jrel0 + 2 * lane);
+  const float2 g2 = make_float2(d.gain, d.gain);
+  const float2 t2 = make_float2(d.tg[0], d.tg[1]);
+  const float2 neg1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+  for (int i = 0; i < FPL / 2; i++) {
+    float2 term[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int fr = 2 * (lane + 32 * i) + e;
+      term[e] = make_float2(0.0f, 0.0f);
+      if (fr >= lo && fr < hi) {
+        const double jj = __dadd_rn(jj0, (double)(64 * i + e));  // exact small integers == (double)j
+        const double x = __dadd_rn(pos, __dmul_rn(jj, speed));   // sampler.cpp:50
+        const double t = __dadd_rd(x, M);                        // floor(x) + 2^52
+        const int ix = __double2loint(t);                        // (int64_t)x, :51
+        const float fx = __double2float_rn(__dsub_rn(x, __dsub_rn(t, M)));  // (float)(x - (double)ix), :52
+        const float2 a = rb[ix], b = rb[ix + 1];
+        const float2 df = __ffma2_rn(a, neg1, b);  // b - a (a * -1 is exact: one rounding)
+        // a + fx * (b - a), :55 — scalar _rn ops on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
+        // FFMA2 when the product has no other use, even under --fmad false (tests/test_host_cpu.py lints SASS)
+        float2 sv;
+        sv.x = __fadd_rn(a.x, __fmul_rn(fx, df.x));
+        sv.y = __fadd_rn(a.y, __fmul_rn(fx, df.y));
+        term[e] = __fmul2_rn(__fmul2_rn(sv, g2), t2);
+        acc[i * 2 + e] = __fadd2_rn(acc[i * 2 + e], term[e]);
+      }
+    }
+    pkL = fmaxf(fmaxf(pkL, fabsf(term[0].x)), fabsf(term[1].x));
+    pkR = fmaxf(fmaxf(pkR, fabsf(term[0].y)), fabsf(term[1].y));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the mix kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -333,8 +406,13 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
         d.src = (const uint8_t*)s.base + a * fbytes;
         d.base = (int32_t)a;
         d.bytes = (uint16_t)bytes;
-        const bool fast = two && unity && s.fmt == F_F32 && s.nch == 2 && lo == 0 && hi == T && first == a;
-        d.kind = fast ? K_FAST : K_GEN;
+        const bool st32 = two && s.fmt == F_F32 && s.nch == 2;  // stereo f32 source into a stereo bus
+        if (st32 && unity)
+          d.kind = (lo == 0 && hi == T && first == a) ? K_FAST : K_UNI;
+        else if (st32 && last < (int64_t)0x3fffffff)
+          d.kind = K_LIN;
+        else
+          d.kind = K_GEN;
       } else {  // window larger than a stage (speed well above 1): read the source straight from global
         d.src = s.base;
         d.kind = K_DIRECT;
@@ -418,7 +496,7 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
       while (ip < lim && (n_issued - n_consumed) < (uint32_t)STAGES) {
         const Desc* dd = &ring[ip & (L::RING - 1)];
         const uint32_t kind = dd->kind;
-        if (kind == K_FAST || kind == K_GEN) {
+        if (kind != K_SILENT && kind != K_DIRECT) {
           if (lane == 0) {
             const uint32_t st = n_issued % STAGES;
             const uint32_t bar = bars_s + 8 * st;
@@ -462,6 +540,10 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
           const uint8_t* row = wbase + (size_t)st * L::STAGE_BYTES;
           if (kind == K_FAST) {
             consume_fast<FPL>(row, dp->gain, dp->tg[0], dp->tg[1], acc, pkL, pkR, lane);
+          } else if (kind == K_UNI) {
+            consume_uni<FPL>(*dp, row, acc, pkL, pkR, lane);
+          } else if (kind == K_LIN) {
+            consume_lin<FPL>(*dp, row, acc, pkL, pkR, lane);
           } else {
             const Desc d = *dp;
             consume_gen<FPL>(d, kind == K_DIRECT ? d.src : (const void*)row, acc, pkL, pkR, lane, two);
