@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "wbx_device.cuh"
 
@@ -249,9 +250,9 @@ __device__ __forceinline__ void accumulate2(float2 s, float2 g2, float2 t2, floa
 
 // Stereo f32, unity speed, window not aligned to the tile (odd start frame, partial coverage): 64-bit shared
 // loads of (L, R) frames, packed math.
-template <int FPL>
-__device__ __forceinline__ void consume_uni(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
-                                            float& pkR, int lane) {
+template <int FPL, bool FULL>
+__device__ __forceinline__ void consume_uni_t(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
+                                              float& pkR, int lane) {
   const float2* r2 = reinterpret_cast<const float2*>(row);
   const int lo = d.lo, hi = d.hi;
   const int shift = (int)((int64_t)(uint32_t)(int64_t)d.pos + d.jrel0 - d.base);  // window index of tile frame 0
@@ -262,18 +263,27 @@ __device__ __forceinline__ void consume_uni(const Desc& d, const uint8_t* row, f
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const int fr = 2 * (lane + 32 * i) + e;
-      if (fr >= lo && fr < hi) accumulate2(r2[fr + shift], g2, t2, acc[i * 2 + e], pkL, pkR);
+      if (FULL || (fr >= lo && fr < hi)) accumulate2(r2[fr + shift], g2, t2, acc[i * 2 + e], pkL, pkR);
     }
   }
+}
+
+template <int FPL>
+__device__ __forceinline__ void consume_uni(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
+                                            float& pkR, int lane) {
+  if (d.lo == 0 && d.hi == 32 * FPL)  // whole tile: no per-frame range checks
+    consume_uni_t<FPL, true>(d, row, acc, pkL, pkR, lane);
+  else
+    consume_uni_t<FPL, false>(d, row, acc, pkL, pkR, lane);
 }
 
 // Stereo f32, 2-tap linear resample (sample_linear<float, F32>, dsp/sampler.cpp:34-59) from the staged window.
 // The position split avoids the slow f64<->int conversions: for 0 <= x < 2^31, t = x + 2^52 rounded TOWARDS
 // -INF is exactly floor(x) + 2^52 (the ulp there is 1), so its low mantissa word is (int64_t)x and
 // x - (t - 2^52) is x - (double)ix — both subtractions exact — as in sampler.cpp:51-52.
-template <int FPL>
-__device__ __forceinline__ void consume_lin(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
-                                            float& pkR, int lane) {
+template <int FPL, bool FULL>
+__device__ __forceinline__ void consume_lin_t(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
+                                              float& pkR, int lane) {
   const float2* r2 = reinterpret_cast<const float2*>(row);
   const int lo = d.lo, hi = d.hi;
   const float2* rb = r2 - d.base;
@@ -290,7 +300,7 @@ __device__ __forceinline__ void consume_lin(const Desc& d, const uint8_t* row, f
     for (int e = 0; e < 2; e++) {
       const int fr = 2 * (lane + 32 * i) + e;
       term[e] = make_float2(0.0f, 0.0f);
-      if (fr >= lo && fr < hi) {
+      if (FULL || (fr >= lo && fr < hi)) {
         const double jj = __dadd_rn(jj0, (double)(64 * i + e));  // exact small integers == (double)j
         const double x = __dadd_rn(pos, __dmul_rn(jj, speed));   // sampler.cpp:50
         const double t = __dadd_rd(x, M);                        // floor(x) + 2^52
@@ -310,6 +320,15 @@ __device__ __forceinline__ void consume_lin(const Desc& d, const uint8_t* row, f
     pkL = fmaxf(fmaxf(pkL, fabsf(term[0].x)), fabsf(term[1].x));
     pkR = fmaxf(fmaxf(pkR, fabsf(term[0].y)), fabsf(term[1].y));
   }
+}
+
+template <int FPL>
+__device__ __forceinline__ void consume_lin(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
+                                            float& pkR, int lane) {
+  if (d.lo == 0 && d.hi == 32 * FPL)  // whole tile: no per-frame range checks
+    consume_lin_t<FPL, true>(d, row, acc, pkL, pkR, lane);
+  else
+    consume_lin_t<FPL, false>(d, row, acc, pkL, pkR, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -753,7 +772,16 @@ static cudaError_t launch_mix_t(const MixParams& p, int n_sm, cudaStream_t strea
   return cudaGetLastError();
 }
 
+// 512-frame tiles: 2 stages x 8 warps per CTA (16 warps/SM, the register-file limit at 128 regs) measured faster
+// than 3 stages x 7 warps (14 warps/SM) on both cfg 2 (6.84 vs 6.42 TB/s) and cfg 3 (4.50 vs 4.42 TB/s);
+// WBX_VARIANT=a selects the latter for experiments.
+static int variant_b() {
+  const char* v = getenv("WBX_VARIANT");
+  return !(v && v[0] == 'a');
+}
+
 cudaError_t launch_mix(const MixParams& p, int fpl, int n_sm, cudaStream_t stream, int* ctas_out) {
+  if (fpl == 16 && variant_b()) return launch_mix_t<16, 2, 8>(p, n_sm, stream, ctas_out);
   switch (fpl) {
     case 16: return launch_mix_t<16, 3, 7>(p, n_sm, stream, ctas_out);
     case 8: return launch_mix_t<8, 3, 8>(p, n_sm, stream, ctas_out);
@@ -767,6 +795,7 @@ int mix_warps_per_sm(int fpl) {
     int ctas = (227 * 1024) / (warp_bytes * warps + 1024);
     return (ctas < 1 ? 1 : ctas) * warps;
   };
+  if (fpl == 16 && variant_b()) return per_sm(MixLayout<16, 2>::WARP_BYTES, 8);
   switch (fpl) {
     case 16: return per_sm(MixLayout<16, 3>::WARP_BYTES, 7);
     case 8: return per_sm(MixLayout<8, 3>::WARP_BYTES, 8);
