@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define WBX_ABI_VERSION 1
+#define WBX_ABI_VERSION 2
 
 typedef struct wbx_engine wbx_engine;
 
@@ -72,8 +72,21 @@ typedef struct wbx_segment {
   double src_pos;      /* Sampler::sample_offset_ at the first call */
   double speed;        /* Sampler::playback_speed_ = src_rate / dst_rate * clip speed (sampler.h:24), > 0 */
   float gain;          /* AudioClip::gain (engine/clip.h:44) */
-  uint32_t reserved;   /* must be 0 */
+  uint32_t flags;      /* WBX_SEG_FADE or 0 */
+  /* Fade envelope — EXTENSION, not in the reference: AudioClip::fade_start / fade_end (engine/clip.h:41-42)
+   * are stored and drawn by whitebox but no audio code reads them. Spec (oracle/wb_oracle.c, "parity unpinned"):
+   * for clip-relative output frame n = clip_frame + j,
+   *     env(n) = (float)( min(1, n / fade_in_frames) * min(1, max(0, (clip_len_frames - n) / fade_out_frames)) )
+   * (a factor is 1 when its length is <= 0) and the frame contributes (src * gain) * env. Ignored unless
+   * WBX_SEG_FADE is set; with both lengths 0 the path is the reference's, bit for bit. For a run,
+   * clip_frame advances by `length` per callback. */
+  double clip_frame;       /* output frames since the clip's start at this call's first frame (integer value) */
+  double fade_in_frames;   /* beat_to_samples(fade_start) */
+  double fade_out_frames;  /* beat_to_samples(fade_end) */
+  double clip_len_frames;  /* beat_to_samples(max_time - min_time) */
 } wbx_segment;
+
+#define WBX_SEG_FADE 1u
 
 /* Bus summation order (wbx_set_sum_mode). */
 typedef enum wbx_sum_mode {

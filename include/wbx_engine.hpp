@@ -38,6 +38,7 @@ struct AudioClip {  // engine/clip.h:39-45 + Clip time placement (:68-70)
   double start_offset = 0;            // source frames
   double speed = 1.0;
   float gain = 1.0f;
+  double fade_start = 0, fade_end = 0;  // beats (engine/clip.h:41-42); extension: the reference never reads them
   uint32_t sample_id = 0;
   uint32_t sample_rate = 0;
   bool internal_state_changed = false;
@@ -50,6 +51,7 @@ struct AudioEvent {  // engine/event.h:66-74
   uint32_t buffer_offset = 0;
   double time = 0, speed = 0;
   uint64_t sample_offset = 0;
+  uint64_t clip_frame = 0;  // output frames since the clip's start (fade extension)
   const AudioClip* clip = nullptr;
 };
 
@@ -65,6 +67,7 @@ struct Track {
   AudioEvent current_audio_event;
   // dsp::Sampler state (dsp/sampler.h:14-16); the device replays the same recurrence
   double playback_speed = 0, sample_offset = 0;
+  uint64_t clip_frame = 0;  // output frames since the playing clip's start (fade extension)
   TrackParameterState ui_parameter_state, parameter_state;
   struct Msg {
     uint32_t id;
@@ -100,7 +103,7 @@ class Engine {
   int add_sample(int format, uint32_t channels, uint64_t frames, uint32_t sample_rate, const void* const* planar);
   // engine/engine.cpp:293-309 + add_to_cliplist (:409-461) for clips that do not overlap an existing one.
   int add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
-                     double speed, float gain);
+                     double speed, float gain, double fade_start = 0.0, double fade_end = 0.0);
   void play();  // engine/engine.cpp:68-80
   void stop();  // :82-92
 
@@ -135,11 +138,13 @@ class Engine {
   void track_block(Track& t, uint32_t track_index, uint32_t block, double sample_rate, double beat_duration,
                    double start_time, double end_time, double block_sample_position, bool currently_playing);
   uint32_t quiet_blocks(const Track& t, uint32_t k, uint32_t K) const;
+  void fill_fade(wbx_segment& s, const AudioClip* clip, uint64_t clip_frame) const;
   void stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t q);
   std::vector<double> blk_start_, blk_end_, blk_spos_;  // per-callback transport of the current schedule()
   wbx_engine* dev_ = nullptr;
   bool host_only_ = false;
   uint32_t out_channels_ = 2, buffer_size_ = 512, sample_rate_ = 48000;
+  double cur_sample_rate_ = 48000.0;  // sample rate of the schedule() in progress
   double beat_duration_ = 0.5;
   struct SampleInfo {
     uint64_t count;

@@ -34,6 +34,10 @@ int wbxh_add_sample(wbxh_engine* h, int format, uint32_t channels, uint64_t fram
                     const void* const* planar);
 int wbxh_add_clip(wbxh_engine* h, int track, int sample, double min_beat, double max_beat, double start_offset,
                   double speed, float gain);
+/* as wbxh_add_clip plus AudioClip::fade_start / fade_end in beats (engine/clip.h:41-42) — the fade EXTENSION
+ * specified in wbx.h; (0, 0) is the reference path. */
+int wbxh_add_clip_fade(wbxh_engine* h, int track, int sample, double min_beat, double max_beat, double start_offset,
+                       double speed, float gain, double fade_start, double fade_end);
 void wbxh_set_playhead(wbxh_engine* h, double beat);
 void wbxh_play(wbxh_engine* h);
 void wbxh_stop(wbxh_engine* h);

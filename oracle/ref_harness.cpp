@@ -90,6 +90,17 @@ int wbo_add_clip(wbo_session* s, int track, int sample, double min_beat, double 
   return 0;
 }
 
+int wbo_add_clip_fade(wbo_session* s, int track, int sample, double min_beat, double max_beat, double start_offset,
+                      double speed, float gain, double fade_start, double fade_end) {
+  SampleAsset* asset = s->samples[sample];
+  asset->add_ref();
+  // the fields are stored (clip.h:41-42) — and ignored by every audio path of the reference
+  s->engine.add_audio_clip(
+      s->engine.tracks[track], "c", min_beat, max_beat, start_offset,
+      AudioClip{ .asset = asset, .fade_start = fade_start, .fade_end = fade_end, .speed = speed, .gain = gain });
+  return 0;
+}
+
 void wbo_set_playhead(wbo_session* s, double beat) { s->engine.set_playhead_position(beat); }
 void wbo_play(wbo_session* s) { s->engine.play(); }
 void wbo_stop(wbo_session* s) { s->engine.stop(); }

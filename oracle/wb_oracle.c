@@ -41,6 +41,7 @@ typedef struct {
   double min_time, max_time, start_offset; /* clip.h:68-70 */
   double speed;                            /* AudioClip::speed clip.h:43 */
   float gain;                              /* AudioClip::gain  clip.h:44 */
+  double fade_start, fade_end;             /* AudioClip::fade_start/fade_end clip.h:41-42 (EXTENSION, see fade_env) */
   o_sample* sample;
   int internal_state_changed; /* clip.h:62 — only UI edits set it */
 } o_clip;
@@ -52,6 +53,7 @@ typedef struct { /* AudioEvent, event.h:66-74 */
   uint32_t buffer_offset;
   double time, speed;
   size_t sample_offset;
+  uint64_t clip_frame; /* EXTENSION: output frames since the clip's start when the event fires */
   o_clip* clip;
   o_sample* sample;
 } o_event;
@@ -73,6 +75,7 @@ typedef struct {
   o_event current; /* Track::current_audio_event, track.h:118 */
   /* dsp::Sampler, sampler.h:14-16 */
   double playback_speed, sample_offset;
+  uint64_t clip_frame; /* EXTENSION: output frames since the playing clip's start */
   /* parameter_state, track.h:46-53 */
   float volume, pan, pan_coeffs[2];
   int mute;
@@ -269,6 +272,11 @@ static void reset_playback_state(o_track* tr, double time_pos, int refresh_voice
  * reset_playback_state(playhead, true). */
 int wbo_add_clip(wbo_session* s, int track, int sample, double min_beat, double max_beat, double start_offset,
                  double speed, float gain) {
+  return wbo_add_clip_fade(s, track, sample, min_beat, max_beat, start_offset, speed, gain, 0.0, 0.0);
+}
+
+int wbo_add_clip_fade(wbo_session* s, int track, int sample, double min_beat, double max_beat, double start_offset,
+                      double speed, float gain, double fade_start, double fade_end) {
   o_track* tr = s->tracks[track];
   for (uint32_t i = 0; i < tr->n_clips; i++) /* Track::query_clip_by_range (track.cpp:112-160) finds one */
     if (min_beat < tr->clips[i]->max_time && max_beat > tr->clips[i]->min_time) return -1;
@@ -278,6 +286,8 @@ int wbo_add_clip(wbo_session* s, int track, int sample, double min_beat, double 
   c->start_offset = start_offset;
   c->speed = speed;
   c->gain = gain;
+  c->fade_start = fade_start;
+  c->fade_end = fade_end;
   c->sample = s->samples[sample];
   if (tr->n_clips == tr->cap_clips) {
     tr->cap_clips = tr->cap_clips ? tr->cap_clips * 2 : 4;
@@ -336,9 +346,11 @@ static void push_stop(o_track* tr, uint32_t buffer_offset, double time) {
   push_event(tr, e);
 }
 
-static void push_play(o_track* tr, uint32_t buffer_offset, double time, o_clip* clip, size_t sample_offset) {
+static void push_play(o_track* tr, uint32_t buffer_offset, double time, o_clip* clip, size_t sample_offset,
+                      uint64_t clip_frame) {
   o_event e;
   memset(&e, 0, sizeof(e));
+  e.clip_frame = clip_frame;
   e.type = EV_PLAY;
   e.buffer_offset = buffer_offset;
   e.time = time;
@@ -405,20 +417,20 @@ static void process_event(o_track* tr, double start_time, double end_time, doubl
       double offset_from_start = beat_to_samples(min_time - start_time, sample_rate, beat_duration);
       double sample_offset = sample_position + offset_from_start;
       uint32_t buffer_offset = (uint32_t)((uint64_t)sample_offset % (uint64_t)buffer_size);
-      push_play(tr, buffer_offset, min_time, clip, (size_t)clip->start_offset);
+      push_play(tr, buffer_offset, min_time, clip, (size_t)clip->start_offset, 0);
       clip->internal_state_changed = 0;
     } else if (start_time > min_time && !tr->partially_ended) { /* started in the middle, :376-395 */
       double relative_start_time = start_time - min_time;
       double sample_pos = beat_to_samples(relative_start_time, sample_rate, beat_duration);
       size_t sample_offset = (size_t)(clip->start_offset + (sample_pos * clip->speed));
-      push_play(tr, 0, start_time, clip, sample_offset);
+      push_play(tr, 0, start_time, clip, sample_offset, (uint64_t)sample_pos);
       clip->internal_state_changed = 0;
     } else if (clip->internal_state_changed && tr->partially_ended) { /* :396-421 */
       double relative_start_time = start_time - min_time;
       double sample_pos = beat_to_samples(relative_start_time, sample_rate, beat_duration);
       size_t sample_offset = (size_t)(clip->start_offset + (sample_pos * clip->speed));
       push_stop(tr, 0, start_time);
-      push_play(tr, 0, start_time, clip, sample_offset);
+      push_play(tr, 0, start_time, clip, sample_offset, (uint64_t)sample_pos);
       clip->internal_state_changed = 0;
     }
 
@@ -542,6 +554,57 @@ static void sampler_stream(o_track* tr, o_sample* sm, uint32_t num_channels, uin
   tr->sample_offset = next_sample_offset; /* :209 */
 }
 
+/* ---- EXTENSION (parity unpinned w.r.t. whitebox): clip fade envelope ------------------------------------- */
+/* The reference stores AudioClip::fade_start / fade_end (clip.h:41-42, project.cpp:189-190) and draws the
+ * handles, but no audio code reads them. Builder's specification, shared with include/wbx.h:
+ *   n     clip-relative OUTPUT frame (0 at the clip's first rendered frame; a mid-clip start begins at
+ *         (uint64)beat_to_samples(start_time - min_time), like the sample offset of track.cpp:378-379)
+ *   Fin   beat_to_samples(fade_start), Fout = beat_to_samples(fade_end), L = beat_to_samples(max_time - min_time)
+ *   env   (float)( (Fin > 0 ? min(1, n / Fin) : 1) * (Fout > 0 ? min(1, max(0, (L - n) / Fout)) : 1) )   [f64 math]
+ *   frame (src * gain) * env     — env == 1.0f leaves the reference's value untouched, so (0, 0) fades are the
+ *                                  reference path bit for bit. */
+static float fade_env(double n, double fin, double fout, double len) {
+  double e = 1.0;
+  if (fin > 0.0) {
+    double r = n / fin;
+    e = r < 1.0 ? r : 1.0;
+  }
+  if (fout > 0.0) {
+    double r = (len - n) / fout;
+    r = r > 0.0 ? r : 0.0;
+    r = r < 1.0 ? r : 1.0;
+    e = e * r;
+  }
+  return (float)e;
+}
+
+/* One Sampler::stream call as Track::process issues it, plus the fade extension. The mixing buffer holds 0 in
+ * the frames a call writes (one voice per track), so scaling what the call just added is exactly
+ * (0 + src * gain) * env. */
+static void track_stream(wbo_session* s, o_track* tr, uint32_t num_samples, uint32_t buffer_offset, float** out) {
+  o_clip* clip = tr->current.clip;
+  o_sample* sm = tr->current.sample;
+  const uint64_t clip_frame = tr->clip_frame;
+  tr->clip_frame += num_samples;
+  if (!(clip->fade_start > 0.0 || clip->fade_end > 0.0)) {
+    sampler_stream(tr, sm, s->C, num_samples, buffer_offset, clip->gain, out);
+    return;
+  }
+  if (tr->sample_offset >= (double)sm->count) return;
+  double stream_max_length = ((double)sm->count - tr->sample_offset) / tr->playback_speed;
+  uint32_t ceil_len = (uint32_t)ceil(stream_max_length);
+  uint32_t n = num_samples < ceil_len ? num_samples : ceil_len;
+  sampler_stream(tr, sm, s->C, num_samples, buffer_offset, clip->gain, out);
+  const double rate = (double)s->rate;
+  const double fin = beat_to_samples(clip->fade_start, rate, s->beat_duration);
+  const double fout = beat_to_samples(clip->fade_end, rate, s->beat_duration);
+  const double len = beat_to_samples(clip->max_time - clip->min_time, rate, s->beat_duration);
+  for (uint32_t j = 0; j < n; j++) {
+    const float env = fade_env((double)clip_frame + (double)j, fin, fout, len);
+    for (uint32_t c = 0; c < s->C; c++) out[c][buffer_offset + j] = out[c][buffer_offset + j] * env;
+  }
+}
+
 /* ---- Track::process (engine/track.cpp:587-736) ---------------------------------------------------------- */
 
 static void track_process(wbo_session* s, o_track* tr, float** out, double sample_rate, double beat_duration,
@@ -578,17 +641,17 @@ static void track_process(wbo_session* s, o_track* tr, float** out, double sampl
           event_length = 0;
           if (tr->current.type == EV_PLAY) tr->current.type = EV_NONE;
         }
-        if (tr->current.type == EV_PLAY)
-          sampler_stream(tr, tr->current.sample, s->C, event_length, start_sample, tr->current.clip->gain, out);
-        if (ne->type == EV_PLAY)
+        if (tr->current.type == EV_PLAY) track_stream(s, tr, event_length, start_sample, out);
+        if (ne->type == EV_PLAY) {
           sampler_reset(tr, (double)ne->sample_offset, ne->speed, (double)ne->sample->rate, sample_rate);
+          tr->clip_frame = ne->clip_frame;
+        }
         tr->current = *ne;
         start_sample += event_length;
         next++;
       } else {
         uint32_t event_length = B - start_sample;
-        if (tr->current.type == EV_PLAY)
-          sampler_stream(tr, tr->current.sample, s->C, event_length, start_sample, tr->current.clip->gain, out);
+        if (tr->current.type == EV_PLAY) track_stream(s, tr, event_length, start_sample, out);
         start_sample = B;
       }
     }

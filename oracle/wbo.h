@@ -44,6 +44,15 @@ int wbo_add_sample(wbo_session*, int format, uint32_t channels, uint64_t frames,
 int wbo_add_clip(wbo_session*, int track, int sample, double min_beat, double max_beat, double start_offset,
                  double speed, float gain);
 
+/* As wbo_add_clip, also setting AudioClip::fade_start / fade_end (beats, engine/clip.h:41-42).
+ * EXTENSION — PARITY UNPINNED w.r.t. whitebox: the reference stores these fields but no audio code reads them,
+ * so libwbref.so renders such a clip WITHOUT a fade; the port implements the builder's specification
+ * (wb_oracle.c fade_env): for clip-relative output frame n,
+ *   env(n) = (float)(min(1, n / Fin) * min(1, max(0, (L - n) / Fout))),  a factor is 1 when its length <= 0,
+ *   Fin/Fout/L = beat_to_samples(fade_start / fade_end / max_time - min_time); frame value (src * gain) * env. */
+int wbo_add_clip_fade(wbo_session*, int track, int sample, double min_beat, double max_beat, double start_offset,
+                      double speed, float gain, double fade_start, double fade_end);
+
 void wbo_set_playhead(wbo_session*, double beat); /* Engine::set_playhead_position */
 void wbo_play(wbo_session*);                      /* Engine::play */
 void wbo_stop(wbo_session*);                      /* Engine::stop */

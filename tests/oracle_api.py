@@ -35,6 +35,7 @@ def _load(path):
     lib.wbo_set_mute.argtypes = [vp, i32, i32]
     lib.wbo_add_sample.argtypes = [vp, i32, u32, u64, u32, C.POINTER(vp)]
     lib.wbo_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
+    lib.wbo_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
     lib.wbo_set_playhead.argtypes = [vp, dbl]
     lib.wbo_play.argtypes = [vp]
     lib.wbo_stop.argtypes = [vp]
@@ -106,7 +107,11 @@ class Session:
         ptrs = (C.c_void_p * ch)(*[data[c].ctypes.data for c in range(ch)])
         return self.lib.wbo_add_sample(self.h, fmt, ch, frames, rate, ptrs)
 
-    def add_clip(self, track, sample, min_beat, max_beat, start_offset=0.0, speed=1.0, gain=1.0):
+    def add_clip(self, track, sample, min_beat, max_beat, start_offset=0.0, speed=1.0, gain=1.0, fade_start=0.0,
+                 fade_end=0.0):
+        if fade_start or fade_end:
+            return self.lib.wbo_add_clip_fade(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain,
+                                              fade_start, fade_end)
         return self.lib.wbo_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain)
 
     def set_playhead(self, beat):

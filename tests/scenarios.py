@@ -222,6 +222,34 @@ def empty(make_engine):
     return dict(out=np.concatenate([a[0], b[0]]), peaks=b[1])
 
 
+def fades(make_engine):
+    """EXTENSION scenario (parity unpinned w.r.t. whitebox — the reference has no fades): fade-in / fade-out
+    ramps on unity, resampled, mono and int16 clips, ramps longer than the clip, a mid-clip start inside a ramp."""
+    rng = np.random.RandomState(606)
+    B, rate = 256, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    spb = rate * 0.5
+    cfgs = [  # (channels, src_rate, fmt, start_frame, length_frames, speed, fade_in_frames, fade_out_frames)
+        (2, 48000, FMT_F32, 0, 2000, 1.0, 700, 500),
+        (2, 44100, FMT_F32, 100, 1800, 1.0, 300, 0),
+        (1, 48000, FMT_F32, 37, 1500, 1.0, 0, 1000),
+        (2, 48000, FMT_I16, 0, 900, 1.0, 2000, 2000),   # ramps longer than the clip: they overlap
+        (2, 48000, FMT_F32, 256, 1024, 0.5, 256, 256),
+        (2, 96000, FMT_F32, 10, 2200, 1.0, 1, 3),
+    ]
+    for t, (ch, sr, fmt, start, length, speed, fi, fo) in enumerate(cfgs):
+        eng.add_track(-2.0 - t, -0.6 + 0.25 * t, False)
+        sid = eng.add_sample(_src(rng, ch, 6000, 6, fmt), sr, fmt)
+        eng.add_clip(t, sid, start / spb, (start + length) / spb, 3.0, speed, 0.9, fi / spb, fo / spb)
+    eng.play()
+    outs = [eng.process(5), eng.process(6)]
+    eng.stop()
+    eng.set_playhead(333.0 / spb)  # inside several fade-ins
+    eng.play()
+    outs.append(eng.process(4))
+    return _collect(eng, outs, len(cfgs))
+
+
 def fuzz(make_engine, seed):
     """Random session: random rates / formats / speeds / clip layouts / block size, params changed mid-run."""
     rng = np.random.RandomState(1000 + seed)
@@ -263,6 +291,8 @@ def fuzz(make_engine, seed):
             eng.set_mute(t, bool(rng.rand() < 0.5))
     return _collect(eng, outs, n_tracks)
 
+
+EXT = dict(fades=fades)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
            event_split=event_split, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)

@@ -34,6 +34,20 @@ def _lin(data, fmt, idx):
     return (norm * v.astype(np.float64)).astype(f32)
 
 
+def _env(n, fin, fout, ln):
+    """fade extension (include/wbx.h): envelope of clip-relative output frames n (float64 array)."""
+    e = np.ones_like(n)
+    if fin > 0.0:
+        r = n / fin
+        e = np.where(r < 1.0, r, 1.0)
+    if fout > 0.0:
+        r = (ln - n) / fout
+        r = np.where(r > 0.0, r, 0.0)
+        r = np.where(r < 1.0, r, 1.0)
+        e = e * r
+    return e.astype(f32)
+
+
 def render(segs, gains, samples, C, B, n_blocks, n_tracks, clamp=True):
     """samples: {id: (data[ch][frames], fmt)} -> (out [K][C][B], peaks [K][N][2])"""
     mix = np.zeros((n_blocks, n_tracks, C, B), f32)
@@ -61,7 +75,12 @@ def render(segs, gains, samples, C, B, n_blocks, n_tracks, clamp=True):
                     a, bb = _lin(ch, fmt, ix), _lin(ch, fmt, ix + 1)
                     v = (a + fx * (bb - a)).astype(f32)
                 d0 = int(s["dst_offset"])
-                mix[k, int(s["track"]), c, d0:d0 + n_act] += (v * gain).astype(f32)
+                m = (v * gain).astype(f32)
+                if int(s["flags"]) & 1:
+                    nn = float(s["clip_frame"]) + float(b) * float(length) + j.astype(np.float64)
+                    m = (m * _env(nn, float(s["fade_in_frames"]), float(s["fade_out_frames"]),
+                                  float(s["clip_len_frames"]))).astype(f32)
+                mix[k, int(s["track"]), c, d0:d0 + n_act] += m
             pos = pos + float(length) * speed
     g = np.asarray(gains, f32).reshape(n_tracks, 2)
     out = np.zeros((n_blocks, C, B), f32)

@@ -100,6 +100,14 @@ def test_golden_every_tile_shape(wb, golden_dir, name, fpl, monkeypatch):
     assert_exact(sc.ALL[name](gpu_engine(wb, True)), gold, "%s fpl=%s" % (name, fpl))
 
 
+@pytest.mark.parametrize("batched", [True, False])
+def test_fade_extension_vs_port(wb, batched):
+    """EXTENSION, parity unpinned w.r.t. whitebox (the reference has no fades): CUDA == the C port's
+    specification of the fade envelope, bit for bit; and a (0, 0) fade is the reference path."""
+    ref = sc.fades(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm))
+    assert_exact(sc.fades(gpu_engine(wb, batched)), ref, "fades")
+
+
 def test_scalars_and_interleave(wb, golden_dir):
     g = np.load(os.path.join(golden_dir, "scalars.npz"))
     planar = g["planar"] + np.float32(0)  # the bus starts at +0, so a -0.0 source sample mixes to +0.0
@@ -195,7 +203,7 @@ def big(wb):
     for t in range(N):
         x = ((rng.random((2, frames), dtype=np.float32) * 2 - 1) * np.float32(0.5 / 32)).astype(np.float32)
         sid = dev.sample_upload(x, 48000)
-        segs[t] = (t, 0, K, 0, B, sid, 0.0, 1.0, 0.5 + 0.001 * (t % 512), 0)
+        segs[t] = (t, 0, K, 0, B, sid, 0.0, 1.0, 0.5 + 0.001 * (t % 512), 0, 0.0, 0.0, 0.0, 0.0)
     gains = np.stack([np.float32(0.15) + np.float32(0.001) * (np.arange(N) % 97),
                       np.float32(0.3) - np.float32(0.0005) * (np.arange(N) % 89)], axis=1).astype(np.float32)
     return dict(dev=dev, segs=segs, gains=gains, N=N, K=K, B=B)
@@ -260,7 +268,7 @@ def test_errors_are_reported(wb):
     dev.configure(2, 512, 48000)
     dev.set_track_count(2)
     segs = np.zeros(1, wb.SEGMENT_DTYPE)
-    segs[0] = (5, 0, 1, 0, 512, 0, 0.0, 1.0, 1.0, 0)  # track out of range, unknown sample
+    segs[0] = (5, 0, 1, 0, 512, 0, 0.0, 1.0, 1.0, 0, 0.0, 0.0, 0.0, 0.0)  # track out of range, unknown sample
     with pytest.raises(wb.WbxError):
         dev.submit(segs, np.ones((2, 2), np.float32), 1)
     with pytest.raises(wb.WbxError):

@@ -37,12 +37,13 @@ def test_library_exports_every_declared_symbol(wb):
         assert sorted(listed) == declared, "python symbol list out of date for " + header
         for name in declared:
             assert hasattr(L, name), "%s declared in %s but not exported" % (name, header)
-    assert L.wbx_abi_version() == 1
+    assert L.wbx_abi_version() == 2
 
 
 def test_segment_struct_layout(wb):
-    assert ctypes.sizeof(wb.Segment) == 48 and wb.SEGMENT_DTYPE.itemsize == 48
-    for f in ("track", "block", "n_blocks", "dst_offset", "length", "sample_id", "src_pos", "speed", "gain"):
+    assert ctypes.sizeof(wb.Segment) == 80 and wb.SEGMENT_DTYPE.itemsize == 80
+    for f in ("track", "block", "n_blocks", "dst_offset", "length", "sample_id", "src_pos", "speed", "gain", "flags",
+              "clip_frame", "fade_in_frames", "fade_out_frames", "clip_len_frames"):
         assert getattr(wb.Segment, f).offset == wb.SEGMENT_DTYPE.fields[f][1]
 
 
@@ -106,6 +107,17 @@ def test_host_scheduler_matches_port_fuzz(wb):
             assert _same(res[k], ref[k]), "fuzz%d: %s" % (seed, k)
         ran += 1
     assert ran > 35
+
+
+@pytest.mark.parametrize("batched", [True, False])
+def test_fade_extension_host_matches_port(wb, batched):
+    """EXTENSION (parity unpinned w.r.t. whitebox): the product's scheduler + documented segment semantics
+    reproduce the C port's fade specification bit for bit."""
+    import oracle_api as o
+    ref = sc.fades(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm))
+    res = sc.fades(lambda C, B, r, bpm: sr.ScheduleOnlyEngine(C, B, r, bpm, batched))
+    for k in ref:
+        assert _same(res[k], ref[k]), k
 
 
 def test_runs_are_merged(wb):

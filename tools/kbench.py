@@ -34,7 +34,7 @@ def main():
     t0 = time.time()
     for t in range(N):
         sid = dev.sample_upload(np.roll(base, t * 17, axis=1), args.rate)
-        segs[t] = (t, 0, K, 0, B, sid, float(args.offset), speed, 0.5 + 0.001 * (t % 512), 0)
+        segs[t] = (t, 0, K, 0, B, sid, float(args.offset), speed, 0.5 + 0.001 * (t % 512), 0, 0.0, 0.0, 0.0, 0.0)
     gains = np.full((N, 2), 0.7, np.float32)
     print("setup %.1fs, %.2f GiB" % (time.time() - t0, N * 2 * frames * 4 / 2**30), flush=True)
     stream = torch.cuda.Stream()

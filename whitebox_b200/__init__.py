@@ -23,13 +23,16 @@ class Segment(C.Structure):
     """wbx_segment (include/wbx.h)."""
     _fields_ = [("track", C.c_uint32), ("block", C.c_uint32), ("n_blocks", C.c_uint32), ("dst_offset", C.c_uint32),
                 ("length", C.c_uint32), ("sample_id", C.c_uint32), ("src_pos", C.c_double), ("speed", C.c_double),
-                ("gain", C.c_float), ("reserved", C.c_uint32)]
+                ("gain", C.c_float), ("flags", C.c_uint32), ("clip_frame", C.c_double), ("fade_in_frames", C.c_double),
+                ("fade_out_frames", C.c_double), ("clip_len_frames", C.c_double)]
 
 
 SEGMENT_DTYPE = np.dtype([("track", "<u4"), ("block", "<u4"), ("n_blocks", "<u4"), ("dst_offset", "<u4"),
                           ("length", "<u4"), ("sample_id", "<u4"), ("src_pos", "<f8"), ("speed", "<f8"),
-                          ("gain", "<f4"), ("reserved", "<u4")])
-assert SEGMENT_DTYPE.itemsize == C.sizeof(Segment) == 48
+                          ("gain", "<f4"), ("flags", "<u4"), ("clip_frame", "<f8"), ("fade_in_frames", "<f8"),
+                          ("fade_out_frames", "<f8"), ("clip_len_frames", "<f8")])
+assert SEGMENT_DTYPE.itemsize == C.sizeof(Segment) == 80
+SEG_FADE = 1
 
 # every symbol include/wbx.h and include/wbx_host.h declare
 WBX_SYMBOLS = [
@@ -40,7 +43,8 @@ WBX_SYMBOLS = [
 ]
 WBXH_SYMBOLS = [
     "wbxh_create", "wbxh_destroy", "wbxh_last_error", "wbxh_device", "wbxh_add_track", "wbxh_set_volume",
-    "wbxh_set_pan", "wbxh_set_mute", "wbxh_add_sample", "wbxh_add_clip", "wbxh_set_playhead", "wbxh_play",
+    "wbxh_set_pan", "wbxh_set_mute", "wbxh_add_sample", "wbxh_add_clip", "wbxh_add_clip_fade", "wbxh_set_playhead",
+    "wbxh_play",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
 ]
@@ -107,6 +111,7 @@ def lib():
     L.wbxh_set_mute.restype = None
     L.wbxh_add_sample.argtypes = [vp, i32, u32, u64, u32, pp]
     L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
+    L.wbxh_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
     L.wbxh_set_playhead.argtypes = [vp, dbl]
     L.wbxh_set_playhead.restype = None
     for f in ("wbxh_play", "wbxh_stop"):
@@ -352,7 +357,11 @@ class Engine:
         assert all(c.flags["C_CONTIGUOUS"] and c.dtype == _NP[fmt] and c.size == channels[0].size for c in channels)
         return self._ck(self.L.wbxh_add_sample(self.h, fmt, len(channels), channels[0].size, rate, ptrs))
 
-    def add_clip(self, track, sample, min_beat, max_beat, start_offset=0.0, speed=1.0, gain=1.0):
+    def add_clip(self, track, sample, min_beat, max_beat, start_offset=0.0, speed=1.0, gain=1.0, fade_start=0.0,
+                 fade_end=0.0):
+        if fade_start or fade_end:
+            return self._ck(self.L.wbxh_add_clip_fade(self.h, track, sample, min_beat, max_beat, start_offset, speed,
+                                                      gain, fade_start, fade_end))
         return self._ck(self.L.wbxh_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain))
 
     def set_playhead(self, beat):

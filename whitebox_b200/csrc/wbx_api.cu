@@ -325,7 +325,9 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
       return fail(e, WBX_ERR_INVALID, "segment %u: unknown sample %u", i, sg.sample_id);
     if (!(sg.speed > 0.0) || !(sg.src_pos >= 0.0) || !(sg.speed < 1e6))
       return fail(e, WBX_ERR_INVALID, "segment %u: speed/src_pos must be positive and finite", i);
-    if (sg.reserved != 0) return fail(e, WBX_ERR_INVALID, "segment %u: reserved must be 0", i);
+    if (sg.flags & ~WBX_SEG_FADE) return fail(e, WBX_ERR_INVALID, "segment %u: unknown flags 0x%x", i, sg.flags);
+    if ((sg.flags & WBX_SEG_FADE) && !(sg.clip_frame >= 0.0 && sg.clip_frame < 9.0e15 && sg.clip_len_frames >= 0.0))
+      return fail(e, WBX_ERR_INVALID, "segment %u: bad fade parameters", i);
     const SampleRec& sm = e->samples[sg.sample_id];
     // slot = first one free at sg.block for this track (segments of a track arrive in block order)
     uint32_t slot = 0;
@@ -356,7 +358,11 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     d.fmt = sm.fmt;
     d.slot = slot;
     d.nch = sm.nch;
-    d.pad = 0;
+    d.fade = (sg.flags & WBX_SEG_FADE) ? 1u : 0u;
+    d.clip_frame = d.fade ? sg.clip_frame : 0.0;
+    d.fade_in = d.fade ? sg.fade_in_frames : 0.0;
+    d.fade_out = d.fade ? sg.fade_out_frames : 0.0;
+    d.clip_len = d.fade ? sg.clip_len_frames : 0.0;
   }
   if (N) memcpy(e->h_gains.p, track_gains, (size_t)N * 2 * sizeof(float));
 

@@ -34,9 +34,10 @@ struct __align__(16) DSpan {
   uint32_t fmt;   // wbx_format
   uint32_t slot;  // which of the `slots` cells of (block, track) this span writes
   uint32_t nch;   // channels stored on the device (1 or 2)
-  uint32_t pad;
+  uint32_t fade;  // WBX_SEG_FADE: the envelope fields below apply
+  double clip_frame, fade_in, fade_out, clip_len;  // fade extension (include/wbx.h), in output frames
 };
-static_assert(sizeof(DSpan) == 80, "DSpan layout");
+static_assert(sizeof(DSpan) == 112, "DSpan layout");
 
 struct __align__(16) DCell {
   double pos;      // sample_offset_ when the call is made
@@ -52,7 +53,9 @@ enum : uint32_t {
   K_GEN = 2,     // anything else whose window fits a stage: per-frame path on the staged window
   K_DIRECT = 3,  // window larger than a stage (speed well above 1): per-frame path straight from global
   K_UNI = 4,     // stereo f32, unity speed, odd start frame or partial tile: 64-bit loads + packed math
-  K_LIN = 5      // stereo f32, 2-tap linear resample from the staged window, conversion-free position split
+  K_LIN = 5,     // stereo f32, 2-tap linear resample from the staged window, conversion-free position split
+  K_FADE = 6,        // a fade ramp overlaps this tile: per-frame path times the envelope (staged window)
+  K_DIRECT_FADE = 7  // K_DIRECT with a fade ramp
 };
 
 // Resolved per-(cell, tile) descriptor, lives in shared memory (64 B).
@@ -69,7 +72,8 @@ struct __align__(16) Desc {
   uint16_t bytes;  // bytes to stage (multiple of 16)
   uint8_t kind;
   uint8_t fmt;     // wbx_format | 0x80 when the device copy has one channel (both outputs read it)
-  uint32_t pad[2];
+  uint32_t span;   // span index (K_FADE reads the envelope parameters from it)
+  uint32_t block_in_run;  // callbacks since the run's first one (clip_frame advances by length per callback)
 };
 static_assert(sizeof(Desc) == 64, "Desc layout");
 

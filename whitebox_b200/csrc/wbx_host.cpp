@@ -153,7 +153,7 @@ int Engine::add_sample(int format, uint32_t channels, uint64_t frames, uint32_t 
 }
 
 int Engine::add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
-                           double speed, float gain) {
+                           double speed, float gain, double fade_start, double fade_end) {
   if (!track || sample_id >= samples_.size() || !(max_time >= min_time)) return WBX_ERR_INVALID;
   for (auto* c : track->clips)  // the reference would trim/split here (Engine::reserve_track_region): out of scope
     if (min_time < c->max_time && max_time > c->min_time) return WBX_ERR_UNSUPPORTED;
@@ -163,6 +163,8 @@ int Engine::add_audio_clip(Track* track, double min_time, double max_time, doubl
   clip->start_offset = start_offset;
   clip->speed = speed;
   clip->gain = gain;
+  clip->fade_start = fade_start;
+  clip->fade_end = fade_end;
   clip->sample_id = sample_id;
   clip->sample_rate = samples_[sample_id].rate;
   auto pos = std::upper_bound(track->clips.begin(), track->clips.end(), clip,
@@ -197,13 +199,15 @@ void Engine::process_event(Track& t, double start_time, double end_time, double 
     e.time = time;
     t.audio_event_buffer.push_back(e);
   };
-  auto push_play = [&](uint32_t off, double time, const AudioClip* clip, uint64_t sample_offset) {
+  auto push_play = [&](uint32_t off, double time, const AudioClip* clip, uint64_t sample_offset,
+                       uint64_t clip_frame = 0) {
     AudioEvent e;
     e.type = EventType::PlaySample;
     e.buffer_offset = off;
     e.time = time;
     e.speed = clip->speed;
     e.sample_offset = sample_offset;
+    e.clip_frame = clip_frame;
     e.clip = clip;
     t.audio_event_buffer.push_back(e);
   };
@@ -259,13 +263,13 @@ void Engine::process_event(Track& t, double start_time, double end_time, double 
     } else if (start_time > min_time && !t.partially_ended) {  // playback starts in the middle of the clip
       const double sample_pos = beat_to_samples(start_time - min_time, sample_rate, beat_duration);
       const uint64_t sample_offset = (uint64_t)(clip->start_offset + (sample_pos * clip->speed));
-      push_play(0, start_time, clip, sample_offset);
+      push_play(0, start_time, clip, sample_offset, (uint64_t)sample_pos);
       clip->internal_state_changed = false;
     } else if (clip->internal_state_changed && t.partially_ended) {  // clip edited while it plays
       const double sample_pos = beat_to_samples(start_time - min_time, sample_rate, beat_duration);
       const uint64_t sample_offset = (uint64_t)(clip->start_offset + (sample_pos * clip->speed));
       push_stop(0, start_time);
-      push_play(0, start_time, clip, sample_offset);
+      push_play(0, start_time, clip, sample_offset, (uint64_t)sample_pos);
       clip->internal_state_changed = false;
     }
 
@@ -284,12 +288,27 @@ void Engine::process_event(Track& t, double start_time, double end_time, double 
   t.clip_idx = next_clip;
 }
 
+// Fade extension (include/wbx.h): ramp lengths of the clip in output frames.
+void Engine::fill_fade(wbx_segment& s, const AudioClip* clip, uint64_t clip_frame) const {
+  s.flags = 0;
+  s.clip_frame = s.fade_in_frames = s.fade_out_frames = s.clip_len_frames = 0.0;
+  if (clip->fade_start > 0.0 || clip->fade_end > 0.0) {
+    s.flags = WBX_SEG_FADE;
+    s.clip_frame = (double)clip_frame;
+    s.fade_in_frames = beat_to_samples(clip->fade_start, cur_sample_rate_, beat_duration_);
+    s.fade_out_frames = beat_to_samples(clip->fade_end, cur_sample_rate_, beat_duration_);
+    s.clip_len_frames = beat_to_samples(clip->max_time - clip->min_time, cur_sample_rate_, beat_duration_);
+  }
+}
+
 // One dsp::Sampler::stream call (dsp/sampler.cpp:88-210) becomes one wbx_segment — or extends the track's
 // open run when it is the whole-block continuation of the previous callback's call. Host keeps only the
 // position bookkeeping (sampler.cpp:99-103,209); the device clips to the sample's end itself.
 void Engine::stream(Track& t, uint32_t track_index, uint32_t block, uint32_t num_samples, uint32_t buffer_offset) {
   const AudioClip* clip = t.current_audio_event.clip;
   const double count = (double)samples_[clip->sample_id].count;
+  const uint64_t clip_frame = t.clip_frame;
+  t.clip_frame += num_samples;  // the clip's own timeline advances whether or not the sample still has data
   if (t.sample_offset >= count) return;  // has finished streaming: position no longer advances
   if (num_samples != 0) {
     bool extended = false;
@@ -311,7 +330,7 @@ void Engine::stream(Track& t, uint32_t track_index, uint32_t block, uint32_t num
       s.src_pos = t.sample_offset;
       s.speed = t.playback_speed;
       s.gain = clip->gain;
-      s.reserved = 0;
+      fill_fade(s, clip, clip_frame);
       segs_.push_back(s);
       // only a whole-block call can be continued by the next callback's whole-block call
       t.open_run = (buffer_offset == 0 && num_samples == buffer_size_) ? (int32_t)segs_.size() - 1 : -1;
@@ -367,6 +386,7 @@ void Engine::track_block(Track& t, uint32_t track_index, uint32_t block, double 
       if (ne.type == EventType::PlaySample) {  // Sampler::reset_state, dsp/sampler.h:18-27
         t.playback_speed = ((double)ne.clip->sample_rate / sample_rate) * ne.speed;
         t.sample_offset = (double)ne.sample_offset;
+        t.clip_frame = ne.clip_frame;
       }
       t.current_audio_event = ne;
       start_sample += event_length;
@@ -408,8 +428,11 @@ void Engine::stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t
   if (t.current_audio_event.type != EventType::PlaySample || q == 0) return;
   const AudioClip* clip = t.current_audio_event.clip;
   const double count = (double)samples_[clip->sample_id].count;
-  if (t.sample_offset >= count) return;
   const uint32_t B = buffer_size_;
+  if (t.sample_offset >= count) {
+    t.clip_frame += (uint64_t)q * B;
+    return;
+  }
   const double adv = (double)B * t.playback_speed;
   double off = t.sample_offset;
   uint32_t streamed = 0;
@@ -443,15 +466,17 @@ void Engine::stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t
     s.src_pos = t.sample_offset;
     s.speed = t.playback_speed;
     s.gain = clip->gain;
-    s.reserved = 0;
+    fill_fade(s, clip, t.clip_frame);
     segs_.push_back(s);
     t.open_run = (int32_t)segs_.size() - 1;
   }
+  t.clip_frame += (uint64_t)q * B;
   t.sample_offset = off;
 }
 
 int Engine::schedule(uint32_t n_blocks, double sample_rate) {
   if (sample_rate == 0.0) sample_rate = (double)sample_rate_;
+  cur_sample_rate_ = sample_rate;
   segs_.clear();
   const uint32_t N = (uint32_t)tracks.size();
   const uint32_t K = n_blocks;
@@ -582,6 +607,12 @@ int wbxh_add_clip(wbxh_engine* h, int track, int sample, double min_beat, double
                   double speed, float gain) {
   if (track < 0 || (size_t)track >= h->eng.tracks.size() || sample < 0) return WBX_ERR_INVALID;
   return h->eng.add_audio_clip(h->eng.tracks[track], min_beat, max_beat, start_offset, (uint32_t)sample, speed, gain);
+}
+int wbxh_add_clip_fade(wbxh_engine* h, int track, int sample, double min_beat, double max_beat, double start_offset,
+                       double speed, float gain, double fade_start, double fade_end) {
+  if (track < 0 || (size_t)track >= h->eng.tracks.size() || sample < 0) return WBX_ERR_INVALID;
+  return h->eng.add_audio_clip(h->eng.tracks[track], min_beat, max_beat, start_offset, (uint32_t)sample, speed, gain,
+                               fade_start, fade_end);
 }
 void wbxh_set_playhead(wbxh_engine* h, double beat) { h->eng.set_playhead_position(beat); }
 void wbxh_play(wbxh_engine* h) { h->eng.play(); }

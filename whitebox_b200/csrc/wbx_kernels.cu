@@ -57,31 +57,55 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // ---------------------------------------------------------------------------------------------------------
 // schedule expansion
 // ---------------------------------------------------------------------------------------------------------
+// num_actual_samples = min(num_samples, (uint32_t)ceil((count - offset) / speed))   (sampler.cpp:102-104)
+__device__ __forceinline__ uint32_t clipped_length(double cnt, double pos, double speed, uint32_t length, double safe) {
+  const double rem = __dsub_rn(cnt, pos);
+  if (rem >= safe) return length;  // rem >= (length + 1) * speed  =>  ceil(rem / speed) >= length
+  const double m = ceil(__ddiv_rn(rem, speed));
+  const uint32_t mm = m >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)m;
+  return mm < length ? mm : length;
+}
+
+// One WARP per segment. Unity-speed runs that start on an integer frame advance by exact integer additions, so
+// pos_b = pos0 + b * length in closed form and the lanes take callbacks b = lane, lane + 32, ... Any other run
+// replays the reference's recurrence pos += (double)num_samples * speed, one rounding per callback
+// (sampler.cpp:103,209) — every lane carries the same chain, lane b % 32 writes callback b's cell.
 __global__ void expand_schedule(const DSpan* __restrict__ spans, uint32_t n_spans, DCell* __restrict__ cells,
                                 uint32_t n_tracks, uint32_t slots) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_spans) return;
-  const DSpan s = spans[i];
-  double pos = s.pos0;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (w >= n_spans) return;
+  const DSpan s = spans[w];
   const double cnt = (double)s.count;
-  const double adv = __dmul_rn((double)s.length, s.speed);           // (double)num_samples * playback_speed_
-  const double safe = __dmul_rn((double)s.length + 1.0, s.speed);    // rem >= safe  =>  ceil(rem/speed) >= length
-  for (uint32_t b = 0; b < s.n_blocks; b++) {
-    if (pos >= cnt) break;  // finished streaming; sample_offset_ no longer advances (sampler.cpp:99-100)
-    uint32_t n_act = s.length;
-    const double rem = __dsub_rn(cnt, pos);
-    if (rem < safe) {
-      // num_actual_samples = min(num_samples, (uint32_t)ceil((count - offset) / speed))   (sampler.cpp:102-104)
-      const double m = ceil(__ddiv_rn(rem, s.speed));
-      const uint32_t mm = m >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)m;
-      n_act = mm < n_act ? mm : n_act;
+  const double len = (double)s.length;
+  const double adv = __dmul_rn(len, s.speed);                  // (double)num_samples * playback_speed_
+  const double safe = __dmul_rn(len + 1.0, s.speed);
+  DCell* out = cells + ((size_t)s.block0 * n_tracks + s.track) * slots + s.slot;
+  const size_t stride = (size_t)n_tracks * slots;
+  const bool closed = s.speed == 1.0 && floor(s.pos0) == s.pos0 && s.pos0 + (double)s.n_blocks * len < 4.0e15;
+  if (closed) {
+    for (uint32_t b = lane; b < s.n_blocks; b += 32) {
+      const double pos = s.pos0 + (double)b * len;  // exact
+      if (pos >= cnt) break;  // finished streaming; sample_offset_ no longer advances (sampler.cpp:99-100)
+      DCell c;
+      c.pos = pos;
+      c.span = w;
+      c.n_act = clipped_length(cnt, pos, s.speed, s.length, safe);
+      out[(size_t)b * stride] = c;
     }
-    DCell c;
-    c.pos = pos;
-    c.span = i;
-    c.n_act = n_act;
-    cells[((size_t)(s.block0 + b) * n_tracks + s.track) * slots + s.slot] = c;
-    pos = __dadd_rn(pos, adv);  // next_sample_offset (sampler.cpp:103,209)
+  } else {
+    double pos = s.pos0;
+    for (uint32_t b = 0; b < s.n_blocks; b++) {
+      if (pos >= cnt) break;
+      if ((b & 31u) == lane) {
+        DCell c;
+        c.pos = pos;
+        c.span = w;
+        c.n_act = clipped_length(cnt, pos, s.speed, s.length, safe);
+        out[(size_t)b * stride] = c;
+      }
+      pos = __dadd_rn(pos, adv);  // next_sample_offset (sampler.cpp:103,209)
+    }
   }
 }
 
@@ -136,6 +160,24 @@ __device__ __forceinline__ float load_lin(const void* row, int64_t idx) {
   }
 }
 
+// run-time format dispatch for the generic path (keeps its code size down: it is the rare path)
+__device__ __forceinline__ float load_unity_rt(uint32_t fmt, const void* row, int64_t idx) {
+  switch (fmt) {
+    case F_I16: return load_unity<F_I16>(row, idx);
+    case F_I24: return load_unity<F_I24>(row, idx);
+    case F_I32: return load_unity<F_I32>(row, idx);
+    default: return load_unity<F_F32>(row, idx);
+  }
+}
+__device__ __forceinline__ float load_lin_rt(uint32_t fmt, const void* row, int64_t idx) {
+  switch (fmt) {
+    case F_I16: return load_lin<F_I16>(row, idx);
+    case F_I24: return load_lin<F_I24>(row, idx);
+    case F_I32: return load_lin<F_I32>(row, idx);
+    default: return load_lin<F_F32>(row, idx);
+  }
+}
+
 // term = (sample * clip_gain) * track_gain, bus += term, peak = max(peak, |term|)
 __device__ __forceinline__ void accumulate(float s, float gain, float tg, float& acc, float& pk) {
   const float term = __fmul_rn(__fmul_rn(s, gain), tg);  // sampler.cpp:154 then dsp_ops.h:29
@@ -149,10 +191,33 @@ __device__ __forceinline__ void accumulate(float s, float gain, float tg, float&
 
 // Generic per-frame path: any format, unity or linear, staged window (shared) or direct (global) rows.
 // `row` points at window frame 0 (frame-interleaved, NCH channels); d.base is that frame's sample index.
-template <int FPL, uint32_t FMT, bool UNITY, int NCH>
+// Fade extension (include/wbx.h): envelope of clip-relative output frame n.
+struct FadeEnv {
+  double n0;  // clip frame of segment-relative frame 0
+  double fin, fout, len;
+  __device__ __forceinline__ float at(int32_t jj) const {
+    const double n = __dadd_rn(n0, (double)jj);
+    double e = 1.0;
+    if (fin > 0.0) {
+      const double r = __ddiv_rn(n, fin);
+      e = r < 1.0 ? r : 1.0;
+    }
+    if (fout > 0.0) {
+      double r = __ddiv_rn(__dsub_rn(len, n), fout);
+      r = r > 0.0 ? r : 0.0;
+      r = r < 1.0 ? r : 1.0;
+      e = __dmul_rn(e, r);
+    }
+    return __double2float_rn(e);
+  }
+};
+
+template <int FPL, bool UNITY, bool FADE>
 __device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
-                                              float& pkR, int lane, bool two) {
+                                              float& pkR, int lane, bool two, const FadeEnv& fe) {
   const int64_t ip = (int64_t)(uint32_t)(int64_t)d.pos;  // (uint32_t)sample_offset_, sampler.cpp:107
+  const uint32_t FMT = d.fmt & 0x7fu;
+  const int NCH = (d.fmt & 0x80u) ? 1 : 2;
 #pragma unroll
   for (int i = 0; i < FPL / 2; i++) {
 #pragma unroll
@@ -163,58 +228,72 @@ __device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, fl
         float sL, sR = 0.0f;
         if (UNITY) {
           const int64_t idx = (ip + jj - d.base) * NCH;
-          sL = load_unity<FMT>(row, idx);
-          if (two) sR = (NCH == 2) ? load_unity<FMT>(row, idx + 1) : sL;
+          sL = load_unity_rt(FMT, row, idx);
+          if (two) sR = (NCH == 2) ? load_unity_rt(FMT, row, idx + 1) : sL;
         } else {
           const double x = __dadd_rn(d.pos, __dmul_rn((double)jj, d.speed));  // sampler.cpp:50
           const int64_t ix = __double2ll_rz(x);                                // :51
           const float fx = __double2float_rn(__dsub_rn(x, __ll2double_rn(ix)));  // :52
           const int64_t idx = (ix - d.base) * NCH;
-          const float a = load_lin<FMT>(row, idx), b = load_lin<FMT>(row, idx + NCH);
+          const float a = load_lin_rt(FMT, row, idx), b = load_lin_rt(FMT, row, idx + NCH);
           sL = __fadd_rn(a, __fmul_rn(fx, __fsub_rn(b, a)));  // :55
           if (two) {
             if (NCH == 2) {
-              const float a2 = load_lin<FMT>(row, idx + 1), b2 = load_lin<FMT>(row, idx + 3);
+              const float a2 = load_lin_rt(FMT, row, idx + 1), b2 = load_lin_rt(FMT, row, idx + 3);
               sR = __fadd_rn(a2, __fmul_rn(fx, __fsub_rn(b2, a2)));
             } else {
               sR = sL;
             }
           }
         }
-        accumulate(sL, d.gain, d.tg[0], acc[i * 2 + e].x, pkL);
-        if (two) accumulate(sR, d.gain, d.tg[1], acc[i * 2 + e].y, pkR);
+        if (FADE) {  // (src * gain) * env, then the track gain as usual
+          const float env = fe.at(jj);
+          const float mL = __fmul_rn(__fmul_rn(sL, d.gain), env);
+          const float tL = __fmul_rn(mL, d.tg[0]);
+          acc[i * 2 + e].x = __fadd_rn(acc[i * 2 + e].x, tL);
+          pkL = fmaxf(pkL, fabsf(tL));
+          if (two) {
+            const float mR = __fmul_rn(__fmul_rn(sR, d.gain), env);
+            const float tR = __fmul_rn(mR, d.tg[1]);
+            acc[i * 2 + e].y = __fadd_rn(acc[i * 2 + e].y, tR);
+            pkR = fmaxf(pkR, fabsf(tR));
+          }
+        } else {
+          accumulate(sL, d.gain, d.tg[0], acc[i * 2 + e].x, pkL);
+          if (two) accumulate(sR, d.gain, d.tg[1], acc[i * 2 + e].y, pkR);
+        }
       }
     }
   }
 }
 
-template <int FPL, uint32_t FMT, bool UNITY>
-__device__ __forceinline__ void consume_gen_n(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
-                                              float& pkR, int lane, bool two) {
-  if (d.fmt & 0x80u)
-    consume_gen_t<FPL, FMT, UNITY, 1>(d, row, acc, pkL, pkR, lane, two);
+template <int FPL, bool FADE>
+__device__ __forceinline__ void consume_gen_f(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
+                                              float& pkR, int lane, bool two, const FadeEnv& fe) {
+  if (d.speed == 1.0)  // playback_speed_ == 1.0, sampler.cpp:106
+    consume_gen_t<FPL, true, FADE>(d, row, acc, pkL, pkR, lane, two, fe);
   else
-    consume_gen_t<FPL, FMT, UNITY, 2>(d, row, acc, pkL, pkR, lane, two);
+    consume_gen_t<FPL, false, FADE>(d, row, acc, pkL, pkR, lane, two, fe);
 }
 
 template <int FPL>
 __device__ __forceinline__ void consume_gen(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
-                                            float& pkR, int lane, bool two) {
-  const uint32_t fmt = d.fmt & 0x7fu;
-  if (d.speed == 1.0) {  // playback_speed_ == 1.0, sampler.cpp:106
-    switch (fmt) {
-      case F_I16: consume_gen_n<FPL, F_I16, true>(d, row, acc, pkL, pkR, lane, two); break;
-      case F_I24: consume_gen_n<FPL, F_I24, true>(d, row, acc, pkL, pkR, lane, two); break;
-      case F_I32: consume_gen_n<FPL, F_I32, true>(d, row, acc, pkL, pkR, lane, two); break;
-      default: consume_gen_n<FPL, F_F32, true>(d, row, acc, pkL, pkR, lane, two); break;
-    }
+                                            float& pkR, int lane, bool two, const DSpan* spans) {
+  FadeEnv fe;
+  fe.n0 = 0.0;
+  fe.fin = 0.0;
+  fe.fout = 0.0;
+  fe.len = 0.0;
+  if (d.kind == K_FADE || d.kind == K_DIRECT_FADE) {
+    const DSpan* sp = spans + d.span;
+    fe.fin = __ldg(&sp->fade_in);
+    fe.fout = __ldg(&sp->fade_out);
+    fe.len = __ldg(&sp->clip_len);
+    // clip frame of segment-relative frame 0 in this callback (exact: integers)
+    fe.n0 = __ldg(&sp->clip_frame) + (double)d.block_in_run * (double)__ldg(&sp->length);
+    consume_gen_f<FPL, true>(d, row, acc, pkL, pkR, lane, two, fe);
   } else {
-    switch (fmt) {
-      case F_I16: consume_gen_n<FPL, F_I16, false>(d, row, acc, pkL, pkR, lane, two); break;
-      case F_I24: consume_gen_n<FPL, F_I24, false>(d, row, acc, pkL, pkR, lane, two); break;
-      case F_I32: consume_gen_n<FPL, F_I32, false>(d, row, acc, pkL, pkR, lane, two); break;
-      default: consume_gen_n<FPL, F_F32, false>(d, row, acc, pkL, pkR, lane, two); break;
-    }
+    consume_gen_f<FPL, false>(d, row, acc, pkL, pkR, lane, two, fe);
   }
 }
 
@@ -376,7 +455,7 @@ __device__ __forceinline__ DSpan load_span(const DSpan* spans, const DCell& c) {
 // Turn (cell, span) into the per-tile descriptor: which frames, which source window, which code path.
 template <int STAGE_BYTES, int T>
 __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, const float* __restrict__ gains,
-                                              int f0, int tile_len, bool two, Desc* out) {
+                                              int f0, int tile_len, bool two, uint32_t k, Desc* out) {
   Desc d;
   d.src = nullptr;
   d.pos = c.pos;
@@ -392,8 +471,8 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
   d.bytes = 0;
   d.kind = K_SILENT;
   d.fmt = (uint8_t)(s.fmt | (s.nch == 1 ? 0x80u : 0u));
-  d.pad[0] = 0;
-  d.pad[1] = 0;
+  d.span = c.span;
+  d.block_in_run = k - s.block0;
   if (c.span != kSilent) {
     const int seg_lo = (int)s.dst_off, seg_hi = (int)(s.dst_off + c.n_act);
     const int lo = (seg_lo > f0 ? seg_lo : f0) - f0;
@@ -421,12 +500,21 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
       const int64_t a = first & ~(align - 1);
       const int64_t end = (last + align) & ~(align - 1);
       const int64_t bytes = (end - a) * fbytes;
+      // fade extension: does a ramp overlap the frames of this item?
+      bool fading = false;
+      if (s.fade) {
+        const double n_lo = s.clip_frame + (double)d.block_in_run * (double)s.length + (double)jj_lo;
+        const double n_hi = s.clip_frame + (double)d.block_in_run * (double)s.length + (double)jj_hi;
+        fading = (s.fade_in > 0.0 && n_lo < s.fade_in) || (s.fade_out > 0.0 && s.clip_len - n_hi < s.fade_out);
+      }
       if (bytes <= STAGE_BYTES) {
         d.src = (const uint8_t*)s.base + a * fbytes;
         d.base = (int32_t)a;
         d.bytes = (uint16_t)bytes;
         const bool st32 = two && s.fmt == F_F32 && s.nch == 2;  // stereo f32 source into a stereo bus
-        if (st32 && unity)
+        if (fading)
+          d.kind = K_FADE;
+        else if (st32 && unity)
           d.kind = (lo == 0 && hi == T && first == a) ? K_FAST : K_UNI;
         else if (st32 && last < (int64_t)0x3fffffff)
           d.kind = K_LIN;
@@ -434,7 +522,7 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
           d.kind = K_GEN;
       } else {  // window larger than a stage (speed well above 1): read the source straight from global
         d.src = s.base;
-        d.kind = K_DIRECT;
+        d.kind = fading ? K_DIRECT_FADE : K_DIRECT;
       }
     }
   }
@@ -497,7 +585,7 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
     if (lane < BATCH) {
       const DCell c0 = load_cell(cells, lane, n_cells);
       const DSpan s0 = load_span(p.spans, c0);
-      resolve_store<L::STAGE_BYTES, L::T>(c0, s0, p.gains, f0, tile_len, two, &ring[lane]);
+      resolve_store<L::STAGE_BYTES, L::T>(c0, s0, p.gains, f0, tile_len, two, k, &ring[lane]);
     }
     __syncwarp();
     uint32_t limit = BATCH;  // cells [0, limit) have descriptors
@@ -515,7 +603,7 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
       while (ip < lim && (n_issued - n_consumed) < (uint32_t)STAGES) {
         const Desc* dd = &ring[ip & (L::RING - 1)];
         const uint32_t kind = dd->kind;
-        if (kind != K_SILENT && kind != K_DIRECT) {
+        if (kind != K_SILENT && kind != K_DIRECT && kind != K_DIRECT_FADE) {
           if (lane == 0) {
             const uint32_t st = n_issued % STAGES;
             const uint32_t bar = bars_s + 8 * st;
@@ -539,7 +627,7 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
         if (more && i == BATCH / 4 && lane < BATCH) sN = load_span(p.spans, cN);
         if (more && i == BATCH / 2) {
           if (lane < BATCH)
-            resolve_store<L::STAGE_BYTES, L::T>(cN, sN, p.gains, f0, tile_len, two, &ring[((b + 1) & 1) * BATCH + lane]);
+            resolve_store<L::STAGE_BYTES, L::T>(cN, sN, p.gains, f0, tile_len, two, k, &ring[((b + 1) & 1) * BATCH + lane]);
           __syncwarp();
           limit += BATCH;
         }
@@ -551,7 +639,8 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
           active = true;
           cur_track = dp->track;
           const uint32_t st = n_consumed % STAGES;
-          if (kind != K_DIRECT) {
+          const bool staged = (kind != K_DIRECT && kind != K_DIRECT_FADE);
+          if (staged) {
             const uint32_t par = (n_consumed / STAGES) & 1u;
             while (!mbar_try_wait(bars_s + 8 * st, par)) {
             }
@@ -565,9 +654,9 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
             consume_lin<FPL>(*dp, row, acc, pkL, pkR, lane);
           } else {
             const Desc d = *dp;
-            consume_gen<FPL>(d, kind == K_DIRECT ? d.src : (const void*)row, acc, pkL, pkR, lane, two);
+            consume_gen<FPL>(d, staged ? (const void*)row : d.src, acc, pkL, pkR, lane, two, p.spans);
           }
-          if (kind != K_DIRECT) {
+          if (staged) {
             __syncwarp();  // every lane is done reading the stage before lane 0 may refill it
             n_consumed++;
           }
@@ -817,7 +906,7 @@ cudaError_t launch_interleave_sample(const void* planar, size_t plane_bytes, uin
 cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, uint32_t n_tracks, uint32_t slots,
                           cudaStream_t stream) {
   if (n_spans == 0) return cudaSuccess;
-  expand_schedule<<<(n_spans + 127) / 128, 128, 0, stream>>>(spans, n_spans, cells, n_tracks, slots);
+  expand_schedule<<<(n_spans + 3) / 4, 128, 0, stream>>>(spans, n_spans, cells, n_tracks, slots);  // warp per span
   return cudaGetLastError();
 }
 
