@@ -119,6 +119,10 @@ int wbx_set_stream(wbx_engine* e, void* cuda_stream);
 int wbx_sample_upload(wbx_engine* e, int format, uint32_t channels, uint64_t frames, uint32_t sample_rate,
                       const void* const* planar, uint32_t* out_id);
 int wbx_sample_release(wbx_engine* e, uint32_t id);
+/* Overwrite the data of an existing sample (same format / channels / frames) — streaming sources from host
+ * memory. Asynchronous on the engine's stream when planar[c] are page-locked (wbx_host_alloc): the arrays
+ * must then stay valid until the next wbx_synchronize / wbx_fetch; pageable arrays are copied before return. */
+int wbx_sample_update(wbx_engine* e, uint32_t id, const void* const* planar);
 
 /* ---- render ----------------------------------------------------------------------------------------- */
 /* One call = n_blocks consecutive Engine::process callbacks (n_blocks = 1 is the realtime callback).

@@ -275,3 +275,14 @@ def test_errors_are_reported(wb):
         dev.configure(3, 512, 48000)  # pan_coeffs[2]: at most 2 output channels
     with pytest.raises(wb.WbxError):
         dev.mix()  # nothing submitted
+
+
+def test_cpp_dropin_demo(wb, tmp_path):
+    """examples/dropin_demo.cpp: a pure C++ caller (no Python) drives wbx::Engine::process per callback with
+    AudioBuffer-shaped buffers and gets the same samples as one offline bounce."""
+    import subprocess
+    from test_host_cpu import build_dropin_demo
+    exe = build_dropin_demo(str(tmp_path))
+    r = subprocess.run([exe, "96", "40"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 samples differ" in r.stdout

@@ -163,3 +163,28 @@ def test_no_fma_contraction_in_mix_kernels(wb):
                     bad.append((fn[:40], line.strip()[:90]))
     assert seen > 1000, "mix_kernel SASS not found"
     assert not bad, "fused multiply-adds on the audio path: %s" % bad[:5]
+
+
+def build_dropin_demo(tmp):
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("g++ not available")
+    exe = os.path.join(tmp, "dropin_demo")
+    lib_dir = os.path.join(ROOT, "whitebox_b200")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "dropin_demo.cpp"), "-L" + lib_dir, "-lwbx",
+                    "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
+    return exe
+
+
+def test_cpp_adaptor_builds_and_refuses_without_device(wb, tmp_path):
+    """The C++ adaptor (include/wbx_engine.hpp) links against libwbx.so from plain g++; without a GPU the demo
+    exits with the no-device status instead of rendering on the CPU."""
+    import subprocess
+    import torch
+    exe = build_dropin_demo(str(tmp_path))
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU path" in r.stderr

@@ -65,6 +65,7 @@ struct wbx_engine {
   uint32_t n_blocks = 0, n_spans = 0, slots = 1;
   bool submitted = false, mixed = false;
   uint64_t launches = 0;
+  uint32_t upload_flip = 0;
   char err[256] = {0};
   char kernel_name[64] = {0};
 };
@@ -286,6 +287,30 @@ int wbx_sample_upload(wbx_engine* e, int format, uint32_t channels, uint64_t fra
   return WBX_OK;
 }
 
+static bool is_pinned(const void* p);
+
+int wbx_sample_update(wbx_engine* e, uint32_t id, const void* const* planar) {
+  if (!e || !planar || id >= e->samples.size() || !e->samples[id].live) return fail(e, WBX_ERR_INVALID, "bad sample id");
+  CU(e, cudaSetDevice(e->device));
+  const SampleRec& r = e->samples[id];
+  const size_t plane_bytes = (((size_t)r.frames * r.esize) + 255) & ~(size_t)255;
+  // two staging halves alternate so the next sample's H2D overlaps this one's interleave kernel
+  int rc = dev_reserve(e, e->d_upload, 2 * plane_bytes * r.nch);
+  if (rc) return rc;
+  uint8_t* stage = (uint8_t*)e->d_upload.p + (size_t)(e->upload_flip & 1u) * plane_bytes * r.nch;
+  e->upload_flip++;
+  bool pinned = true;
+  for (uint32_t c = 0; c < r.nch; c++) {
+    pinned = pinned && is_pinned(planar[c]);
+    CU(e, cudaMemcpyAsync(stage + c * plane_bytes, planar[c], (size_t)r.frames * r.esize, cudaMemcpyHostToDevice,
+                          e->stream));
+  }
+  CU(e, launch_interleave_sample(stage, plane_bytes, r.frames, r.nch, r.esize, r.d_base, e->n_sm, e->stream));
+  e->launches++;
+  if (!pinned) CU(e, cudaStreamSynchronize(e->stream));
+  return WBX_OK;
+}
+
 int wbx_sample_release(wbx_engine* e, uint32_t id) {
   if (!e || id >= e->samples.size() || !e->samples[id].live) return fail(e, WBX_ERR_INVALID, "bad sample id");
   CU(e, cudaSetDevice(e->device));
@@ -446,7 +471,7 @@ int wbx_mix(wbx_engine* e, uint32_t flags) {
   return WBX_OK;
 }
 
-// true when p is page-locked host memory the device can copy to directly (cudaMallocHost / cudaHostRegister)
+// true when p is page-locked host memory the device can copy to/from directly (cudaMallocHost / cudaHostRegister)
 static bool is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
