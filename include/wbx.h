@@ -124,6 +124,31 @@ int wbx_sample_release(wbx_engine* e, uint32_t id);
  * must then stay valid until the next wbx_synchronize / wbx_fetch; pageable arrays are copied before return. */
 int wbx_sample_update(wbx_engine* e, uint32_t id, const void* const* planar);
 
+/* ---- per-track effect chain — EXTENSION, not in the reference ---------------------------------------------- */
+/* whitebox has no DSP effects (its per-track slot is a third-party VST3 instance, engine/track.h:124,
+ * engine/track.cpp:645-662). This is the built-in chain a PluginFormat::Native effect would provide
+ * (plughost/plugin_interface.h:31-35), specified by the builder (oracle/wb_oracle.c apply_effects — "parity
+ * unpinned"): 4-band RBJ biquad EQ (band 0 low shelf, 1/2 peaking, 3 high shelf; transposed direct form II in
+ * f32 with fused multiply-adds) then a per-channel peak compressor (attack/release one-poles, hard knee, ratio
+ * 2/4/8/limiter evaluated with IEEE divide and square roots only), applied to the track's signal after its
+ * clips are rendered and before volume/pan and the VU meter. Filter state persists across renders. */
+typedef struct wbx_effect_params { /* musical parameters */
+  float eq_freq[4], eq_gain_db[4], eq_q[4];
+  float comp_threshold_db, comp_attack_ms, comp_release_ms, comp_makeup_db;
+  int32_t comp_ratio_code; /* 0 off, 1 = 2:1, 2 = 4:1, 3 = 8:1, 4 = limiter */
+} wbx_effect_params;
+typedef struct wbx_effects { /* designed coefficients */
+  uint32_t eq_on, comp_on;
+  float b0[4], b1[4], b2[4], a1[4], a2[4]; /* normalised by a0 */
+  float comp_threshold, comp_attack, comp_release, comp_makeup; /* linear / one-pole coefficients */
+  uint32_t comp_ratio_code;
+} wbx_effects;
+/* f64 coefficient design (host only). */
+int wbx_effects_design(const wbx_effect_params* params, uint32_t sample_rate, wbx_effects* out);
+/* Attach (fx != NULL) or remove (NULL) a track's chain and clear its state. Tracks without a chain take the
+ * reference path untouched. */
+int wbx_set_track_effects(wbx_engine* e, uint32_t track, const wbx_effects* fx);
+
 /* ---- render ----------------------------------------------------------------------------------------- */
 /* One call = n_blocks consecutive Engine::process callbacks (n_blocks = 1 is the realtime callback).
  *   track_gains  [n_tracks][2] f32: (mute ? 0 : volume) * pan_coeffs[c]            (track.cpp:728-731)

@@ -76,6 +76,10 @@ struct Track {
   std::vector<Msg> track_msg_queue;  // UI -> audio parameter messages (engine/track.h:131)
   float level[2] = {0, 0};           // VUMeter::level (engine/vu_meter.h:17): max since last read
   int32_t open_run = -1;             // index of this track's extendable run in the segment list
+  // built-in effect chain (extension, see wbx.h): applied on the device between the clips and volume/pan
+  wbx_effect_params effect_params{};
+  bool effects_on = false, effects_dirty = false;
+  void set_effects(const wbx_effect_params* params);  // nullptr removes the chain
   ~Track();
   void set_volume(float db);  // engine/track.cpp:47-57
   void set_pan(float pan);    // :59-68

@@ -38,6 +38,8 @@ int wbxh_add_clip(wbxh_engine* h, int track, int sample, double min_beat, double
  * specified in wbx.h; (0, 0) is the reference path. */
 int wbxh_add_clip_fade(wbxh_engine* h, int track, int sample, double min_beat, double max_beat, double start_offset,
                        double speed, float gain, double fade_start, double fade_end);
+/* attach (params != NULL) or remove the built-in EQ + compressor chain of a track (extension, see wbx.h) */
+int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params);
 void wbxh_set_playhead(wbxh_engine* h, double beat);
 void wbxh_play(wbxh_engine* h);
 void wbxh_stop(wbxh_engine* h);

@@ -101,6 +101,8 @@ int wbo_add_clip_fade(wbo_session* s, int track, int sample, double min_beat, do
   return 0;
 }
 
+int wbo_set_effects(wbo_session*, int, const wbo_effects*) { return -1; }  // the reference has no effects
+
 void wbo_set_playhead(wbo_session* s, double beat) { s->engine.set_playhead_position(beat); }
 void wbo_play(wbo_session* s) { s->engine.play(); }
 void wbo_stop(wbo_session* s) { s->engine.stop(); }

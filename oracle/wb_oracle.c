@@ -63,9 +63,19 @@ typedef struct {
   double value;
 } o_msg;
 
+/* EXTENSION: designed effect chain + its running state (see apply_effects) */
+typedef struct {
+  int eq_on, comp_on;
+  float b0[4], b1[4], b2[4], a1[4], a2[4];
+  float thr, att, rel, makeup;
+  int ratio_code;
+  float s1[2][4], s2[2][4], env[2];
+} o_fx;
+
 typedef struct {
   o_clip** clips;
   uint32_t n_clips, cap_clips;
+  o_fx fx;
   /* TrackEventState, track.h:36-44 */
   int has_clip_idx;
   uint32_t clip_idx;
@@ -605,6 +615,99 @@ static void track_stream(wbo_session* s, o_track* tr, uint32_t num_samples, uint
   }
 }
 
+/* ---- EXTENSION (parity unpinned w.r.t. whitebox): per-track EQ + compressor ----------------------------- */
+/* RBJ "Audio EQ Cookbook" biquads, designed in f64, normalised by a0, stored as f32. */
+static void design_band(int band, double freq, double gain_db, double q, double rate, float* b0, float* b1, float* b2,
+                        float* a1, float* a2) {
+  const double pi = 3.141592653589793238462643383279502884;
+  const double A = pow(10.0, gain_db / 40.0);
+  const double w0 = 2.0 * pi * freq / rate;
+  const double cw = cos(w0), sw = sin(w0);
+  const double alpha = sw / (2.0 * q);
+  double B0, B1, B2, A0, A1, A2;
+  if (band == 0) { /* low shelf */
+    const double sq = 2.0 * sqrt(A) * alpha;
+    B0 = A * ((A + 1.0) - (A - 1.0) * cw + sq);
+    B1 = 2.0 * A * ((A - 1.0) - (A + 1.0) * cw);
+    B2 = A * ((A + 1.0) - (A - 1.0) * cw - sq);
+    A0 = (A + 1.0) + (A - 1.0) * cw + sq;
+    A1 = -2.0 * ((A - 1.0) + (A + 1.0) * cw);
+    A2 = (A + 1.0) + (A - 1.0) * cw - sq;
+  } else if (band == 3) { /* high shelf */
+    const double sq = 2.0 * sqrt(A) * alpha;
+    B0 = A * ((A + 1.0) + (A - 1.0) * cw + sq);
+    B1 = -2.0 * A * ((A - 1.0) + (A + 1.0) * cw);
+    B2 = A * ((A + 1.0) + (A - 1.0) * cw - sq);
+    A0 = (A + 1.0) - (A - 1.0) * cw + sq;
+    A1 = 2.0 * ((A - 1.0) - (A + 1.0) * cw);
+    A2 = (A + 1.0) - (A - 1.0) * cw - sq;
+  } else { /* peaking */
+    B0 = 1.0 + alpha * A;
+    B1 = -2.0 * cw;
+    B2 = 1.0 - alpha * A;
+    A0 = 1.0 + alpha / A;
+    A1 = -2.0 * cw;
+    A2 = 1.0 - alpha / A;
+  }
+  *b0 = (float)(B0 / A0);
+  *b1 = (float)(B1 / A0);
+  *b2 = (float)(B2 / A0);
+  *a1 = (float)(A1 / A0);
+  *a2 = (float)(A2 / A0);
+}
+
+int wbo_set_effects(wbo_session* s, int track, const wbo_effects* fx) {
+  o_fx* f = &s->tracks[track]->fx;
+  memset(f, 0, sizeof(*f));
+  if (!fx) return 0;
+  for (int b = 0; b < 4; b++) {
+    if (fx->eq_gain_db[b] != 0.0f) f->eq_on = 1;
+    design_band(b, fx->eq_freq[b], fx->eq_gain_db[b], fx->eq_q[b], (double)s->rate, &f->b0[b], &f->b1[b], &f->b2[b],
+                &f->a1[b], &f->a2[b]);
+  }
+  f->ratio_code = fx->comp_ratio_code;
+  f->comp_on = fx->comp_ratio_code != 0;
+  f->thr = (float)pow(10.0, (double)fx->comp_threshold_db / 20.0);
+  f->makeup = (float)pow(10.0, (double)fx->comp_makeup_db / 20.0);
+  f->att = (float)exp(-1.0 / ((double)fx->comp_attack_ms * 0.001 * (double)s->rate));
+  f->rel = (float)exp(-1.0 / ((double)fx->comp_release_ms * 0.001 * (double)s->rate));
+  return 0;
+}
+
+/* One channel, one callback, in place. Every operation is a single IEEE-754 rn op (fmaf = fused). */
+static void apply_effects(o_fx* f, int c, float* buf, uint32_t n) {
+  for (uint32_t j = 0; j < n; j++) {
+    float x = buf[j];
+    if (f->eq_on) {
+      for (int b = 0; b < 4; b++) { /* transposed direct form II */
+        const float y = fmaf(f->b0[b], x, f->s1[c][b]);
+        f->s1[c][b] = fmaf(f->b1[b], x, fmaf(-f->a1[b], y, f->s2[c][b]));
+        f->s2[c][b] = fmaf(f->b2[b], x, -(f->a2[b] * y));
+        x = y;
+      }
+    }
+    if (f->comp_on) {
+      const float xa = fabsf(x);
+      float env = f->env[c];
+      env = xa > env ? fmaf(f->att, env - xa, xa) : fmaf(f->rel, env - xa, xa); /* peak follower */
+      f->env[c] = env;
+      float g = 1.0f;
+      if (env > f->thr) {
+        const float r = f->thr / env; /* (thr/env)^(1 - 1/ratio) with divide and square roots only */
+        const float r2 = sqrtf(r);
+        switch (f->ratio_code) {
+          case 1: g = r2; break;                                /* 2:1 -> r^(1/2) */
+          case 2: g = r2 * sqrtf(r2); break;                    /* 4:1 -> r^(3/4) */
+          case 3: g = (r2 * sqrtf(r2)) * sqrtf(sqrtf(r2)); break; /* 8:1 -> r^(7/8) */
+          default: g = r; break;                                /* limiter */
+        }
+      }
+      x = (x * g) * f->makeup;
+    }
+    buf[j] = x;
+  }
+}
+
 /* ---- Track::process (engine/track.cpp:587-736) ---------------------------------------------------------- */
 
 static void track_process(wbo_session* s, o_track* tr, float** out, double sample_rate, double beat_duration,
@@ -659,6 +762,9 @@ static void track_process(wbo_session* s, o_track* tr, float** out, double sampl
 
   /* dsp::apply_gain (dsp/dsp_ops.h:27-31) + VUMeter::push_samples (engine/vu_meter.h:20-30), :728-733.
    * pan_coeffs has two entries, so C <= 2 (track.h:50). */
+  if (tr->fx.eq_on || tr->fx.comp_on) /* EXTENSION: where a native PluginInterface::process would run */
+    for (uint32_t c = 0; c < s->C; c++) apply_effects(&tr->fx, (int)c, out[c], B);
+
   float volume = tr->mute ? 0.0f : tr->volume;
   for (uint32_t c = 0; c < s->C; c++) {
     float* buf = out[c];

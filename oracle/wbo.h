@@ -53,6 +53,22 @@ int wbo_add_clip(wbo_session*, int track, int sample, double min_beat, double ma
 int wbo_add_clip_fade(wbo_session*, int track, int sample, double min_beat, double max_beat, double start_offset,
                       double speed, float gain, double fade_start, double fade_end);
 
+/* Per-track effect chain — EXTENSION, PARITY UNPINNED w.r.t. whitebox (the reference has no DSP effects; its
+ * only per-track effect slot is a third-party VST3 instance, engine/track.h:124). Builder's specification
+ * (wb_oracle.c apply_effects), placed where a native PluginInterface::process would sit: on the track's mixing
+ * buffer after the clips are rendered and before dsp::apply_gain / the VU meter (engine/track.cpp:726-733).
+ *   4-band EQ: RBJ biquads (0 low shelf, 1/2 peaking, 3 high shelf), coefficients designed in f64, stored f32,
+ *              transposed direct form II in f32 with fused multiply-adds, per channel.
+ *   compressor: per channel peak follower (attack/release one-poles), hard knee, ratio 2/4/8/limiter evaluated
+ *              with IEEE divide + square roots only (bit-reproducible), then make-up gain.
+ * eq_gain_db[b] == 0 for all b and ratio_code == 0 disables the respective stage. */
+typedef struct wbo_effects {
+  float eq_freq[4], eq_gain_db[4], eq_q[4];
+  float comp_threshold_db, comp_attack_ms, comp_release_ms, comp_makeup_db;
+  int comp_ratio_code; /* 0 off, 1 = 2:1, 2 = 4:1, 3 = 8:1, 4 = limiter */
+} wbo_effects;
+int wbo_set_effects(wbo_session*, int track, const wbo_effects* fx); /* port only; libwbref.so returns -1 */
+
 void wbo_set_playhead(wbo_session*, double beat); /* Engine::set_playhead_position */
 void wbo_play(wbo_session*);                      /* Engine::play */
 void wbo_stop(wbo_session*);                      /* Engine::stop */

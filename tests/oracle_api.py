@@ -36,6 +36,7 @@ def _load(path):
     lib.wbo_add_sample.argtypes = [vp, i32, u32, u64, u32, C.POINTER(vp)]
     lib.wbo_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     lib.wbo_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
+    lib.wbo_set_effects.argtypes = [vp, i32, vp]
     lib.wbo_set_playhead.argtypes = [vp, dbl]
     lib.wbo_play.argtypes = [vp]
     lib.wbo_stop.argtypes = [vp]
@@ -113,6 +114,10 @@ class Session:
             return self.lib.wbo_add_clip_fade(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain,
                                               fade_start, fade_end)
         return self.lib.wbo_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain)
+
+    def set_effects(self, track, params):
+        """params: a ctypes struct laid out like wbo_effects (whitebox_b200.EffectParams) or None."""
+        return self.lib.wbo_set_effects(self.h, track, C.byref(params) if params is not None else None)
 
     def set_playhead(self, beat):
         self.lib.wbo_set_playhead(self.h, beat)

@@ -250,6 +250,34 @@ def fades(make_engine):
     return _collect(eng, outs, len(cfgs))
 
 
+def effects(make_engine, fxp):
+    """EXTENSION scenario (parity unpinned w.r.t. whitebox): BASELINE cfg 4 shape at test size — tracks with a
+    4-band EQ + compressor chain next to plain tracks, chain state carried across renders, one chain removed
+    mid-session. fxp(eq=..., threshold_db=..., ratio_code=...) builds the parameter struct."""
+    rng = np.random.RandomState(808)
+    B, rate = 256, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    n = 10
+    for t in range(n):
+        eng.add_track(-3.0 - t, -0.8 + 0.18 * t, False)
+        fmt = FMT_I16 if t == 7 else FMT_F32
+        sid = eng.add_sample(_src(rng, 1 if t == 5 else 2, 9000, 4, fmt), 44100 if t % 4 == 3 else 48000, fmt)
+        eng.add_clip(t, sid, (t % 3) * 0.01, 8.0, float(t), 1.0, 0.9, 0.02 if t == 2 else 0.0, 0.0)
+    eq_a = ((120.0, 4.0, 0.7), (800.0, -6.0, 1.2), (2500.0, 3.0, 2.0), (8000.0, 5.0, 0.7))
+    eq_b = ((80.0, -3.0, 0.9), (400.0, 2.0, 0.8), (5000.0, -4.0, 1.5), (12000.0, 2.5, 0.6))
+    eng.set_effects(0, fxp(eq=eq_a, threshold_db=-30.0, ratio_code=2, attack_ms=2.0, release_ms=60.0, makeup_db=3.0))
+    eng.set_effects(2, fxp(eq=eq_b))                                     # EQ only
+    eng.set_effects(3, fxp(threshold_db=-36.0, ratio_code=4))             # limiter only, resampled source
+    eng.set_effects(5, fxp(eq=eq_a, threshold_db=-40.0, ratio_code=1))    # mono source
+    eng.set_effects(7, fxp(eq=eq_b, threshold_db=-32.0, ratio_code=3))    # int16 source
+    eng.play()
+    outs = [eng.process(3), eng.process(4)]
+    eng.set_effects(2, None)  # chain removed: the track is the reference path again
+    eng.set_effects(9, fxp(eq=eq_a, threshold_db=-28.0, ratio_code=2))
+    outs.append(eng.process(3))
+    return _collect(eng, outs, n)
+
+
 def fuzz(make_engine, seed):
     """Random session: random rates / formats / speeds / clip layouts / block size, params changed mid-run."""
     rng = np.random.RandomState(1000 + seed)
@@ -292,7 +320,7 @@ def fuzz(make_engine, seed):
     return _collect(eng, outs, n_tracks)
 
 
-EXT = dict(fades=fades)  # builder-specified extensions: checked against the C port only
+EXT = dict(fades=fades, effects=effects)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
            event_split=event_split, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)

@@ -108,6 +108,31 @@ def test_fade_extension_vs_port(wb, batched):
     assert_exact(sc.fades(gpu_engine(wb, batched)), ref, "fades")
 
 
+@pytest.mark.parametrize("batched", [True, False])
+def test_effects_extension_vs_port(wb, batched):
+    """EXTENSION, parity unpinned w.r.t. whitebox (BASELINE cfg 4: 4-band biquad EQ + compressor per track): CUDA ==
+    the C port's specification bit for bit, including chain state carried across renders."""
+    ref = sc.effects(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params)
+    assert_exact(sc.effects(gpu_engine(wb, batched), wb.effect_params), ref, "effects")
+
+
+def test_effects_identity_properties(wb):
+    """A compressor that never reaches its threshold multiplies by exactly 1: bit-identical to no chain."""
+    def run(with_fx):
+        rng = np.random.RandomState(11)
+        eng = wb.Engine(2, 512, 48000, 120.0, device=0, sum_mode=wb.SUM_EXACT)
+        for t in range(6):
+            eng.add_track(-4.0, 0.1 * t, False)
+            sid = eng.add_sample(sc._src(rng, 2, 5000, 6), 48000)
+            eng.add_clip(t, sid, 0.0, 8.0, 0.0, 1.0, 0.8)
+            if with_fx and t % 2 == 0:
+                eng.set_effects(t, wb.effect_params(threshold_db=20.0, ratio_code=2))
+        eng.play()
+        return eng.render(6)
+    (a, pa), (b, pb) = run(False), run(True)
+    assert same_bits(a, b) and same_bits(pa, pb)
+
+
 def test_scalars_and_interleave(wb, golden_dir):
     g = np.load(os.path.join(golden_dir, "scalars.npz"))
     planar = g["planar"] + np.float32(0)  # the bus starts at +0, so a -0.0 source sample mixes to +0.0

@@ -27,6 +27,23 @@ class Segment(C.Structure):
                 ("fade_out_frames", C.c_double), ("clip_len_frames", C.c_double)]
 
 
+class EffectParams(C.Structure):
+    """wbx_effect_params (include/wbx.h) — same layout as the oracle's wbo_effects."""
+    _fields_ = [("eq_freq", C.c_float * 4), ("eq_gain_db", C.c_float * 4), ("eq_q", C.c_float * 4),
+                ("comp_threshold_db", C.c_float), ("comp_attack_ms", C.c_float), ("comp_release_ms", C.c_float),
+                ("comp_makeup_db", C.c_float), ("comp_ratio_code", C.c_int32)]
+
+
+def effect_params(eq=((100.0, 0.0, 0.7), (500.0, 0.0, 1.0), (3000.0, 0.0, 1.0), (9000.0, 0.0, 0.7)),
+                  threshold_db=0.0, ratio_code=0, attack_ms=5.0, release_ms=80.0, makeup_db=0.0):
+    p = EffectParams()
+    for b, (f, g, q) in enumerate(eq):
+        p.eq_freq[b], p.eq_gain_db[b], p.eq_q[b] = f, g, q
+    p.comp_threshold_db, p.comp_ratio_code = threshold_db, ratio_code
+    p.comp_attack_ms, p.comp_release_ms, p.comp_makeup_db = attack_ms, release_ms, makeup_db
+    return p
+
+
 SEGMENT_DTYPE = np.dtype([("track", "<u4"), ("block", "<u4"), ("n_blocks", "<u4"), ("dst_offset", "<u4"),
                           ("length", "<u4"), ("sample_id", "<u4"), ("src_pos", "<f8"), ("speed", "<f8"),
                           ("gain", "<f4"), ("flags", "<u4"), ("clip_frame", "<f8"), ("fade_in_frames", "<f8"),
@@ -39,12 +56,12 @@ WBX_SYMBOLS = [
     "wbx_abi_version", "wbx_create", "wbx_destroy", "wbx_last_error", "wbx_configure", "wbx_set_track_count",
     "wbx_set_sum_mode", "wbx_set_stream", "wbx_sample_upload", "wbx_sample_release", "wbx_sample_update", "wbx_render", "wbx_submit",
     "wbx_mix", "wbx_fetch", "wbx_fetch_levels", "wbx_host_alloc", "wbx_host_free", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
-    "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel",
+    "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel", "wbx_effects_design", "wbx_set_track_effects",
 ]
 WBXH_SYMBOLS = [
     "wbxh_create", "wbxh_destroy", "wbxh_last_error", "wbxh_device", "wbxh_add_track", "wbxh_set_volume",
     "wbxh_set_pan", "wbxh_set_mute", "wbxh_add_sample", "wbxh_add_clip", "wbxh_add_clip_fade", "wbxh_set_playhead",
-    "wbxh_play",
+    "wbxh_play", "wbxh_set_effects",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
 ]
@@ -113,6 +130,7 @@ def lib():
     L.wbxh_add_sample.argtypes = [vp, i32, u32, u64, u32, pp]
     L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     L.wbxh_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
+    L.wbxh_set_effects.argtypes = [vp, i32, vp]
     L.wbxh_set_playhead.argtypes = [vp, dbl]
     L.wbxh_set_playhead.restype = None
     for f in ("wbxh_play", "wbxh_stop"):
@@ -368,6 +386,10 @@ class Engine:
             return self._ck(self.L.wbxh_add_clip_fade(self.h, track, sample, min_beat, max_beat, start_offset, speed,
                                                       gain, fade_start, fade_end))
         return self._ck(self.L.wbxh_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain))
+
+    def set_effects(self, track, params):
+        """params: EffectParams (see effect_params()) or None to remove the chain."""
+        self._ck(self.L.wbxh_set_effects(self.h, track, C.byref(params) if params is not None else None))
 
     def set_playhead(self, beat):
         self.L.wbxh_set_playhead(self.h, beat)

@@ -2,6 +2,7 @@
 // kernel launches, result copies. No torch, no CPU fallback: every entry point fails loudly without a device.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +24,8 @@ cudaError_t launch_interleave(const float* bus, uint64_t frames, uint32_t channe
 cudaError_t launch_interleave_sample(const void* planar, size_t plane_bytes, uint64_t frames, uint32_t nch,
                                      uint32_t esize, void* dst, int n_sm, cudaStream_t stream);
 int mix_warps_per_sm(int fpl);
+cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
+                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, cudaStream_t stream);
 }  // namespace wbx
 
 using namespace wbx;
@@ -57,8 +60,8 @@ struct wbx_engine {
   uint32_t C = 2, B = 512, rate = 48000, n_tracks = 0;
   int sum_mode = WBX_SUM_AUTO;
   std::vector<SampleRec> samples;
-  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels;
-  HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv, h_levels;
+  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels, d_fx, d_trackbuf;
+  HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv, h_levels, h_fx;
   std::vector<uint32_t> slot_busy;  // [track][slot] -> first free block
   uint32_t slot_cap = 0;
   // last submit
@@ -66,6 +69,12 @@ struct wbx_engine {
   bool submitted = false, mixed = false;
   uint64_t launches = 0;
   uint32_t upload_flip = 0;
+  // effect chains (extension): host copy of the designed coefficients per track, device array with state
+  std::vector<wbx_effects> fx;       // indexed by track
+  std::vector<uint8_t> fx_on;        // track has a chain
+  std::vector<uint8_t> fx_reset;     // clear the track's state at the next submit
+  bool fx_dirty = false;
+  uint32_t n_fx = 0;                 // chains resident in d_fx
   char err[256] = {0};
   char kernel_name[64] = {0};
 };
@@ -203,9 +212,9 @@ int wbx_destroy(wbx_engine* e) {
   for (auto& s : e->samples)
     if (s.live) cudaFree(s.d_base);
   for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv,
-                    &e->d_upload, &e->d_levels})
+                    &e->d_upload, &e->d_levels, &e->d_fx, &e->d_trackbuf})
     if (b->p) cudaFree(b->p);
-  for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels})
+  for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
     if (b->p) cudaFreeHost(b->p);
   cudaStreamDestroy(e->own_stream);
   delete e;
@@ -228,6 +237,12 @@ int wbx_configure(wbx_engine* e, uint32_t out_channels, uint32_t block_frames, u
 
 int wbx_set_track_count(wbx_engine* e, uint32_t n_tracks) {
   if (!e) return WBX_ERR_INVALID;
+  if (n_tracks != e->n_tracks && !e->fx.empty()) {  // chains are attached to track indices
+    e->fx.resize(n_tracks);
+    e->fx_on.resize(n_tracks, 0);
+    e->fx_reset.resize(n_tracks, 1);
+    e->fx_dirty = true;
+  }
   e->n_tracks = n_tracks;
   e->submitted = e->mixed = false;
   return WBX_OK;
@@ -320,6 +335,133 @@ int wbx_sample_release(wbx_engine* e, uint32_t id) {
   return WBX_OK;
 }
 
+// RBJ "Audio EQ Cookbook" biquad, designed in f64, normalised by a0, stored f32 (same formulas as the C port).
+static void design_band(int band, double freq, double gain_db, double q, double rate, float* b0, float* b1, float* b2,
+                        float* a1, float* a2) {
+  const double pi = 3.141592653589793238462643383279502884;
+  const double A = std::pow(10.0, gain_db / 40.0);
+  const double w0 = 2.0 * pi * freq / rate;
+  const double cw = std::cos(w0), sw = std::sin(w0);
+  const double alpha = sw / (2.0 * q);
+  double B0, B1, B2, A0, A1, A2;
+  if (band == 0) {  // low shelf
+    const double sq = 2.0 * std::sqrt(A) * alpha;
+    B0 = A * ((A + 1.0) - (A - 1.0) * cw + sq);
+    B1 = 2.0 * A * ((A - 1.0) - (A + 1.0) * cw);
+    B2 = A * ((A + 1.0) - (A - 1.0) * cw - sq);
+    A0 = (A + 1.0) + (A - 1.0) * cw + sq;
+    A1 = -2.0 * ((A - 1.0) + (A + 1.0) * cw);
+    A2 = (A + 1.0) + (A - 1.0) * cw - sq;
+  } else if (band == 3) {  // high shelf
+    const double sq = 2.0 * std::sqrt(A) * alpha;
+    B0 = A * ((A + 1.0) + (A - 1.0) * cw + sq);
+    B1 = -2.0 * A * ((A - 1.0) + (A + 1.0) * cw);
+    B2 = A * ((A + 1.0) + (A - 1.0) * cw - sq);
+    A0 = (A + 1.0) - (A - 1.0) * cw + sq;
+    A1 = 2.0 * ((A - 1.0) - (A + 1.0) * cw);
+    A2 = (A + 1.0) - (A - 1.0) * cw - sq;
+  } else {  // peaking
+    B0 = 1.0 + alpha * A;
+    B1 = -2.0 * cw;
+    B2 = 1.0 - alpha * A;
+    A0 = 1.0 + alpha / A;
+    A1 = -2.0 * cw;
+    A2 = 1.0 - alpha / A;
+  }
+  *b0 = (float)(B0 / A0);
+  *b1 = (float)(B1 / A0);
+  *b2 = (float)(B2 / A0);
+  *a1 = (float)(A1 / A0);
+  *a2 = (float)(A2 / A0);
+}
+
+int wbx_effects_design(const wbx_effect_params* p, uint32_t sample_rate, wbx_effects* out) {
+  if (!p || !out || sample_rate == 0) return WBX_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  for (int b = 0; b < 4; b++) {
+    if (p->eq_gain_db[b] != 0.0f) out->eq_on = 1;
+    if (!(p->eq_freq[b] > 0.0f) || !(p->eq_q[b] > 0.0f)) return WBX_ERR_INVALID;
+    design_band(b, p->eq_freq[b], p->eq_gain_db[b], p->eq_q[b], (double)sample_rate, &out->b0[b], &out->b1[b],
+                &out->b2[b], &out->a1[b], &out->a2[b]);
+  }
+  if (p->comp_ratio_code < 0 || p->comp_ratio_code > 4) return WBX_ERR_INVALID;
+  out->comp_ratio_code = (uint32_t)p->comp_ratio_code;
+  out->comp_on = p->comp_ratio_code != 0;
+  out->comp_threshold = (float)std::pow(10.0, (double)p->comp_threshold_db / 20.0);
+  out->comp_makeup = (float)std::pow(10.0, (double)p->comp_makeup_db / 20.0);
+  out->comp_attack = (float)std::exp(-1.0 / ((double)p->comp_attack_ms * 0.001 * (double)sample_rate));
+  out->comp_release = (float)std::exp(-1.0 / ((double)p->comp_release_ms * 0.001 * (double)sample_rate));
+  return WBX_OK;
+}
+
+int wbx_set_track_effects(wbx_engine* e, uint32_t track, const wbx_effects* fx) {
+  if (!e) return WBX_ERR_INVALID;
+  if (track >= e->n_tracks) return fail(e, WBX_ERR_INVALID, "effects: track %u >= %u", track, e->n_tracks);
+  if (e->fx.size() < e->n_tracks) {
+    e->fx.resize(e->n_tracks);
+    e->fx_on.resize(e->n_tracks, 0);
+    e->fx_reset.resize(e->n_tracks, 0);
+  }
+  const bool on = fx && (fx->eq_on || fx->comp_on);
+  if (on) e->fx[track] = *fx;
+  e->fx_on[track] = on ? 1 : 0;
+  e->fx_reset[track] = 1;
+  e->fx_dirty = true;
+  return WBX_OK;
+}
+
+// (re)build the compact device array of chains, keeping the running state of tracks whose chain did not change
+static int sync_effects(wbx_engine* e) {
+  if (!e->fx_dirty) return WBX_OK;
+  std::vector<DFx> old;
+  if (e->n_fx) {
+    old.resize(e->n_fx);
+    CU(e, cudaMemcpyAsync(old.data(), e->d_fx.p, e->n_fx * sizeof(DFx), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+  }
+  std::vector<DFx> cur;
+  for (uint32_t t = 0; t < e->n_tracks && t < e->fx_on.size(); t++) {
+    if (!e->fx_on[t]) continue;
+    DFx d;
+    memset(&d, 0, sizeof(d));
+    const wbx_effects& f = e->fx[t];
+    d.track = t;
+    d.eq_on = f.eq_on;
+    d.comp_on = f.comp_on;
+    d.ratio_code = f.comp_ratio_code;
+    for (int b = 0; b < 4; b++) {
+      d.b0[b] = f.b0[b];
+      d.b1[b] = f.b1[b];
+      d.b2[b] = f.b2[b];
+      d.a1[b] = f.a1[b];
+      d.a2[b] = f.a2[b];
+    }
+    d.thr = f.comp_threshold;
+    d.att = f.comp_attack;
+    d.rel = f.comp_release;
+    d.makeup = f.comp_makeup;
+    if (!e->fx_reset[t])
+      for (const DFx& o : old)
+        if (o.track == t) {
+          memcpy(d.s1, o.s1, sizeof(d.s1));
+          memcpy(d.s2, o.s2, sizeof(d.s2));
+          memcpy(d.env, o.env, sizeof(d.env));
+        }
+    cur.push_back(d);
+  }
+  std::fill(e->fx_reset.begin(), e->fx_reset.end(), 0);
+  e->n_fx = (uint32_t)cur.size();
+  if (e->n_fx) {
+    int rc = dev_reserve(e, e->d_fx, cur.size() * sizeof(DFx));
+    if (rc) return rc;
+    if ((rc = host_reserve(e, e->h_fx, cur.size() * sizeof(DFx)))) return rc;
+    memcpy(e->h_fx.p, cur.data(), cur.size() * sizeof(DFx));
+    CU(e, cudaMemcpyAsync(e->d_fx.p, e->h_fx.p, cur.size() * sizeof(DFx), cudaMemcpyHostToDevice, e->stream));
+  }
+  e->fx_dirty = false;
+  return WBX_OK;
+}
+
 int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
                uint32_t n_blocks) {
   if (!e) return WBX_ERR_INVALID;
@@ -331,7 +473,9 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   int rc;
 
   // ---- validate + resolve segments into spans (pinned staging), assign cell slots --------------------
-  if ((rc = host_reserve(e, e->h_spans, (size_t)(n_segs ? n_segs : 1) * sizeof(DSpan)))) return rc;
+  if ((rc = sync_effects(e))) return rc;
+  const uint32_t n_fx = e->n_fx;
+  if ((rc = host_reserve(e, e->h_spans, (size_t)(n_segs + n_fx + 1) * sizeof(DSpan)))) return rc;
   if ((rc = host_reserve(e, e->h_gains, (size_t)(N ? N : 1) * 2 * sizeof(float)))) return rc;
   DSpan* hs = (DSpan*)e->h_spans.p;
   uint32_t slots = 1;
@@ -395,19 +539,48 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   const size_t n_cells = (size_t)n_blocks * N * slots;
   const size_t bus_floats = (size_t)C * n_blocks * B;
   const size_t peak_floats = (size_t)n_blocks * N * 2;
-  if ((rc = dev_reserve(e, e->d_spans, (size_t)(n_segs ? n_segs : 1) * sizeof(DSpan)))) return rc;
+  if ((rc = dev_reserve(e, e->d_spans, (size_t)(n_segs + n_fx + 1) * sizeof(DSpan)))) return rc;
+  if (n_fx) {
+    // tracks with an effect chain are rendered to a per-track buffer (frame-interleaved stereo f32) that the mix
+    // kernel then reads as one whole-block unity-speed call per callback with clip gain 1.0
+    const size_t tb_floats = (size_t)n_fx * n_blocks * B * 2;
+    if ((rc = dev_reserve(e, e->d_trackbuf, tb_floats * sizeof(float) + 256))) return rc;
+    const DFx* hf = (const DFx*)e->h_fx.p;
+    for (uint32_t i = 0; i < n_fx; i++) {
+      DSpan& d = hs[n_segs + i];
+      memset(&d, 0, sizeof(d));
+      d.base = (const float*)e->d_trackbuf.p + (size_t)i * n_blocks * B * 2;
+      d.pos0 = 0.0;
+      d.speed = 1.0;
+      d.count = (uint64_t)n_blocks * B;
+      d.gain = 1.0f;
+      d.track = hf[i].track;
+      d.block0 = 0;
+      d.n_blocks = n_blocks;
+      d.dst_off = 0;
+      d.length = B;
+      d.fmt = WBX_FMT_F32;
+      d.slot = 0;
+      d.nch = 2;
+    }
+  }
   if ((rc = dev_reserve(e, e->d_gains, (size_t)(N ? N : 1) * 2 * sizeof(float)))) return rc;
   if ((rc = dev_reserve(e, e->d_cells, (n_cells ? n_cells : 1) * sizeof(DCell)))) return rc;
   if ((rc = dev_reserve(e, e->d_bus, bus_floats * sizeof(float)))) return rc;
   if ((rc = dev_reserve(e, e->d_peaks, (peak_floats ? peak_floats : 1) * sizeof(float)))) return rc;
 
-  if (n_segs)
-    CU(e, cudaMemcpyAsync(e->d_spans.p, hs, (size_t)n_segs * sizeof(DSpan), cudaMemcpyHostToDevice, e->stream));
+  if (n_segs + n_fx)
+    CU(e, cudaMemcpyAsync(e->d_spans.p, hs, (size_t)(n_segs + n_fx) * sizeof(DSpan), cudaMemcpyHostToDevice, e->stream));
   if (N) CU(e, cudaMemcpyAsync(e->d_gains.p, e->h_gains.p, (size_t)N * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   if (n_cells) CU(e, cudaMemsetAsync(e->d_cells.p, 0xFF, n_cells * sizeof(DCell), e->stream));  // span = kSilent
   if (n_segs && N) {
     CU(e, launch_expand((const DSpan*)e->d_spans.p, n_segs, (DCell*)e->d_cells.p, N, slots, e->stream));
     e->launches++;
+  }
+  if (n_fx && N) {
+    CU(e, launch_effects((const DSpan*)e->d_spans.p, (DCell*)e->d_cells.p, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
+                         n_segs, (float*)e->d_trackbuf.p, e->stream));
+    e->launches += 3;
   }
   e->n_blocks = n_blocks;
   e->n_spans = n_segs;

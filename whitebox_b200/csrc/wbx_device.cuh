@@ -77,6 +77,16 @@ struct __align__(16) Desc {
 };
 static_assert(sizeof(Desc) == 64, "Desc layout");
 
+// effect chain of one track (extension, include/wbx.h): coefficients + running state
+struct DFx {
+  uint32_t track, eq_on, comp_on, ratio_code;
+  float b0[4], b1[4], b2[4], a1[4], a2[4];
+  float thr, att, rel, makeup;
+  float s1[2][4], s2[2][4], env[2];  // state, persists across renders
+  uint32_t pad[2];
+};
+static_assert(sizeof(DFx) == 16 + 80 + 16 + 72 + 8, "DFx layout");
+
 struct MixParams {
   const DSpan* spans;
   const DCell* cells;

@@ -54,6 +54,11 @@ void Track::set_pan(float pan) {
   ui_parameter_state.pan = pan;
   track_msg_queue.push_back({kParamPan, (double)pan});
 }
+void Track::set_effects(const wbx_effect_params* params) {
+  effects_on = params != nullptr;
+  if (params) effect_params = *params;
+  effects_dirty = true;
+}
 void Track::set_mute(bool mute) {
   ui_parameter_state.mute = mute;
   track_msg_queue.push_back({kParamMute, (double)mute});
@@ -538,6 +543,19 @@ int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, 
   const uint32_t N = (uint32_t)tracks.size();
   int rc = wbx_set_track_count(dev_, N);
   if (rc) return rc;
+  for (uint32_t i = 0; i < N; i++) {  // effect chains edited since the last render
+    Track& t = *tracks[i];
+    if (!t.effects_dirty) continue;
+    wbx_effects fx;
+    if (t.effects_on) {
+      if ((rc = wbx_effects_design(&t.effect_params, sample_rate_, &fx))) return rc;
+      rc = wbx_set_track_effects(dev_, i, &fx);
+    } else {
+      rc = wbx_set_track_effects(dev_, i, nullptr);
+    }
+    if (rc) return rc;
+    t.effects_dirty = false;
+  }
   schedule(n_blocks, sample_rate);
   rc = wbx_submit(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n_blocks);
   if (rc) return rc;
@@ -613,6 +631,11 @@ int wbxh_add_clip_fade(wbxh_engine* h, int track, int sample, double min_beat, d
   if (track < 0 || (size_t)track >= h->eng.tracks.size() || sample < 0) return WBX_ERR_INVALID;
   return h->eng.add_audio_clip(h->eng.tracks[track], min_beat, max_beat, start_offset, (uint32_t)sample, speed, gain,
                                fade_start, fade_end);
+}
+int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params) {
+  if (track < 0 || (size_t)track >= h->eng.tracks.size()) return WBX_ERR_INVALID;
+  h->eng.tracks[track]->set_effects(params);
+  return WBX_OK;
 }
 void wbxh_set_playhead(wbxh_engine* h, double beat) { h->eng.set_playhead_position(beat); }
 void wbxh_play(wbxh_engine* h) { h->eng.play(); }

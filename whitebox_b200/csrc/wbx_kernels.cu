@@ -771,6 +771,144 @@ __global__ void interleave_sample_kernel(const uint8_t* __restrict__ planar, siz
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// effect chain (extension): render the tracks that carry a chain into a per-track buffer, run the chain
+// sequentially in time, then let the mix kernel read that buffer like any other resident sample
+// ---------------------------------------------------------------------------------------------------------
+
+// value one Sampler::stream call adds at segment-relative frame jj for output channel c (generic, from global)
+__device__ __forceinline__ float stream_value(const DSpan& sp, const DCell& cell, int32_t jj, uint32_t c,
+                                              uint32_t block_in_run) {
+  const uint32_t nch = sp.nch;
+  const uint32_t ch = c % nch;
+  float sv;
+  if (sp.speed == 1.0) {
+    const int64_t ip = (int64_t)(uint32_t)(int64_t)cell.pos;
+    sv = load_unity_rt(sp.fmt, sp.base, (ip + jj) * nch + ch);
+  } else {
+    const double x = __dadd_rn(cell.pos, __dmul_rn((double)jj, sp.speed));
+    const int64_t ix = __double2ll_rz(x);
+    const float fx = __double2float_rn(__dsub_rn(x, __ll2double_rn(ix)));
+    const float a = load_lin_rt(sp.fmt, sp.base, ix * nch + ch), b = load_lin_rt(sp.fmt, sp.base, (ix + 1) * nch + ch);
+    sv = __fadd_rn(a, __fmul_rn(fx, __fsub_rn(b, a)));
+  }
+  float m = __fmul_rn(sv, sp.gain);
+  if (sp.fade) {
+    FadeEnv fe;
+    fe.n0 = sp.clip_frame + (double)block_in_run * (double)sp.length;
+    fe.fin = sp.fade_in;
+    fe.fout = sp.fade_out;
+    fe.len = sp.clip_len;
+    m = __fmul_rn(m, fe.at(jj));
+  }
+  return m;
+}
+
+// one warp per (effect track e, callback k): the track's mixing buffer before effects, frame-interleaved stereo
+__global__ void render_tracks_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells,
+                                     const DFx* __restrict__ fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
+                                     uint32_t B, uint32_t C, float* __restrict__ trackbuf) {
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (w >= (uint64_t)n_fx * K) return;
+  const uint32_t e = (uint32_t)(w / K), k = (uint32_t)(w % K);
+  const uint32_t t = fx[e].track;
+  float2* out = reinterpret_cast<float2*>(trackbuf) + ((size_t)e * K + k) * B;
+  for (uint32_t j = lane; j < B; j += 32) {
+    float2 v = make_float2(0.0f, 0.0f);
+    for (uint32_t s = 0; s < S; s++) {
+      const DCell cell = cells[((size_t)k * N + t) * S + s];
+      if (cell.span == kSilent) continue;
+      const DSpan sp = spans[cell.span];
+      if (j >= sp.dst_off && j < sp.dst_off + cell.n_act) {
+        const int32_t jj = (int32_t)(j - sp.dst_off);
+        v.x = __fadd_rn(v.x, stream_value(sp, cell, jj, 0, k - sp.block0));  // dst += ... on a cleared buffer
+        if (C == 2) v.y = __fadd_rn(v.y, stream_value(sp, cell, jj, 1, k - sp.block0));
+      }
+    }
+    out[j] = v;
+  }
+}
+
+// one thread per (effect track, channel): the chain is a recurrence in time. Same operations, same order as
+// oracle/wb_oracle.c apply_effects (every op a single IEEE rn op; __fmaf_rn = fmaf).
+__global__ void effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t frames,
+                               float* __restrict__ trackbuf) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_fx * C) return;
+  const uint32_t e = id / C, c = id % C;
+  DFx* f = fx + e;
+  float* buf = trackbuf + (size_t)e * frames * 2 + c;
+  const bool eq_on = f->eq_on != 0, comp_on = f->comp_on != 0;
+  float b0[4], b1[4], b2[4], a1[4], a2[4], s1[4], s2[4];
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    b0[b] = f->b0[b];
+    b1[b] = f->b1[b];
+    b2[b] = f->b2[b];
+    a1[b] = f->a1[b];
+    a2[b] = f->a2[b];
+    s1[b] = f->s1[c][b];
+    s2[b] = f->s2[c][b];
+  }
+  const float thr = f->thr, att = f->att, rel = f->rel, makeup = f->makeup;
+  const uint32_t code = f->ratio_code;
+  float env = f->env[c];
+  for (uint64_t j = 0; j < frames; j++) {
+    float x = buf[j * 2];
+    if (eq_on) {
+#pragma unroll
+      for (int b = 0; b < 4; b++) {  // transposed direct form II
+        const float y = __fmaf_rn(b0[b], x, s1[b]);
+        s1[b] = __fmaf_rn(b1[b], x, __fmaf_rn(-a1[b], y, s2[b]));
+        s2[b] = __fmaf_rn(b2[b], x, -__fmul_rn(a2[b], y));
+        x = y;
+      }
+    }
+    if (comp_on) {
+      const float xa = fabsf(x);
+      env = xa > env ? __fmaf_rn(att, __fsub_rn(env, xa), xa) : __fmaf_rn(rel, __fsub_rn(env, xa), xa);
+      float g = 1.0f;
+      if (env > thr) {
+        const float r = __fdiv_rn(thr, env);
+        const float r2 = __fsqrt_rn(r);
+        switch (code) {
+          case 1: g = r2; break;
+          case 2: g = __fmul_rn(r2, __fsqrt_rn(r2)); break;
+          case 3: g = __fmul_rn(__fmul_rn(r2, __fsqrt_rn(r2)), __fsqrt_rn(__fsqrt_rn(r2))); break;
+          default: g = r; break;
+        }
+      }
+      x = __fmul_rn(__fmul_rn(x, g), makeup);
+    }
+    buf[j * 2] = x;
+  }
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    f->s1[c][b] = s1[b];
+    f->s2[c][b] = s2[b];
+  }
+  f->env[c] = env;
+}
+
+// point the cells of effect tracks at their processed buffer: one whole-block unity call per callback
+__global__ void patch_fx_cells_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
+                                      uint32_t B, uint32_t first_fx_span, DCell* __restrict__ cells) {
+  const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (uint64_t)n_fx * K) return;
+  const uint32_t e = (uint32_t)(id / K), k = (uint32_t)(id % K);
+  DCell* c = cells + ((size_t)k * N + fx[e].track) * S;
+  DCell v;
+  v.pos = (double)k * (double)B;
+  v.span = first_fx_span + e;
+  v.n_act = B;
+  c[0] = v;
+  v.pos = 0.0;
+  v.span = kSilent;
+  v.n_act = 0;
+  for (uint32_t s = 1; s < S; s++) c[s] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------------------
 __global__ void clamp_kernel(float* __restrict__ x, uint64_t n) {
@@ -907,6 +1045,16 @@ cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, ui
                           cudaStream_t stream) {
   if (n_spans == 0) return cudaSuccess;
   expand_schedule<<<(n_spans + 3) / 4, 128, 0, stream>>>(spans, n_spans, cells, n_tracks, slots);  // warp per span
+  return cudaGetLastError();
+}
+
+cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
+                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, cudaStream_t stream) {
+  if (n_fx == 0) return cudaSuccess;
+  const uint64_t warps = (uint64_t)n_fx * K;
+  render_tracks_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, trackbuf);
+  effects_kernel<<<(n_fx * C + 31) / 32, 32, 0, stream>>>(fx, n_fx, C, (uint64_t)K * B, trackbuf);
+  patch_fx_cells_kernel<<<(unsigned)((warps + 127) / 128), 128, 0, stream>>>(fx, n_fx, N, S, K, B, first_fx_span, cells);
   return cudaGetLastError();
 }
 
