@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--rate", type=int, default=48000, help="source sample rate (44100 -> linear resample)")
     ap.add_argument("--offset", type=int, default=0, help="clip start offset in frames (unaligned windows)")
     ap.add_argument("--tree", type=int, default=0)
+    ap.add_argument("--fx", type=int, default=0, help="1: every track carries the 4-band EQ + compressor chain (cfg 4)")
     args = ap.parse_args()
     import torch
     import whitebox_b200 as wb
@@ -40,6 +41,25 @@ def main():
     stream = torch.cuda.Stream()
     dev.set_stream(stream.cuda_stream)
     dev.set_sum_mode(wb.SUM_TREE if args.tree else wb.SUM_EXACT)
+    if args.fx:
+        import ctypes as C
+        p = wb.effect_params(eq=((120.0, 4.0, 0.7), (800.0, -6.0, 1.2), (2500.0, 3.0, 2.0), (8000.0, 5.0, 0.7)),
+                             threshold_db=-30.0, ratio_code=2, attack_ms=2.0, release_ms=60.0, makeup_db=3.0)
+        fx = (C.c_uint8 * 256)()
+        assert wb.lib().wbx_effects_design(C.byref(p), 48000, fx) == 0
+        for t in range(N):
+            assert wb.lib().wbx_set_track_effects(dev.h, t, fx) == 0
+        with torch.cuda.stream(stream):
+            dev.submit(segs, gains, K)  # warm-up (allocations)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.iters):
+                dev.submit(segs, gains, K)  # expand + render tracks + effect chains + cell patch
+            e1.record(stream)
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        print("fx submit (expand + render_tracks + effects + patch), %d tracks x %d callbacks: %.3f ms  %.3e track-frames/s" %
+              (N, K, ms, N * K * B / ms * 1e3), flush=True)
     dev.submit(segs, gains, K)
     bytes_alg = N * K * B * 8 * speed
     for fpl in args.fpl.split(","):

@@ -110,6 +110,8 @@ def lib():
     L.wbx_device_peaks.argtypes = [vp, pp, C.POINTER(u64)]
     L.wbx_clamp_device.argtypes = [vp, vp, u64]
     L.wbx_synchronize.argtypes = [vp]
+    L.wbx_effects_design.argtypes = [vp, u32, vp]
+    L.wbx_set_track_effects.argtypes = [vp, u32, vp]
     L.wbx_launch_count.argtypes = [vp]
     L.wbx_launch_count.restype = u64
     L.wbx_last_kernel.argtypes = [vp]

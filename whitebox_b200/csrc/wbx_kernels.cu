@@ -829,17 +829,54 @@ __global__ void render_tracks_kernel(const DSpan* __restrict__ spans, const DCel
   }
 }
 
-// one thread per (effect track, channel): the chain is a recurrence in time. Same operations, same order as
-// oracle/wb_oracle.c apply_effects (every op a single IEEE rn op; __fmaf_rn = fmaf).
+// The chain is a recurrence in time: one THREAD per (effect track, channel) carries the state in registers and
+// walks the whole render, 16 frames at a time so the loads of a chunk are in flight together. Same operations, same order as oracle/wb_oracle.c apply_effects (every op a single IEEE rn op;
+// __fmaf_rn = fmaf). Time-parallel (scan) evaluation of the biquads would re-associate and is left for later.
+struct FxChannel {
+  float s1[4], s2[4], env;
+};
+
+__device__ __forceinline__ float fx_sample(float x, FxChannel& st, const float (&b0)[4], const float (&b1)[4],
+                                           const float (&b2)[4], const float (&a1)[4], const float (&a2)[4], bool eq_on,
+                                           bool comp_on, float thr, float att, float rel, float makeup, uint32_t code) {
+  if (eq_on) {
+#pragma unroll
+    for (int b = 0; b < 4; b++) {  // transposed direct form II
+      const float y = __fmaf_rn(b0[b], x, st.s1[b]);
+      st.s1[b] = __fmaf_rn(b1[b], x, __fmaf_rn(-a1[b], y, st.s2[b]));
+      st.s2[b] = __fmaf_rn(b2[b], x, -__fmul_rn(a2[b], y));
+      x = y;
+    }
+  }
+  if (comp_on) {
+    const float xa = fabsf(x);
+    st.env = xa > st.env ? __fmaf_rn(att, __fsub_rn(st.env, xa), xa) : __fmaf_rn(rel, __fsub_rn(st.env, xa), xa);
+    float g = 1.0f;
+    if (st.env > thr) {
+      const float r = __fdiv_rn(thr, st.env);
+      const float r2 = __fsqrt_rn(r);
+      switch (code) {
+        case 1: g = r2; break;
+        case 2: g = __fmul_rn(r2, __fsqrt_rn(r2)); break;
+        case 3: g = __fmul_rn(__fmul_rn(r2, __fsqrt_rn(r2)), __fsqrt_rn(__fsqrt_rn(r2))); break;
+        default: g = r; break;
+      }
+    }
+    x = __fmul_rn(__fmul_rn(x, g), makeup);
+  }
+  return x;
+}
+
 __global__ void effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t frames,
                                float* __restrict__ trackbuf) {
   const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_fx * C) return;
   const uint32_t e = id / C, c = id % C;
   DFx* f = fx + e;
-  float* buf = trackbuf + (size_t)e * frames * 2 + c;
+  float* buf = trackbuf + (size_t)e * frames * 2 + c;  // this channel: every second float
   const bool eq_on = f->eq_on != 0, comp_on = f->comp_on != 0;
-  float b0[4], b1[4], b2[4], a1[4], a2[4], s1[4], s2[4];
+  float b0[4], b1[4], b2[4], a1[4], a2[4];
+  FxChannel st;
 #pragma unroll
   for (int b = 0; b < 4; b++) {
     b0[b] = f->b0[b];
@@ -847,47 +884,30 @@ __global__ void effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, 
     b2[b] = f->b2[b];
     a1[b] = f->a1[b];
     a2[b] = f->a2[b];
-    s1[b] = f->s1[c][b];
-    s2[b] = f->s2[c][b];
+    st.s1[b] = f->s1[c][b];
+    st.s2[b] = f->s2[c][b];
   }
+  st.env = f->env[c];
   const float thr = f->thr, att = f->att, rel = f->rel, makeup = f->makeup;
   const uint32_t code = f->ratio_code;
-  float env = f->env[c];
-  for (uint64_t j = 0; j < frames; j++) {
-    float x = buf[j * 2];
-    if (eq_on) {
+  constexpr int CH = 16;  // frames per chunk: the chunk's loads are in flight together
+  uint64_t j = 0;
+  for (; j + CH <= frames; j += CH) {
+    float v[CH];
 #pragma unroll
-      for (int b = 0; b < 4; b++) {  // transposed direct form II
-        const float y = __fmaf_rn(b0[b], x, s1[b]);
-        s1[b] = __fmaf_rn(b1[b], x, __fmaf_rn(-a1[b], y, s2[b]));
-        s2[b] = __fmaf_rn(b2[b], x, -__fmul_rn(a2[b], y));
-        x = y;
-      }
-    }
-    if (comp_on) {
-      const float xa = fabsf(x);
-      env = xa > env ? __fmaf_rn(att, __fsub_rn(env, xa), xa) : __fmaf_rn(rel, __fsub_rn(env, xa), xa);
-      float g = 1.0f;
-      if (env > thr) {
-        const float r = __fdiv_rn(thr, env);
-        const float r2 = __fsqrt_rn(r);
-        switch (code) {
-          case 1: g = r2; break;
-          case 2: g = __fmul_rn(r2, __fsqrt_rn(r2)); break;
-          case 3: g = __fmul_rn(__fmul_rn(r2, __fsqrt_rn(r2)), __fsqrt_rn(__fsqrt_rn(r2))); break;
-          default: g = r; break;
-        }
-      }
-      x = __fmul_rn(__fmul_rn(x, g), makeup);
-    }
-    buf[j * 2] = x;
+    for (int q = 0; q < CH; q++) v[q] = buf[(j + q) * 2];
+#pragma unroll
+    for (int q = 0; q < CH; q++) v[q] = fx_sample(v[q], st, b0, b1, b2, a1, a2, eq_on, comp_on, thr, att, rel, makeup, code);
+#pragma unroll
+    for (int q = 0; q < CH; q++) buf[(j + q) * 2] = v[q];
   }
+  for (; j < frames; j++) buf[j * 2] = fx_sample(buf[j * 2], st, b0, b1, b2, a1, a2, eq_on, comp_on, thr, att, rel, makeup, code);
 #pragma unroll
   for (int b = 0; b < 4; b++) {
-    f->s1[c][b] = s1[b];
-    f->s2[c][b] = s2[b];
+    f->s1[c][b] = st.s1[b];
+    f->s2[c][b] = st.s2[b];
   }
-  f->env[c] = env;
+  f->env[c] = st.env;
 }
 
 // point the cells of effect tracks at their processed buffer: one whole-block unity call per callback
