@@ -124,6 +124,15 @@ int wbx_sample_release(wbx_engine* e, uint32_t id);
  * must then stay valid until the next wbx_synchronize / wbx_fetch; pageable arrays are copied before return. */
 int wbx_sample_update(wbx_engine* e, uint32_t id, const void* const* planar);
 
+/* Waveform peak mip-maps of a resident sample — WaveformVisual::create + summarize_for_mipmaps_impl
+ * (gfx/waveform_visual.cpp:9-173,181-248), which the reference runs on every sample import
+ * (engine/assets_table.cpp:34,56). quality 0 = Low (int8), 1 = High (int16); level l summarises chunks of
+ * 2^(2l+1) frames into (first, second) = (min, max) ordered by first occurrence; layout [channels][*count].
+ * Copies level `level` to host memory `out` when it fits cap_elems elements (out may be NULL to query *count)
+ * and returns the number of levels (>= 0) or a negative wbx_status. */
+int wbx_sample_mipmap(wbx_engine* e, uint32_t id, int quality, int level, void* out, uint64_t cap_elems,
+                      uint32_t* count);
+
 /* ---- per-track effect chain — EXTENSION, not in the reference ---------------------------------------------- */
 /* whitebox has no DSP effects (its per-track slot is a third-party VST3 instance, engine/track.h:124,
  * engine/track.cpp:645-662). This is the built-in chain a PluginFormat::Native effect would provide

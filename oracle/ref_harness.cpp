@@ -13,9 +13,15 @@
 #include "engine/assets_table.h"
 #include "engine/engine.h"
 #include "engine/track.h"
+#include "gfx/renderer.h"
+#include "gfx/waveform_visual.h"
 #include "wbo.h"
 
 using namespace wb;
+
+namespace wb {
+void* wbref_buffer_memory(GPUBuffer* b);  // ref_stubs.cpp: host memory behind a buffer of the stand-in renderer
+}
 
 struct wbo_session {
   Engine engine;
@@ -132,6 +138,21 @@ double wbo_time_process(wbo_session* s, uint32_t n_blocks) {
     s->engine.process(s->in, s->out, (double)s->rate);
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int wbo_mipmap(wbo_session* s, int sample, int quality, int level, void* out, uint64_t cap_elems, uint32_t* count) {
+  Sample* smp = &s->samples[sample]->sample_instance;
+  WaveformVisual* v = WaveformVisual::create(smp, quality ? WaveformVisualQuality::High : WaveformVisualQuality::Low);
+  if (!v) return -1;
+  const int n_levels = (int)v->mipmaps.size();
+  if (level >= 0 && level < n_levels) {
+    const WaveformMipmap& m = v->mipmaps[level];
+    const uint64_t elems = (uint64_t)m.count * smp->channels;
+    if (count) *count = m.count;
+    if (out && elems <= cap_elems) std::memcpy(out, wbref_buffer_memory(m.data), elems * (quality ? 2 : 1));
+  }
+  delete v;
+  return n_levels;
 }
 
 double wbo_sampler_offset(wbo_session* s, int track) { return s->engine.tracks[track]->sampler.sample_offset_; }

@@ -10,6 +10,7 @@
 
 #include "core/midi_file.h"
 #include "dsp/sample.h"
+#include "gfx/renderer.h"
 #include "gfx/waveform_visual.h"
 #include "plughost/plugin_manager.h"
 
@@ -50,9 +51,50 @@ void Sample::resize(size_t n, uint32_t new_channels, bool) {
 
 std::optional<Sample> Sample::load_file(const std::filesystem::path&) noexcept { return {}; }
 
-// --- gfx/waveform_visual.cpp stand-ins (real file uploads min/max mip-maps to the Vulkan renderer) -----
-WaveformVisual::~WaveformVisual() {}
-WaveformVisual* WaveformVisual::create(Sample*, WaveformVisualQuality) { return new WaveformVisual{}; }
+// --- gfx: the mip-map builder (gfx/waveform_visual.cpp) is compiled from the reference unmodified; it uploads
+// its results through the abstract GPURenderer (gfx/renderer.h:165-209). The Vulkan renderer is replaced by a
+// host-memory one: create_buffer mallocs, begin_upload_data hands the memory out. No arithmetic here.
+struct HostBuffer : GPUBuffer {
+  void* mem = nullptr;
+};
+struct HostRenderer : GPURenderer {
+  GPUBuffer* create_buffer(GPUBufferUsageFlags usage, size_t buffer_size, bool, size_t, const void*) override {
+    HostBuffer* b = new HostBuffer();
+    b->usage = usage;
+    b->size = buffer_size;
+    b->mem = std::calloc(1, buffer_size ? buffer_size : 1);
+    return b;
+  }
+  GPUTexture* create_texture(GPUTextureUsageFlags, GPUFormat, uint32_t, uint32_t, bool, uint32_t, uint32_t, const void*) override { return nullptr; }
+  GPUPipeline* create_pipeline(const GPUPipelineDesc&) override { return nullptr; }
+  void destroy_buffer(GPUBuffer* buffer) override {
+    HostBuffer* b = static_cast<HostBuffer*>(buffer);
+    if (b) std::free(b->mem);
+    delete b;
+  }
+  void destroy_texture(GPUTexture*) override {}
+  void destroy_pipeline(GPUPipeline*) override {}
+  void add_viewport(ImGuiViewport*) override {}
+  void remove_viewport(ImGuiViewport*) override {}
+  void resize_viewport(ImGuiViewport*, ImVec2) override {}
+  void end_frame() override {}
+  void present() override {}
+  void* map_buffer(GPUBuffer* buffer) override { return static_cast<HostBuffer*>(buffer)->mem; }
+  void unmap_buffer(GPUBuffer*) override {}
+  void* begin_upload_data(GPUBuffer* buffer, size_t) override { return static_cast<HostBuffer*>(buffer)->mem; }
+  void end_upload_data() override {}
+  void begin_render(GPUTexture*, const ImVec4&) override {}
+  void end_render() override {}
+  void set_shader_parameter(size_t, const void*) override {}
+  void flush_state() override {}
+};
+// the three non-pure virtuals of GPURenderer live in gfx/renderer.cpp (ImGui/SDL code): empty stand-ins
+bool GPURenderer::init(SDL_Window*) { return true; }
+void GPURenderer::shutdown() {}
+void GPURenderer::begin_frame() {}
+static HostRenderer g_host_renderer;
+GPURenderer* g_renderer = &g_host_renderer;
+void* wbref_buffer_memory(GPUBuffer* b) { return static_cast<HostBuffer*>(b)->mem; }
 
 // --- plughost / midi file stand-ins ----------------------------------------------------------------------
 PluginInterface* pm_open_plugin(PluginUID) { return nullptr; }

@@ -849,6 +849,82 @@ double wbo_sampler_offset(wbo_session* s, int track) { return s->tracks[track]->
 double wbo_sample_position(wbo_session* s) { return s->sample_position; }
 double wbo_playhead(wbo_session* s) { return s->playhead; }
 
+/* ---- gfx/waveform_visual.cpp: waveform peak mip-maps ------------------------------------------------------- */
+/* summarize_for_mipmaps_impl<T> (:9-173) for one channel. T = int16 (quality High) or int8 (Low); per chunk the
+ * converted min and max with their FIRST occurrences, emitted in order of occurrence. */
+static void summarize(int fmt, size_t sample_count, const void* data, size_t chunk_count, size_t block_count,
+                      size_t output_count, int high, void* output) {
+  const long tmin = high ? -32768 : -128, tmax = high ? 32767 : 127;
+  for (size_t i = 0; i < output_count; i += 2) {
+    size_t idx = i * block_count;
+    size_t rem = sample_count - idx;
+    size_t chunk_length = chunk_count < rem ? chunk_count : rem;
+    long min_val = tmax, max_val = tmin; /* numeric_limits<T>::max() / ::min() */
+    size_t min_idx = 0, max_idx = 0;
+    for (size_t j = 0; j < chunk_length; j++) {
+      long value;
+      if (fmt == WBO_FMT_F32) { /* :143-151 */
+        float v = ((const float*)data)[idx + j];
+        float conv = v * (v >= 0.0f ? (float)tmax : (float)(-tmin));
+        value = high ? (long)(int16_t)conv : (long)(int8_t)conv;
+      } else if (fmt == WBO_FMT_I16) { /* :66-76 */
+        const float dmin = (float)tmin / (float)INT16_MIN, dmax = (float)tmax / (float)INT16_MAX;
+        int16_t v = ((const int16_t*)data)[idx + j];
+        float conv = (float)v * (v >= 0 ? dmax : dmin);
+        value = high ? (long)(int16_t)conv : (long)(int8_t)conv;
+      } else { /* I32, :104-114, in double */
+        const double dmin = (double)tmin / (double)INT32_MIN, dmax = (double)tmax / (double)INT32_MAX;
+        int32_t v = ((const int32_t*)data)[idx + j];
+        double conv = (double)v * (v >= 0 ? dmax : dmin);
+        value = high ? (long)(int16_t)conv : (long)(int8_t)conv;
+      }
+      if (value < min_val) {
+        min_val = value;
+        min_idx = j;
+      }
+      if (value > max_val) {
+        max_val = value;
+        max_idx = j;
+      }
+    }
+    long first = max_idx < min_idx ? max_val : min_val, second = max_idx < min_idx ? min_val : max_val;
+    if (high) {
+      ((int16_t*)output)[i] = (int16_t)first;
+      ((int16_t*)output)[i + 1] = (int16_t)second;
+    } else {
+      ((int8_t*)output)[i] = (int8_t)first;
+      ((int8_t*)output)[i + 1] = (int8_t)second;
+    }
+  }
+}
+
+/* WaveformVisual::create (:181-248): levels current_mip = 1, 3, 5, ... while sample_count > 64 (/= 4 per level). */
+int wbo_mipmap(wbo_session* s, int sample, int quality, int level, void* out, uint64_t cap_elems, uint32_t* count) {
+  o_sample* sm = s->samples[sample];
+  if (sm->fmt == WBO_FMT_I24) return 0; /* `default: break` — the loader never produces this tag */
+  size_t sample_count = sm->count;
+  uint32_t current_mip = 1;
+  int n_levels = 0;
+  const size_t esz = quality ? 2 : 1;
+  while (sample_count > 64) {
+    size_t chunk_count = (size_t)1 << current_mip;
+    size_t block_count = (size_t)1 << (current_mip - 1);
+    size_t mip_data_count = sm->count / block_count;
+    mip_data_count += mip_data_count % 2;
+    if (n_levels == level) {
+      if (count) *count = (uint32_t)mip_data_count;
+      if (out && mip_data_count * sm->channels <= cap_elems)
+        for (uint32_t c = 0; c < sm->channels; c++)
+          summarize(sm->fmt, sm->count, sm->data[c], chunk_count, block_count, mip_data_count, quality,
+                    (char*)out + mip_data_count * c * esz);
+    }
+    n_levels++;
+    sample_count /= 4;
+    current_mip += 2;
+  }
+  return n_levels;
+}
+
 /* ---- core/audio_format_conv.cpp:5-106: planar f32 -> interleaved device format -------------------------- */
 
 void wbo_interleave(void* dst, const float* const* src, uint32_t offset, uint32_t frames, uint32_t channels,

@@ -92,6 +92,13 @@ float wbo_db_to_linear(float db);
 void wbo_interleave(void* dst, const float* const* src, uint32_t offset, uint32_t frames, uint32_t channels,
                     int fmt);
 
+/* Waveform peak mip-maps of a resident sample (gfx/waveform_visual.cpp:9-173 summarize_for_mipmaps_impl,
+ * :181-248 WaveformVisual::create). quality 0 = Low (int8), 1 = High (int16). Level l uses chunks of
+ * 2^(2l+1) frames; its data is [channels][count] elements, each chunk giving a (first, second) pair = (min, max)
+ * ordered by which occurs first. Copies level `level` into out (capacity cap_elems elements) and returns the
+ * number of levels, or a negative value; *count = elements per channel of that level. */
+int wbo_mipmap(wbo_session*, int sample, int quality, int level, void* out, uint64_t cap_elems, uint32_t* count);
+
 /* CPU timing of the same loop (bench.py cpu_baseline / --impl reference only): runs n_blocks callbacks
  * without copying results out and returns elapsed seconds (steady clock). */
 double wbo_time_process(wbo_session*, uint32_t n_blocks);

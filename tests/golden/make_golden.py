@@ -28,6 +28,15 @@ def main():
     for seed in range(4):
         res = sc.fuzz(mk, seed)
         np.savez_compressed(os.path.join(HERE, "fuzz%d.npz" % seed), **res)
+    # waveform mip-maps (gfx/waveform_visual.cpp) of three small samples, both qualities
+    mip = {}
+    for name, (fmt, frames, ch) in sc.MIP_CASES.items():
+        s = o.Session("reference")
+        sid = s.add_sample(sc.mip_source(fmt, frames, ch), 48000, fmt)
+        for q in (0, 1):
+            for lv, a in enumerate(s.mipmaps(sid, q)):
+                mip["%s_q%d_l%d" % (name, q, lv)] = a
+    np.savez_compressed(os.path.join(HERE, "mipmaps.npz"), **mip)
     pans = np.linspace(-1, 1, 41).astype(np.float32)
     dbs = np.array([0, -6, -12, 6, -72, -71.9, -3.3, 12, -40.5, -100], np.float32)
     pc = np.array([o.panning_coefs("reference", float(p)) for p in pans], np.float32)

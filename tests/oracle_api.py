@@ -53,6 +53,7 @@ def _load(path):
     lib.wbo_db_to_linear.argtypes = [flt]
     lib.wbo_db_to_linear.restype = flt
     lib.wbo_interleave.argtypes = [vp, C.POINTER(vp), u32, u32, u32, i32]
+    lib.wbo_mipmap.argtypes = [vp, i32, i32, i32, vp, u64, C.POINTER(u32)]
     _libs[path] = lib
     return lib
 
@@ -79,6 +80,7 @@ class Session:
         self.h = self.lib.wbo_create(out_channels, block, rate, bpm)
         self.n_tracks = 0
         self._keep = []
+        self._channels = {}
 
     def close(self):
         if self.h:
@@ -106,7 +108,9 @@ class Session:
         data = np.ascontiguousarray(data, dtype=_NP[fmt])
         ch, frames = data.shape
         ptrs = (C.c_void_p * ch)(*[data[c].ctypes.data for c in range(ch)])
-        return self.lib.wbo_add_sample(self.h, fmt, ch, frames, rate, ptrs)
+        sid = self.lib.wbo_add_sample(self.h, fmt, ch, frames, rate, ptrs)
+        self._channels[sid] = ch
+        return sid
 
     def add_clip(self, track, sample, min_beat, max_beat, start_offset=0.0, speed=1.0, gain=1.0, fade_start=0.0,
                  fade_end=0.0):
@@ -133,6 +137,19 @@ class Session:
         peaks = np.zeros((n_blocks, self.n_tracks, 2), np.float32)
         self.lib.wbo_process(self.h, n_blocks, out.ctypes.data, peaks.ctypes.data)
         return out, peaks
+
+    def mipmaps(self, sample, quality):
+        """-> list of [channels][count] arrays (int16 for quality 1, int8 for 0), one per mip level."""
+        dt = np.int16 if quality else np.int8
+        cnt = C.c_uint32()
+        n = self.lib.wbo_mipmap(self.h, sample, quality, -1, None, 0, C.byref(cnt))
+        out = []
+        for lv in range(max(n, 0)):
+            self.lib.wbo_mipmap(self.h, sample, quality, lv, None, 0, C.byref(cnt))
+            buf = np.zeros(cnt.value * self._channels[sample], dt)
+            self.lib.wbo_mipmap(self.h, sample, quality, lv, buf.ctypes.data, buf.size, C.byref(cnt))
+            out.append(buf.reshape(self._channels[sample], cnt.value))
+        return out
 
     def time_process(self, n_blocks):
         return self.lib.wbo_time_process(self.h, n_blocks)

@@ -320,6 +320,16 @@ def fuzz(make_engine, seed):
     return _collect(eng, outs, n_tracks)
 
 
+MIP_CASES = dict(f32s=(FMT_F32, 20011, 2), i16m=(FMT_I16, 4100, 1), i32s=(FMT_I32, 777, 2))
+
+
+def mip_source(fmt, frames, ch):
+    data = _src(np.random.RandomState(frames), ch, frames, 1, fmt)
+    if fmt == FMT_F32:
+        data[:, :7] = [1, -1, 0, 0.5, -0.5, 1, -1]
+    return data
+
+
 EXT = dict(fades=fades, effects=effects)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,

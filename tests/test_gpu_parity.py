@@ -133,6 +133,30 @@ def test_effects_identity_properties(wb):
     assert same_bits(a, b) and same_bits(pa, pb)
 
 
+def test_waveform_mipmaps_vs_reference(wb):
+    """WaveformVisual mip-maps (gfx/waveform_visual.cpp) of resident samples == the CPU checker
+    (the reference's own summarize_for_mipmaps_impl when oracle/_ref travelled, else the C restatement)."""
+    kind = "reference" if o.have_ref() else "port"
+    rng = np.random.RandomState(5)
+    dev = wb.DeviceEngine(0)
+    dev.configure(2, 512, 48000)
+    for fmt, frames, ch in [(9, 100000, 2), (9, 70, 1), (9, 65, 2), (9, 64, 1), (3, 33333, 2), (7, 5000, 1),
+                            (9, 4097, 2), (9, 1 << 16, 1), (9, 300001, 2)]:
+        data = sc._src(rng, ch, frames, 1, fmt)
+        if fmt == 9:
+            data[:, :7] = [1, -1, 0, 0.5, -0.5, 1, -1]
+        s = o.Session(kind)
+        ref_id = s.add_sample(data, 48000, fmt)
+        sid = dev.sample_upload(data, 48000, fmt)
+        for q in (0, 1):
+            want = s.mipmaps(ref_id, q)
+            got = dev.sample_mipmaps(sid, q, ch)
+            assert len(got) == len(want), (fmt, frames, ch, q)
+            for lv, (a, b) in enumerate(zip(got, want)):
+                assert a.shape == b.shape and np.array_equal(a, b), "mip level %d differs (%s)" % (lv, (fmt, frames, ch, q))
+        dev.sample_release(sid)
+
+
 def test_scalars_and_interleave(wb, golden_dir):
     g = np.load(os.path.join(golden_dir, "scalars.npz"))
     planar = g["planar"] + np.float32(0)  # the bus starts at +0, so a -0.0 source sample mixes to +0.0

@@ -47,6 +47,22 @@ def test_port_scalars_match_golden(golden_dir):
         assert same_bits(o.interleave("port", g["planar"], f), g["conv_%d" % f]), f
 
 
+def test_port_mipmaps_match_golden(golden_dir):
+    """Waveform mip-maps (gfx/waveform_visual.cpp:9-173,181-248): restatement == vectors the reference produced."""
+    gold = np.load(os.path.join(golden_dir, "mipmaps.npz"))
+    seen = 0
+    for name, (fmt, frames, ch) in sc.MIP_CASES.items():
+        s = o.Session("port")
+        sid = s.add_sample(sc.mip_source(fmt, frames, ch), 48000, fmt)
+        for q in (0, 1):
+            levels = s.mipmaps(sid, q)
+            for lv, a in enumerate(levels):
+                assert same_bits(a, gold["%s_q%d_l%d" % (name, q, lv)]), (name, q, lv)
+                seen += 1
+            assert "%s_q%d_l%d" % (name, q, len(levels)) not in gold
+    assert seen == len(gold.files)
+
+
 def test_survey_known_answers(golden_dir):
     """values the compiled reference printed during the survey."""
     k = sc.kat(mk("port"))

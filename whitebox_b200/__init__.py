@@ -54,7 +54,7 @@ SEG_FADE = 1
 # every symbol include/wbx.h and include/wbx_host.h declare
 WBX_SYMBOLS = [
     "wbx_abi_version", "wbx_create", "wbx_destroy", "wbx_last_error", "wbx_configure", "wbx_set_track_count",
-    "wbx_set_sum_mode", "wbx_set_stream", "wbx_sample_upload", "wbx_sample_release", "wbx_sample_update", "wbx_render", "wbx_submit",
+    "wbx_set_sum_mode", "wbx_set_stream", "wbx_sample_upload", "wbx_sample_release", "wbx_sample_update", "wbx_sample_mipmap", "wbx_render", "wbx_submit",
     "wbx_mix", "wbx_fetch", "wbx_fetch_levels", "wbx_host_alloc", "wbx_host_free", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
     "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel", "wbx_effects_design", "wbx_set_track_effects",
 ]
@@ -96,6 +96,7 @@ def lib():
     L.wbx_sample_upload.argtypes = [vp, i32, u32, u64, u32, pp, C.POINTER(u32)]
     L.wbx_sample_release.argtypes = [vp, u32]
     L.wbx_sample_update.argtypes = [vp, u32, pp]
+    L.wbx_sample_mipmap.argtypes = [vp, u32, i32, i32, vp, u64, C.POINTER(u32)]
     L.wbx_render.argtypes = [vp, vp, u32, vp, u32, pp, vp]
     L.wbx_submit.argtypes = [vp, vp, u32, vp, u32]
     L.wbx_mix.argtypes = [vp, u32]
@@ -249,6 +250,23 @@ class DeviceEngine:
         sid = C.c_uint32()
         self._ck(self.L.wbx_sample_upload(self.h, fmt, len(channels), channels[0].size, rate, ptrs, C.byref(sid)))
         return sid.value
+
+    def sample_mipmaps(self, sid, quality, channels):
+        """-> list of [channels][count] arrays (int16 for quality 1, int8 for 0), one per mip level."""
+        dt = np.int16 if quality else np.int8
+        cnt = C.c_uint32()
+        n = self.L.wbx_sample_mipmap(self.h, sid, quality, -1, None, 0, C.byref(cnt))
+        if n < 0:
+            self._ck(n)
+        out = []
+        for lv in range(n):
+            self.L.wbx_sample_mipmap(self.h, sid, quality, lv, None, 0, C.byref(cnt))
+            buf = np.zeros(cnt.value * channels, dt)
+            r = self.L.wbx_sample_mipmap(self.h, sid, quality, lv, buf.ctypes.data, buf.size, C.byref(cnt))
+            if r < 0:
+                self._ck(r)
+            out.append(buf.reshape(channels, cnt.value))
+        return out
 
     def sample_update_planar(self, sid, channels):
         ptrs = (C.c_void_p * len(channels))(*[c.ctypes.data for c in channels])

@@ -24,6 +24,8 @@ cudaError_t launch_interleave(const float* bus, uint64_t frames, uint32_t channe
 cudaError_t launch_interleave_sample(const void* planar, size_t plane_bytes, uint64_t frames, uint32_t nch,
                                      uint32_t esize, void* dst, int n_sm, cudaStream_t stream);
 int mix_warps_per_sm(int fpl);
+cudaError_t launch_mipmap(const void* base, uint32_t fmt, uint32_t nch, uint64_t count, uint64_t chunk, uint64_t block,
+                          uint64_t mdc, int high, void* out, cudaStream_t stream);
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, cudaStream_t stream);
 }  // namespace wbx
@@ -324,6 +326,43 @@ int wbx_sample_update(wbx_engine* e, uint32_t id, const void* const* planar) {
   e->launches++;
   if (!pinned) CU(e, cudaStreamSynchronize(e->stream));
   return WBX_OK;
+}
+
+int wbx_sample_mipmap(wbx_engine* e, uint32_t id, int quality, int level, void* out, uint64_t cap_elems,
+                      uint32_t* count) {
+  if (!e || id >= e->samples.size() || !e->samples[id].live) return fail(e, WBX_ERR_INVALID, "bad sample id");
+  const SampleRec& r = e->samples[id];
+  if (r.channels > 2) return fail(e, WBX_ERR_UNSUPPORTED, "mip-maps: only the 2 resident channels are available");
+  if (r.fmt == WBX_FMT_I24) return 0;  // the reference's switch has no case for this tag (`default: break`)
+  CU(e, cudaSetDevice(e->device));
+  // WaveformVisual::create (gfx/waveform_visual.cpp:181-248): levels with chunk 2, 8, 32, ... while count/4^l > 64
+  uint64_t sample_count = r.frames;
+  uint32_t current_mip = 1;
+  int n_levels = 0;
+  const size_t esz = quality ? 2 : 1;
+  while (sample_count > 64) {
+    if (n_levels == level) {
+      const uint64_t chunk = 1ull << current_mip, block = 1ull << (current_mip - 1);
+      uint64_t mdc = r.frames / block;
+      mdc += mdc % 2;
+      if (count) *count = (uint32_t)mdc;
+      const uint64_t elems = mdc * r.nch;
+      if (out && elems <= cap_elems) {
+        int rc;
+        if ((rc = dev_reserve(e, e->d_conv, elems * esz))) return rc;
+        if ((rc = host_reserve(e, e->h_conv, elems * esz))) return rc;
+        CU(e, launch_mipmap(r.d_base, r.fmt, r.nch, r.frames, chunk, block, mdc, quality ? 1 : 0, e->d_conv.p, e->stream));
+        e->launches++;
+        CU(e, cudaMemcpyAsync(e->h_conv.p, e->d_conv.p, elems * esz, cudaMemcpyDeviceToHost, e->stream));
+        CU(e, cudaStreamSynchronize(e->stream));
+        memcpy(out, e->h_conv.p, elems * esz);
+      }
+    }
+    n_levels++;
+    sample_count /= 4;
+    current_mip += 2;
+  }
+  return n_levels;
 }
 
 int wbx_sample_release(wbx_engine* e, uint32_t id) {

@@ -993,6 +993,111 @@ __global__ void interleave_kernel(const float* __restrict__ bus, uint64_t frames
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// waveform peak mip-maps (gfx/waveform_visual.cpp:9-173): per chunk of `chunk` frames the converted min and max
+// with their first occurrences, stored in order of occurrence. A second HBM-bound scan over the resident samples.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mip_convert(uint32_t fmt, const void* base, uint64_t elem, bool high) {
+  const int tmin = high ? -32768 : -128, tmax = high ? 32767 : 127;
+  int q;
+  if (fmt == F_F32) {  // :143-151
+    const float v = ((const float*)base)[elem];
+    q = __float2int_rz(__fmul_rn(v, v >= 0.0f ? (float)tmax : (float)(-tmin)));
+  } else if (fmt == F_I16) {  // :66-76
+    const int16_t v = ((const int16_t*)base)[elem];
+    const float dmin = high ? (-32768.0f / -32768.0f) : (-128.0f / -32768.0f);
+    const float dmax = high ? (32767.0f / 32767.0f) : (127.0f / 32767.0f);
+    q = __float2int_rz(__fmul_rn((float)v, v >= 0 ? dmax : dmin));
+  } else {  // I32 (:104-114), in double
+    const int32_t v = ((const int32_t*)base)[elem];
+    const double dmin = high ? (-32768.0 / -2147483648.0) : (-128.0 / -2147483648.0);
+    const double dmax = high ? (32767.0 / 2147483647.0) : (127.0 / 2147483647.0);
+    q = __double2int_rz(__dmul_rn((double)v, v >= 0 ? dmax : dmin));
+  }
+  return high ? (int)(int16_t)q : (int)(int8_t)q;  // (T)conv
+}
+
+struct MipAcc {
+  int mn, mx;
+  uint32_t mn_i, mx_i;
+  __device__ __forceinline__ void add(int v, uint32_t j) {  // strict compares: first occurrence wins
+    if (v < mn) {
+      mn = v;
+      mn_i = j;
+    }
+    if (v > mx) {
+      mx = v;
+      mx_i = j;
+    }
+  }
+  __device__ __forceinline__ void merge(int omn, uint32_t omn_i, int omx, uint32_t omx_i) {
+    if (omn < mn || (omn == mn && omn_i < mn_i)) {
+      mn = omn;
+      mn_i = omn_i;
+    }
+    if (omx > mx || (omx == mx && omx_i < mx_i)) {
+      mx = omx;
+      mx_i = omx_i;
+    }
+  }
+};
+
+// WARP == false: one thread per (channel, chunk) — small chunks; WARP == true: one warp per (channel, chunk).
+template <bool WARP>
+__global__ void mipmap_kernel(const void* __restrict__ base, uint32_t fmt, uint32_t nch, uint64_t count,
+                              uint64_t chunk, uint64_t block, uint64_t mdc, int high, void* __restrict__ out) {
+  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t unit = WARP ? (gid >> 5) : gid;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t pairs = mdc / 2;
+  if (unit >= pairs * nch) return;
+  const uint32_t c = (uint32_t)(unit / pairs);
+  const uint64_t pi = unit % pairs;
+  const uint64_t idx = 2 * pi * block;  // i * block_count with i = 2 * pair
+  const uint64_t rem = count - idx;
+  const uint64_t len = chunk < rem ? chunk : rem;
+  MipAcc a;
+  a.mn = high ? 32767 : 127;  // numeric_limits<T>::max() / ::min()
+  a.mx = high ? -32768 : -128;
+  a.mn_i = 0;
+  a.mx_i = 0;
+  if (WARP) {
+    for (uint64_t j = lane; j < len; j += 32) a.add(mip_convert(fmt, base, (idx + j) * nch + c, high != 0), (uint32_t)j);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int omn = __shfl_xor_sync(0xffffffffu, a.mn, o), omx = __shfl_xor_sync(0xffffffffu, a.mx, o);
+      const uint32_t omn_i = __shfl_xor_sync(0xffffffffu, a.mn_i, o), omx_i = __shfl_xor_sync(0xffffffffu, a.mx_i, o);
+      // a lane that saw no element keeps the initial (max, min) with index 0: it can only tie with another
+      // lane's value when that value IS the initial one, and then index 0 is the reference's answer too
+      a.merge(omn, omn_i, omx, omx_i);
+    }
+    if (lane != 0) return;
+  } else {
+    for (uint64_t j = 0; j < len; j++) a.add(mip_convert(fmt, base, (idx + j) * nch + c, high != 0), (uint32_t)j);
+  }
+  const int first = a.mx_i < a.mn_i ? a.mx : a.mn, second = a.mx_i < a.mn_i ? a.mn : a.mx;
+  const uint64_t o = mdc * c + 2 * pi;
+  if (high) {
+    ((int16_t*)out)[o] = (int16_t)first;
+    ((int16_t*)out)[o + 1] = (int16_t)second;
+  } else {
+    ((int8_t*)out)[o] = (int8_t)first;
+    ((int8_t*)out)[o + 1] = (int8_t)second;
+  }
+}
+
+cudaError_t launch_mipmap(const void* base, uint32_t fmt, uint32_t nch, uint64_t count, uint64_t chunk, uint64_t block,
+                          uint64_t mdc, int high, void* out, cudaStream_t stream) {
+  const uint64_t units = (mdc / 2) * nch;
+  if (units == 0) return cudaSuccess;
+  if (chunk <= 32) {
+    mipmap_kernel<false><<<(unsigned)((units + 127) / 128), 128, 0, stream>>>(base, fmt, nch, count, chunk, block, mdc, high, out);
+  } else {
+    mipmap_kernel<true><<<(unsigned)((units * 32 + 127) / 128), 128, 0, stream>>>(base, fmt, nch, count, chunk, block, mdc, high, out);
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host-callable launchers (used by wbx_api.cu)
 // ---------------------------------------------------------------------------------------------------------
 struct MixVariant {
