@@ -145,15 +145,23 @@ typedef struct wbx_effect_params { /* musical parameters */
   float eq_freq[4], eq_gain_db[4], eq_q[4];
   float comp_threshold_db, comp_attack_ms, comp_release_ms, comp_makeup_db;
   int32_t comp_ratio_code; /* 0 off, 1 = 2:1, 2 = 4:1, 3 = 8:1, 4 = limiter */
+  int32_t reverb_on;       /* 1: last stage = convolution with the engine's impulse response (BASELINE cfg 5) */
 } wbx_effect_params;
 typedef struct wbx_effects { /* designed coefficients */
   uint32_t eq_on, comp_on;
   float b0[4], b1[4], b2[4], a1[4], a2[4]; /* normalised by a0 */
   float comp_threshold, comp_attack, comp_release, comp_makeup; /* linear / one-pole coefficients */
   uint32_t comp_ratio_code;
+  uint32_t reverb_on;
 } wbx_effects;
 /* f64 coefficient design (host only). */
 int wbx_effects_design(const wbx_effect_params* params, uint32_t sample_rate, wbx_effects* out);
+/* Convolution reverb (extension, BASELINE cfg 5): one impulse response h[0..n_taps) per engine, applied as the last
+ * stage of every chain with reverb_on: y[n] = sum_k h[k] * x[n-k] with the history carried across renders.
+ * Specification = f64 accumulation (oracle/wb_oracle.c apply_reverb); this implementation is a direct form on the
+ * CUDA cores (f32 fused multiply-adds per 256-tap tile, tiles summed in f64), held to 1e-5 of the block peak.
+ * h == NULL or n_taps == 0 removes it. Changing it clears every track's reverb history. */
+int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps);
 /* Attach (fx != NULL) or remove (NULL) a track's chain and clear its state. Tracks without a chain take the
  * reference path untouched. */
 int wbx_set_track_effects(wbx_engine* e, uint32_t track, const wbx_effects* fx);

@@ -108,6 +108,8 @@ class Engine {
   // engine/engine.cpp:293-309 + add_to_cliplist (:409-461) for clips that do not overlap an existing one.
   int add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
                      double speed, float gain, double fade_start = 0.0, double fade_end = 0.0);
+  // convolution reverb (extension, see wbx.h): one impulse response per engine, used by chains with reverb_on
+  int set_impulse_response(const float* h, uint32_t n_taps);
   void play();  // engine/engine.cpp:68-80
   void stop();  // :82-92
 

@@ -70,6 +70,9 @@ typedef struct {
   float thr, att, rel, makeup;
   int ratio_code;
   float s1[2][4], s2[2][4], env[2];
+  int reverb_on;
+  float* hist[2]; /* last n_taps - 1 chain outputs per channel (ring), zero at attach time */
+  uint64_t hist_pos;
 } o_fx;
 
 typedef struct {
@@ -105,9 +108,12 @@ struct wbo_session {
   uint32_t n_samples, cap_samples;
   float** mixing; /* Engine::mixing_buffer, engine.h:57 */
   float** out;
+  float* ir; /* EXTENSION: session impulse response */
+  uint32_t ir_taps;
 };
 
 const char* wbo_kind(void) { return "port"; }
+static void fx_free(o_fx* f);
 
 static uint64_t g_ub_count = 0;
 /* port only: how many times a scenario drove the reference algorithm into undefined behaviour */
@@ -165,6 +171,7 @@ void wbo_destroy(wbo_session* s) {
     o_track* tr = s->tracks[t];
     for (uint32_t i = 0; i < tr->n_clips; i++) free(tr->clips[i]);
     free(tr->clips);
+    fx_free(&tr->fx);
     free(tr->events);
     free(tr->msgs);
     free(tr);
@@ -182,6 +189,7 @@ void wbo_destroy(wbo_session* s) {
   }
   free(s->mixing);
   free(s->out);
+  free(s->ir);
   free(s);
 }
 
@@ -656,10 +664,35 @@ static void design_band(int band, double freq, double gain_db, double q, double 
   *a2 = (float)(A2 / A0);
 }
 
+static void fx_free(o_fx* f) {
+  free(f->hist[0]);
+  free(f->hist[1]);
+  f->hist[0] = f->hist[1] = NULL;
+}
+
+int wbo_set_impulse_response(wbo_session* s, const float* h, uint32_t n_taps) {
+  free(s->ir);
+  s->ir = NULL;
+  s->ir_taps = 0;
+  if (h && n_taps) {
+    s->ir = (float*)malloc(n_taps * sizeof(float));
+    memcpy(s->ir, h, n_taps * sizeof(float));
+    s->ir_taps = n_taps;
+  }
+  for (uint32_t t = 0; t < s->n_tracks; t++) { /* a new response starts from silence */
+    o_fx* f = &s->tracks[t]->fx;
+    fx_free(f);
+    f->hist_pos = 0;
+  }
+  return 0;
+}
+
 int wbo_set_effects(wbo_session* s, int track, const wbo_effects* fx) {
   o_fx* f = &s->tracks[track]->fx;
+  fx_free(f);
   memset(f, 0, sizeof(*f));
   if (!fx) return 0;
+  f->reverb_on = fx->reverb_on != 0;
   for (int b = 0; b < 4; b++) {
     if (fx->eq_gain_db[b] != 0.0f) f->eq_on = 1;
     design_band(b, fx->eq_freq[b], fx->eq_gain_db[b], fx->eq_q[b], (double)s->rate, &f->b0[b], &f->b1[b], &f->b2[b],
@@ -672,6 +705,25 @@ int wbo_set_effects(wbo_session* s, int track, const wbo_effects* fx) {
   f->att = (float)exp(-1.0 / ((double)fx->comp_attack_ms * 0.001 * (double)s->rate));
   f->rel = (float)exp(-1.0 / ((double)fx->comp_release_ms * 0.001 * (double)s->rate));
   return 0;
+}
+
+/* Convolution reverb, one channel, one callback, in place: y[n] = (float) sum_k h[k] * x[n-k] in f64, k ascending. */
+static void apply_reverb(wbo_session* s, o_fx* f, int c, float* buf, uint32_t n, uint64_t pos0) {
+  const uint32_t L = s->ir_taps;
+  if (L == 0) return;
+  const uint32_t H = L > 1 ? L - 1 : 1;
+  if (!f->hist[c]) f->hist[c] = (float*)calloc(H, sizeof(float));
+  float* x = (float*)malloc(((size_t)H + n) * sizeof(float)); /* [history | this callback's input] */
+  for (uint32_t i = 0; i < H; i++) x[i] = L > 1 ? f->hist[c][(pos0 + i) % H] : 0.0f; /* oldest first */
+  memcpy(x + H, buf, n * sizeof(float));
+  for (uint32_t j = 0; j < n; j++) {
+    double acc = 0.0;
+    for (uint32_t k = 0; k < L; k++) acc += (double)s->ir[k] * (double)x[H + j - k];
+    buf[j] = (float)acc;
+  }
+  if (L > 1)
+    for (uint32_t j = 0; j < n; j++) f->hist[c][(pos0 + j) % H] = x[H + j]; /* ring: overwrite the oldest */
+  free(x);
 }
 
 /* One channel, one callback, in place. Every operation is a single IEEE-754 rn op (fmaf = fused). */
@@ -764,6 +816,10 @@ static void track_process(wbo_session* s, o_track* tr, float** out, double sampl
    * pan_coeffs has two entries, so C <= 2 (track.h:50). */
   if (tr->fx.eq_on || tr->fx.comp_on) /* EXTENSION: where a native PluginInterface::process would run */
     for (uint32_t c = 0; c < s->C; c++) apply_effects(&tr->fx, (int)c, out[c], B);
+  if (tr->fx.reverb_on && s->ir_taps) {
+    for (uint32_t c = 0; c < s->C; c++) apply_reverb(s, &tr->fx, (int)c, out[c], B, tr->fx.hist_pos);
+    tr->fx.hist_pos += B;
+  }
 
   float volume = tr->mute ? 0.0f : tr->volume;
   for (uint32_t c = 0; c < s->C; c++) {

@@ -66,8 +66,14 @@ typedef struct wbo_effects {
   float eq_freq[4], eq_gain_db[4], eq_q[4];
   float comp_threshold_db, comp_attack_ms, comp_release_ms, comp_makeup_db;
   int comp_ratio_code; /* 0 off, 1 = 2:1, 2 = 4:1, 3 = 8:1, 4 = limiter */
+  int reverb_on;       /* 1: convolve the chain's output with the session's impulse response (BASELINE cfg 5) */
 } wbo_effects;
 int wbo_set_effects(wbo_session*, int track, const wbo_effects* fx); /* port only; libwbref.so returns -1 */
+/* Convolution reverb — EXTENSION, PARITY UNPINNED: one impulse response h[0..n_taps) per session, applied as the
+ * last stage of a track's chain: y[n] = (float) sum_k (double)h[k] * (double)x[n - k], k ascending, accumulated in
+ * f64 (the ground truth a tensor-core or f32 implementation is held to within 1e-5 of the block peak); x before
+ * the chain was attached is 0 and the history persists across callbacks. */
+int wbo_set_impulse_response(wbo_session*, const float* h, uint32_t n_taps); /* port only */
 
 void wbo_set_playhead(wbo_session*, double beat); /* Engine::set_playhead_position */
 void wbo_play(wbo_session*);                      /* Engine::play */

@@ -278,6 +278,29 @@ def effects(make_engine, fxp):
     return _collect(eng, outs, n)
 
 
+def reverb(make_engine, fxp, taps=777):
+    """EXTENSION scenario (parity unpinned w.r.t. whitebox): BASELINE cfg 5 shape at test size — tracks whose chain
+    ends in a convolution with a shared impulse response, history carried across renders."""
+    rng = np.random.RandomState(909)
+    B, rate = 256, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    ir = (rng.uniform(-1, 1, taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.2).astype(np.float32)
+    ir[0] = 1.0
+    eng.set_impulse_response(ir)
+    n = 5
+    for t in range(n):
+        eng.add_track(-6.0 - t, -0.5 + 0.25 * t, False)
+        sid = eng.add_sample(_src(rng, 2, 6000, 4), 48000)
+        eng.add_clip(t, sid, 0.0, 8.0, 0.0, 1.0, 0.9)
+    eq = ((120.0, 4.0, 0.7), (800.0, -6.0, 1.2), (2500.0, 3.0, 2.0), (8000.0, 5.0, 0.7))
+    eng.set_effects(0, fxp(reverb=True))
+    eng.set_effects(2, fxp(eq=eq, threshold_db=-30.0, ratio_code=2, reverb=True))
+    eng.set_effects(3, fxp(eq=eq))
+    eng.play()
+    outs = [eng.process(3), eng.process(1), eng.process(4)]
+    return _collect(eng, outs, n)
+
+
 def fuzz(make_engine, seed):
     """Random session: random rates / formats / speeds / clip layouts / block size, params changed mid-run."""
     rng = np.random.RandomState(1000 + seed)
@@ -330,7 +353,7 @@ def mip_source(fmt, frames, ch):
     return data
 
 
-EXT = dict(fades=fades, effects=effects)  # builder-specified extensions: checked against the C port only
+EXT = dict(fades=fades, effects=effects, reverb=reverb)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
            event_split=event_split, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)

@@ -116,6 +116,39 @@ def test_effects_extension_vs_port(wb, batched):
     assert_exact(sc.effects(gpu_engine(wb, batched), wb.effect_params), ref, "effects")
 
 
+@pytest.mark.parametrize("taps", [1, 2, 777, 2048])
+def test_reverb_extension_vs_port(wb, taps):
+    """EXTENSION, parity unpinned (BASELINE cfg 5 at test size): the direct-form CUDA convolution against the port's
+    f64-accumulated specification, within 1e-5 of the block peak (bus and VU peaks), history across renders."""
+    ref = sc.reverb(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params, taps)
+    res = sc.reverb(gpu_engine(wb, True), wb.effect_params, taps)
+    peak = np.abs(ref["out"]).max(axis=(1, 2), keepdims=True)
+    err = np.abs(res["out"].astype(np.float64) - ref["out"])
+    assert np.all(err <= 1e-5 * peak), "reverb bus error %.3g of block peak" % float((err / peak).max())
+    pk = np.abs(ref["peaks"]).max()
+    assert np.all(np.abs(res["peaks"].astype(np.float64) - ref["peaks"]) <= 1e-5 * pk)
+    assert same_bits(res["sampler_offsets"], ref["sampler_offsets"])
+
+
+def test_reverb_delta_is_identity(wb):
+    """h = [1]: the convolution multiplies by exactly 1, so the render equals the chain-free one bit for bit."""
+    def run(with_ir):
+        rng = np.random.RandomState(12)
+        eng = wb.Engine(2, 512, 48000, 120.0, device=0, sum_mode=wb.SUM_EXACT)
+        if with_ir:
+            eng.set_impulse_response(np.array([1.0, 0.0, 0.0], np.float32))
+        for t in range(4):
+            eng.add_track(-4.0, 0.1 * t, False)
+            sid = eng.add_sample(sc._src(rng, 2, 5000, 4), 48000)
+            eng.add_clip(t, sid, 0.0, 8.0, 0.0, 1.0, 0.8)
+            if with_ir and t < 2:
+                eng.set_effects(t, wb.effect_params(reverb=True))
+        eng.play()
+        return eng.render(5)
+    (a, pa), (b, pb) = run(False), run(True)
+    assert same_bits(a, b) and same_bits(pa, pb)
+
+
 def test_effects_identity_properties(wb):
     """A compressor that never reaches its threshold multiplies by exactly 1: bit-identical to no chain."""
     def run(with_fx):

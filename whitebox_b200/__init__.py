@@ -31,16 +31,17 @@ class EffectParams(C.Structure):
     """wbx_effect_params (include/wbx.h) — same layout as the oracle's wbo_effects."""
     _fields_ = [("eq_freq", C.c_float * 4), ("eq_gain_db", C.c_float * 4), ("eq_q", C.c_float * 4),
                 ("comp_threshold_db", C.c_float), ("comp_attack_ms", C.c_float), ("comp_release_ms", C.c_float),
-                ("comp_makeup_db", C.c_float), ("comp_ratio_code", C.c_int32)]
+                ("comp_makeup_db", C.c_float), ("comp_ratio_code", C.c_int32), ("reverb_on", C.c_int32)]
 
 
 def effect_params(eq=((100.0, 0.0, 0.7), (500.0, 0.0, 1.0), (3000.0, 0.0, 1.0), (9000.0, 0.0, 0.7)),
-                  threshold_db=0.0, ratio_code=0, attack_ms=5.0, release_ms=80.0, makeup_db=0.0):
+                  threshold_db=0.0, ratio_code=0, attack_ms=5.0, release_ms=80.0, makeup_db=0.0, reverb=False):
     p = EffectParams()
     for b, (f, g, q) in enumerate(eq):
         p.eq_freq[b], p.eq_gain_db[b], p.eq_q[b] = f, g, q
     p.comp_threshold_db, p.comp_ratio_code = threshold_db, ratio_code
     p.comp_attack_ms, p.comp_release_ms, p.comp_makeup_db = attack_ms, release_ms, makeup_db
+    p.reverb_on = int(reverb)
     return p
 
 
@@ -57,11 +58,12 @@ WBX_SYMBOLS = [
     "wbx_set_sum_mode", "wbx_set_stream", "wbx_sample_upload", "wbx_sample_release", "wbx_sample_update", "wbx_sample_mipmap", "wbx_render", "wbx_submit",
     "wbx_mix", "wbx_fetch", "wbx_fetch_levels", "wbx_host_alloc", "wbx_host_free", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
     "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel", "wbx_effects_design", "wbx_set_track_effects",
+    "wbx_set_impulse_response",
 ]
 WBXH_SYMBOLS = [
     "wbxh_create", "wbxh_destroy", "wbxh_last_error", "wbxh_device", "wbxh_add_track", "wbxh_set_volume",
     "wbxh_set_pan", "wbxh_set_mute", "wbxh_add_sample", "wbxh_add_clip", "wbxh_add_clip_fade", "wbxh_set_playhead",
-    "wbxh_play", "wbxh_set_effects",
+    "wbxh_play", "wbxh_set_effects", "wbxh_set_impulse_response",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
 ]
@@ -134,6 +136,8 @@ def lib():
     L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     L.wbxh_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
     L.wbxh_set_effects.argtypes = [vp, i32, vp]
+    L.wbxh_set_impulse_response.argtypes = [vp, vp, u32]
+    L.wbx_set_impulse_response.argtypes = [vp, vp, u32]
     L.wbxh_set_playhead.argtypes = [vp, dbl]
     L.wbxh_set_playhead.restype = None
     for f in ("wbxh_play", "wbxh_stop"):
@@ -410,6 +414,13 @@ class Engine:
     def set_effects(self, track, params):
         """params: EffectParams (see effect_params()) or None to remove the chain."""
         self._ck(self.L.wbxh_set_effects(self.h, track, C.byref(params) if params is not None else None))
+
+    def set_impulse_response(self, h):
+        """Convolution-reverb impulse response (f32 array) shared by every chain with reverb=True; None removes it."""
+        if h is None:
+            return self._ck(self.L.wbxh_set_impulse_response(self.h, None, 0))
+        h = np.ascontiguousarray(h, np.float32)
+        return self._ck(self.L.wbxh_set_impulse_response(self.h, h.ctypes.data, h.size))
 
     def set_playhead(self, beat):
         self.L.wbxh_set_playhead(self.h, beat)

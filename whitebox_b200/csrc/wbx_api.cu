@@ -27,7 +27,8 @@ int mix_warps_per_sm(int fpl);
 cudaError_t launch_mipmap(const void* base, uint32_t fmt, uint32_t nch, uint64_t count, uint64_t chunk, uint64_t block,
                           uint64_t mdc, int high, void* out, cudaStream_t stream);
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
-                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, cudaStream_t stream);
+                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
+                           float* fir_hist, float* fir_in, cudaStream_t stream);
 }  // namespace wbx
 
 using namespace wbx;
@@ -62,7 +63,7 @@ struct wbx_engine {
   uint32_t C = 2, B = 512, rate = 48000, n_tracks = 0;
   int sum_mode = WBX_SUM_AUTO;
   std::vector<SampleRec> samples;
-  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels, d_fx, d_trackbuf;
+  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels, d_fx, d_trackbuf, d_ir, d_firhist, d_firin;
   HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv, h_levels, h_fx;
   std::vector<uint32_t> slot_busy;  // [track][slot] -> first free block
   uint32_t slot_cap = 0;
@@ -77,6 +78,8 @@ struct wbx_engine {
   std::vector<uint8_t> fx_reset;     // clear the track's state at the next submit
   bool fx_dirty = false;
   uint32_t n_fx = 0;                 // chains resident in d_fx
+  uint32_t ir_taps = 0;              // convolution reverb: taps of the impulse response in d_ir
+  uint32_t firhist_tracks = 0;       // tracks d_firhist is sized (and zeroed) for
   char err[256] = {0};
   char kernel_name[64] = {0};
 };
@@ -214,7 +217,7 @@ int wbx_destroy(wbx_engine* e) {
   for (auto& s : e->samples)
     if (s.live) cudaFree(s.d_base);
   for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv,
-                    &e->d_upload, &e->d_levels, &e->d_fx, &e->d_trackbuf})
+                    &e->d_upload, &e->d_levels, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin})
     if (b->p) cudaFree(b->p);
   for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
     if (b->p) cudaFreeHost(b->p);
@@ -430,6 +433,22 @@ int wbx_effects_design(const wbx_effect_params* p, uint32_t sample_rate, wbx_eff
   out->comp_makeup = (float)std::pow(10.0, (double)p->comp_makeup_db / 20.0);
   out->comp_attack = (float)std::exp(-1.0 / ((double)p->comp_attack_ms * 0.001 * (double)sample_rate));
   out->comp_release = (float)std::exp(-1.0 / ((double)p->comp_release_ms * 0.001 * (double)sample_rate));
+  out->reverb_on = p->reverb_on != 0;
+  return WBX_OK;
+}
+
+int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps) {
+  if (!e) return WBX_ERR_INVALID;
+  CU(e, cudaSetDevice(e->device));
+  CU(e, cudaStreamSynchronize(e->stream));
+  e->ir_taps = 0;
+  e->firhist_tracks = 0;  // histories are re-created (zeroed) at the next submit
+  if (!h || n_taps == 0) return WBX_OK;
+  int rc = dev_reserve(e, e->d_ir, (size_t)n_taps * sizeof(float));
+  if (rc) return rc;
+  CU(e, cudaMemcpyAsync(e->d_ir.p, h, (size_t)n_taps * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  e->ir_taps = n_taps;
   return WBX_OK;
 }
 
@@ -441,7 +460,7 @@ int wbx_set_track_effects(wbx_engine* e, uint32_t track, const wbx_effects* fx) 
     e->fx_on.resize(e->n_tracks, 0);
     e->fx_reset.resize(e->n_tracks, 0);
   }
-  const bool on = fx && (fx->eq_on || fx->comp_on);
+  const bool on = fx && (fx->eq_on || fx->comp_on || fx->reverb_on);
   if (on) e->fx[track] = *fx;
   e->fx_on[track] = on ? 1 : 0;
   e->fx_reset[track] = 1;
@@ -451,6 +470,7 @@ int wbx_set_track_effects(wbx_engine* e, uint32_t track, const wbx_effects* fx) 
 
 // (re)build the compact device array of chains, keeping the running state of tracks whose chain did not change
 static int sync_effects(wbx_engine* e) {
+  if (e->ir_taps > 1 && e->firhist_tracks != e->n_tracks && !e->fx_on.empty()) e->fx_dirty = true;
   if (!e->fx_dirty) return WBX_OK;
   std::vector<DFx> old;
   if (e->n_fx) {
@@ -475,6 +495,7 @@ static int sync_effects(wbx_engine* e) {
       d.a1[b] = f.a1[b];
       d.a2[b] = f.a2[b];
     }
+    d.reverb_on = f.reverb_on;
     d.thr = f.comp_threshold;
     d.att = f.comp_attack;
     d.rel = f.comp_release;
@@ -487,6 +508,20 @@ static int sync_effects(wbx_engine* e) {
           memcpy(d.env, o.env, sizeof(d.env));
         }
     cur.push_back(d);
+  }
+  // reverb histories: [n_tracks][2][taps-1]; (re)attached chains start from silence
+  if (e->ir_taps > 1) {
+    const size_t H = e->ir_taps - 1;
+    if (e->firhist_tracks != e->n_tracks) {
+      int rc = dev_reserve(e, e->d_firhist, (size_t)e->n_tracks * 2 * H * sizeof(float));
+      if (rc) return rc;
+      CU(e, cudaMemsetAsync(e->d_firhist.p, 0, (size_t)e->n_tracks * 2 * H * sizeof(float), e->stream));
+      e->firhist_tracks = e->n_tracks;
+    } else {
+      for (uint32_t t = 0; t < e->n_tracks && t < e->fx_reset.size(); t++)
+        if (e->fx_reset[t])
+          CU(e, cudaMemsetAsync((float*)e->d_firhist.p + (size_t)t * 2 * H, 0, 2 * H * sizeof(float), e->stream));
+    }
   }
   std::fill(e->fx_reset.begin(), e->fx_reset.end(), 0);
   e->n_fx = (uint32_t)cur.size();
@@ -617,9 +652,17 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     e->launches++;
   }
   if (n_fx && N) {
+    const bool reverb = e->ir_taps > 0 && e->firhist_tracks == N;
+    if (e->ir_taps > 0) {
+      const size_t H = e->ir_taps - 1;
+      if ((rc = dev_reserve(e, e->d_firin, (size_t)n_fx * C * (H + (size_t)n_blocks * B) * sizeof(float) + 256))) return rc;
+      if (H == 0 && (rc = dev_reserve(e, e->d_firhist, 256))) return rc;
+    }
+    const bool rv = e->ir_taps > 0 && (reverb || e->ir_taps == 1);
     CU(e, launch_effects((const DSpan*)e->d_spans.p, (DCell*)e->d_cells.p, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
-                         n_segs, (float*)e->d_trackbuf.p, e->stream));
-    e->launches += 3;
+                         n_segs, (float*)e->d_trackbuf.p, rv ? (const float*)e->d_ir.p : nullptr, rv ? e->ir_taps : 0,
+                         (float*)e->d_firhist.p, (float*)e->d_firin.p, e->stream));
+    e->launches += rv ? 6 : 3;
   }
   e->n_blocks = n_blocks;
   e->n_spans = n_segs;

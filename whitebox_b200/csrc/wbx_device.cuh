@@ -83,7 +83,8 @@ struct DFx {
   float b0[4], b1[4], b2[4], a1[4], a2[4];
   float thr, att, rel, makeup;
   float s1[2][4], s2[2][4], env[2];  // state, persists across renders
-  uint32_t pad[2];
+  uint32_t reverb_on;
+  uint32_t pad;
 };
 static_assert(sizeof(DFx) == 16 + 80 + 16 + 72 + 8, "DFx layout");
 

@@ -179,6 +179,11 @@ int Engine::add_audio_clip(Track* track, double min_time, double max_time, doubl
   return WBX_OK;
 }
 
+int Engine::set_impulse_response(const float* h, uint32_t n_taps) {
+  if (!dev_) return WBX_ERR_NO_DEVICE;
+  return wbx_set_impulse_response(dev_, h, n_taps);
+}
+
 void Engine::play() {
   for (auto* t : tracks) reset_playback_state(*t, playhead_start, false);
   sample_position = 0;
@@ -636,6 +641,9 @@ int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params)
   if (track < 0 || (size_t)track >= h->eng.tracks.size()) return WBX_ERR_INVALID;
   h->eng.tracks[track]->set_effects(params);
   return WBX_OK;
+}
+int wbxh_set_impulse_response(wbxh_engine* h, const float* ir, uint32_t n_taps) {
+  return h->eng.set_impulse_response(ir, n_taps);
 }
 void wbxh_set_playhead(wbxh_engine* h, double beat) { h->eng.set_playhead_position(beat); }
 void wbxh_play(wbxh_engine* h) { h->eng.play(); }

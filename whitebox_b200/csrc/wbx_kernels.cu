@@ -910,6 +910,68 @@ __global__ void effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, 
   f->env[c] = st.env;
 }
 
+// ---- convolution reverb (extension, cfg 5): direct form on the CUDA cores --------------------------------
+// xin  [n_fx][C][H + T] planar: H = taps - 1 history frames (oldest first) followed by this render's T chain outputs
+// hist [n_tracks][2][H] persists across renders (indexed by track, so it survives chain list rebuilds)
+__global__ void fir_gather_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T,
+                                  const float* __restrict__ hist, const float* __restrict__ trackbuf,
+                                  float* __restrict__ xin) {
+  const uint32_t ec = blockIdx.y;
+  const uint32_t e = ec / C, c = ec % C;
+  if (!fx[e].reverb_on) return;
+  const float* h = hist + ((size_t)fx[e].track * 2 + c) * H;
+  const float* tb = trackbuf + (size_t)e * T * 2 + c;
+  float* x = xin + (size_t)ec * (H + T);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H + T; i += (uint64_t)gridDim.x * blockDim.x)
+    x[i] = i < H ? h[i] : tb[(i - H) * 2];
+}
+
+// 256 consecutive outputs of one (track, channel) per CTA; taps in tiles of 256 staged in shared memory
+__global__ void __launch_bounds__(256) fir_kernel(const DFx* __restrict__ fx, uint32_t C, uint64_t H, uint64_t T,
+                                                   const float* __restrict__ ir, uint32_t L,
+                                                   const float* __restrict__ xin, float* __restrict__ trackbuf) {
+  __shared__ __align__(16) float hs[256];
+  __shared__ float xs[512];
+  const uint32_t ec = blockIdx.y;
+  const uint32_t e = ec / C, c = ec % C;
+  if (!fx[e].reverb_on) return;
+  const uint32_t tid = threadIdx.x;
+  const int64_t n0 = (int64_t)blockIdx.x * 256;
+  const float* x = xin + (size_t)ec * (H + T) + H;  // x[n - k], n - k >= -H
+  double total = 0.0;
+  for (uint32_t k0 = 0; k0 < L; k0 += 256) {
+    __syncthreads();
+    hs[tid] = (k0 + tid < L) ? __ldg(ir + k0 + tid) : 0.0f;
+    for (uint32_t i = tid; i < 511; i += 256) {  // xs[i] = x[n0 - k0 - 255 + i]
+      const int64_t p = n0 - (int64_t)k0 - 255 + (int64_t)i;
+      xs[i] = (p >= -(int64_t)H && p < (int64_t)T) ? x[p] : 0.0f;
+    }
+    __syncthreads();
+    float part = 0.0f;
+#pragma unroll 8
+    for (uint32_t kk = 0; kk < 256; kk += 4) {
+      const float4 h4 = *reinterpret_cast<const float4*>(&hs[kk]);
+      part = __fmaf_rn(h4.x, xs[tid + 255 - kk], part);
+      part = __fmaf_rn(h4.y, xs[tid + 254 - kk], part);
+      part = __fmaf_rn(h4.z, xs[tid + 253 - kk], part);
+      part = __fmaf_rn(h4.w, xs[tid + 252 - kk], part);
+    }
+    total += (double)part;
+  }
+  const int64_t n = n0 + tid;
+  if (n < (int64_t)T) trackbuf[((size_t)e * T + n) * 2 + c] = (float)total;
+}
+
+__global__ void fir_save_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T,
+                                const float* __restrict__ xin, float* __restrict__ hist) {
+  const uint32_t ec = blockIdx.y;
+  const uint32_t e = ec / C, c = ec % C;
+  if (!fx[e].reverb_on) return;
+  float* h = hist + ((size_t)fx[e].track * 2 + c) * H;
+  const float* x = xin + (size_t)ec * (H + T) + T;  // the last H entries
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H; i += (uint64_t)gridDim.x * blockDim.x) h[i] = x[i];
+}
+
 // point the cells of effect tracks at their processed buffer: one whole-block unity call per callback
 __global__ void patch_fx_cells_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                                       uint32_t B, uint32_t first_fx_span, DCell* __restrict__ cells) {
@@ -1174,11 +1236,20 @@ cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, ui
 }
 
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
-                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, cudaStream_t stream) {
+                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
+                           float* fir_hist, float* fir_in, cudaStream_t stream) {
   if (n_fx == 0) return cudaSuccess;
   const uint64_t warps = (uint64_t)n_fx * K;
   render_tracks_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, trackbuf);
   effects_kernel<<<(n_fx * C + 31) / 32, 32, 0, stream>>>(fx, n_fx, C, (uint64_t)K * B, trackbuf);
+  if (L && ir && fir_hist && fir_in) {  // convolution reverb as the chain's last stage
+    const uint64_t T = (uint64_t)K * B, H = L - 1;
+    const dim3 gcopy((unsigned)(((H + T) + 255) / 256 < 4096 ? ((H + T) + 255) / 256 : 4096), n_fx * C);
+    fir_gather_kernel<<<gcopy, 256, 0, stream>>>(fx, n_fx, C, H, T, fir_hist, trackbuf, fir_in);
+    fir_kernel<<<dim3((unsigned)((T + 255) / 256), n_fx * C), 256, 0, stream>>>(fx, C, H, T, ir, L, fir_in, trackbuf);
+    if (H) fir_save_kernel<<<dim3((unsigned)((H + 255) / 256 < 1024 ? (H + 255) / 256 : 1024), n_fx * C), 256, 0, stream>>>(
+        fx, n_fx, C, H, T, fir_in, fir_hist);
+  }
   patch_fx_cells_kernel<<<(unsigned)((warps + 127) / 128), 128, 0, stream>>>(fx, n_fx, N, S, K, B, first_fx_span, cells);
   return cudaGetLastError();
 }
