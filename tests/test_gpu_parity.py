@@ -116,10 +116,13 @@ def test_effects_extension_vs_port(wb, batched):
     assert_exact(sc.effects(gpu_engine(wb, batched), wb.effect_params), ref, "effects")
 
 
+@pytest.mark.parametrize("mode", ["direct", "tc"])
 @pytest.mark.parametrize("taps", [1, 2, 777, 2048])
-def test_reverb_extension_vs_port(wb, taps):
-    """EXTENSION, parity unpinned (BASELINE cfg 5 at test size): the direct-form CUDA convolution against the port's
-    f64-accumulated specification, within 1e-5 of the block peak (bus and VU peaks), history across renders."""
+def test_reverb_extension_vs_port(wb, taps, mode, monkeypatch):
+    """EXTENSION, parity unpinned (BASELINE cfg 5 at test size): the convolution reverb — direct form on the CUDA
+    cores and the tcgen05 tensor-core Toeplitz GEMM (3-term bf16 split) — against the port's f64-accumulated
+    specification, within 1e-5 of the block peak (bus and VU peaks), history carried across renders."""
+    monkeypatch.setenv("WBX_FIR", mode)
     ref = sc.reverb(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params, taps)
     res = sc.reverb(gpu_engine(wb, True), wb.effect_params, taps)
     peak = np.abs(ref["out"]).max(axis=(1, 2), keepdims=True)

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libwbx.so")
-SOURCES = ["wbx_kernels.cu", "wbx_api.cu", "wbx_host.cpp"]
+SOURCES = ["wbx_kernels.cu", "wbx_fir_tc.cu", "wbx_api.cu", "wbx_host.cpp"]
 HEADERS = [os.path.join(CSRC, "wbx_device.cuh")] + [
     os.path.join(ROOT, "include", h) for h in ("wbx.h", "wbx_host.h", "wbx_engine.hpp")]
 

@@ -28,7 +28,10 @@ cudaError_t launch_mipmap(const void* base, uint32_t fmt, uint32_t nch, uint64_t
                           uint64_t mdc, int high, void* out, cudaStream_t stream);
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
-                           float* fir_hist, float* fir_in, cudaStream_t stream);
+                           float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, cudaStream_t stream);
+size_t fir_tc_tiles_bytes(uint32_t L);
+uint64_t fir_tc_plane_width(uint64_t H, uint64_t T);
+cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, cudaStream_t stream);
 }  // namespace wbx
 
 using namespace wbx;
@@ -63,7 +66,7 @@ struct wbx_engine {
   uint32_t C = 2, B = 512, rate = 48000, n_tracks = 0;
   int sum_mode = WBX_SUM_AUTO;
   std::vector<SampleRec> samples;
-  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels, d_fx, d_trackbuf, d_ir, d_firhist, d_firin;
+  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels, d_fx, d_trackbuf, d_ir, d_firhist, d_firin, d_irtiles, d_firplanes;
   HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv, h_levels, h_fx;
   std::vector<uint32_t> slot_busy;  // [track][slot] -> first free block
   uint32_t slot_cap = 0;
@@ -80,6 +83,7 @@ struct wbx_engine {
   uint32_t n_fx = 0;                 // chains resident in d_fx
   uint32_t ir_taps = 0;              // convolution reverb: taps of the impulse response in d_ir
   uint32_t firhist_tracks = 0;       // tracks d_firhist is sized (and zeroed) for
+  bool fir_tc = false;               // impulse response expanded for the tensor-core path (d_irtiles)
   char err[256] = {0};
   char kernel_name[64] = {0};
 };
@@ -217,7 +221,7 @@ int wbx_destroy(wbx_engine* e) {
   for (auto& s : e->samples)
     if (s.live) cudaFree(s.d_base);
   for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv,
-                    &e->d_upload, &e->d_levels, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin})
+                    &e->d_upload, &e->d_levels, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin, &e->d_irtiles, &e->d_firplanes})
     if (b->p) cudaFree(b->p);
   for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
     if (b->p) cudaFreeHost(b->p);
@@ -447,6 +451,14 @@ int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps) {
   int rc = dev_reserve(e, e->d_ir, (size_t)n_taps * sizeof(float));
   if (rc) return rc;
   CU(e, cudaMemcpyAsync(e->d_ir.p, h, (size_t)n_taps * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  // long responses run on the tensor cores (WBX_FIR=direct / tc overrides the 1024-tap threshold)
+  const char* mode = getenv("WBX_FIR");
+  e->fir_tc = mode ? (mode[0] == 't') : (n_taps >= 1024);
+  if (e->fir_tc) {
+    if ((rc = dev_reserve(e, e->d_irtiles, fir_tc_tiles_bytes(n_taps)))) return rc;
+    CU(e, launch_fir_tc_prepare((const float*)e->d_ir.p, n_taps, e->d_irtiles.p, e->stream));
+    e->launches++;
+  }
   CU(e, cudaStreamSynchronize(e->stream));
   e->ir_taps = n_taps;
   return WBX_OK;
@@ -659,10 +671,16 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
       if (H == 0 && (rc = dev_reserve(e, e->d_firhist, 256))) return rc;
     }
     const bool rv = e->ir_taps > 0 && (reverb || e->ir_taps == 1);
+    const bool tc = rv && e->fir_tc;
+    if (tc) {
+      const uint64_t W = fir_tc_plane_width(e->ir_taps - 1, (uint64_t)n_blocks * B);
+      if ((rc = dev_reserve(e, e->d_firplanes, (size_t)3 * n_fx * C * W * 2 + 256))) return rc;
+    }
     CU(e, launch_effects((const DSpan*)e->d_spans.p, (DCell*)e->d_cells.p, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
                          n_segs, (float*)e->d_trackbuf.p, rv ? (const float*)e->d_ir.p : nullptr, rv ? e->ir_taps : 0,
-                         (float*)e->d_firhist.p, (float*)e->d_firin.p, e->stream));
-    e->launches += rv ? 6 : 3;
+                         (float*)e->d_firhist.p, (float*)e->d_firin.p, tc ? e->d_irtiles.p : nullptr,
+                         tc ? e->d_firplanes.p : nullptr, e->stream));
+    e->launches += rv ? (tc ? 7 : 6) : 3;
   }
   e->n_blocks = n_blocks;
   e->n_spans = n_segs;

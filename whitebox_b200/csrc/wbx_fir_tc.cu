@@ -1,0 +1,324 @@
+// wbx_fir_tc.cu — convolution reverb on the 5th-generation tensor cores (BASELINE cfg 5; extension, see wbx.h).
+//
+// y[n, s] = sum_k h[k] * x[n - k, s] for S signals (track x channel) as a GEMM with a Toeplitz operand:
+//     D[128 output times, 128 signals] += A_i[128, 64] * B_i[64, 128]        for tap chunks i = 0 .. n_chunks-1
+//     A_i[m][j] = h[64 i - 64 + m - j]      (depends only on the impulse response: expanded once per IR, L2-resident)
+//     B_i[j][s] = x[n0 + 64 - 64 i + j, s]  (a plain K-major slice of the signal planes, fetched by TMA; out-of-range
+//                                            times are zero-filled by the tensor map)
+// tcgen05.mma (kind::f16, bf16 inputs, f32 accumulators in TMEM) issued by one thread; operands staged by
+// cp.async.bulk.tensor into 128B-swizzled shared memory through a 2-stage mbarrier pipeline; accumulators read
+// back with tcgen05.ld. f32 accuracy from a 3-term bf16 split of both operands (x = x1 + x2 + x3 exactly to 24
+// bits), keeping the six products of order <= 2^-16: h1x1, h1x2, h2x1, h1x3, h2x2, h3x1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "wbx_device.cuh"
+
+namespace wbx {
+
+namespace {
+
+constexpr int TC_M = 128;               // output times per CTA (UMMA M, TMEM lanes)
+constexpr int TC_N = 128;               // signals per CTA (UMMA N, TMEM columns)
+constexpr int TC_K = 64;                // input times per chunk = one 128-byte swizzle row of bf16
+constexpr int TC_STAGES = 2;
+constexpr int TC_TILE_BYTES = 128 * TC_K * 2;        // 16 KiB: [128 rows][64 bf16], SWIZZLE_128B
+constexpr int TC_STAGE_BYTES = 6 * TC_TILE_BYTES;    // A1 A2 A3 B1 B2 B3
+constexpr int TC_THREADS = 192;                      // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile [rows][64 bf16]: 8-row groups are 1024 B apart (SBO), rows 128 B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {  // arrives on `bar` when all prior MMAs have completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct FirTcParams {
+  const DFx* fx;
+  float* trackbuf;  // [n_fx][T][2]
+  uint32_t C;       // bus channels: signal index = e * C + c
+  uint32_t n_signals;
+  uint64_t H, T;    // history frames (taps - 1), frames in this render
+  uint32_t n_chunks;
+};
+
+}  // namespace
+
+// x -> x1 + x2 + x3 with bf16 terms (exact to 24 bits); planes are [signals][W] with W >= len, zero padded
+__global__ void split_bf16_kernel(const float* __restrict__ x, uint64_t len, uint64_t W, uint32_t n_signals,
+                                  __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2,
+                                  __nv_bfloat16* __restrict__ p3) {
+  const uint32_t s = blockIdx.y;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < W; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float v = i < len ? x[(size_t)s * len + i] : 0.0f;
+    const __nv_bfloat16 a = __float2bfloat16_rn(v);
+    const float r1 = __fsub_rn(v, __bfloat162float(a));
+    const __nv_bfloat16 b = __float2bfloat16_rn(r1);
+    const float r2 = __fsub_rn(r1, __bfloat162float(b));
+    p1[(size_t)s * W + i] = a;
+    p2[(size_t)s * W + i] = b;
+    p3[(size_t)s * W + i] = __float2bfloat16_rn(r2);
+  }
+}
+
+// Toeplitz expansion of the impulse response: tiles[i][m][j] = h[64 i - 64 + m - j], three bf16 terms
+__global__ void toeplitz_kernel(const float* __restrict__ h, uint32_t L, uint32_t n_chunks, __nv_bfloat16* __restrict__ a1,
+                                __nv_bfloat16* __restrict__ a2, __nv_bfloat16* __restrict__ a3) {
+  const uint64_t total = (uint64_t)n_chunks * TC_M * TC_K;
+  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t j = (uint32_t)(o % TC_K), m = (uint32_t)((o / TC_K) % TC_M), i = (uint32_t)(o / (TC_K * TC_M));
+    const int64_t k = 64 * (int64_t)i - 64 + (int64_t)m - (int64_t)j;
+    const float v = (k >= 0 && k < (int64_t)L) ? h[k] : 0.0f;
+    const __nv_bfloat16 a = __float2bfloat16_rn(v);
+    const float r1 = __fsub_rn(v, __bfloat162float(a));
+    const __nv_bfloat16 b = __float2bfloat16_rn(r1);
+    const float r2 = __fsub_rn(r1, __bfloat162float(b));
+    a1[o] = a;
+    a2[o] = b;
+    a3[o] = __float2bfloat16_rn(r2);
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+fir_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+              const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapX1,
+              const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapX3, const FirTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // operand tiles need 1024-byte alignment (128B swizzle atoms)
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * TC_STAGE_BYTES);
+  const uint32_t full0 = s32(&bars[0]), empty0 = s32(&bars[TC_STAGES]), tmem_full = s32(&bars[2 * TC_STAGES]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * TC_STAGES + 1]);
+
+  const int64_t n0 = (int64_t)blockIdx.x * TC_M;
+  const int s0 = (int)blockIdx.y * TC_N;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; s++) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 128 columns of f32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"((uint32_t)TC_N)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (uint32_t i = 0; i < p.n_chunks; i++) {
+        const uint32_t st = i % TC_STAGES;
+        mbar_wait(empty0 + 8 * st, ((i / TC_STAGES) & 1u) ^ 1u);
+        const uint32_t base = s32(tiles + (size_t)st * TC_STAGE_BYTES);
+        const uint32_t bar = full0 + 8 * st;
+        mbar_expect_tx(bar, TC_STAGE_BYTES);
+        const int arow = (int)(i * TC_M);
+        tma_load_2d(base + 0 * TC_TILE_BYTES, &mapA1, 0, arow, bar);
+        tma_load_2d(base + 1 * TC_TILE_BYTES, &mapA2, 0, arow, bar);
+        tma_load_2d(base + 2 * TC_TILE_BYTES, &mapA3, 0, arow, bar);
+        const int t = (int)((int64_t)p.H + n0 + 64 - 64 * (int64_t)i);  // plane column of input time n0 + 64 - 64 i
+        tma_load_2d(base + 3 * TC_TILE_BYTES, &mapX1, t, s0, bar);
+        tma_load_2d(base + 4 * TC_TILE_BYTES, &mapX2, t, s0, bar);
+        tma_load_2d(base + 5 * TC_TILE_BYTES, &mapX3, t, s0, bar);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    const uint32_t idesc = umma_idesc(TC_M, TC_N);
+    for (uint32_t i = 0; i < p.n_chunks; i++) {
+      const uint32_t st = i % TC_STAGES;
+      mbar_wait(full0 + 8 * st, (i / TC_STAGES) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t base = s32(tiles + (size_t)st * TC_STAGE_BYTES);
+        // (h term, x term): all products of order <= 2^-16
+        const int ha[6] = {0, 0, 1, 0, 1, 2}, xb[6] = {0, 1, 0, 2, 1, 0};
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          const uint64_t da = umma_desc(base + ha[q] * TC_TILE_BYTES);
+          const uint64_t db = umma_desc(base + (3 + xb[q]) * TC_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < TC_K / 16; ks++)  // UMMA K = 16 bf16 = 32 bytes = +2 in 16-byte address units
+            umma_bf16(tmem_base, da + 2 * ks, db + 2 * ks, idesc, (i | q | ks) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * st);                        // frees this stage's shared memory
+        if (i + 1 == p.n_chunks) umma_commit(tmem_full);     // accumulators complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> track buffer =====
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t quarter = warp & 3u;  // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
+    const int64_t n = n0 + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_N; c0 += 16) {
+      uint32_t v[16];
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (n < (int64_t)p.T) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          const uint32_t sig = (uint32_t)(s0 + c0 + q);
+          if (sig < p.n_signals) {
+            const uint32_t e = sig / p.C, c = sig % p.C;
+            if (p.fx[e].reverb_on) p.trackbuf[((size_t)e * p.T + (size_t)n) * 2 + c] = __uint_as_float(v[q]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_N) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] (cols contiguous), box = 64 cols x 128 rows, 128-byte swizzle, zero fill
+static bool make_map(CUtensorMap* m, void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {pitch_elems * 2};
+  const cuuint32_t box[2] = {TC_K, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+uint32_t fir_tc_chunks(uint32_t L) { return (L - 1 + 64 + 63) / 64 + 1; }
+size_t fir_tc_tiles_bytes(uint32_t L) { return (size_t)3 * fir_tc_chunks(L) * TC_TILE_BYTES; }
+uint64_t fir_tc_plane_width(uint64_t H, uint64_t T) { return (H + T + 7) & ~(uint64_t)7; }
+
+// once per impulse response: the three Toeplitz term planes, each [n_chunks * 128][64] bf16
+cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, cudaStream_t stream) {
+  const uint32_t nc = fir_tc_chunks(L);
+  __nv_bfloat16* a = (__nv_bfloat16*)tiles;
+  const size_t plane = (size_t)nc * TC_M * TC_K;
+  toeplitz_kernel<<<1024, 256, 0, stream>>>(ir, L, nc, a, a + plane, a + 2 * plane);
+  return cudaGetLastError();
+}
+
+// xin: f32 [n_signals][H + T]; planes: scratch for 3 x [n_signals][W] bf16
+cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T, uint32_t L, void* tiles,
+                          const float* xin, void* planes, float* trackbuf, cudaStream_t stream) {
+  const uint32_t S = n_fx * C;
+  if (S == 0 || T == 0) return cudaSuccess;
+  const uint64_t W = fir_tc_plane_width(H, T);
+  const uint32_t nc = fir_tc_chunks(L);
+  __nv_bfloat16* x1 = (__nv_bfloat16*)planes;
+  __nv_bfloat16* x2 = x1 + (size_t)S * W;
+  __nv_bfloat16* x3 = x2 + (size_t)S * W;
+  split_bf16_kernel<<<dim3((unsigned)((W + 255) / 256 < 2048 ? (W + 255) / 256 : 2048), S), 256, 0, stream>>>(xin, H + T, W, S,
+                                                                                                             x1, x2, x3);
+  CUtensorMap mA[3], mX[3];
+  __nv_bfloat16* a = (__nv_bfloat16*)tiles;
+  const size_t aplane = (size_t)nc * TC_M * TC_K;
+  for (int t = 0; t < 3; t++) {
+    if (!make_map(&mA[t], a + t * aplane, TC_K, (uint64_t)nc * TC_M, TC_K)) return cudaErrorNotSupported;
+    if (!make_map(&mX[t], x1 + (size_t)t * S * W, W, S, W)) return cudaErrorNotSupported;
+  }
+  cudaError_t err = cudaFuncSetAttribute(fir_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (err != cudaSuccess) return err;
+  FirTcParams p;
+  p.fx = fx;
+  p.trackbuf = trackbuf;
+  p.C = C;
+  p.n_signals = S;
+  p.H = H;
+  p.T = T;
+  p.n_chunks = nc;
+  fir_tc_kernel<<<dim3((unsigned)((T + TC_M - 1) / TC_M), (S + TC_N - 1) / TC_N), TC_THREADS, TC_SMEM, stream>>>(
+      mA[0], mA[1], mA[2], mX[0], mX[1], mX[2], p);
+  return cudaGetLastError();
+}
+
+}  // namespace wbx

@@ -1235,9 +1235,12 @@ cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, ui
   return cudaGetLastError();
 }
 
+cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T, uint32_t L, void* tiles,
+                          const float* xin, void* planes, float* trackbuf, cudaStream_t stream);  // wbx_fir_tc.cu
+
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
-                           float* fir_hist, float* fir_in, cudaStream_t stream) {
+                           float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, cudaStream_t stream) {
   if (n_fx == 0) return cudaSuccess;
   const uint64_t warps = (uint64_t)n_fx * K;
   render_tracks_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, trackbuf);
@@ -1246,7 +1249,12 @@ cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n
     const uint64_t T = (uint64_t)K * B, H = L - 1;
     const dim3 gcopy((unsigned)(((H + T) + 255) / 256 < 4096 ? ((H + T) + 255) / 256 : 4096), n_fx * C);
     fir_gather_kernel<<<gcopy, 256, 0, stream>>>(fx, n_fx, C, H, T, fir_hist, trackbuf, fir_in);
-    fir_kernel<<<dim3((unsigned)((T + 255) / 256), n_fx * C), 256, 0, stream>>>(fx, C, H, T, ir, L, fir_in, trackbuf);
+    if (tc_tiles && tc_planes) {  // tensor-core path (wbx_fir_tc.cu)
+      cudaError_t err = launch_fir_tc(fx, n_fx, C, H, T, L, tc_tiles, fir_in, tc_planes, trackbuf, stream);
+      if (err != cudaSuccess) return err;
+    } else {
+      fir_kernel<<<dim3((unsigned)((T + 255) / 256), n_fx * C), 256, 0, stream>>>(fx, C, H, T, ir, L, fir_in, trackbuf);
+    }
     if (H) fir_save_kernel<<<dim3((unsigned)((H + 255) / 256 < 1024 ? (H + 255) / 256 : 1024), n_fx * C), 256, 0, stream>>>(
         fx, n_fx, C, H, T, fir_in, fir_hist);
   }
