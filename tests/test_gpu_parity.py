@@ -133,6 +133,16 @@ def test_reverb_extension_vs_port(wb, taps, mode, monkeypatch):
     assert same_bits(res["sampler_offsets"], ref["sampler_offsets"])
 
 
+def test_reverb_cfg5_tap_count_tensor_cores(wb, monkeypatch):
+    """BASELINE cfg 5's 65536-tap impulse response on the tensor-core path, against the f64 specification."""
+    monkeypatch.setenv("WBX_FIR", "tc")
+    ref = sc.reverb(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params, 65536)
+    res = sc.reverb(gpu_engine(wb, True), wb.effect_params, 65536)
+    peak = np.abs(ref["out"]).max(axis=(1, 2), keepdims=True)
+    err = np.abs(res["out"].astype(np.float64) - ref["out"])
+    assert np.all(err <= 1e-5 * peak), "reverb bus error %.3g of block peak" % float((err / peak).max())
+
+
 def test_reverb_delta_is_identity(wb):
     """h = [1]: the convolution multiplies by exactly 1, so the render equals the chain-free one bit for bit."""
     def run(with_ir):

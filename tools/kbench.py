@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--offset", type=int, default=0, help="clip start offset in frames (unaligned windows)")
     ap.add_argument("--tree", type=int, default=0)
     ap.add_argument("--fx", type=int, default=0, help="1: every track carries the 4-band EQ + compressor chain (cfg 4)")
+    ap.add_argument("--reverb", type=int, default=0, help="taps of a convolution reverb on every track (cfg 5)")
     args = ap.parse_args()
     import torch
     import whitebox_b200 as wb
@@ -41,6 +42,29 @@ def main():
     stream = torch.cuda.Stream()
     dev.set_stream(stream.cuda_stream)
     dev.set_sum_mode(wb.SUM_TREE if args.tree else wb.SUM_EXACT)
+    if args.reverb:
+        import ctypes as C
+        ir = (np.random.default_rng(2).standard_normal(args.reverb) * np.exp(-np.arange(args.reverb) / (args.reverb / 6.0)) * 0.01).astype(np.float32)
+        ir[0] = 1.0
+        assert wb.lib().wbx_set_impulse_response(dev.h, ir.ctypes.data, ir.size) == 0
+        p = wb.effect_params(reverb=True)
+        fx = (C.c_uint8 * 256)()
+        assert wb.lib().wbx_effects_design(C.byref(p), 48000, fx) == 0
+        for t in range(N):
+            assert wb.lib().wbx_set_track_effects(dev.h, t, fx) == 0
+        with torch.cuda.stream(stream):
+            dev.submit(segs, gains, K)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.iters):
+                dev.submit(segs, gains, K)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        macs = N * 2 * K * B * args.reverb
+        print("reverb submit (%s), %d tracks x %d callbacks x %d taps: %.3f ms  %.3e MAC/s (%.1f TFLOP/s direct-form count)  %.2fx realtime" %
+              (os.environ.get("WBX_FIR", "auto"), N, K, args.reverb, ms, macs / ms * 1e3, 2 * macs / ms * 1e3 / 1e12,
+               K * B / 48000.0 / (ms * 1e-3)), flush=True)
     if args.fx:
         import ctypes as C
         p = wb.effect_params(eq=((120.0, 4.0, 0.7), (800.0, -6.0, 1.2), (2500.0, 3.0, 2.0), (8000.0, 5.0, 0.7)),

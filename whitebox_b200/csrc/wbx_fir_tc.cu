@@ -9,6 +9,10 @@
 // cp.async.bulk.tensor into 128B-swizzled shared memory through a 2-stage mbarrier pipeline; accumulators read
 // back with tcgen05.ld. f32 accuracy from a 3-term bf16 split of both operands (x = x1 + x2 + x3 exactly to 24
 // bits), keeping the six products of order <= 2^-16: h1x1, h1x2, h2x1, h1x3, h2x2, h3x1.
+// The tensor core's f32 accumulate truncates, so a long accumulation chain drifts (measured 7e-6 of peak after
+// 336 accumulate steps): the leading product h1x1 and the five small ones go to SEPARATE TMEM accumulators, and
+// every TC_G chunks the epilogue warps drain both into f32 registers (round-to-nearest adds) while the MMA warp
+// continues in a second TMEM buffer (2 buffers x 2 accumulators x 128 columns = all 512 TMEM columns).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -25,6 +29,7 @@ constexpr int TC_M = 128;               // output times per CTA (UMMA M, TMEM la
 constexpr int TC_N = 128;               // signals per CTA (UMMA N, TMEM columns)
 constexpr int TC_K = 64;                // input times per chunk = one 128-byte swizzle row of bf16
 constexpr int TC_STAGES = 2;
+constexpr int TC_G = 8;                 // chunks accumulated in TMEM before a drain (32 full-magnitude MMA steps)
 constexpr int TC_TILE_BYTES = 128 * TC_K * 2;        // 16 KiB: [128 rows][64 bf16], SWIZZLE_128B
 constexpr int TC_STAGE_BYTES = 6 * TC_TILE_BYTES;    // A1 A2 A3 B1 B2 B3
 constexpr int TC_THREADS = 192;                      // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
@@ -90,19 +95,20 @@ struct FirTcParams {
   float* trackbuf;  // [n_fx][T][2]
   uint32_t C;       // bus channels: signal index = e * C + c
   uint32_t n_signals;
-  uint64_t H, T;    // history frames (taps - 1), frames in this render
+  uint64_t H, T;    // plane column of input time 0 (history rounded up to 8 columns), frames in this render
   uint32_t n_chunks;
 };
 
 }  // namespace
 
-// x -> x1 + x2 + x3 with bf16 terms (exact to 24 bits); planes are [signals][W] with W >= len, zero padded
-__global__ void split_bf16_kernel(const float* __restrict__ x, uint64_t len, uint64_t W, uint32_t n_signals,
+// x -> x1 + x2 + x3 with bf16 terms (exact to 24 bits); planes are [signals][W]: `lead` zero columns (so that the
+// TMA box start — 16-byte aligned — lands on a multiple of 8 columns), then the len inputs, then zero padding
+__global__ void split_bf16_kernel(const float* __restrict__ x, uint64_t len, uint64_t lead, uint64_t W, uint32_t n_signals,
                                   __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2,
                                   __nv_bfloat16* __restrict__ p3) {
   const uint32_t s = blockIdx.y;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < W; i += (uint64_t)gridDim.x * blockDim.x) {
-    const float v = i < len ? x[(size_t)s * len + i] : 0.0f;
+    const float v = (i >= lead && i - lead < len) ? x[(size_t)s * len + (i - lead)] : 0.0f;
     const __nv_bfloat16 a = __float2bfloat16_rn(v);
     const float r1 = __fsub_rn(v, __bfloat162float(a));
     const __nv_bfloat16 b = __float2bfloat16_rn(r1);
@@ -140,8 +146,9 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__
   // operand tiles need 1024-byte alignment (128B swizzle atoms)
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * TC_STAGE_BYTES);
-  const uint32_t full0 = s32(&bars[0]), empty0 = s32(&bars[TC_STAGES]), tmem_full = s32(&bars[2 * TC_STAGES]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * TC_STAGES + 1]);
+  const uint32_t full0 = s32(&bars[0]), empty0 = s32(&bars[TC_STAGES]);
+  const uint32_t tfull0 = s32(&bars[2 * TC_STAGES]), tempty0 = s32(&bars[2 * TC_STAGES + 2]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * TC_STAGES + 4]);
 
   const int64_t n0 = (int64_t)blockIdx.x * TC_M;
   const int s0 = (int)blockIdx.y * TC_N;
@@ -151,12 +158,15 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(tfull0 + 8 * b, 1);   // tcgen05.commit of the group's last MMA
+      mbar_init(tempty0 + 8 * b, 4);  // one arrival per epilogue warp once it has drained the buffer
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 128 columns of f32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"((uint32_t)TC_N)
+  if (warp == 1) {  // TMEM: 2 buffers x (leading-product + small-products) accumulators x 128 f32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -189,49 +199,71 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__
     const uint32_t idesc = umma_idesc(TC_M, TC_N);
     for (uint32_t i = 0; i < p.n_chunks; i++) {
       const uint32_t st = i % TC_STAGES;
+      const uint32_t g = i / TC_G, b = g & 1u, ig = i % TC_G;
+      if (ig == 0) mbar_wait(tempty0 + 8 * b, ((g >> 1) & 1u) ^ 1u);  // epilogue drained this TMEM buffer
       mbar_wait(full0 + 8 * st, (i / TC_STAGES) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t base = s32(tiles + (size_t)st * TC_STAGE_BYTES);
-        // (h term, x term): all products of order <= 2^-16
+        const uint32_t d_hi = tmem_base + b * 256u, d_lo = d_hi + 128u;
+        // (h term, x term): all products of order <= 2^-16; q == 0 is the leading product
         const int ha[6] = {0, 0, 1, 0, 1, 2}, xb[6] = {0, 1, 0, 2, 1, 0};
 #pragma unroll
         for (int q = 0; q < 6; q++) {
           const uint64_t da = umma_desc(base + ha[q] * TC_TILE_BYTES);
           const uint64_t db = umma_desc(base + (3 + xb[q]) * TC_TILE_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < TC_K / 16; ks++)  // UMMA K = 16 bf16 = 32 bytes = +2 in 16-byte address units
-            umma_bf16(tmem_base, da + 2 * ks, db + 2 * ks, idesc, (i | q | ks) ? 1u : 0u);
+          for (int ks = 0; ks < TC_K / 16; ks++) {  // UMMA K = 16 bf16 = 32 bytes = +2 in 16-byte address units
+            const uint32_t first = (q == 0) ? (ig | ks) : (ig | (q - 1) | ks);  // 0 on the accumulator's first MMA of the group
+            umma_bf16(q == 0 ? d_hi : d_lo, da + 2 * ks, db + 2 * ks, idesc, first ? 1u : 0u);
+          }
         }
-        umma_commit(empty0 + 8 * st);                        // frees this stage's shared memory
-        if (i + 1 == p.n_chunks) umma_commit(tmem_full);     // accumulators complete
+        umma_commit(empty0 + 8 * st);                                       // frees this stage's shared memory
+        if (ig == TC_G - 1 || i + 1 == p.n_chunks) umma_commit(tfull0 + 8 * b);  // this group's accumulators are complete
       }
       __syncwarp();
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> track buffer =====
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ===== epilogue: drain TMEM groups into f32 registers, then registers -> track buffer =====
     const uint32_t quarter = warp & 3u;  // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
     const int64_t n = n0 + quarter * 32 + lane;
-#pragma unroll 1
-    for (int c0 = 0; c0 < TC_N; c0 += 16) {
-      uint32_t v[16];
-      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (n < (int64_t)p.T) {
+    float acc[TC_N];
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-          const uint32_t sig = (uint32_t)(s0 + c0 + q);
-          if (sig < p.n_signals) {
-            const uint32_t e = sig / p.C, c = sig % p.C;
-            if (p.fx[e].reverb_on) p.trackbuf[((size_t)e * p.T + (size_t)n) * 2 + c] = __uint_as_float(v[q]);
-          }
+    for (int q = 0; q < TC_N; q++) acc[q] = 0.0f;
+    const uint32_t n_groups = (p.n_chunks + TC_G - 1) / TC_G;
+    for (uint32_t g = 0; g < n_groups; g++) {
+      const uint32_t b = g & 1u;
+      mbar_wait(tfull0 + 8 * b, (g >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow = tmem_base + ((quarter * 32u) << 16) + b * 256u;
+#pragma unroll
+      for (int c0 = 0; c0 < TC_N; c0 += 16) {
+        uint32_t v[16], w[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(trow + (uint32_t)c0));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+              "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+            : "r"(trow + 128u + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 16; q++) acc[c0 + q] = __fadd_rn(acc[c0 + q], __fadd_rn(__uint_as_float(v[q]), __uint_as_float(w[q])));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * b) : "memory");
+    }
+    if (n < (int64_t)p.T) {
+#pragma unroll
+      for (int q = 0; q < TC_N; q++) {
+        const uint32_t sig = (uint32_t)(s0 + q);
+        if (sig < p.n_signals) {
+          const uint32_t e = sig / p.C, c = sig % p.C;
+          if (p.fx[e].reverb_on) p.trackbuf[((size_t)e * p.T + (size_t)n) * 2 + c] = acc[q];
         }
       }
     }
@@ -239,7 +271,7 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_N) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -276,7 +308,8 @@ static bool make_map(CUtensorMap* m, void* base, uint64_t cols, uint64_t rows, u
 
 uint32_t fir_tc_chunks(uint32_t L) { return (L - 1 + 64 + 63) / 64 + 1; }
 size_t fir_tc_tiles_bytes(uint32_t L) { return (size_t)3 * fir_tc_chunks(L) * TC_TILE_BYTES; }
-uint64_t fir_tc_plane_width(uint64_t H, uint64_t T) { return (H + T + 7) & ~(uint64_t)7; }
+static uint64_t fir_tc_origin(uint64_t H) { return (H + 7) & ~(uint64_t)7; }  // plane column of input time 0
+uint64_t fir_tc_plane_width(uint64_t H, uint64_t T) { return (fir_tc_origin(H) + T + 7) & ~(uint64_t)7; }
 
 // once per impulse response: the three Toeplitz term planes, each [n_chunks * 128][64] bf16
 cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, cudaStream_t stream) {
@@ -297,8 +330,9 @@ cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, 
   __nv_bfloat16* x1 = (__nv_bfloat16*)planes;
   __nv_bfloat16* x2 = x1 + (size_t)S * W;
   __nv_bfloat16* x3 = x2 + (size_t)S * W;
-  split_bf16_kernel<<<dim3((unsigned)((W + 255) / 256 < 2048 ? (W + 255) / 256 : 2048), S), 256, 0, stream>>>(xin, H + T, W, S,
-                                                                                                             x1, x2, x3);
+  const uint64_t origin = fir_tc_origin(H);
+  split_bf16_kernel<<<dim3((unsigned)((W + 255) / 256 < 2048 ? (W + 255) / 256 : 2048), S), 256, 0, stream>>>(
+      xin, H + T, origin - H, W, S, x1, x2, x3);
   CUtensorMap mA[3], mX[3];
   __nv_bfloat16* a = (__nv_bfloat16*)tiles;
   const size_t aplane = (size_t)nc * TC_M * TC_K;
@@ -313,7 +347,7 @@ cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, 
   p.trackbuf = trackbuf;
   p.C = C;
   p.n_signals = S;
-  p.H = H;
+  p.H = origin;  // the kernel only needs the plane column of input time 0
   p.T = T;
   p.n_chunks = nc;
   fir_tc_kernel<<<dim3((unsigned)((T + TC_M - 1) / TC_M), (S + TC_N - 1) / TC_N), TC_THREADS, TC_SMEM, stream>>>(
