@@ -72,7 +72,7 @@ typedef struct wbx_segment {
   double src_pos;      /* Sampler::sample_offset_ at the first call */
   double speed;        /* Sampler::playback_speed_ = src_rate / dst_rate * clip speed (sampler.h:24), > 0 */
   float gain;          /* AudioClip::gain (engine/clip.h:44) */
-  uint32_t flags;      /* WBX_SEG_FADE or 0 */
+  uint32_t flags;      /* WBX_SEG_FADE | WBX_SEG_POLYPHASE or 0 */
   /* Fade envelope — EXTENSION, not in the reference: AudioClip::fade_start / fade_end (engine/clip.h:41-42)
    * are stored and drawn by whitebox but no audio code reads them. Spec (oracle/wb_oracle.c, "parity unpinned"):
    * for clip-relative output frame n = clip_frame + j,
@@ -87,6 +87,11 @@ typedef struct wbx_segment {
 } wbx_segment;
 
 #define WBX_SEG_FADE 1u
+/* Polyphase quality mode — EXTENSION, not in the reference (its only resampler is the 2-tap linear one,
+ * dsp/sampler.h:8-11): a call with speed != 1 on a stereo f32 sample into a stereo bus is resampled with a 128-phase
+ * x 16-tap Blackman-windowed sinc (oracle/wb_oracle.c sample_polyphase, "parity unpinned") instead of the lerp; the
+ * position arithmetic is the reference's. Every other case ignores the flag. */
+#define WBX_SEG_POLYPHASE 2u
 
 /* Bus summation order (wbx_set_sum_mode). */
 typedef enum wbx_sum_mode {

@@ -136,6 +136,9 @@ class Engine {
   double playhead = 0, playhead_start = 0, sample_position = 0;
   bool playing = false;
   bool fast_forward = true;  // skip event-free callbacks in closed form while scheduling (same results)
+  // dsp::ResamplerType (dsp/sampler.h:8-11): 0 = Linear, what Track::process hard-codes (track.cpp:692-697);
+  // 1 = polyphase windowed sinc (extension, see WBX_SEG_POLYPHASE in wbx.h)
+  int resampler_mode = 0;
 
  private:
   void process_event(Track& t, double start_time, double end_time, double sample_position_, double beat_duration,

@@ -41,6 +41,7 @@ int wbxh_add_clip_fade(wbxh_engine* h, int track, int sample, double min_beat, d
 /* attach (params != NULL) or remove the built-in EQ + compressor chain of a track (extension, see wbx.h) */
 int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params);
 int wbxh_set_impulse_response(wbxh_engine* h, const float* ir, uint32_t n_taps); /* convolution reverb IR (wbx.h) */
+void wbxh_set_resampler(wbxh_engine* h, int mode); /* 0 linear (reference), 1 polyphase (extension, wbx.h) */
 void wbxh_set_playhead(wbxh_engine* h, double beat);
 void wbxh_play(wbxh_engine* h);
 void wbxh_stop(wbxh_engine* h);

@@ -109,6 +109,7 @@ int wbo_add_clip_fade(wbo_session* s, int track, int sample, double min_beat, do
 
 int wbo_set_effects(wbo_session*, int, const wbo_effects*) { return -1; }  // the reference has no effects
 int wbo_set_impulse_response(wbo_session*, const float*, uint32_t) { return -1; }
+void wbo_set_resampler(wbo_session*, int) {}  // the reference has only the linear resampler
 
 void wbo_set_playhead(wbo_session* s, double beat) { s->engine.set_playhead_position(beat); }
 void wbo_play(wbo_session* s) { s->engine.play(); }

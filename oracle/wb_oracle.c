@@ -110,6 +110,8 @@ struct wbo_session {
   float** out;
   float* ir; /* EXTENSION: session impulse response */
   uint32_t ir_taps;
+  int resampler;          /* EXTENSION: 0 linear (reference), 1 polyphase */
+  float poly[128 * 16];   /* polyphase coefficient table */
 };
 
 const char* wbo_kind(void) { return "port"; }
@@ -467,6 +469,46 @@ static void process_event(o_track* tr, double start_time, double end_time, doubl
   tr->clip_idx = next_clip; /* :450 */
 }
 
+/* ---- EXTENSION (parity unpinned w.r.t. whitebox): polyphase resampler ------------------------------------ */
+#define POLY_PHASES 128
+#define POLY_TAPS 16
+/* h[ph][k] = sinc(u) * blackman(u), u = (k - 7) - ph / 128, normalised to unit DC gain per phase; f64 -> f32. */
+static void design_polyphase(float* table) {
+  const double pi = 3.141592653589793238462643383279502884;
+  for (int ph = 0; ph < POLY_PHASES; ph++) {
+    double h[POLY_TAPS], sum = 0.0;
+    for (int k = 0; k < POLY_TAPS; k++) {
+      const double u = (double)(k - 7) - (double)ph / (double)POLY_PHASES;
+      const double sinc = u == 0.0 ? 1.0 : sin(pi * u) / (pi * u);
+      const double w = 0.42 + 0.5 * cos(pi * u / 8.0) + 0.08 * cos(2.0 * pi * u / 8.0);
+      h[k] = sinc * w;
+      sum += h[k];
+    }
+    for (int k = 0; k < POLY_TAPS; k++) table[ph * POLY_TAPS + k] = (float)(h[k] / sum);
+  }
+}
+
+void wbo_set_resampler(wbo_session* s, int mode) {
+  s->resampler = mode;
+  if (mode == 1) design_polyphase(s->poly);
+}
+
+/* Same position arithmetic as sample_linear (sampler.cpp:50-52); the fractional part picks a phase, the 16 taps sit
+ * on source frames ix - 7 .. ix + 8 (zero outside the sample), f32 fused multiply-adds in tap order. */
+static float sample_polyphase(const float* table, const float* src, size_t count, double x) {
+  const int64_t ix = (int64_t)x;
+  const double fd = x - (double)ix;
+  const int ph = (int)(fd * (double)POLY_PHASES);
+  const float* h = table + ph * POLY_TAPS;
+  float acc = 0.0f;
+  for (int k = 0; k < POLY_TAPS; k++) {
+    const int64_t i = ix - 7 + k;
+    const float v = (i >= 0 && i < (int64_t)(count + SAMPLE_PADDING)) ? src[i] : 0.0f;
+    acc = fmaf(h[k], v, acc);
+  }
+  return acc;
+}
+
 /* ---- sampler --------------------------------------------------------------------------------------- */
 
 static float clampf(float x, float lo, float hi) { /* math::clamp, core_math.h:34-38 */
@@ -485,6 +527,8 @@ static void sampler_reset(o_track* tr, double sample_offset, double speed, doubl
 }
 
 /* dsp::Sampler::stream (dsp/sampler.cpp:88-210) incl. sample_linear<T,Fmt> (dsp/sampler.cpp:34-59). */
+static const float* g_poly_table = NULL; /* non-NULL while a session in polyphase mode is rendering */
+
 static void sampler_stream(o_track* tr, o_sample* sm, uint32_t num_channels, uint32_t num_samples,
                            uint32_t buffer_offset, float gain, float** dst) {
   const float i16_norm = 1.0f / (float)INT16_MAX;              /* :95 */
@@ -534,6 +578,15 @@ static void sampler_stream(o_track* tr, o_sample* sm, uint32_t num_channels, uin
           for (uint32_t j = 0; j < n; j++) out[j] += d[off + j] * gain;
           break;
         }
+      }
+    }
+  } else if (g_poly_table && sm->fmt == WBO_FMT_F32 && sm->channels >= 2 && num_channels == 2) {
+    /* EXTENSION: polyphase quality mode (stereo f32 sources on a stereo bus) */
+    for (uint32_t i = 0; i < num_channels; i++) {
+      float* out = dst[i] + buffer_offset;
+      for (uint32_t j = 0; j < n; j++) {
+        const double x = tr->sample_offset + ((double)j * tr->playback_speed);
+        out[j] += sample_polyphase(g_poly_table, (const float*)sm->data[i], sm->count, x) * gain;
       }
     }
   } else { /* sample_linear, :34-59. The reference indexes src_channels[i] without `% channels`
@@ -840,6 +893,7 @@ static void track_process(wbo_session* s, o_track* tr, float** out, double sampl
 
 static void engine_process(wbo_session* s) {
   const uint32_t B = s->B, C = s->C;
+  g_poly_table = s->resampler == 1 ? s->poly : NULL;
   const double sample_rate = (double)s->rate;
   double buffer_duration = (double)B / sample_rate;
   double current_beat_duration = s->beat_duration;

@@ -75,6 +75,13 @@ int wbo_set_effects(wbo_session*, int track, const wbo_effects* fx); /* port onl
  * the chain was attached is 0 and the history persists across callbacks. */
 int wbo_set_impulse_response(wbo_session*, const float* h, uint32_t n_taps); /* port only */
 
+/* Resampler quality — EXTENSION, PARITY UNPINNED: the reference only has the 2-tap linear resampler
+ * (dsp/sampler.h:8-11; Track::process hard-codes ResamplerType::Linear, track.cpp:692-697). mode 1 selects the
+ * builder's polyphase windowed-sinc resampler (wb_oracle.c sample_polyphase: 128 phases x 16 taps, Blackman window,
+ * f32 fused multiply-add accumulation in tap order) for stereo f32 sources on a stereo bus at speed != 1; every
+ * other case keeps the reference's linear path. mode 0 (default) is the reference path. */
+void wbo_set_resampler(wbo_session*, int mode);
+
 void wbo_set_playhead(wbo_session*, double beat); /* Engine::set_playhead_position */
 void wbo_play(wbo_session*);                      /* Engine::play */
 void wbo_stop(wbo_session*);                      /* Engine::stop */

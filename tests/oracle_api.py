@@ -37,6 +37,7 @@ def _load(path):
     lib.wbo_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     lib.wbo_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
     lib.wbo_set_effects.argtypes = [vp, i32, vp]
+    lib.wbo_set_resampler.argtypes = [vp, i32]
     lib.wbo_set_impulse_response.argtypes = [vp, vp, u32]
     lib.wbo_set_playhead.argtypes = [vp, dbl]
     lib.wbo_play.argtypes = [vp]
@@ -129,6 +130,9 @@ class Session:
             return self.lib.wbo_set_impulse_response(self.h, None, 0)
         h = np.ascontiguousarray(h, np.float32)
         return self.lib.wbo_set_impulse_response(self.h, h.ctypes.data, h.size)
+
+    def set_resampler(self, mode):
+        self.lib.wbo_set_resampler(self.h, mode)
 
     def set_playhead(self, beat):
         self.lib.wbo_set_playhead(self.h, beat)

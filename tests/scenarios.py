@@ -301,6 +301,36 @@ def reverb(make_engine, fxp, taps=777):
     return _collect(eng, outs, n)
 
 
+def polyphase(make_engine, fxp=None):
+    """EXTENSION scenario (parity unpinned w.r.t. whitebox): BASELINE cfg 3 wording — 44.1 -> 48 kHz through the
+    polyphase windowed-sinc resampler — plus other ratios, clip starts at frame 0 (taps reach before the sample),
+    sample exhaustion (taps reach past the end), a fade on a resampled clip, mono / int16 sources (stay linear)."""
+    rng = np.random.RandomState(1212)
+    B, rate = 256, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    eng.set_resampler(1)
+    spb = rate * 0.5
+    cfgs = [  # (channels, src_rate, fmt, start_frame, speed, start_offset, frames, fade_in)
+        (2, 44100, FMT_F32, 0, 1.0, 0.0, 6000, 0.0),
+        (2, 44100, FMT_F32, 100, 1.0, 33.0, 6000, 200.0),
+        (2, 96000, FMT_F32, 0, 1.0, 0.0, 3000, 0.0),      # exhausts
+        (2, 48000, FMT_F32, 37, 0.5, 5.0, 4000, 0.0),
+        (2, 48000, FMT_F32, 0, 1.3, 0.0, 5000, 0.0),
+        (1, 44100, FMT_F32, 0, 1.0, 0.0, 6000, 0.0),      # mono: linear
+        (2, 44100, FMT_I16, 0, 1.0, 0.0, 6000, 0.0),      # int16: linear
+        (2, 48000, FMT_F32, 0, 1.0, 0.0, 6000, 0.0),      # unity: copy
+    ]
+    for t, (ch, sr, fmt, start, speed, off, frames, fi) in enumerate(cfgs):
+        eng.add_track(-2.0 - t, -0.6 + 0.2 * t, False)
+        sid = eng.add_sample(_src(rng, ch, frames, 6, fmt), sr, fmt)
+        eng.add_clip(t, sid, start / spb, 8.0, off, speed, 0.9, fi / spb, 0.0)
+    if fxp is not None:  # one resampled track through the effect path as well
+        eng.set_effects(1, fxp(threshold_db=-30.0, ratio_code=1))
+    eng.play()
+    outs = [eng.process(4), eng.process(5)]
+    return _collect(eng, outs, len(cfgs))
+
+
 def fuzz(make_engine, seed):
     """Random session: random rates / formats / speeds / clip layouts / block size, params changed mid-run."""
     rng = np.random.RandomState(1000 + seed)
@@ -353,7 +383,7 @@ def mip_source(fmt, frames, ch):
     return data
 
 
-EXT = dict(fades=fades, effects=effects, reverb=reverb)  # builder-specified extensions: checked against the C port only
+EXT = dict(fades=fades, effects=effects, reverb=reverb, polyphase=polyphase)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
            event_split=event_split, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)

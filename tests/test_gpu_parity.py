@@ -109,6 +109,14 @@ def test_fade_extension_vs_port(wb, batched):
 
 
 @pytest.mark.parametrize("batched", [True, False])
+def test_polyphase_extension_vs_port(wb, batched):
+    """EXTENSION, parity unpinned (BASELINE cfg 3 names a polyphase resampler; the reference only has the linear
+    one): CUDA == the C port's 128-phase x 16-tap specification bit for bit, incl. fades and the effect path."""
+    ref = sc.polyphase(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params)
+    assert_exact(sc.polyphase(gpu_engine(wb, batched), wb.effect_params), ref, "polyphase")
+
+
+@pytest.mark.parametrize("batched", [True, False])
 def test_effects_extension_vs_port(wb, batched):
     """EXTENSION, parity unpinned w.r.t. whitebox (BASELINE cfg 4: 4-band biquad EQ + compressor per track): CUDA ==
     the C port's specification bit for bit, including chain state carried across renders."""

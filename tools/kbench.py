@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--rate", type=int, default=48000, help="source sample rate (44100 -> linear resample)")
     ap.add_argument("--offset", type=int, default=0, help="clip start offset in frames (unaligned windows)")
     ap.add_argument("--tree", type=int, default=0)
+    ap.add_argument("--poly", type=int, default=0, help="1: polyphase quality mode (with --rate != 48000)")
     ap.add_argument("--fx", type=int, default=0, help="1: every track carries the 4-band EQ + compressor chain (cfg 4)")
     ap.add_argument("--reverb", type=int, default=0, help="taps of a convolution reverb on every track (cfg 5)")
     args = ap.parse_args()
@@ -36,7 +37,7 @@ def main():
     t0 = time.time()
     for t in range(N):
         sid = dev.sample_upload(np.roll(base, t * 17, axis=1), args.rate)
-        segs[t] = (t, 0, K, 0, B, sid, float(args.offset), speed, 0.5 + 0.001 * (t % 512), 0, 0.0, 0.0, 0.0, 0.0)
+        segs[t] = (t, 0, K, 0, B, sid, float(args.offset), speed, 0.5 + 0.001 * (t % 512), 2 if args.poly else 0, 0.0, 0.0, 0.0, 0.0)
     gains = np.full((N, 2), 0.7, np.float32)
     print("setup %.1fs, %.2f GiB" % (time.time() - t0, N * 2 * frames * 4 / 2**30), flush=True)
     stream = torch.cuda.Stream()

@@ -50,7 +50,7 @@ SEGMENT_DTYPE = np.dtype([("track", "<u4"), ("block", "<u4"), ("n_blocks", "<u4"
                           ("gain", "<f4"), ("flags", "<u4"), ("clip_frame", "<f8"), ("fade_in_frames", "<f8"),
                           ("fade_out_frames", "<f8"), ("clip_len_frames", "<f8")])
 assert SEGMENT_DTYPE.itemsize == C.sizeof(Segment) == 80
-SEG_FADE = 1
+SEG_FADE, SEG_POLYPHASE = 1, 2
 
 # every symbol include/wbx.h and include/wbx_host.h declare
 WBX_SYMBOLS = [
@@ -63,7 +63,7 @@ WBX_SYMBOLS = [
 WBXH_SYMBOLS = [
     "wbxh_create", "wbxh_destroy", "wbxh_last_error", "wbxh_device", "wbxh_add_track", "wbxh_set_volume",
     "wbxh_set_pan", "wbxh_set_mute", "wbxh_add_sample", "wbxh_add_clip", "wbxh_add_clip_fade", "wbxh_set_playhead",
-    "wbxh_play", "wbxh_set_effects", "wbxh_set_impulse_response",
+    "wbxh_play", "wbxh_set_effects", "wbxh_set_impulse_response", "wbxh_set_resampler",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
 ]
@@ -136,6 +136,8 @@ def lib():
     L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     L.wbxh_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
     L.wbxh_set_effects.argtypes = [vp, i32, vp]
+    L.wbxh_set_resampler.argtypes = [vp, i32]
+    L.wbxh_set_resampler.restype = None
     L.wbxh_set_impulse_response.argtypes = [vp, vp, u32]
     L.wbx_set_impulse_response.argtypes = [vp, vp, u32]
     L.wbxh_set_playhead.argtypes = [vp, dbl]
@@ -421,6 +423,10 @@ class Engine:
             return self._ck(self.L.wbxh_set_impulse_response(self.h, None, 0))
         h = np.ascontiguousarray(h, np.float32)
         return self._ck(self.L.wbxh_set_impulse_response(self.h, h.ctypes.data, h.size))
+
+    def set_resampler(self, mode):
+        """0 = linear (the reference's only resampler), 1 = polyphase windowed sinc (extension)."""
+        self.L.wbxh_set_resampler(self.h, mode)
 
     def set_playhead(self, beat):
         self.L.wbxh_set_playhead(self.h, beat)

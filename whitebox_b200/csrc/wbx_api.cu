@@ -28,7 +28,8 @@ cudaError_t launch_mipmap(const void* base, uint32_t fmt, uint32_t nch, uint64_t
                           uint64_t mdc, int high, void* out, cudaStream_t stream);
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
-                           float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, cudaStream_t stream);
+                           float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, const float* poly,
+                           cudaStream_t stream);
 size_t fir_tc_tiles_bytes(uint32_t L);
 uint64_t fir_tc_plane_width(uint64_t H, uint64_t T);
 cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, cudaStream_t stream);
@@ -38,8 +39,11 @@ using namespace wbx;
 
 namespace {
 
+constexpr size_t kSampleHeadBytes = 256;  // zero bytes in front of frame 0 (polyphase taps reach 7 frames back)
+
 struct SampleRec {
-  void* d_base = nullptr;   // frame-interleaved, nch channels
+  void* d_alloc = nullptr;  // the allocation: kSampleHeadBytes of zeros, then the frames
+  void* d_base = nullptr;   // frame 0: frame-interleaved, nch channels
   uint32_t channels = 0;    // channels of the Sample as uploaded
   uint32_t nch = 0;         // channels kept on the device: min(channels, 2)
   uint32_t rate = 0, fmt = 0, esize = 0;
@@ -66,7 +70,7 @@ struct wbx_engine {
   uint32_t C = 2, B = 512, rate = 48000, n_tracks = 0;
   int sum_mode = WBX_SUM_AUTO;
   std::vector<SampleRec> samples;
-  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels, d_fx, d_trackbuf, d_ir, d_firhist, d_firin, d_irtiles, d_firplanes;
+  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels, d_fx, d_trackbuf, d_ir, d_firhist, d_firin, d_irtiles, d_firplanes, d_poly;
   HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv, h_levels, h_fx;
   std::vector<uint32_t> slot_busy;  // [track][slot] -> first free block
   uint32_t slot_cap = 0;
@@ -210,6 +214,30 @@ int wbx_create(wbx_engine** out, int device_ordinal) {
     return WBX_ERR_CUDA;
   }
   e->stream = e->own_stream;
+  // polyphase coefficient table (extension, include/wbx.h): h[ph][k] = sinc(u) * blackman(u), u = (k - 7) - ph / 128,
+  // unit DC gain per phase, designed in f64 (same formulas as oracle/wb_oracle.c design_polyphase)
+  {
+    std::vector<float> table(128 * 16);
+    const double pi = 3.141592653589793238462643383279502884;
+    for (int ph = 0; ph < 128; ph++) {
+      double h[16], sum = 0.0;
+      for (int k = 0; k < 16; k++) {
+        const double u = (double)(k - 7) - (double)ph / 128.0;
+        const double sinc = u == 0.0 ? 1.0 : std::sin(pi * u) / (pi * u);
+        const double w = 0.42 + 0.5 * std::cos(pi * u / 8.0) + 0.08 * std::cos(2.0 * pi * u / 8.0);
+        h[k] = sinc * w;
+        sum += h[k];
+      }
+      for (int k = 0; k < 16; k++) table[ph * 16 + k] = (float)(h[k] / sum);
+    }
+    if (cudaMalloc(&e->d_poly.p, table.size() * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(e->d_poly.p, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaStreamDestroy(e->own_stream);
+      delete e;
+      return WBX_ERR_CUDA;
+    }
+    e->d_poly.cap = table.size() * sizeof(float);
+  }
   *out = e;
   return WBX_OK;
 }
@@ -219,9 +247,9 @@ int wbx_destroy(wbx_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (auto& s : e->samples)
-    if (s.live) cudaFree(s.d_base);
+    if (s.live) cudaFree(s.d_alloc);
   for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv,
-                    &e->d_upload, &e->d_levels, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin, &e->d_irtiles, &e->d_firplanes})
+                    &e->d_upload, &e->d_levels, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin, &e->d_irtiles, &e->d_firplanes, &e->d_poly})
     if (b->p) cudaFree(b->p);
   for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
     if (b->p) cudaFreeHost(b->p);
@@ -290,9 +318,10 @@ int wbx_sample_upload(wbx_engine* e, int format, uint32_t channels, uint64_t fra
   const size_t plane_bytes = (((size_t)frames * es) + 255) & ~(size_t)255;
   int rc = dev_reserve(e, e->d_upload, plane_bytes * r.nch);
   if (rc) return rc;
-  cudaError_t err = cudaMalloc(&r.d_base, bytes);
+  cudaError_t err = cudaMalloc(&r.d_alloc, bytes + kSampleHeadBytes);
   if (err != cudaSuccess) return fail(e, WBX_ERR_NOMEM, "cudaMalloc(%zu) for sample failed", bytes);
-  CU(e, cudaMemsetAsync(r.d_base, 0, bytes, e->stream));
+  r.d_base = (uint8_t*)r.d_alloc + kSampleHeadBytes;
+  CU(e, cudaMemsetAsync(r.d_alloc, 0, bytes + kSampleHeadBytes, e->stream));
   for (uint32_t c = 0; c < r.nch; c++)
     CU(e, cudaMemcpyAsync((uint8_t*)e->d_upload.p + c * plane_bytes, planar[c], (size_t)frames * es,
                           cudaMemcpyHostToDevice, e->stream));
@@ -376,7 +405,7 @@ int wbx_sample_release(wbx_engine* e, uint32_t id) {
   if (!e || id >= e->samples.size() || !e->samples[id].live) return fail(e, WBX_ERR_INVALID, "bad sample id");
   CU(e, cudaSetDevice(e->device));
   CU(e, cudaStreamSynchronize(e->stream));
-  CU(e, cudaFree(e->samples[id].d_base));
+  CU(e, cudaFree(e->samples[id].d_alloc));
   e->samples[id] = SampleRec();
   return WBX_OK;
 }
@@ -580,7 +609,8 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
       return fail(e, WBX_ERR_INVALID, "segment %u: unknown sample %u", i, sg.sample_id);
     if (!(sg.speed > 0.0) || !(sg.src_pos >= 0.0) || !(sg.speed < 1e6))
       return fail(e, WBX_ERR_INVALID, "segment %u: speed/src_pos must be positive and finite", i);
-    if (sg.flags & ~WBX_SEG_FADE) return fail(e, WBX_ERR_INVALID, "segment %u: unknown flags 0x%x", i, sg.flags);
+    if (sg.flags & ~(WBX_SEG_FADE | WBX_SEG_POLYPHASE))
+      return fail(e, WBX_ERR_INVALID, "segment %u: unknown flags 0x%x", i, sg.flags);
     if ((sg.flags & WBX_SEG_FADE) && !(sg.clip_frame >= 0.0 && sg.clip_frame < 9.0e15 && sg.clip_len_frames >= 0.0))
       return fail(e, WBX_ERR_INVALID, "segment %u: bad fade parameters", i);
     const SampleRec& sm = e->samples[sg.sample_id];
@@ -613,11 +643,12 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     d.fmt = sm.fmt;
     d.slot = slot;
     d.nch = sm.nch;
-    d.fade = (sg.flags & WBX_SEG_FADE) ? 1u : 0u;
-    d.clip_frame = d.fade ? sg.clip_frame : 0.0;
-    d.fade_in = d.fade ? sg.fade_in_frames : 0.0;
-    d.fade_out = d.fade ? sg.fade_out_frames : 0.0;
-    d.clip_len = d.fade ? sg.clip_len_frames : 0.0;
+    const bool fade = (sg.flags & WBX_SEG_FADE) != 0;
+    d.fade = sg.flags & (WBX_SEG_FADE | WBX_SEG_POLYPHASE);
+    d.clip_frame = fade ? sg.clip_frame : 0.0;
+    d.fade_in = fade ? sg.fade_in_frames : 0.0;
+    d.fade_out = fade ? sg.fade_out_frames : 0.0;
+    d.clip_len = fade ? sg.clip_len_frames : 0.0;
   }
   if (N) memcpy(e->h_gains.p, track_gains, (size_t)N * 2 * sizeof(float));
 
@@ -679,7 +710,7 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     CU(e, launch_effects((const DSpan*)e->d_spans.p, (DCell*)e->d_cells.p, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
                          n_segs, (float*)e->d_trackbuf.p, rv ? (const float*)e->d_ir.p : nullptr, rv ? e->ir_taps : 0,
                          (float*)e->d_firhist.p, (float*)e->d_firin.p, tc ? e->d_irtiles.p : nullptr,
-                         tc ? e->d_firplanes.p : nullptr, e->stream));
+                         tc ? e->d_firplanes.p : nullptr, (const float*)e->d_poly.p, e->stream));
     e->launches += rv ? (tc ? 7 : 6) : 3;
   }
   e->n_blocks = n_blocks;
@@ -722,6 +753,7 @@ int wbx_mix(wbx_engine* e, uint32_t flags) {
   p.spans = (const DSpan*)e->d_spans.p;
   p.cells = (const DCell*)e->d_cells.p;
   p.gains = (const float*)e->d_gains.p;
+  p.poly = (const float*)e->d_poly.p;
   p.bus = (float*)e->d_bus.p;
   p.peaks = (float*)e->d_peaks.p;
   p.ws = (float*)e->d_ws.p;

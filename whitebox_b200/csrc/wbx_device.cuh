@@ -34,7 +34,7 @@ struct __align__(16) DSpan {
   uint32_t fmt;   // wbx_format
   uint32_t slot;  // which of the `slots` cells of (block, track) this span writes
   uint32_t nch;   // channels stored on the device (1 or 2)
-  uint32_t fade;  // WBX_SEG_FADE: the envelope fields below apply
+  uint32_t fade;  // segment flags: bit 0 WBX_SEG_FADE (the envelope fields below apply), bit 1 WBX_SEG_POLYPHASE
   double clip_frame, fade_in, fade_out, clip_len;  // fade extension (include/wbx.h), in output frames
 };
 static_assert(sizeof(DSpan) == 112, "DSpan layout");
@@ -55,7 +55,8 @@ enum : uint32_t {
   K_UNI = 4,     // stereo f32, unity speed, odd start frame or partial tile: 64-bit loads + packed math
   K_LIN = 5,     // stereo f32, 2-tap linear resample from the staged window, conversion-free position split
   K_FADE = 6,        // a fade ramp overlaps this tile: per-frame path times the envelope (staged window)
-  K_DIRECT_FADE = 7  // K_DIRECT with a fade ramp
+  K_DIRECT_FADE = 7, // K_DIRECT with a fade ramp
+  K_POLY = 8         // stereo f32, polyphase windowed-sinc resample (extension) from the staged window
 };
 
 // Resolved per-(cell, tile) descriptor, lives in shared memory (64 B).
@@ -71,7 +72,7 @@ struct __align__(16) Desc {
   uint16_t lo, hi; // tile-relative frame range [lo, hi) this item covers
   uint16_t bytes;  // bytes to stage (multiple of 16)
   uint8_t kind;
-  uint8_t fmt;     // wbx_format | 0x80 when the device copy has one channel (both outputs read it)
+  uint8_t fmt;     // wbx_format | 0x80 when the device copy has one channel | 0x40 polyphase quality mode
   uint32_t span;   // span index (K_FADE reads the envelope parameters from it)
   uint32_t block_in_run;  // callbacks since the run's first one (clip_frame advances by length per callback)
 };
@@ -92,6 +93,7 @@ struct MixParams {
   const DSpan* spans;
   const DCell* cells;
   const float* gains;   // [n_tracks][2]
+  const float* poly;    // polyphase coefficient table [128][16] (extension)
   float* bus;           // [C][n_blocks*B]
   float* peaks;         // [n_blocks][n_tracks][2], pre-zeroed
   float* ws;            // tree mode: [tiles][groups][2][T] partial sums

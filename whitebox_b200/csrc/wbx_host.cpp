@@ -300,10 +300,10 @@ void Engine::process_event(Track& t, double start_time, double end_time, double 
 
 // Fade extension (include/wbx.h): ramp lengths of the clip in output frames.
 void Engine::fill_fade(wbx_segment& s, const AudioClip* clip, uint64_t clip_frame) const {
-  s.flags = 0;
+  s.flags = (resampler_mode == 1 && s.speed != 1.0) ? WBX_SEG_POLYPHASE : 0u;
   s.clip_frame = s.fade_in_frames = s.fade_out_frames = s.clip_len_frames = 0.0;
   if (clip->fade_start > 0.0 || clip->fade_end > 0.0) {
-    s.flags = WBX_SEG_FADE;
+    s.flags |= WBX_SEG_FADE;
     s.clip_frame = (double)clip_frame;
     s.fade_in_frames = beat_to_samples(clip->fade_start, cur_sample_rate_, beat_duration_);
     s.fade_out_frames = beat_to_samples(clip->fade_end, cur_sample_rate_, beat_duration_);
@@ -645,6 +645,7 @@ int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params)
 int wbxh_set_impulse_response(wbxh_engine* h, const float* ir, uint32_t n_taps) {
   return h->eng.set_impulse_response(ir, n_taps);
 }
+void wbxh_set_resampler(wbxh_engine* h, int mode) { h->eng.resampler_mode = mode; }
 void wbxh_set_playhead(wbxh_engine* h, double beat) { h->eng.set_playhead_position(beat); }
 void wbxh_play(wbxh_engine* h) { h->eng.play(); }
 void wbxh_stop(wbxh_engine* h) { h->eng.stop(); }

@@ -191,6 +191,30 @@ __device__ __forceinline__ void accumulate(float s, float gain, float tg, float&
 
 // Generic per-frame path: any format, unity or linear, staged window (shared) or direct (global) rows.
 // `row` points at window frame 0 (frame-interleaved, NCH channels); d.base is that frame's sample index.
+// Polyphase extension (include/wbx.h): 16 taps of phase floor(frac * 128) on source frames ix - 7 .. ix + 8, f32 fused
+// multiply-adds in tap order (oracle/wb_oracle.c sample_polyphase). `row` addresses frame 0 of a frame-interleaved
+// stereo f32 buffer; frames before the sample and after its end read the zero padding of the device layout.
+__device__ __forceinline__ float2 poly_frame(const float* __restrict__ table, const float2* row, int64_t ix, double fd) {
+  const int ph = __double2int_rz(__dmul_rn(fd, 128.0));
+  const float4* h4 = reinterpret_cast<const float4*>(table + ph * 16);
+  float2 acc = make_float2(0.0f, 0.0f);
+  const float2* p = row + (ix - 7);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const float4 h = __ldg(h4 + q);
+    const float2 s0 = p[4 * q + 0], s1 = p[4 * q + 1], s2 = p[4 * q + 2], s3 = p[4 * q + 3];
+    acc.x = __fmaf_rn(h.x, s0.x, acc.x);
+    acc.y = __fmaf_rn(h.x, s0.y, acc.y);
+    acc.x = __fmaf_rn(h.y, s1.x, acc.x);
+    acc.y = __fmaf_rn(h.y, s1.y, acc.y);
+    acc.x = __fmaf_rn(h.z, s2.x, acc.x);
+    acc.y = __fmaf_rn(h.z, s2.y, acc.y);
+    acc.x = __fmaf_rn(h.w, s3.x, acc.x);
+    acc.y = __fmaf_rn(h.w, s3.y, acc.y);
+  }
+  return acc;
+}
+
 // Fade extension (include/wbx.h): envelope of clip-relative output frame n.
 struct FadeEnv {
   double n0;  // clip frame of segment-relative frame 0
@@ -214,10 +238,11 @@ struct FadeEnv {
 
 template <int FPL, bool UNITY, bool FADE>
 __device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
-                                              float& pkR, int lane, bool two, const FadeEnv& fe) {
+                                              float& pkR, int lane, bool two, const FadeEnv& fe, const float* poly) {
   const int64_t ip = (int64_t)(uint32_t)(int64_t)d.pos;  // (uint32_t)sample_offset_, sampler.cpp:107
-  const uint32_t FMT = d.fmt & 0x7fu;
+  const uint32_t FMT = d.fmt & 0x3fu;
   const int NCH = (d.fmt & 0x80u) ? 1 : 2;
+  const bool use_poly = !UNITY && (d.fmt & 0x40u) && poly != nullptr;  // resolve only sets 0x40 for stereo f32 -> stereo
 #pragma unroll
   for (int i = 0; i < FPL / 2; i++) {
 #pragma unroll
@@ -235,6 +260,12 @@ __device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, fl
           const int64_t ix = __double2ll_rz(x);                                // :51
           const float fx = __double2float_rn(__dsub_rn(x, __ll2double_rn(ix)));  // :52
           const int64_t idx = (ix - d.base) * NCH;
+          if (use_poly) {
+            const float2 pv = poly_frame(poly, reinterpret_cast<const float2*>(row) - d.base, ix,
+                                         __dsub_rn(x, __ll2double_rn(ix)));
+            sL = pv.x;
+            sR = pv.y;
+          } else {
           const float a = load_lin_rt(FMT, row, idx), b = load_lin_rt(FMT, row, idx + NCH);
           sL = __fadd_rn(a, __fmul_rn(fx, __fsub_rn(b, a)));  // :55
           if (two) {
@@ -244,6 +275,7 @@ __device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, fl
             } else {
               sR = sL;
             }
+          }
           }
         }
         if (FADE) {  // (src * gain) * env, then the track gain as usual
@@ -269,16 +301,16 @@ __device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, fl
 
 template <int FPL, bool FADE>
 __device__ __forceinline__ void consume_gen_f(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
-                                              float& pkR, int lane, bool two, const FadeEnv& fe) {
+                                              float& pkR, int lane, bool two, const FadeEnv& fe, const float* poly) {
   if (d.speed == 1.0)  // playback_speed_ == 1.0, sampler.cpp:106
-    consume_gen_t<FPL, true, FADE>(d, row, acc, pkL, pkR, lane, two, fe);
+    consume_gen_t<FPL, true, FADE>(d, row, acc, pkL, pkR, lane, two, fe, poly);
   else
-    consume_gen_t<FPL, false, FADE>(d, row, acc, pkL, pkR, lane, two, fe);
+    consume_gen_t<FPL, false, FADE>(d, row, acc, pkL, pkR, lane, two, fe, poly);
 }
 
 template <int FPL>
 __device__ __forceinline__ void consume_gen(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
-                                            float& pkR, int lane, bool two, const DSpan* spans) {
+                                            float& pkR, int lane, bool two, const DSpan* spans, const float* poly) {
   FadeEnv fe;
   fe.n0 = 0.0;
   fe.fin = 0.0;
@@ -291,9 +323,9 @@ __device__ __forceinline__ void consume_gen(const Desc& d, const void* row, floa
     fe.len = __ldg(&sp->clip_len);
     // clip frame of segment-relative frame 0 in this callback (exact: integers)
     fe.n0 = __ldg(&sp->clip_frame) + (double)d.block_in_run * (double)__ldg(&sp->length);
-    consume_gen_f<FPL, true>(d, row, acc, pkL, pkR, lane, two, fe);
+    consume_gen_f<FPL, true>(d, row, acc, pkL, pkR, lane, two, fe, poly);
   } else {
-    consume_gen_f<FPL, false>(d, row, acc, pkL, pkR, lane, two, fe);
+    consume_gen_f<FPL, false>(d, row, acc, pkL, pkR, lane, two, fe, poly);
   }
 }
 
@@ -410,6 +442,36 @@ __device__ __forceinline__ void consume_lin(const Desc& d, const uint8_t* row, f
     consume_lin_t<FPL, false>(d, row, acc, pkL, pkR, lane);
 }
 
+// Stereo f32, polyphase windowed-sinc resample (extension) from the staged window: the lin path's position split,
+// then 16 taps per frame.
+template <int FPL>
+__device__ __forceinline__ void consume_poly(const Desc& d, const uint8_t* row, const float* __restrict__ poly,
+                                             float2 (&acc)[FPL], float& pkL, float& pkR, int lane) {
+  const float2* rb = reinterpret_cast<const float2*>(row) - d.base;
+  const int lo = d.lo, hi = d.hi;
+  const double pos = d.pos, speed = d.speed;
+  const double M = 4503599627370496.0;  // 2^52
+  const double jj0 = (double)(d.jrel0 + 2 * lane);
+  const float2 g2 = make_float2(d.gain, d.gain);
+  const float2 t2 = make_float2(d.tg[0], d.tg[1]);
+#pragma unroll
+  for (int i = 0; i < FPL / 2; i++) {
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int fr = 2 * (lane + 32 * i) + e;
+      if (fr >= lo && fr < hi) {
+        const double jj = __dadd_rn(jj0, (double)(64 * i + e));
+        const double x = __dadd_rn(pos, __dmul_rn(jj, speed));
+        const double t = __dadd_rd(x, M);  // floor(x) + 2^52 (x >= 0)
+        const int ix = __double2loint(t);
+        const double fd = __dsub_rn(x, __dsub_rn(t, M));
+        const float2 sv = poly_frame(poly, rb, (int64_t)ix, fd);
+        accumulate2(sv, g2, t2, acc[i * 2 + e], pkL, pkR);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the mix kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -486,23 +548,26 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
       const int fbytes = (int)s.nch * ((s.fmt == F_I16) ? 2 : 4);  // bytes per frame on the device
       const int64_t jj_lo = lo + d.jrel0, jj_hi = hi - 1 + d.jrel0;
       const bool unity = (s.speed == 1.0);
+      // polyphase quality mode applies to stereo f32 sources on a stereo bus at speed != 1 (include/wbx.h)
+      const bool poly = !unity && (s.fade & 2u) && two && s.fmt == F_F32 && s.nch == 2;
+      if (poly) d.fmt |= 0x40u;
       int64_t first, last;  // first / last source frame the item can touch
       if (unity) {
         const int64_t ip = (int64_t)(uint32_t)(int64_t)c.pos;
         first = ip + jj_lo;
         last = ip + jj_hi;
-      } else {  // conservative superset of [floor(x_lo), floor(x_hi) + 1]
-        first = (int64_t)(c.pos + (double)jj_lo * s.speed) - 1;
-        last = (int64_t)(c.pos + (double)jj_hi * s.speed) + 2;
+      } else {  // conservative superset of [floor(x_lo), floor(x_hi) + 1] (+ the 16-tap reach in polyphase mode)
+        first = (int64_t)(c.pos + (double)jj_lo * s.speed) - (poly ? 8 : 1);
+        last = (int64_t)(c.pos + (double)jj_hi * s.speed) + (poly ? 9 : 2);
       }
-      if (first < 0) first = 0;
+      if (first < 0 && !poly) first = 0;  // polyphase taps may reach into the zero frames before the sample
       const int64_t align = 16 / fbytes;  // frames per 16 bytes: 2 (stereo f32), 4 (mono f32 / stereo i16), 8
       const int64_t a = first & ~(align - 1);
       const int64_t end = (last + align) & ~(align - 1);
       const int64_t bytes = (end - a) * fbytes;
       // fade extension: does a ramp overlap the frames of this item?
       bool fading = false;
-      if (s.fade) {
+      if (s.fade & 1u) {
         const double n_lo = s.clip_frame + (double)d.block_in_run * (double)s.length + (double)jj_lo;
         const double n_hi = s.clip_frame + (double)d.block_in_run * (double)s.length + (double)jj_hi;
         fading = (s.fade_in > 0.0 && n_lo < s.fade_in) || (s.fade_out > 0.0 && s.clip_len - n_hi < s.fade_out);
@@ -514,6 +579,8 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
         const bool st32 = two && s.fmt == F_F32 && s.nch == 2;  // stereo f32 source into a stereo bus
         if (fading)
           d.kind = K_FADE;
+        else if (poly)
+          d.kind = K_POLY;
         else if (st32 && unity)
           d.kind = (lo == 0 && hi == T && first == a) ? K_FAST : K_UNI;
         else if (st32 && last < (int64_t)0x3fffffff)
@@ -652,9 +719,11 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
             consume_uni<FPL>(*dp, row, acc, pkL, pkR, lane);
           } else if (kind == K_LIN) {
             consume_lin<FPL>(*dp, row, acc, pkL, pkR, lane);
+          } else if (kind == K_POLY) {
+            consume_poly<FPL>(*dp, row, p.poly, acc, pkL, pkR, lane);
           } else {
             const Desc d = *dp;
-            consume_gen<FPL>(d, staged ? (const void*)row : d.src, acc, pkL, pkR, lane, two, p.spans);
+            consume_gen<FPL>(d, staged ? (const void*)row : d.src, acc, pkL, pkR, lane, two, p.spans, p.poly);
           }
           if (staged) {
             __syncwarp();  // every lane is done reading the stage before lane 0 may refill it
@@ -777,7 +846,7 @@ __global__ void interleave_sample_kernel(const uint8_t* __restrict__ planar, siz
 
 // value one Sampler::stream call adds at segment-relative frame jj for output channel c (generic, from global)
 __device__ __forceinline__ float stream_value(const DSpan& sp, const DCell& cell, int32_t jj, uint32_t c,
-                                              uint32_t block_in_run) {
+                                              uint32_t block_in_run, const float* poly, bool two) {
   const uint32_t nch = sp.nch;
   const uint32_t ch = c % nch;
   float sv;
@@ -787,12 +856,17 @@ __device__ __forceinline__ float stream_value(const DSpan& sp, const DCell& cell
   } else {
     const double x = __dadd_rn(cell.pos, __dmul_rn((double)jj, sp.speed));
     const int64_t ix = __double2ll_rz(x);
-    const float fx = __double2float_rn(__dsub_rn(x, __ll2double_rn(ix)));
-    const float a = load_lin_rt(sp.fmt, sp.base, ix * nch + ch), b = load_lin_rt(sp.fmt, sp.base, (ix + 1) * nch + ch);
-    sv = __fadd_rn(a, __fmul_rn(fx, __fsub_rn(b, a)));
+    if ((sp.fade & 2u) && two && sp.fmt == F_F32 && nch == 2 && poly) {
+      const float2 pv = poly_frame(poly, reinterpret_cast<const float2*>(sp.base), ix, __dsub_rn(x, __ll2double_rn(ix)));
+      sv = c ? pv.y : pv.x;
+    } else {
+      const float fx = __double2float_rn(__dsub_rn(x, __ll2double_rn(ix)));
+      const float a = load_lin_rt(sp.fmt, sp.base, ix * nch + ch), b = load_lin_rt(sp.fmt, sp.base, (ix + 1) * nch + ch);
+      sv = __fadd_rn(a, __fmul_rn(fx, __fsub_rn(b, a)));
+    }
   }
   float m = __fmul_rn(sv, sp.gain);
-  if (sp.fade) {
+  if (sp.fade & 1u) {
     FadeEnv fe;
     fe.n0 = sp.clip_frame + (double)block_in_run * (double)sp.length;
     fe.fin = sp.fade_in;
@@ -806,7 +880,7 @@ __device__ __forceinline__ float stream_value(const DSpan& sp, const DCell& cell
 // one warp per (effect track e, callback k): the track's mixing buffer before effects, frame-interleaved stereo
 __global__ void render_tracks_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells,
                                      const DFx* __restrict__ fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
-                                     uint32_t B, uint32_t C, float* __restrict__ trackbuf) {
+                                     uint32_t B, uint32_t C, const float* __restrict__ poly, float* __restrict__ trackbuf) {
   const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (w >= (uint64_t)n_fx * K) return;
@@ -821,8 +895,8 @@ __global__ void render_tracks_kernel(const DSpan* __restrict__ spans, const DCel
       const DSpan sp = spans[cell.span];
       if (j >= sp.dst_off && j < sp.dst_off + cell.n_act) {
         const int32_t jj = (int32_t)(j - sp.dst_off);
-        v.x = __fadd_rn(v.x, stream_value(sp, cell, jj, 0, k - sp.block0));  // dst += ... on a cleared buffer
-        if (C == 2) v.y = __fadd_rn(v.y, stream_value(sp, cell, jj, 1, k - sp.block0));
+        v.x = __fadd_rn(v.x, stream_value(sp, cell, jj, 0, k - sp.block0, poly, C == 2));  // dst += ... on a cleared buffer
+        if (C == 2) v.y = __fadd_rn(v.y, stream_value(sp, cell, jj, 1, k - sp.block0, poly, true));
       }
     }
     out[j] = v;
@@ -1240,10 +1314,11 @@ cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, 
 
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
-                           float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, cudaStream_t stream) {
+                           float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, const float* poly,
+                           cudaStream_t stream) {
   if (n_fx == 0) return cudaSuccess;
   const uint64_t warps = (uint64_t)n_fx * K;
-  render_tracks_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, trackbuf);
+  render_tracks_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf);
   effects_kernel<<<(n_fx * C + 31) / 32, 32, 0, stream>>>(fx, n_fx, C, (uint64_t)K * B, trackbuf);
   if (L && ir && fir_hist && fir_in) {  // convolution reverb as the chain's last stage
     const uint64_t T = (uint64_t)K * B, H = L - 1;
