@@ -77,6 +77,7 @@ struct wbx_engine {
   // last submit
   uint32_t n_blocks = 0, n_spans = 0, slots = 1;
   bool submitted = false, mixed = false;
+  uint32_t seg_flags = 0;  // OR of the submitted segments' flags
   uint64_t launches = 0;
   uint32_t upload_flip = 0;
   // effect chains (extension): host copy of the designed coefficients per track, device array with state
@@ -594,6 +595,7 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   if ((rc = host_reserve(e, e->h_gains, (size_t)(N ? N : 1) * 2 * sizeof(float)))) return rc;
   DSpan* hs = (DSpan*)e->h_spans.p;
   uint32_t slots = 1;
+  uint32_t seg_flags = 0;
   if (e->slot_cap == 0) e->slot_cap = 2;
   if (e->slot_busy.size() < (size_t)N * e->slot_cap) e->slot_busy.resize((size_t)N * e->slot_cap);
   std::fill(e->slot_busy.begin(), e->slot_busy.end(), 0u);
@@ -643,6 +645,7 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     d.fmt = sm.fmt;
     d.slot = slot;
     d.nch = sm.nch;
+    seg_flags |= sg.flags;
     const bool fade = (sg.flags & WBX_SEG_FADE) != 0;
     d.fade = sg.flags & (WBX_SEG_FADE | WBX_SEG_POLYPHASE);
     d.clip_frame = fade ? sg.clip_frame : 0.0;
@@ -716,6 +719,7 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   e->n_blocks = n_blocks;
   e->n_spans = n_segs;
   e->slots = slots;
+  e->seg_flags = seg_flags;
   e->submitted = true;
   e->mixed = false;
   return WBX_OK;
@@ -768,6 +772,7 @@ int wbx_mix(wbx_engine* e, uint32_t flags) {
   p.tracks_per_group = tpg;
   p.n_items = K * n_tiles * groups;
   p.clamp = (flags & WBX_MIX_NO_CLAMP) ? 0u : 1u;
+  p.ext = e->seg_flags ? 1u : 0u;
   int ctas = 0;
   CU(e, launch_mix(p, fpl, e->n_sm, e->stream, &ctas));
   e->launches++;

@@ -105,6 +105,7 @@ struct MixParams {
   uint32_t tracks_per_group;
   uint32_t n_items;     // n_blocks * n_tiles * groups
   uint32_t clamp;       // apply the [-1, 1] clamp
+  uint32_t ext;         // some segment carries an extension flag (fade / polyphase): use the full kernel build
 };
 
 }  // namespace wbx

@@ -236,13 +236,13 @@ struct FadeEnv {
   }
 };
 
-template <int FPL, bool UNITY, bool FADE>
+template <int FPL, bool UNITY, bool FADE, bool POLY>
 __device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
                                               float& pkR, int lane, bool two, const FadeEnv& fe, const float* poly) {
   const int64_t ip = (int64_t)(uint32_t)(int64_t)d.pos;  // (uint32_t)sample_offset_, sampler.cpp:107
   const uint32_t FMT = d.fmt & 0x3fu;
   const int NCH = (d.fmt & 0x80u) ? 1 : 2;
-  const bool use_poly = !UNITY && (d.fmt & 0x40u) && poly != nullptr;  // resolve only sets 0x40 for stereo f32 -> stereo
+  const bool use_poly = POLY && !UNITY && (d.fmt & 0x40u) && poly != nullptr;  // 0x40: stereo f32 -> stereo bus only
 #pragma unroll
   for (int i = 0; i < FPL / 2; i++) {
 #pragma unroll
@@ -299,16 +299,18 @@ __device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, fl
   }
 }
 
-template <int FPL, bool FADE>
+template <int FPL, bool FADE, bool POLY>
 __device__ __forceinline__ void consume_gen_f(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
                                               float& pkR, int lane, bool two, const FadeEnv& fe, const float* poly) {
   if (d.speed == 1.0)  // playback_speed_ == 1.0, sampler.cpp:106
-    consume_gen_t<FPL, true, FADE>(d, row, acc, pkL, pkR, lane, two, fe, poly);
+    consume_gen_t<FPL, true, FADE, false>(d, row, acc, pkL, pkR, lane, two, fe, poly);
   else
-    consume_gen_t<FPL, false, FADE>(d, row, acc, pkL, pkR, lane, two, fe, poly);
+    consume_gen_t<FPL, false, FADE, POLY>(d, row, acc, pkL, pkR, lane, two, fe, poly);
 }
 
-template <int FPL>
+// EXT == false is the lean build used when no segment of the render carries an extension flag (fade, polyphase):
+// the rarely used paths then cost neither registers nor instruction-cache space on the reference-parity path.
+template <int FPL, bool EXT>
 __device__ __forceinline__ void consume_gen(const Desc& d, const void* row, float2 (&acc)[FPL], float& pkL,
                                             float& pkR, int lane, bool two, const DSpan* spans, const float* poly) {
   FadeEnv fe;
@@ -316,16 +318,16 @@ __device__ __forceinline__ void consume_gen(const Desc& d, const void* row, floa
   fe.fin = 0.0;
   fe.fout = 0.0;
   fe.len = 0.0;
-  if (d.kind == K_FADE || d.kind == K_DIRECT_FADE) {
+  if (EXT && (d.kind == K_FADE || d.kind == K_DIRECT_FADE)) {
     const DSpan* sp = spans + d.span;
     fe.fin = __ldg(&sp->fade_in);
     fe.fout = __ldg(&sp->fade_out);
     fe.len = __ldg(&sp->clip_len);
     // clip frame of segment-relative frame 0 in this callback (exact: integers)
     fe.n0 = __ldg(&sp->clip_frame) + (double)d.block_in_run * (double)__ldg(&sp->length);
-    consume_gen_f<FPL, true>(d, row, acc, pkL, pkR, lane, two, fe, poly);
+    consume_gen_f<FPL, true, EXT>(d, row, acc, pkL, pkR, lane, two, fe, poly);
   } else {
-    consume_gen_f<FPL, false>(d, row, acc, pkL, pkR, lane, two, fe, poly);
+    consume_gen_f<FPL, false, EXT>(d, row, acc, pkL, pkR, lane, two, fe, poly);
   }
 }
 
@@ -601,7 +603,7 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
   o[3] = q[3];
 }
 
-template <int FPL, int STAGES, int WARPS>
+template <int FPL, int STAGES, int WARPS, bool EXT>
 __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
   using L = MixLayout<FPL, STAGES>;
   constexpr int BATCH = L::BATCH;
@@ -719,11 +721,11 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
             consume_uni<FPL>(*dp, row, acc, pkL, pkR, lane);
           } else if (kind == K_LIN) {
             consume_lin<FPL>(*dp, row, acc, pkL, pkR, lane);
-          } else if (kind == K_POLY) {
+          } else if (EXT && kind == K_POLY) {
             consume_poly<FPL>(*dp, row, p.poly, acc, pkL, pkR, lane);
           } else {
             const Desc d = *dp;
-            consume_gen<FPL>(d, staged ? (const void*)row : d.src, acc, pkL, pkR, lane, two, p.spans, p.poly);
+            consume_gen<FPL, EXT>(d, staged ? (const void*)row : d.src, acc, pkL, pkR, lane, two, p.spans, p.poly);
           }
           if (staged) {
             __syncwarp();  // every lane is done reading the stage before lane 0 may refill it
@@ -1240,10 +1242,10 @@ struct MixVariant {
   int fpl, stages, warps;
 };
 
-template <int FPL, int STAGES, int WARPS>
-static cudaError_t launch_mix_t(const MixParams& p, int n_sm, cudaStream_t stream, int* ctas_out) {
+template <int FPL, int STAGES, int WARPS, bool EXT>
+static cudaError_t launch_mix_e(const MixParams& p, int n_sm, cudaStream_t stream, int* ctas_out) {
   using L = MixLayout<FPL, STAGES>;
-  auto kfn = mix_kernel<FPL, STAGES, WARPS>;
+  auto kfn = mix_kernel<FPL, STAGES, WARPS, EXT>;
   const int smem = L::WARP_BYTES * WARPS;
   cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
@@ -1263,6 +1265,12 @@ static cudaError_t launch_mix_t(const MixParams& p, int n_sm, cudaStream_t strea
 // 512-frame tiles: 2 stages x 8 warps per CTA (16 warps/SM, the register-file limit at 128 regs) measured faster
 // than 3 stages x 7 warps (14 warps/SM) on both cfg 2 (6.84 vs 6.42 TB/s) and cfg 3 (4.50 vs 4.42 TB/s);
 // WBX_VARIANT=a selects the latter for experiments.
+template <int FPL, int STAGES, int WARPS>
+static cudaError_t launch_mix_t(const MixParams& p, int n_sm, cudaStream_t stream, int* ctas_out) {
+  return p.ext ? launch_mix_e<FPL, STAGES, WARPS, true>(p, n_sm, stream, ctas_out)
+               : launch_mix_e<FPL, STAGES, WARPS, false>(p, n_sm, stream, ctas_out);
+}
+
 static int variant_b() {
   const char* v = getenv("WBX_VARIANT");
   return !(v && v[0] == 'a');
