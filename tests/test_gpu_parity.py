@@ -265,6 +265,26 @@ def test_cfg1_mono_many_blocks(wb):
     assert_exact(sc.standard(gpu_engine(wb), 16, 1, 48000, 700), ref, "cfg1 K=700")
 
 
+@pytest.mark.parametrize("block", [1, 37, 1000, 2048, 4096])
+def test_block_sizes(wb, block):
+    """Engine::set_audio_channel_config buffer sizes off the beaten path: odd sizes (scalar bus stores), blocks larger
+    than a 512-frame tile (several tiles per block, VU peaks merged with atomicMax), a single-frame block."""
+    def run(mk):
+        rng = np.random.RandomState(block)
+        eng = mk(2, block, 48000, 120.0)
+        n = 9
+        for t in range(n):
+            eng.add_track(-3.0 - t, -0.9 + 0.2 * t, False)
+            fmt = sc.FMT_I16 if t == 4 else sc.FMT_F32
+            sid = eng.add_sample(sc._src(rng, 1 if t == 6 else 2, 30000, n, fmt), 44100 if t % 3 == 2 else 48000, fmt)
+            eng.add_clip(t, sid, 0.013 * t, 64.0, float(t % 5), 1.0, 0.8)
+        eng.play()
+        k = max(3, min(40, 9000 // block))
+        return sc._collect(eng, [eng.process(k), eng.process(2)], n)
+    assert_exact(run(gpu_engine(wb)), run(cpu_engine()), "block=%d" % block)
+    assert_tree(run(gpu_engine(wb, True, wb.SUM_TREE)), run(cpu_engine()), "block=%d tree" % block)
+
+
 def test_unaligned_offsets_and_speeds(wb):
     """Start offsets 1..7 frames (16-byte-unaligned windows), speeds straddling the staged-window limit."""
     def run(mk):
