@@ -131,6 +131,24 @@ def make_sources(n_tracks, n_blocks, seed):
         yield t, [pool[o:o + frames] for o in offs]
 
 
+def ncu_traffic(n_tracks, n_blocks):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one mix-kernel launch from the committed `ncu --set full`
+    capture of this exact shape (profiles/), or None when no capture of the shape exists."""
+    if (n_tracks, n_blocks) != (1024, 4096):
+        return None
+    try:
+        rd = wr = None
+        for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_full_mix_fpl16_K4096.txt")):
+            f = ln.split()
+            if ln.startswith("dram__bytes_read.sum"):
+                rd = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+            if ln.startswith("dram__bytes_write.sum"):
+                wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+        return None if rd is None or wr is None else rd + wr
+    except Exception:
+        return None
+
+
 def track_params(t):
     return -6.0 - (t % 7), -1.0 + 0.2 * (t % 11), float(np.float32(0.5 + 0.001 * (t % 512)))
 
@@ -384,7 +402,8 @@ def run_ours(args):
                 "e2e_equals_device_run": same,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "traffic": ncu_traffic(N, K), "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "traffic_source": "profiles/r01_ncu_full_mix_fpl16_K4096.txt (ncu --set full, bytes per launch)" if ncu_traffic(N, K) else None,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": e2e_value, "unit": "stereo track-frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
@@ -414,7 +433,7 @@ def main():
     ap.add_argument("--tracks", type=int, default=1024, help="stereo tracks per GPU")
     ap.add_argument("--blocks", type=int, default=4096, help="512-frame callbacks per step (our arm)")
     ap.add_argument("--ref-blocks", type=int, default=96, help="callbacks per step of the reference arm")
-    ap.add_argument("--cpu-blocks", type=int, default=256, help="callbacks of the cpu_baseline sample")
+    ap.add_argument("--cpu-blocks", type=int, default=1024, help="callbacks of the cpu_baseline sample")
     ap.add_argument("--exact", type=int, default=1, help="1: bit-exact sequential track order, 0: auto")
     ap.add_argument("--cold", type=int, default=1, help="also measure e2e_cold (N=1 only)")
     args = ap.parse_args()

@@ -24,8 +24,10 @@ cudaError_t launch_interleave(const float* bus, uint64_t frames, uint32_t channe
 cudaError_t launch_interleave_sample(const void* planar, size_t plane_bytes, uint64_t frames, uint32_t nch,
                                      uint32_t esize, void* dst, int n_sm, cudaStream_t stream);
 int mix_warps_per_sm(int fpl);
-cudaError_t launch_mipmap(const void* base, uint32_t fmt, uint32_t nch, uint64_t count, uint64_t chunk, uint64_t block,
-                          uint64_t mdc, int high, void* out, cudaStream_t stream);
+cudaError_t launch_mip_level0(const void* base, uint32_t fmt, uint32_t nch, uint64_t count, uint64_t mdc, int high, void* out,
+                              int n_sm, cudaStream_t stream);
+cudaError_t launch_mip_merge(const void* child, uint64_t child_mdc, void* parent, uint64_t parent_mdc, uint32_t nch, int high,
+                             int n_sm, cudaStream_t stream);
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
                            float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, const float* poly,
@@ -49,6 +51,10 @@ struct SampleRec {
   uint32_t rate = 0, fmt = 0, esize = 0;
   uint64_t frames = 0;
   bool live = false;
+  // waveform mip-maps (WaveformVisual::create): all levels of one quality, built on first request, kept resident
+  void* d_mip[2] = {nullptr, nullptr};
+  std::vector<uint64_t> mip_count[2];   // elements per channel of each level
+  std::vector<uint64_t> mip_offset[2];  // byte offset of each level in d_mip[q]
 };
 
 // grow-only device / pinned-host buffers: no allocation in steady state
@@ -248,7 +254,11 @@ int wbx_destroy(wbx_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (auto& s : e->samples)
-    if (s.live) cudaFree(s.d_alloc);
+    if (s.live) {
+      cudaFree(s.d_alloc);
+      for (int q = 0; q < 2; q++)
+        if (s.d_mip[q]) cudaFree(s.d_mip[q]);
+    }
   for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv,
                     &e->d_upload, &e->d_levels, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin, &e->d_irtiles, &e->d_firplanes, &e->d_poly})
     if (b->p) cudaFree(b->p);
@@ -346,7 +356,16 @@ static bool is_pinned(const void* p);
 int wbx_sample_update(wbx_engine* e, uint32_t id, const void* const* planar) {
   if (!e || !planar || id >= e->samples.size() || !e->samples[id].live) return fail(e, WBX_ERR_INVALID, "bad sample id");
   CU(e, cudaSetDevice(e->device));
-  const SampleRec& r = e->samples[id];
+  SampleRec& r = e->samples[id];
+  for (int q = 0; q < 2; q++) {  // the data changes: cached mip-maps are stale
+    if (r.d_mip[q]) {
+      CU(e, cudaStreamSynchronize(e->stream));
+      CU(e, cudaFree(r.d_mip[q]));
+      r.d_mip[q] = nullptr;
+    }
+    r.mip_count[q].clear();
+    r.mip_offset[q].clear();
+  }
   const size_t plane_bytes = (((size_t)r.frames * r.esize) + 255) & ~(size_t)255;
   // two staging halves alternate so the next sample's H2D overlaps this one's interleave kernel
   int rc = dev_reserve(e, e->d_upload, 2 * plane_bytes * r.nch);
@@ -368,36 +387,54 @@ int wbx_sample_update(wbx_engine* e, uint32_t id, const void* const* planar) {
 int wbx_sample_mipmap(wbx_engine* e, uint32_t id, int quality, int level, void* out, uint64_t cap_elems,
                       uint32_t* count) {
   if (!e || id >= e->samples.size() || !e->samples[id].live) return fail(e, WBX_ERR_INVALID, "bad sample id");
-  const SampleRec& r = e->samples[id];
+  SampleRec& r = e->samples[id];
   if (r.channels > 2) return fail(e, WBX_ERR_UNSUPPORTED, "mip-maps: only the 2 resident channels are available");
   if (r.fmt == WBX_FMT_I24) return 0;  // the reference's switch has no case for this tag (`default: break`)
   CU(e, cudaSetDevice(e->device));
-  // WaveformVisual::create (gfx/waveform_visual.cpp:181-248): levels with chunk 2, 8, 32, ... while count/4^l > 64
-  uint64_t sample_count = r.frames;
-  uint32_t current_mip = 1;
-  int n_levels = 0;
-  const size_t esz = quality ? 2 : 1;
-  while (sample_count > 64) {
-    if (n_levels == level) {
-      const uint64_t chunk = 1ull << current_mip, block = 1ull << (current_mip - 1);
+  const int q = quality ? 1 : 0;
+  const size_t esz = q ? 2 : 1;
+  if (r.mip_count[q].empty() && r.frames > 64) {
+    // WaveformVisual::create (gfx/waveform_visual.cpp:181-248): levels with chunk 2, 8, 32, ... while count/4^l > 64
+    uint64_t sample_count = r.frames, total = 0;
+    uint32_t current_mip = 1;
+    while (sample_count > 64) {
+      const uint64_t block = 1ull << (current_mip - 1);
       uint64_t mdc = r.frames / block;
       mdc += mdc % 2;
-      if (count) *count = (uint32_t)mdc;
-      const uint64_t elems = mdc * r.nch;
-      if (out && elems <= cap_elems) {
-        int rc;
-        if ((rc = dev_reserve(e, e->d_conv, elems * esz))) return rc;
-        if ((rc = host_reserve(e, e->h_conv, elems * esz))) return rc;
-        CU(e, launch_mipmap(r.d_base, r.fmt, r.nch, r.frames, chunk, block, mdc, quality ? 1 : 0, e->d_conv.p, e->stream));
-        e->launches++;
-        CU(e, cudaMemcpyAsync(e->h_conv.p, e->d_conv.p, elems * esz, cudaMemcpyDeviceToHost, e->stream));
-        CU(e, cudaStreamSynchronize(e->stream));
-        memcpy(out, e->h_conv.p, elems * esz);
-      }
+      r.mip_count[q].push_back(mdc);
+      r.mip_offset[q].push_back(total);
+      total += ((mdc * r.nch * esz) + 255) & ~(uint64_t)255;
+      sample_count /= 4;
+      current_mip += 2;
     }
-    n_levels++;
-    sample_count /= 4;
-    current_mip += 2;
+    cudaError_t err = cudaMalloc(&r.d_mip[q], total);
+    if (err != cudaSuccess) {
+      r.mip_count[q].clear();
+      r.mip_offset[q].clear();
+      return fail(e, WBX_ERR_NOMEM, "cudaMalloc(%llu) for mip-maps failed", (unsigned long long)total);
+    }
+    uint8_t* base = (uint8_t*)r.d_mip[q];
+    CU(e, launch_mip_level0(r.d_base, r.fmt, r.nch, r.frames, r.mip_count[q][0], q, base, e->n_sm, e->stream));
+    e->launches++;
+    for (size_t l = 1; l < r.mip_count[q].size(); l++) {  // each level from the previous one (4 chunks -> 1)
+      CU(e, launch_mip_merge(base + r.mip_offset[q][l - 1], r.mip_count[q][l - 1], base + r.mip_offset[q][l],
+                             r.mip_count[q][l], r.nch, q, e->n_sm, e->stream));
+      e->launches++;
+    }
+  }
+  const int n_levels = (int)r.mip_count[q].size();
+  if (level >= 0 && level < n_levels) {
+    const uint64_t mdc = r.mip_count[q][level];
+    if (count) *count = (uint32_t)mdc;
+    const uint64_t elems = mdc * r.nch;
+    if (out && elems <= cap_elems) {
+      int rc;
+      if ((rc = host_reserve(e, e->h_conv, elems * esz))) return rc;
+      CU(e, cudaMemcpyAsync(e->h_conv.p, (uint8_t*)r.d_mip[q] + r.mip_offset[q][level], elems * esz, cudaMemcpyDeviceToHost,
+                            e->stream));
+      CU(e, cudaStreamSynchronize(e->stream));
+      memcpy(out, e->h_conv.p, elems * esz);
+    }
   }
   return n_levels;
 }
@@ -407,6 +444,8 @@ int wbx_sample_release(wbx_engine* e, uint32_t id) {
   CU(e, cudaSetDevice(e->device));
   CU(e, cudaStreamSynchronize(e->stream));
   CU(e, cudaFree(e->samples[id].d_alloc));
+  for (int q = 0; q < 2; q++)
+    if (e->samples[id].d_mip[q]) CU(e, cudaFree(e->samples[id].d_mip[q]));
   e->samples[id] = SampleRec();
   return WBX_OK;
 }

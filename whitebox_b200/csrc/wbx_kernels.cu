@@ -1154,84 +1154,93 @@ __device__ __forceinline__ int mip_convert(uint32_t fmt, const void* base, uint6
   return high ? (int)(int16_t)q : (int)(int8_t)q;  // (T)conv
 }
 
-struct MipAcc {
-  int mn, mx;
-  uint32_t mn_i, mx_i;
-  __device__ __forceinline__ void add(int v, uint32_t j) {  // strict compares: first occurrence wins
-    if (v < mn) {
-      mn = v;
-      mn_i = j;
-    }
-    if (v > mx) {
-      mx = v;
-      mx_i = j;
-    }
-  }
-  __device__ __forceinline__ void merge(int omn, uint32_t omn_i, int omx, uint32_t omx_i) {
-    if (omn < mn || (omn == mn && omn_i < mn_i)) {
-      mn = omn;
-      mn_i = omn_i;
-    }
-    if (omx > mx || (omx == mx && omx_i < mx_i)) {
-      mx = omx;
-      mx_i = omx_i;
-    }
-  }
-};
-
-// WARP == false: one thread per (channel, chunk) — small chunks; WARP == true: one warp per (channel, chunk).
-template <bool WARP>
-__global__ void mipmap_kernel(const void* __restrict__ base, uint32_t fmt, uint32_t nch, uint64_t count,
-                              uint64_t chunk, uint64_t block, uint64_t mdc, int high, void* __restrict__ out) {
-  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t unit = WARP ? (gid >> 5) : gid;
-  const uint32_t lane = threadIdx.x & 31;
+// Level 0 (chunks of 2 frames): for a full chunk (v0, v1) the first-occurrence rule always yields (v0, v1) itself —
+// v1 < v0 makes v0 the earlier max, v1 > v0 makes v0 the earlier min — and a 1-frame tail chunk yields (v0, v0).
+// So level 0 is one streaming pass: read the sample once, write the converted values. One thread per frame pair,
+// both channels (one 128-bit load for stereo f32).
+__global__ void mip_level0_kernel(const void* __restrict__ base, uint32_t fmt, uint32_t nch, uint64_t count, uint64_t mdc,
+                                  int high, void* __restrict__ out) {
   const uint64_t pairs = mdc / 2;
-  if (unit >= pairs * nch) return;
-  const uint32_t c = (uint32_t)(unit / pairs);
-  const uint64_t pi = unit % pairs;
-  const uint64_t idx = 2 * pi * block;  // i * block_count with i = 2 * pair
-  const uint64_t rem = count - idx;
-  const uint64_t len = chunk < rem ? chunk : rem;
-  MipAcc a;
-  a.mn = high ? 32767 : 127;  // numeric_limits<T>::max() / ::min()
-  a.mx = high ? -32768 : -128;
-  a.mn_i = 0;
-  a.mx_i = 0;
-  if (WARP) {
-    for (uint64_t j = lane; j < len; j += 32) a.add(mip_convert(fmt, base, (idx + j) * nch + c, high != 0), (uint32_t)j);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int omn = __shfl_xor_sync(0xffffffffu, a.mn, o), omx = __shfl_xor_sync(0xffffffffu, a.mx, o);
-      const uint32_t omn_i = __shfl_xor_sync(0xffffffffu, a.mn_i, o), omx_i = __shfl_xor_sync(0xffffffffu, a.mx_i, o);
-      // a lane that saw no element keeps the initial (max, min) with index 0: it can only tie with another
-      // lane's value when that value IS the initial one, and then index 0 is the reference's answer too
-      a.merge(omn, omn_i, omx, omx_i);
+  for (uint64_t pi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pi < pairs; pi += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t f0 = 2 * pi;
+    const bool two_frames = f0 + 1 < count;
+    for (uint32_t c = 0; c < nch; c++) {
+      const int v0 = mip_convert(fmt, base, f0 * nch + c, high != 0);
+      const int v1 = two_frames ? mip_convert(fmt, base, (f0 + 1) * nch + c, high != 0) : v0;
+      const uint64_t o = mdc * c + f0;
+      if (high) {
+        reinterpret_cast<int16_t*>(out)[o] = (int16_t)v0;
+        reinterpret_cast<int16_t*>(out)[o + 1] = (int16_t)v1;
+      } else {
+        reinterpret_cast<int8_t*>(out)[o] = (int8_t)v0;
+        reinterpret_cast<int8_t*>(out)[o + 1] = (int8_t)v1;
+      }
     }
-    if (lane != 0) return;
-  } else {
-    for (uint64_t j = 0; j < len; j++) a.add(mip_convert(fmt, base, (idx + j) * nch + c, high != 0), (uint32_t)j);
-  }
-  const int first = a.mx_i < a.mn_i ? a.mx : a.mn, second = a.mx_i < a.mn_i ? a.mn : a.mx;
-  const uint64_t o = mdc * c + 2 * pi;
-  if (high) {
-    ((int16_t*)out)[o] = (int16_t)first;
-    ((int16_t*)out)[o + 1] = (int16_t)second;
-  } else {
-    ((int8_t*)out)[o] = (int8_t)first;
-    ((int8_t*)out)[o + 1] = (int8_t)second;
   }
 }
 
-cudaError_t launch_mipmap(const void* base, uint32_t fmt, uint32_t nch, uint64_t count, uint64_t chunk, uint64_t block,
-                          uint64_t mdc, int high, void* out, cudaStream_t stream) {
-  const uint64_t units = (mdc / 2) * nch;
-  if (units == 0) return cudaSuccess;
-  if (chunk <= 32) {
-    mipmap_kernel<false><<<(unsigned)((units + 127) / 128), 128, 0, stream>>>(base, fmt, nch, count, chunk, block, mdc, high, out);
-  } else {
-    mipmap_kernel<true><<<(unsigned)((units * 32 + 127) / 128), 128, 0, stream>>>(base, fmt, nch, count, chunk, block, mdc, high, out);
+// Level l+1 from level l: a chunk of level l+1 is four consecutive chunks of level l. Each child pair (first, second)
+// carries its min, its max and which came first; the parent's min / max are the first child (in order) attaining
+// them, and their relative order follows from child order or, inside one child, from that child's pair order —
+// exactly the first-occurrence indices summarize_for_mipmaps_impl tracks over the raw samples
+// (gfx/waveform_visual.cpp:33-52), because the conversion to int8/int16 happens before the comparisons there too.
+template <typename T>
+__global__ void mip_merge_kernel(const T* __restrict__ child, uint64_t child_mdc, T* __restrict__ parent,
+                                 uint64_t parent_mdc, uint32_t nch, int tmin, int tmax) {
+  const uint64_t ppairs = parent_mdc / 2, cpairs = child_mdc / 2;
+  const uint64_t total = ppairs * nch;
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = (uint32_t)(u / ppairs);
+    const uint64_t P = u % ppairs;
+    int gmin = tmax, gmax = tmin;  // numeric_limits<T>::max() / ::min(), strict compares below
+    uint32_t min_pos = 0, max_pos = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+      const uint64_t cp = 4 * P + k;
+      if (cp < cpairs) {
+        const int f = child[child_mdc * c + 2 * cp], s2 = child[child_mdc * c + 2 * cp + 1];
+        const int cmin = f < s2 ? f : s2, cmax = f < s2 ? s2 : f;
+        const bool min_first = (f == cmin);
+        const uint32_t pmin = 2 * k + ((min_first || cmin == cmax) ? 0u : 1u);
+        const uint32_t pmax = 2 * k + ((min_first && cmin != cmax) ? 1u : 0u);
+        if (cmin < gmin) {
+          gmin = cmin;
+          min_pos = pmin;
+        }
+        if (cmax > gmax) {
+          gmax = cmax;
+          max_pos = pmax;
+        }
+      }
+    }
+    const bool max_first = max_pos < min_pos;
+    parent[parent_mdc * c + 2 * P] = (T)(max_first ? gmax : gmin);
+    parent[parent_mdc * c + 2 * P + 1] = (T)(max_first ? gmin : gmax);
   }
+}
+
+cudaError_t launch_mip_level0(const void* base, uint32_t fmt, uint32_t nch, uint64_t count, uint64_t mdc, int high, void* out,
+                              int n_sm, cudaStream_t stream) {
+  const uint64_t pairs = mdc / 2;
+  if (pairs == 0) return cudaSuccess;
+  uint64_t blocks = (pairs + 255) / 256;
+  if (blocks > (uint64_t)n_sm * 32) blocks = (uint64_t)n_sm * 32;
+  mip_level0_kernel<<<(unsigned)blocks, 256, 0, stream>>>(base, fmt, nch, count, mdc, high, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mip_merge(const void* child, uint64_t child_mdc, void* parent, uint64_t parent_mdc, uint32_t nch, int high,
+                             int n_sm, cudaStream_t stream) {
+  const uint64_t total = (parent_mdc / 2) * nch;
+  if (total == 0) return cudaSuccess;
+  uint64_t blocks = (total + 255) / 256;
+  if (blocks > (uint64_t)n_sm * 32) blocks = (uint64_t)n_sm * 32;
+  if (high)
+    mip_merge_kernel<int16_t><<<(unsigned)blocks, 256, 0, stream>>>((const int16_t*)child, child_mdc, (int16_t*)parent, parent_mdc,
+                                                                   nch, -32768, 32767);
+  else
+    mip_merge_kernel<int8_t><<<(unsigned)blocks, 256, 0, stream>>>((const int8_t*)child, child_mdc, (int8_t*)parent, parent_mdc, nch,
+                                                                  -128, 127);
   return cudaGetLastError();
 }
 
