@@ -409,3 +409,37 @@ def test_cpp_dropin_demo(wb, tmp_path):
     r = subprocess.run([exe, "96", "40"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 samples differ" in r.stdout
+
+
+def test_device_api_side_doors(wb):
+    """wbx_sample_update (streamed sources), wbx_fetch_levels (VU level = max over callbacks), page-locked output
+    channels (direct D2H) and the three-stage submit / mix / fetch split all agree with the plain wbx_render path."""
+    rng = np.random.RandomState(77)
+    N, K, B = 24, 9, 512
+    dev = wb.DeviceEngine(0)
+    dev.configure(2, B, 48000)
+    dev.set_track_count(N)
+    dev.set_sum_mode(wb.SUM_EXACT)
+    frames = K * B + 64
+    data = [sc._src(rng, 2, frames, N) for _ in range(N)]
+    segs = np.zeros(N, wb.SEGMENT_DTYPE)
+    for t in range(N):
+        sid = dev.sample_upload(np.zeros_like(data[t]), 48000)  # placeholder content ...
+        segs[t] = (t, 0, K, 0, B, sid, 0.0, 1.0, 0.7, 0, 0.0, 0.0, 0.0, 0.0)
+    for t in range(N):
+        dev.sample_update_planar(t, [data[t][0], data[t][1]])  # ... replaced in place
+    gains = np.full((N, 2), 0.5, np.float32)
+    out, peaks = dev.render(segs, gains, K)
+    ref = wb.DeviceEngine(0)
+    ref.configure(2, B, 48000)
+    ref.set_track_count(N)
+    ref.set_sum_mode(wb.SUM_EXACT)
+    for t in range(N):
+        ref.sample_upload(data[t], 48000)
+    out2, peaks2 = ref.render(segs, gains, K)
+    assert same_bits(out, out2) and same_bits(peaks, peaks2), "sample_update != fresh upload"
+    assert same_bits(dev.fetch_levels(), peaks.max(axis=0)), "fetch_levels != max over callbacks"
+    pinned = wb.PinnedArray((2, K * B))
+    assert dev.L.wbx_fetch(dev.h, wb._chan_ptrs(pinned.array), None) == 0
+    assert same_bits(pinned.array, out), "page-locked direct fetch differs"
+    assert dev.launch_count() > 0 and "exact" in dev.last_kernel()
