@@ -156,42 +156,60 @@ def track_params(t):
 # ---------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU engine (oracle/_ref) or the C port, on the host cores
 # ---------------------------------------------------------------------------------------------------------
-def cpu_engine_run(kind, n_tracks, n_blocks, threads, seed=1234, total_tracks=None):
-    """Times Engine::process on the CPU. threads == 1 is the faithful single-threaded reference; threads > 1
-    runs that many independent engine instances, n_tracks/threads tracks each (the generous all-cores row).
-    Returns (track_frames_per_s, seconds)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_api as o
-    total_tracks = total_tracks or n_tracks
-    per = [n_tracks // threads + (1 if i < n_tracks % threads else 0) for i in range(threads)]
-    sessions = []
-    src = make_sources(n_tracks, n_blocks, seed)
-    for i in range(threads):
-        s = o.Session(kind, 2, BLOCK, RATE, 120.0)
-        for j in range(per[i]):
-            t, x = next(src)
-            vol, pan, gain = track_params(t)
-            s.add_track(vol, pan, False)
-            sid = s.add_sample(np.stack(x), RATE)
-            s.add_clip(j, sid, 0.0, 1e9, 0.0, 1.0, gain)
-        s.play()
-        s.time_process(1)  # warm-up callback (consumes the constructor's parameter messages)
-        sessions.append(s)
-    secs = [0.0] * threads
+class CpuEngines:
+    """The reference CPU engine (oracle/_ref, else the C port) set up once for the bench workload.
+    threads == 1 is the faithful single-threaded reference; threads > 1 builds that many independent engine
+    instances with n_tracks/threads tracks each (the generous all-cores row)."""
 
-    def run(i):
-        secs[i] = sessions[i].time_process(n_blocks)
+    def __init__(self, kind, n_tracks, n_blocks, threads, seed=1234):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api as o
+        self.n_tracks, self.n_blocks, self.threads = n_tracks, n_blocks, threads
+        per = [n_tracks // threads + (1 if i < n_tracks % threads else 0) for i in range(threads)]
+        self.sessions = []
+        src = make_sources(n_tracks, n_blocks, seed)
+        for i in range(threads):
+            s = o.Session(kind, 2, BLOCK, RATE, 120.0)
+            for j in range(per[i]):
+                t, x = next(src)
+                vol, pan, gain = track_params(t)
+                s.add_track(vol, pan, False)
+                sid = s.add_sample(np.stack(x), RATE)
+                s.add_clip(j, sid, 0.0, 1e9, 0.0, 1.0, gain)
+            self.sessions.append(s)
 
-    ths = [threading.Thread(target=run, args=(i,)) for i in range(threads)]
-    t0 = time.perf_counter()
-    for th in ths:
-        th.start()
-    for th in ths:
-        th.join()
-    wall = time.perf_counter() - t0
-    for s in sessions:
-        s.close()
-    return n_tracks * n_blocks * BLOCK / wall, wall
+    def run(self):
+        """One pass over n_blocks callbacks from beat 0 -> (track_frames_per_s, seconds)."""
+        for s in self.sessions:
+            s.stop()
+            s.play()
+            s.time_process(1)  # warm-up callback (consumes pending parameter messages)
+        secs = [0.0] * self.threads
+
+        def work(i):
+            secs[i] = self.sessions[i].time_process(self.n_blocks)
+
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(self.threads)]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        wall = time.perf_counter() - t0
+        return self.n_tracks * self.n_blocks * BLOCK / wall, wall
+
+    def close(self):
+        for s in self.sessions:
+            s.close()
+        self.sessions = []
+
+
+def cpu_engine_run(kind, n_tracks, n_blocks, threads, seed=1234):
+    eng = CpuEngines(kind, n_tracks, n_blocks, threads, seed)
+    try:
+        return eng.run()
+    finally:
+        eng.close()
 
 
 def oracle_kind():
@@ -212,13 +230,15 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 32))
     n_tracks = args.tracks * args.gpus
-    blocks = args.ref_blocks
+    blocks = max(64, args.ref_blocks // args.gpus)  # keeps the host-memory footprint of the sample bounded
     vals = []
+    engines = CpuEngines(kind, n_tracks, blocks, threads)
     for i in range(args.warmup + args.steps):
-        v, secs = cpu_engine_run(kind, n_tracks, blocks, threads)
+        v, secs = engines.run()
         log("reference step %d: %.3e track-frames/s (%.2fs)" % (i, v, secs))
         if i >= args.warmup:
             vals.append((v, secs))
+    engines.close()
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([s for _, s in vals])) * 1e3
     one, _ = cpu_engine_run(kind, min(n_tracks, 1024), max(8, blocks // 4), 1)
@@ -432,7 +452,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tracks", type=int, default=1024, help="stereo tracks per GPU")
     ap.add_argument("--blocks", type=int, default=4096, help="512-frame callbacks per step (our arm)")
-    ap.add_argument("--ref-blocks", type=int, default=96, help="callbacks per step of the reference arm")
+    ap.add_argument("--ref-blocks", type=int, default=1024, help="callbacks per step of the reference arm (at 1 GPU)")
     ap.add_argument("--cpu-blocks", type=int, default=1024, help="callbacks of the cpu_baseline sample")
     ap.add_argument("--exact", type=int, default=1, help="1: bit-exact sequential track order, 0: auto")
     ap.add_argument("--cold", type=int, default=1, help="also measure e2e_cold (N=1 only)")
