@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
         objs.append(o)
-    cmd = [NVCC, "-shared", "-cudart", "static", "-o", OUT] + objs
+    cmd = [NVCC, "-shared", "-cudart", "static", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
