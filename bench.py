@@ -16,7 +16,8 @@ f32 tracks per GPU (BASELINE cfg 2: gain/pan + bus sum; fade = 0, the reference 
            counts uploading every source sample from host memory each step.
   roofline achieved = algorithmic bytes (8 B per stereo track-frame + cells) / mean mix-kernel duration.
 N > 1 (torchrun): tracks shard across ranks (weak scaling: --tracks per GPU), each rank mixes its shard
-unclamped, ONE NCCL all-reduce sums the partial buses, then the clamp runs (engine.cpp:1627 after the reduce).
+unclamped and the partial buses are summed and clamped (engine.cpp:1627 after the sum) by the exchange fused into
+the mix kernel over peer memory (include/wbx.h "sharded render"; --exchange nccl: one NCCL all-reduce instead).
 """
 import argparse
 import json
@@ -313,11 +314,45 @@ def run_ours(args):
     dev.set_track_count(N)
     flags = wb.MIX_NO_CLAMP if world > 1 else 0
 
-    def reduce_and_clamp():
-        if world > 1:
-            ptr, n = dev.device_bus()
-            dist.all_reduce(shard.bus_tensor(dev))  # the single NCCL reduce of the partial buses (sum, f32)
-            dev.clamp_device(ptr, n)
+    # ---- bus exchange across ranks: peer memory fused into the mix (default) or one NCCL all-reduce -----
+    exchange = "none"
+    if world > 1:
+        exchange = "nccl" if args.exchange == "nccl" else "peer"
+        if exchange == "peer":
+            try:
+                handle = dev.shard_init(rank, world, K)
+                handles = [None] * world
+                dist.all_gather_object(handles, handle)
+                dev.shard_connect_ipc(handles)
+                ok = 1
+            except Exception as ex:  # e.g. CUDA IPC not permitted in this container
+                log("rank %d: peer-memory exchange unavailable (%s) - using the NCCL all-reduce" % (rank, ex))
+                ok = 0
+            t_ok = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            if int(t_ok.item()) == 0:
+                dev.shard_close()
+                exchange = "nccl"
+
+    def mix_step(ev_pair=None):
+        """One step's device work: mix this rank's tracks, sum the bus across ranks, clamp. ev_pair brackets the
+        mix kernel alone (for the roofline)."""
+        if ev_pair:
+            ev_pair[0].record(stream)
+        if exchange == "peer":
+            dev.mix_sharded(0)  # mix; tiles -> owners' exchange buffers over NVLink while mixing; arrival signal
+            if ev_pair:
+                ev_pair[1].record(stream)
+            dev.mix_sharded(1)  # wait for all ranks, owner reduce in rank order + clamp -> rank 0's master bus
+            dev.mix_sharded(2)  # wait until every slice is in
+        else:
+            dev.mix(flags)
+            if ev_pair:
+                ev_pair[1].record(stream)
+            if world > 1:
+                ptr, n = dev.device_bus()
+                dist.all_reduce(shard.bus_tensor(dev))  # one NCCL all-reduce of the partial buses (sum, f32)
+                dev.clamp_device(ptr, n)
 
     # ---- (1) device-resident throughput: schedule submitted once, K launches of the mix kernel ---------
     eng.play()
@@ -326,8 +361,7 @@ def run_ours(args):
     dev.synchronize()
     with torch.cuda.stream(stream):
         for _ in range(max(3, args.warmup)):
-            dev.mix(flags)
-            reduce_and_clamp()
+            mix_step()
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:
@@ -338,10 +372,7 @@ def run_ours(args):
         barrier()
         e0.record(stream)
         for i in range(args.steps):
-            ev[i][0].record(stream)
-            dev.mix(flags)
-            ev[i][1].record(stream)
-            reduce_and_clamp()
+            mix_step(ev[i])
         e1.record(stream)
         barrier()
         launches = dev.launch_count() - launches0
@@ -349,7 +380,7 @@ def run_ours(args):
     total_ms = e0.elapsed_time(e1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     kernel_name = dev.last_kernel()
-    out_dev, _ = dev.fetch(False)
+    out_dev, _ = dev.fetch(False, want_bus=(rank == 0 or exchange != "peer"))
 
     # ---- (2) end to end through the host engine API with host buffers --------------------------------
     def e2e_step(cold):
@@ -360,10 +391,11 @@ def run_ours(args):
         eng.play()
         if world == 1:  # the public call: host scheduling, H2D table, expand, mix, D2H bus + VU levels
             return eng.render(K, want_peaks=False, out=pinned_out.array)
+        if exchange == "peer":  # the public call on every rank; rank 0 receives the master bus
+            return eng.render(K, want_peaks=False, out=pinned_out.array if rank == 0 else None, want_bus=(rank == 0))
         segs2, gains2 = eng.schedule(K)
         dev.submit(segs2, gains2, K)
-        dev.mix(flags)
-        reduce_and_clamp()
+        mix_step()
         if rank == 0:
             dev.L.wbx_fetch(dev.h, wb._chan_ptrs(pinned_out.array), None)
             return pinned_out.array, dev.fetch_levels()
@@ -418,7 +450,8 @@ def run_ours(args):
                 "tracks_per_gpu": N, "total_tracks": N * world, "block_frames": BLOCK, "blocks_per_step": K,
                 "out_frames_per_s": value / (N * world), "realtime_x": value / (N * world) / RATE,
                 "l2": "inputs larger than L2 (%.2f GiB streamed per step per GPU vs 126 MB)" % (alg_bytes / 2**30),
-                "kernel": kernel_name, "parallelism": "tracks sharded x%d, 1 NCCL all-reduce of the bus" % world if world > 1 else "1 GPU",
+                "kernel": kernel_name, "parallelism": ("tracks sharded x%d, %s" % (world, "bus exchange over peer memory fused into the mix kernel (tiles stored into the owner rank's buffer, flag barrier, owner reduce + clamp into rank 0)" if exchange == "peer" else "1 NCCL all-reduce of the bus")) if world > 1 else "1 GPU",
+                "bus_exchange": exchange,
                 "e2e_equals_device_run": same,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -456,6 +489,8 @@ def main():
     ap.add_argument("--cpu-blocks", type=int, default=1024, help="callbacks of the cpu_baseline sample")
     ap.add_argument("--exact", type=int, default=1, help="1: bit-exact sequential track order, 0: auto")
     ap.add_argument("--cold", type=int, default=1, help="also measure e2e_cold (N=1 only)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: bus sum over peer memory fused into the mix kernel, or one NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define WBX_ABI_VERSION 2
+#define WBX_ABI_VERSION 3
 
 typedef struct wbx_engine wbx_engine;
 
@@ -181,6 +181,13 @@ int wbx_set_track_effects(wbx_engine* e, uint32_t track, const wbx_effects* fx);
  *                offers to `level` in that callback (vu_meter.h:20-30); may be NULL. */
 int wbx_render(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
                uint32_t n_blocks, float* const* out_channels, float* peaks);
+/* wbx_render that also returns levels[n_tracks][2] (see wbx_fetch_levels; may be NULL) under the same single
+ * synchronisation. When every out_channels[c] is page-locked (wbx_host_alloc) the mix kernel stores each finished bus
+ * tile into the caller's channels itself (posted writes over PCIe, next to the device copy of the bus), so no
+ * device-to-host copy of the bus follows the kernel. On an engine in a connected sharded setup (wbx_shard_*) the mix is
+ * the sharded one: out_channels is only written on rank 0. */
+int wbx_render_levels(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
+                      uint32_t n_blocks, float* const* out_channels, float* peaks, float* levels);
 
 /* The three stages of wbx_render, for callers that keep data on the device (sharded multi-GPU mixing,
  * benchmarking the kernel alone):
@@ -212,6 +219,40 @@ int wbx_device_peaks(wbx_engine* e, float** d_peaks, uint64_t* n_floats);
  * that must follow the cross-GPU bus reduce when tracks are sharded. */
 int wbx_clamp_device(wbx_engine* e, float* d_bus, uint64_t n_floats);
 int wbx_synchronize(wbx_engine* e);
+
+/* ---- sharded render: tracks split over the GPUs of one box ---------------------------------------
+ * Tracks are independent until AudioBuffer::mix adds them into the bus (engine/engine.cpp:1600-1617), so every rank
+ * (one engine per GPU; one process per GPU or several engines in one process) owns a subset of the tracks and its
+ * samples, and the only exchange is the bus sum, followed by the clamp (engine.cpp:1627-1636). That exchange runs
+ * over peer memory (NVLink / NVSwitch), fused into the mix: callback k belongs to owner rank k / ceil(n_blocks /
+ * world); each rank's mix kernel stores its UNCLAMPED bus tiles directly into the owner's exchange buffer while it
+ * mixes, a flag barrier between the GPUs follows, every owner adds the world partial buses of its callbacks in rank
+ * order 0..world-1 (deterministic; re-associated relative to one engine holding all tracks, like WBX_SUM_TREE),
+ * clamps, and stores the slice into rank 0's master bus; a second barrier completes the step.
+ *   1. wbx_shard_init on every rank (after wbx_configure): allocates the rank's exchange block and returns its CUDA
+ *      IPC handle (WBX_IPC_HANDLE_BYTES bytes; ipc_handle_out may be NULL for same-process use);
+ *   2. ranks exchange the handles by any means (bench.py: torch.distributed all_gather) and call
+ *      wbx_shard_connect_ipc(handles[world][WBX_IPC_HANDLE_BYTES]) — or, engines of one process,
+ *      wbx_shard_connect_local(engines[world]) once every engine is initialised;
+ *   3. per render: wbx_submit, then wbx_mix_sharded on EVERY rank, the same number of times and with the same
+ *      n_blocks <= max_blocks (it is a collective). wbx_fetch / wbx_device_bus / wbx_fetch_interleaved on rank 0 then
+ *      see the clamped master bus; peaks and levels stay per rank (they are per track).
+ * A rank that never arrives makes the barrier give up after 10 s (WBX_SHARD_TIMEOUT_MS) and the next synchronising
+ * call return WBX_ERR_CUDA instead of hanging the GPU. */
+#define WBX_IPC_HANDLE_BYTES 64
+#define WBX_MAX_SHARD_RANKS 16
+int wbx_shard_init(wbx_engine* e, uint32_t rank, uint32_t world, uint32_t max_blocks, void* ipc_handle_out);
+int wbx_shard_connect_ipc(wbx_engine* e, const void* handles);
+int wbx_shard_connect_local(wbx_engine* e, wbx_engine* const* engines);
+int wbx_mix_sharded(wbx_engine* e);
+/* The same collective in its three phases, for ONE thread driving several engines (it must issue phase p on every
+ * engine before phase p+1 on any, so that no engine's stream waits for work that has not been enqueued yet):
+ *   0  mix into the owners' exchange buffers + arrival signal      1  wait, reduce own slice + clamp into the master
+ *   bus, signal      2  wait. wbx_mix_sharded(e) = phases 0, 1, 2 back to back (one process or thread per GPU). */
+int wbx_mix_sharded_phase(wbx_engine* e, int phase);
+int wbx_shard_close(wbx_engine* e);
+/* rank / world of a connected sharded setup, (0, 1) otherwise */
+int wbx_shard_info(const wbx_engine* e, uint32_t* rank, uint32_t* world);
 
 /* ---- introspection --------------------------------------------------------------------------------- */
 /* Number of CUDA kernels this engine has launched since creation (bench.py's gpu_launches). */

@@ -443,3 +443,193 @@ def test_device_api_side_doors(wb):
     assert dev.L.wbx_fetch(dev.h, wb._chan_ptrs(pinned.array), None) == 0
     assert same_bits(pinned.array, out), "page-locked direct fetch differs"
     assert dev.launch_count() > 0 and "exact" in dev.last_kernel()
+
+
+# ---- page-locked output channels written by the mix kernel itself; the sharded bus exchange over peer memory ---------
+
+@pytest.mark.parametrize("K,B,mode", [(33, 512, "exact"), (1, 512, "tree"), (5, 37, "exact"), (3, 1000, "tree"),
+                                      (2, 2048, "exact")])
+def test_render_into_page_locked_channels(wb, K, B, mode):
+    """wbx_render_levels with page-locked out_channels: the kernel's own stores into host memory (no D2H copy) carry
+    exactly the device bus, and the levels returned under the same synchronise are the max of the block peaks."""
+    rng = np.random.RandomState(5)
+    N = 40
+    dev = wb.DeviceEngine(0)
+    dev.configure(2, B, 48000)
+    dev.set_track_count(N)
+    dev.set_sum_mode(wb.SUM_EXACT if mode == "exact" else wb.SUM_TREE)
+    frames = K * B + 64
+    segs = np.zeros(N, wb.SEGMENT_DTYPE)
+    for t in range(N):
+        sid = dev.sample_upload(sc._src(rng, 2, frames, 4), 48000)  # hot enough to hit the clamp now and then
+        segs[t] = (t, 0, K, 0, B, sid, 0.0, 1.0 if t % 3 else 0.77, 0.7, 0, 0.0, 0.0, 0.0, 0.0)
+    gains = np.full((N, 2), 0.5, np.float32)
+    out, peaks = dev.render(segs, gains, K)
+    pinned = wb.PinnedArray((2, K * B))
+    pinned.array[:] = 7.0
+    lv = np.zeros((N, 2), np.float32)
+    pk = np.zeros((K, N, 2), np.float32)
+    rc = dev.L.wbx_render_levels(dev.h, segs.ctypes.data, N, gains.ctypes.data, K, wb._chan_ptrs(pinned.array),
+                                 pk.ctypes.data, lv.ctypes.data)
+    assert rc == 0
+    assert same_bits(pinned.array, out), "kernel-written host channels differ from the device bus"
+    assert same_bits(pk, peaks) and same_bits(lv, peaks.max(axis=0))
+    out_dev, _ = dev.fetch(False)  # the device copy of the bus is still there (fetch_interleaved etc. rely on it)
+    assert same_bits(out_dev, out)
+    # pageable channels through the same entry point
+    plain = np.zeros((2, K * B), np.float32)
+    assert dev.L.wbx_render_levels(dev.h, segs.ctypes.data, N, gains.ctypes.data, K, wb._chan_ptrs(plain), None, None) == 0
+    assert same_bits(plain, out)
+
+
+def _sharded_setup(wb, world, N, K, B, C=2, seed=11, empty_rank=None):
+    """`world` engines on device 0, tracks dealt contiguously (whitebox_b200.shard.track_range); -> engines + data."""
+    from whitebox_b200 import shard
+    rng = np.random.RandomState(seed)
+    frames = K * B + 64
+    data = [sc._src(rng, 2, frames, 1) for _ in range(N)]  # hot: the summed bus reaches the clamp
+    gains = (0.2 + 0.6 * rng.rand(N, 2)).astype(np.float32)
+    clip_gain = (0.5 + 0.5 * rng.rand(N)).astype(np.float32)
+    devs, parts = [], []
+    for r in range(world):
+        lo, hi = shard.track_range(N, r, world)
+        if empty_rank == r:
+            hi = lo
+        dev = wb.DeviceEngine(0)
+        dev.configure(C, B, 48000)
+        dev.set_track_count(hi - lo)
+        dev.set_sum_mode(wb.SUM_EXACT)
+        segs = np.zeros(hi - lo, wb.SEGMENT_DTYPE)
+        for i, t in enumerate(range(lo, hi)):
+            sid = dev.sample_upload(data[t], 48000)
+            segs[i] = (i, 0, K, 0, B, sid, 3.0 if t % 2 else 0.0, 1.0 if t % 4 else 0.9, clip_gain[t], 0, 0.0, 0.0, 0.0, 0.0)
+        devs.append(dev)
+        parts.append((segs, gains[lo:hi].copy()))
+    return devs, parts
+
+
+@pytest.mark.parametrize("world,K,B,C", [(2, 8, 512, 2), (3, 7, 512, 2), (4, 2, 37, 2), (2, 5, 256, 1), (8, 3, 128, 2)])
+def test_sharded_peer_memory_exchange(wb, world, K, B, C):
+    """The sharded render (wbx_mix_sharded: tiles stored into the owners' exchange buffers, flag barrier, owner reduce
+    in rank order + clamp into rank 0's master bus) against the same partial buses mixed unclamped per shard and added
+    in rank order on the host — bit for bit — for even / ragged callback splits and mono / stereo buses."""
+    from whitebox_b200 import shard
+    N = 24
+    devs, parts = _sharded_setup(wb, world, N, K, B, C)
+    partial = []
+    for dev, (segs, gains) in zip(devs, parts):
+        dev.submit(segs, gains, K)
+        dev.mix(wb.MIX_NO_CLAMP)
+        partial.append(dev.fetch(True))
+    want = partial[0][0].copy()
+    for r in range(1, world):
+        want = (want + partial[r][0]).astype(np.float32)
+    assert np.abs(want).max() > 1.0, "fixture should reach the clamp"
+    want = np.where(want > 1, np.float32(1), np.where(want < -1, np.float32(-1), want)).astype(np.float32)
+    for r, dev in enumerate(devs):
+        dev.shard_init(r, world, K + 3)
+    for dev in devs:
+        dev.shard_connect_local(devs)
+    for rep in range(3):  # epochs advance; buffers are reused
+        for dev, (segs, gains) in zip(devs, parts):
+            dev.submit(segs, gains, K)
+        shard.mix_sharded_lockstep(devs)
+        out, pk0 = devs[0].fetch(True)
+        assert same_bits(out, want), "sharded master bus (repeat %d)" % rep
+        assert same_bits(pk0, partial[0][1])
+        for r in range(1, world):
+            _, pk = devs[r].fetch(True, want_bus=False)
+            assert same_bits(pk, partial[r][1]), "rank %d peaks" % r
+            with pytest.raises(wb.WbxError):
+                devs[r].fetch(False)  # only rank 0 holds the master bus
+    assert "peer-reduce" in devs[0].last_kernel()
+    assert devs[1].shard_info() == (1, world)
+    for dev in devs:
+        dev.shard_close()
+    assert devs[1].shard_info() == (0, 1)
+
+
+def test_sharded_rank_without_tracks_and_full_mix(wb):
+    """A rank whose shard is empty contributes silence; the sharded result stays within tolerance of one engine holding
+    every track (re-association across shards only)."""
+    world, N, K, B = 3, 18, 6, 512
+    devs, parts = _sharded_setup(wb, world, N, K, B, seed=3, empty_rank=1)
+    for r, dev in enumerate(devs):
+        dev.shard_init(r, world, K)
+    for dev in devs:
+        dev.shard_connect_local(devs)
+    from whitebox_b200 import shard
+    for dev, (segs, gains) in zip(devs, parts):
+        dev.submit(segs, gains, K)
+    shard.mix_sharded_lockstep(devs)
+    out, _ = devs[0].fetch(False)
+    devs[1].synchronize()
+    devs[2].synchronize()
+    # one engine with the tracks of ranks 0 and 2
+    one, parts1 = _sharded_setup(wb, 1, N, K, B, seed=3)
+    keep = [t for r in (0, 2) for t in range(*shard.track_range(N, r, world))]
+    segs, gains = parts1[0]
+    full, _ = one[0].render(segs[keep], gains, K)  # gains stay indexed by track id
+    peak = max(float(np.abs(full).max()), 1e-30)
+    assert np.abs(out.astype(np.float64) - full).max() <= TREE_TOL * peak
+
+
+def test_sharded_errors(wb):
+    dev = wb.DeviceEngine(0)
+    dev.configure(2, 512, 48000)
+    dev.set_track_count(0)
+    dev.submit(np.zeros(0, wb.SEGMENT_DTYPE), np.zeros((0, 2), np.float32), 2)
+    with pytest.raises(wb.WbxError):
+        dev.mix_sharded()  # not initialised
+    with pytest.raises(wb.WbxError):
+        dev.shard_init(3, 2, 8)  # rank >= world
+    dev.shard_init(0, 1, 1)
+    dev.shard_connect_local([dev])
+    with pytest.raises(wb.WbxError):
+        dev.mix_sharded()  # 2 callbacks > max_blocks 1
+    dev.shard_init(0, 1, 4)  # re-init replaces the block; world 1 is a plain clamp
+    dev.shard_connect_local([dev])
+    dev.mix_sharded()
+    out, _ = dev.fetch(False)
+    assert not out.any()
+
+
+def test_sharded_two_devices_one_process(wb):
+    """Two engines on two GPUs of one box, driven by one thread: real peer stores over NVLink (skipped on 1-GPU boxes;
+    the one-process-per-GPU form over CUDA IPC is what bench.py --gpus N runs)."""
+    import torch
+    from whitebox_b200 import shard
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.RandomState(21)
+    N, K, B, world = 16, 10, 512, 2
+    frames = K * B + 64
+    devs, parts, partial = [], [], []
+    for r in range(world):
+        lo, hi = shard.track_range(N, r, world)
+        dev = wb.DeviceEngine(r)
+        dev.configure(2, B, 48000)
+        dev.set_track_count(hi - lo)
+        dev.set_sum_mode(wb.SUM_EXACT)
+        segs = np.zeros(hi - lo, wb.SEGMENT_DTYPE)
+        for i in range(hi - lo):
+            sid = dev.sample_upload(sc._src(rng, 2, frames, 1), 48000)
+            segs[i] = (i, 0, K, 0, B, sid, 0.0, 1.0, 0.8, 0, 0.0, 0.0, 0.0, 0.0)
+        gains = np.full((hi - lo, 2), 0.4, np.float32)
+        dev.submit(segs, gains, K)
+        dev.mix(wb.MIX_NO_CLAMP)
+        partial.append(dev.fetch(False)[0])
+        devs.append(dev)
+        parts.append((segs, gains))
+    want = np.clip((partial[0] + partial[1]).astype(np.float32), np.float32(-1), np.float32(1))
+    for r, dev in enumerate(devs):
+        dev.shard_init(r, world, K)
+    for dev in devs:
+        dev.shard_connect_local(devs)
+    for _ in range(2):
+        for dev, (segs, gains) in zip(devs, parts):
+            dev.submit(segs, gains, K)
+        shard.mix_sharded_lockstep(devs)
+        out, _ = devs[0].fetch(False)
+        devs[1].synchronize()
+        assert same_bits(out, want)

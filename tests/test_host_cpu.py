@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(wb):
         assert sorted(listed) == declared, "python symbol list out of date for " + header
         for name in declared:
             assert hasattr(L, name), "%s declared in %s but not exported" % (name, header)
-    assert L.wbx_abi_version() == 2
+    assert L.wbx_abi_version() == 3
 
 
 def test_segment_struct_layout(wb):

@@ -51,6 +51,7 @@ SEGMENT_DTYPE = np.dtype([("track", "<u4"), ("block", "<u4"), ("n_blocks", "<u4"
                           ("fade_out_frames", "<f8"), ("clip_len_frames", "<f8")])
 assert SEGMENT_DTYPE.itemsize == C.sizeof(Segment) == 80
 SEG_FADE, SEG_POLYPHASE = 1, 2
+IPC_HANDLE_BYTES = 64
 
 # every symbol include/wbx.h and include/wbx_host.h declare
 WBX_SYMBOLS = [
@@ -58,7 +59,8 @@ WBX_SYMBOLS = [
     "wbx_set_sum_mode", "wbx_set_stream", "wbx_sample_upload", "wbx_sample_release", "wbx_sample_update", "wbx_sample_mipmap", "wbx_render", "wbx_submit",
     "wbx_mix", "wbx_fetch", "wbx_fetch_levels", "wbx_host_alloc", "wbx_host_free", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
     "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel", "wbx_effects_design", "wbx_set_track_effects",
-    "wbx_set_impulse_response",
+    "wbx_set_impulse_response", "wbx_render_levels", "wbx_shard_init", "wbx_shard_connect_ipc",
+    "wbx_shard_connect_local", "wbx_mix_sharded", "wbx_mix_sharded_phase", "wbx_shard_close", "wbx_shard_info",
 ]
 WBXH_SYMBOLS = [
     "wbxh_create", "wbxh_destroy", "wbxh_last_error", "wbxh_device", "wbxh_add_track", "wbxh_set_volume",
@@ -100,6 +102,14 @@ def lib():
     L.wbx_sample_update.argtypes = [vp, u32, pp]
     L.wbx_sample_mipmap.argtypes = [vp, u32, i32, i32, vp, u64, C.POINTER(u32)]
     L.wbx_render.argtypes = [vp, vp, u32, vp, u32, pp, vp]
+    L.wbx_render_levels.argtypes = [vp, vp, u32, vp, u32, pp, vp, vp]
+    L.wbx_shard_init.argtypes = [vp, u32, u32, u32, vp]
+    L.wbx_shard_connect_ipc.argtypes = [vp, vp]
+    L.wbx_shard_connect_local.argtypes = [vp, pp]
+    L.wbx_mix_sharded.argtypes = [vp]
+    L.wbx_mix_sharded_phase.argtypes = [vp, i32]
+    L.wbx_shard_close.argtypes = [vp]
+    L.wbx_shard_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     L.wbx_submit.argtypes = [vp, vp, u32, vp, u32]
     L.wbx_mix.argtypes = [vp, u32]
     L.wbx_fetch.argtypes = [vp, pp, vp]
@@ -294,11 +304,42 @@ class DeviceEngine:
     def mix(self, flags=0):
         self._ck(self.L.wbx_mix(self.h, flags))
 
-    def fetch(self, want_peaks=True):
-        out = np.empty((self.C, self.n_blocks * self.B), np.float32)
+    def fetch(self, want_peaks=True, want_bus=True):
+        out = np.empty((self.C, self.n_blocks * self.B), np.float32) if want_bus else None
         peaks = np.empty((self.n_blocks, self.n_tracks, 2), np.float32) if want_peaks else None
-        self._ck(self.L.wbx_fetch(self.h, _chan_ptrs(out), peaks.ctypes.data if want_peaks else None))
+        self._ck(self.L.wbx_fetch(self.h, _chan_ptrs(out) if want_bus else None,
+                                  peaks.ctypes.data if want_peaks else None))
         return out, peaks
+
+    # ---- sharded render (include/wbx.h "sharded render"): the bus exchange over peer memory ----------------
+    def shard_init(self, rank, world, max_blocks):
+        """-> this rank's CUDA IPC handle (64 bytes) for the other ranks' shard_connect_ipc."""
+        h = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._ck(self.L.wbx_shard_init(self.h, rank, world, max_blocks, h))
+        return h.raw
+
+    def shard_connect_ipc(self, handles):
+        """handles: list of `world` 64-byte handles, indexed by rank (one process per GPU)."""
+        blob = b"".join(handles)
+        assert len(blob) == IPC_HANDLE_BYTES * len(handles)
+        self._ck(self.L.wbx_shard_connect_ipc(self.h, blob))
+
+    def shard_connect_local(self, engines):
+        """engines: the `world` DeviceEngines of this process, indexed by rank (all after shard_init)."""
+        arr = (C.c_void_p * len(engines))(*[getattr(en.h, "value", en.h) for en in engines])
+        self._ck(self.L.wbx_shard_connect_local(self.h, arr))
+
+    def mix_sharded(self, phase=None):
+        """The collective sharded mix; phase 0/1/2 = its three stages (one thread driving several engines)."""
+        self._ck(self.L.wbx_mix_sharded(self.h) if phase is None else self.L.wbx_mix_sharded_phase(self.h, phase))
+
+    def shard_close(self):
+        self._ck(self.L.wbx_shard_close(self.h))
+
+    def shard_info(self):
+        r, w = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.wbx_shard_info(self.h, C.byref(r), C.byref(w)))
+        return r.value, w.value
 
     def fetch_levels(self):
         lv = np.zeros((self.n_tracks, 2), np.float32)
@@ -437,13 +478,14 @@ class Engine:
     def stop(self):
         self.L.wbxh_stop(self.h)
 
-    def render(self, n_blocks, want_peaks=True, out=None):
+    def render(self, n_blocks, want_peaks=True, out=None, want_bus=True):
         """-> (bus [C][n_blocks*B], peaks [n_blocks][N][2]) from one device launch. `out` may be a
-        caller-owned [C][n_blocks*B] f32 array (e.g. PinnedArray(...).array)."""
-        if out is None:
+        caller-owned [C][n_blocks*B] f32 array (e.g. PinnedArray(...).array: the kernel then writes it directly).
+        want_bus=False: ranks > 0 of a sharded setup, which do not receive the master bus."""
+        if out is None and want_bus:
             out = np.empty((self.C, n_blocks * self.B), np.float32)
         peaks = np.zeros((n_blocks, self.n_tracks, 2), np.float32) if want_peaks else None
-        self._ck(self.L.wbxh_render(self.h, n_blocks, _chan_ptrs(out),
+        self._ck(self.L.wbxh_render(self.h, n_blocks, _chan_ptrs(out) if want_bus else None,
                                     peaks.ctypes.data if (peaks is not None and self.n_tracks) else None))
         if self.dev is not None:  # keep the device view's shape in step (fetch / fetch_interleaved after render)
             self.dev.C, self.dev.B, self.dev.n_tracks, self.dev.n_blocks = self.C, self.B, self.n_tracks, n_blocks

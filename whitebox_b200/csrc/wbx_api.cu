@@ -32,6 +32,12 @@ cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
                            float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, const float* poly,
                            cudaStream_t stream);
+cudaError_t launch_shard_signal(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch, cudaStream_t stream);
+cudaError_t launch_shard_wait(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch,
+                              unsigned long long timeout_ns, uint32_t* status, cudaStream_t stream);
+cudaError_t launch_shard_reduce(const float* xchg, uint32_t W, uint32_t C, uint64_t plane, uint64_t valid,
+                                const ShardPeers& peers, uint64_t chan_stride, uint64_t dst_off, int n_sm,
+                                cudaStream_t stream);
 size_t fir_tc_tiles_bytes(uint32_t L);
 uint64_t fir_tc_plane_width(uint64_t H, uint64_t T);
 cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, cudaStream_t stream);
@@ -67,6 +73,21 @@ struct HostBuf {
   size_t cap = 0;
 };
 
+// Sharded render state: one device block per rank = [arrival words | exchange buffer | master bus],
+// visible to every peer rank (CUDA IPC across processes, peer access within one process).
+constexpr size_t kShardHeaderBytes = 4096;
+struct Shard {
+  bool on = false, connected = false;
+  uint32_t rank = 0, world = 1, max_blocks = 0, B = 0, C = 0;
+  void* block = nullptr;
+  size_t xchg_off = 0, bus_off = 0, bytes = 0;
+  void* peer_block[kMaxPeers] = {nullptr};
+  bool peer_ipc[kMaxPeers] = {false};
+  uint32_t epoch = 0;
+  uint32_t* status = nullptr;  // page-locked host word raised by a barrier that timed out
+  unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+};
+
 }  // namespace
 
 struct wbx_engine {
@@ -95,6 +116,12 @@ struct wbx_engine {
   uint32_t ir_taps = 0;              // convolution reverb: taps of the impulse response in d_ir
   uint32_t firhist_tracks = 0;       // tracks d_firhist is sized (and zeroed) for
   bool fir_tc = false;               // impulse response expanded for the tensor-core path (d_irtiles)
+  float* mirror[2] = {nullptr, nullptr};       // device view of page-locked caller channels the running render also writes
+  float* mirror_host[2] = {nullptr, nullptr};  // ... and the caller's pointers they belong to (wbx_render)
+  bool levels_queued = false;              // level reduce + copy into h_levels already enqueued for this mix
+  Shard shard;
+  bool shard_result = false;               // the last mix was sharded: the master bus is shard.block + bus_off (rank 0)
+  int shard_phase = 0;                     // next phase of the running sharded mix (0 = none running)
   char err[256] = {0};
   char kernel_name[64] = {0};
 };
@@ -253,6 +280,7 @@ int wbx_destroy(wbx_engine* e) {
   if (!e) return WBX_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  wbx_shard_close(e);
   for (auto& s : e->samples)
     if (s.live) {
       cudaFree(s.d_alloc);
@@ -351,7 +379,15 @@ int wbx_sample_upload(wbx_engine* e, int format, uint32_t channels, uint64_t fra
   return WBX_OK;
 }
 
-static bool is_pinned(const void* p);
+// true when p is page-locked host memory the device can copy to/from directly (cudaMallocHost / cudaHostRegister)
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
 
 int wbx_sample_update(wbx_engine* e, uint32_t id, const void* const* planar) {
   if (!e || !planar || id >= e->samples.size() || !e->samples[id].live) return fail(e, WBX_ERR_INVALID, "bad sample id");
@@ -764,15 +800,28 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   return WBX_OK;
 }
 
-int wbx_mix(wbx_engine* e, uint32_t flags) {
-  if (!e) return WBX_ERR_INVALID;
-  if (!e->submitted) return fail(e, WBX_ERR_INVALID, "wbx_mix before wbx_submit");
+static ShardPeers shard_peers(const Shard& sh) {
+  ShardPeers peers;
+  for (uint32_t j = 0; j < kMaxPeers; j++) {
+    peers.flags[j] = j < sh.world ? (uint32_t*)sh.peer_block[j] : nullptr;
+    peers.dst[j] = nullptr;
+  }
+  peers.dst[0] = (float*)((uint8_t*)sh.peer_block[0] + sh.bus_off);  // rank 0 holds the master bus
+  peers.n_dst = 1;
+  return peers;
+}
+
+static int do_mix(wbx_engine* e, uint32_t flags, bool sharded) {
   CU(e, cudaSetDevice(e->device));
   const uint32_t N = e->n_tracks, B = e->B, C = e->C, K = e->n_blocks;
   const size_t bus_floats = (size_t)C * K * B;
   const size_t peak_floats = (size_t)K * N * 2;
-  if (N == 0) {  // Engine::process with no tracks: output_buffer.clear() (engine.cpp:1598)
+  e->levels_queued = false;
+  e->shard_result = false;
+  if (N == 0 && !sharded) {  // Engine::process with no tracks: output_buffer.clear() (engine.cpp:1598)
     CU(e, cudaMemsetAsync(e->d_bus.p, 0, bus_floats * sizeof(float), e->stream));
+    for (uint32_t c = 0; c < C; c++)
+      if (e->mirror[c]) CU(e, cudaMemsetAsync(e->mirror[c], 0, (size_t)K * B * sizeof(float), e->stream));
     snprintf(e->kernel_name, sizeof(e->kernel_name), "clear");
     e->mixed = true;
     return WBX_OK;
@@ -782,8 +831,8 @@ int wbx_mix(wbx_engine* e, uint32_t flags) {
   choose_shape(e, K, &fpl, &groups);
   const uint32_t T = 32u * fpl;
   const uint32_t n_tiles = (B + T - 1) / T;
-  const uint32_t tpg = (N + groups - 1) / groups;
-  groups = (N + tpg - 1) / tpg;
+  const uint32_t tpg = N ? (N + groups - 1) / groups : 0;  // N == 0 (a sharded rank without tracks): silent tiles
+  groups = N ? (N + tpg - 1) / tpg : 1;
   int rc;
   const size_t n_counters = 1 + (size_t)K * n_tiles;
   if ((rc = dev_reserve(e, e->d_counters, n_counters * sizeof(uint32_t)))) return rc;
@@ -812,27 +861,125 @@ int wbx_mix(wbx_engine* e, uint32_t flags) {
   p.n_items = K * n_tiles * groups;
   p.clamp = (flags & WBX_MIX_NO_CLAMP) ? 0u : 1u;
   p.ext = e->seg_flags ? 1u : 0u;
+  p.mirror[0] = e->mirror[0];
+  p.mirror[1] = e->mirror[1];
+  for (uint32_t j = 0; j < kMaxPeers; j++) p.xchg[j] = nullptr;
+  p.shard_blocks = 0;
+  p.shard_rank = 0;
+  const Shard& sh = e->shard;
+  const uint32_t Ks = sharded ? (K + sh.world - 1) / sh.world : 0;
+  if (sharded) {
+    // every rank's unclamped tiles go straight into the owner's exchange buffer; the clamp follows the reduce
+    for (uint32_t j = 0; j < sh.world; j++) p.xchg[j] = (float*)((uint8_t*)sh.peer_block[j] + sh.xchg_off);
+    p.shard_blocks = Ks;
+    p.shard_rank = sh.rank;
+    p.clamp = 0;
+    p.mirror[0] = p.mirror[1] = nullptr;
+  }
   int ctas = 0;
   CU(e, launch_mix(p, fpl, e->n_sm, e->stream, &ctas));
   e->launches++;
-  snprintf(e->kernel_name, sizeof(e->kernel_name), "%s/fpl%d/g%u/ctas%d", groups == 1 ? "exact" : "tree", fpl, groups, ctas);
+  snprintf(e->kernel_name, sizeof(e->kernel_name), "%s/fpl%d/g%u/ctas%d%s", groups == 1 ? "exact" : "tree", fpl, groups, ctas,
+           sharded ? "/peer-reduce" : "");
+  if (sharded) {
+    // all of this rank's tiles are on their way into the owners' exchange buffers: tell every rank (phase 0 ends)
+    const ShardPeers peers = shard_peers(e->shard);
+    CU(e, launch_shard_signal(peers, sh.rank, sh.world, ++e->shard.epoch, e->stream));
+    e->launches++;
+    e->shard_phase = 1;
+    e->shard_result = true;
+  }
   e->mixed = true;
   return WBX_OK;
 }
 
-// true when p is page-locked host memory the device can copy to/from directly (cudaMallocHost / cudaHostRegister)
-static bool is_pinned(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
+// phase 1 of a sharded mix: wait until every rank's tiles have landed here, reduce this rank's slice of callbacks into
+// rank 0's master bus (rank order, then the clamp), tell every rank; phase 2: wait until every slice is in the master
+// bus — which also keeps a fast rank from overwriting an exchange buffer that is still being read.
+static int shard_phase(wbx_engine* e, int phase) {
+  Shard& sh = e->shard;
+  if (e->shard_phase != phase) return fail(e, WBX_ERR_INVALID, "sharded mix: phase %d called in phase %d", phase, e->shard_phase);
+  CU(e, cudaSetDevice(e->device));
+  const ShardPeers peers = shard_peers(sh);
+  CU(e, launch_shard_wait(peers, sh.rank, sh.world, sh.epoch, sh.timeout_ns, sh.status, e->stream));
+  e->launches++;
+  if (phase == 1) {
+    const uint32_t K = e->n_blocks, B = e->B;
+    const uint32_t Ks = (K + sh.world - 1) / sh.world;
+    const uint64_t k0 = (uint64_t)sh.rank * Ks;
+    const uint64_t valid = k0 < K ? ((k0 + Ks < K ? Ks : K - k0) * (uint64_t)B) : 0;
+    CU(e, launch_shard_reduce((const float*)((uint8_t*)sh.block + sh.xchg_off), sh.world, e->C, (uint64_t)Ks * B, valid, peers,
+                              (uint64_t)K * B, k0 * B, e->n_sm, e->stream));
+    CU(e, launch_shard_signal(peers, sh.rank, sh.world, ++sh.epoch, e->stream));
+    e->launches += valid ? 2 : 1;
+    e->shard_phase = 2;
+  } else {
+    e->shard_phase = 0;
   }
-  return a.type == cudaMemoryTypeHost;
+  return WBX_OK;
+}
+
+int wbx_mix(wbx_engine* e, uint32_t flags) {
+  if (!e) return WBX_ERR_INVALID;
+  if (!e->submitted) return fail(e, WBX_ERR_INVALID, "wbx_mix before wbx_submit");
+  return do_mix(e, flags, false);
+}
+
+int wbx_mix_sharded_phase(wbx_engine* e, int phase) {
+  if (!e) return WBX_ERR_INVALID;
+  if (phase == 1 || phase == 2) return shard_phase(e, phase);
+  if (phase != 0) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded_phase: phase %d", phase);
+  if (!e->submitted) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded before wbx_submit");
+  const Shard& sh = e->shard;
+  if (!sh.on || !sh.connected) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded: call wbx_shard_init and wbx_shard_connect_* first");
+  if (sh.B != e->B || sh.C != e->C) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded: engine reconfigured since wbx_shard_init");
+  if (e->n_blocks > sh.max_blocks)
+    return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded: %u callbacks > max_blocks %u of wbx_shard_init", e->n_blocks, sh.max_blocks);
+  if (e->shard_phase != 0) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded: the previous sharded mix stopped in phase %d", e->shard_phase);
+  return do_mix(e, 0, true);
+}
+
+int wbx_mix_sharded(wbx_engine* e) {
+  int rc = wbx_mix_sharded_phase(e, 0);
+  if (!rc) rc = wbx_mix_sharded_phase(e, 1);
+  if (!rc) rc = wbx_mix_sharded_phase(e, 2);
+  return rc;
+}
+
+// the bus the last mix produced: the engine's own, or — after a sharded mix — the master bus (rank 0 only)
+static float* result_bus(wbx_engine* e) {
+  if (!e->shard_result) return (float*)e->d_bus.p;
+  return e->shard.rank == 0 ? (float*)((uint8_t*)e->shard.block + e->shard.bus_off) : nullptr;
+}
+
+static int check_shard_status(wbx_engine* e) {
+  if (e->shard.on && e->shard.status && *e->shard.status) {
+    *e->shard.status = 0;
+    return fail(e, WBX_ERR_CUDA, "sharded render: a peer rank did not reach the bus exchange within %.1f s",
+                (double)e->shard.timeout_ns * 1e-9);
+  }
+  return WBX_OK;
+}
+
+// enqueue the VUMeter::level reduce of the last mix and its copy into page-locked h_levels (no synchronise)
+static int queue_levels(wbx_engine* e) {
+  const uint32_t NC = e->n_tracks * 2;
+  if (NC == 0 || e->levels_queued) return WBX_OK;
+  int rc;
+  if ((rc = dev_reserve(e, e->d_levels, NC * sizeof(float)))) return rc;
+  if ((rc = host_reserve(e, e->h_levels, NC * sizeof(float)))) return rc;
+  CU(e, cudaMemsetAsync(e->d_levels.p, 0, NC * sizeof(float), e->stream));
+  CU(e, launch_levels((const float*)e->d_peaks.p, e->n_blocks, NC, (float*)e->d_levels.p, e->stream));
+  e->launches++;
+  CU(e, cudaMemcpyAsync(e->h_levels.p, e->d_levels.p, NC * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  e->levels_queued = true;
+  return WBX_OK;
 }
 
 int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks) {
   if (!e) return WBX_ERR_INVALID;
   if (!e->mixed) return fail(e, WBX_ERR_INVALID, "wbx_fetch before wbx_mix");
+  if (e->shard_phase != 0) return fail(e, WBX_ERR_INVALID, "wbx_fetch: the sharded mix stopped in phase %d", e->shard_phase);
   CU(e, cudaSetDevice(e->device));
   const size_t chan_floats = (size_t)e->n_blocks * e->B;
   const size_t bus_floats = chan_floats * e->C;
@@ -840,15 +987,22 @@ int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks) {
   int rc;
   bool staged_bus = false, staged_peaks = false;
   if (out_channels) {
+    const float* bus = result_bus(e);
+    if (!bus) return fail(e, WBX_ERR_INVALID, "wbx_fetch: after a sharded mix only rank 0 holds the master bus");
     bool direct = true;  // page-locked caller buffers (wbx_host_alloc) take the D2H copy directly
-    for (uint32_t c = 0; c < e->C; c++) direct = direct && out_channels[c] && is_pinned(out_channels[c]);
-    if (direct) {
+    bool written = true;  // ... unless the mix kernel already wrote them (wbx_render's mirror)
+    for (uint32_t c = 0; c < e->C; c++) {
+      direct = direct && out_channels[c] && is_pinned(out_channels[c]);
+      written = written && out_channels[c] && e->mirror[c] && e->mirror_host[c] == out_channels[c];
+    }
+    if (written) {
+    } else if (direct) {
       for (uint32_t c = 0; c < e->C; c++)
-        CU(e, cudaMemcpyAsync(out_channels[c], (const float*)e->d_bus.p + c * chan_floats, chan_floats * sizeof(float),
+        CU(e, cudaMemcpyAsync(out_channels[c], bus + c * chan_floats, chan_floats * sizeof(float),
                               cudaMemcpyDeviceToHost, e->stream));
     } else {
       if ((rc = host_reserve(e, e->h_bus, bus_floats * sizeof(float)))) return rc;
-      CU(e, cudaMemcpyAsync(e->h_bus.p, e->d_bus.p, bus_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+      CU(e, cudaMemcpyAsync(e->h_bus.p, bus, bus_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
       staged_bus = true;
     }
   }
@@ -862,6 +1016,7 @@ int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks) {
     }
   }
   CU(e, cudaStreamSynchronize(e->stream));
+  if ((rc = check_shard_status(e))) return rc;
   if (staged_bus)
     for (uint32_t c = 0; c < e->C; c++)
       if (out_channels[c]) memcpy(out_channels[c], (const float*)e->h_bus.p + c * chan_floats, chan_floats * sizeof(float));
@@ -876,12 +1031,7 @@ int wbx_fetch_levels(wbx_engine* e, float* levels) {
   if (NC == 0) return WBX_OK;
   CU(e, cudaSetDevice(e->device));
   int rc;
-  if ((rc = dev_reserve(e, e->d_levels, NC * sizeof(float)))) return rc;
-  if ((rc = host_reserve(e, e->h_levels, NC * sizeof(float)))) return rc;
-  CU(e, cudaMemsetAsync(e->d_levels.p, 0, NC * sizeof(float), e->stream));
-  CU(e, launch_levels((const float*)e->d_peaks.p, e->n_blocks, NC, (float*)e->d_levels.p, e->stream));
-  e->launches++;
-  CU(e, cudaMemcpyAsync(e->h_levels.p, e->d_levels.p, NC * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  if ((rc = queue_levels(e))) return rc;  // no-op when wbx_render_levels / an earlier call already queued it
   CU(e, cudaStreamSynchronize(e->stream));
   memcpy(levels, e->h_levels.p, NC * sizeof(float));
   return WBX_OK;
@@ -919,7 +1069,9 @@ int wbx_fetch_interleaved(wbx_engine* e, void* dst, int dst_format) {
   int rc;
   if ((rc = dev_reserve(e, e->d_conv, bytes))) return rc;
   if ((rc = host_reserve(e, e->h_conv, bytes))) return rc;
-  CU(e, launch_interleave((const float*)e->d_bus.p, frames, e->C, dst_format, e->d_conv.p, e->n_sm, e->stream));
+  const float* bus = result_bus(e);
+  if (!bus) return fail(e, WBX_ERR_INVALID, "wbx_fetch_interleaved: after a sharded mix only rank 0 holds the master bus");
+  CU(e, launch_interleave(bus, frames, e->C, dst_format, e->d_conv.p, e->n_sm, e->stream));
   e->launches++;
   CU(e, cudaMemcpyAsync(e->h_conv.p, e->d_conv.p, bytes, cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaStreamSynchronize(e->stream));
@@ -927,17 +1079,167 @@ int wbx_fetch_interleaved(wbx_engine* e, void* dst, int dst_format) {
   return WBX_OK;
 }
 
-int wbx_render(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
-               uint32_t n_blocks, float* const* out_channels, float* peaks) {
+int wbx_render_levels(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
+                      uint32_t n_blocks, float* const* out_channels, float* peaks, float* levels) {
   int rc = wbx_submit(e, segs, n_segs, track_gains, n_blocks);
   if (rc) return rc;
-  if ((rc = wbx_mix(e, 0))) return rc;
-  return wbx_fetch(e, out_channels, peaks);
+  const bool sharded = e->shard.on && e->shard.connected;
+  // Page-locked caller channels (wbx_host_alloc) are written by the mix kernel itself, tile by tile, next to the
+  // device bus: no device-to-host copy of the bus follows the kernel.
+  bool direct = out_channels != nullptr && !sharded;
+  float* dview[2] = {nullptr, nullptr};
+  for (uint32_t c = 0; direct && c < e->C; c++) {
+    direct = out_channels[c] && is_pinned(out_channels[c]) &&
+             cudaHostGetDevicePointer((void**)&dview[c], out_channels[c], 0) == cudaSuccess && dview[c];
+    if (!direct) cudaGetLastError();
+  }
+  for (uint32_t c = 0; c < 2; c++) {
+    e->mirror[c] = (direct && c < e->C) ? dview[c] : nullptr;
+    e->mirror_host[c] = (direct && c < e->C) ? out_channels[c] : nullptr;
+  }
+  rc = sharded ? wbx_mix_sharded(e) : wbx_mix(e, 0);
+  if (!rc && levels) rc = queue_levels(e);
+  if (!rc) rc = wbx_fetch(e, (sharded && e->shard.rank != 0) ? nullptr : out_channels, peaks);  // the one synchronise
+  e->mirror[0] = e->mirror[1] = nullptr;
+  e->mirror_host[0] = e->mirror_host[1] = nullptr;
+  if (rc) return rc;
+  if (levels && e->n_tracks) memcpy(levels, e->h_levels.p, (size_t)e->n_tracks * 2 * sizeof(float));
+  return WBX_OK;
+}
+
+int wbx_render(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const float* track_gains,
+               uint32_t n_blocks, float* const* out_channels, float* peaks) {
+  return wbx_render_levels(e, segs, n_segs, track_gains, n_blocks, out_channels, peaks, nullptr);
+}
+
+// ---- sharded render (tracks split over the GPUs of one box) -------------------------------------------------------
+int wbx_shard_init(wbx_engine* e, uint32_t rank, uint32_t world, uint32_t max_blocks, void* ipc_handle_out) {
+  if (!e) return WBX_ERR_INVALID;
+  if (world < 1 || world > kMaxPeers || rank >= world || max_blocks == 0)
+    return fail(e, WBX_ERR_INVALID, "wbx_shard_init: rank %u / world %u (max %u) / max_blocks %u", rank, world, kMaxPeers,
+                max_blocks);
+  CU(e, cudaSetDevice(e->device));
+  int rc = wbx_shard_close(e);
+  if (rc) return rc;
+  Shard& sh = e->shard;
+  const size_t Ks = (max_blocks + world - 1) / world;
+  const size_t xchg_bytes = (((size_t)world * e->C * Ks * e->B * sizeof(float)) + 255) & ~(size_t)255;
+  const size_t bus_bytes = (((size_t)e->C * max_blocks * e->B * sizeof(float)) + 255) & ~(size_t)255;
+  sh.xchg_off = kShardHeaderBytes;
+  sh.bus_off = kShardHeaderBytes + xchg_bytes;
+  sh.bytes = sh.bus_off + bus_bytes;
+  cudaError_t err = cudaMalloc(&sh.block, sh.bytes);
+  if (err != cudaSuccess) return fail(e, WBX_ERR_NOMEM, "cudaMalloc(%zu) for the shard block failed: %s", sh.bytes, cudaGetErrorString(err));
+  CU(e, cudaMemset(sh.block, 0, sh.bytes));
+  if (cudaHostAlloc((void**)&sh.status, sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    cudaFree(sh.block);
+    sh.block = nullptr;
+    return fail(e, WBX_ERR_NOMEM, "cudaHostAlloc for the shard status word failed");
+  }
+  *sh.status = 0;
+  if (const char* t = getenv("WBX_SHARD_TIMEOUT_MS"))
+    if (atof(t) > 0) sh.timeout_ns = (unsigned long long)(atof(t) * 1e6);
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == WBX_IPC_HANDLE_BYTES, "IPC handle size");
+    err = cudaIpcGetMemHandle(&h, sh.block);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      memset(ipc_handle_out, 0, WBX_IPC_HANDLE_BYTES);  // same-process use (wbx_shard_connect_local) still works
+    } else {
+      memcpy(ipc_handle_out, &h, WBX_IPC_HANDLE_BYTES);
+    }
+  }
+  sh.rank = rank;
+  sh.world = world;
+  sh.max_blocks = max_blocks;
+  sh.B = e->B;
+  sh.C = e->C;
+  sh.epoch = 0;
+  sh.on = true;
+  sh.connected = false;
+  return WBX_OK;
+}
+
+int wbx_shard_connect_ipc(wbx_engine* e, const void* handles) {
+  if (!e || !handles) return WBX_ERR_INVALID;
+  Shard& sh = e->shard;
+  if (!sh.on) return fail(e, WBX_ERR_INVALID, "wbx_shard_connect_ipc before wbx_shard_init");
+  CU(e, cudaSetDevice(e->device));
+  for (uint32_t j = 0; j < sh.world; j++) {
+    if (j == sh.rank) {
+      sh.peer_block[j] = sh.block;
+      sh.peer_ipc[j] = false;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const uint8_t*)handles + (size_t)j * WBX_IPC_HANDLE_BYTES, sizeof(h));
+    cudaError_t err = cudaIpcOpenMemHandle(&sh.peer_block[j], h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      return fail(e, WBX_ERR_CUDA, "cudaIpcOpenMemHandle(rank %u) failed: %s", j, cudaGetErrorString(err));
+    }
+    sh.peer_ipc[j] = true;
+  }
+  sh.connected = true;
+  return WBX_OK;
+}
+
+int wbx_shard_connect_local(wbx_engine* e, wbx_engine* const* engines) {
+  if (!e || !engines) return WBX_ERR_INVALID;
+  Shard& sh = e->shard;
+  if (!sh.on) return fail(e, WBX_ERR_INVALID, "wbx_shard_connect_local before wbx_shard_init");
+  CU(e, cudaSetDevice(e->device));
+  for (uint32_t j = 0; j < sh.world; j++) {
+    const wbx_engine* pe = engines[j];
+    if (!pe || !pe->shard.on || pe->shard.world != sh.world || pe->shard.rank != j || pe->shard.bytes != sh.bytes)
+      return fail(e, WBX_ERR_INVALID, "wbx_shard_connect_local: engine %u is not rank %u of the same sharded setup", j, j);
+    if (pe->device != e->device) {
+      int can = 0;
+      CU(e, cudaDeviceCanAccessPeer(&can, e->device, pe->device));
+      if (!can) return fail(e, WBX_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", e->device, pe->device);
+      cudaError_t err = cudaDeviceEnablePeerAccess(pe->device, 0);
+      if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(e, WBX_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", pe->device, cudaGetErrorString(err));
+      cudaGetLastError();
+    }
+    sh.peer_block[j] = pe->shard.block;
+    sh.peer_ipc[j] = false;
+  }
+  sh.connected = true;
+  return WBX_OK;
+}
+
+int wbx_shard_close(wbx_engine* e) {
+  if (!e) return WBX_ERR_INVALID;
+  Shard& sh = e->shard;
+  if (!sh.on) return WBX_OK;
+  CU(e, cudaSetDevice(e->device));
+  CU(e, cudaStreamSynchronize(e->stream));
+  for (uint32_t j = 0; j < kMaxPeers; j++) {
+    if (sh.peer_ipc[j] && sh.peer_block[j]) cudaIpcCloseMemHandle(sh.peer_block[j]);
+    sh.peer_block[j] = nullptr;
+    sh.peer_ipc[j] = false;
+  }
+  if (sh.block) cudaFree(sh.block);
+  if (sh.status) cudaFreeHost(sh.status);
+  sh = Shard();
+  e->shard_result = false;
+  e->shard_phase = 0;
+  return WBX_OK;
+}
+
+int wbx_shard_info(const wbx_engine* e, uint32_t* rank, uint32_t* world) {
+  if (!e) return WBX_ERR_INVALID;
+  const bool on = e->shard.on && e->shard.connected;
+  if (rank) *rank = on ? e->shard.rank : 0;
+  if (world) *world = on ? e->shard.world : 1;
+  return WBX_OK;
 }
 
 int wbx_device_bus(wbx_engine* e, float** d_bus, uint64_t* n_floats) {
   if (!e || !e->submitted) return WBX_ERR_INVALID;
-  if (d_bus) *d_bus = (float*)e->d_bus.p;
+  if (d_bus) *d_bus = e->mixed ? result_bus(e) : (float*)e->d_bus.p;
   if (n_floats) *n_floats = (uint64_t)e->C * e->n_blocks * e->B;
   return WBX_OK;
 }
@@ -961,7 +1263,7 @@ int wbx_synchronize(wbx_engine* e) {
   if (!e) return WBX_ERR_INVALID;
   CU(e, cudaSetDevice(e->device));
   CU(e, cudaStreamSynchronize(e->stream));
-  return WBX_OK;
+  return check_shard_status(e);
 }
 
 uint64_t wbx_launch_count(const wbx_engine* e) { return e ? e->launches : 0; }

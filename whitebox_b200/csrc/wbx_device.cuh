@@ -89,6 +89,8 @@ struct DFx {
 };
 static_assert(sizeof(DFx) == 16 + 80 + 16 + 72 + 8, "DFx layout");
 
+constexpr uint32_t kMaxPeers = 16;  // ranks of one sharded render (one NVSwitch box has 8)
+
 struct MixParams {
   const DSpan* spans;
   const DCell* cells;
@@ -106,6 +108,21 @@ struct MixParams {
   uint32_t n_items;     // n_blocks * n_tiles * groups
   uint32_t clamp;       // apply the [-1, 1] clamp
   uint32_t ext;         // some segment carries an extension flag (fade / polyphase): use the full kernel build
+  // optional second destination of every bus tile: the caller's page-locked AudioBuffer channels, written from the
+  // kernel over PCIe (posted stores) so no device-to-host copy follows the mix. nullptr = off.
+  float* mirror[2];
+  // sharded render (tracks split over ranks): callback k belongs to owner rank k / shard_blocks and this
+  // rank's UNCLAMPED tile goes straight into the owner's exchange buffer (peer memory over NVLink),
+  // xchg[owner] laid out [src_rank][C][shard_blocks * B]. shard_blocks == 0 = off (tile goes to `bus`).
+  float* xchg[kMaxPeers];
+  uint32_t shard_blocks, shard_rank;
+};
+
+// ranks' views of one another for a sharded render (all pointers valid on this rank's device)
+struct ShardPeers {
+  uint32_t* flags[kMaxPeers];  // flags[j] = rank j's arrival words [kMaxPeers]
+  float* dst[kMaxPeers];       // master-bus copies the reduced slices are written to (dst[0..n_dst))
+  uint32_t n_dst;
 };
 
 }  // namespace wbx

@@ -562,18 +562,16 @@ int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, 
     t.effects_dirty = false;
   }
   schedule(n_blocks, sample_rate);
-  rc = wbx_submit(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n_blocks);
+  // submit + mix + bus/peaks/levels back under one synchronise; on an engine that is part of a sharded setup
+  // (wbx_shard_*) the mix is the sharded one and only rank 0 receives the master bus
+  if (N) levels_.resize((size_t)N * 2);
+  rc = wbx_render_levels(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n_blocks, out_channels, peaks,
+                         N ? levels_.data() : nullptr);
   if (rc) return rc;
-  if ((rc = wbx_mix(dev_, 0))) return rc;
-  if ((rc = wbx_fetch(dev_, out_channels, peaks))) return rc;
   // VUMeter::push_samples: level only rises until the UI reads it (vu_meter.h:25-29)
-  if (N) {
-    levels_.resize((size_t)N * 2);
-    if ((rc = wbx_fetch_levels(dev_, levels_.data()))) return rc;
-    for (uint32_t i = 0; i < N; i++)
-      for (uint32_t c = 0; c < 2; c++)
-        if (tracks[i]->level[c] < levels_[2 * i + c]) tracks[i]->level[c] = levels_[2 * i + c];
-  }
+  for (uint32_t i = 0; i < N; i++)
+    for (uint32_t c = 0; c < 2; c++)
+      if (tracks[i]->level[c] < levels_[2 * i + c]) tracks[i]->level[c] = levels_[2 * i + c];
   return WBX_OK;
 }
 

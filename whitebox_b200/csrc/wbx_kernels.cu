@@ -760,7 +760,20 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
     }
 
     // ---- bus write ------------------------------------------------------------------------------------
-    const size_t chan_stride = (size_t)p.n_blocks * p.B;
+    // destination of channel c of this tile: the planar device bus, or — sharded render — this rank's plane in the
+    // exchange buffer of the rank that owns callback k (a peer-memory store over NVLink, overlapped with the mix)
+    float* outp[2];
+    if (p.shard_blocks) {
+      const uint32_t owner = k / p.shard_blocks;
+      const size_t plane = (size_t)p.shard_blocks * p.B;
+      float* xb = p.xchg[owner] + (size_t)p.shard_rank * p.C * plane + (size_t)(k - owner * p.shard_blocks) * p.B + f0;
+      outp[0] = xb;
+      outp[1] = xb + plane;
+    } else {
+      const size_t chan_stride = (size_t)p.n_blocks * p.B;
+      outp[0] = p.bus + (size_t)k * p.B + f0;
+      outp[1] = outp[0] + chan_stride;
+    }
     const size_t out_off = (size_t)k * p.B + f0;
     const bool vec_ok = (p.B & 1u) == 0;  // frame pairs are 8-byte aligned in the planar bus
     if (p.groups == 1) {
@@ -771,17 +784,23 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
 #pragma unroll
         for (int c = 0; c < 2; c++) {
           if (c == 1 && !two) break;
-          float* out = p.bus + c * chan_stride + out_off;
+          float* out = outp[c];
           float x0 = v[c][0], x1 = v[c][1];
           if (p.clamp) {  // engine.cpp:1627-1636 (NaN passes)
             x0 = x0 > 1.0f ? 1.0f : (x0 < -1.0f ? -1.0f : x0);
             x1 = x1 > 1.0f ? 1.0f : (x1 < -1.0f ? -1.0f : x1);
           }
+          float* mir = p.mirror[c] ? p.mirror[c] + out_off : nullptr;
           if (vec_ok && fr + 1 < tile_len) {
             *reinterpret_cast<float2*>(out + fr) = make_float2(x0, x1);
+            if (mir) *reinterpret_cast<float2*>(mir + fr) = make_float2(x0, x1);
           } else {
             if (fr < tile_len) out[fr] = x0;
             if (fr + 1 < tile_len) out[fr + 1] = x1;
+            if (mir) {
+              if (fr < tile_len) mir[fr] = x0;
+              if (fr + 1 < tile_len) mir[fr + 1] = x1;
+            }
           }
         }
       }
@@ -804,7 +823,8 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
         __threadfence();
         const float2* base = reinterpret_cast<const float2*>(p.ws) + (size_t)tile_id * p.groups * 2 * (L::T / 2);
         for (int c = 0; c < (two ? 2 : 1); c++) {
-          float* out = p.bus + c * chan_stride + out_off;
+          float* out = outp[c];
+          float* mir = p.mirror[c] ? p.mirror[c] + out_off : nullptr;
           for (int i = 0; i < FPL / 2; i++) {
             const int q = lane + 32 * i;
             const int fr = 2 * q;
@@ -818,8 +838,17 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
               sum.x = sum.x > 1.0f ? 1.0f : (sum.x < -1.0f ? -1.0f : sum.x);
               sum.y = sum.y > 1.0f ? 1.0f : (sum.y < -1.0f ? -1.0f : sum.y);
             }
-            if (fr < tile_len) out[fr] = sum.x;
-            if (fr + 1 < tile_len) out[fr + 1] = sum.y;
+            if (vec_ok && fr + 1 < tile_len) {
+              *reinterpret_cast<float2*>(out + fr) = sum;
+              if (mir) *reinterpret_cast<float2*>(mir + fr) = sum;
+            } else {
+              if (fr < tile_len) out[fr] = sum.x;
+              if (fr + 1 < tile_len) out[fr + 1] = sum.y;
+              if (mir) {
+                if (fr < tile_len) mir[fr] = sum.x;
+                if (fr + 1 < tile_len) mir[fr + 1] = sum.y;
+              }
+            }
           }
         }
       }
@@ -1076,6 +1105,76 @@ __global__ void clamp_kernel(float* __restrict__ x, uint64_t n) {
       x[i] = 1.0f;
     else if (v < -1.0f)
       x[i] = -1.0f;
+  }
+}
+
+// ---- sharded render: exchange step over peer memory ------------------------------------------
+// Cross-GPU barrier in two halves. signal: lane j publishes `epoch` into rank j's arrival word for this rank (a peer
+// store, after a system-scope fence so this rank's earlier peer stores — the mix kernel's tiles, the reduced slices —
+// are visible first). wait: lane j spins until rank j's word here reaches `epoch`. Epochs only grow and a rank cannot
+// run two barriers ahead of a peer, so one word per pair suffices. A peer that never arrives (crashed process) must
+// not hang the GPU: after `timeout_ns` the wait gives up and raises *status (page-locked host word the API checks
+// after the next synchronise).
+__global__ void shard_signal_kernel(ShardPeers peers, uint32_t rank, uint32_t world, uint32_t epoch) {
+  __threadfence_system();
+  const uint32_t j = threadIdx.x;
+  if (j < world) *(volatile uint32_t*)(peers.flags[j] + rank) = epoch;
+}
+
+__global__ void shard_wait_kernel(ShardPeers peers, uint32_t rank, uint32_t world, uint32_t epoch,
+                                  unsigned long long timeout_ns, volatile uint32_t* status) {
+  const uint32_t j = threadIdx.x;
+  if (j < world) {
+    volatile uint32_t* mine = peers.flags[rank] + j;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int32_t)(*mine - epoch) < 0) {
+      __nanosleep(100);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {
+        *status = 1u;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+// Owner rank's reduce of its slice of callbacks: out = clamp(sum over source ranks 0..W-1, in rank order) — the bus sum
+// of AudioBuffer::mix continued across shards, then the clamp that must follow it (engine.cpp:1600-1617, 1627-1636).
+// xchg [W][C][plane] is this rank's exchange buffer (filled by every rank's mix kernel, read past L1: the lines were
+// written by peers); the result goes to dst[d] + c * chan_stride + dst_off (rank 0's master bus, a peer store).
+template <int V>
+__global__ void shard_reduce_kernel(const float* __restrict__ xchg, uint32_t W, uint32_t C, uint64_t plane, uint64_t valid,
+                                    ShardPeers peers, uint64_t chan_stride, uint64_t dst_off) {
+  const uint64_t n = valid / V;
+  for (uint32_t c = 0; c < C; c++) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+      float acc[V];
+#pragma unroll
+      for (int q = 0; q < V; q++) acc[q] = 0.0f;
+      for (uint32_t s = 0; s < W; s++) {
+        const float* src = xchg + ((size_t)s * C + c) * plane;
+        float v[V];
+        if constexpr (V == 4) {
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(src) + i);
+          v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+        } else {
+          v[0] = __ldcg(src + i);
+        }
+#pragma unroll
+        for (int q = 0; q < V; q++) acc[q] = s == 0 ? v[q] : __fadd_rn(acc[q], v[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < V; q++) acc[q] = acc[q] > 1.0f ? 1.0f : (acc[q] < -1.0f ? -1.0f : acc[q]);  // NaN passes
+      for (uint32_t d = 0; d < peers.n_dst; d++) {
+        float* out = peers.dst[d] + (size_t)c * chan_stride + dst_off;
+        if constexpr (V == 4)
+          reinterpret_cast<float4*>(out)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else
+          out[i] = acc[0];
+      }
+    }
   }
 }
 
@@ -1359,6 +1458,32 @@ cudaError_t launch_levels(const float* peaks, uint32_t K, uint32_t NC, float* le
   const uint32_t chunk = 32;
   const uint64_t threads = (uint64_t)((K + chunk - 1) / chunk) * NC;
   level_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(peaks, K, NC, chunk, levels);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_shard_signal(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch, cudaStream_t stream) {
+  shard_signal_kernel<<<1, 32, 0, stream>>>(peers, rank, world, epoch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_shard_wait(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch,
+                              unsigned long long timeout_ns, uint32_t* status, cudaStream_t stream) {
+  shard_wait_kernel<<<1, 32, 0, stream>>>(peers, rank, world, epoch, timeout_ns, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_shard_reduce(const float* xchg, uint32_t W, uint32_t C, uint64_t plane, uint64_t valid,
+                                const ShardPeers& peers, uint64_t chan_stride, uint64_t dst_off, int n_sm,
+                                cudaStream_t stream) {
+  if (valid == 0) return cudaSuccess;
+  const bool v4 = (plane % 4 == 0) && (valid % 4 == 0) && (chan_stride % 4 == 0) && (dst_off % 4 == 0);
+  const uint64_t n = v4 ? valid / 4 : valid;
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > (uint64_t)n_sm * 8) blocks = (uint64_t)n_sm * 8;
+  if (v4)
+    shard_reduce_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(xchg, W, C, plane, valid, peers, chan_stride, dst_off);
+  else
+    shard_reduce_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(xchg, W, C, plane, valid, peers, chan_stride, dst_off);
   return cudaGetLastError();
 }
 

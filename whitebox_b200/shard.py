@@ -39,3 +39,10 @@ def mix_sharded(dev, dist, world):
 def clamp_bus(x):
     """engine.cpp:1627-1636 on a host array (used by the CPU tests of the sharded path)."""
     return np.where(x > np.float32(1.0), np.float32(1.0), np.where(x < np.float32(-1.0), np.float32(-1.0), x)).astype(np.float32)
+
+
+def mix_sharded_lockstep(devs):
+    """One thread driving all ranks' engines (same process): the three phases of the collective in lock step."""
+    for phase in (0, 1, 2):
+        for d in devs:
+            d.mix_sharded(phase)
