@@ -38,6 +38,9 @@ cudaError_t launch_shard_wait(const ShardPeers& peers, uint32_t rank, uint32_t w
 cudaError_t launch_shard_reduce(const float* xchg, uint32_t W, uint32_t C, uint64_t plane, uint64_t valid,
                                 const ShardPeers& peers, uint64_t chan_stride, uint64_t dst_off, int n_sm,
                                 cudaStream_t stream);
+cudaError_t launch_ingest(const void* host_table, void* table, size_t table_bytes, void* zero, size_t zero_bytes,
+                          cudaStream_t stream);
+cudaError_t launch_levels_direct(const float* peaks, uint32_t K, uint32_t NC, float* levels_host, cudaStream_t stream);
 size_t fir_tc_tiles_bytes(uint32_t L);
 uint64_t fir_tc_plane_width(uint64_t H, uint64_t T);
 cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, cudaStream_t stream);
@@ -97,8 +100,17 @@ struct wbx_engine {
   uint32_t C = 2, B = 512, rate = 48000, n_tracks = 0;
   int sum_mode = WBX_SUM_AUTO;
   std::vector<SampleRec> samples;
-  DevBuf d_spans, d_gains, d_cells, d_bus, d_peaks, d_ws, d_counters, d_conv, d_upload, d_levels, d_fx, d_trackbuf, d_ir, d_firhist, d_firin, d_irtiles, d_firplanes, d_poly;
-  HostBuf h_spans, h_gains, h_bus, h_peaks, h_conv, h_levels, h_fx;
+  DevBuf d_spans, d_cells, d_bus, d_zero, d_ws, d_conv, d_upload, d_fx, d_trackbuf, d_ir, d_firhist, d_firin, d_irtiles, d_firplanes, d_poly;
+  HostBuf h_spans, h_bus, h_peaks, h_conv, h_levels, h_fx;
+  // views into d_spans (the submitted table: spans | gains | cells of a one-callback render) and d_zero (the region one
+  // memset clears before a mix: work counters | peaks | levels)
+  float* gains_ptr = nullptr;
+  DCell* cells_ptr = nullptr;
+  uint32_t* counters_ptr = nullptr;
+  float* peaks_ptr = nullptr;
+  float* levels_ptr = nullptr;
+  // one-callback render: table bytes the next mix's ingest kernel still has to pull from h_spans (0 = already on the device)
+  size_t ingest_bytes = 0;
   std::vector<uint32_t> slot_busy;  // [track][slot] -> first free block
   uint32_t slot_cap = 0;
   // last submit
@@ -177,6 +189,33 @@ int host_reserve(wbx_engine* e, HostBuf& b, size_t bytes) {
   return WBX_OK;
 }
 
+// grow a page-locked buffer while keeping its first keep_bytes
+int host_reserve_keep(wbx_engine* e, HostBuf& b, size_t bytes, size_t keep_bytes) {
+  if (bytes <= b.cap) return WBX_OK;
+  void* np = nullptr;
+  const size_t cap = bytes + bytes / 4 + 256;
+  if (cudaMallocHost(&np, cap) != cudaSuccess) return fail(e, WBX_ERR_NOMEM, "cudaMallocHost(%zu) failed", cap);
+  if (b.p) {
+    CU(e, cudaStreamSynchronize(e->stream));
+    memcpy(np, b.p, keep_bytes < b.cap ? keep_bytes : b.cap);
+    CU(e, cudaFreeHost(b.p));
+  }
+  b.p = np;
+  b.cap = cap;
+  return WBX_OK;
+}
+
+// num_actual_samples of one Sampler::stream call — the host twin of clipped_length in wbx_kernels.cu (same IEEE
+// operations; this file is built with -ffp-contract=off): min(n, (uint32)ceil((count - offset) / speed)), sampler.cpp:102-104
+uint32_t host_clipped_length(double cnt, double pos, double speed, uint32_t length) {
+  const double safe = ((double)length + 1.0) * speed;
+  const double rem = cnt - pos;
+  if (rem >= safe) return length;
+  const double m = std::ceil(rem / speed);
+  const uint32_t mm = m >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)m;
+  return mm < length ? mm : length;
+}
+
 uint32_t esize_of(int fmt) {
   switch (fmt) {
     case WBX_FMT_I16: return 2;
@@ -210,7 +249,7 @@ void choose_shape(const wbx_engine* e, uint32_t n_blocks, int* fpl_out, uint32_t
   bool tree = e->sum_mode == WBX_SUM_TREE || (e->sum_mode == WBX_SUM_AUTO && items < warps);
   if (tree && N > 32) {
     long want = (2 * warps + items - 1) / items;  // ~2 items per resident warp
-    long max_groups = (N + 31) / 32;              // at least 32 tracks per group
+    long max_groups = (N + 15) / 16;              // at least 16 tracks per group
     if (want > max_groups) want = max_groups;
     if (want < 1) want = 1;
     groups = (uint32_t)want;
@@ -287,10 +326,10 @@ int wbx_destroy(wbx_engine* e) {
       for (int q = 0; q < 2; q++)
         if (s.d_mip[q]) cudaFree(s.d_mip[q]);
     }
-  for (DevBuf* b : {&e->d_spans, &e->d_gains, &e->d_cells, &e->d_bus, &e->d_peaks, &e->d_ws, &e->d_counters, &e->d_conv,
-                    &e->d_upload, &e->d_levels, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin, &e->d_irtiles, &e->d_firplanes, &e->d_poly})
+  for (DevBuf* b : {&e->d_spans, &e->d_cells, &e->d_bus, &e->d_zero, &e->d_ws, &e->d_conv,
+                    &e->d_upload, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin, &e->d_irtiles, &e->d_firplanes, &e->d_poly})
     if (b->p) cudaFree(b->p);
-  for (HostBuf* b : {&e->h_spans, &e->h_gains, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
+  for (HostBuf* b : {&e->h_spans, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
     if (b->p) cudaFreeHost(b->p);
   cudaStreamDestroy(e->own_stream);
   delete e;
@@ -666,12 +705,17 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   // ---- validate + resolve segments into spans (pinned staging), assign cell slots --------------------
   if ((rc = sync_effects(e))) return rc;
   const uint32_t n_fx = e->n_fx;
-  if ((rc = host_reserve(e, e->h_spans, (size_t)(n_segs + n_fx + 1) * sizeof(DSpan)))) return rc;
-  if ((rc = host_reserve(e, e->h_gains, (size_t)(N ? N : 1) * 2 * sizeof(float)))) return rc;
+  // one page-locked table, one H2D copy: spans | track gains | (one-callback render: the cells, written here on the
+  // host — a callback is one Sampler::stream call per segment, nothing to replay — so no cell memset / expand kernel)
+  const size_t span_bytes = (size_t)(n_segs + n_fx + 1) * sizeof(DSpan);
+  const size_t gain_bytes = (((size_t)N * 2 * sizeof(float)) + 15) & ~(size_t)15;
+  const bool host_cells = n_blocks == 1;
+  if (e->slot_cap == 0) e->slot_cap = 2;
+  if ((rc = host_reserve(e, e->h_spans, span_bytes + gain_bytes + (host_cells ? (size_t)N * e->slot_cap * sizeof(DCell) : 0))))
+    return rc;
   DSpan* hs = (DSpan*)e->h_spans.p;
   uint32_t slots = 1;
   uint32_t seg_flags = 0;
-  if (e->slot_cap == 0) e->slot_cap = 2;
   if (e->slot_busy.size() < (size_t)N * e->slot_cap) e->slot_busy.resize((size_t)N * e->slot_cap);
   std::fill(e->slot_busy.begin(), e->slot_busy.end(), 0u);
   for (uint32_t i = 0; i < n_segs; i++) {
@@ -728,13 +772,26 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     d.fade_out = fade ? sg.fade_out_frames : 0.0;
     d.clip_len = fade ? sg.clip_len_frames : 0.0;
   }
-  if (N) memcpy(e->h_gains.p, track_gains, (size_t)N * 2 * sizeof(float));
-
   // ---- device buffers ------------------------------------------------------------------------------
   const size_t n_cells = (size_t)n_blocks * N * slots;
+  const size_t cell_bytes = host_cells ? n_cells * sizeof(DCell) : 0;
+  if ((rc = host_reserve_keep(e, e->h_spans, span_bytes + gain_bytes + cell_bytes, span_bytes))) return rc;
+  hs = (DSpan*)e->h_spans.p;
+  if (N) memcpy((uint8_t*)hs + span_bytes, track_gains, (size_t)N * 2 * sizeof(float));
+  if (host_cells && n_cells) {
+    DCell* hc = (DCell*)((uint8_t*)hs + span_bytes + gain_bytes);
+    memset(hc, 0xFF, cell_bytes);  // span = kSilent
+    for (uint32_t i = 0; i < n_segs; i++) {
+      const DSpan& d = hs[i];
+      if (d.pos0 >= (double)d.count) continue;  // has finished streaming (sampler.cpp:99-100)
+      DCell& c = hc[(size_t)d.track * slots + d.slot];
+      c.pos = d.pos0;
+      c.span = i;
+      c.n_act = host_clipped_length((double)d.count, d.pos0, d.speed, d.length);
+    }
+  }
   const size_t bus_floats = (size_t)C * n_blocks * B;
-  const size_t peak_floats = (size_t)n_blocks * N * 2;
-  if ((rc = dev_reserve(e, e->d_spans, (size_t)(n_segs + n_fx + 1) * sizeof(DSpan)))) return rc;
+  if ((rc = dev_reserve(e, e->d_spans, span_bytes + gain_bytes + cell_bytes))) return rc;
   if (n_fx) {
     // tracks with an effect chain are rendered to a per-track buffer (frame-interleaved stereo f32) that the mix
     // kernel then reads as one whole-block unity-speed call per callback with clip gain 1.0
@@ -759,18 +816,23 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
       d.nch = 2;
     }
   }
-  if ((rc = dev_reserve(e, e->d_gains, (size_t)(N ? N : 1) * 2 * sizeof(float)))) return rc;
-  if ((rc = dev_reserve(e, e->d_cells, (n_cells ? n_cells : 1) * sizeof(DCell)))) return rc;
+  if (!host_cells && (rc = dev_reserve(e, e->d_cells, (n_cells ? n_cells : 1) * sizeof(DCell)))) return rc;
   if ((rc = dev_reserve(e, e->d_bus, bus_floats * sizeof(float)))) return rc;
-  if ((rc = dev_reserve(e, e->d_peaks, (peak_floats ? peak_floats : 1) * sizeof(float)))) return rc;
+  e->gains_ptr = (float*)((uint8_t*)e->d_spans.p + span_bytes);
+  e->cells_ptr = host_cells ? (DCell*)((uint8_t*)e->d_spans.p + span_bytes + gain_bytes) : (DCell*)e->d_cells.p;
 
-  if (n_segs + n_fx)
-    CU(e, cudaMemcpyAsync(e->d_spans.p, hs, (size_t)(n_segs + n_fx) * sizeof(DSpan), cudaMemcpyHostToDevice, e->stream));
-  if (N) CU(e, cudaMemcpyAsync(e->d_gains.p, e->h_gains.p, (size_t)N * 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  if (n_cells) CU(e, cudaMemsetAsync(e->d_cells.p, 0xFF, n_cells * sizeof(DCell), e->stream));  // span = kSilent
-  if (n_segs && N) {
-    CU(e, launch_expand((const DSpan*)e->d_spans.p, n_segs, (DCell*)e->d_cells.p, N, slots, e->stream));
-    e->launches++;
+  // a one-callback render without effect chains leaves the table to the mix's ingest kernel (kernels only, no copy engine)
+  e->ingest_bytes = 0;
+  if (host_cells && !n_fx && !getenv("WBX_NO_INGEST"))
+    e->ingest_bytes = (span_bytes + gain_bytes + cell_bytes + 15) & ~(size_t)15;
+  else
+    CU(e, cudaMemcpyAsync(e->d_spans.p, hs, span_bytes + gain_bytes + cell_bytes, cudaMemcpyHostToDevice, e->stream));
+  if (!host_cells) {
+    if (n_cells) CU(e, cudaMemsetAsync(e->d_cells.p, 0xFF, n_cells * sizeof(DCell), e->stream));  // span = kSilent
+    if (n_segs && N) {
+      CU(e, launch_expand((const DSpan*)e->d_spans.p, n_segs, e->cells_ptr, N, slots, e->stream));
+      e->launches++;
+    }
   }
   if (n_fx && N) {
     const bool reverb = e->ir_taps > 0 && e->firhist_tracks == N;
@@ -785,7 +847,7 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
       const uint64_t W = fir_tc_plane_width(e->ir_taps - 1, (uint64_t)n_blocks * B);
       if ((rc = dev_reserve(e, e->d_firplanes, (size_t)3 * n_fx * C * W * 2 + 256))) return rc;
     }
-    CU(e, launch_effects((const DSpan*)e->d_spans.p, (DCell*)e->d_cells.p, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
+    CU(e, launch_effects((const DSpan*)e->d_spans.p, e->cells_ptr, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
                          n_segs, (float*)e->d_trackbuf.p, rv ? (const float*)e->d_ir.p : nullptr, rv ? e->ir_taps : 0,
                          (float*)e->d_firhist.p, (float*)e->d_firin.p, tc ? e->d_irtiles.p : nullptr,
                          tc ? e->d_firplanes.p : nullptr, (const float*)e->d_poly.p, e->stream));
@@ -834,22 +896,38 @@ static int do_mix(wbx_engine* e, uint32_t flags, bool sharded) {
   const uint32_t tpg = N ? (N + groups - 1) / groups : 0;  // N == 0 (a sharded rank without tracks): silent tiles
   groups = N ? (N + tpg - 1) / tpg : 1;
   int rc;
+  // one zero-filled region per mix: work / arrival counters | block peaks | levels
   const size_t n_counters = 1 + (size_t)K * n_tiles;
-  if ((rc = dev_reserve(e, e->d_counters, n_counters * sizeof(uint32_t)))) return rc;
+  const size_t counter_bytes = ((n_counters * sizeof(uint32_t)) + 255) & ~(size_t)255;
+  const size_t peak_bytes = ((peak_floats * sizeof(float)) + 255) & ~(size_t)255;
+  const size_t level_bytes = (size_t)N * 2 * sizeof(float);
+  if ((rc = dev_reserve(e, e->d_zero, counter_bytes + peak_bytes + level_bytes + 256))) return rc;
   if (groups > 1)
     if ((rc = dev_reserve(e, e->d_ws, (size_t)K * n_tiles * groups * 2 * T * sizeof(float)))) return rc;
-  CU(e, cudaMemsetAsync(e->d_counters.p, 0, n_counters * sizeof(uint32_t), e->stream));
-  CU(e, cudaMemsetAsync(e->d_peaks.p, 0, peak_floats * sizeof(float), e->stream));
+  e->counters_ptr = (uint32_t*)e->d_zero.p;
+  e->peaks_ptr = (float*)((uint8_t*)e->d_zero.p + counter_bytes);
+  e->levels_ptr = (float*)((uint8_t*)e->d_zero.p + counter_bytes + peak_bytes);
+  const size_t zero_bytes = (counter_bytes + peak_bytes + level_bytes + 15) & ~(size_t)15;
+  void* host_view = nullptr;
+  if (e->ingest_bytes && cudaHostGetDevicePointer(&host_view, e->h_spans.p, 0) == cudaSuccess && host_view) {
+    CU(e, launch_ingest(host_view, e->d_spans.p, e->ingest_bytes, e->d_zero.p, zero_bytes, e->stream));
+    e->launches++;
+  } else {
+    if (e->ingest_bytes)
+      CU(e, cudaMemcpyAsync(e->d_spans.p, e->h_spans.p, e->ingest_bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaMemsetAsync(e->d_zero.p, 0, zero_bytes, e->stream));
+  }
+  e->ingest_bytes = 0;
 
   MixParams p;
   p.spans = (const DSpan*)e->d_spans.p;
-  p.cells = (const DCell*)e->d_cells.p;
-  p.gains = (const float*)e->d_gains.p;
+  p.cells = e->cells_ptr;
+  p.gains = e->gains_ptr;
   p.poly = (const float*)e->d_poly.p;
   p.bus = (float*)e->d_bus.p;
-  p.peaks = (float*)e->d_peaks.p;
+  p.peaks = e->peaks_ptr;
   p.ws = (float*)e->d_ws.p;
-  p.counters = (uint32_t*)e->d_counters.p;
+  p.counters = e->counters_ptr;
   p.n_tracks = N;
   p.n_blocks = K;
   p.slots = e->slots;
@@ -966,12 +1044,18 @@ static int queue_levels(wbx_engine* e) {
   const uint32_t NC = e->n_tracks * 2;
   if (NC == 0 || e->levels_queued) return WBX_OK;
   int rc;
-  if ((rc = dev_reserve(e, e->d_levels, NC * sizeof(float)))) return rc;
   if ((rc = host_reserve(e, e->h_levels, NC * sizeof(float)))) return rc;
-  CU(e, cudaMemsetAsync(e->d_levels.p, 0, NC * sizeof(float), e->stream));
-  CU(e, launch_levels((const float*)e->d_peaks.p, e->n_blocks, NC, (float*)e->d_levels.p, e->stream));
-  e->launches++;
-  CU(e, cudaMemcpyAsync(e->h_levels.p, e->d_levels.p, NC * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  void* host_view = nullptr;
+  if (e->n_blocks <= 32 && cudaHostGetDevicePointer(&host_view, e->h_levels.p, 0) == cudaSuccess && host_view) {
+    // few callbacks: one thread per (track, channel) stores its level straight into the page-locked result
+    CU(e, launch_levels_direct(e->peaks_ptr, e->n_blocks, NC, (float*)host_view, e->stream));
+    e->launches++;
+  } else {
+    // levels were zeroed with the rest of the mix's zero region; the reduce is a max, so running it twice is harmless
+    CU(e, launch_levels(e->peaks_ptr, e->n_blocks, NC, e->levels_ptr, e->stream));
+    e->launches++;
+    CU(e, cudaMemcpyAsync(e->h_levels.p, e->levels_ptr, NC * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  }
   e->levels_queued = true;
   return WBX_OK;
 }
@@ -1008,10 +1092,10 @@ int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks) {
   }
   if (peaks && peak_floats) {
     if (is_pinned(peaks)) {
-      CU(e, cudaMemcpyAsync(peaks, e->d_peaks.p, peak_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+      CU(e, cudaMemcpyAsync(peaks, e->peaks_ptr, peak_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     } else {
       if ((rc = host_reserve(e, e->h_peaks, peak_floats * sizeof(float)))) return rc;
-      CU(e, cudaMemcpyAsync(e->h_peaks.p, e->d_peaks.p, peak_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+      CU(e, cudaMemcpyAsync(e->h_peaks.p, e->peaks_ptr, peak_floats * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
       staged_peaks = true;
     }
   }
@@ -1245,8 +1329,8 @@ int wbx_device_bus(wbx_engine* e, float** d_bus, uint64_t* n_floats) {
 }
 
 int wbx_device_peaks(wbx_engine* e, float** d_peaks, uint64_t* n_floats) {
-  if (!e || !e->submitted) return WBX_ERR_INVALID;
-  if (d_peaks) *d_peaks = (float*)e->d_peaks.p;
+  if (!e || !e->mixed) return WBX_ERR_INVALID;
+  if (d_peaks) *d_peaks = e->peaks_ptr;
   if (n_floats) *n_floats = (uint64_t)e->n_blocks * e->n_tracks * 2;
   return WBX_OK;
 }

@@ -516,19 +516,22 @@ int Engine::schedule(uint32_t n_blocks, double sample_rate) {
   // Tracks are independent until the bus sum, so walk each track through all callbacks in turn; callbacks
   // that provably hold no event for the track are skipped in closed form (fast_forward).
   for (uint32_t i = 0; i < N; i++) {
+    if (i + 2 < N) __builtin_prefetch(tracks[i + 2]);
     Track& t = *tracks[i];
     t.open_run = -1;
     uint32_t k = 0;
     while (k < K) {
-      track_block(t, i, k, sample_rate, current_beat_duration, blk_start_[k], blk_end_[k], blk_spos_[k],
-                  currently_playing);
-      k++;
-      if (!fast_forward || k >= K) continue;
-      const uint32_t q = quiet_blocks(t, k, K);
+      // event-free callbacks (the steady state of every playing or idle track): Track::process reduces to one
+      // whole-block Sampler::stream call per callback, taken in closed form without walking process_event
+      const uint32_t q = fast_forward ? quiet_blocks(t, k, K) : 0;
       if (q) {
         if (currently_playing) stream_run(t, i, k, q);
         k += q;
+        continue;
       }
+      track_block(t, i, k, sample_rate, current_beat_duration, blk_start_[k], blk_end_[k], blk_spos_[k],
+                  currently_playing);
+      k++;
     }
   }
   // gain used this render = (mute ? 0 : volume) * pan_coeffs[ch]   (track.cpp:728-731)

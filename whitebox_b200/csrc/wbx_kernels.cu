@@ -828,11 +828,20 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
           for (int i = 0; i < FPL / 2; i++) {
             const int q = lane + 32 * i;
             const int fr = 2 * q;
+            // partials added in group order; loads issued eight groups at a time so their latencies overlap
             float2 sum = make_float2(0.f, 0.f);
-            for (uint32_t gg = 0; gg < p.groups; gg++) {
-              const float2 v = __ldcg(base + ((size_t)gg * 2 + c) * (L::T / 2) + q);
-              sum.x = __fadd_rn(sum.x, v.x);
-              sum.y = __fadd_rn(sum.y, v.y);
+            for (uint32_t g0 = 0; g0 < p.groups; g0 += 8) {
+              float2 v[8];
+#pragma unroll
+              for (uint32_t u = 0; u < 8; u++)
+                v[u] = (g0 + u < p.groups) ? __ldcg(base + ((size_t)(g0 + u) * 2 + c) * (L::T / 2) + q) : make_float2(0.f, 0.f);
+#pragma unroll
+              for (uint32_t u = 0; u < 8; u++) {
+                if (g0 + u < p.groups) {
+                  sum.x = __fadd_rn(sum.x, v[u].x);
+                  sum.y = __fadd_rn(sum.y, v[u].y);
+                }
+              }
             }
             if (p.clamp) {
               sum.x = sum.x > 1.0f ? 1.0f : (sum.x < -1.0f ? -1.0f : sum.x);
@@ -972,47 +981,224 @@ __device__ __forceinline__ float fx_sample(float x, FxChannel& st, const float (
   return x;
 }
 
-__global__ void effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t frames,
-                               float* __restrict__ trackbuf) {
-  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= n_fx * C) return;
-  const uint32_t e = id / C, c = id % C;
-  DFx* f = fx + e;
-  float* buf = trackbuf + (size_t)e * frames * 2 + c;  // this channel: every second float
-  const bool eq_on = f->eq_on != 0, comp_on = f->comp_on != 0;
-  float b0[4], b1[4], b2[4], a1[4], a2[4];
-  FxChannel st;
-#pragma unroll
-  for (int b = 0; b < 4; b++) {
-    b0[b] = f->b0[b];
-    b1[b] = f->b1[b];
-    b2[b] = f->b2[b];
-    a1[b] = f->a1[b];
-    a2[b] = f->a2[b];
-    st.s1[b] = f->s1[c][b];
-    st.s2[b] = f->s2[c][b];
+// The memoryless part of the compressor: gain from the envelope, applied with the make-up gain.
+__device__ __forceinline__ float fx_gain(float x, float env, float thr, float makeup, uint32_t code) {
+  float g = 1.0f;
+  if (env > thr) {
+    const float r = __fdiv_rn(thr, env);
+    const float r2 = __fsqrt_rn(r);
+    switch (code) {
+      case 1: g = r2; break;
+      case 2: g = __fmul_rn(r2, __fsqrt_rn(r2)); break;
+      case 3: g = __fmul_rn(__fmul_rn(r2, __fsqrt_rn(r2)), __fsqrt_rn(__fsqrt_rn(r2))); break;
+      default: g = r; break;
+    }
   }
-  st.env = f->env[c];
-  const float thr = f->thr, att = f->att, rel = f->rel, makeup = f->makeup;
-  const uint32_t code = f->ratio_code;
-  constexpr int CH = 16;  // frames per chunk: the chunk's loads are in flight together
-  uint64_t j = 0;
-  for (; j + CH <= frames; j += CH) {
-    float v[CH];
-#pragma unroll
-    for (int q = 0; q < CH; q++) v[q] = buf[(j + q) * 2];
-#pragma unroll
-    for (int q = 0; q < CH; q++) v[q] = fx_sample(v[q], st, b0, b1, b2, a1, a2, eq_on, comp_on, thr, att, rel, makeup, code);
-#pragma unroll
-    for (int q = 0; q < CH; q++) buf[(j + q) * 2] = v[q];
+  return __fmul_rn(__fmul_rn(x, g), makeup);
+}
+
+// The chain is five recurrences in series (4 biquads, the envelope follower) and one memoryless map (gain computer).
+// A thread that walks them sample by sample is bound by the dependent-FMA latency of all five in a row while the GPU
+// idles. Here one WARP carries P (track, channel) pairs as a software pipeline over 32-frame chunks held in shared
+// memory: lane p*4+s runs biquad s of pair p on chunk i-s, lane p also runs pair p's envelope follower on chunk i-4 —
+// both recurrences sit in the same instruction stream, so their latencies overlap — and all 32 lanes then evaluate the
+// gain computer of chunk i-5 one frame per lane and store it. Every frame still sees exactly the operations of
+// fx_sample in the same order (a stage's input is the previous stage's rounded output either way): bit-identical to
+// the one-thread walk and to oracle/wb_oracle.c apply_effects.
+template <int P>
+struct FxLayout {
+  static constexpr int DEPTH = 4;                      // chunk slots per stage buffer (writer and readers 2 apart)
+  static constexpr int ROW = 33;                       // 32 frames + 1 pad: lanes of one phase hit distinct banks
+  static constexpr int ROWS = (5 * DEPTH) * P + DEPTH * P + 1;  // X[0..4], E, one scratch row for idle lanes
+  static constexpr int WARP_FLOATS = ROWS * ROW;
+  __device__ static int x_row(int stage, int slot, int pair) { return (stage * DEPTH + slot) * P + pair; }
+  __device__ static int e_row(int slot, int pair) { return (5 * DEPTH + slot) * P + pair; }
+  static constexpr int SCRATCH = (5 * DEPTH) * P + DEPTH * P;
+};
+
+template <int P>
+__global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t frames,
+                                                       float* __restrict__ trackbuf) {
+  using L = FxLayout<P>;
+  extern __shared__ float fx_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sm = fx_smem + (size_t)warp * L::WARP_FLOATS;
+  const uint32_t n_pairs = n_fx * C;
+  const uint32_t pair0 = (blockIdx.x * (blockDim.x >> 5) + warp) * P;
+  if (pair0 >= n_pairs) return;
+
+  // biquad role: lane = p*4 + s
+  const int bp = lane >> 2, bs = lane & 3;
+  const bool bq_lane = bp < P && pair0 + bp < n_pairs;
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f, s1 = 0.f, s2 = 0.f;
+  bool eq_on = false;
+  if (bq_lane) {
+    const uint32_t g = pair0 + bp;
+    const DFx* f = fx + g / C;
+    const uint32_t c = g % C;
+    eq_on = f->eq_on != 0;
+    b0 = f->b0[bs], b1 = f->b1[bs], b2 = f->b2[bs], a1 = f->a1[bs], a2 = f->a2[bs];
+    s1 = f->s1[c][bs], s2 = f->s2[c][bs];
   }
-  for (; j < frames; j++) buf[j * 2] = fx_sample(buf[j * 2], st, b0, b1, b2, a1, a2, eq_on, comp_on, thr, att, rel, makeup, code);
-#pragma unroll
-  for (int b = 0; b < 4; b++) {
-    f->s1[c][b] = st.s1[b];
-    f->s2[c][b] = st.s2[b];
+  // envelope role: lane = p
+  bool env_lane = lane < P && pair0 + lane < n_pairs;
+  float env = 0.f, att = 0.f, rel = 0.f;
+  if (env_lane) {
+    const uint32_t g = pair0 + lane;
+    const DFx* f = fx + g / C;
+    env = f->env[g % C];
+    att = f->att, rel = f->rel;
+    env_lane = f->comp_on != 0;  // without a compressor the envelope state is left alone (fx_sample)
   }
-  f->env[c] = st.env;
+  // gain role: every lane, pair r in turn — per-pair constants and the pair's channel in the interleaved track buffer
+  float thr[P], makeup[P];
+  uint32_t code[P];
+  bool comp_on[P];
+  float* buf[P];
+#pragma unroll
+  for (int r = 0; r < P; r++) {
+    const uint32_t g = pair0 + r < n_pairs ? pair0 + r : n_pairs - 1;
+    const DFx* f = fx + g / C;
+    thr[r] = f->thr, makeup[r] = f->makeup, code[r] = f->ratio_code, comp_on[r] = f->comp_on != 0;
+    buf[r] = trackbuf + (size_t)(g / C) * frames * 2 + (g % C);
+  }
+
+  const uint64_t n_chunks = (frames + 31) / 32;
+  auto chunk_len = [&](int64_t c) -> int {
+    if (c < 0 || (uint64_t)c >= n_chunks) return 0;
+    const uint64_t left = frames - (uint64_t)c * 32;
+    return left < 32 ? (int)left : 32;
+  };
+  // chunk 0 into X[0][0]
+#pragma unroll
+  for (int r = 0; r < P; r++)
+    if (pair0 + r < n_pairs && (uint64_t)lane < frames) sm[L::x_row(0, 0, r) * L::ROW + lane] = buf[r][(size_t)lane * 2];
+  __syncwarp();
+
+  for (uint64_t i = 0; i < n_chunks + 5; i++) {
+    // next chunk's input: loads in flight during this iteration's recurrences
+    float nxt[P];
+    const uint64_t fn = (i + 1) * 32 + lane;
+#pragma unroll
+    for (int r = 0; r < P; r++) nxt[r] = (pair0 + r < n_pairs && fn < frames) ? buf[r][fn * 2] : 0.0f;
+
+    // ---- recurrences: biquad s on chunk i-s, envelope on chunk i-4 -------------------------------------------
+    const int64_t cb = (int64_t)i - bs, ce = (int64_t)i - 4;
+    const int nb = bq_lane ? chunk_len(cb) : 0;
+    const int ne = env_lane ? chunk_len(ce) : 0;
+    const float* xin = sm + (nb ? L::x_row(bs, (int)(cb & 3), bp) : L::SCRATCH) * L::ROW;
+    float* xout = sm + (nb ? L::x_row(bs + 1, (int)(cb & 3), bp) : L::SCRATCH) * L::ROW;
+    const float* ein = sm + (ne ? L::x_row(4, (int)(ce & 3), lane) : L::SCRATCH) * L::ROW;
+    float* eout = sm + (ne ? L::e_row((int)(ce & 3), lane) : L::SCRATCH) * L::ROW;
+    const bool steady = i >= 4 && i + 1 < n_chunks;  // every active lane has a full chunk: no per-frame bounds
+    if (steady) {
+      // every active lane has a full chunk; idle lanes run the same instructions on the scratch row (their state is
+      // never stored), so the loop carries no predicates: two independent dependency chains per lane
+      // the chunk is staged in registers: a shared-memory load between dependent FMAs (the compiler cannot move it
+      // above the previous frame's store) would put its latency into every step of the recurrence
+      float xv[32], ev[32];
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        xv[q] = xin[q];
+        ev[q] = ein[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const float x = xv[q];
+        const float y = __fmaf_rn(b0, x, s1);  // transposed direct form II (fx_sample)
+        s1 = __fmaf_rn(b1, x, __fmaf_rn(-a1, y, s2));
+        s2 = __fmaf_rn(b2, x, -__fmul_rn(a2, y));
+        xv[q] = eq_on ? y : x;
+        const float xa = fabsf(ev[q]);
+        const float d = __fsub_rn(env, xa);
+        env = xa > env ? __fmaf_rn(att, d, xa) : __fmaf_rn(rel, d, xa);
+        ev[q] = env;
+      }
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        xout[q] = xv[q];
+        eout[q] = ev[q];
+      }
+    } else {
+      for (int q = 0; q < 32; q++) {
+        if (q < nb) {
+          const float x = xin[q];
+          const float y = __fmaf_rn(b0, x, s1);
+          s1 = __fmaf_rn(b1, x, __fmaf_rn(-a1, y, s2));
+          s2 = __fmaf_rn(b2, x, -__fmul_rn(a2, y));
+          xout[q] = eq_on ? y : x;
+        }
+        if (q < ne) {
+          const float xa = fabsf(ein[q]);
+          const float d = __fsub_rn(env, xa);
+          env = xa > env ? __fmaf_rn(att, d, xa) : __fmaf_rn(rel, d, xa);
+          eout[q] = env;
+        }
+      }
+    }
+    // ---- gain computer + store of chunk i-5, one frame per lane ------------------------------------------------
+    const int64_t cg = (int64_t)i - 5;
+    const int ng = chunk_len(cg);
+    if (lane < ng) {
+#pragma unroll
+      for (int r = 0; r < P; r++) {
+        if (pair0 + r >= n_pairs) break;
+        const float x = sm[L::x_row(4, (int)(cg & 3), r) * L::ROW + lane];
+        const float e = sm[L::e_row((int)(cg & 3), r) * L::ROW + lane];
+        buf[r][((size_t)cg * 32 + lane) * 2] = comp_on[r] ? fx_gain(x, e, thr[r], makeup[r], code[r]) : x;
+      }
+    }
+    // ---- stage the next input chunk -------------------------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < P; r++) sm[L::x_row(0, (int)((i + 1) & 3), r) * L::ROW + lane] = nxt[r];
+    __syncwarp();
+  }
+
+  if (bq_lane && eq_on) {
+    const uint32_t g = pair0 + bp;
+    DFx* f = fx + g / C;
+    f->s1[g % C][bs] = s1;
+    f->s2[g % C][bs] = s2;
+  }
+  if (env_lane) {
+    const uint32_t g = pair0 + lane;
+    fx[g / C].env[g % C] = env;
+  }
+}
+
+template <int P>
+static cudaError_t launch_effects_p(DFx* fx, uint32_t n_fx, uint32_t C, uint64_t frames, float* trackbuf, cudaStream_t stream) {
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)FxLayout<P>::WARP_FLOATS * WARPS * sizeof(float);
+  auto kfn = effects_kernel<P>;
+  cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  const uint32_t warps = (n_fx * C + P - 1) / P;
+  kfn<<<(warps + WARPS - 1) / WARPS, WARPS * 32, smem, stream>>>(fx, n_fx, C, frames, trackbuf);
+  return cudaGetLastError();
+}
+
+// pairs per warp: the fewest that leave at most one warp per scheduler (4 per SM) — small sessions spread over the
+// whole machine; beyond one warp per scheduler the chain is instruction-issue-bound and fuller warps (more pairs per
+// recurrence instruction) win (measured: 512 tracks, P = 1 with two warps per scheduler 17.7 ms)
+static cudaError_t launch_effects_chain(DFx* fx, uint32_t n_fx, uint32_t C, uint64_t frames, float* trackbuf, int n_sm,
+                                        cudaStream_t stream) {
+  const uint32_t pairs = n_fx * C;
+  const uint32_t slots = (uint32_t)n_sm * 4;  // one warp per scheduler: beyond that the chain is instruction-issue-bound
+  int P = 8;
+  if (pairs <= slots) P = 1;
+  else if (pairs <= 2 * slots) P = 2;
+  else if (pairs <= 4 * slots) P = 4;
+  if (const char* env = getenv("WBX_FX_PAIRS")) {
+    const int v = atoi(env);
+    if (v == 1 || v == 2 || v == 4 || v == 8) P = v;
+  }
+  switch (P) {
+    case 1: return launch_effects_p<1>(fx, n_fx, C, frames, trackbuf, stream);
+    case 2: return launch_effects_p<2>(fx, n_fx, C, frames, trackbuf, stream);
+    case 4: return launch_effects_p<4>(fx, n_fx, C, frames, trackbuf, stream);
+    default: return launch_effects_p<8>(fx, n_fx, C, frames, trackbuf, stream);
+  }
 }
 
 // ---- convolution reverb (extension, cfg 5): direct form on the CUDA cores --------------------------------
@@ -1176,6 +1362,26 @@ __global__ void shard_reduce_kernel(const float* __restrict__ xchg, uint32_t W, 
       }
     }
   }
+}
+
+// Realtime callback (one-callback render): the submitted table (spans | gains | cells) is pulled from page-locked host
+// memory by this kernel and the mix's zero region is cleared by it too, so the callback is kernels only — no hop between
+// the copy engine and the SMs (each costs several microseconds of the ~60 a callback takes).
+__global__ void ingest_kernel(const uint4* __restrict__ host_table, uint4* __restrict__ table, size_t n_table,
+                              uint4* __restrict__ zero, size_t n_zero) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_table; i += stride) table[i] = host_table[i];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += stride) zero[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// level_kernel for renders of few callbacks: one thread per (track, channel), result stored straight into page-locked
+// host memory (no atomics, no copy afterwards)
+__global__ void level_direct_kernel(const float* __restrict__ peaks, uint32_t K, uint32_t NC, float* __restrict__ levels_host) {
+  const uint32_t tc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tc >= NC) return;
+  float m = 0.0f;
+  for (uint32_t k = 0; k < K; k++) m = fmaxf(m, __ldcg(peaks + (size_t)k * NC + tc));
+  levels_host[tc] = m;
 }
 
 // VUMeter::level semantics over a whole render: max over callbacks of the block peaks (vu_meter.h:25-29).
@@ -1355,18 +1561,35 @@ static cudaError_t launch_mix_e(const MixParams& p, int n_sm, cudaStream_t strea
   using L = MixLayout<FPL, STAGES>;
   auto kfn = mix_kernel<FPL, STAGES, WARPS, EXT>;
   const int smem = L::WARP_BYTES * WARPS;
-  cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  // attribute + occupancy are properties of the instantiation (per device of the same kind): queried once, not on the
+  // realtime callback's path
+  static int per_sm_cached[64] = {0};
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
   if (err != cudaSuccess) return err;
-  int per_sm = 0;
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, WARPS * 32, smem);
-  if (err != cudaSuccess) return err;
-  if (per_sm < 1) per_sm = 1;
+  int per_sm = (dev >= 0 && dev < 64) ? per_sm_cached[dev] : 0;
+  if (per_sm == 0) {
+    err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, WARPS * 32, smem);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) per_sm = 1;
+    if (dev >= 0 && dev < 64) per_sm_cached[dev] = per_sm;
+  }
   long ctas = (long)n_sm * per_sm;
-  const long need = ((long)p.n_items + WARPS - 1) / WARPS;
+  // a render with few work items (the realtime callback) is spread over the SMs with fewer warps per CTA: the bulk-copy
+  // issue rate is a per-SM resource, so 8 warps on each of 16 SMs stage their windows 8x slower than 1 warp on each of 128
+  int wpc = WARPS;
+  if ((long)p.n_items < (long)n_sm * WARPS) {
+    wpc = (int)(((long)p.n_items + n_sm - 1) / n_sm);
+    if (wpc < 1) wpc = 1;
+    if (wpc > WARPS) wpc = WARPS;
+  }
+  const long need = ((long)p.n_items + wpc - 1) / wpc;
   if (ctas > need) ctas = need;
   if (ctas < 1) ctas = 1;
   if (ctas_out) *ctas_out = (int)ctas;
-  kfn<<<(unsigned)ctas, WARPS * 32, smem, stream>>>(p);
+  kfn<<<(unsigned)ctas, wpc * 32, (size_t)L::WARP_BYTES * wpc, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -1435,7 +1658,13 @@ cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n
   if (n_fx == 0) return cudaSuccess;
   const uint64_t warps = (uint64_t)n_fx * K;
   render_tracks_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf);
-  effects_kernel<<<(n_fx * C + 31) / 32, 32, 0, stream>>>(fx, n_fx, C, (uint64_t)K * B, trackbuf);
+  {
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t err = launch_effects_chain(fx, n_fx, C, (uint64_t)K * B, trackbuf, n_sm, stream);
+    if (err != cudaSuccess) return err;
+  }
   if (L && ir && fir_hist && fir_in) {  // convolution reverb as the chain's last stage
     const uint64_t T = (uint64_t)K * B, H = L - 1;
     const dim3 gcopy((unsigned)(((H + T) + 255) / 256 < 4096 ? ((H + T) + 255) / 256 : 4096), n_fx * C);
@@ -1484,6 +1713,23 @@ cudaError_t launch_shard_reduce(const float* xchg, uint32_t W, uint32_t C, uint6
     shard_reduce_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(xchg, W, C, plane, valid, peers, chan_stride, dst_off);
   else
     shard_reduce_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(xchg, W, C, plane, valid, peers, chan_stride, dst_off);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ingest(const void* host_table, void* table, size_t table_bytes, void* zero, size_t zero_bytes,
+                          cudaStream_t stream) {
+  const size_t n = (table_bytes / 16 > zero_bytes / 16 ? table_bytes : zero_bytes) / 16;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 128) blocks = 128;
+  if (blocks < 1) blocks = 1;
+  ingest_kernel<<<blocks, 256, 0, stream>>>((const uint4*)host_table, (uint4*)table, table_bytes / 16, (uint4*)zero,
+                                            zero_bytes / 16);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_levels_direct(const float* peaks, uint32_t K, uint32_t NC, float* levels_host, cudaStream_t stream) {
+  if (NC == 0) return cudaSuccess;
+  level_direct_kernel<<<(NC + 127) / 128, 128, 0, stream>>>(peaks, K, NC, levels_host);
   return cudaGetLastError();
 }
 
