@@ -132,22 +132,29 @@ def make_sources(n_tracks, n_blocks, seed):
         yield t, [pool[o:o + frames] for o in offs]
 
 
+NCU_MIX_CAPTURES = ["r01b_ncu_full_mix_fpl16_K4096.txt", "r01_ncu_full_mix_fpl16_K4096.txt"]  # newest first
+
+
 def ncu_traffic(n_tracks, n_blocks):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one mix-kernel launch from the committed `ncu --set full`
-    capture of this exact shape (profiles/), or None when no capture of the shape exists."""
+    """(dram__bytes_read.sum + dram__bytes_write.sum of one mix-kernel launch, file) from the newest committed
+    `ncu --set full` capture of this exact shape (profiles/), or (None, None) when no capture of the shape exists."""
     if (n_tracks, n_blocks) != (1024, 4096):
-        return None
-    try:
-        rd = wr = None
-        for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_full_mix_fpl16_K4096.txt")):
-            f = ln.split()
-            if ln.startswith("dram__bytes_read.sum"):
-                rd = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
-            if ln.startswith("dram__bytes_write.sum"):
-                wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
-        return None if rd is None or wr is None else rd + wr
-    except Exception:
-        return None
+        return None, None
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    for name in NCU_MIX_CAPTURES:
+        try:
+            rd = wr = None
+            for ln in open(os.path.join(ROOT, "profiles", name)):
+                f = ln.split()
+                if ln.startswith("dram__bytes_read.sum"):
+                    rd = float(f[2]) * scale[f[1]]
+                if ln.startswith("dram__bytes_write.sum"):
+                    wr = float(f[2]) * scale[f[1]]
+            if rd is not None and wr is not None:
+                return rd + wr, "profiles/" + name
+        except Exception:
+            continue
+    return None, None
 
 
 def track_params(t):
@@ -455,8 +462,8 @@ def run_ours(args):
                 "e2e_equals_device_run": same,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": ncu_traffic(N, K), "peak_source": peak_src, "kernel_ms": kern_ms,
-                         "traffic_source": "profiles/r01_ncu_full_mix_fpl16_K4096.txt (ncu --set full, bytes per launch)" if ncu_traffic(N, K) else None,
+                         "traffic": ncu_traffic(N, K)[0], "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "traffic_source": (ncu_traffic(N, K)[1] + " (ncu --set full, bytes per launch)") if ncu_traffic(N, K)[0] else None,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": e2e_value, "unit": "stereo track-frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,

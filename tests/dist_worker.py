@@ -38,9 +38,23 @@ def main():
             eng.add_clip(i, sid, 0.0, beats, 0.0, 1.0, float(p["gain"]))
     eng.play()
     part, peaks = eng.process(n_blocks)  # unclamped partial bus [K][C][B], peaks of the shard
-    bus = torch.from_numpy(np.ascontiguousarray(part))
+    bus = torch.from_numpy(np.array(part, dtype=np.float32, copy=True))  # all_reduce works in place: keep `part`
     dist.all_reduce(bus)  # the single exchange step
     out = shard.clamp_bus(bus.numpy())
+    # the same exchange the way the product does it over peer memory: every rank hands every owner its slice of callbacks
+    # (here: all_gather of the partial buses stands in for the peer stores), each owner adds the slices in rank order and
+    # clamps, rank 0 collects the owners' slices. Must equal the all-reduce form bit for bit at world 2 (one add).
+    parts = [torch.zeros_like(torch.from_numpy(part)) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(part)))
+    mine = shard.reduce_owned([p.numpy() for p in parts], rank, world)
+    lo_k, hi_k = shard.owner_blocks(n_blocks, rank, world)
+    assert mine.shape[0] == hi_k - lo_k
+    slices = [None] * world
+    dist.all_gather_object(slices, mine)
+    master = np.concatenate(slices, axis=0)
+    assert master.shape == out.shape
+    if world == 2:
+        assert np.array_equal(master.view(np.uint32), out.view(np.uint32)), "owner-reduced bus != all-reduced bus"
     all_peaks = [torch.zeros((n_blocks, shard.track_range(n_tracks, r, world)[1] - shard.track_range(n_tracks, r, world)[0], 2))
                  for r in range(world)]
     dist.all_gather(all_peaks, torch.from_numpy(np.ascontiguousarray(peaks)))

@@ -12,6 +12,25 @@ def track_range(n_tracks, rank, world):
     return lo, lo + per + (1 if rank < rem else 0)
 
 
+def owner_blocks(n_blocks, rank, world):
+    """Callbacks [lo, hi) whose bus rank `rank` reduces in the peer-memory exchange (include/wbx.h, "sharded render"):
+    callback k belongs to rank k // ceil(n_blocks / world); ranks past the end own nothing."""
+    per = (n_blocks + world - 1) // world
+    lo = min(rank * per, n_blocks)
+    return lo, min(lo + per, n_blocks)
+
+
+def reduce_owned(partials, rank, world):
+    """What an owner computes for its callbacks: the partial buses [K][C][B] of ranks 0..world-1 added in rank order
+    (f32, one rounding per add), then the clamp. `partials` is indexed by source rank. numpy statement of
+    shard_reduce_kernel, used by the CPU tests of the exchange's host logic."""
+    lo, hi = owner_blocks(partials[0].shape[0], rank, world)
+    acc = partials[0][lo:hi].astype(np.float32).copy()
+    for r in range(1, world):
+        acc = (acc + partials[r][lo:hi]).astype(np.float32)
+    return clamp_bus(acc)
+
+
 class _DevPtr:
     """Raw device pointer -> torch tensor without a copy (__cuda_array_interface__)."""
 
