@@ -104,11 +104,15 @@ _POOL = {}
 PIN_POOL = False
 
 
-def make_sources(n_tracks, n_blocks, seed):
+def source_frames(n_blocks, src_rate=RATE):
+    return int((n_blocks + 4) * BLOCK * src_rate / RATE) + 64
+
+
+def make_sources(n_tracks, n_blocks, seed, src_rate=RATE):
     """SURVEY §8(d) fixture at bench size: stereo f32 sources of (n_blocks+4)*512+64 frames, uniform(-1,1) *
     0.5/sqrt(N). Every track/channel is a different window of one 256 MiB MT-seeded random pool (generating
     16 GiB of fresh random numbers per run would dominate the bench's wall time); yields (t, [L, R]) views."""
-    frames = (n_blocks + 4) * BLOCK + 64
+    frames = source_frames(n_blocks, src_rate)
     pool_len = max(1 << 26, 2 * frames)
     key = (seed, pool_len, n_tracks)
     if key not in _POOL:
@@ -169,20 +173,20 @@ class CpuEngines:
     threads == 1 is the faithful single-threaded reference; threads > 1 builds that many independent engine
     instances with n_tracks/threads tracks each (the generous all-cores row)."""
 
-    def __init__(self, kind, n_tracks, n_blocks, threads, seed=1234):
+    def __init__(self, kind, n_tracks, n_blocks, threads, seed=1234, src_rate=RATE):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_api as o
         self.n_tracks, self.n_blocks, self.threads = n_tracks, n_blocks, threads
         per = [n_tracks // threads + (1 if i < n_tracks % threads else 0) for i in range(threads)]
         self.sessions = []
-        src = make_sources(n_tracks, n_blocks, seed)
+        src = make_sources(n_tracks, n_blocks, seed, src_rate)
         for i in range(threads):
             s = o.Session(kind, 2, BLOCK, RATE, 120.0)
             for j in range(per[i]):
                 t, x = next(src)
                 vol, pan, gain = track_params(t)
                 s.add_track(vol, pan, False)
-                sid = s.add_sample(np.stack(x), RATE)
+                sid = s.add_sample(np.stack(x), src_rate)
                 s.add_clip(j, sid, 0.0, 1e9, 0.0, 1.0, gain)
             self.sessions.append(s)
 
@@ -212,8 +216,8 @@ class CpuEngines:
         self.sessions = []
 
 
-def cpu_engine_run(kind, n_tracks, n_blocks, threads, seed=1234):
-    eng = CpuEngines(kind, n_tracks, n_blocks, threads, seed)
+def cpu_engine_run(kind, n_tracks, n_blocks, threads, seed=1234, src_rate=RATE):
+    eng = CpuEngines(kind, n_tracks, n_blocks, threads, seed, src_rate)
     try:
         return eng.run()
     finally:
@@ -294,9 +298,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    N, K = args.tracks, args.blocks
+    # ---- workload: BASELINE.json configs[1] by default; configs[2..4] selectable (profiles/, not the contract line) ----
+    wl = args.workload
+    defaults = {"cfg2": (1024, 4096), "cfg3": (1024, 4096), "cfg4": (512, 1024), "cfg5": (256 // world, 64)}[wl]
+    N = args.tracks if args.tracks else defaults[0]
+    K = args.blocks if args.blocks else defaults[1]
+    src_rate = 44100 if wl == "cfg3" else RATE
+    resubmit = wl in ("cfg4", "cfg5")  # the effect chains run at submit: a step is submit + mix
     hbm_peak, peak_src, sm_max = peaks_json()
     global PIN_POOL
+    args.cold = args.cold if wl == "cfg2" else 0
     PIN_POOL = bool(args.cold) and world == 1
 
     # ---- session: N tracks on this rank (global track index rank*N + t) --------------------------------
@@ -305,16 +316,32 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     eng.dev.set_stream(stream.cuda_stream)
     host_sources = []
-    for t, x in make_sources(N, K, 1234 + rank):
+    for t, x in make_sources(N, K, 1234 + rank, src_rate):
         vol, pan, gain = track_params(rank * N + t)
         eng.add_track(vol - 3.0 * np.log2(world), pan, False)  # keep the N*world-track bus inside +/-1
-        sid = eng.add_sample_planar(x, RATE)
+        sid = eng.add_sample_planar(x, src_rate)
         eng.add_clip(t, sid, 0.0, 1e9, 0.0, 1.0, gain)
         if args.cold and rank == 0:
             host_sources.append(x)
+    if wl == "cfg4":  # 4-band EQ + compressor on every track (extension, "parity unpinned": include/wbx.h)
+        fxp = wb.effect_params(eq=((120.0, 4.0, 0.7), (800.0, -6.0, 1.2), (2500.0, 3.0, 2.0), (8000.0, 5.0, 0.7)),
+                               threshold_db=-30.0, ratio_code=2, attack_ms=2.0, release_ms=60.0, makeup_db=3.0)
+        for t in range(N):
+            eng.set_effects(t, fxp)
+    if wl == "cfg5":  # one 65536-tap impulse response, convolution reverb on every track (tensor-core path)
+        taps = args.taps
+        ir = (np.random.default_rng(2).standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 6.0)) * 0.01).astype(np.float32)
+        ir[0] = 1.0
+        eng.set_impulse_response(ir)
+        for t in range(N):
+            eng.set_effects(t, wb.effect_params(reverb=True))
+    if wl in ("cfg4", "cfg5"):  # the host engine hands edited chains to the device at its next render: do one now
+        eng.play()
+        eng.render(1, want_peaks=False)
+        eng.stop()
     if rank == 0:
-        log("setup: %d tracks x %d blocks (%.2f GiB of sources per GPU) in %.1fs" %
-            (N, K, N * 2 * ((K + 4) * BLOCK + 64) * 4 / 2**30, time.perf_counter() - t_setup))
+        log("setup: %s, %d tracks x %d blocks (%.2f GiB of sources per GPU) in %.1fs" %
+            (wl, N, K, N * 2 * source_frames(K, src_rate) * 4 / 2**30, time.perf_counter() - t_setup))
 
     track_frames_per_step = N * K * BLOCK  # per rank
     dev = eng.dev
@@ -344,7 +371,11 @@ def run_ours(args):
     def mix_step(ev_pair=None):
         """One step's device work: mix this rank's tracks, sum the bus across ranks, clamp. ev_pair brackets the
         mix kernel alone (for the roofline)."""
-        if ev_pair:
+        if ev_pair and resubmit:
+            ev_pair[0].record(stream)
+        if resubmit:  # render the tracks with a chain + run the chains (wbx_submit), then mix
+            dev.submit_raw(segs_ptr, n_segs_dev, gains_ptr, K)
+        if ev_pair and not resubmit:
             ev_pair[0].record(stream)
         if exchange == "peer":
             dev.mix_sharded(0)  # mix; tiles -> owners' exchange buffers over NVLink while mixing; arrival signal
@@ -364,6 +395,9 @@ def run_ours(args):
     # ---- (1) device-resident throughput: schedule submitted once, K launches of the mix kernel ---------
     eng.play()
     segs, gains = eng.schedule(K)
+    segs = np.ascontiguousarray(segs, dtype=wb.SEGMENT_DTYPE)
+    gains = np.ascontiguousarray(gains, dtype=np.float32)
+    segs_ptr, gains_ptr, n_segs_dev = segs.ctypes.data, gains.ctypes.data, len(segs)
     dev.submit(segs, gains, K)
     dev.synchronize()
     with torch.cuda.stream(stream):
@@ -439,21 +473,47 @@ def run_ours(args):
     total_ms, kern_ms, e2e_s = [float(v) for v in t.tolist()]
 
     if rank == 0:
-        same = bool(np.array_equal(out_dev.view(np.uint32), out_e2e.view(np.uint32))) if out_e2e is not None else None
+        same = (bool(np.array_equal(out_dev.view(np.uint32), out_e2e.view(np.uint32)))
+                if (out_e2e is not None and not resubmit) else None)  # chain state carries over between renders
         ms_per_step = total_ms / args.steps
         value = world * track_frames_per_step / (ms_per_step * 1e-3)
-        alg_bytes = track_frames_per_step * ALG_BYTES_PER_TRACK_FRAME
+        alg_bytes = track_frames_per_step * ALG_BYTES_PER_TRACK_FRAME * src_rate / RATE  # each source sample read once
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(N, K) if wl == "cfg2" else (None, None)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms,
+                    "traffic_source": (traffic_src + " (ncu --set full, bytes per launch)") if traffic else None,
+                    "algorithmic_bytes_per_launch": alg_bytes}
+        if wl == "cfg4":
+            roofline["note"] = ("kernel_ms = the whole step (render tracks + effect chains + mix); the chains are recurrences in time, "
+                                "bound by dependent-FMA latency, not by HBM (DESIGN.md 5.5)")
+        if wl == "cfg5":
+            pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            tf_peak = float(pj.get("bf16_tflops_sustained", pj.get("bf16_tflops", 1590.0)))
+            flops = 2.0 * args.taps * 2 * track_frames_per_step  # direct-form count: 2 * taps per output sample and channel
+            tf = flops / (kern_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": tf * 6, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf * 6 / tf_peak,
+                        "traffic": None, "kernel_ms": kern_ms, "direct_form_tflops": tf,
+                        "note": "kernel_ms = the whole step (render tracks + reverb chain + mix); achieved = direct-form flops x 6 "
+                                "(3-term bf16 split of both operands, six products: the bf16 tensor work actually issued)",
+                        "peak_source": "MEASURED_PEAKS.json bf16 (sustained)" if pj else "fallback 1590 TFLOP/s"}
         e2e_value = world * track_frames_per_step * args.steps / e2e_s
         cpu_kind = oracle_kind()
         cpu_blocks = args.cpu_blocks
-        cpu_val, cpu_secs = cpu_engine_run(cpu_kind, N, cpu_blocks, 1) if world == 1 else (None, None)
+        cpu_val, cpu_secs = (cpu_engine_run(cpu_kind, N, cpu_blocks, 1, src_rate=src_rate)
+                             if world == 1 and wl in ("cfg2", "cfg3") else (None, None))
         res = {
             "metric": "mixed stereo samples/sec at N tracks", "value": value, "unit": "stereo track-frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if (wl == "cfg5" and not args.tracks) else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "cfg2: %d stereo tracks/GPU, 48 kHz f32, gain/pan + bus sum (fade=0: the reference has none), 512-frame block" % N,
+                "workload": {
+                    "cfg2": "cfg2: %d stereo tracks/GPU, 48 kHz f32, gain/pan + bus sum (fade=0: the reference has none), 512-frame block",
+                    "cfg3": "cfg3: %d stereo tracks/GPU, 44.1 kHz f32 sources resampled to 48 kHz (2-tap linear, the reference's resampler) + mix, 512-frame block",
+                    "cfg4": "cfg4: %d stereo tracks/GPU, 48 kHz f32, 4-band biquad EQ + compressor chain on every track (extension, parity unpinned) + mix; a step = chains (wbx_submit) + mix",
+                    "cfg5": "cfg5: %d stereo tracks/GPU, 48 kHz f32, " + str(args.taps) + "-tap convolution reverb on every track (tensor-core path; extension, parity unpinned) + mix; a step = chains (wbx_submit) + mix",
+                }[wl] % N,
                 "tracks_per_gpu": N, "total_tracks": N * world, "block_frames": BLOCK, "blocks_per_step": K,
                 "out_frames_per_s": value / (N * world), "realtime_x": value / (N * world) / RATE,
                 "l2": "inputs larger than L2 (%.2f GiB streamed per step per GPU vs 126 MB)" % (alg_bytes / 2**30),
@@ -461,18 +521,15 @@ def run_ours(args):
                 "bus_exchange": exchange,
                 "e2e_equals_device_run": same,
             },
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": ncu_traffic(N, K)[0], "peak_source": peak_src, "kernel_ms": kern_ms,
-                         "traffic_source": (ncu_traffic(N, K)[1] + " (ncu --set full, bytes per launch)") if ncu_traffic(N, K)[0] else None,
-                         "algorithmic_bytes_per_launch": alg_bytes},
+            "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "stereo track-frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "note": "wbx::Engine::render through the C ABI: host clip scheduling + H2D segment table + schedule expansion + mix + D2H of the clamped bus into page-locked host channels and of the VU levels; source samples resident (engine state, as wb::Sample in the reference)"},
+                    "note": "wbx::Engine::render through the C ABI with host buffers: host clip scheduling + H2D segment table + schedule expansion (+ effect chains) + mix + the clamped bus into page-locked host channels (written by the mix kernel itself at N=1, copied from rank 0's master bus at N>1) + VU levels to the host; source samples resident (engine state, as wb::Sample in the reference)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if e2e_cold_s:
-            src_bytes = N * 2 * ((K + 4) * BLOCK + 64) * 4
+            src_bytes = N * 2 * source_frames(K, src_rate) * 4
             res["e2e_cold"] = {"value": track_frames_per_step / e2e_cold_s, "unit": "stereo track-frames/s",
                                "h2d_bytes_per_step": h2d + src_bytes, "d2h_bytes_per_step": d2h,
                                "note": "as e2e, plus streaming every source sample from page-locked host memory over PCIe each step (wbx_sample_update)"}
@@ -490,8 +547,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--tracks", type=int, default=1024, help="stereo tracks per GPU")
-    ap.add_argument("--blocks", type=int, default=4096, help="512-frame callbacks per step (our arm)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs[1] (the contract line, default) or configs[2..4] (profiles/)")
+    ap.add_argument("--tracks", type=int, default=0, help="stereo tracks per GPU (0: 1024; cfg4 512; cfg5 256 / gpus = strong scaling)")
+    ap.add_argument("--blocks", type=int, default=0, help="512-frame callbacks per step (0: 4096; cfg4 1024; cfg5 64)")
+    ap.add_argument("--taps", type=int, default=65536, help="cfg5: taps of the impulse response")
     ap.add_argument("--ref-blocks", type=int, default=1024, help="callbacks per step of the reference arm (at 1 GPU)")
     ap.add_argument("--cpu-blocks", type=int, default=1024, help="callbacks of the cpu_baseline sample")
     ap.add_argument("--exact", type=int, default=1, help="1: bit-exact sequential track order, 0: auto")
@@ -500,6 +560,7 @@ def main():
                     help="N>1: bus sum over peer memory fused into the mix kernel, or one NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
+        args.tracks = args.tracks or 1024
         run_reference(args)
     else:
         run_ours(args)

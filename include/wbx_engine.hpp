@@ -31,6 +31,9 @@ struct PanningCoefficient {
 };
 // core/panning_law.cpp:9-32 (ConstantPower_3db) and core/core_math.h:83-89 — host-only scalar math
 PanningCoefficient calculate_panning_coefs(float pan);
+// `while (steps < n && off < limit) { off = off + adv; steps++; }` — the position recurrence of dsp::Sampler::stream
+// (dsp/sampler.cpp:103,209) over n event-free callbacks — in O(binades) exact integer steps; returns steps
+uint32_t advance_rounded(double* off, double adv, uint32_t n, double limit);
 float db_to_linear(float db);
 
 struct AudioClip {  // engine/clip.h:39-45 + Clip time placement (:68-70)

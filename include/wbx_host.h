@@ -59,6 +59,8 @@ double wbxh_sampler_offset(wbxh_engine* h, int track); /* Track::sampler.sample_
 double wbxh_sample_position(wbxh_engine* h);           /* Engine::sample_position */
 double wbxh_playhead(wbxh_engine* h);                  /* Engine::playhead */
 float wbxh_level(wbxh_engine* h, int track, int channel, int reset); /* VUMeter::level (+ exchange(0)) */
+/* wbx::advance_rounded (wbx_engine.hpp): the sampler position recurrence over n callbacks, exact, closed form per binade */
+uint32_t wbxh_advance_rounded(double* off, double adv, uint32_t n, double limit);
 void wbxh_panning_coefs(float pan, float* left, float* right);
 float wbxh_db_to_linear(float db);
 

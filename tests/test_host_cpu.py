@@ -188,3 +188,45 @@ def test_cpp_adaptor_builds_and_refuses_without_device(wb, tmp_path):
         pytest.skip("a GPU is present")
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 2 and "no CPU path" in r.stderr
+
+
+def test_position_recurrence_closed_form_is_exact():
+    """wbx::advance_rounded == the sampler's step-by-step `off = off + adv` (dsp/sampler.cpp:103,209), one rounding per
+    callback, bit for bit: random starts / advances / limits, exact ties (adv/ulp halfway), binade crossings, tiny and
+    huge values. Python floats are IEEE doubles, so the naive loop below is the reference's arithmetic."""
+    import ctypes as C
+    import whitebox_b200 as wb
+    L = wb.lib()
+    rng = np.random.default_rng(0)
+
+    def naive(x, a, n, lim):
+        s = 0
+        while s < n and x < lim:
+            x = x + a
+            s += 1
+        return x, s
+
+    cases = [(3.0, 512 * 44100 / 48000, 4096, 1e300), (0.0, 470.4, 4096, 1e6), (1.0, 2.0 ** -30, 3000, 1e300),
+             (2.0 ** 40, 0.75, 2500, 1e300), (5.0, 0.0, 10, 1e300)]
+    for i in range(1500):
+        kind = i % 6
+        if kind == 0:
+            x, a = float(rng.integers(0, 1 << 20)), 512 * 44100 / 48000
+        elif kind == 1:
+            x, a = rng.random() * 1e6, rng.random() * 1000 + 1e-3
+        elif kind == 2:
+            x, a = float(rng.integers(0, 1000)) + 0.25, float(rng.integers(1, 2000)) + 0.5
+        elif kind == 3:
+            x, a = rng.random() * 10, 512 * rng.random() * 4
+        elif kind == 4:
+            x, a = float(2 ** int(rng.integers(0, 30))), 2.0 ** -int(rng.integers(0, 40)) * int(rng.integers(1, 1 << 20))
+        else:
+            x, a = rng.random() * 1e-3, rng.random() * 1e-2
+        n = int(rng.integers(1, 5000))
+        lim = x + a * rng.random() * 6000 if i % 3 else 1e300
+        cases.append((float(x), float(a), n, float(lim)))
+    for x, a, n, lim in cases:
+        want_x, want_s = naive(x, a, n, lim)
+        off = C.c_double(x)
+        got_s = L.wbxh_advance_rounded(C.byref(off), a, n, lim)
+        assert (got_s, off.value) == (want_s, want_x), (x, a, n, lim)

@@ -68,6 +68,7 @@ WBXH_SYMBOLS = [
     "wbxh_play", "wbxh_set_effects", "wbxh_set_impulse_response", "wbxh_set_resampler",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
+    "wbxh_advance_rounded",
 ]
 
 _lib = None
@@ -168,6 +169,8 @@ def lib():
     L.wbxh_level.restype = flt
     L.wbxh_panning_coefs.argtypes = [flt, C.POINTER(flt), C.POINTER(flt)]
     L.wbxh_panning_coefs.restype = None
+    L.wbxh_advance_rounded.argtypes = [C.POINTER(dbl), dbl, u32, dbl]
+    L.wbxh_advance_rounded.restype = u32
     L.wbxh_db_to_linear.argtypes = [flt]
     L.wbxh_db_to_linear.restype = flt
     _lib = L

@@ -17,10 +17,74 @@
 //   peaks     [n_blocks][n_tracks][2] f32 (VUMeter block peaks, engine/vu_meter.h:20-30)
 #pragma once
 #include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define WBX_HD __host__ __device__
+#else
+#define WBX_HD
+#endif
 
 namespace wbx {
 
 constexpr uint32_t kSilent = 0xFFFFFFFFu;
+
+// The sampler's position recurrence `off = fl(off + adv)` (dsp/sampler.cpp:103,209: one rounding per callback), run for
+// up to n callbacks while off < limit; returns the number of steps taken — exactly what the step-by-step loop
+//     while (steps < n && off < limit) { off = off + adv; steps++; }
+// produces, bit for bit, in O(binades crossed) instead of O(n). Inside one binade [2^e, 2^(e+1)) every value is a
+// multiple of u = ulp and fl(x + adv) = x + A*u with A = adv/u rounded to nearest — a fixed integer unless adv/u is
+// exactly halfway (then round-to-even depends on x and the steps are taken for real) — so m steps are x + m*A*u, exact
+// in 64-bit integers. The jump stops a safe margin before the binade's end and before `limit`; the steps in between are
+// real additions. Shared by the host scheduler (wbx_host.cpp) and expand_schedule; both are built without FMA contraction.
+WBX_HD inline uint32_t advance_rounded_impl(double* off_io, double adv, uint32_t n, double limit) {
+  double x = *off_io;
+  uint32_t steps = 0;
+  while (steps < n && x < limit) {
+    bool jumped = false;
+    if (n - steps > 4 && x > 0.0 && adv > 0.0) {
+      uint64_t xb;
+      memcpy(&xb, &x, 8);
+      const uint64_t ex = (xb >> 52) & 0x7FFu;  // biased exponent: x in [2^(ex-1023), 2^(ex-1022))
+      if (ex > 54 && ex < 0x7FEu) {
+        const uint64_t ub = (ex - 52) << 52, hb = (ex + 1) << 52, ib = (2046 - (ex - 52)) << 52;
+        double u, hi, inv_u;
+        memcpy(&u, &ub, 8);      // ulp of the binade
+        memcpy(&hi, &hb, 8);     // binade end
+        memcpy(&inv_u, &ib, 8);  // 1 / u (a power of two as well)
+        const double qa = adv * inv_u;  // scaling by a power of two: exact
+        if (qa >= 16.0 && qa < 4503599627370496.0) {  // 16 <= adv/ulp < 2^52
+          const uint64_t fl = (uint64_t)qa;            // floor (qa > 0)
+          const double frac = qa - (double)fl;         // exact
+          if (frac != 0.5) {
+            const uint64_t A = frac > 0.5 ? fl + 1 : fl;  // adv/u rounded to nearest
+            const double au = (double)A * u;              // exact
+            // every closed-form step must keep the exact sum x_k + adv below the binade end and x_k below limit
+            const double room = (hi < limit ? hi : limit) - x - 2.0 * adv - au;
+            if (room > 0.0) {
+              double m = room / au;
+              const double left = (double)(n - steps);
+              if (m > left) m = left;
+              const uint64_t mi = (uint64_t)m;
+              if (mi >= 1) {
+                const uint64_t X = (uint64_t)(x * inv_u);  // < 2^53, exact
+                x = (double)(X + mi * A) * u;          // <= 2^53 ulps, exact
+                steps += (uint32_t)mi;
+                jumped = true;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (!jumped) {
+      x = x + adv;
+      steps++;
+    }
+  }
+  *off_io = x;
+  return steps;
+}
 
 struct __align__(16) DSpan {
   const void* base;   // frame-interleaved sample data

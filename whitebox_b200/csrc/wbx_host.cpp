@@ -11,6 +11,7 @@
 
 #include "../../include/wbx_engine.hpp"
 #include "../../include/wbx_host.h"
+#include "wbx_device.cuh"
 
 namespace wbx {
 
@@ -433,6 +434,11 @@ uint32_t Engine::quiet_blocks(const Track& t, uint32_t k, uint32_t K) const {
   return (uint32_t)(it - first);
 }
 
+// `while (steps < n && off < limit) { off = off + adv; steps++; }` in O(binades): see advance_rounded_impl (wbx_device.cuh)
+uint32_t advance_rounded(double* off_io, double adv, uint32_t n, double limit) {
+  return advance_rounded_impl(off_io, adv, n, limit);
+}
+
 // q consecutive event-free callbacks: each one is `stream(whole block)` when a sample is playing (:713-719).
 void Engine::stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t q) {
   if (t.current_audio_event.type != EventType::PlaySample || q == 0) return;
@@ -452,10 +458,7 @@ void Engine::stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t
     streamed = calls < (double)q ? (uint32_t)calls : q;
     off = off + (double)streamed * (double)B;
   } else {
-    while (streamed < q && off < count) {  // the reference's own recurrence, one rounding per callback
-      off = off + adv;
-      streamed++;
-    }
+    streamed = advance_rounded(&off, adv, q, count);  // the reference's own recurrence, one rounding per callback
   }
   bool extended = false;
   if (t.open_run >= 0) {
@@ -673,6 +676,10 @@ float wbxh_level(wbxh_engine* h, int track, int channel, int reset) {
   if (reset) h->eng.tracks[track]->level[channel] = 0.0f;
   return v;
 }
+uint32_t wbxh_advance_rounded(double* off, double adv, uint32_t n, double limit) {
+  return wbx::advance_rounded(off, adv, n, limit);
+}
+
 void wbxh_panning_coefs(float pan, float* left, float* right) {
   wbx::PanningCoefficient c = wbx::calculate_panning_coefs(pan);
   *left = c.left;

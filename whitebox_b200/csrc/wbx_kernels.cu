@@ -69,7 +69,8 @@ __device__ __forceinline__ uint32_t clipped_length(double cnt, double pos, doubl
 // One WARP per segment. Unity-speed runs that start on an integer frame advance by exact integer additions, so
 // pos_b = pos0 + b * length in closed form and the lanes take callbacks b = lane, lane + 32, ... Any other run
 // replays the reference's recurrence pos += (double)num_samples * speed, one rounding per callback
-// (sampler.cpp:103,209) — every lane carries the same chain, lane b % 32 writes callback b's cell.
+// (sampler.cpp:103,209) — split over the lanes by callback range, each lane reaching its range's start with the exact
+// per-binade closed form of that recurrence.
 __global__ void expand_schedule(const DSpan* __restrict__ spans, uint32_t n_spans, DCell* __restrict__ cells,
                                 uint32_t n_tracks, uint32_t slots) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -94,17 +95,25 @@ __global__ void expand_schedule(const DSpan* __restrict__ spans, uint32_t n_span
       out[(size_t)b * stride] = c;
     }
   } else {
-    double pos = s.pos0;
-    for (uint32_t b = 0; b < s.n_blocks; b++) {
-      if (pos >= cnt) break;
-      if ((b & 31u) == lane) {
-        DCell c;
-        c.pos = pos;
-        c.span = w;
-        c.n_act = clipped_length(cnt, pos, s.speed, s.length, safe);
-        out[(size_t)b * stride] = c;
+    // lane L owns callbacks [L*chunk, (L+1)*chunk): it jumps to its first one with the exact closed form of the
+    // recurrence (advance_rounded_impl: same values as stepping from callback 0) and steps through its own 1/32
+    const uint32_t chunk = (s.n_blocks + 31) / 32;
+    const uint32_t b0 = lane * chunk;
+    if (b0 < s.n_blocks) {
+      double pos = s.pos0;
+      const uint32_t done = advance_rounded_impl(&pos, adv, b0, cnt);
+      if (done == b0) {  // otherwise the sample was exhausted before this lane's range: its cells stay silent
+        const uint32_t b1 = b0 + chunk < s.n_blocks ? b0 + chunk : s.n_blocks;
+        for (uint32_t b = b0; b < b1; b++) {
+          if (pos >= cnt) break;  // finished streaming; sample_offset_ no longer advances (sampler.cpp:99-100)
+          DCell c;
+          c.pos = pos;
+          c.span = w;
+          c.n_act = clipped_length(cnt, pos, s.speed, s.length, safe);
+          out[(size_t)b * stride] = c;
+          pos = __dadd_rn(pos, adv);  // next_sample_offset (sampler.cpp:103,209)
+        }
       }
-      pos = __dadd_rn(pos, adv);  // next_sample_offset (sampler.cpp:103,209)
     }
   }
 }
