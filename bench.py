@@ -41,6 +41,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result. Libraries write banners to fd 1 behind Python's back (NCCL
+    prints its version there at communicator init), so fd 1 is pointed at stderr for the whole run and the result line
+    goes to a private duplicate of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def peaks_json():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -268,7 +291,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "stereo track-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -536,7 +559,7 @@ def run_ours(args):
         if cpu_val:
             res["cpu_baseline"] = {"value": cpu_val, "unit": "stereo track-frames/s", "cores": 1, "kind": cpu_kind,
                                    "sample": "%d callbacks of the same %d-track workload through Engine::process, 1 thread (the reference mix is single-threaded), %.1fs" % (cpu_blocks, N, cpu_secs)}
-        print(json.dumps(res), flush=True)
+        emit(res)
     if world > 1:
         dist.destroy_process_group()
 
@@ -559,6 +582,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: bus sum over peer memory fused into the mix kernel, or one NCCL all-reduce")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         args.tracks = args.tracks or 1024
         run_reference(args)
