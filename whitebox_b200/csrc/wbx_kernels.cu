@@ -1018,11 +1018,11 @@ template <int P>
 struct FxLayout {
   static constexpr int DEPTH = 4;                      // chunk slots per stage buffer (writer and readers 2 apart)
   static constexpr int ROW = 33;                       // 32 frames + 1 pad: lanes of one phase hit distinct banks
-  static constexpr int ROWS = (5 * DEPTH) * P + DEPTH * P + 1;  // X[0..4], E, one scratch row for idle lanes
+  static constexpr int ROWS = (5 * DEPTH) * P + DEPTH * P;  // X[0..4], E
   static constexpr int WARP_FLOATS = ROWS * ROW;
   __device__ static int x_row(int stage, int slot, int pair) { return (stage * DEPTH + slot) * P + pair; }
   __device__ static int e_row(int slot, int pair) { return (5 * DEPTH + slot) * P + pair; }
-  static constexpr int SCRATCH = (5 * DEPTH) * P + DEPTH * P;
+  static constexpr int IDLE = 0;  // row idle lanes point at (never dereferenced)
 };
 
 template <int P>
@@ -1095,21 +1095,22 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
     const int64_t cb = (int64_t)i - bs, ce = (int64_t)i - 4;
     const int nb = bq_lane ? chunk_len(cb) : 0;
     const int ne = env_lane ? chunk_len(ce) : 0;
-    const float* xin = sm + (nb ? L::x_row(bs, (int)(cb & 3), bp) : L::SCRATCH) * L::ROW;
-    float* xout = sm + (nb ? L::x_row(bs + 1, (int)(cb & 3), bp) : L::SCRATCH) * L::ROW;
-    const float* ein = sm + (ne ? L::x_row(4, (int)(ce & 3), lane) : L::SCRATCH) * L::ROW;
-    float* eout = sm + (ne ? L::e_row((int)(ce & 3), lane) : L::SCRATCH) * L::ROW;
+    const float* xin = sm + (nb ? L::x_row(bs, (int)(cb & 3), bp) : L::IDLE) * L::ROW;
+    float* xout = sm + (nb ? L::x_row(bs + 1, (int)(cb & 3), bp) : L::IDLE) * L::ROW;
+    const float* ein = sm + (ne ? L::x_row(4, (int)(ce & 3), lane) : L::IDLE) * L::ROW;
+    float* eout = sm + (ne ? L::e_row((int)(ce & 3), lane) : L::IDLE) * L::ROW;
     const bool steady = i >= 4 && i + 1 < n_chunks;  // every active lane has a full chunk: no per-frame bounds
     if (steady) {
-      // every active lane has a full chunk; idle lanes run the same instructions on the scratch row (their state is
-      // never stored), so the loop carries no predicates: two independent dependency chains per lane
-      // the chunk is staged in registers: a shared-memory load between dependent FMAs (the compiler cannot move it
-      // above the previous frame's store) would put its latency into every step of the recurrence
+      // every active lane has a full chunk. Idle lanes run the same arithmetic on zeros (their state is never stored):
+      // only the shared-memory accesses are predicated on the lane's role, the recurrences carry no predicate.
+      // The chunk is staged in registers: a shared-memory load between dependent FMAs (the compiler cannot move it
+      // above the previous frame's store) would put its latency into every step of the recurrence.
+      const bool bq = nb != 0, en = ne != 0;
       float xv[32], ev[32];
 #pragma unroll
       for (int q = 0; q < 32; q++) {
-        xv[q] = xin[q];
-        ev[q] = ein[q];
+        xv[q] = bq ? xin[q] : 0.0f;
+        ev[q] = en ? ein[q] : 0.0f;
       }
 #pragma unroll
       for (int q = 0; q < 32; q++) {
@@ -1125,8 +1126,8 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
       }
 #pragma unroll
       for (int q = 0; q < 32; q++) {
-        xout[q] = xv[q];
-        eout[q] = ev[q];
+        if (bq) xout[q] = xv[q];
+        if (en) eout[q] = ev[q];
       }
     } else {
       for (int q = 0; q < 32; q++) {
