@@ -127,6 +127,12 @@ class Engine {
   // receives n_blocks * buffer_size frames; peaks (optional) [n_blocks][n_tracks][2].
   int render(uint32_t n_blocks, float* const* out_channels, float* peaks, double sample_rate = 0.0);
 
+  // render() in two halves, for one thread driving several engines of a sharded setup (include/wbx_sharded.hpp):
+  // render_begin = host schedule + wbx_submit; the caller then runs wbx_mix_sharded_phase(device(), 0..2) in lock step
+  // over all engines; render_end = bus (rank 0; others pass nullptr) / peaks / levels back.
+  int render_begin(uint32_t n_blocks, double sample_rate = 0.0);
+  int render_end(float* const* out_channels, float* peaks);
+
   // Build the segment table for n_blocks callbacks and advance the transport, without touching the device
   // (render = schedule + wbx_render). Exposed for tests, multi-GPU sharding and benchmarks.
   int schedule(uint32_t n_blocks, double sample_rate = 0.0);
@@ -134,6 +140,8 @@ class Engine {
   const std::vector<float>& track_gains() const { return gains_; }
 
   wbx_engine* device() const { return dev_; }
+  uint32_t buffer_size() const { return buffer_size_; }
+  uint32_t out_channels() const { return out_channels_; }
   std::vector<Track*> tracks;
   double ppq = 96.0;
   double playhead = 0, playhead_start = 0, sample_position = 0;
@@ -149,6 +157,8 @@ class Engine {
   void stream(Track& t, uint32_t track_index, uint32_t block, uint32_t num_samples, uint32_t buffer_offset);
   void track_block(Track& t, uint32_t track_index, uint32_t block, double sample_rate, double beat_duration,
                    double start_time, double end_time, double block_sample_position, bool currently_playing);
+  int prepare(uint32_t n_blocks, double sample_rate);
+  void merge_levels();
   uint32_t quiet_blocks(const Track& t, uint32_t k, uint32_t K) const;
   void fill_fade(wbx_segment& s, const AudioClip* clip, uint64_t clip_frame) const;
   void stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t q);

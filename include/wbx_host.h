@@ -50,6 +50,11 @@ void wbxh_set_fast_forward(wbxh_engine* h, int on);
 /* n_blocks consecutive Engine::process callbacks: out_channels[c] -> n_blocks*block_frames f32 (clamped bus),
  * peaks (optional) [n_blocks][n_tracks][2]. */
 int wbxh_render(wbxh_engine* h, uint32_t n_blocks, float* const* out_channels, float* peaks);
+/* wbxh_render in two halves for one thread driving several engines of a sharded setup (wbx.h "sharded render"):
+ * begin = host schedule + wbx_submit; then wbx_mix_sharded_phase(wbxh_device(h), 0..2) in lock step over all engines;
+ * end = bus (rank 0 only, others pass NULL) / peaks / levels back. */
+int wbxh_render_begin(wbxh_engine* h, uint32_t n_blocks);
+int wbxh_render_end(wbxh_engine* h, float* const* out_channels, float* peaks);
 /* host scheduling only: builds the wbx_segment table + track gains for n_blocks callbacks and advances the
  * transport; pointers stay valid until the next call on this engine. */
 int wbxh_schedule(wbxh_engine* h, uint32_t n_blocks, const wbx_segment** segs, uint32_t* n_segs,

@@ -633,3 +633,39 @@ def test_sharded_two_devices_one_process(wb):
         out, _ = devs[0].fetch(False)
         devs[1].synchronize()
         assert same_bits(out, want)
+
+
+# ---- every golden scenario through a sharded session (tracks dealt over 3 engines, bus exchange over peer memory) -------
+
+@pytest.mark.parametrize("name", sorted(sc.ALL))
+def test_golden_sharded_session(wb, golden_dir, name):
+    """whitebox_b200.shard.ShardedEngine (= include/wbx_sharded.hpp): the same editing / transport calls, tracks i % 3 on
+    three engines, master bus from the exchange. Against the reference's golden vectors: VU peaks bit-exact, bus within
+    the re-association tolerance (the partial buses are added in rank order, not track order)."""
+    from whitebox_b200 import shard
+    gold = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    made = []
+
+    def make(C, B, r, bpm):
+        eng = shard.ShardedEngine([0, 0, 0], C, B, r, bpm, max_blocks=4096)
+        made.append(eng)
+        return eng
+
+    res = sc.ALL[name](make)
+    assert_tree(res, gold, name + " (3 shards)")
+    for eng in made:
+        eng.close()
+
+
+def test_cpp_sharded_demo(wb, tmp_path):
+    """examples/sharded_demo.cpp: wbx::ShardedEngine (header-only C++) with 2 shards == one wbx::Engine within tolerance,
+    through Engine::process-shaped calls."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "sharded_demo")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "sharded_demo.cpp"),
+                    "-L" + os.path.join(root, "whitebox_b200"), "-lwbx", "-Wl,-rpath," + os.path.join(root, "whitebox_b200"),
+                    "-o", exe], check=True)
+    r = subprocess.run([exe, "48", "12"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sharded == single within tolerance" in r.stdout

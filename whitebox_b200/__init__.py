@@ -68,7 +68,7 @@ WBXH_SYMBOLS = [
     "wbxh_play", "wbxh_set_effects", "wbxh_set_impulse_response", "wbxh_set_resampler",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
-    "wbxh_advance_rounded",
+    "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end",
 ]
 
 _lib = None
@@ -159,6 +159,8 @@ def lib():
     L.wbxh_set_fast_forward.argtypes = [vp, i32]
     L.wbxh_set_fast_forward.restype = None
     L.wbxh_render.argtypes = [vp, u32, pp, vp]
+    L.wbxh_render_begin.argtypes = [vp, u32]
+    L.wbxh_render_end.argtypes = [vp, pp, vp]
     L.wbxh_schedule.argtypes = [vp, u32, pp, C.POINTER(u32), pp]
     L.wbxh_sampler_offset.argtypes = [vp, i32]
     L.wbxh_sampler_offset.restype = dbl
@@ -492,6 +494,18 @@ class Engine:
                                     peaks.ctypes.data if (peaks is not None and self.n_tracks) else None))
         if self.dev is not None:  # keep the device view's shape in step (fetch / fetch_interleaved after render)
             self.dev.C, self.dev.B, self.dev.n_tracks, self.dev.n_blocks = self.C, self.B, self.n_tracks, n_blocks
+        return out, peaks
+
+    def render_begin(self, n_blocks):
+        """First half of render() for lock-step sharded rendering (whitebox_b200.shard.ShardedEngine)."""
+        self._ck(self.L.wbxh_render_begin(self.h, n_blocks))
+        self.dev.C, self.dev.B, self.dev.n_tracks, self.dev.n_blocks = self.C, self.B, self.n_tracks, n_blocks
+
+    def render_end(self, n_blocks, want_bus=True, want_peaks=True):
+        out = np.empty((self.C, n_blocks * self.B), np.float32) if want_bus else None
+        peaks = np.zeros((n_blocks, self.n_tracks, 2), np.float32) if want_peaks else None
+        self._ck(self.L.wbxh_render_end(self.h, _chan_ptrs(out) if want_bus else None,
+                                        peaks.ctypes.data if (peaks is not None and self.n_tracks) else None))
         return out, peaks
 
     def process(self, n_blocks):

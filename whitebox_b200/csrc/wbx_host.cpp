@@ -548,7 +548,8 @@ int Engine::schedule(uint32_t n_blocks, double sample_rate) {
   return WBX_OK;
 }
 
-int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, double sample_rate) {
+// track count + edited effect chains -> device, then the host schedule of the next n_blocks callbacks
+int Engine::prepare(uint32_t n_blocks, double sample_rate) {
   if (!dev_) return WBX_ERR_NO_DEVICE;
   if (n_blocks == 0) return WBX_ERR_INVALID;
   const uint32_t N = (uint32_t)tracks.size();
@@ -567,17 +568,49 @@ int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, 
     if (rc) return rc;
     t.effects_dirty = false;
   }
-  schedule(n_blocks, sample_rate);
+  return schedule(n_blocks, sample_rate);
+}
+
+// VUMeter::push_samples: level only rises until the UI reads it (vu_meter.h:25-29)
+void Engine::merge_levels() {
+  const uint32_t N = (uint32_t)tracks.size();
+  for (uint32_t i = 0; i < N; i++)
+    for (uint32_t c = 0; c < 2; c++)
+      if (tracks[i]->level[c] < levels_[2 * i + c]) tracks[i]->level[c] = levels_[2 * i + c];
+}
+
+int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, double sample_rate) {
+  int rc = prepare(n_blocks, sample_rate);
+  if (rc) return rc;
+  const uint32_t N = (uint32_t)tracks.size();
   // submit + mix + bus/peaks/levels back under one synchronise; on an engine that is part of a sharded setup
   // (wbx_shard_*) the mix is the sharded one and only rank 0 receives the master bus
   if (N) levels_.resize((size_t)N * 2);
   rc = wbx_render_levels(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n_blocks, out_channels, peaks,
                          N ? levels_.data() : nullptr);
   if (rc) return rc;
-  // VUMeter::push_samples: level only rises until the UI reads it (vu_meter.h:25-29)
-  for (uint32_t i = 0; i < N; i++)
-    for (uint32_t c = 0; c < 2; c++)
-      if (tracks[i]->level[c] < levels_[2 * i + c]) tracks[i]->level[c] = levels_[2 * i + c];
+  merge_levels();
+  return WBX_OK;
+}
+
+// render() in two halves for a thread that drives several sharded engines (wbx_sharded.hpp): render_begin on every
+// engine, the phases of wbx_mix_sharded_phase on every engine's device(), render_end on every engine.
+int Engine::render_begin(uint32_t n_blocks, double sample_rate) {
+  int rc = prepare(n_blocks, sample_rate);
+  if (rc) return rc;
+  return wbx_submit(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n_blocks);
+}
+
+int Engine::render_end(float* const* out_channels, float* peaks) {
+  if (!dev_) return WBX_ERR_NO_DEVICE;
+  const uint32_t N = (uint32_t)tracks.size();
+  int rc = wbx_fetch(dev_, out_channels, peaks);
+  if (rc) return rc;
+  if (N) {
+    levels_.resize((size_t)N * 2);
+    if ((rc = wbx_fetch_levels(dev_, levels_.data()))) return rc;
+    merge_levels();
+  }
   return WBX_OK;
 }
 
@@ -654,6 +687,9 @@ void wbxh_set_playhead(wbxh_engine* h, double beat) { h->eng.set_playhead_positi
 void wbxh_play(wbxh_engine* h) { h->eng.play(); }
 void wbxh_stop(wbxh_engine* h) { h->eng.stop(); }
 void wbxh_set_fast_forward(wbxh_engine* h, int on) { h->eng.fast_forward = on != 0; }
+
+int wbxh_render_begin(wbxh_engine* h, uint32_t n_blocks) { return h->eng.render_begin(n_blocks); }
+int wbxh_render_end(wbxh_engine* h, float* const* out_channels, float* peaks) { return h->eng.render_end(out_channels, peaks); }
 
 int wbxh_render(wbxh_engine* h, uint32_t n_blocks, float* const* out_channels, float* peaks) {
   return h->eng.render(n_blocks, out_channels, peaks);

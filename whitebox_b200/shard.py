@@ -65,3 +65,127 @@ def mix_sharded_lockstep(devs):
     for phase in (0, 1, 2):
         for d in devs:
             d.mix_sharded(phase)
+
+
+class ShardedEngine:
+    """One process, several GPUs (or several shards on one GPU): the host engine API of whitebox_b200.Engine in front of
+    `len(devices)` engines. Track i lives on shard i % W; a sample is uploaded to a shard the first time one of that
+    shard's clips uses it; every render runs the peer-memory bus exchange (include/wbx.h "sharded render") in lock step
+    from this thread. Python twin of include/wbx_sharded.hpp, with the scenario API the parity tests drive."""
+
+    def __init__(self, devices, out_channels=2, block=512, rate=48000, bpm=120.0, max_blocks=64, sum_mode=None):
+        from . import Engine, SUM_EXACT
+        self.C, self.B, self.rate = out_channels, block, rate
+        self.W = len(devices)
+        self.shards = [Engine(out_channels, block, rate, bpm, device=d, sum_mode=SUM_EXACT if sum_mode is None else sum_mode)
+                       for d in devices]
+        self.max_blocks = max_blocks
+        for r, e in enumerate(self.shards):
+            e.dev.shard_init(r, self.W, max_blocks)
+        devs = [e.dev for e in self.shards]
+        for e in self.shards:
+            e.dev.shard_connect_local(devs)
+        self.tracks = []      # global track index -> (shard, local index)
+        self.samples = []     # global sample id -> (data, rate, fmt, {shard: local id})
+
+    def close(self):
+        for e in self.shards:
+            e.close()
+
+    def add_track(self, volume_db=0.0, pan=0.0, mute=False):
+        s = len(self.tracks) % self.W
+        self.tracks.append((s, self.shards[s].add_track(volume_db, pan, mute)))
+        return len(self.tracks) - 1
+
+    def add_sample(self, data, rate, fmt=None):
+        from . import FMT_F32
+        self.samples.append((data, rate, FMT_F32 if fmt is None else fmt, {}))
+        return len(self.samples) - 1
+
+    def _resident(self, sample, shard):
+        data, rate, fmt, where = self.samples[sample]
+        if shard not in where:
+            where[shard] = self.shards[shard].add_sample(data, rate, fmt)
+        return where[shard]
+
+    def add_clip(self, track, sample, min_beat, max_beat, start_offset=0.0, speed=1.0, gain=1.0, fade_start=0.0,
+                 fade_end=0.0):
+        s, t = self.tracks[track]
+        return self.shards[s].add_clip(t, self._resident(sample, s), min_beat, max_beat, start_offset, speed, gain,
+                                       fade_start, fade_end)
+
+    def _track(self, track):
+        s, t = self.tracks[track]
+        return self.shards[s], t
+
+    def set_volume(self, t, db):
+        e, i = self._track(t)
+        e.set_volume(i, db)
+
+    def set_pan(self, t, pan):
+        e, i = self._track(t)
+        e.set_pan(i, pan)
+
+    def set_mute(self, t, m):
+        e, i = self._track(t)
+        e.set_mute(i, m)
+
+    def set_effects(self, t, params):
+        e, i = self._track(t)
+        e.set_effects(i, params)
+
+    def set_impulse_response(self, h):
+        for e in self.shards:
+            e.set_impulse_response(h)
+
+    def set_resampler(self, mode):
+        for e in self.shards:
+            e.set_resampler(mode)
+
+    def set_playhead(self, beat):
+        for e in self.shards:
+            e.set_playhead(beat)
+
+    def play(self):
+        for e in self.shards:
+            e.play()
+
+    def stop(self):
+        for e in self.shards:
+            e.stop()
+
+    def sampler_offset(self, t):
+        e, i = self._track(t)
+        return e.sampler_offset(i)
+
+    def sample_position(self):
+        return self.shards[0].sample_position()
+
+    def playhead(self):
+        return self.shards[0].playhead()
+
+    def level(self, t, c, reset=False):
+        e, i = self._track(t)
+        return e.level(i, c, reset)
+
+    def render(self, n_blocks):
+        """-> (master bus [C][n_blocks*B] from rank 0, peaks [n_blocks][N][2] re-assembled in session track order)."""
+        assert n_blocks <= self.max_blocks
+        for e in self.shards:
+            e.render_begin(n_blocks)
+        mix_sharded_lockstep([e.dev for e in self.shards])
+        out = None
+        peaks = np.zeros((n_blocks, len(self.tracks), 2), np.float32)
+        for r, e in enumerate(self.shards):
+            o, p = e.render_end(n_blocks, want_bus=(r == 0))
+            if r == 0:
+                out = o
+            for g, (s, t) in enumerate(self.tracks):
+                if s == r:
+                    peaks[:, g, :] = p[:, t, :]
+        return out, peaks
+
+    def process(self, n_blocks):
+        """Scenario API shared with the CPU checkers: -> (out [K][C][B], peaks [K][N][2])."""
+        out, peaks = self.render(n_blocks)
+        return np.ascontiguousarray(out.reshape(self.C, n_blocks, self.B).transpose(1, 0, 2)), peaks
