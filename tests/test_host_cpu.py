@@ -230,3 +230,24 @@ def test_position_recurrence_closed_form_is_exact():
         off = C.c_double(x)
         got_s = L.wbxh_advance_rounded(C.byref(off), a, n, lim)
         assert (got_s, off.value) == (want_s, want_x), (x, a, n, lim)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """The driver parses stdout of `bench.py --impl reference`: exactly one line, JSON, with the contract's keys; everything
+    else (progress, library banners) goes to stderr."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-blocks", "64", "--tracks", "32"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

@@ -111,6 +111,10 @@ struct wbx_engine {
   float* levels_ptr = nullptr;
   // one-callback render: table bytes the next mix's ingest kernel still has to pull from h_spans (0 = already on the device)
   size_t ingest_bytes = 0;
+  // the staging table (h_spans) is read asynchronously by the H2D copy / ingest kernel: the next submit waits for that
+  // read before it overwrites the table (matters for callers that submit again without fetching in between)
+  cudaEvent_t staging_read = nullptr;
+  bool staging_busy = false;
   std::vector<uint32_t> slot_busy;  // [track][slot] -> first free block
   uint32_t slot_cap = 0;
   // last submit
@@ -287,6 +291,11 @@ int wbx_create(wbx_engine** out, int device_ordinal) {
     return WBX_ERR_CUDA;
   }
   e->stream = e->own_stream;
+  if (cudaEventCreateWithFlags(&e->staging_read, cudaEventDisableTiming) != cudaSuccess) {
+    cudaStreamDestroy(e->own_stream);
+    delete e;
+    return WBX_ERR_CUDA;
+  }
   // polyphase coefficient table (extension, include/wbx.h): h[ph][k] = sinc(u) * blackman(u), u = (k - 7) - ph / 128,
   // unit DC gain per phase, designed in f64 (same formulas as oracle/wb_oracle.c design_polyphase)
   {
@@ -331,6 +340,7 @@ int wbx_destroy(wbx_engine* e) {
     if (b->p) cudaFree(b->p);
   for (HostBuf* b : {&e->h_spans, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
     if (b->p) cudaFreeHost(b->p);
+  if (e->staging_read) cudaEventDestroy(e->staging_read);
   cudaStreamDestroy(e->own_stream);
   delete e;
   return WBX_OK;
@@ -703,6 +713,10 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   int rc;
 
   // ---- validate + resolve segments into spans (pinned staging), assign cell slots --------------------
+  if (e->staging_busy) {  // the previous table may still be being read by its copy / ingest kernel
+    CU(e, cudaEventSynchronize(e->staging_read));
+    e->staging_busy = false;
+  }
   if ((rc = sync_effects(e))) return rc;
   const uint32_t n_fx = e->n_fx;
   // one page-locked table, one H2D copy: spans | track gains | (one-callback render: the cells, written here on the
@@ -825,8 +839,11 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   e->ingest_bytes = 0;
   if (host_cells && !n_fx && !getenv("WBX_NO_INGEST"))
     e->ingest_bytes = (span_bytes + gain_bytes + cell_bytes + 15) & ~(size_t)15;
-  else
+  else {
     CU(e, cudaMemcpyAsync(e->d_spans.p, hs, span_bytes + gain_bytes + cell_bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaEventRecord(e->staging_read, e->stream));
+    e->staging_busy = true;
+  }
   if (!host_cells) {
     if (n_cells) CU(e, cudaMemsetAsync(e->d_cells.p, 0xFF, n_cells * sizeof(DCell), e->stream));  // span = kSilent
     if (n_segs && N) {
@@ -912,9 +929,14 @@ static int do_mix(wbx_engine* e, uint32_t flags, bool sharded) {
   if (e->ingest_bytes && cudaHostGetDevicePointer(&host_view, e->h_spans.p, 0) == cudaSuccess && host_view) {
     CU(e, launch_ingest(host_view, e->d_spans.p, e->ingest_bytes, e->d_zero.p, zero_bytes, e->stream));
     e->launches++;
+    CU(e, cudaEventRecord(e->staging_read, e->stream));
+    e->staging_busy = true;
   } else {
-    if (e->ingest_bytes)
+    if (e->ingest_bytes) {
       CU(e, cudaMemcpyAsync(e->d_spans.p, e->h_spans.p, e->ingest_bytes, cudaMemcpyHostToDevice, e->stream));
+      CU(e, cudaEventRecord(e->staging_read, e->stream));
+      e->staging_busy = true;
+    }
     CU(e, cudaMemsetAsync(e->d_zero.p, 0, zero_bytes, e->stream));
   }
   e->ingest_bytes = 0;
