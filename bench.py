@@ -454,9 +454,9 @@ def run_ours(args):
         eng.stop()
         eng.play()
         if world == 1:  # the public call: host scheduling, H2D table, expand, mix, D2H bus + VU levels
-            return eng.render(K, want_peaks=False, out=pinned_out.array)
+            return eng.render(K, want_peaks=False, out=out_host)
         if exchange == "peer":  # the public call on every rank; rank 0 receives the master bus
-            return eng.render(K, want_peaks=False, out=pinned_out.array if rank == 0 else None, want_bus=(rank == 0))
+            return eng.render(K, want_peaks=False, out=out_host if rank == 0 else None, want_bus=(rank == 0))
         segs2, gains2 = eng.schedule(K)
         dev.submit(segs2, gains2, K)
         mix_step()
@@ -467,6 +467,33 @@ def run_ours(args):
         return None, None
 
     pinned_out = wb.PinnedArray((2, K * BLOCK))
+    out_host = pinned_out.array
+    host_output = "page-locked channels written by the mix kernel" if world == 1 else "copied from rank 0's master bus"
+    shm_path = None
+    if exchange == "peer":
+        # one host output buffer shared by all ranks (/dev/shm segment, registered with CUDA by every process): each owner
+        # stores its reduced slice there over its own PCIe link, nobody copies the whole bus
+        shm_path = "/dev/shm/wbx_bench_%s" % os.environ.get("MASTER_PORT", "0")
+        ok = 1
+        try:
+            if rank == 0:
+                np.memmap(shm_path, dtype=np.float32, mode="w+", shape=(2, K * BLOCK)).flush()
+        except Exception as ex:
+            log("rank 0: cannot create %s (%s)" % (shm_path, ex))
+        dist.barrier()
+        try:
+            shared = np.memmap(shm_path, dtype=np.float32, mode="r+", shape=(2, K * BLOCK))
+            if dev.L.wbx_host_register(shared.ctypes.data, shared.nbytes) != 0:
+                raise RuntimeError("cudaHostRegister of the shared segment failed")
+        except Exception as ex:
+            log("rank %d: shared host output unavailable (%s) - rank 0 copies the master bus instead" % (rank, ex))
+            ok = 0
+        t_ok = torch.tensor([ok], device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 1:
+            dev.shard_set_host_output(shared)
+            out_host = shared
+            host_output = "shared page-locked segment, every owner rank stores its slice of the master bus into it"
     with torch.cuda.stream(stream):
         for _ in range(2):
             e2e_step(False)
@@ -541,7 +568,7 @@ def run_ours(args):
                 "out_frames_per_s": value / (N * world), "realtime_x": value / (N * world) / RATE,
                 "l2": "inputs larger than L2 (%.2f GiB streamed per step per GPU vs 126 MB)" % (alg_bytes / 2**30),
                 "kernel": kernel_name, "parallelism": ("tracks sharded x%d, %s" % (world, "bus exchange over peer memory fused into the mix kernel (tiles stored into the owner rank's buffer, flag barrier, owner reduce + clamp into rank 0)" if exchange == "peer" else "1 NCCL all-reduce of the bus")) if world > 1 else "1 GPU",
-                "bus_exchange": exchange,
+                "bus_exchange": exchange, "e2e_host_output": host_output,
                 "e2e_equals_device_run": same,
             },
             "roofline": roofline,
@@ -561,6 +588,9 @@ def run_ours(args):
                                    "sample": "%d callbacks of the same %d-track workload through Engine::process, 1 thread (the reference mix is single-threaded), %.1fs" % (cpu_blocks, N, cpu_secs)}
         emit(res)
     if world > 1:
+        dist.barrier()
+        if shm_path and rank == 0 and os.path.exists(shm_path):
+            os.remove(shm_path)
         dist.destroy_process_group()
 
 

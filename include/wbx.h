@@ -250,6 +250,15 @@ int wbx_mix_sharded(wbx_engine* e);
  *   0  mix into the owners' exchange buffers + arrival signal      1  wait, reduce own slice + clamp into the master
  *   bus, signal      2  wait. wbx_mix_sharded(e) = phases 0, 1, 2 back to back (one process or thread per GPU). */
 int wbx_mix_sharded_phase(wbx_engine* e, int phase);
+/* Optional: the host buffer the master bus is wanted in (channels[c] -> frames_per_channel f32, page-locked and mapped on
+ * this engine's device: wbx_host_alloc memory within one process, or a shared-memory segment every process registered with
+ * wbx_host_register). Set on EVERY rank, each with its own mapping of the SAME buffer: an owner then also stores its reduced
+ * slice there (over its own PCIe link) and rank 0's wbx_fetch / wbx_render into exactly these channels copies nothing.
+ * channels == NULL clears it. Renders longer than frames_per_channel fall back to the copy from rank 0's master bus. */
+int wbx_shard_set_host_output(wbx_engine* e, float* const* channels, uint64_t frames_per_channel);
+/* cudaHostRegister(portable | mapped) / cudaHostUnregister for caller-owned host memory (e.g. a shared-memory segment) */
+int wbx_host_register(void* p, size_t bytes);
+int wbx_host_unregister(void* p);
 int wbx_shard_close(wbx_engine* e);
 /* rank / world of a connected sharded setup, (0, 1) otherwise */
 int wbx_shard_info(const wbx_engine* e, uint32_t* rank, uint32_t* world);

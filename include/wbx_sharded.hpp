@@ -91,6 +91,18 @@ class ShardedEngine {
   // n_blocks consecutive callbacks; out_channels[c] receives n_blocks * buffer_size clamped frames of the master bus.
   int render(uint32_t n_blocks, float* const* out_channels, double sample_rate = 0.0) {
     if (n_blocks > max_blocks_) return WBX_ERR_INVALID;
+    // page-locked output channels (wbx_host_alloc): every owner shard stores its slice of the master bus into them itself
+    const uint64_t frames = (uint64_t)n_blocks * shards_[0]->buffer_size();
+    if (out_channels && (out_channels[0] != host_out_[0] || out_channels[1 % shards_[0]->out_channels()] != host_out_[1] ||
+                         frames > host_frames_)) {
+      bool ok = true;
+      for (uint32_t r = 0; r < world(); r++) ok = wbx_shard_set_host_output(shards_[r]->device(), out_channels, frames) == WBX_OK && ok;
+      if (!ok)  // pageable channels: rank 0 copies the master bus instead
+        for (uint32_t r = 0; r < world(); r++) wbx_shard_set_host_output(shards_[r]->device(), nullptr, 0);
+      host_out_[0] = out_channels[0];
+      host_out_[1] = out_channels[1 % shards_[0]->out_channels()];
+      host_frames_ = frames;
+    }
     for (uint32_t r = 0; r < world(); r++)
       if (int rc = fail_on(r, shards_[r]->render_begin(n_blocks, sample_rate))) return rc;
     for (int phase = 0; phase < 3; phase++)  // every engine finishes a phase's enqueue before any starts the next
@@ -108,6 +120,8 @@ class ShardedEngine {
   }
   std::vector<std::unique_ptr<Engine>> shards_;
   uint32_t n_tracks_ = 0, max_blocks_ = 0, err_shard_ = 0;
+  float* host_out_[2] = {nullptr, nullptr};  // output channels the shards were last pointed at
+  uint64_t host_frames_ = 0;
 };
 
 }  // namespace wbx

@@ -530,12 +530,22 @@ def test_sharded_peer_memory_exchange(wb, world, K, B, C):
         dev.shard_init(r, world, K + 3)
     for dev in devs:
         dev.shard_connect_local(devs)
+    host = wb.PinnedArray((C, K * B))
     for rep in range(3):  # epochs advance; buffers are reused
+        if rep == 2:  # owners also mirror their slices into one host buffer every rank maps: rank 0 copies nothing
+            host.array[:] = 9.0
+            for dev in devs:
+                dev.shard_set_host_output(host.array)
         for dev, (segs, gains) in zip(devs, parts):
             dev.submit(segs, gains, K)
         shard.mix_sharded_lockstep(devs)
         out, pk0 = devs[0].fetch(True)
         assert same_bits(out, want), "sharded master bus (repeat %d)" % rep
+        if rep == 2:
+            assert devs[0].L.wbx_fetch(devs[0].h, wb._chan_ptrs(host.array), None) == 0
+            for dev in devs[1:]:
+                dev.synchronize()
+            assert same_bits(host.array, want), "host output written by the owner ranks"
         assert same_bits(pk0, partial[0][1])
         for r in range(1, world):
             _, pk = devs[r].fetch(True, want_bus=False)

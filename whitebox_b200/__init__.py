@@ -60,7 +60,8 @@ WBX_SYMBOLS = [
     "wbx_mix", "wbx_fetch", "wbx_fetch_levels", "wbx_host_alloc", "wbx_host_free", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
     "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel", "wbx_effects_design", "wbx_set_track_effects",
     "wbx_set_impulse_response", "wbx_render_levels", "wbx_shard_init", "wbx_shard_connect_ipc",
-    "wbx_shard_connect_local", "wbx_mix_sharded", "wbx_mix_sharded_phase", "wbx_shard_close", "wbx_shard_info",
+    "wbx_shard_connect_local", "wbx_mix_sharded", "wbx_mix_sharded_phase", "wbx_shard_set_host_output", "wbx_host_register",
+    "wbx_host_unregister", "wbx_shard_close", "wbx_shard_info",
 ]
 WBXH_SYMBOLS = [
     "wbxh_create", "wbxh_destroy", "wbxh_last_error", "wbxh_device", "wbxh_add_track", "wbxh_set_volume",
@@ -110,6 +111,9 @@ def lib():
     L.wbx_mix_sharded.argtypes = [vp]
     L.wbx_mix_sharded_phase.argtypes = [vp, i32]
     L.wbx_shard_close.argtypes = [vp]
+    L.wbx_shard_set_host_output.argtypes = [vp, pp, u64]
+    L.wbx_host_register.argtypes = [vp, C.c_size_t]
+    L.wbx_host_unregister.argtypes = [vp]
     L.wbx_shard_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     L.wbx_submit.argtypes = [vp, vp, u32, vp, u32]
     L.wbx_mix.argtypes = [vp, u32]
@@ -337,6 +341,14 @@ class DeviceEngine:
     def mix_sharded(self, phase=None):
         """The collective sharded mix; phase 0/1/2 = its three stages (one thread driving several engines)."""
         self._ck(self.L.wbx_mix_sharded(self.h) if phase is None else self.L.wbx_mix_sharded_phase(self.h, phase))
+
+    def shard_set_host_output(self, out):
+        """out: [C][frames] f32 array in page-locked memory every rank maps (PinnedArray within one process, a registered
+        shared-memory segment across processes), or None to clear."""
+        if out is None:
+            self._ck(self.L.wbx_shard_set_host_output(self.h, None, 0))
+        else:
+            self._ck(self.L.wbx_shard_set_host_output(self.h, _chan_ptrs(out), out.shape[1]))
 
     def shard_close(self):
         self._ck(self.L.wbx_shard_close(self.h))

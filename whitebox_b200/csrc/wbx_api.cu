@@ -87,6 +87,9 @@ struct Shard {
   void* peer_block[kMaxPeers] = {nullptr};
   bool peer_ipc[kMaxPeers] = {false};
   uint32_t epoch = 0;
+  float* host_out[2] = {nullptr, nullptr};       // device view of the host output channels (wbx_shard_set_host_output)
+  float* host_out_host[2] = {nullptr, nullptr};  // ... and the host pointers they were given as
+  uint64_t host_out_frames = 0;
   uint32_t* status = nullptr;  // page-locked host word raised by a barrier that timed out
   unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
 };
@@ -887,6 +890,8 @@ static ShardPeers shard_peers(const Shard& sh) {
   }
   peers.dst[0] = (float*)((uint8_t*)sh.peer_block[0] + sh.bus_off);  // rank 0 holds the master bus
   peers.n_dst = 1;
+  peers.host_dst[0] = sh.host_out[0];
+  peers.host_dst[1] = sh.host_out[1];
   return peers;
 }
 
@@ -1000,7 +1005,8 @@ static int shard_phase(wbx_engine* e, int phase) {
   Shard& sh = e->shard;
   if (e->shard_phase != phase) return fail(e, WBX_ERR_INVALID, "sharded mix: phase %d called in phase %d", phase, e->shard_phase);
   CU(e, cudaSetDevice(e->device));
-  const ShardPeers peers = shard_peers(sh);
+  ShardPeers peers = shard_peers(sh);
+  if ((uint64_t)e->n_blocks * e->B > sh.host_out_frames) peers.host_dst[0] = peers.host_dst[1] = nullptr;
   CU(e, launch_shard_wait(peers, sh.rank, sh.world, sh.epoch, sh.timeout_ns, sh.status, e->stream));
   e->launches++;
   if (phase == 1) {
@@ -1097,9 +1103,12 @@ int wbx_fetch(wbx_engine* e, float* const* out_channels, float* peaks) {
     if (!bus) return fail(e, WBX_ERR_INVALID, "wbx_fetch: after a sharded mix only rank 0 holds the master bus");
     bool direct = true;  // page-locked caller buffers (wbx_host_alloc) take the D2H copy directly
     bool written = true;  // ... unless the mix kernel already wrote them (wbx_render's mirror)
+    const bool by_owners = e->shard_result && chan_floats <= e->shard.host_out_frames;
     for (uint32_t c = 0; c < e->C; c++) {
       direct = direct && out_channels[c] && is_pinned(out_channels[c]);
-      written = written && out_channels[c] && e->mirror[c] && e->mirror_host[c] == out_channels[c];
+      written = written && out_channels[c] &&
+                ((e->mirror[c] && e->mirror_host[c] == out_channels[c]) ||
+                 (by_owners && e->shard.host_out[c] && e->shard.host_out_host[c] == out_channels[c]));
     }
     if (written) {
     } else if (direct) {
@@ -1145,7 +1154,8 @@ int wbx_fetch_levels(wbx_engine* e, float* levels) {
 
 void* wbx_host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+  // portable + mapped: every device of the process can copy to / store into it (sharded renders mirror into it)
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
@@ -1313,6 +1323,46 @@ int wbx_shard_connect_local(wbx_engine* e, wbx_engine* const* engines) {
     sh.peer_ipc[j] = false;
   }
   sh.connected = true;
+  return WBX_OK;
+}
+
+int wbx_shard_set_host_output(wbx_engine* e, float* const* channels, uint64_t frames_per_channel) {
+  if (!e) return WBX_ERR_INVALID;
+  Shard& sh = e->shard;
+  if (!sh.on) return fail(e, WBX_ERR_INVALID, "wbx_shard_set_host_output before wbx_shard_init");
+  CU(e, cudaSetDevice(e->device));
+  for (int c = 0; c < 2; c++) sh.host_out[c] = sh.host_out_host[c] = nullptr;
+  sh.host_out_frames = 0;
+  if (!channels || frames_per_channel == 0) return WBX_OK;
+  for (uint32_t c = 0; c < e->C; c++) {
+    void* dv = nullptr;
+    if (!channels[c] || !is_pinned(channels[c]) || cudaHostGetDevicePointer(&dv, channels[c], 0) != cudaSuccess || !dv) {
+      cudaGetLastError();
+      for (int q = 0; q < 2; q++) sh.host_out[q] = sh.host_out_host[q] = nullptr;
+      return fail(e, WBX_ERR_INVALID, "wbx_shard_set_host_output: channel %u is not page-locked memory mapped on device %d", c, e->device);
+    }
+    sh.host_out[c] = (float*)dv;
+    sh.host_out_host[c] = channels[c];
+  }
+  sh.host_out_frames = frames_per_channel;
+  return WBX_OK;
+}
+
+int wbx_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return WBX_ERR_INVALID;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+    cudaGetLastError();
+    return WBX_ERR_CUDA;
+  }
+  return WBX_OK;
+}
+
+int wbx_host_unregister(void* p) {
+  if (!p) return WBX_ERR_INVALID;
+  if (cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return WBX_ERR_CUDA;
+  }
   return WBX_OK;
 }
 

@@ -187,6 +187,8 @@ struct ShardPeers {
   uint32_t* flags[kMaxPeers];  // flags[j] = rank j's arrival words [kMaxPeers]
   float* dst[kMaxPeers];       // master-bus copies the reduced slices are written to (dst[0..n_dst))
   uint32_t n_dst;
+  float* host_dst[2];          // optional: the host output channels (page-locked, mapped on this device) — the owner also
+                               // stores its slice there, so no rank copies the whole bus to the host afterwards
 };
 
 }  // namespace wbx

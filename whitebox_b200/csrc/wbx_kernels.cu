@@ -1370,6 +1370,13 @@ __global__ void shard_reduce_kernel(const float* __restrict__ xchg, uint32_t W, 
         else
           out[i] = acc[0];
       }
+      if (peers.host_dst[c]) {  // posted stores over this rank's own PCIe link
+        float* out = peers.host_dst[c] + dst_off;
+        if constexpr (V == 4)
+          reinterpret_cast<float4*>(out)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else
+          out[i] = acc[0];
+      }
     }
   }
 }
@@ -1715,7 +1722,9 @@ cudaError_t launch_shard_reduce(const float* xchg, uint32_t W, uint32_t C, uint6
                                 const ShardPeers& peers, uint64_t chan_stride, uint64_t dst_off, int n_sm,
                                 cudaStream_t stream) {
   if (valid == 0) return cudaSuccess;
-  const bool v4 = (plane % 4 == 0) && (valid % 4 == 0) && (chan_stride % 4 == 0) && (dst_off % 4 == 0);
+  bool v4 = (plane % 4 == 0) && (valid % 4 == 0) && (chan_stride % 4 == 0) && (dst_off % 4 == 0);
+  for (int c = 0; c < 2; c++)
+    if (peers.host_dst[c] && ((uintptr_t)peers.host_dst[c] & 15u)) v4 = false;
   const uint64_t n = v4 ? valid / 4 : valid;
   uint64_t blocks = (n + 255) / 256;
   if (blocks > (uint64_t)n_sm * 8) blocks = (uint64_t)n_sm * 8;
