@@ -831,40 +831,65 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
       if (prev == p.groups - 1) {
         __threadfence();
         const float2* base = reinterpret_cast<const float2*>(p.ws) + (size_t)tile_id * p.groups * 2 * (L::T / 2);
-        for (int c = 0; c < (two ? 2 : 1); c++) {
+        // This warp is the tail of the whole render, and every load below is an L2 round trip: keep many in flight. All
+        // (channel, frame-pair) combinations of GB groups are loaded together, then added per output element in group
+        // order (the association is unchanged: partial 0, 1, 2, ... for every element).
+        // (512-frame tiles keep one group per batch: tree order at that tile size is a corner case and the hot exact-order
+        // path of that instantiation must not lose registers to it)
+        constexpr int NP = FPL / 2;                      // frame pairs per lane and channel
+        constexpr int GB = FPL <= 8 ? 32 / (2 * NP) : 1;  // groups per batch: <= 32 float2 in flight
+        const int nc = two ? 2 : 1;
+        float2 sum[2][NP];
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int i = 0; i < NP; i++) sum[c][i] = make_float2(0.f, 0.f);
+        for (uint32_t g0 = 0; g0 < p.groups; g0 += GB) {
+          float2 v[GB][2][NP];
+#pragma unroll
+          for (int u = 0; u < GB; u++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+              for (int i = 0; i < NP; i++)
+                v[u][c][i] = (g0 + u < p.groups && c < nc)
+                                 ? __ldcg(base + ((size_t)(g0 + u) * 2 + c) * (L::T / 2) + lane + 32 * i)
+                                 : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < GB; u++) {
+            if (g0 + u < p.groups) {
+#pragma unroll
+              for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                  sum[c][i].x = __fadd_rn(sum[c][i].x, v[u][c][i].x);
+                  sum[c][i].y = __fadd_rn(sum[c][i].y, v[u][c][i].y);
+                }
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          if (c >= nc) break;
           float* out = outp[c];
           float* mir = p.mirror[c] ? p.mirror[c] + out_off : nullptr;
-          for (int i = 0; i < FPL / 2; i++) {
-            const int q = lane + 32 * i;
-            const int fr = 2 * q;
-            // partials added in group order; loads issued eight groups at a time so their latencies overlap
-            float2 sum = make_float2(0.f, 0.f);
-            for (uint32_t g0 = 0; g0 < p.groups; g0 += 8) {
-              float2 v[8];
 #pragma unroll
-              for (uint32_t u = 0; u < 8; u++)
-                v[u] = (g0 + u < p.groups) ? __ldcg(base + ((size_t)(g0 + u) * 2 + c) * (L::T / 2) + q) : make_float2(0.f, 0.f);
-#pragma unroll
-              for (uint32_t u = 0; u < 8; u++) {
-                if (g0 + u < p.groups) {
-                  sum.x = __fadd_rn(sum.x, v[u].x);
-                  sum.y = __fadd_rn(sum.y, v[u].y);
-                }
-              }
-            }
+          for (int i = 0; i < NP; i++) {
+            const int fr = 2 * (lane + 32 * i);
+            float2 r = sum[c][i];
             if (p.clamp) {
-              sum.x = sum.x > 1.0f ? 1.0f : (sum.x < -1.0f ? -1.0f : sum.x);
-              sum.y = sum.y > 1.0f ? 1.0f : (sum.y < -1.0f ? -1.0f : sum.y);
+              r.x = r.x > 1.0f ? 1.0f : (r.x < -1.0f ? -1.0f : r.x);
+              r.y = r.y > 1.0f ? 1.0f : (r.y < -1.0f ? -1.0f : r.y);
             }
             if (vec_ok && fr + 1 < tile_len) {
-              *reinterpret_cast<float2*>(out + fr) = sum;
-              if (mir) *reinterpret_cast<float2*>(mir + fr) = sum;
+              *reinterpret_cast<float2*>(out + fr) = r;
+              if (mir) *reinterpret_cast<float2*>(mir + fr) = r;
             } else {
-              if (fr < tile_len) out[fr] = sum.x;
-              if (fr + 1 < tile_len) out[fr + 1] = sum.y;
+              if (fr < tile_len) out[fr] = r.x;
+              if (fr + 1 < tile_len) out[fr + 1] = r.y;
               if (mir) {
-                if (fr < tile_len) mir[fr] = sum.x;
-                if (fr + 1 < tile_len) mir[fr + 1] = sum.y;
+                if (fr < tile_len) mir[fr] = r.x;
+                if (fr + 1 < tile_len) mir[fr + 1] = r.y;
               }
             }
           }
