@@ -1042,7 +1042,12 @@ __device__ __forceinline__ float fx_gain(float x, float env, float thr, float ma
 template <int P>
 struct FxLayout {
   static constexpr int DEPTH = 4;                      // chunk slots per stage buffer (writer and readers 2 apart)
-  static constexpr int ROW = 33;                       // 32 frames + 1 pad: lanes of one phase hit distinct banks
+  // 32 frames + pad. P <= 4: 36 — rows stay 16-B aligned for 128-bit accesses and the rows a quarter-warp touches
+  // start 4 banks apart (measured 16.0 -> 14.5 ms at 512 tracks). P = 8: 33 — with all 32 lanes active the 36-float
+  // stride is a 4-way bank conflict (measured 11.7 -> 13.2 ms at 4096 tracks), so that size keeps scalar accesses with
+  // one row per bank.
+  static constexpr int ROW = P <= 4 ? 36 : 33;
+  static constexpr bool VEC = ROW % 4 == 0;
   static constexpr int ROWS = (5 * DEPTH) * P + DEPTH * P;  // X[0..4], E
   static constexpr int WARP_FLOATS = ROWS * ROW;
   __device__ static int x_row(int stage, int slot, int pair) { return (stage * DEPTH + slot) * P + pair; }
@@ -1050,16 +1055,30 @@ struct FxLayout {
   static constexpr int IDLE = 0;  // row idle lanes point at (never dereferenced)
 };
 
-template <int P>
+// DUO: the P pairs are carried by a TEAM of two warps on different schedulers — warp 0 runs only the recurrences, warp 1
+// the input loads, the gain computer and the stores — meeting at a named barrier once per chunk; the chunk slots each
+// side touches within an iteration are disjoint (same schedule as the one-warp form). Used while the session is too
+// small to give every scheduler of the GPU a warp otherwise: the step is bound by per-warp latency, not by issue slots.
+template <int P, bool DUO>
 __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t frames,
                                                        float* __restrict__ trackbuf) {
   using L = FxLayout<P>;
-  extern __shared__ float fx_smem[];
+  extern __shared__ __align__(16) float fx_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sm = fx_smem + (size_t)warp * L::WARP_FLOATS;
+  const int team = DUO ? warp >> 1 : warp;
+  const int teams_per_cta = DUO ? (int)(blockDim.x >> 6) : (int)(blockDim.x >> 5);
+  const bool do_rec = !DUO || (warp & 1) == 0;  // this warp runs the recurrences
+  const bool do_io = !DUO || (warp & 1) == 1;   // this warp loads, computes gains and stores
+  float* sm = fx_smem + (size_t)team * L::WARP_FLOATS;
   const uint32_t n_pairs = n_fx * C;
-  const uint32_t pair0 = (blockIdx.x * (blockDim.x >> 5) + warp) * P;
-  if (pair0 >= n_pairs) return;
+  const uint32_t pair0 = (blockIdx.x * teams_per_cta + team) * P;
+  if (pair0 >= n_pairs) return;  // both warps of a team leave together
+  auto team_sync = [&]() {
+    if (DUO)
+      asm volatile("bar.sync %0, 64;" ::"r"(team + 1) : "memory");
+    else
+      __syncwarp();
+  };
 
   // biquad role: lane = p*4 + s
   const int bp = lane >> 2, bs = lane & 3;
@@ -1103,18 +1122,31 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
     const uint64_t left = frames - (uint64_t)c * 32;
     return left < 32 ? (int)left : 32;
   };
-  // chunk 0 into X[0][0]
+  // input chunk c (one frame per lane) of pair r; the track buffer is larger than L2, so every chunk is an HBM round trip
+  auto load_chunk = [&](uint64_t c, int r) -> float {
+    const uint64_t f = c * 32 + lane;
+    return (do_io && pair0 + r < n_pairs && f < frames) ? buf[r][f * 2] : 0.0f;
+  };
+  // chunk 0 into X[0][0]; chunks 1 and 2 on their way (the loop keeps three chunks in flight in registers)
+  float nxt0[P], nxt1[P];
+  if (do_io) {
 #pragma unroll
-  for (int r = 0; r < P; r++)
-    if (pair0 + r < n_pairs && (uint64_t)lane < frames) sm[L::x_row(0, 0, r) * L::ROW + lane] = buf[r][(size_t)lane * 2];
-  __syncwarp();
+    for (int r = 0; r < P; r++)
+      if (pair0 + r < n_pairs && (uint64_t)lane < frames) sm[L::x_row(0, 0, r) * L::ROW + lane] = buf[r][(size_t)lane * 2];
+  }
+#pragma unroll
+  for (int r = 0; r < P; r++) {
+    nxt0[r] = load_chunk(1, r);
+    nxt1[r] = load_chunk(2, r);
+  }
+  team_sync();
 
   for (uint64_t i = 0; i < n_chunks + 5; i++) {
-    // next chunk's input: loads in flight during this iteration's recurrences
-    float nxt[P];
-    const uint64_t fn = (i + 1) * 32 + lane;
+    // input of chunk i+3: issued now, stored into its slot two iterations from now — an HBM latency is longer than one
+    // iteration of the recurrences
+    float nxt2[P];
 #pragma unroll
-    for (int r = 0; r < P; r++) nxt[r] = (pair0 + r < n_pairs && fn < frames) ? buf[r][fn * 2] : 0.0f;
+    for (int r = 0; r < P; r++) nxt2[r] = load_chunk(i + 3, r);
 
     // ---- recurrences: biquad s on chunk i-s, envelope on chunk i-4 -------------------------------------------
     const int64_t cb = (int64_t)i - bs, ce = (int64_t)i - 4;
@@ -1125,17 +1157,28 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
     const float* ein = sm + (ne ? L::x_row(4, (int)(ce & 3), lane) : L::IDLE) * L::ROW;
     float* eout = sm + (ne ? L::e_row((int)(ce & 3), lane) : L::IDLE) * L::ROW;
     const bool steady = i >= 4 && i + 1 < n_chunks;  // every active lane has a full chunk: no per-frame bounds
-    if (steady) {
+    if (!do_rec) {
+    } else if (steady) {
       // every active lane has a full chunk. Idle lanes run the same arithmetic on zeros (their state is never stored):
       // only the shared-memory accesses are predicated on the lane's role, the recurrences carry no predicate.
       // The chunk is staged in registers: a shared-memory load between dependent FMAs (the compiler cannot move it
       // above the previous frame's store) would put its latency into every step of the recurrence.
       const bool bq = nb != 0, en = ne != 0;
       float xv[32], ev[32];
+      if constexpr (L::VEC) {
 #pragma unroll
-      for (int q = 0; q < 32; q++) {
-        xv[q] = bq ? xin[q] : 0.0f;
-        ev[q] = en ? ein[q] : 0.0f;
+        for (int q = 0; q < 32; q += 4) {  // 128-bit shared-memory accesses: 8 + 8 loads instead of 32 + 32
+          const float4 a = bq ? *reinterpret_cast<const float4*>(xin + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 e4 = en ? *reinterpret_cast<const float4*>(ein + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xv[q] = a.x, xv[q + 1] = a.y, xv[q + 2] = a.z, xv[q + 3] = a.w;
+          ev[q] = e4.x, ev[q + 1] = e4.y, ev[q + 2] = e4.z, ev[q + 3] = e4.w;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+          xv[q] = bq ? xin[q] : 0.0f;
+          ev[q] = en ? ein[q] : 0.0f;
+        }
       }
 #pragma unroll
       for (int q = 0; q < 32; q++) {
@@ -1149,10 +1192,18 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
         env = xa > env ? __fmaf_rn(att, d, xa) : __fmaf_rn(rel, d, xa);
         ev[q] = env;
       }
+      if constexpr (L::VEC) {
 #pragma unroll
-      for (int q = 0; q < 32; q++) {
-        if (bq) xout[q] = xv[q];
-        if (en) eout[q] = ev[q];
+        for (int q = 0; q < 32; q += 4) {
+          if (bq) *reinterpret_cast<float4*>(xout + q) = make_float4(xv[q], xv[q + 1], xv[q + 2], xv[q + 3]);
+          if (en) *reinterpret_cast<float4*>(eout + q) = make_float4(ev[q], ev[q + 1], ev[q + 2], ev[q + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+          if (bq) xout[q] = xv[q];
+          if (en) eout[q] = ev[q];
+        }
       }
     } else {
       for (int q = 0; q < 32; q++) {
@@ -1173,7 +1224,7 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
     }
     // ---- gain computer + store of chunk i-5, one frame per lane ------------------------------------------------
     const int64_t cg = (int64_t)i - 5;
-    const int ng = chunk_len(cg);
+    const int ng = do_io ? chunk_len(cg) : 0;
     if (lane < ng) {
 #pragma unroll
       for (int r = 0; r < P; r++) {
@@ -1184,11 +1235,19 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
       }
     }
     // ---- stage the next input chunk -------------------------------------------------------------------------------
+    if (do_io) {
 #pragma unroll
-    for (int r = 0; r < P; r++) sm[L::x_row(0, (int)((i + 1) & 3), r) * L::ROW + lane] = nxt[r];
-    __syncwarp();
+      for (int r = 0; r < P; r++) sm[L::x_row(0, (int)((i + 1) & 3), r) * L::ROW + lane] = nxt0[r];
+    }
+#pragma unroll
+    for (int r = 0; r < P; r++) {
+      nxt0[r] = nxt1[r];
+      nxt1[r] = nxt2[r];
+    }
+    team_sync();
   }
 
+  if (!do_rec) return;
   if (bq_lane && eq_on) {
     const uint32_t g = pair0 + bp;
     DFx* f = fx + g / C;
@@ -1201,15 +1260,16 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
   }
 }
 
-template <int P>
+template <int P, bool DUO>
 static cudaError_t launch_effects_p(DFx* fx, uint32_t n_fx, uint32_t C, uint64_t frames, float* trackbuf, cudaStream_t stream) {
   constexpr int WARPS = 4;
-  const size_t smem = (size_t)FxLayout<P>::WARP_FLOATS * WARPS * sizeof(float);
-  auto kfn = effects_kernel<P>;
+  constexpr int TEAMS = DUO ? WARPS / 2 : WARPS;  // teams (= shared-memory regions) per CTA
+  const size_t smem = (size_t)FxLayout<P>::WARP_FLOATS * TEAMS * sizeof(float);
+  auto kfn = effects_kernel<P, DUO>;
   cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  const uint32_t warps = (n_fx * C + P - 1) / P;
-  kfn<<<(warps + WARPS - 1) / WARPS, WARPS * 32, smem, stream>>>(fx, n_fx, C, frames, trackbuf);
+  const uint32_t teams = (n_fx * C + P - 1) / P;
+  kfn<<<(teams + TEAMS - 1) / TEAMS, WARPS * 32, smem, stream>>>(fx, n_fx, C, frames, trackbuf);
   return cudaGetLastError();
 }
 
@@ -1228,11 +1288,14 @@ static cudaError_t launch_effects_chain(DFx* fx, uint32_t n_fx, uint32_t C, uint
     const int v = atoi(env);
     if (v == 1 || v == 2 || v == 4 || v == 8) P = v;
   }
+  // two-warp teams while that still leaves at most ~two warps per scheduler
+  bool duo = (pairs + P - 1) / P <= slots;
+  if (const char* env = getenv("WBX_FX_DUO")) duo = atoi(env) != 0;
   switch (P) {
-    case 1: return launch_effects_p<1>(fx, n_fx, C, frames, trackbuf, stream);
-    case 2: return launch_effects_p<2>(fx, n_fx, C, frames, trackbuf, stream);
-    case 4: return launch_effects_p<4>(fx, n_fx, C, frames, trackbuf, stream);
-    default: return launch_effects_p<8>(fx, n_fx, C, frames, trackbuf, stream);
+    case 1: return duo ? launch_effects_p<1, true>(fx, n_fx, C, frames, trackbuf, stream) : launch_effects_p<1, false>(fx, n_fx, C, frames, trackbuf, stream);
+    case 2: return duo ? launch_effects_p<2, true>(fx, n_fx, C, frames, trackbuf, stream) : launch_effects_p<2, false>(fx, n_fx, C, frames, trackbuf, stream);
+    case 4: return duo ? launch_effects_p<4, true>(fx, n_fx, C, frames, trackbuf, stream) : launch_effects_p<4, false>(fx, n_fx, C, frames, trackbuf, stream);
+    default: return duo ? launch_effects_p<8, true>(fx, n_fx, C, frames, trackbuf, stream) : launch_effects_p<8, false>(fx, n_fx, C, frames, trackbuf, stream);
   }
 }
 
