@@ -961,6 +961,40 @@ __global__ void render_tracks_kernel(const DSpan* __restrict__ spans, const DCel
   const uint32_t e = (uint32_t)(w / K), k = (uint32_t)(w % K);
   const uint32_t t = fx[e].track;
   float2* out = reinterpret_cast<float2*>(trackbuf) + ((size_t)e * K + k) * B;
+  if (S == 1) {  // one Sampler::stream call per callback (the steady state): cell and span read once per warp
+    const DCell cell = cells[(size_t)k * N + t];
+    if (cell.span == kSilent) {
+      for (uint32_t j = lane; j < B; j += 32) out[j] = make_float2(0.0f, 0.0f);
+      return;
+    }
+    const DSpan sp = spans[cell.span];
+    const uint32_t lo = sp.dst_off, hi = sp.dst_off + cell.n_act;
+    if (sp.fmt == F_F32 && sp.nch == 2 && sp.speed == 1.0 && sp.fade == 0 && C == 2) {
+      // unity-speed stereo f32 clip: a scaled copy — the same rounded operations as stream_value (src * gain, then the
+      // add into the cleared mixing buffer: 0 + m)
+      const float2* src = reinterpret_cast<const float2*>(sp.base) + (int64_t)(uint32_t)(int64_t)cell.pos;
+      for (uint32_t j = lane; j < B; j += 32) {
+        float2 v = make_float2(0.0f, 0.0f);
+        if (j >= lo && j < hi) {
+          const float2 x = src[j - lo];
+          v.x = __fadd_rn(0.0f, __fmul_rn(x.x, sp.gain));
+          v.y = __fadd_rn(0.0f, __fmul_rn(x.y, sp.gain));
+        }
+        out[j] = v;
+      }
+      return;
+    }
+    for (uint32_t j = lane; j < B; j += 32) {
+      float2 v = make_float2(0.0f, 0.0f);
+      if (j >= lo && j < hi) {
+        const int32_t jj = (int32_t)(j - lo);
+        v.x = __fadd_rn(v.x, stream_value(sp, cell, jj, 0, k - sp.block0, poly, C == 2));
+        if (C == 2) v.y = __fadd_rn(v.y, stream_value(sp, cell, jj, 1, k - sp.block0, poly, true));
+      }
+      out[j] = v;
+    }
+    return;
+  }
   for (uint32_t j = lane; j < B; j += 32) {
     float2 v = make_float2(0.0f, 0.0f);
     for (uint32_t s = 0; s < S; s++) {
