@@ -602,6 +602,20 @@ def test_sharded_errors(wb):
     dev.mix_sharded()
     out, _ = dev.fetch(False)
     assert not out.any()
+    # host output: pageable memory is refused, registered memory is accepted and written by the owner's reduce
+    plain = np.full((2, 2 * 512), 5.0, np.float32)
+    with pytest.raises(wb.WbxError):
+        dev.shard_set_host_output(plain)
+    assert dev.L.wbx_host_register(plain.ctypes.data, plain.nbytes) == 0
+    dev.shard_set_host_output(plain)
+    dev.mix_sharded()
+    assert dev.L.wbx_fetch(dev.h, wb._chan_ptrs(plain), None) == 0
+    assert not plain.any()
+    dev.shard_set_host_output(None)
+    assert dev.L.wbx_host_unregister(plain.ctypes.data) == 0
+    assert dev.L.wbx_host_register(None, 16) != 0
+    with pytest.raises(wb.WbxError):
+        dev.mix_sharded(2)  # phase out of order
 
 
 def test_sharded_two_devices_one_process(wb):

@@ -1150,15 +1150,16 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
     buf[r] = trackbuf + (size_t)(g / C) * frames * 2 + (g % C);
   }
 
-  const uint64_t n_chunks = (frames + 31) / 32;
-  auto chunk_len = [&](int64_t c) -> int {
-    if (c < 0 || (uint64_t)c >= n_chunks) return 0;
-    const uint64_t left = frames - (uint64_t)c * 32;
-    return left < 32 ? (int)left : 32;
+  // chunk counters are 32-bit: 2^32 chunks of 32 frames is 33 days of 48 kHz audio in one render
+  const uint32_t n_chunks = (uint32_t)((frames + 31) / 32);
+  const int last_len = (int)(frames - (uint64_t)(n_chunks ? n_chunks - 1 : 0) * 32);
+  auto chunk_len = [&](int32_t c) -> int {
+    if (c < 0 || (uint32_t)c >= n_chunks) return 0;
+    return (uint32_t)c + 1 == n_chunks ? last_len : 32;
   };
   // input chunk c (one frame per lane) of pair r; the track buffer is larger than L2, so every chunk is an HBM round trip
-  auto load_chunk = [&](uint64_t c, int r) -> float {
-    const uint64_t f = c * 32 + lane;
+  auto load_chunk = [&](uint32_t c, int r) -> float {
+    const uint64_t f = (uint64_t)c * 32 + lane;
     return (do_io && pair0 + r < n_pairs && f < frames) ? buf[r][f * 2] : 0.0f;
   };
   // chunk 0 into X[0][0]; chunks 1 and 2 on their way (the loop keeps three chunks in flight in registers)
@@ -1175,7 +1176,7 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
   }
   team_sync();
 
-  for (uint64_t i = 0; i < n_chunks + 5; i++) {
+  for (uint32_t i = 0; i < n_chunks + 5; i++) {
     // input of chunk i+3: issued now, stored into its slot two iterations from now — an HBM latency is longer than one
     // iteration of the recurrences
     float nxt2[P];
@@ -1183,14 +1184,14 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
     for (int r = 0; r < P; r++) nxt2[r] = load_chunk(i + 3, r);
 
     // ---- recurrences: biquad s on chunk i-s, envelope on chunk i-4 -------------------------------------------
-    const int64_t cb = (int64_t)i - bs, ce = (int64_t)i - 4;
-    const int nb = bq_lane ? chunk_len(cb) : 0;
-    const int ne = env_lane ? chunk_len(ce) : 0;
+    const bool steady = i >= 5 && i + 1 < n_chunks;  // every role has a full chunk this iteration: no bounds work
+    const int32_t cb = (int32_t)i - bs, ce = (int32_t)i - 4;
+    const int nb = bq_lane ? (steady ? 32 : chunk_len(cb)) : 0;
+    const int ne = env_lane ? (steady ? 32 : chunk_len(ce)) : 0;
     const float* xin = sm + (nb ? L::x_row(bs, (int)(cb & 3), bp) : L::IDLE) * L::ROW;
     float* xout = sm + (nb ? L::x_row(bs + 1, (int)(cb & 3), bp) : L::IDLE) * L::ROW;
     const float* ein = sm + (ne ? L::x_row(4, (int)(ce & 3), lane) : L::IDLE) * L::ROW;
     float* eout = sm + (ne ? L::e_row((int)(ce & 3), lane) : L::IDLE) * L::ROW;
-    const bool steady = i >= 4 && i + 1 < n_chunks;  // every active lane has a full chunk: no per-frame bounds
     if (!do_rec) {
     } else if (steady) {
       // every active lane has a full chunk. Idle lanes run the same arithmetic on zeros (their state is never stored):
@@ -1257,15 +1258,15 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
       }
     }
     // ---- gain computer + store of chunk i-5, one frame per lane ------------------------------------------------
-    const int64_t cg = (int64_t)i - 5;
-    const int ng = do_io ? chunk_len(cg) : 0;
+    const int32_t cg = (int32_t)i - 5;
+    const int ng = do_io ? (steady ? 32 : chunk_len(cg)) : 0;
     if (lane < ng) {
 #pragma unroll
       for (int r = 0; r < P; r++) {
         if (pair0 + r >= n_pairs) break;
         const float x = sm[L::x_row(4, (int)(cg & 3), r) * L::ROW + lane];
         const float e = sm[L::e_row((int)(cg & 3), r) * L::ROW + lane];
-        buf[r][((size_t)cg * 32 + lane) * 2] = comp_on[r] ? fx_gain(x, e, thr[r], makeup[r], code[r]) : x;
+        buf[r][((size_t)(uint32_t)cg * 32 + lane) * 2] = comp_on[r] ? fx_gain(x, e, thr[r], makeup[r], code[r]) : x;
       }
     }
     // ---- stage the next input chunk -------------------------------------------------------------------------------
