@@ -16,7 +16,7 @@
 namespace wbx {
 cudaError_t launch_mix(const MixParams& p, int fpl, int n_sm, cudaStream_t stream, int* ctas_out);
 cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, uint32_t n_tracks, uint32_t slots,
-                          cudaStream_t stream);
+                          uint32_t n_blocks, cudaStream_t stream);
 cudaError_t launch_clamp(float* x, uint64_t n, int n_sm, cudaStream_t stream);
 cudaError_t launch_levels(const float* peaks, uint32_t K, uint32_t NC, float* levels, cudaStream_t stream);
 cudaError_t launch_interleave(const float* bus, uint64_t frames, uint32_t channels, int fmt, void* dst, int n_sm,
@@ -850,8 +850,8 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   if (!host_cells) {
     if (n_cells) CU(e, cudaMemsetAsync(e->d_cells.p, 0xFF, n_cells * sizeof(DCell), e->stream));  // span = kSilent
     if (n_segs && N) {
-      CU(e, launch_expand((const DSpan*)e->d_spans.p, n_segs, e->cells_ptr, N, slots, e->stream));
-      e->launches++;
+      CU(e, launch_expand((const DSpan*)e->d_spans.p, n_segs, e->cells_ptr, N, slots, n_blocks, e->stream));
+      e->launches += (n_blocks >= 64 && n_segs >= 32) ? 2 : 1;
     }
   }
   if (n_fx && N) {

@@ -71,8 +71,41 @@ __device__ __forceinline__ uint32_t clipped_length(double cnt, double pos, doubl
 // replays the reference's recurrence pos += (double)num_samples * speed, one rounding per callback
 // (sampler.cpp:103,209) — split over the lanes by callback range, each lane reaching its range's start with the exact
 // per-binade closed form of that recurrence.
+__device__ __forceinline__ bool span_closed_form(const DSpan& s) {
+  return s.speed == 1.0 && floor(s.pos0) == s.pos0 && s.pos0 + (double)s.n_blocks * (double)s.length < 4.0e15;
+}
+
+// Closed-form runs of a long render, one LANE per span: consecutive spans are consecutive tracks in the common case, so
+// the 32 cells a warp writes for one callback are one coalesced 512-byte store (the warp-per-span form below writes
+// cells n_tracks * slots * 16 B apart). blockIdx.y selects a range of 64 callbacks.
+__global__ void expand_closed_kernel(const DSpan* __restrict__ spans, uint32_t n_spans, DCell* __restrict__ cells,
+                                     uint32_t n_tracks, uint32_t slots, uint32_t n_blocks) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_spans) return;
+  const DSpan s = spans[i];
+  if (!span_closed_form(s)) return;
+  const double cnt = (double)s.count;
+  const double len = (double)s.length;
+  const double safe = __dmul_rn(len + 1.0, s.speed);
+  const size_t stride = (size_t)n_tracks * slots;
+  DCell* out = cells + (size_t)s.track * slots + s.slot;
+  const uint32_t lo = blockIdx.y * 64u > s.block0 ? blockIdx.y * 64u : s.block0;
+  uint32_t hi = blockIdx.y * 64u + 64u;
+  if (hi > n_blocks) hi = n_blocks;
+  if (hi > s.block0 + s.n_blocks) hi = s.block0 + s.n_blocks;
+  for (uint32_t k = lo; k < hi; k++) {
+    const double pos = s.pos0 + (double)(k - s.block0) * len;  // exact
+    if (pos >= cnt) break;  // finished streaming; sample_offset_ no longer advances (sampler.cpp:99-100)
+    DCell c;
+    c.pos = pos;
+    c.span = i;
+    c.n_act = clipped_length(cnt, pos, s.speed, s.length, safe);
+    out[(size_t)k * stride] = c;
+  }
+}
+
 __global__ void expand_schedule(const DSpan* __restrict__ spans, uint32_t n_spans, DCell* __restrict__ cells,
-                                uint32_t n_tracks, uint32_t slots) {
+                                uint32_t n_tracks, uint32_t slots, uint32_t skip_closed) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (w >= n_spans) return;
@@ -83,7 +116,8 @@ __global__ void expand_schedule(const DSpan* __restrict__ spans, uint32_t n_span
   const double safe = __dmul_rn(len + 1.0, s.speed);
   DCell* out = cells + ((size_t)s.block0 * n_tracks + s.track) * slots + s.slot;
   const size_t stride = (size_t)n_tracks * slots;
-  const bool closed = s.speed == 1.0 && floor(s.pos0) == s.pos0 && s.pos0 + (double)s.n_blocks * len < 4.0e15;
+  const bool closed = span_closed_form(s);
+  if (closed && skip_closed) return;  // written by expand_closed_kernel
   if (closed) {
     for (uint32_t b = lane; b < s.n_blocks; b += 32) {
       const double pos = s.pos0 + (double)b * len;  // exact
@@ -1782,9 +1816,15 @@ cudaError_t launch_interleave_sample(const void* planar, size_t plane_bytes, uin
 }
 
 cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, uint32_t n_tracks, uint32_t slots,
-                          cudaStream_t stream) {
+                          uint32_t n_blocks, cudaStream_t stream) {
   if (n_spans == 0) return cudaSuccess;
-  expand_schedule<<<(n_spans + 3) / 4, 128, 0, stream>>>(spans, n_spans, cells, n_tracks, slots);  // warp per span
+  // long renders: closed-form runs lane-per-span (coalesced cell stores), everything else warp-per-span
+  const uint32_t split = n_blocks >= 64 && n_spans >= 32 ? 1u : 0u;
+  if (split) {
+    const dim3 grid((n_spans + 127) / 128, (n_blocks + 63) / 64);
+    expand_closed_kernel<<<grid, 128, 0, stream>>>(spans, n_spans, cells, n_tracks, slots, n_blocks);
+  }
+  expand_schedule<<<(n_spans + 3) / 4, 128, 0, stream>>>(spans, n_spans, cells, n_tracks, slots, split);  // warp per span
   return cudaGetLastError();
 }
 
