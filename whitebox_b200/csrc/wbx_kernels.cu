@@ -18,6 +18,8 @@
 // x86-64 build (no FMA contraction); the arithmetic that decides parity also uses explicit _rn intrinsics.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include <cstdint>
 #include <cstdlib>
 
@@ -1123,27 +1125,32 @@ struct FxLayout {
   static constexpr int IDLE = 0;  // row idle lanes point at (never dereferenced)
 };
 
-// DUO: the P pairs are carried by a TEAM of two warps on different schedulers — warp 0 runs only the recurrences, warp 1
-// the input loads, the gain computer and the stores — meeting at a named barrier once per chunk; the chunk slots each
-// side touches within an iteration are disjoint (same schedule as the one-warp form). Used while the session is too
-// small to give every scheduler of the GPU a warp otherwise: the step is bound by per-warp latency, not by issue slots.
-template <int P, bool DUO>
-__global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t frames,
+// T > 1: the P pairs are carried by a TEAM of T warps on different schedulers, meeting at a named barrier once per chunk;
+// the chunk slots each role touches within an iteration are disjoint (same schedule as the one-warp form).
+//   T = 2: warp 0 runs the recurrences, warp 1 the input loads, the gain computer and the stores;
+//   T = 3: the envelope followers get their own warp (ptxas schedules the two recurrences of one warp mostly one after
+//          the other instead of interleaving them, and moving the followers to the I/O warp just moves the long pole).
+// Used while the session is too small to give every scheduler of the GPU a warp otherwise: the step is then bound by
+// per-warp latency, not by issue slots.
+template <int P, int T>
+__global__ void __launch_bounds__(T == 3 ? 192 : 128) effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t frames,
                                                        float* __restrict__ trackbuf) {
   using L = FxLayout<P>;
   extern __shared__ __align__(16) float fx_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int team = DUO ? warp >> 1 : warp;
-  const int teams_per_cta = DUO ? (int)(blockDim.x >> 6) : (int)(blockDim.x >> 5);
-  const bool do_rec = !DUO || (warp & 1) == 0;  // this warp runs the recurrences
-  const bool do_io = !DUO || (warp & 1) == 1;   // this warp loads, computes gains and stores
+  constexpr bool DUO = T > 1;  // (kept as a name for "several warps per team")
+  const int team = warp / T, role = warp % T;
+  const int teams_per_cta = (int)(blockDim.x >> 5) / T;
+  const bool do_rec = T == 1 || role == 0;                       // this warp runs the biquads
+  const bool do_io = T == 1 || role == 1;                        // this warp loads, computes gains and stores
+  const bool do_env = T == 1 || (T == 2 ? role == 0 : role == 2);  // this warp runs the envelope followers
   float* sm = fx_smem + (size_t)team * L::WARP_FLOATS;
   const uint32_t n_pairs = n_fx * C;
   const uint32_t pair0 = (blockIdx.x * teams_per_cta + team) * P;
   if (pair0 >= n_pairs) return;  // both warps of a team leave together
   auto team_sync = [&]() {
     if (DUO)
-      asm volatile("bar.sync %0, 64;" ::"r"(team + 1) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(32 * T) : "memory");
     else
       __syncwarp();
   };
@@ -1220,60 +1227,80 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
     // ---- recurrences: biquad s on chunk i-s, envelope on chunk i-4 -------------------------------------------
     const bool steady = i >= 5 && i + 1 < n_chunks;  // every role has a full chunk this iteration: no bounds work
     const int32_t cb = (int32_t)i - bs, ce = (int32_t)i - 4;
-    const int nb = bq_lane ? (steady ? 32 : chunk_len(cb)) : 0;
-    const int ne = env_lane ? (steady ? 32 : chunk_len(ce)) : 0;
+    const int nb = (bq_lane && do_rec) ? (steady ? 32 : chunk_len(cb)) : 0;
+    const int ne = (env_lane && do_env) ? (steady ? 32 : chunk_len(ce)) : 0;
     const float* xin = sm + (nb ? L::x_row(bs, (int)(cb & 3), bp) : L::IDLE) * L::ROW;
     float* xout = sm + (nb ? L::x_row(bs + 1, (int)(cb & 3), bp) : L::IDLE) * L::ROW;
     const float* ein = sm + (ne ? L::x_row(4, (int)(ce & 3), lane) : L::IDLE) * L::ROW;
     float* eout = sm + (ne ? L::e_row((int)(ce & 3), lane) : L::IDLE) * L::ROW;
-    if (!do_rec) {
-    } else if (steady) {
-      // every active lane has a full chunk. Idle lanes run the same arithmetic on zeros (their state is never stored):
-      // only the shared-memory accesses are predicated on the lane's role, the recurrences carry no predicate.
-      // The chunk is staged in registers: a shared-memory load between dependent FMAs (the compiler cannot move it
-      // above the previous frame's store) would put its latency into every step of the recurrence.
+    // One steady-state pass over a full chunk for the roles this warp holds. Idle lanes run the same arithmetic on zeros
+    // (their state is never stored): only the shared-memory accesses are predicated on the lane's role, the recurrences
+    // carry no predicate. The chunk is staged in registers: a shared-memory load between dependent FMAs (the compiler
+    // cannot move it above the previous frame's store) would put its latency into every step of the recurrence.
+    auto steady_pass = [&](auto bq_tag, auto en_tag) {
+      constexpr bool BQ = decltype(bq_tag)::value, EN = decltype(en_tag)::value;
       const bool bq = nb != 0, en = ne != 0;
-      float xv[32], ev[32];
+      float xv[BQ ? 32 : 1], ev[EN ? 32 : 1];
       if constexpr (L::VEC) {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {  // 128-bit shared-memory accesses: 8 + 8 loads instead of 32 + 32
-          const float4 a = bq ? *reinterpret_cast<const float4*>(xin + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 e4 = en ? *reinterpret_cast<const float4*>(ein + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          xv[q] = a.x, xv[q + 1] = a.y, xv[q + 2] = a.z, xv[q + 3] = a.w;
-          ev[q] = e4.x, ev[q + 1] = e4.y, ev[q + 2] = e4.z, ev[q + 3] = e4.w;
+        for (int q = 0; q < 32; q += 4) {  // 128-bit shared-memory accesses: 8 loads instead of 32 per role
+          if constexpr (BQ) {
+            const float4 a = bq ? *reinterpret_cast<const float4*>(xin + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[q] = a.x, xv[q + 1] = a.y, xv[q + 2] = a.z, xv[q + 3] = a.w;
+          }
+          if constexpr (EN) {
+            const float4 e4 = en ? *reinterpret_cast<const float4*>(ein + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ev[q] = e4.x, ev[q + 1] = e4.y, ev[q + 2] = e4.z, ev[q + 3] = e4.w;
+          }
         }
       } else {
 #pragma unroll
         for (int q = 0; q < 32; q++) {
-          xv[q] = bq ? xin[q] : 0.0f;
-          ev[q] = en ? ein[q] : 0.0f;
+          if constexpr (BQ) xv[q] = bq ? xin[q] : 0.0f;
+          if constexpr (EN) ev[q] = en ? ein[q] : 0.0f;
         }
       }
 #pragma unroll
       for (int q = 0; q < 32; q++) {
-        const float x = xv[q];
-        const float y = __fmaf_rn(b0, x, s1);  // transposed direct form II (fx_sample)
-        s1 = __fmaf_rn(b1, x, __fmaf_rn(-a1, y, s2));
-        s2 = __fmaf_rn(b2, x, -__fmul_rn(a2, y));
-        xv[q] = eq_on ? y : x;
-        const float xa = fabsf(ev[q]);
-        const float d = __fsub_rn(env, xa);
-        env = xa > env ? __fmaf_rn(att, d, xa) : __fmaf_rn(rel, d, xa);
-        ev[q] = env;
+        if constexpr (BQ) {
+          const float x = xv[q];
+          const float y = __fmaf_rn(b0, x, s1);  // transposed direct form II (fx_sample)
+          s1 = __fmaf_rn(b1, x, __fmaf_rn(-a1, y, s2));
+          s2 = __fmaf_rn(b2, x, -__fmul_rn(a2, y));
+          xv[q] = eq_on ? y : x;
+        }
+        if constexpr (EN) {
+          const float xa = fabsf(ev[q]);
+          const float d = __fsub_rn(env, xa);
+          env = xa > env ? __fmaf_rn(att, d, xa) : __fmaf_rn(rel, d, xa);
+          ev[q] = env;
+        }
       }
       if constexpr (L::VEC) {
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
-          if (bq) *reinterpret_cast<float4*>(xout + q) = make_float4(xv[q], xv[q + 1], xv[q + 2], xv[q + 3]);
-          if (en) *reinterpret_cast<float4*>(eout + q) = make_float4(ev[q], ev[q + 1], ev[q + 2], ev[q + 3]);
+          if constexpr (BQ)
+            if (bq) *reinterpret_cast<float4*>(xout + q) = make_float4(xv[q], xv[q + 1], xv[q + 2], xv[q + 3]);
+          if constexpr (EN)
+            if (en) *reinterpret_cast<float4*>(eout + q) = make_float4(ev[q], ev[q + 1], ev[q + 2], ev[q + 3]);
         }
       } else {
 #pragma unroll
         for (int q = 0; q < 32; q++) {
-          if (bq) xout[q] = xv[q];
-          if (en) eout[q] = ev[q];
+          if constexpr (BQ)
+            if (bq) xout[q] = xv[q];
+          if constexpr (EN)
+            if (en) eout[q] = ev[q];
         }
       }
+    };
+    if (steady) {
+      if (do_rec && do_env)
+        steady_pass(std::true_type{}, std::true_type{});
+      else if (do_rec)
+        steady_pass(std::true_type{}, std::false_type{});
+      else if (do_env)
+        steady_pass(std::false_type{}, std::true_type{});
     } else {
       for (int q = 0; q < 32; q++) {
         if (q < nb) {
@@ -1316,25 +1343,24 @@ __global__ void __launch_bounds__(128) effects_kernel(DFx* __restrict__ fx, uint
     team_sync();
   }
 
-  if (!do_rec) return;
-  if (bq_lane && eq_on) {
+  if (do_rec && bq_lane && eq_on) {
     const uint32_t g = pair0 + bp;
     DFx* f = fx + g / C;
     f->s1[g % C][bs] = s1;
     f->s2[g % C][bs] = s2;
   }
-  if (env_lane) {
+  if (do_env && env_lane) {
     const uint32_t g = pair0 + lane;
     fx[g / C].env[g % C] = env;
   }
 }
 
-template <int P, bool DUO>
+template <int P, int T>
 static cudaError_t launch_effects_p(DFx* fx, uint32_t n_fx, uint32_t C, uint64_t frames, float* trackbuf, cudaStream_t stream) {
-  constexpr int WARPS = 4;
-  constexpr int TEAMS = DUO ? WARPS / 2 : WARPS;  // teams (= shared-memory regions) per CTA
+  constexpr int TEAMS = T == 1 ? 4 : 2;  // teams (= shared-memory regions) per CTA
+  constexpr int WARPS = TEAMS * T;
   const size_t smem = (size_t)FxLayout<P>::WARP_FLOATS * TEAMS * sizeof(float);
-  auto kfn = effects_kernel<P, DUO>;
+  auto kfn = effects_kernel<P, T>;
   cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   const uint32_t teams = (n_fx * C + P - 1) / P;
@@ -1357,15 +1383,27 @@ static cudaError_t launch_effects_chain(DFx* fx, uint32_t n_fx, uint32_t C, uint
     const int v = atoi(env);
     if (v == 1 || v == 2 || v == 4 || v == 8) P = v;
   }
-  // two-warp teams while that still leaves at most ~two warps per scheduler
-  bool duo = (pairs + P - 1) / P <= slots;
-  if (const char* env = getenv("WBX_FX_DUO")) duo = atoi(env) != 0;
-  switch (P) {
-    case 1: return duo ? launch_effects_p<1, true>(fx, n_fx, C, frames, trackbuf, stream) : launch_effects_p<1, false>(fx, n_fx, C, frames, trackbuf, stream);
-    case 2: return duo ? launch_effects_p<2, true>(fx, n_fx, C, frames, trackbuf, stream) : launch_effects_p<2, false>(fx, n_fx, C, frames, trackbuf, stream);
-    case 4: return duo ? launch_effects_p<4, true>(fx, n_fx, C, frames, trackbuf, stream) : launch_effects_p<4, false>(fx, n_fx, C, frames, trackbuf, stream);
-    default: return duo ? launch_effects_p<8, true>(fx, n_fx, C, frames, trackbuf, stream) : launch_effects_p<8, false>(fx, n_fx, C, frames, trackbuf, stream);
+  // warps per team: 3 (biquads / envelope followers / loads + gain + stores) while that still leaves at most ~3 warps per
+  // scheduler, else 1
+  int T = (pairs + P - 1) / P <= slots ? 3 : 1;
+  if (const char* env = getenv("WBX_FX_TEAM")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= 3) T = v;
   }
+#define WBX_FX_CASE(PP)                                                                                \
+  case PP:                                                                                             \
+    return T == 3   ? launch_effects_p<PP, 3>(fx, n_fx, C, frames, trackbuf, stream)                   \
+           : T == 2 ? launch_effects_p<PP, 2>(fx, n_fx, C, frames, trackbuf, stream)                   \
+                    : launch_effects_p<PP, 1>(fx, n_fx, C, frames, trackbuf, stream);
+  switch (P) {
+    WBX_FX_CASE(1)
+    WBX_FX_CASE(2)
+    WBX_FX_CASE(4)
+    default: return T == 3   ? launch_effects_p<8, 3>(fx, n_fx, C, frames, trackbuf, stream)
+                    : T == 2 ? launch_effects_p<8, 2>(fx, n_fx, C, frames, trackbuf, stream)
+                             : launch_effects_p<8, 1>(fx, n_fx, C, frames, trackbuf, stream);
+  }
+#undef WBX_FX_CASE
 }
 
 // ---- convolution reverb (extension, cfg 5): direct form on the CUDA cores --------------------------------
