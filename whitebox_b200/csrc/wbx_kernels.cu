@@ -1368,24 +1368,27 @@ static cudaError_t launch_effects_p(DFx* fx, uint32_t n_fx, uint32_t C, uint64_t
   return cudaGetLastError();
 }
 
-// pairs per warp: the fewest that leave at most one warp per scheduler (4 per SM) — small sessions spread over the
-// whole machine; beyond one warp per scheduler the chain is instruction-issue-bound and fuller warps (more pairs per
-// recurrence instruction) win (measured: 512 tracks, P = 1 with two warps per scheduler 17.7 ms)
+// Shape of the chain kernel. Small and medium sessions cannot fill the GPU's 4 schedulers per SM with one warp per P
+// pairs, and are bound by per-warp latency: they run as three-warp teams with the fewest pairs per team that keep the
+// total at ~1.5 warps per scheduler (measured at 512 tracks = 1024 pairs: P = 4 / 768 warps 11.3 ms, P = 2 / 1536 warps
+// 12.5 ms, P = 1 / 3072 warps 16.9 ms; single warps 17.2 ms). Large sessions are instruction-issue-bound: one warp per 8
+// pairs (measured at 4096 tracks: 10.0 ms, three-warp teams 13.1 ms).
 static cudaError_t launch_effects_chain(DFx* fx, uint32_t n_fx, uint32_t C, uint64_t frames, float* trackbuf, int n_sm,
                                         cudaStream_t stream) {
   const uint32_t pairs = n_fx * C;
-  const uint32_t slots = (uint32_t)n_sm * 4;  // one warp per scheduler: beyond that the chain is instruction-issue-bound
-  int P = 8;
-  if (pairs <= slots) P = 1;
-  else if (pairs <= 2 * slots) P = 2;
-  else if (pairs <= 4 * slots) P = 4;
+  const uint32_t slots = (uint32_t)n_sm * 4;  // warp schedulers of the GPU
+  auto teams = [&](uint32_t p) { return (pairs + p - 1) / p; };
+  int P = 4, T = 3;
+  if (3 * teams(1) <= slots + slots / 2) P = 1;
+  else if (3 * teams(2) <= slots + slots / 2) P = 2;
+  if (3 * teams(4) > 3 * slots) {  // even 4 pairs per team would put more than ~3 warps on every scheduler
+    T = 1;
+    P = pairs <= 4 * slots ? 4 : 8;
+  }
   if (const char* env = getenv("WBX_FX_PAIRS")) {
     const int v = atoi(env);
     if (v == 1 || v == 2 || v == 4 || v == 8) P = v;
   }
-  // warps per team: 3 (biquads / envelope followers / loads + gain + stores) while that still leaves at most ~3 warps per
-  // scheduler, else 1
-  int T = (pairs + P - 1) / P <= slots ? 3 : 1;
   if (const char* env = getenv("WBX_FX_TEAM")) {
     const int v = atoi(env);
     if (v >= 1 && v <= 3) T = v;
