@@ -45,6 +45,7 @@ struct AudioClip {  // engine/clip.h:39-45 + Clip time placement (:68-70)
   uint32_t sample_id = 0;
   uint32_t sample_rate = 0;
   bool internal_state_changed = false;
+  bool deleted = false;  // Clip::mark_deleted (engine/clip.h): removed at the next update_clip_ordering
 };
 
 enum class EventType : uint8_t { None, StopSample, PlaySample };  // engine/event.h:11-15
@@ -61,6 +62,7 @@ struct AudioEvent {  // engine/event.h:66-74
 struct Track {
   std::string name;
   std::vector<AudioClip*> clips;  // sorted by min_time, never overlapping
+  std::vector<AudioClip*> graveyard;  // clips trimmed away by later edits, kept alive for voices still playing them
   // scheduler state (TrackEventState, engine/track.h:36-44)
   bool has_clip_idx = false;
   uint32_t clip_idx = 0;
@@ -108,7 +110,8 @@ class Engine {
   Track* add_track(const std::string& name);  // engine/engine.cpp:199-207
   // Resident Sample (dsp/sample.h:18-28); returns the id clips refer to, or a negative wbx_status.
   int add_sample(int format, uint32_t channels, uint64_t frames, uint32_t sample_rate, const void* const* planar);
-  // engine/engine.cpp:293-309 + add_to_cliplist (:409-461) for clips that do not overlap an existing one.
+  // engine/engine.cpp:293-309 + add_to_cliplist (:409-461): overlapping clips are trimmed / split / deleted first
+  // (Engine::reserve_track_region, :478-569).
   int add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
                      double speed, float gain, double fade_start = 0.0, double fade_end = 0.0);
   // convolution reverb (extension, see wbx.h): one impulse response per engine, used by chains with reverb_on
@@ -161,6 +164,7 @@ class Engine {
   void merge_levels();
   uint32_t quiet_blocks(const Track& t, uint32_t k, uint32_t K) const;
   void fill_fade(wbx_segment& s, const AudioClip* clip, uint64_t clip_frame) const;
+  void reserve_track_region(Track& t, uint32_t first_clip, uint32_t last_clip, double min, double max);
   void stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t q);
   std::vector<double> blk_start_, blk_end_, blk_spos_;  // per-callback transport of the current schedule()
   wbx_engine* dev_ = nullptr;

@@ -13,9 +13,9 @@
  * separately rounded exactly as in the reference's ISO-C++ x86-64 build.
  *
  * Scope notes (documented deviations, none reachable through wbo.h calls used by the tests):
- *  - clips added through wbo_add_clip must not overlap an existing clip of the track (abutting is fine);
- *    the reference would trim/split the old clip (Engine::reserve_track_region, engine.cpp:478-569) —
- *    editing logic, out of scope. Overlap returns -1.
+ *  - a clip removed by a later overlapping clip (Engine::reserve_track_region, engine.cpp:478-569) is parked in a
+ *    per-track graveyard instead of being destroyed at once (the reference destroys it in update_clip_ordering while a
+ *    playing voice may still point at it).
  *  - the per-track message ring (capacity 64, track.cpp:23) is an unbounded list here.
  *  - MIDI clips, plugins and recording are not restated.
  */
@@ -44,6 +44,7 @@ typedef struct {
   double fade_start, fade_end;             /* AudioClip::fade_start/fade_end clip.h:41-42 (EXTENSION, see fade_env) */
   o_sample* sample;
   int internal_state_changed; /* clip.h:62 — only UI edits set it */
+  int deleted;                /* Clip::mark_deleted */
 } o_clip;
 
 enum { EV_NONE, EV_STOP, EV_PLAY }; /* EventType, event.h:11-15 */
@@ -78,6 +79,8 @@ typedef struct {
 typedef struct {
   o_clip** clips;
   uint32_t n_clips, cap_clips;
+  o_clip** graveyard; /* clips trimmed away by later edits */
+  uint32_t n_grave, cap_grave;
   o_fx fx;
   /* TrackEventState, track.h:36-44 */
   int has_clip_idx;
@@ -173,6 +176,8 @@ void wbo_destroy(wbo_session* s) {
     o_track* tr = s->tracks[t];
     for (uint32_t i = 0; i < tr->n_clips; i++) free(tr->clips[i]);
     free(tr->clips);
+    for (uint32_t i = 0; i < tr->n_grave; i++) free(tr->graveyard[i]);
+    free(tr->graveyard);
     fx_free(&tr->fx);
     free(tr->events);
     free(tr->msgs);
@@ -295,11 +300,113 @@ int wbo_add_clip(wbo_session* s, int track, int sample, double min_beat, double 
   return wbo_add_clip_fade(s, track, sample, min_beat, max_beat, start_offset, speed, gain, 0.0, 0.0);
 }
 
+/* core/core_math.h:204-207 */
+static double samples_to_beat(double samples, double sample_rate, double beat_duration) {
+  double sec = samples / sample_rate;
+  return sec / beat_duration;
+}
+
+/* shift_clip_content + calc_clip_shift, audio clips (engine/clip_edit.h:128-150); sample_rate = the asset's */
+static double shift_clip_content(const o_clip* clip, double relative_pos, double beat_duration) {
+  double sample_rate = (double)clip->sample->rate;
+  relative_pos *= clip->speed;
+  double offset_in_beat = samples_to_beat(clip->start_offset, sample_rate, beat_duration);
+  double shifted = offset_in_beat - relative_pos;
+  return beat_to_samples(shifted > 0.0 ? shifted : 0.0, sample_rate, beat_duration);
+}
+
+static void clips_push(o_track* tr, o_clip* c) {
+  if (tr->n_clips == tr->cap_clips) {
+    tr->cap_clips = tr->cap_clips ? tr->cap_clips * 2 : 4;
+    tr->clips = (o_clip**)realloc(tr->clips, tr->cap_clips * sizeof(o_clip*));
+  }
+  tr->clips[tr->n_clips++] = c;
+}
+
+/* Track::query_clip_by_range (track.cpp:112-157) with wb::find_lower_bound (core/algorithm.h:25-40) */
+static int query_clip_by_range(const o_track* tr, double min, double max, uint32_t* first_out, uint32_t* last_out) {
+  if (tr->n_clips == 0) return 0;
+  if (max <= tr->clips[0]->min_time) return 0;
+  if (min >= tr->clips[tr->n_clips - 1]->max_time) return 0;
+  uint32_t first_clip = lower_bound_max_time(tr->clips, tr->n_clips, min);
+  uint32_t last_clip = lower_bound_max_time(tr->clips, tr->n_clips, max);
+  const o_clip* first = tr->clips[first_clip];
+  const o_clip* last = tr->clips[last_clip];
+  if (first_clip == last_clip && (max <= first->min_time || min >= last->max_time)) return 0;
+  if (min > first->max_time) first_clip++;
+  if (!(max > last->min_time)) last_clip--;
+  *first_out = first_clip;
+  *last_out = last_clip;
+  return 1;
+}
+
+static int clip_min_time_less(const void* a, const void* b) {
+  const o_clip* x = *(o_clip* const*)a;
+  const o_clip* y = *(o_clip* const*)b;
+  return (x->min_time > y->min_time) - (x->min_time < y->min_time);
+}
+
+/* Track::update_clip_ordering (track.cpp:159-180): drop deleted clips, sort by min_time */
+static void update_clip_ordering(o_track* tr) {
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < tr->n_clips; i++) {
+    o_clip* c = tr->clips[i];
+    if (c->deleted) {
+      if (tr->n_grave == tr->cap_grave) {
+        tr->cap_grave = tr->cap_grave ? tr->cap_grave * 2 : 4;
+        tr->graveyard = (o_clip**)realloc(tr->graveyard, tr->cap_grave * sizeof(o_clip*));
+      }
+      tr->graveyard[tr->n_grave++] = c;
+    } else {
+      tr->clips[n++] = c;
+    }
+  }
+  tr->n_clips = n;
+  qsort(tr->clips, tr->n_clips, sizeof(o_clip*), clip_min_time_less);
+}
+
+/* Engine::reserve_track_region (engine.cpp:478-569), ignore_clip == nullptr */
+static void reserve_track_region(wbo_session* s, o_track* tr, uint32_t first_clip, uint32_t last_clip, double min, double max) {
+  if (tr->n_clips == 0) return;
+  double current_beat_duration = s->beat_duration;
+  if (first_clip == last_clip) {
+    o_clip* clip = tr->clips[first_clip];
+    if (min > clip->min_time && max < clip->max_time) { /* split into two parts */
+      o_clip* right = (o_clip*)malloc(sizeof(*right));
+      *right = *clip;
+      right->min_time = max;
+      right->start_offset = shift_clip_content(right, clip->min_time - max, current_beat_duration);
+      clip->max_time = min;
+      clips_push(tr, right);
+    } else if (min > clip->min_time) {
+      clip->max_time = min;
+    } else if (max < clip->max_time) {
+      clip->start_offset = shift_clip_content(clip, clip->min_time - max, current_beat_duration);
+      clip->min_time = max;
+    } else {
+      clip->deleted = 1;
+    }
+    return;
+  }
+  o_clip* first = tr->clips[first_clip];
+  o_clip* last = tr->clips[last_clip];
+  if (min > first->min_time) {
+    first->max_time = min;
+    first_clip++;
+  }
+  if (max < last->max_time) {
+    last->start_offset = shift_clip_content(last, last->min_time - max, current_beat_duration);
+    last->min_time = max;
+    last_clip--;
+  }
+  if (first_clip <= last_clip && last_clip < tr->n_clips)
+    for (uint32_t i = first_clip; i <= last_clip; i++) tr->clips[i]->deleted = 1;
+}
+
+/* Engine::add_audio_clip (engine.cpp:293-309) + add_to_cliplist (:409-461) */
 int wbo_add_clip_fade(wbo_session* s, int track, int sample, double min_beat, double max_beat, double start_offset,
                       double speed, float gain, double fade_start, double fade_end) {
   o_track* tr = s->tracks[track];
-  for (uint32_t i = 0; i < tr->n_clips; i++) /* Track::query_clip_by_range (track.cpp:112-160) finds one */
-    if (min_beat < tr->clips[i]->max_time && max_beat > tr->clips[i]->min_time) return -1;
   o_clip* c = (o_clip*)calloc(1, sizeof(*c));
   c->min_time = min_beat;
   c->max_time = max_beat;
@@ -309,17 +416,19 @@ int wbo_add_clip_fade(wbo_session* s, int track, int sample, double min_beat, do
   c->fade_start = fade_start;
   c->fade_end = fade_end;
   c->sample = s->samples[sample];
-  if (tr->n_clips == tr->cap_clips) {
-    tr->cap_clips = tr->cap_clips ? tr->cap_clips * 2 : 4;
-    tr->clips = (o_clip**)realloc(tr->clips, tr->cap_clips * sizeof(o_clip*));
+  if (tr->n_clips == 0 || tr->clips[tr->n_clips - 1]->max_time < c->min_time) { /* first clip / add to the back */
+    clips_push(tr, c);
+  } else if (tr->clips[0]->min_time > c->max_time) { /* add to the front */
+    clips_push(tr, c);
+    for (uint32_t i = tr->n_clips - 1; i > 0; i--) tr->clips[i] = tr->clips[i - 1];
+    tr->clips[0] = c;
+  } else {
+    uint32_t first = 0, last = 0;
+    if (query_clip_by_range(tr, c->min_time, c->max_time, &first, &last))
+      reserve_track_region(s, tr, first, last, c->min_time, c->max_time);
+    clips_push(tr, c);
+    update_clip_ordering(tr);
   }
-  uint32_t pos = tr->n_clips;
-  while (pos > 0 && tr->clips[pos - 1]->min_time > min_beat) {
-    tr->clips[pos] = tr->clips[pos - 1];
-    pos--;
-  }
-  tr->clips[pos] = c;
-  tr->n_clips++;
   reset_playback_state(tr, s->playhead, 1);
   return 0;
 }

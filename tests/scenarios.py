@@ -158,6 +158,71 @@ def event_split(make_engine):
     return _collect(eng, outs, n)
 
 
+def overlaps(make_engine):
+    """Clips added on top of existing ones: Engine::add_to_cliplist + reserve_track_region (engine.cpp:409-461, 478-569)
+    trim the old clip's tail, trim its head (shifting its content start, clip_edit.h:128-150), split it in two, delete
+    it, or do all of that across several clips; plus add-to-front / add-to-back / no-overlap insertion in the middle, a
+    resampled clip whose head is trimmed, and an overlapping clip added while the session is playing."""
+    rng = np.random.RandomState(9876)
+    B, rate = 128, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    spb = rate * 0.5  # samples per beat at bpm 120
+    n = 0
+
+    def tr(vol=-3.0, pan=0.0):
+        nonlocal n
+        eng.add_track(vol, pan, False)
+        n += 1
+        return n - 1
+
+    def smp(frames, ch=2, r=48000):
+        return eng.add_sample(_src(rng, ch, frames, 8), r, FMT_F32)
+
+    # t0: new clip cuts the TAIL of an old one (old [0, 900) -> [0, 500), new [500, 1100))
+    t = tr(-2.0, -0.3)
+    eng.add_clip(t, smp(6000), 0.0, 900.0 / spb, 0.0, 1.0, 0.8)
+    eng.add_clip(t, smp(6000), 500.0 / spb, 1100.0 / spb, 3.0, 1.0, 0.6)
+    # t1: new clip cuts the HEAD of an old one (old [300, 1200) -> [700, 1200) with its content shifted by 400 frames)
+    t = tr(-4.0, 0.4)
+    eng.add_clip(t, smp(6000), 300.0 / spb, 1200.0 / spb, 21.0, 1.0, 0.7)
+    eng.add_clip(t, smp(6000), 100.0 / spb, 700.0 / spb, 0.0, 1.0, 0.9)
+    # t2: new clip in the MIDDLE of an old one: split into [0, 400) and [650, 1300) (right part shifted)
+    t = tr(0.0, 0.0)
+    eng.add_clip(t, smp(8000), 0.0, 1300.0 / spb, 5.0, 1.0, 1.0)
+    eng.add_clip(t, smp(3000), 400.0 / spb, 650.0 / spb, 0.0, 1.0, 0.5)
+    # t3: new clip COVERS an old one entirely (deleted), old neighbours untouched
+    t = tr(-1.0, 0.1)
+    eng.add_clip(t, smp(3000), 0.0, 150.0 / spb, 0.0, 1.0, 0.6)
+    eng.add_clip(t, smp(3000), 300.0 / spb, 500.0 / spb, 0.0, 1.0, 0.6)
+    eng.add_clip(t, smp(3000), 900.0 / spb, 1250.0 / spb, 0.0, 1.0, 0.6)
+    eng.add_clip(t, smp(3000), 250.0 / spb, 600.0 / spb, 7.0, 1.0, 0.4)
+    # t4: new clip spans FOUR old ones: first tail-trimmed, two deleted, last head-trimmed
+    t = tr(-1.5, -0.8)
+    for i in range(4):
+        eng.add_clip(t, smp(3000), (i * 300.0) / spb, (i * 300.0 + 260.0) / spb, 2.0 * i, 1.0, 0.5 + 0.1 * i)
+    eng.add_clip(t, smp(6000), 130.0 / spb, 1010.0 / spb, 0.0, 1.0, 0.3)
+    # t5: add to the front, to the back, and into a gap (no overlap: plain insertion + ordering)
+    t = tr(-7.0, 0.9)
+    eng.add_clip(t, smp(2000), 600.0 / spb, 800.0 / spb, 0.0, 1.0, 1.1)
+    eng.add_clip(t, smp(2000), 0.0, 200.0 / spb, 0.0, 1.0, 0.9)
+    eng.add_clip(t, smp(2000), 1000.0 / spb, 1300.0 / spb, 0.0, 1.0, 0.8)
+    eng.add_clip(t, smp(2000), 300.0 / spb, 500.0 / spb, 0.0, 1.0, 0.7)
+    # t6: resampled 44.1 kHz clip at speed 1.25 whose head is cut: the shift is scaled by the clip speed and uses the
+    # asset's own sample rate
+    t = tr(-5.0, 0.5)
+    eng.add_clip(t, smp(9000, 2, 44100), 100.0 / spb, 1200.0 / spb, 11.0, 1.25, 0.75)
+    eng.add_clip(t, smp(2000), 0.0, 450.0 / spb, 0.0, 1.0, 0.5)
+    # t7: edited while playing (below)
+    t7 = tr(-3.0, -1.0)
+    eng.add_clip(t7, smp(8000), 0.0, 1400.0 / spb, 0.0, 1.0, 0.5)
+    late = smp(4000)
+    eng.play()
+    outs = [eng.process(4)]
+    eng.add_clip(t7, late, 700.0 / spb, 1000.0 / spb, 0.0, 1.0, 0.9)  # splits the clip that is playing right now
+    outs.append(eng.process(8))
+    return _collect(eng, outs, n)
+
+
 def params(make_engine):
     """Volume / pan / mute changes between callbacks, not-playing callbacks, stop/play (track.cpp:618-643)."""
     rng = np.random.RandomState(99)
@@ -386,4 +451,4 @@ def mip_source(fmt, frames, ch):
 EXT = dict(fades=fades, effects=effects, reverb=reverb, polyphase=polyphase)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
-           event_split=event_split, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)
+           event_split=event_split, overlaps=overlaps, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)

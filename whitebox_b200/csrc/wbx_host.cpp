@@ -44,6 +44,7 @@ PanningCoefficient calculate_panning_coefs(float p) {
 enum : uint32_t { kParamVolume = 0, kParamPan = 1, kParamMute = 2 };  // TrackParameter, engine/track.h:29-34
 
 Track::~Track() {
+  for (auto* c : graveyard) delete c;
   for (auto* c : clips) delete c;
 }
 void Track::set_volume(float db) {
@@ -158,11 +159,114 @@ int Engine::add_sample(int format, uint32_t channels, uint64_t frames, uint32_t 
   return (int)id;
 }
 
+// core/core_math.h:199-212
+static inline double samples_to_beat(double samples, double sample_rate, double beat_duration) {
+  const double sec = samples / sample_rate;
+  return sec / beat_duration;
+}
+
+// shift_clip_content + calc_clip_shift for audio clips (engine/clip_edit.h:128-150): the clip's content start after its
+// left edge moved by -relative_pos beats; sample_rate is the ASSET's rate.
+static double shift_clip_content(const AudioClip* clip, double relative_pos, double beat_duration) {
+  const double sample_rate = (double)clip->sample_rate;
+  relative_pos *= clip->speed;
+  const double offset_in_beat = samples_to_beat(clip->start_offset, sample_rate, beat_duration);
+  const double shifted = offset_in_beat - relative_pos;
+  return beat_to_samples(shifted > 0.0 ? shifted : 0.0, sample_rate, beat_duration);
+}
+
+// wb::find_lower_bound (core/algorithm.h:25-40): NOT std::lower_bound — the search ends at the last element
+template <class Pred>
+static uint32_t find_lower_bound_idx(const std::vector<AudioClip*>& clips, double value, Pred pred) {
+  int64_t left = 0, right = (int64_t)clips.size() - 1;
+  while (left < right) {
+    const int64_t middle = (left + right) >> 1;
+    if (pred(clips[(size_t)middle], value))
+      left = middle + 1;
+    else
+      right = middle;
+  }
+  return (uint32_t)right;
+}
+
+// Track::query_clip_by_range (engine/track.cpp:112-157): first / last clip touched by [min, max]
+static bool query_clip_by_range(const Track& t, double min, double max, uint32_t* first_out, uint32_t* last_out) {
+  const auto& clips = t.clips;
+  if (clips.empty()) return false;
+  if (max <= clips.front()->min_time) return false;
+  if (min >= clips.back()->max_time) return false;
+  auto ends_before = [](const AudioClip* c, double time) { return c->max_time <= time; };
+  uint32_t first_clip = find_lower_bound_idx(clips, min, ends_before);
+  uint32_t last_clip = find_lower_bound_idx(clips, max, ends_before);
+  const AudioClip* first = clips[first_clip];
+  const AudioClip* last = clips[last_clip];
+  if (first_clip == last_clip && (max <= first->min_time || min >= last->max_time)) return false;
+  if (min > first->max_time) first_clip++;
+  if (!(max > last->min_time)) last_clip--;
+  *first_out = first_clip;
+  *last_out = last_clip;
+  return true;
+}
+
+// Track::mark_clip_deleted + update_clip_ordering (engine/track.cpp:107-110,159-180). Removed clips are parked in the
+// track's graveyard instead of being destroyed: a voice that is still playing one keeps a valid pointer until the
+// refresh at the next callback stops it.
+static void update_clip_ordering(Track& t) {
+  std::vector<AudioClip*> kept;
+  for (AudioClip* c : t.clips) {
+    if (c->deleted)
+      t.graveyard.push_back(c);
+    else
+      kept.push_back(c);
+  }
+  t.clips.swap(kept);
+  std::sort(t.clips.begin(), t.clips.end(), [](const AudioClip* a, const AudioClip* b) { return a->min_time < b->min_time; });
+}
+
+// Engine::reserve_track_region (engine/engine.cpp:478-569) with ignore_clip == nullptr: make room for [min, max] by
+// trimming, splitting or deleting the clips first_clip..last_clip.
+void Engine::reserve_track_region(Track& t, uint32_t first_clip, uint32_t last_clip, double min, double max) {
+  auto& clips = t.clips;
+  if (clips.empty()) return;
+  const double current_beat_duration = beat_duration_;
+  if (first_clip == last_clip) {
+    AudioClip* clip = clips[first_clip];
+    if (min > clip->min_time && max < clip->max_time) {  // split the clip into two parts
+      AudioClip* right = new AudioClip(*clip);
+      right->min_time = max;
+      right->start_offset = shift_clip_content(right, clip->min_time - max, current_beat_duration);
+      clip->max_time = min;
+      clips.push_back(right);
+    } else if (min > clip->min_time) {
+      clip->max_time = min;
+    } else if (max < clip->max_time) {
+      clip->start_offset = shift_clip_content(clip, clip->min_time - max, current_beat_duration);
+      clip->min_time = max;
+    } else {
+      clip->deleted = true;
+    }
+    return;
+  }
+  AudioClip* first = clips[first_clip];
+  AudioClip* last = clips[last_clip];
+  if (min > first->min_time) {
+    first->max_time = min;
+    first_clip++;
+  }
+  if (max < last->max_time) {
+    last->start_offset = shift_clip_content(last, last->min_time - max, current_beat_duration);
+    last->min_time = max;
+    last_clip--;
+  }
+  if (first_clip <= last_clip && last_clip < clips.size())
+    for (uint32_t i = first_clip; i <= last_clip; i++) clips[i]->deleted = true;
+}
+
+// Engine::add_audio_clip (engine/engine.cpp:293-309) + add_to_cliplist (:409-461): a clip that overlaps existing ones
+// trims / splits / deletes them first (reserve_track_region).
 int Engine::add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
                            double speed, float gain, double fade_start, double fade_end) {
   if (!track || sample_id >= samples_.size() || !(max_time >= min_time)) return WBX_ERR_INVALID;
-  for (auto* c : track->clips)  // the reference would trim/split here (Engine::reserve_track_region): out of scope
-    if (min_time < c->max_time && max_time > c->min_time) return WBX_ERR_UNSUPPORTED;
   AudioClip* clip = new AudioClip();
   clip->min_time = min_time;
   clip->max_time = max_time;
@@ -173,9 +277,18 @@ int Engine::add_audio_clip(Track* track, double min_time, double max_time, doubl
   clip->fade_end = fade_end;
   clip->sample_id = sample_id;
   clip->sample_rate = samples_[sample_id].rate;
-  auto pos = std::upper_bound(track->clips.begin(), track->clips.end(), clip,
-                              [](const AudioClip* a, const AudioClip* b) { return a->min_time < b->min_time; });
-  track->clips.insert(pos, clip);
+  auto& clips = track->clips;
+  if (clips.empty() || clips.back()->max_time < clip->min_time) {  // first clip, or add to the back
+    clips.push_back(clip);
+  } else if (clips.front()->min_time > clip->max_time) {  // add to the front
+    clips.insert(clips.begin(), clip);
+  } else {
+    uint32_t first = 0, last = 0;
+    if (query_clip_by_range(*track, clip->min_time, clip->max_time, &first, &last))
+      reserve_track_region(*track, first, last, clip->min_time, clip->max_time);  // trim to reserve space for the clip
+    clips.push_back(clip);
+    update_clip_ordering(*track);
+  }
   reset_playback_state(*track, playhead, true);  // add_to_cliplist, engine.cpp:415,425,...
   return WBX_OK;
 }
