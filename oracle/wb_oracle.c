@@ -365,6 +365,15 @@ static void update_clip_ordering(o_track* tr) {
   qsort(tr->clips, tr->n_clips, sizeof(o_clip*), clip_min_time_less);
 }
 
+/* Track::mark_clip_deleted. If a voice is playing this very clip, the reference goes on reading
+ * current_audio_event.clip->audio.gain (track.cpp:676,716) after update_clip_ordering destroyed the clip and its pool
+ * slot was handed to the next new clip: a use-after-free with no defined answer. Counted like the other UB case so
+ * that comparisons against the reference skip such sessions; port and product keep the clip (and its gain) alive. */
+static void mark_deleted(o_track* tr, o_clip* clip) {
+  clip->deleted = 1;
+  if (tr->current.type == EV_PLAY && tr->current.clip == clip) g_ub_count++;
+}
+
 /* Engine::reserve_track_region (engine.cpp:478-569), ignore_clip == nullptr */
 static void reserve_track_region(wbo_session* s, o_track* tr, uint32_t first_clip, uint32_t last_clip, double min, double max) {
   if (tr->n_clips == 0) return;
@@ -384,7 +393,7 @@ static void reserve_track_region(wbo_session* s, o_track* tr, uint32_t first_cli
       clip->start_offset = shift_clip_content(clip, clip->min_time - max, current_beat_duration);
       clip->min_time = max;
     } else {
-      clip->deleted = 1;
+      mark_deleted(tr, clip);
     }
     return;
   }
@@ -400,7 +409,7 @@ static void reserve_track_region(wbo_session* s, o_track* tr, uint32_t first_cli
     last_clip--;
   }
   if (first_clip <= last_clip && last_clip < tr->n_clips)
-    for (uint32_t i = first_clip; i <= last_clip; i++) tr->clips[i]->deleted = 1;
+    for (uint32_t i = first_clip; i <= last_clip; i++) mark_deleted(tr, tr->clips[i]);
 }
 
 /* Engine::add_audio_clip (engine.cpp:293-309) + add_to_cliplist (:409-461) */

@@ -438,6 +438,50 @@ def fuzz(make_engine, seed):
     return _collect(eng, outs, n_tracks)
 
 
+def fuzz_overlap(make_engine, seed):
+    """Random session whose clips are dropped anywhere on the timeline — on top of one another, inside one another, across
+    several — so every add goes through add_to_cliplist / reserve_track_region (engine.cpp:409-461, 478-569); a third of
+    the sessions add more clips while playing."""
+    rng = np.random.RandomState(5000 + seed)
+    B = int(rng.choice([32, 64, 128, 256]))
+    rate = int(rng.choice([44100, 48000]))
+    bpm = float(rng.choice([90.0, 120.0, 150.0]))
+    eng = make_engine(2, B, rate, bpm)
+    spb = rate * 60.0 / bpm
+    n_tracks = int(rng.randint(1, 6))
+    n_blocks = int(rng.randint(6, 14))
+    total = n_blocks * B
+    samples = []
+
+    def drop_clip(t):
+        srate = int(rng.choice([rate, rate, 44100, 96000]))
+        speed = float(rng.choice([1.0, 1.0, 1.0, 0.5, 1.3]))
+        if not samples or rng.rand() < 0.5:
+            samples.append((eng.add_sample(_src(rng, 2, int(rng.randint(200, 6000)), n_tracks), srate, FMT_F32), srate))
+        sid, _ = samples[int(rng.randint(0, len(samples)))]
+        a = float(rng.randint(0, total))
+        b = a + float(rng.randint(1, total // 2 + 2))
+        # distinct fractional parts keep min_time ties (an unstable sort in the reference) out of the fixture
+        a += float(rng.randint(1, 1000)) / 1024.0
+        eng.add_clip(t, sid, a / spb, b / spb, float(rng.randint(0, 40)), speed, float(rng.uniform(0.1, 1.2)))
+
+    for t in range(n_tracks):
+        eng.add_track(float(rng.uniform(-20, 3)), float(rng.uniform(-1, 1)), False)
+        for _ in range(int(rng.randint(1, 7))):
+            drop_clip(t)
+    eng.play()
+    outs = []
+    done = 0
+    live_edits = seed % 3 == 0
+    while done < n_blocks:
+        n = int(min(n_blocks - done, rng.randint(1, 5)))
+        outs.append(eng.process(n))
+        done += n
+        if live_edits and done < n_blocks:
+            drop_clip(int(rng.randint(0, n_tracks)))
+    return _collect(eng, outs, n_tracks)
+
+
 MIP_CASES = dict(f32s=(FMT_F32, 20011, 2), i16m=(FMT_I16, 4100, 1), i32s=(FMT_I32, 777, 2))
 
 

@@ -109,6 +109,24 @@ def test_host_scheduler_matches_port_fuzz(wb):
     assert ran > 35
 
 
+def test_host_scheduler_matches_port_overlap_fuzz(wb):
+    """The product's clip-list editing (overlapping adds) + scheduler against the C restatement on random sessions."""
+    import oracle_api as o
+    L = o.lib("port")
+    L.wbo_ub_count.restype = ctypes.c_uint64
+    ran = 0
+    for seed in range(80):
+        before = L.wbo_ub_count()
+        ref = sc.fuzz_overlap(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), seed)
+        if L.wbo_ub_count() != before:
+            continue
+        res = sc.fuzz_overlap(lambda C, B, r, bpm: sr.ScheduleOnlyEngine(C, B, r, bpm, seed % 2 == 0), seed)
+        for k in ref:
+            assert _same(res[k], ref[k]), "fuzz_overlap%d: %s" % (seed, k)
+        ran += 1
+    assert ran > 50
+
+
 @pytest.mark.parametrize("batched", [True, False])
 def test_fade_extension_host_matches_port(wb, batched):
     """EXTENSION (parity unpinned w.r.t. whitebox): the product's scheduler + documented segment semantics

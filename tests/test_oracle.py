@@ -109,6 +109,23 @@ def test_port_matches_reference_fuzz():
 
 
 @needs_ref
+def test_port_matches_reference_overlap_fuzz():
+    """Random sessions of overlapping clips (add_to_cliplist / reserve_track_region / query_clip_by_range /
+    shift_clip_content), a third of them edited while playing: the C restatement against the reference itself."""
+    L = o.lib("port")
+    L.wbo_ub_count.restype = ctypes.c_uint64
+    ran = 0
+    for seed in range(150):
+        before = L.wbo_ub_count()
+        p = sc.fuzz_overlap(mk("port"), seed)
+        if L.wbo_ub_count() != before:
+            continue
+        assert_same(p, sc.fuzz_overlap(mk("reference"), seed), "fuzz_overlap%d" % seed)
+        ran += 1
+    assert ran > 100
+
+
+@needs_ref
 def test_golden_is_current(golden_dir):
     """The committed vectors are what the reference produces today."""
     for name in ("kat", "event_split", "cfg3_small"):
