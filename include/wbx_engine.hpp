@@ -114,6 +114,14 @@ class Engine {
   // (Engine::reserve_track_region, :478-569).
   int add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
                      double speed, float gain, double fade_start = 0.0, double fade_end = 0.0);
+  // Clip editing that feeds the scheduler (engine/engine.cpp:336-407, engine/clip_edit.h): the clip must belong to the
+  // track. Neighbours the new extent overlaps are trimmed / split / deleted (reserve_track_region); a clip moved or
+  // shift/stretch-resized while it plays restarts at its new content offset on the next callback.
+  int move_clip(Track* track, AudioClip* clip, double relative_pos);
+  int resize_clip(Track* track, AudioClip* clip, double relative_pos, double resize_limit, double min_length, bool left_side,
+                  bool shift = false, bool stretch = false);
+  int delete_clip(Track* track, AudioClip* clip);
+  int duplicate_clip(Track* track, const AudioClip* clip_to_duplicate, double min_time, double max_time);
   // convolution reverb (extension, see wbx.h): one impulse response per engine, used by chains with reverb_on
   int set_impulse_response(const float* h, uint32_t n_taps);
   void play();  // engine/engine.cpp:68-80
@@ -164,7 +172,9 @@ class Engine {
   void merge_levels();
   uint32_t quiet_blocks(const Track& t, uint32_t k, uint32_t K) const;
   void fill_fade(wbx_segment& s, const AudioClip* clip, uint64_t clip_frame) const;
-  void reserve_track_region(Track& t, uint32_t first_clip, uint32_t last_clip, double min, double max);
+  void reserve_track_region(Track& t, uint32_t first_clip, uint32_t last_clip, double min, double max,
+                            const AudioClip* ignore_clip);
+  void add_to_cliplist(Track* track, AudioClip* clip);
   void stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t q);
   std::vector<double> blk_start_, blk_end_, blk_spos_;  // per-callback transport of the current schedule()
   wbx_engine* dev_ = nullptr;

@@ -38,6 +38,14 @@ int wbxh_add_clip(wbxh_engine* h, int track, int sample, double min_beat, double
  * specified in wbx.h; (0, 0) is the reference path. */
 int wbxh_add_clip_fade(wbxh_engine* h, int track, int sample, double min_beat, double max_beat, double start_offset,
                        double speed, float gain, double fade_start, double fade_end);
+/* Clip editing, `clip` = index in the track's clip list (ordered by min_beat) at the time of the call: Engine::move_clip
+ * (engine/engine.cpp:346), resize_clip (:365), delete_clip (:400), duplicate_clip (:336). 0 or a negative wbx_status. */
+int wbxh_clip_count(wbxh_engine* h, int track);
+int wbxh_move_clip(wbxh_engine* h, int track, int clip, double relative_pos);
+int wbxh_resize_clip(wbxh_engine* h, int track, int clip, double relative_pos, double resize_limit, double min_length,
+                     int left_side, int shift, int stretch);
+int wbxh_delete_clip(wbxh_engine* h, int track, int clip);
+int wbxh_duplicate_clip(wbxh_engine* h, int track, int clip, double min_beat, double max_beat);
 /* attach (params != NULL) or remove the built-in EQ + compressor chain of a track (extension, see wbx.h) */
 int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params);
 int wbxh_set_impulse_response(wbxh_engine* h, const float* ir, uint32_t n_taps); /* convolution reverb IR (wbx.h) */

@@ -107,6 +107,43 @@ int wbo_add_clip_fade(wbo_session* s, int track, int sample, double min_beat, do
   return 0;
 }
 
+int wbo_clip_count(wbo_session* s, int track) { return (int)s->engine.tracks[track]->clips.size(); }
+
+static Clip* clip_at(wbo_session* s, int track, int clip) {
+  auto& clips = s->engine.tracks[track]->clips;
+  return (clip < 0 || (size_t)clip >= clips.size()) ? nullptr : clips[clip];
+}
+
+int wbo_move_clip(wbo_session* s, int track, int clip, double relative_pos) {
+  Clip* c = clip_at(s, track, clip);
+  if (!c) return -1;
+  s->engine.move_clip(s->engine.tracks[track], c, relative_pos);
+  return 0;
+}
+
+int wbo_resize_clip(wbo_session* s, int track, int clip, double relative_pos, double resize_limit, double min_length,
+                    int left_side, int shift, int stretch) {
+  Clip* c = clip_at(s, track, clip);
+  if (!c) return -1;
+  s->engine.resize_clip(s->engine.tracks[track], c, relative_pos, resize_limit, min_length, left_side != 0, shift != 0,
+                        stretch != 0);
+  return 0;
+}
+
+int wbo_delete_clip(wbo_session* s, int track, int clip) {
+  Clip* c = clip_at(s, track, clip);
+  if (!c) return -1;
+  s->engine.delete_clip(s->engine.tracks[track], c);
+  return 0;
+}
+
+int wbo_duplicate_clip(wbo_session* s, int track, int clip, double min_beat, double max_beat) {
+  Clip* c = clip_at(s, track, clip);
+  if (!c) return -1;
+  s->engine.duplicate_clip(s->engine.tracks[track], c, min_beat, max_beat);
+  return 0;
+}
+
 int wbo_set_effects(wbo_session*, int, const wbo_effects*) { return -1; }  // the reference has no effects
 int wbo_set_impulse_response(wbo_session*, const float*, uint32_t) { return -1; }
 void wbo_set_resampler(wbo_session*, int) {}  // the reference has only the linear resampler

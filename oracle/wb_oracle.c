@@ -375,11 +375,13 @@ static void mark_deleted(o_track* tr, o_clip* clip) {
 }
 
 /* Engine::reserve_track_region (engine.cpp:478-569), ignore_clip == nullptr */
-static void reserve_track_region(wbo_session* s, o_track* tr, uint32_t first_clip, uint32_t last_clip, double min, double max) {
+static void reserve_track_region(wbo_session* s, o_track* tr, uint32_t first_clip, uint32_t last_clip, double min, double max,
+                                 const o_clip* ignore_clip) {
   if (tr->n_clips == 0) return;
   double current_beat_duration = s->beat_duration;
   if (first_clip == last_clip) {
     o_clip* clip = tr->clips[first_clip];
+    if (clip == ignore_clip) return;
     if (min > clip->min_time && max < clip->max_time) { /* split into two parts */
       o_clip* right = (o_clip*)malloc(sizeof(*right));
       *right = *clip;
@@ -399,17 +401,18 @@ static void reserve_track_region(wbo_session* s, o_track* tr, uint32_t first_cli
   }
   o_clip* first = tr->clips[first_clip];
   o_clip* last = tr->clips[last_clip];
-  if (min > first->min_time) {
+  if (first != ignore_clip && min > first->min_time) {
     first->max_time = min;
     first_clip++;
   }
-  if (max < last->max_time) {
+  if (last != ignore_clip && max < last->max_time) {
     last->start_offset = shift_clip_content(last, last->min_time - max, current_beat_duration);
     last->min_time = max;
     last_clip--;
   }
   if (first_clip <= last_clip && last_clip < tr->n_clips)
-    for (uint32_t i = first_clip; i <= last_clip; i++) mark_deleted(tr, tr->clips[i]);
+    for (uint32_t i = first_clip; i <= last_clip; i++)
+      if (tr->clips[i] != ignore_clip) mark_deleted(tr, tr->clips[i]);
 }
 
 /* Engine::add_audio_clip (engine.cpp:293-309) + add_to_cliplist (:409-461) */
@@ -434,11 +437,157 @@ int wbo_add_clip_fade(wbo_session* s, int track, int sample, double min_beat, do
   } else {
     uint32_t first = 0, last = 0;
     if (query_clip_by_range(tr, c->min_time, c->max_time, &first, &last))
-      reserve_track_region(s, tr, first, last, c->min_time, c->max_time);
+      reserve_track_region(s, tr, first, last, c->min_time, c->max_time, NULL);
     clips_push(tr, c);
     update_clip_ordering(tr);
   }
   reset_playback_state(tr, s->playhead, 1);
+  return 0;
+}
+
+/* Engine::add_to_cliplist (engine.cpp:409-461) for an already constructed clip */
+static void add_to_cliplist(wbo_session* s, o_track* tr, o_clip* c) {
+  if (tr->n_clips == 0 || tr->clips[tr->n_clips - 1]->max_time < c->min_time) {
+    clips_push(tr, c);
+  } else if (tr->clips[0]->min_time > c->max_time) {
+    clips_push(tr, c);
+    for (uint32_t i = tr->n_clips - 1; i > 0; i--) tr->clips[i] = tr->clips[i - 1];
+    tr->clips[0] = c;
+  } else {
+    uint32_t first = 0, last = 0;
+    if (query_clip_by_range(tr, c->min_time, c->max_time, &first, &last))
+      reserve_track_region(s, tr, first, last, c->min_time, c->max_time, NULL);
+    clips_push(tr, c);
+    update_clip_ordering(tr);
+  }
+  reset_playback_state(tr, s->playhead, 1);
+}
+
+int wbo_clip_count(wbo_session* s, int track) { return (int)s->tracks[track]->n_clips; }
+
+static o_clip* clip_at(wbo_session* s, int track, int clip) {
+  o_track* tr = s->tracks[track];
+  return (clip < 0 || (uint32_t)clip >= tr->n_clips) ? NULL : tr->clips[clip];
+}
+
+/* Engine::move_clip (engine.cpp:346-363) + calc_move_clip (clip_edit.h:10-16) */
+int wbo_move_clip(wbo_session* s, int track, int clip, double relative_pos) {
+  o_track* tr = s->tracks[track];
+  o_clip* c = clip_at(s, track, clip);
+  if (!c) return -1;
+  if (relative_pos == 0.0) return 0;
+  double new_pos = c->min_time + relative_pos;
+  if (!(new_pos > 0.0)) new_pos = 0.0; /* math::max(.., min_move = 0.0) */
+  double min_time = new_pos, max_time = new_pos + (c->max_time - c->min_time);
+  uint32_t first = 0, last = 0;
+  if (query_clip_by_range(tr, min_time, max_time, &first, &last))
+    reserve_track_region(s, tr, first, last, min_time, max_time, c);
+  c->min_time = min_time;
+  c->max_time = max_time;
+  c->internal_state_changed = 1;
+  update_clip_ordering(tr);
+  reset_playback_state(tr, s->playhead, 1);
+  return 0;
+}
+
+/* Engine::resize_clip (engine.cpp:365-398) + calc_resize_clip (clip_edit.h:18-126), audio clips,
+ * clamp_at_resize_pos = false */
+int wbo_resize_clip(wbo_session* s, int track, int clip, double relative_pos, double resize_limit, double min_length,
+                    int left_side, int shift, int stretch) {
+  o_track* tr = s->tracks[track];
+  o_clip* c = clip_at(s, track, clip);
+  if (!c) return -1;
+  if (relative_pos == 0.0) return 0;
+  const double beat_duration = s->beat_duration;
+  const double asset_rate = (double)c->sample->rate;
+  const double sample_count = (double)c->sample->count;
+  double min_time, max_time, start_offset = c->start_offset, new_speed = 1.0;
+  if (!left_side) {
+    const double old_max = c->max_time;
+    const double actual_min_length = resize_limit + min_length - c->min_time;
+    double new_max = c->max_time + relative_pos;
+    if (!(new_max > 0.0)) new_max = 0.0;
+    double length = new_max - c->min_time;
+    if (length < actual_min_length) new_max = c->min_time + actual_min_length;
+    if (shift) {
+      double mult = c->speed;
+      start_offset = samples_to_beat(start_offset, asset_rate, beat_duration);
+      if (old_max < new_max)
+        start_offset -= (new_max - old_max) * mult;
+      else
+        start_offset += (old_max - new_max) * mult;
+      if (!(start_offset > 0.0)) start_offset = 0.0;
+      if (!(start_offset < sample_count)) start_offset = sample_count; /* math::min(start_offset, count) */
+      start_offset = beat_to_samples(start_offset, asset_rate, beat_duration);
+    }
+    if (stretch) {
+      double old_length = sample_count / c->speed;
+      double num_samples = beat_to_samples(relative_pos, asset_rate, beat_duration);
+      new_speed = sample_count / (old_length + num_samples);
+    }
+    min_time = c->min_time;
+    max_time = new_max;
+  } else {
+    const double old_min = c->min_time;
+    const double actual_min_length = c->max_time - resize_limit + min_length;
+    double new_min = c->min_time + relative_pos;
+    if (!(new_min > 0.0)) new_min = 0.0;
+    double length = c->max_time - new_min;
+    if (length < actual_min_length) new_min = c->max_time - actual_min_length;
+    if (!shift) {
+      start_offset = samples_to_beat(start_offset, asset_rate, beat_duration);
+      if (old_min < new_min)
+        start_offset -= old_min - new_min;
+      else
+        start_offset += new_min - old_min;
+      if (start_offset < 0.0) new_min = new_min - start_offset;
+      if (!(start_offset > 0.0)) start_offset = 0.0;
+      start_offset = beat_to_samples(start_offset, asset_rate, beat_duration);
+    }
+    if (stretch) {
+      double old_length = sample_count / c->speed;
+      double num_samples = beat_to_samples(old_min - new_min, asset_rate, beat_duration);
+      new_speed = sample_count / (old_length + num_samples);
+    }
+    min_time = new_min;
+    max_time = c->max_time;
+  }
+  uint32_t first = 0, last = 0;
+  if (query_clip_by_range(tr, min_time, max_time, &first, &last))
+    reserve_track_region(s, tr, first, last, min_time, max_time, c);
+  if (left_side)
+    c->min_time = min_time;
+  else
+    c->max_time = max_time;
+  c->start_offset = start_offset;
+  if (stretch) c->speed = new_speed;
+  c->internal_state_changed = (shift || stretch) ? 1 : 0;
+  update_clip_ordering(tr);
+  reset_playback_state(tr, s->playhead, 1);
+  return 0;
+}
+
+/* Engine::delete_clip (engine.cpp:400-407) */
+int wbo_delete_clip(wbo_session* s, int track, int clip) {
+  o_track* tr = s->tracks[track];
+  o_clip* c = clip_at(s, track, clip);
+  if (!c) return -1;
+  mark_deleted(tr, c);
+  update_clip_ordering(tr);
+  reset_playback_state(tr, s->playhead, 1);
+  return 0;
+}
+
+/* Engine::duplicate_clip (engine.cpp:336-344) */
+int wbo_duplicate_clip(wbo_session* s, int track, int clip, double min_beat, double max_beat) {
+  o_track* tr = s->tracks[track];
+  o_clip* src = clip_at(s, track, clip);
+  if (!src) return -1;
+  o_clip* c = (o_clip*)malloc(sizeof(*c));
+  *c = *src;
+  c->min_time = min_beat;
+  c->max_time = max_beat;
+  add_to_cliplist(s, tr, c);
   return 0;
 }
 

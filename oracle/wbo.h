@@ -44,6 +44,16 @@ int wbo_add_sample(wbo_session*, int format, uint32_t channels, uint64_t frames,
 int wbo_add_clip(wbo_session*, int track, int sample, double min_beat, double max_beat, double start_offset,
                  double speed, float gain);
 
+/* Clip editing (audio clips). `clip` = index in the track's clip list (ordered by min_time) at the time of the call:
+ * Engine::move_clip (engine.cpp:346-363), resize_clip (:365-398, calc_resize_clip clip_edit.h:18-126), delete_clip
+ * (:400-407), duplicate_clip (:336-344). Return 0, or -1 for a bad index. */
+int wbo_clip_count(wbo_session*, int track);
+int wbo_move_clip(wbo_session*, int track, int clip, double relative_pos);
+int wbo_resize_clip(wbo_session*, int track, int clip, double relative_pos, double resize_limit, double min_length,
+                    int left_side, int shift, int stretch);
+int wbo_delete_clip(wbo_session*, int track, int clip);
+int wbo_duplicate_clip(wbo_session*, int track, int clip, double min_beat, double max_beat);
+
 /* As wbo_add_clip, also setting AudioClip::fade_start / fade_end (beats, engine/clip.h:41-42).
  * EXTENSION — PARITY UNPINNED w.r.t. whitebox: the reference stores these fields but no audio code reads them,
  * so libwbref.so renders such a clip WITHOUT a fade; the port implements the builder's specification

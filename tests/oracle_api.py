@@ -36,6 +36,11 @@ def _load(path):
     lib.wbo_add_sample.argtypes = [vp, i32, u32, u64, u32, C.POINTER(vp)]
     lib.wbo_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     lib.wbo_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
+    lib.wbo_clip_count.argtypes = [vp, i32]
+    lib.wbo_move_clip.argtypes = [vp, i32, i32, dbl]
+    lib.wbo_resize_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, i32, i32, i32]
+    lib.wbo_delete_clip.argtypes = [vp, i32, i32]
+    lib.wbo_duplicate_clip.argtypes = [vp, i32, i32, dbl, dbl]
     lib.wbo_set_effects.argtypes = [vp, i32, vp]
     lib.wbo_set_resampler.argtypes = [vp, i32]
     lib.wbo_set_impulse_response.argtypes = [vp, vp, u32]
@@ -120,6 +125,22 @@ class Session:
             return self.lib.wbo_add_clip_fade(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain,
                                               fade_start, fade_end)
         return self.lib.wbo_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain)
+
+    def clip_count(self, track):
+        return self.lib.wbo_clip_count(self.h, track)
+
+    def move_clip(self, track, clip, relative_pos):
+        return self.lib.wbo_move_clip(self.h, track, clip, relative_pos)
+
+    def resize_clip(self, track, clip, relative_pos, resize_limit, min_length, left_side, shift=False, stretch=False):
+        return self.lib.wbo_resize_clip(self.h, track, clip, relative_pos, resize_limit, min_length, int(left_side),
+                                        int(shift), int(stretch))
+
+    def delete_clip(self, track, clip):
+        return self.lib.wbo_delete_clip(self.h, track, clip)
+
+    def duplicate_clip(self, track, clip, min_beat, max_beat):
+        return self.lib.wbo_duplicate_clip(self.h, track, clip, min_beat, max_beat)
 
     def set_effects(self, track, params):
         """params: a ctypes struct laid out like wbo_effects (whitebox_b200.EffectParams) or None."""

@@ -223,6 +223,59 @@ def overlaps(make_engine):
     return _collect(eng, outs, n)
 
 
+def edits(make_engine):
+    """Clip editing calls that feed the scheduler: Engine::move_clip (sets internal_state_changed: a clip moved while it
+    plays is stopped and restarted at its new offset, track.cpp:394-419), resize_clip (left / right, shift, stretch —
+    calc_resize_clip, clip_edit.h:18-126), delete_clip, duplicate_clip, and a move onto a neighbour (reserve_track_region
+    with the moved clip ignored). `clip` arguments are indices into the track's clip list ordered by min_time."""
+    rng = np.random.RandomState(2468)
+    B, rate = 128, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    spb = rate * 0.5
+    n = 0
+
+    def tr(vol=-3.0, pan=0.0):
+        nonlocal n
+        eng.add_track(vol, pan, False)
+        n += 1
+        return n - 1
+
+    def smp(frames, ch=2, r=48000):
+        return eng.add_sample(_src(rng, ch, frames, 8), r, FMT_F32)
+
+    t0 = tr(-2.0, -0.3)  # moved while it plays
+    eng.add_clip(t0, smp(6000), 0.0, 1500.0 / spb, 0.0, 1.0, 0.8)
+    t1 = tr(-4.0, 0.4)  # second clip deleted before it starts
+    eng.add_clip(t1, smp(3000), 0.0, 400.0 / spb, 0.0, 1.0, 0.7)
+    eng.add_clip(t1, smp(3000), 600.0 / spb, 1000.0 / spb, 0.0, 1.0, 0.9)
+    t2 = tr(0.0, 0.0)  # duplicated further down the timeline (and onto nothing)
+    eng.add_clip(t2, smp(4000), 100.0 / spb, 700.0 / spb, 9.0, 1.0, 1.0)
+    eng.duplicate_clip(t2, 0, 900.0 / spb, 1400.0 / spb)
+    t3 = tr(-1.0, 0.1)  # left edge resized before playback: content start follows the edge
+    eng.add_clip(t3, smp(6000), 0.0, 1200.0 / spb, 50.0, 1.0, 0.6)
+    eng.resize_clip(t3, 0, 300.0 / spb, 1200.0 / spb, 1.0 / spb, True)
+    t4 = tr(-1.5, -0.8)  # right edge pulled in, then a second clip stretched (speed changes) on its right edge
+    eng.add_clip(t4, smp(6000), 0.0, 800.0 / spb, 0.0, 1.0, 0.5)
+    eng.resize_clip(t4, 0, -250.0 / spb, 0.0, 1.0 / spb, False)
+    eng.add_clip(t4, smp(1000), 700.0 / spb, 1300.0 / spb, 0.0, 1.0, 0.7)
+    eng.resize_clip(t4, 1, 150.0 / spb, 700.0 / spb, 1.0 / spb, False, False, True)
+    t5 = tr(-7.0, 0.9)  # a clip moved onto its neighbour: the neighbour's head is trimmed
+    eng.add_clip(t5, smp(3000), 0.0, 300.0 / spb, 0.0, 1.0, 1.1)
+    eng.add_clip(t5, smp(3000), 500.0 / spb, 1100.0 / spb, 4.0, 1.0, 0.9)
+    eng.move_clip(t5, 0, 350.0 / spb)
+    t6 = tr(-5.0, 0.5)  # left edge resized with shift (content stays put), 44.1 kHz source at speed 1.25
+    eng.add_clip(t6, smp(9000, 2, 44100), 200.0 / spb, 1300.0 / spb, 30.0, 1.25, 0.75)
+    eng.resize_clip(t6, 0, 120.0 / spb, 1300.0 / spb, 1.0 / spb, True, True)
+    eng.play()
+    outs = [eng.process(3)]
+    eng.move_clip(t0, 0, 200.0 / spb)  # the clip that is playing right now
+    eng.delete_clip(t1, 1)
+    outs.append(eng.process(4))
+    eng.resize_clip(t3, 0, -100.0 / spb, 1200.0 / spb, 1.0 / spb, True)  # playing clip, no shift: plain refresh
+    outs.append(eng.process(5))
+    return _collect(eng, outs, n)
+
+
 def params(make_engine):
     """Volume / pan / mute changes between callbacks, not-playing callbacks, stop/play (track.cpp:618-643)."""
     rng = np.random.RandomState(99)
@@ -495,4 +548,4 @@ def mip_source(fmt, frames, ch):
 EXT = dict(fades=fades, effects=effects, reverb=reverb, polyphase=polyphase)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
-           event_split=event_split, overlaps=overlaps, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)
+           event_split=event_split, overlaps=overlaps, edits=edits, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)

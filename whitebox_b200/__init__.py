@@ -69,7 +69,8 @@ WBXH_SYMBOLS = [
     "wbxh_play", "wbxh_set_effects", "wbxh_set_impulse_response", "wbxh_set_resampler",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
-    "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end",
+    "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_move_clip",
+    "wbxh_resize_clip", "wbxh_delete_clip", "wbxh_duplicate_clip",
 ]
 
 _lib = None
@@ -150,6 +151,11 @@ def lib():
     L.wbxh_add_sample.argtypes = [vp, i32, u32, u64, u32, pp]
     L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     L.wbxh_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
+    L.wbxh_clip_count.argtypes = [vp, i32]
+    L.wbxh_move_clip.argtypes = [vp, i32, i32, dbl]
+    L.wbxh_resize_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, i32, i32, i32]
+    L.wbxh_delete_clip.argtypes = [vp, i32, i32]
+    L.wbxh_duplicate_clip.argtypes = [vp, i32, i32, dbl, dbl]
     L.wbxh_set_effects.argtypes = [vp, i32, vp]
     L.wbxh_set_resampler.argtypes = [vp, i32]
     L.wbxh_set_resampler.restype = None
@@ -470,6 +476,24 @@ class Engine:
             return self._ck(self.L.wbxh_add_clip_fade(self.h, track, sample, min_beat, max_beat, start_offset, speed,
                                                       gain, fade_start, fade_end))
         return self._ck(self.L.wbxh_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain))
+
+    # clip editing (clip = index in the track's clip list ordered by min_beat): Engine::move_clip / resize_clip /
+    # delete_clip / duplicate_clip of the reference
+    def clip_count(self, track):
+        return self._ck(self.L.wbxh_clip_count(self.h, track))
+
+    def move_clip(self, track, clip, relative_pos):
+        return self._ck(self.L.wbxh_move_clip(self.h, track, clip, relative_pos))
+
+    def resize_clip(self, track, clip, relative_pos, resize_limit, min_length, left_side, shift=False, stretch=False):
+        return self._ck(self.L.wbxh_resize_clip(self.h, track, clip, relative_pos, resize_limit, min_length, int(left_side),
+                                                int(shift), int(stretch)))
+
+    def delete_clip(self, track, clip):
+        return self._ck(self.L.wbxh_delete_clip(self.h, track, clip))
+
+    def duplicate_clip(self, track, clip, min_beat, max_beat):
+        return self._ck(self.L.wbxh_duplicate_clip(self.h, track, clip, min_beat, max_beat))
 
     def set_effects(self, track, params):
         """params: EffectParams (see effect_params()) or None to remove the chain."""

@@ -223,14 +223,16 @@ static void update_clip_ordering(Track& t) {
   std::sort(t.clips.begin(), t.clips.end(), [](const AudioClip* a, const AudioClip* b) { return a->min_time < b->min_time; });
 }
 
-// Engine::reserve_track_region (engine/engine.cpp:478-569) with ignore_clip == nullptr: make room for [min, max] by
-// trimming, splitting or deleting the clips first_clip..last_clip.
-void Engine::reserve_track_region(Track& t, uint32_t first_clip, uint32_t last_clip, double min, double max) {
+// Engine::reserve_track_region (engine/engine.cpp:478-569): make room for [min, max] by trimming, splitting or deleting
+// the clips first_clip..last_clip (except ignore_clip, the clip being moved / resized).
+void Engine::reserve_track_region(Track& t, uint32_t first_clip, uint32_t last_clip, double min, double max,
+                                  const AudioClip* ignore_clip) {
   auto& clips = t.clips;
   if (clips.empty()) return;
   const double current_beat_duration = beat_duration_;
   if (first_clip == last_clip) {
     AudioClip* clip = clips[first_clip];
+    if (clip == ignore_clip) return;
     if (min > clip->min_time && max < clip->max_time) {  // split the clip into two parts
       AudioClip* right = new AudioClip(*clip);
       right->min_time = max;
@@ -249,21 +251,39 @@ void Engine::reserve_track_region(Track& t, uint32_t first_clip, uint32_t last_c
   }
   AudioClip* first = clips[first_clip];
   AudioClip* last = clips[last_clip];
-  if (min > first->min_time) {
+  if (first != ignore_clip && min > first->min_time) {
     first->max_time = min;
     first_clip++;
   }
-  if (max < last->max_time) {
+  if (last != ignore_clip && max < last->max_time) {
     last->start_offset = shift_clip_content(last, last->min_time - max, current_beat_duration);
     last->min_time = max;
     last_clip--;
   }
   if (first_clip <= last_clip && last_clip < clips.size())
-    for (uint32_t i = first_clip; i <= last_clip; i++) clips[i]->deleted = true;
+    for (uint32_t i = first_clip; i <= last_clip; i++)
+      if (clips[i] != ignore_clip) clips[i]->deleted = true;
 }
 
-// Engine::add_audio_clip (engine/engine.cpp:293-309) + add_to_cliplist (:409-461): a clip that overlaps existing ones
-// trims / splits / deletes them first (reserve_track_region).
+// Engine::add_to_cliplist (engine/engine.cpp:409-461): a clip that overlaps existing ones trims / splits / deletes them
+// first (reserve_track_region).
+void Engine::add_to_cliplist(Track* track, AudioClip* clip) {
+  auto& clips = track->clips;
+  if (clips.empty() || clips.back()->max_time < clip->min_time) {  // first clip, or add to the back
+    clips.push_back(clip);
+  } else if (clips.front()->min_time > clip->max_time) {  // add to the front
+    clips.insert(clips.begin(), clip);
+  } else {
+    uint32_t first = 0, last = 0;
+    if (query_clip_by_range(*track, clip->min_time, clip->max_time, &first, &last))
+      reserve_track_region(*track, first, last, clip->min_time, clip->max_time, nullptr);  // reserve space for the clip
+    clips.push_back(clip);
+    update_clip_ordering(*track);
+  }
+  reset_playback_state(*track, playhead, true);
+}
+
+// Engine::add_audio_clip (engine/engine.cpp:293-309)
 int Engine::add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
                            double speed, float gain, double fade_start, double fade_end) {
   if (!track || sample_id >= samples_.size() || !(max_time >= min_time)) return WBX_ERR_INVALID;
@@ -277,19 +297,125 @@ int Engine::add_audio_clip(Track* track, double min_time, double max_time, doubl
   clip->fade_end = fade_end;
   clip->sample_id = sample_id;
   clip->sample_rate = samples_[sample_id].rate;
-  auto& clips = track->clips;
-  if (clips.empty() || clips.back()->max_time < clip->min_time) {  // first clip, or add to the back
-    clips.push_back(clip);
-  } else if (clips.front()->min_time > clip->max_time) {  // add to the front
-    clips.insert(clips.begin(), clip);
+  add_to_cliplist(track, clip);
+  return WBX_OK;
+}
+
+static bool owns_clip(const Track* track, const AudioClip* clip) {
+  return track && clip && std::find(track->clips.begin(), track->clips.end(), clip) != track->clips.end();
+}
+
+// Engine::duplicate_clip (engine/engine.cpp:336-344)
+int Engine::duplicate_clip(Track* track, const AudioClip* clip_to_duplicate, double min_time, double max_time) {
+  if (!owns_clip(track, clip_to_duplicate) || !(max_time >= min_time)) return WBX_ERR_INVALID;
+  AudioClip* clip = new AudioClip(*clip_to_duplicate);
+  clip->min_time = min_time;
+  clip->max_time = max_time;
+  add_to_cliplist(track, clip);
+  return WBX_OK;
+}
+
+// Engine::move_clip (engine/engine.cpp:346-363) + calc_move_clip (engine/clip_edit.h:10-16). A clip moved while it plays
+// is stopped and restarted at its new content offset by the next callback (internal_state_changed, track.cpp:394-419).
+int Engine::move_clip(Track* track, AudioClip* clip, double relative_pos) {
+  if (!owns_clip(track, clip)) return WBX_ERR_INVALID;
+  if (relative_pos == 0.0) return WBX_OK;
+  double new_pos = clip->min_time + relative_pos;
+  if (!(new_pos > 0.0)) new_pos = 0.0;  // math::max(.., min_move = 0.0)
+  const double min_time = new_pos, max_time = new_pos + (clip->max_time - clip->min_time);
+  uint32_t first = 0, last = 0;
+  if (query_clip_by_range(*track, min_time, max_time, &first, &last))
+    reserve_track_region(*track, first, last, min_time, max_time, clip);
+  clip->min_time = min_time;
+  clip->max_time = max_time;
+  clip->internal_state_changed = true;
+  update_clip_ordering(*track);
+  reset_playback_state(*track, playhead, true);
+  return WBX_OK;
+}
+
+// Engine::resize_clip (engine/engine.cpp:365-398) + calc_resize_clip (engine/clip_edit.h:18-126, clamp_at_resize_pos off):
+// drag the left or right edge by relative_pos beats; `shift` keeps the content in place instead of the edge, `stretch`
+// changes the clip speed so that the same content fills the new length.
+int Engine::resize_clip(Track* track, AudioClip* clip, double relative_pos, double resize_limit, double min_length,
+                        bool left_side, bool shift, bool stretch) {
+  if (!owns_clip(track, clip)) return WBX_ERR_INVALID;
+  if (relative_pos == 0.0) return WBX_OK;
+  const double beat_duration = beat_duration_;
+  const double asset_rate = (double)clip->sample_rate;
+  const double sample_count = (double)samples_[clip->sample_id].count;
+  double min_time, max_time, start_offset = clip->start_offset, new_speed = 1.0;
+  if (!left_side) {
+    const double old_max = clip->max_time;
+    const double actual_min_length = resize_limit + min_length - clip->min_time;
+    double new_max = clip->max_time + relative_pos;
+    if (!(new_max > 0.0)) new_max = 0.0;
+    const double length = new_max - clip->min_time;
+    if (length < actual_min_length) new_max = clip->min_time + actual_min_length;
+    if (shift) {
+      const double mult = clip->speed;
+      start_offset = samples_to_beat(start_offset, asset_rate, beat_duration);
+      if (old_max < new_max)
+        start_offset -= (new_max - old_max) * mult;
+      else
+        start_offset += (old_max - new_max) * mult;
+      if (!(start_offset > 0.0)) start_offset = 0.0;
+      if (!(start_offset < sample_count)) start_offset = sample_count;  // math::min(start_offset, count)
+      start_offset = beat_to_samples(start_offset, asset_rate, beat_duration);
+    }
+    if (stretch) {
+      const double old_length = sample_count / clip->speed;
+      const double num_samples = beat_to_samples(relative_pos, asset_rate, beat_duration);
+      new_speed = sample_count / (old_length + num_samples);
+    }
+    min_time = clip->min_time;
+    max_time = new_max;
   } else {
-    uint32_t first = 0, last = 0;
-    if (query_clip_by_range(*track, clip->min_time, clip->max_time, &first, &last))
-      reserve_track_region(*track, first, last, clip->min_time, clip->max_time);  // trim to reserve space for the clip
-    clips.push_back(clip);
-    update_clip_ordering(*track);
+    const double old_min = clip->min_time;
+    const double actual_min_length = clip->max_time - resize_limit + min_length;
+    double new_min = clip->min_time + relative_pos;
+    if (!(new_min > 0.0)) new_min = 0.0;
+    const double length = clip->max_time - new_min;
+    if (length < actual_min_length) new_min = clip->max_time - actual_min_length;
+    if (!shift) {
+      start_offset = samples_to_beat(start_offset, asset_rate, beat_duration);
+      if (old_min < new_min)
+        start_offset -= old_min - new_min;
+      else
+        start_offset += new_min - old_min;
+      if (start_offset < 0.0) new_min = new_min - start_offset;
+      if (!(start_offset > 0.0)) start_offset = 0.0;
+      start_offset = beat_to_samples(start_offset, asset_rate, beat_duration);
+    }
+    if (stretch) {
+      const double old_length = sample_count / clip->speed;
+      const double num_samples = beat_to_samples(old_min - new_min, asset_rate, beat_duration);
+      new_speed = sample_count / (old_length + num_samples);
+    }
+    min_time = new_min;
+    max_time = clip->max_time;
   }
-  reset_playback_state(*track, playhead, true);  // add_to_cliplist, engine.cpp:415,425,...
+  uint32_t first = 0, last = 0;
+  if (query_clip_by_range(*track, min_time, max_time, &first, &last))
+    reserve_track_region(*track, first, last, min_time, max_time, clip);
+  if (left_side)
+    clip->min_time = min_time;
+  else
+    clip->max_time = max_time;
+  clip->start_offset = start_offset;
+  if (stretch) clip->speed = new_speed;
+  clip->internal_state_changed = shift || stretch;
+  update_clip_ordering(*track);
+  reset_playback_state(*track, playhead, true);
+  return WBX_OK;
+}
+
+// Engine::delete_clip (engine/engine.cpp:400-407). The clip is parked in the track's graveyard (see update_clip_ordering).
+int Engine::delete_clip(Track* track, AudioClip* clip) {
+  if (!owns_clip(track, clip)) return WBX_ERR_INVALID;
+  clip->deleted = true;
+  update_clip_ordering(*track);
+  reset_playback_state(*track, playhead, true);
   return WBX_OK;
 }
 
@@ -787,6 +913,34 @@ int wbxh_add_clip_fade(wbxh_engine* h, int track, int sample, double min_beat, d
   return h->eng.add_audio_clip(h->eng.tracks[track], min_beat, max_beat, start_offset, (uint32_t)sample, speed, gain,
                                fade_start, fade_end);
 }
+static wbx::AudioClip* clip_at(wbxh_engine* h, int track, int clip) {
+  if (track < 0 || (size_t)track >= h->eng.tracks.size()) return nullptr;
+  auto& clips = h->eng.tracks[track]->clips;
+  return (clip < 0 || (size_t)clip >= clips.size()) ? nullptr : clips[clip];
+}
+int wbxh_clip_count(wbxh_engine* h, int track) {
+  return (track < 0 || (size_t)track >= h->eng.tracks.size()) ? WBX_ERR_INVALID : (int)h->eng.tracks[track]->clips.size();
+}
+int wbxh_move_clip(wbxh_engine* h, int track, int clip, double relative_pos) {
+  wbx::AudioClip* c = clip_at(h, track, clip);
+  return c ? h->eng.move_clip(h->eng.tracks[track], c, relative_pos) : WBX_ERR_INVALID;
+}
+int wbxh_resize_clip(wbxh_engine* h, int track, int clip, double relative_pos, double resize_limit, double min_length,
+                     int left_side, int shift, int stretch) {
+  wbx::AudioClip* c = clip_at(h, track, clip);
+  return c ? h->eng.resize_clip(h->eng.tracks[track], c, relative_pos, resize_limit, min_length, left_side != 0, shift != 0,
+                                stretch != 0)
+           : WBX_ERR_INVALID;
+}
+int wbxh_delete_clip(wbxh_engine* h, int track, int clip) {
+  wbx::AudioClip* c = clip_at(h, track, clip);
+  return c ? h->eng.delete_clip(h->eng.tracks[track], c) : WBX_ERR_INVALID;
+}
+int wbxh_duplicate_clip(wbxh_engine* h, int track, int clip, double min_beat, double max_beat) {
+  wbx::AudioClip* c = clip_at(h, track, clip);
+  return c ? h->eng.duplicate_clip(h->eng.tracks[track], c, min_beat, max_beat) : WBX_ERR_INVALID;
+}
+
 int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params) {
   if (track < 0 || (size_t)track >= h->eng.tracks.size()) return WBX_ERR_INVALID;
   h->eng.tracks[track]->set_effects(params);

@@ -134,6 +134,26 @@ class ShardedEngine:
         e, i = self._track(t)
         e.set_effects(i, params)
 
+    def clip_count(self, t):
+        e, i = self._track(t)
+        return e.clip_count(i)
+
+    def move_clip(self, t, clip, relative_pos):
+        e, i = self._track(t)
+        return e.move_clip(i, clip, relative_pos)
+
+    def resize_clip(self, t, clip, *a, **k):
+        e, i = self._track(t)
+        return e.resize_clip(i, clip, *a, **k)
+
+    def delete_clip(self, t, clip):
+        e, i = self._track(t)
+        return e.delete_clip(i, clip)
+
+    def duplicate_clip(self, t, clip, min_beat, max_beat):
+        e, i = self._track(t)
+        return e.duplicate_clip(i, clip, min_beat, max_beat)
+
     def set_impulse_response(self, h):
         for e in self.shards:
             e.set_impulse_response(h)
