@@ -41,6 +41,7 @@ int wbxh_add_clip_fade(wbxh_engine* h, int track, int sample, double min_beat, d
 /* Clip editing, `clip` = index in the track's clip list (ordered by min_beat) at the time of the call: Engine::move_clip
  * (engine/engine.cpp:346), resize_clip (:365), delete_clip (:400), duplicate_clip (:336). 0 or a negative wbx_status. */
 int wbxh_clip_count(wbxh_engine* h, int track);
+int wbxh_clip_range(wbxh_engine* h, int track, int clip, double* min_beat, double* max_beat);
 int wbxh_move_clip(wbxh_engine* h, int track, int clip, double relative_pos);
 int wbxh_resize_clip(wbxh_engine* h, int track, int clip, double relative_pos, double resize_limit, double min_length,
                      int left_side, int shift, int stretch);

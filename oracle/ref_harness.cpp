@@ -114,6 +114,14 @@ static Clip* clip_at(wbo_session* s, int track, int clip) {
   return (clip < 0 || (size_t)clip >= clips.size()) ? nullptr : clips[clip];
 }
 
+int wbo_clip_range(wbo_session* s, int track, int clip, double* min_beat, double* max_beat) {
+  Clip* c = clip_at(s, track, clip);
+  if (!c) return -1;
+  *min_beat = c->min_time;
+  *max_beat = c->max_time;
+  return 0;
+}
+
 int wbo_move_clip(wbo_session* s, int track, int clip, double relative_pos) {
   Clip* c = clip_at(s, track, clip);
   if (!c) return -1;

@@ -384,7 +384,9 @@ static void reserve_track_region(wbo_session* s, o_track* tr, uint32_t first_cli
     if (clip == ignore_clip) return;
     if (min > clip->min_time && max < clip->max_time) { /* split into two parts */
       o_clip* right = (o_clip*)malloc(sizeof(*right));
-      *right = *clip;
+      *right = *clip; /* Clip(const Clip&), clip.h:92-112: `deleted` and `internal_state_changed` are NOT copied */
+      right->deleted = 0;
+      right->internal_state_changed = 0;
       right->min_time = max;
       right->start_offset = shift_clip_content(right, clip->min_time - max, current_beat_duration);
       clip->max_time = min;
@@ -468,6 +470,14 @@ int wbo_clip_count(wbo_session* s, int track) { return (int)s->tracks[track]->n_
 static o_clip* clip_at(wbo_session* s, int track, int clip) {
   o_track* tr = s->tracks[track];
   return (clip < 0 || (uint32_t)clip >= tr->n_clips) ? NULL : tr->clips[clip];
+}
+
+int wbo_clip_range(wbo_session* s, int track, int clip, double* min_beat, double* max_beat) {
+  o_clip* c = clip_at(s, track, clip);
+  if (!c) return -1;
+  *min_beat = c->min_time;
+  *max_beat = c->max_time;
+  return 0;
 }
 
 /* Engine::move_clip (engine.cpp:346-363) + calc_move_clip (clip_edit.h:10-16) */
@@ -584,7 +594,9 @@ int wbo_duplicate_clip(wbo_session* s, int track, int clip, double min_beat, dou
   o_clip* src = clip_at(s, track, clip);
   if (!src) return -1;
   o_clip* c = (o_clip*)malloc(sizeof(*c));
-  *c = *src;
+  *c = *src; /* Clip(const Clip&): flags start cleared, see reserve_track_region */
+  c->deleted = 0;
+  c->internal_state_changed = 0;
   c->min_time = min_beat;
   c->max_time = max_beat;
   add_to_cliplist(s, tr, c);

@@ -48,6 +48,7 @@ int wbo_add_clip(wbo_session*, int track, int sample, double min_beat, double ma
  * Engine::move_clip (engine.cpp:346-363), resize_clip (:365-398, calc_resize_clip clip_edit.h:18-126), delete_clip
  * (:400-407), duplicate_clip (:336-344). Return 0, or -1 for a bad index. */
 int wbo_clip_count(wbo_session*, int track);
+int wbo_clip_range(wbo_session*, int track, int clip, double* min_beat, double* max_beat);
 int wbo_move_clip(wbo_session*, int track, int clip, double relative_pos);
 int wbo_resize_clip(wbo_session*, int track, int clip, double relative_pos, double resize_limit, double min_length,
                     int left_side, int shift, int stretch);

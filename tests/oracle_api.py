@@ -37,6 +37,7 @@ def _load(path):
     lib.wbo_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     lib.wbo_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
     lib.wbo_clip_count.argtypes = [vp, i32]
+    lib.wbo_clip_range.argtypes = [vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
     lib.wbo_move_clip.argtypes = [vp, i32, i32, dbl]
     lib.wbo_resize_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, i32, i32, i32]
     lib.wbo_delete_clip.argtypes = [vp, i32, i32]
@@ -128,6 +129,11 @@ class Session:
 
     def clip_count(self, track):
         return self.lib.wbo_clip_count(self.h, track)
+
+    def clip_range(self, track, clip):
+        a, b = C.c_double(), C.c_double()
+        assert self.lib.wbo_clip_range(self.h, track, clip, C.byref(a), C.byref(b)) == 0
+        return a.value, b.value
 
     def move_clip(self, track, clip, relative_pos):
         return self.lib.wbo_move_clip(self.h, track, clip, relative_pos)

@@ -535,6 +535,67 @@ def fuzz_overlap(make_engine, seed):
     return _collect(eng, outs, n_tracks)
 
 
+def fuzz_edits(make_engine, seed):
+    """Random sessions edited between callbacks: move / resize (left, right, shift) / delete / duplicate / add, some of
+    them on the clip that is playing. (stretch is exercised by `edits`; random stretches drive the speed to absurd
+    values.)"""
+    rng = np.random.RandomState(7000 + seed)
+    B = int(rng.choice([32, 64, 128]))
+    rate = int(rng.choice([44100, 48000]))
+    eng = make_engine(2, B, rate, 120.0)
+    spb = rate * 0.5
+    n_tracks = int(rng.randint(1, 5))
+    n_blocks = int(rng.randint(8, 16))
+    total = n_blocks * B
+    sids = []
+    for _ in range(3):
+        srate = int(rng.choice([rate, 44100, 96000]))
+        sids.append(eng.add_sample(_src(rng, 2, int(rng.randint(500, 8000)), n_tracks), srate, FMT_F32))
+
+    def frac():
+        return float(rng.randint(1, 1000)) / 1024.0  # keeps min_time ties out of the fixture
+
+    def drop_clip(t):
+        a = float(rng.randint(0, total)) + frac()
+        b = a + float(rng.randint(8, total // 2 + 9))
+        eng.add_clip(t, sids[int(rng.randint(0, 3))], a / spb, b / spb, float(rng.randint(0, 40)),
+                     float(rng.choice([1.0, 1.0, 0.5, 1.3])), float(rng.uniform(0.1, 1.2)))
+
+    for t in range(n_tracks):
+        eng.add_track(float(rng.uniform(-20, 3)), float(rng.uniform(-1, 1)), False)
+        for _ in range(int(rng.randint(1, 5))):
+            drop_clip(t)
+    eng.play()
+    outs = []
+    done = 0
+    while done < n_blocks:
+        n = int(min(n_blocks - done, rng.randint(1, 4)))
+        outs.append(eng.process(n))
+        done += n
+        if done >= n_blocks:
+            break
+        t = int(rng.randint(0, n_tracks))
+        nc = eng.clip_count(t)
+        op = int(rng.randint(0, 6))
+        if nc == 0 or op == 0:
+            drop_clip(t)
+            continue
+        c = int(rng.randint(0, nc))
+        lo, hi = eng.clip_range(t, c)  # the UI passes the clip's own opposite edge as the resize limit (timeline.cpp:1428,1436)
+        if op == 1:
+            eng.move_clip(t, c, (float(rng.randint(-total // 3, total // 3)) + frac()) / spb)
+        elif op == 2:
+            eng.resize_clip(t, c, (float(rng.randint(-200, 200)) + frac()) / spb, lo, 4.0 / spb, False, bool(rng.rand() < 0.3))
+        elif op == 3:
+            eng.resize_clip(t, c, (float(rng.randint(-200, 200)) + frac()) / spb, hi, 4.0 / spb, True, bool(rng.rand() < 0.3))
+        elif op == 4:
+            eng.delete_clip(t, c)
+        else:
+            a = float(rng.randint(0, total)) + frac()
+            eng.duplicate_clip(t, c, a / spb, (a + float(rng.randint(8, total // 3 + 9))) / spb)
+    return _collect(eng, outs, n_tracks)
+
+
 MIP_CASES = dict(f32s=(FMT_F32, 20011, 2), i16m=(FMT_I16, 4100, 1), i32s=(FMT_I32, 777, 2))
 
 

@@ -127,6 +127,25 @@ def test_host_scheduler_matches_port_overlap_fuzz(wb):
     assert ran > 50
 
 
+def test_host_scheduler_matches_port_edit_fuzz(wb):
+    """The product's clip editing (move / resize / delete / duplicate, also on the playing clip) + scheduler against the
+    C restatement on random sessions."""
+    import oracle_api as o
+    L = o.lib("port")
+    L.wbo_ub_count.restype = ctypes.c_uint64
+    ran = 0
+    for seed in range(100):
+        before = L.wbo_ub_count()
+        ref = sc.fuzz_edits(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), seed)
+        if L.wbo_ub_count() != before:
+            continue
+        res = sc.fuzz_edits(lambda C, B, r, bpm: sr.ScheduleOnlyEngine(C, B, r, bpm, seed % 2 == 0), seed)
+        for k in ref:
+            assert _same(res[k], ref[k]), "fuzz_edits%d: %s" % (seed, k)
+        ran += 1
+    assert ran > 60
+
+
 @pytest.mark.parametrize("batched", [True, False])
 def test_fade_extension_host_matches_port(wb, batched):
     """EXTENSION (parity unpinned w.r.t. whitebox): the product's scheduler + documented segment semantics

@@ -126,6 +126,23 @@ def test_port_matches_reference_overlap_fuzz():
 
 
 @needs_ref
+def test_port_matches_reference_edit_fuzz():
+    """Random sessions edited between callbacks (move / resize / delete / duplicate / add, also on the playing clip): the
+    C restatement against the reference itself. Found that Clip's copy constructor drops `internal_state_changed`."""
+    L = o.lib("port")
+    L.wbo_ub_count.restype = ctypes.c_uint64
+    ran = 0
+    for seed in range(150):
+        before = L.wbo_ub_count()
+        p = sc.fuzz_edits(mk("port"), seed)
+        if L.wbo_ub_count() != before:
+            continue
+        assert_same(p, sc.fuzz_edits(mk("reference"), seed), "fuzz_edits%d" % seed)
+        ran += 1
+    assert ran > 100
+
+
+@needs_ref
 def test_golden_is_current(golden_dir):
     """The committed vectors are what the reference produces today."""
     for name in ("kat", "event_split", "cfg3_small"):

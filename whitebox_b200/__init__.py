@@ -69,7 +69,7 @@ WBXH_SYMBOLS = [
     "wbxh_play", "wbxh_set_effects", "wbxh_set_impulse_response", "wbxh_set_resampler",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
-    "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_move_clip",
+    "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_clip_range", "wbxh_move_clip",
     "wbxh_resize_clip", "wbxh_delete_clip", "wbxh_duplicate_clip",
 ]
 
@@ -152,6 +152,7 @@ def lib():
     L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     L.wbxh_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
     L.wbxh_clip_count.argtypes = [vp, i32]
+    L.wbxh_clip_range.argtypes = [vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.wbxh_move_clip.argtypes = [vp, i32, i32, dbl]
     L.wbxh_resize_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, i32, i32, i32]
     L.wbxh_delete_clip.argtypes = [vp, i32, i32]
@@ -481,6 +482,11 @@ class Engine:
     # delete_clip / duplicate_clip of the reference
     def clip_count(self, track):
         return self._ck(self.L.wbxh_clip_count(self.h, track))
+
+    def clip_range(self, track, clip):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.wbxh_clip_range(self.h, track, clip, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def move_clip(self, track, clip, relative_pos):
         return self._ck(self.L.wbxh_move_clip(self.h, track, clip, relative_pos))

@@ -235,6 +235,7 @@ void Engine::reserve_track_region(Track& t, uint32_t first_clip, uint32_t last_c
     if (clip == ignore_clip) return;
     if (min > clip->min_time && max < clip->max_time) {  // split the clip into two parts
       AudioClip* right = new AudioClip(*clip);
+      right->deleted = right->internal_state_changed = false;  // Clip(const Clip&) does not copy them (clip.h:92-112)
       right->min_time = max;
       right->start_offset = shift_clip_content(right, clip->min_time - max, current_beat_duration);
       clip->max_time = min;
@@ -309,6 +310,7 @@ static bool owns_clip(const Track* track, const AudioClip* clip) {
 int Engine::duplicate_clip(Track* track, const AudioClip* clip_to_duplicate, double min_time, double max_time) {
   if (!owns_clip(track, clip_to_duplicate) || !(max_time >= min_time)) return WBX_ERR_INVALID;
   AudioClip* clip = new AudioClip(*clip_to_duplicate);
+  clip->deleted = clip->internal_state_changed = false;  // Clip(const Clip&) does not copy them (clip.h:92-112)
   clip->min_time = min_time;
   clip->max_time = max_time;
   add_to_cliplist(track, clip);
@@ -920,6 +922,13 @@ static wbx::AudioClip* clip_at(wbxh_engine* h, int track, int clip) {
 }
 int wbxh_clip_count(wbxh_engine* h, int track) {
   return (track < 0 || (size_t)track >= h->eng.tracks.size()) ? WBX_ERR_INVALID : (int)h->eng.tracks[track]->clips.size();
+}
+int wbxh_clip_range(wbxh_engine* h, int track, int clip, double* min_beat, double* max_beat) {
+  wbx::AudioClip* c = clip_at(h, track, clip);
+  if (!c || !min_beat || !max_beat) return WBX_ERR_INVALID;
+  *min_beat = c->min_time;
+  *max_beat = c->max_time;
+  return WBX_OK;
 }
 int wbxh_move_clip(wbxh_engine* h, int track, int clip, double relative_pos) {
   wbx::AudioClip* c = clip_at(h, track, clip);

@@ -138,6 +138,10 @@ class ShardedEngine:
         e, i = self._track(t)
         return e.clip_count(i)
 
+    def clip_range(self, t, clip):
+        e, i = self._track(t)
+        return e.clip_range(i, clip)
+
     def move_clip(self, t, clip, relative_pos):
         e, i = self._track(t)
         return e.move_clip(i, clip, relative_pos)
