@@ -51,6 +51,7 @@ int wbxh_duplicate_clip(wbxh_engine* h, int track, int clip, double min_beat, do
 int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params);
 int wbxh_set_impulse_response(wbxh_engine* h, const float* ir, uint32_t n_taps); /* convolution reverb IR (wbx.h) */
 void wbxh_set_resampler(wbxh_engine* h, int mode); /* 0 linear (reference), 1 polyphase (extension, wbx.h) */
+void wbxh_set_bpm(wbxh_engine* h, double bpm); /* Engine::set_bpm (engine/engine.cpp:24-30) */
 void wbxh_set_playhead(wbxh_engine* h, double beat);
 void wbxh_play(wbxh_engine* h);
 void wbxh_stop(wbxh_engine* h);

@@ -64,6 +64,7 @@ int wbo_add_track(wbo_session* s, float volume_db, float pan, int mute) {
   return (int)s->engine.tracks.size() - 1;
 }
 
+void wbo_set_bpm(wbo_session* s, double bpm) { s->engine.set_bpm(bpm); }
 void wbo_set_volume(wbo_session* s, int track, float db) { s->engine.tracks[track]->set_volume(db); }
 void wbo_set_pan(wbo_session* s, int track, float pan) { s->engine.tracks[track]->set_pan(pan); }
 void wbo_set_mute(wbo_session* s, int track, int mute) { s->engine.tracks[track]->set_mute(mute != 0); }

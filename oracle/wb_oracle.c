@@ -465,6 +465,8 @@ static void add_to_cliplist(wbo_session* s, o_track* tr, o_clip* c) {
   reset_playback_state(tr, s->playhead, 1);
 }
 
+void wbo_set_bpm(wbo_session* s, double bpm) { s->beat_duration = 60.0 / bpm; } /* engine.cpp:24-30 */
+
 int wbo_clip_count(wbo_session* s, int track) { return (int)s->tracks[track]->n_clips; }
 
 static o_clip* clip_at(wbo_session* s, int track, int clip) {

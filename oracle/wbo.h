@@ -29,6 +29,9 @@ wbo_session* wbo_create(uint32_t out_channels, uint32_t block_frames, uint32_t s
 void wbo_destroy(wbo_session*);
 const char* wbo_kind(void); /* "reference" or "port" */
 
+/* Engine::set_bpm (engine.cpp:24-30): takes effect from the next callback's transport math (engine.cpp:1578-1585). */
+void wbo_set_bpm(wbo_session*, double bpm);
+
 /* Engine::add_track + Track::set_volume/set_pan/set_mute. Returns the track index. */
 int wbo_add_track(wbo_session*, float volume_db, float pan, int mute);
 void wbo_set_volume(wbo_session*, int track, float db);

@@ -36,6 +36,8 @@ def _load(path):
     lib.wbo_add_sample.argtypes = [vp, i32, u32, u64, u32, C.POINTER(vp)]
     lib.wbo_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     lib.wbo_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
+    lib.wbo_set_bpm.argtypes = [vp, dbl]
+    lib.wbo_set_bpm.restype = None
     lib.wbo_clip_count.argtypes = [vp, i32]
     lib.wbo_clip_range.argtypes = [vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
     lib.wbo_move_clip.argtypes = [vp, i32, i32, dbl]
@@ -126,6 +128,9 @@ class Session:
             return self.lib.wbo_add_clip_fade(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain,
                                               fade_start, fade_end)
         return self.lib.wbo_add_clip(self.h, track, sample, min_beat, max_beat, start_offset, speed, gain)
+
+    def set_bpm(self, bpm):
+        self.lib.wbo_set_bpm(self.h, bpm)
 
     def clip_count(self, track):
         return self.lib.wbo_clip_count(self.h, track)

@@ -276,6 +276,31 @@ def edits(make_engine):
     return _collect(eng, outs, n)
 
 
+def tempo(make_engine):
+    """Engine::set_bpm while the session plays: beat_duration feeds the transport math of every callback
+    (engine.cpp:1578-1585) and the beat -> sample conversions of the clip events (track.cpp:359-361, 423-425); voices that
+    are already streaming are untouched. Clips start / stop after the change, one clip is added under the new tempo."""
+    rng = np.random.RandomState(1357)
+    B, rate = 128, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    spb = rate * 0.5
+    for t in range(4):
+        eng.add_track(-3.0 - t, -0.6 + 0.4 * t, False)
+    s = [eng.add_sample(_src(rng, 2, 8000, 4), 48000 if i % 2 == 0 else 44100, FMT_F32) for i in range(4)]
+    eng.add_clip(0, s[0], 0.0, 2000.0 / spb, 0.0, 1.0, 0.8)            # plays across both tempo changes
+    eng.add_clip(1, s[1], 500.0 / spb, 900.0 / spb, 5.0, 1.0, 0.7)     # starts after the first change
+    eng.add_clip(2, s[2], 100.0 / spb, 700.0 / spb, 0.0, 1.0, 0.9)     # stops after the first change
+    eng.add_clip(3, s[3], 1000.0 / spb, 1500.0 / spb, 0.0, 1.3, 0.6)
+    eng.play()
+    outs = [eng.process(3)]
+    eng.set_bpm(93.7)
+    outs.append(eng.process(5))
+    eng.add_clip(1, s[0], 0.05, 0.058, 12.0, 1.0, 0.5)                 # added under the new tempo, ahead of the playhead
+    eng.set_bpm(171.0)
+    outs.append(eng.process(6))
+    return _collect(eng, outs, 4)
+
+
 def params(make_engine):
     """Volume / pan / mute changes between callbacks, not-playing callbacks, stop/play (track.cpp:618-643)."""
     rng = np.random.RandomState(99)
@@ -609,4 +634,4 @@ def mip_source(fmt, frames, ch):
 EXT = dict(fades=fades, effects=effects, reverb=reverb, polyphase=polyphase)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
-           event_split=event_split, overlaps=overlaps, edits=edits, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)
+           event_split=event_split, overlaps=overlaps, edits=edits, tempo=tempo, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)

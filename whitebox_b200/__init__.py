@@ -69,7 +69,7 @@ WBXH_SYMBOLS = [
     "wbxh_play", "wbxh_set_effects", "wbxh_set_impulse_response", "wbxh_set_resampler",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
-    "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_clip_range", "wbxh_move_clip",
+    "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_clip_range", "wbxh_set_bpm", "wbxh_move_clip",
     "wbxh_resize_clip", "wbxh_delete_clip", "wbxh_duplicate_clip",
 ]
 
@@ -162,6 +162,8 @@ def lib():
     L.wbxh_set_resampler.restype = None
     L.wbxh_set_impulse_response.argtypes = [vp, vp, u32]
     L.wbx_set_impulse_response.argtypes = [vp, vp, u32]
+    L.wbxh_set_bpm.argtypes = [vp, dbl]
+    L.wbxh_set_bpm.restype = None
     L.wbxh_set_playhead.argtypes = [vp, dbl]
     L.wbxh_set_playhead.restype = None
     for f in ("wbxh_play", "wbxh_stop"):
@@ -515,6 +517,9 @@ class Engine:
     def set_resampler(self, mode):
         """0 = linear (the reference's only resampler), 1 = polyphase windowed sinc (extension)."""
         self.L.wbxh_set_resampler(self.h, mode)
+
+    def set_bpm(self, bpm):
+        self.L.wbxh_set_bpm(self.h, bpm)
 
     def set_playhead(self, beat):
         self.L.wbxh_set_playhead(self.h, beat)

@@ -959,6 +959,7 @@ int wbxh_set_impulse_response(wbxh_engine* h, const float* ir, uint32_t n_taps) 
   return h->eng.set_impulse_response(ir, n_taps);
 }
 void wbxh_set_resampler(wbxh_engine* h, int mode) { h->eng.resampler_mode = mode; }
+void wbxh_set_bpm(wbxh_engine* h, double bpm) { h->eng.set_bpm(bpm); }
 void wbxh_set_playhead(wbxh_engine* h, double beat) { h->eng.set_playhead_position(beat); }
 void wbxh_play(wbxh_engine* h) { h->eng.play(); }
 void wbxh_stop(wbxh_engine* h) { h->eng.stop(); }

@@ -166,6 +166,10 @@ class ShardedEngine:
         for e in self.shards:
             e.set_resampler(mode)
 
+    def set_bpm(self, bpm):
+        for e in self.shards:
+            e.set_bpm(bpm)
+
     def set_playhead(self, beat):
         for e in self.shards:
             e.set_playhead(beat)
