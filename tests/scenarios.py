@@ -601,7 +601,10 @@ def fuzz_edits(make_engine, seed):
             break
         t = int(rng.randint(0, n_tracks))
         nc = eng.clip_count(t)
-        op = int(rng.randint(0, 6))
+        op = int(rng.randint(0, 7))
+        if op == 6:  # tempo change: later edits shift clip content with the new beat duration
+            eng.set_bpm(float(rng.choice([90.0, 120.0, 133.3, 150.0])))
+            continue
         if nc == 0 or op == 0:
             drop_clip(t)
             continue
