@@ -24,6 +24,7 @@ struct TrackParameterState {
   float pan = 0.0f;
   float pan_coeffs[2] = {0.0f, 0.0f};
   bool mute = false;
+  bool solo = false;  // UI only (engine/track.h:52), kept by Engine::solo_track
 };
 
 struct PanningCoefficient {
@@ -108,6 +109,13 @@ class Engine {
   void set_playhead_position(double beat);
 
   Track* add_track(const std::string& name);  // engine/engine.cpp:199-207
+  // engine/engine.cpp:209-217, 228-243, 245-262, 1460-1464: mixer-side calls that change what the path sums — a track
+  // leaves, the bus summation order changes, every other track is muted / unmuted, a clip's gain changes (the playing
+  // voice reads it every callback, track.cpp:676,716)
+  int delete_track(uint32_t slot);
+  int move_track(uint32_t from_slot, uint32_t to_slot);
+  int solo_track(uint32_t slot);
+  int set_clip_gain(Track* track, uint32_t clip_id, float gain);
   // Resident Sample (dsp/sample.h:18-28); returns the id clips refer to, or a negative wbx_status.
   int add_sample(int format, uint32_t channels, uint64_t frames, uint32_t sample_rate, const void* const* planar);
   // engine/engine.cpp:293-309 + add_to_cliplist (:409-461): overlapping clips are trimmed / split / deleted first

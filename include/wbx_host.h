@@ -40,6 +40,11 @@ int wbxh_add_clip_fade(wbxh_engine* h, int track, int sample, double min_beat, d
                        double speed, float gain, double fade_start, double fade_end);
 /* Clip editing, `clip` = index in the track's clip list (ordered by min_beat) at the time of the call: Engine::move_clip
  * (engine/engine.cpp:346), resize_clip (:365), delete_clip (:400), duplicate_clip (:336). 0 or a negative wbx_status. */
+/* Engine::delete_track (engine/engine.cpp:209), move_track (:228), solo_track (:245), set_clip_gain (:1460) */
+int wbxh_delete_track(wbxh_engine* h, int track);
+int wbxh_move_track(wbxh_engine* h, int from_slot, int to_slot);
+int wbxh_solo_track(wbxh_engine* h, int track);
+int wbxh_set_clip_gain(wbxh_engine* h, int track, int clip, float gain);
 int wbxh_clip_count(wbxh_engine* h, int track);
 int wbxh_clip_range(wbxh_engine* h, int track, int clip, double* min_beat, double* max_beat);
 int wbxh_move_clip(wbxh_engine* h, int track, int clip, double relative_pos);

@@ -153,6 +153,15 @@ int wbo_duplicate_clip(wbo_session* s, int track, int clip, double min_beat, dou
   return 0;
 }
 
+int wbo_set_clip_gain(wbo_session* s, int track, int clip, float gain) {
+  if (!clip_at(s, track, clip)) return -1;
+  s->engine.set_clip_gain(s->engine.tracks[track], (uint32_t)clip, gain);
+  return 0;
+}
+void wbo_solo_track(wbo_session* s, int track) { s->engine.solo_track((uint32_t)track); }
+void wbo_move_track(wbo_session* s, int from_slot, int to_slot) { s->engine.move_track((uint32_t)from_slot, (uint32_t)to_slot); }
+void wbo_delete_track(wbo_session* s, int track) { s->engine.delete_track((uint32_t)track); }
+
 int wbo_set_effects(wbo_session*, int, const wbo_effects*) { return -1; }  // the reference has no effects
 int wbo_set_impulse_response(wbo_session*, const float*, uint32_t) { return -1; }
 void wbo_set_resampler(wbo_session*, int) {}  // the reference has only the linear resampler

@@ -79,6 +79,7 @@ typedef struct {
 typedef struct {
   o_clip** clips;
   uint32_t n_clips, cap_clips;
+  int ui_solo;        /* TrackParameterState::solo of ui_parameter_state (track.h:52, UI only) */
   o_clip** graveyard; /* clips trimmed away by later edits */
   uint32_t n_grave, cap_grave;
   o_fx fx;
@@ -170,18 +171,22 @@ wbo_session* wbo_create(uint32_t out_channels, uint32_t block_frames, uint32_t s
   return s;
 }
 
+static void track_free(o_track* tr) {
+  for (uint32_t i = 0; i < tr->n_clips; i++) free(tr->clips[i]);
+  free(tr->clips);
+  for (uint32_t i = 0; i < tr->n_grave; i++) free(tr->graveyard[i]);
+  free(tr->graveyard);
+  fx_free(&tr->fx);
+  free(tr->events);
+  free(tr->msgs);
+  free(tr);
+}
+
 void wbo_destroy(wbo_session* s) {
   if (!s) return;
   for (uint32_t t = 0; t < s->n_tracks; t++) {
     o_track* tr = s->tracks[t];
-    for (uint32_t i = 0; i < tr->n_clips; i++) free(tr->clips[i]);
-    free(tr->clips);
-    for (uint32_t i = 0; i < tr->n_grave; i++) free(tr->graveyard[i]);
-    free(tr->graveyard);
-    fx_free(&tr->fx);
-    free(tr->events);
-    free(tr->msgs);
-    free(tr);
+    track_free(tr);
   }
   free(s->tracks);
   for (uint32_t i = 0; i < s->n_samples; i++) {
@@ -466,6 +471,50 @@ static void add_to_cliplist(wbo_session* s, o_track* tr, o_clip* c) {
 }
 
 void wbo_set_bpm(wbo_session* s, double bpm) { s->beat_duration = 60.0 / bpm; } /* engine.cpp:24-30 */
+
+/* Engine::set_clip_gain (engine.cpp:1460-1464) */
+int wbo_set_clip_gain(wbo_session* s, int track, int clip, float gain) {
+  o_track* tr = s->tracks[track];
+  if (clip < 0 || (uint32_t)clip >= tr->n_clips) return -1;
+  tr->clips[clip]->gain = gain;
+  return 0;
+}
+
+/* Engine::solo_track (engine.cpp:245-262) */
+void wbo_solo_track(wbo_session* s, int slot) {
+  int mute = 0;
+  if (s->tracks[slot]->ui_solo) {
+    s->tracks[slot]->ui_solo = 0;
+  } else {
+    s->tracks[slot]->ui_solo = 1;
+    wbo_set_mute(s, slot, 0);
+    mute = 1;
+  }
+  for (uint32_t i = 0; i < s->n_tracks; i++) {
+    if ((int)i == slot) continue;
+    if (s->tracks[i]->ui_solo) s->tracks[i]->ui_solo = 0;
+    wbo_set_mute(s, (int)i, mute);
+  }
+}
+
+/* Engine::move_track (engine.cpp:228-243) */
+void wbo_move_track(wbo_session* s, int from_slot, int to_slot) {
+  if (from_slot == to_slot) return;
+  o_track* tmp = s->tracks[from_slot];
+  if (from_slot < to_slot)
+    for (int i = from_slot; i < to_slot; i++) s->tracks[i] = s->tracks[i + 1];
+  else
+    for (int i = from_slot; i > to_slot; i--) s->tracks[i] = s->tracks[i - 1];
+  s->tracks[to_slot] = tmp;
+}
+
+/* Engine::delete_track (engine.cpp:209-217) */
+void wbo_delete_track(wbo_session* s, int slot) {
+  o_track* tr = s->tracks[slot];
+  for (uint32_t i = (uint32_t)slot; i + 1 < s->n_tracks; i++) s->tracks[i] = s->tracks[i + 1];
+  s->n_tracks--;
+  track_free(tr);
+}
 
 int wbo_clip_count(wbo_session* s, int track) { return (int)s->tracks[track]->n_clips; }
 

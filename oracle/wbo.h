@@ -58,6 +58,14 @@ int wbo_resize_clip(wbo_session*, int track, int clip, double relative_pos, doub
 int wbo_delete_clip(wbo_session*, int track, int clip);
 int wbo_duplicate_clip(wbo_session*, int track, int clip, double min_beat, double max_beat);
 
+/* Mixer-side calls that change what the path sums: Engine::set_clip_gain (engine.cpp:1460-1464: the playing voice reads
+ * the clip gain every callback, track.cpp:676,716), solo_track (:245-262, through set_mute), move_track (:228-243: the bus
+ * summation order), delete_track (:209-217). */
+int wbo_set_clip_gain(wbo_session*, int track, int clip, float gain);
+void wbo_solo_track(wbo_session*, int track);
+void wbo_move_track(wbo_session*, int from_slot, int to_slot);
+void wbo_delete_track(wbo_session*, int track);
+
 /* As wbo_add_clip, also setting AudioClip::fade_start / fade_end (beats, engine/clip.h:41-42).
  * EXTENSION — PARITY UNPINNED w.r.t. whitebox: the reference stores these fields but no audio code reads them,
  * so libwbref.so renders such a clip WITHOUT a fade; the port implements the builder's specification

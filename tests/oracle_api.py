@@ -38,6 +38,12 @@ def _load(path):
     lib.wbo_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
     lib.wbo_set_bpm.argtypes = [vp, dbl]
     lib.wbo_set_bpm.restype = None
+    lib.wbo_set_clip_gain.argtypes = [vp, i32, i32, flt]
+    for f in ("wbo_solo_track", "wbo_delete_track"):
+        getattr(lib, f).argtypes = [vp, i32]
+        getattr(lib, f).restype = None
+    lib.wbo_move_track.argtypes = [vp, i32, i32]
+    lib.wbo_move_track.restype = None
     lib.wbo_clip_count.argtypes = [vp, i32]
     lib.wbo_clip_range.argtypes = [vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
     lib.wbo_move_clip.argtypes = [vp, i32, i32, dbl]
@@ -131,6 +137,19 @@ class Session:
 
     def set_bpm(self, bpm):
         self.lib.wbo_set_bpm(self.h, bpm)
+
+    def set_clip_gain(self, track, clip, gain):
+        return self.lib.wbo_set_clip_gain(self.h, track, clip, gain)
+
+    def solo_track(self, track):
+        self.lib.wbo_solo_track(self.h, track)
+
+    def move_track(self, a, b):
+        self.lib.wbo_move_track(self.h, a, b)
+
+    def delete_track(self, track):
+        self.lib.wbo_delete_track(self.h, track)
+        self.n_tracks -= 1
 
     def clip_count(self, track):
         return self.lib.wbo_clip_count(self.h, track)

@@ -301,6 +301,36 @@ def tempo(make_engine):
     return _collect(eng, outs, 4)
 
 
+def mixer(make_engine):
+    """Mixer-side calls between callbacks: Engine::set_clip_gain on a clip that is playing (the voice reads the clip gain
+    every callback, track.cpp:676,716), solo_track on / other / off (through set_mute + the parameter queue), move_track
+    (tracks.cpp order = bus summation order, engine.cpp:1600-1617) and delete_track before playback."""
+    rng = np.random.RandomState(8642)
+    B, rate = 128, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    spb = rate * 0.5
+    for t in range(6):
+        eng.add_track(-3.0 - 1.5 * t, -0.8 + 0.3 * t, False)
+        sid = eng.add_sample(_src(rng, 2, 6000, 3), 48000, FMT_F32)
+        eng.add_clip(t, sid, (40.0 * t) / spb, 1800.0 / spb, 3.0 * t, 1.0, 0.5 + 0.1 * t)
+    eng.delete_track(4)  # tracks 0,1,2,3,5 remain (5 becomes slot 4)
+    eng.play()
+    outs = [eng.process(2)]
+    eng.set_clip_gain(1, 0, 1.7)
+    outs.append(eng.process(2))
+    eng.solo_track(2)
+    outs.append(eng.process(2))
+    eng.solo_track(0)  # solo moves to another track
+    outs.append(eng.process(2))
+    eng.solo_track(0)  # solo off: everything unmuted
+    eng.move_track(0, 3)  # summation order changes: the bus differs in the last bits, the per-slot peaks move
+    outs.append(eng.process(3))
+    eng.move_track(4, 1)
+    eng.set_clip_gain(2, 0, 0.05)
+    outs.append(eng.process(2))
+    return _collect(eng, outs, 5)
+
+
 def params(make_engine):
     """Volume / pan / mute changes between callbacks, not-playing callbacks, stop/play (track.cpp:618-643)."""
     rng = np.random.RandomState(99)
@@ -637,4 +667,4 @@ def mip_source(fmt, frames, ch):
 EXT = dict(fades=fades, effects=effects, reverb=reverb, polyphase=polyphase)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
-           event_split=event_split, overlaps=overlaps, edits=edits, tempo=tempo, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)
+           event_split=event_split, overlaps=overlaps, edits=edits, tempo=tempo, mixer=mixer, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)

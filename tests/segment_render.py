@@ -115,6 +115,10 @@ class ScheduleOnlyEngine:
         self.samples[sid] = (np.array(data), fmt)
         return sid
 
+    def delete_track(self, t):
+        self.n_tracks -= 1
+        return self.eng.delete_track(t)
+
     def __getattr__(self, name):
         return getattr(self.eng, name)
 

@@ -69,7 +69,8 @@ WBXH_SYMBOLS = [
     "wbxh_play", "wbxh_set_effects", "wbxh_set_impulse_response", "wbxh_set_resampler",
     "wbxh_stop", "wbxh_set_fast_forward", "wbxh_render", "wbxh_schedule", "wbxh_sampler_offset",
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
-    "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_clip_range", "wbxh_set_bpm", "wbxh_move_clip",
+    "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_clip_range", "wbxh_set_bpm", "wbxh_delete_track", "wbxh_move_track", "wbxh_solo_track",
+    "wbxh_set_clip_gain", "wbxh_move_clip",
     "wbxh_resize_clip", "wbxh_delete_clip", "wbxh_duplicate_clip",
 ]
 
@@ -151,6 +152,10 @@ def lib():
     L.wbxh_add_sample.argtypes = [vp, i32, u32, u64, u32, pp]
     L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     L.wbxh_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
+    L.wbxh_delete_track.argtypes = [vp, i32]
+    L.wbxh_move_track.argtypes = [vp, i32, i32]
+    L.wbxh_solo_track.argtypes = [vp, i32]
+    L.wbxh_set_clip_gain.argtypes = [vp, i32, i32, flt]
     L.wbxh_clip_count.argtypes = [vp, i32]
     L.wbxh_clip_range.argtypes = [vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.wbxh_move_clip.argtypes = [vp, i32, i32, dbl]
@@ -482,6 +487,19 @@ class Engine:
 
     # clip editing (clip = index in the track's clip list ordered by min_beat): Engine::move_clip / resize_clip /
     # delete_clip / duplicate_clip of the reference
+    def delete_track(self, track):
+        self._ck(self.L.wbxh_delete_track(self.h, track))
+        self.n_tracks -= 1
+
+    def move_track(self, from_slot, to_slot):
+        self._ck(self.L.wbxh_move_track(self.h, from_slot, to_slot))
+
+    def solo_track(self, track):
+        self._ck(self.L.wbxh_solo_track(self.h, track))
+
+    def set_clip_gain(self, track, clip, gain):
+        self._ck(self.L.wbxh_set_clip_gain(self.h, track, clip, gain))
+
     def clip_count(self, track):
         return self._ck(self.L.wbxh_clip_count(self.h, track))
 

@@ -147,6 +147,54 @@ Track* Engine::add_track(const std::string& name) {
   return t;
 }
 
+// Engine::delete_track (engine/engine.cpp:209-217)
+int Engine::delete_track(uint32_t slot) {
+  if (slot >= tracks.size()) return WBX_ERR_INVALID;
+  Track* t = tracks[slot];
+  tracks.erase(tracks.begin() + slot);
+  delete t;
+  return WBX_OK;
+}
+
+// Engine::move_track (engine/engine.cpp:228-243): the track order is the bus summation order
+int Engine::move_track(uint32_t from_slot, uint32_t to_slot) {
+  if (from_slot >= tracks.size() || to_slot >= tracks.size()) return WBX_ERR_INVALID;
+  if (from_slot == to_slot) return WBX_OK;
+  Track* tmp = tracks[from_slot];
+  if (from_slot < to_slot)
+    for (uint32_t i = from_slot; i < to_slot; i++) tracks[i] = tracks[i + 1];
+  else
+    for (uint32_t i = from_slot; i > to_slot; i--) tracks[i] = tracks[i - 1];
+  tracks[to_slot] = tmp;
+  return WBX_OK;
+}
+
+// Engine::solo_track (engine/engine.cpp:245-262): toggles the slot's solo flag and mutes / unmutes every other track
+int Engine::solo_track(uint32_t slot) {
+  if (slot >= tracks.size()) return WBX_ERR_INVALID;
+  bool mute = false;
+  if (tracks[slot]->ui_parameter_state.solo) {
+    tracks[slot]->ui_parameter_state.solo = false;
+  } else {
+    tracks[slot]->ui_parameter_state.solo = true;
+    tracks[slot]->set_mute(false);
+    mute = true;
+  }
+  for (uint32_t i = 0; i < tracks.size(); i++) {
+    if (i == slot) continue;
+    if (tracks[i]->ui_parameter_state.solo) tracks[i]->ui_parameter_state.solo = false;
+    tracks[i]->set_mute(mute);
+  }
+  return WBX_OK;
+}
+
+// Engine::set_clip_gain (engine/engine.cpp:1460-1464)
+int Engine::set_clip_gain(Track* track, uint32_t clip_id, float gain) {
+  if (!track || clip_id >= track->clips.size()) return WBX_ERR_INVALID;
+  track->clips[clip_id]->gain = gain;
+  return WBX_OK;
+}
+
 int Engine::add_sample(int format, uint32_t channels, uint64_t frames, uint32_t sample_rate, const void* const* planar) {
   if (!dev_ && !host_only_) return WBX_ERR_NO_DEVICE;
   uint32_t id = (uint32_t)samples_.size();
@@ -919,6 +967,15 @@ static wbx::AudioClip* clip_at(wbxh_engine* h, int track, int clip) {
   if (track < 0 || (size_t)track >= h->eng.tracks.size()) return nullptr;
   auto& clips = h->eng.tracks[track]->clips;
   return (clip < 0 || (size_t)clip >= clips.size()) ? nullptr : clips[clip];
+}
+int wbxh_delete_track(wbxh_engine* h, int track) { return track < 0 ? WBX_ERR_INVALID : h->eng.delete_track((uint32_t)track); }
+int wbxh_move_track(wbxh_engine* h, int from_slot, int to_slot) {
+  return (from_slot < 0 || to_slot < 0) ? WBX_ERR_INVALID : h->eng.move_track((uint32_t)from_slot, (uint32_t)to_slot);
+}
+int wbxh_solo_track(wbxh_engine* h, int track) { return track < 0 ? WBX_ERR_INVALID : h->eng.solo_track((uint32_t)track); }
+int wbxh_set_clip_gain(wbxh_engine* h, int track, int clip, float gain) {
+  if (track < 0 || (size_t)track >= h->eng.tracks.size() || clip < 0) return WBX_ERR_INVALID;
+  return h->eng.set_clip_gain(h->eng.tracks[track], (uint32_t)clip, gain);
 }
 int wbxh_clip_count(wbxh_engine* h, int track) {
   return (track < 0 || (size_t)track >= h->eng.tracks.size()) ? WBX_ERR_INVALID : (int)h->eng.tracks[track]->clips.size();

@@ -86,6 +86,7 @@ class ShardedEngine:
         for e in self.shards:
             e.dev.shard_connect_local(devs)
         self.tracks = []      # global track index -> (shard, local index)
+        self.solo = []        # Engine::solo_track's UI flag per global track
         self.samples = []     # global sample id -> (data, rate, fmt, {shard: local id})
 
     def close(self):
@@ -95,6 +96,7 @@ class ShardedEngine:
     def add_track(self, volume_db=0.0, pan=0.0, mute=False):
         s = len(self.tracks) % self.W
         self.tracks.append((s, self.shards[s].add_track(volume_db, pan, mute)))
+        self.solo.append(False)
         return len(self.tracks) - 1
 
     def add_sample(self, data, rate, fmt=None):
@@ -133,6 +135,38 @@ class ShardedEngine:
     def set_effects(self, t, params):
         e, i = self._track(t)
         e.set_effects(i, params)
+
+    def set_clip_gain(self, t, clip, gain):
+        e, i = self._track(t)
+        e.set_clip_gain(i, clip, gain)
+
+    def delete_track(self, t):
+        """Engine::delete_track: the track leaves its shard; later tracks of that shard move down one local slot."""
+        s, i = self.tracks.pop(t)
+        self.shards[s].delete_track(i)
+        self.tracks = [(ss, ii - 1 if (ss == s and ii > i) else ii) for ss, ii in self.tracks]
+        self.solo.pop(t)
+
+    def move_track(self, from_slot, to_slot):
+        """Engine::move_track: session order only (which slot a track's peaks are reported in); the bus of a sharded
+        session is summed shard by shard either way."""
+        self.tracks.insert(to_slot, self.tracks.pop(from_slot))
+        self.solo.insert(to_slot, self.solo.pop(from_slot))
+
+    def solo_track(self, slot):
+        """Engine::solo_track (engine/engine.cpp:245-262) across shards."""
+        mute = False
+        if self.solo[slot]:
+            self.solo[slot] = False
+        else:
+            self.solo[slot] = True
+            self.set_mute(slot, False)
+            mute = True
+        for i in range(len(self.tracks)):
+            if i == slot:
+                continue
+            self.solo[i] = False
+            self.set_mute(i, mute)
 
     def clip_count(self, t):
         e, i = self._track(t)
