@@ -177,6 +177,7 @@ class Engine {
   void track_block(Track& t, uint32_t track_index, uint32_t block, double sample_rate, double beat_duration,
                    double start_time, double end_time, double block_sample_position, bool currently_playing);
   int prepare(uint32_t n_blocks, double sample_rate);
+  void reindex_effects();
   void merge_levels();
   uint32_t quiet_blocks(const Track& t, uint32_t k, uint32_t K) const;
   void fill_fade(wbx_segment& s, const AudioClip* clip, uint64_t clip_frame) const;

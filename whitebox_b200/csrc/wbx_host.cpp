@@ -153,7 +153,14 @@ int Engine::delete_track(uint32_t slot) {
   Track* t = tracks[slot];
   tracks.erase(tracks.begin() + slot);
   delete t;
+  reindex_effects();
   return WBX_OK;
+}
+
+// The device addresses effect chains (extension) by track index: after the track list was reordered every chain is handed
+// over again at the next render (its filter state restarts), and slots that now hold a chain-less track are cleared.
+void Engine::reindex_effects() {
+  for (Track* tr : tracks) tr->effects_dirty = true;
 }
 
 // Engine::move_track (engine/engine.cpp:228-243): the track order is the bus summation order
@@ -166,6 +173,7 @@ int Engine::move_track(uint32_t from_slot, uint32_t to_slot) {
   else
     for (uint32_t i = from_slot; i > to_slot; i--) tracks[i] = tracks[i - 1];
   tracks[to_slot] = tmp;
+  reindex_effects();
   return WBX_OK;
 }
 
