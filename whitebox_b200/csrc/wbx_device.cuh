@@ -40,9 +40,10 @@ constexpr uint32_t kSilent = 0xFFFFFFFFu;
 WBX_HD inline uint32_t advance_rounded_impl(double* off_io, double adv, uint32_t n, double limit) {
   double x = *off_io;
   uint32_t steps = 0;
+  double no_jump_below = 0.0;  // end of the binade in which a jump was last refused: real steps until then
   while (steps < n && x < limit) {
     bool jumped = false;
-    if (n - steps > 4 && x > 0.0 && adv > 0.0) {
+    if (n - steps > 4 && x >= no_jump_below && x > 0.0 && adv > 0.0) {
       uint64_t xb;
       memcpy(&xb, &x, 8);
       const uint64_t ex = (xb >> 52) & 0x7FFu;  // biased exponent: x in [2^(ex-1023), 2^(ex-1022))
@@ -59,8 +60,10 @@ WBX_HD inline uint32_t advance_rounded_impl(double* off_io, double adv, uint32_t
           if (frac != 0.5) {
             const uint64_t A = frac > 0.5 ? fl + 1 : fl;  // adv/u rounded to nearest
             const double au = (double)A * u;              // exact
-            // every closed-form step must keep the exact sum x_k + adv below the binade end and x_k below limit
-            const double room = (hi < limit ? hi : limit) - x - 2.0 * adv - au;
+            // every closed-form step must keep the exact sum x_k + adv below the binade end and x_k below limit:
+            // x + (m-1)*au + adv < end  <=  m <= (end - x - adv - au) / au (one step size of slack: au >= 16 ulps,
+            // the rounding slop of this expression and of the division below is under 2)
+            const double room = (hi < limit ? hi : limit) - x - adv - au;
             if (room > 0.0) {
               double m = room / au;
               const double left = (double)(n - steps);
@@ -75,6 +78,7 @@ WBX_HD inline uint32_t advance_rounded_impl(double* off_io, double adv, uint32_t
             }
           }
         }
+        no_jump_below = hi;  // refused, or taken as far as this binade allows: real steps up to the binade's end
       }
     }
     if (!jumped) {
