@@ -130,6 +130,7 @@ class Engine {
                   bool shift = false, bool stretch = false);
   int delete_clip(Track* track, AudioClip* clip);
   int duplicate_clip(Track* track, const AudioClip* clip_to_duplicate, double min_time, double max_time);
+  int delete_region(Track* track, double min, double max);  // engine.cpp:463-473: erase a time range of the track
   // convolution reverb (extension, see wbx.h): one impulse response per engine, used by chains with reverb_on
   int set_impulse_response(const float* h, uint32_t n_taps);
   void play();  // engine/engine.cpp:68-80

@@ -52,6 +52,7 @@ int wbxh_resize_clip(wbxh_engine* h, int track, int clip, double relative_pos, d
                      int left_side, int shift, int stretch);
 int wbxh_delete_clip(wbxh_engine* h, int track, int clip);
 int wbxh_duplicate_clip(wbxh_engine* h, int track, int clip, double min_beat, double max_beat);
+int wbxh_delete_region(wbxh_engine* h, int track, double min_beat, double max_beat); /* Engine::delete_region (:463) */
 /* attach (params != NULL) or remove the built-in EQ + compressor chain of a track (extension, see wbx.h) */
 int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params);
 int wbxh_set_impulse_response(wbxh_engine* h, const float* ir, uint32_t n_taps); /* convolution reverb IR (wbx.h) */

@@ -153,6 +153,15 @@ int wbo_duplicate_clip(wbo_session* s, int track, int clip, double min_beat, dou
   return 0;
 }
 
+int wbo_delete_region(wbo_session* s, int track, double min_beat, double max_beat) {
+  // Engine::delete_region trims through the GLOBAL g_engine (engine.cpp:467-470); in the application that is the only
+  // engine. Mirror this session's tempo and playhead there so the call sees what the application's engine would hold.
+  g_engine.beat_duration.store(s->engine.beat_duration.load(std::memory_order_relaxed), std::memory_order_relaxed);
+  g_engine.playhead = s->engine.playhead;
+  s->engine.delete_region(s->engine.tracks[track], min_beat, max_beat);
+  return 0;
+}
+
 int wbo_set_clip_gain(wbo_session* s, int track, int clip, float gain) {
   if (!clip_at(s, track, clip)) return -1;
   s->engine.set_clip_gain(s->engine.tracks[track], (uint32_t)clip, gain);

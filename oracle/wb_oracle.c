@@ -639,6 +639,17 @@ int wbo_delete_clip(wbo_session* s, int track, int clip) {
   return 0;
 }
 
+/* Engine::delete_region(track, min, max) (engine.cpp:463-473) */
+int wbo_delete_region(wbo_session* s, int track, double min_beat, double max_beat) {
+  o_track* tr = s->tracks[track];
+  uint32_t first = 0, last = 0;
+  if (!query_clip_by_range(tr, min_beat, max_beat, &first, &last)) return 0;
+  reserve_track_region(s, tr, first, last, min_beat, max_beat, NULL);
+  update_clip_ordering(tr);
+  reset_playback_state(tr, s->playhead, 1);
+  return 0;
+}
+
 /* Engine::duplicate_clip (engine.cpp:336-344) */
 int wbo_duplicate_clip(wbo_session* s, int track, int clip, double min_beat, double max_beat) {
   o_track* tr = s->tracks[track];

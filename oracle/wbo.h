@@ -57,6 +57,8 @@ int wbo_resize_clip(wbo_session*, int track, int clip, double relative_pos, doub
                     int left_side, int shift, int stretch);
 int wbo_delete_clip(wbo_session*, int track, int clip);
 int wbo_duplicate_clip(wbo_session*, int track, int clip, double min_beat, double max_beat);
+/* Engine::delete_region(track, min, max) (engine.cpp:463-473): erase a time range — clips inside it are trimmed / split / deleted */
+int wbo_delete_region(wbo_session*, int track, double min_beat, double max_beat);
 
 /* Mixer-side calls that change what the path sums: Engine::set_clip_gain (engine.cpp:1460-1464: the playing voice reads
  * the clip gain every callback, track.cpp:676,716), solo_track (:245-262, through set_mute), move_track (:228-243: the bus

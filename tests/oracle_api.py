@@ -50,6 +50,7 @@ def _load(path):
     lib.wbo_resize_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, i32, i32, i32]
     lib.wbo_delete_clip.argtypes = [vp, i32, i32]
     lib.wbo_duplicate_clip.argtypes = [vp, i32, i32, dbl, dbl]
+    lib.wbo_delete_region.argtypes = [vp, i32, dbl, dbl]
     lib.wbo_set_effects.argtypes = [vp, i32, vp]
     lib.wbo_set_resampler.argtypes = [vp, i32]
     lib.wbo_set_impulse_response.argtypes = [vp, vp, u32]
@@ -171,6 +172,9 @@ class Session:
 
     def duplicate_clip(self, track, clip, min_beat, max_beat):
         return self.lib.wbo_duplicate_clip(self.h, track, clip, min_beat, max_beat)
+
+    def delete_region(self, track, min_beat, max_beat):
+        return self.lib.wbo_delete_region(self.h, track, min_beat, max_beat)
 
     def set_effects(self, track, params):
         """params: a ctypes struct laid out like wbo_effects (whitebox_b200.EffectParams) or None."""

@@ -331,6 +331,39 @@ def mixer(make_engine):
     return _collect(eng, outs, 5)
 
 
+def erase(make_engine):
+    """Engine::delete_region (engine.cpp:463-473): a time range erased from a track — inside one clip (split), across a
+    clip's tail and the next clip's head, over whole clips, over nothing, and under the clip that is playing (its tail
+    goes; the voice stops at the new end)."""
+    rng = np.random.RandomState(1122)
+    B, rate = 128, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    spb = rate * 0.5
+    for t in range(5):
+        eng.add_track(-3.0 - t, -0.7 + 0.35 * t, False)
+
+    def smp(frames, r=48000):
+        return eng.add_sample(_src(rng, 2, frames, 5), r, FMT_F32)
+
+    eng.add_clip(0, smp(8000), 0.0, 1500.0 / spb, 0.0, 1.0, 0.8)
+    eng.delete_region(0, 400.0 / spb, 650.0 / spb)                      # split
+    eng.add_clip(1, smp(4000), 0.0, 500.0 / spb, 0.0, 1.0, 0.7)
+    eng.add_clip(1, smp(4000, 44100), 600.0 / spb, 1400.0 / spb, 9.0, 1.25, 0.9)
+    eng.delete_region(1, 350.0 / spb, 820.0 / spb)                      # tail of one, head of the next (resampled: shifted)
+    for i in range(4):
+        eng.add_clip(2, smp(3000), (i * 350.0) / spb, (i * 350.0 + 300.0) / spb, 0.0, 1.0, 0.6)
+    eng.delete_region(2, 340.0 / spb, 1060.0 / spb)                     # two whole clips
+    eng.add_clip(3, smp(3000), 200.0 / spb, 600.0 / spb, 0.0, 1.0, 0.5)
+    eng.delete_region(3, 700.0 / spb, 900.0 / spb)                      # nothing there
+    eng.delete_region(3, 0.0, 100.0 / spb)                              # nothing there either
+    eng.add_clip(4, smp(8000), 0.0, 1500.0 / spb, 0.0, 1.0, 0.8)
+    eng.play()
+    outs = [eng.process(4)]
+    eng.delete_region(4, 800.0 / spb, 2000.0 / spb)                     # the tail of the clip that is playing
+    outs.append(eng.process(8))
+    return _collect(eng, outs, 5)
+
+
 def params(make_engine):
     """Volume / pan / mute changes between callbacks, not-playing callbacks, stop/play (track.cpp:618-643)."""
     rng = np.random.RandomState(99)
@@ -667,4 +700,4 @@ def mip_source(fmt, frames, ch):
 EXT = dict(fades=fades, effects=effects, reverb=reverb, polyphase=polyphase)  # builder-specified extensions: checked against the C port only
 
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
-           event_split=event_split, overlaps=overlaps, edits=edits, tempo=tempo, mixer=mixer, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)
+           event_split=event_split, overlaps=overlaps, edits=edits, tempo=tempo, mixer=mixer, erase=erase, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)

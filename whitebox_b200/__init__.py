@@ -71,7 +71,7 @@ WBXH_SYMBOLS = [
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
     "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_clip_range", "wbxh_set_bpm", "wbxh_delete_track", "wbxh_move_track", "wbxh_solo_track",
     "wbxh_set_clip_gain", "wbxh_move_clip",
-    "wbxh_resize_clip", "wbxh_delete_clip", "wbxh_duplicate_clip",
+    "wbxh_resize_clip", "wbxh_delete_clip", "wbxh_duplicate_clip", "wbxh_delete_region",
 ]
 
 _lib = None
@@ -162,6 +162,7 @@ def lib():
     L.wbxh_resize_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, i32, i32, i32]
     L.wbxh_delete_clip.argtypes = [vp, i32, i32]
     L.wbxh_duplicate_clip.argtypes = [vp, i32, i32, dbl, dbl]
+    L.wbxh_delete_region.argtypes = [vp, i32, dbl, dbl]
     L.wbxh_set_effects.argtypes = [vp, i32, vp]
     L.wbxh_set_resampler.argtypes = [vp, i32]
     L.wbxh_set_resampler.restype = None
@@ -520,6 +521,9 @@ class Engine:
 
     def duplicate_clip(self, track, clip, min_beat, max_beat):
         return self._ck(self.L.wbxh_duplicate_clip(self.h, track, clip, min_beat, max_beat))
+
+    def delete_region(self, track, min_beat, max_beat):
+        return self._ck(self.L.wbxh_delete_region(self.h, track, min_beat, max_beat))
 
     def set_effects(self, track, params):
         """params: EffectParams (see effect_params()) or None to remove the chain."""

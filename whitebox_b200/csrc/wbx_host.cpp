@@ -468,6 +468,18 @@ int Engine::resize_clip(Track* track, AudioClip* clip, double relative_pos, doub
   return WBX_OK;
 }
 
+// Engine::delete_region(track, min, max) (engine/engine.cpp:463-473): erase a time range — the clips it touches are
+// trimmed, split or deleted.
+int Engine::delete_region(Track* track, double min, double max) {
+  if (!track || !(max >= min)) return WBX_ERR_INVALID;
+  uint32_t first = 0, last = 0;
+  if (!query_clip_by_range(*track, min, max, &first, &last)) return WBX_OK;
+  reserve_track_region(*track, first, last, min, max, nullptr);
+  update_clip_ordering(*track);
+  reset_playback_state(*track, playhead, true);
+  return WBX_OK;
+}
+
 // Engine::delete_clip (engine/engine.cpp:400-407). The clip is parked in the track's graveyard (see update_clip_ordering).
 int Engine::delete_clip(Track* track, AudioClip* clip) {
   if (!owns_clip(track, clip)) return WBX_ERR_INVALID;
@@ -1013,6 +1025,11 @@ int wbxh_delete_clip(wbxh_engine* h, int track, int clip) {
 int wbxh_duplicate_clip(wbxh_engine* h, int track, int clip, double min_beat, double max_beat) {
   wbx::AudioClip* c = clip_at(h, track, clip);
   return c ? h->eng.duplicate_clip(h->eng.tracks[track], c, min_beat, max_beat) : WBX_ERR_INVALID;
+}
+
+int wbxh_delete_region(wbxh_engine* h, int track, double min_beat, double max_beat) {
+  if (track < 0 || (size_t)track >= h->eng.tracks.size()) return WBX_ERR_INVALID;
+  return h->eng.delete_region(h->eng.tracks[track], min_beat, max_beat);
 }
 
 int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params) {

@@ -192,6 +192,10 @@ class ShardedEngine:
         e, i = self._track(t)
         return e.duplicate_clip(i, clip, min_beat, max_beat)
 
+    def delete_region(self, t, min_beat, max_beat):
+        e, i = self._track(t)
+        return e.delete_region(i, min_beat, max_beat)
+
     def set_impulse_response(self, h):
         for e in self.shards:
             e.set_impulse_response(h)
