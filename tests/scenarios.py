@@ -664,9 +664,13 @@ def fuzz_edits(make_engine, seed):
             break
         t = int(rng.randint(0, n_tracks))
         nc = eng.clip_count(t)
-        op = int(rng.randint(0, 7))
+        op = int(rng.randint(0, 8))
         if op == 6:  # tempo change: later edits shift clip content with the new beat duration
             eng.set_bpm(float(rng.choice([90.0, 120.0, 133.3, 150.0])))
+            continue
+        if op == 7:  # erase a time range
+            a = float(rng.randint(0, total)) + frac()
+            eng.delete_region(t, a / spb, (a + float(rng.randint(8, total // 3 + 9))) / spb)
             continue
         if nc == 0 or op == 0:
             drop_clip(t)
