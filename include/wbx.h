@@ -252,6 +252,12 @@ int wbx_mix_sharded(wbx_engine* e);
  *   0  mix into the owners' exchange buffers + arrival signal      1  wait, reduce own slice + clamp into the master
  *   bus, signal      2  wait. wbx_mix_sharded(e) = phases 0, 1, 2 back to back (one process or thread per GPU). */
 int wbx_mix_sharded_phase(wbx_engine* e, int phase);
+/* Recovery. A phase that fails (a launch error, or a peer that never arrived: WBX_ERR_CUDA from the next synchronising
+ * call) ends the running collective on this rank — the engine accepts a new wbx_mix_sharded afterwards — but the ranks'
+ * barrier epochs may then disagree. To resume, EVERY rank calls wbx_shard_reset (drains its stream, clears its arrival
+ * words, restarts its epoch at 0), the caller makes sure all ranks have done so (any host-side barrier), and rendering
+ * continues with the connections and buffers as they were. */
+int wbx_shard_reset(wbx_engine* e);
 /* Optional: the host buffer the master bus is wanted in (channels[c] -> frames_per_channel f32, page-locked and mapped on
  * this engine's device: wbx_host_alloc memory within one process, or a shared-memory segment every process registered with
  * wbx_host_register). Set on EVERY rank, each with its own mapping of the SAME buffer: an owner then also stores its reduced

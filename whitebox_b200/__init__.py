@@ -60,7 +60,7 @@ WBX_SYMBOLS = [
     "wbx_mix", "wbx_fetch", "wbx_fetch_levels", "wbx_host_alloc", "wbx_host_free", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
     "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel", "wbx_effects_design", "wbx_set_track_effects",
     "wbx_set_impulse_response", "wbx_render_levels", "wbx_shard_init", "wbx_shard_connect_ipc",
-    "wbx_shard_connect_local", "wbx_mix_sharded", "wbx_mix_sharded_phase", "wbx_shard_set_host_output", "wbx_host_register",
+    "wbx_shard_connect_local", "wbx_mix_sharded", "wbx_mix_sharded_phase", "wbx_shard_reset", "wbx_shard_set_host_output", "wbx_host_register",
     "wbx_host_unregister", "wbx_shard_close", "wbx_shard_info",
 ]
 WBXH_SYMBOLS = [
@@ -113,6 +113,7 @@ def lib():
     L.wbx_mix_sharded.argtypes = [vp]
     L.wbx_mix_sharded_phase.argtypes = [vp, i32]
     L.wbx_shard_close.argtypes = [vp]
+    L.wbx_shard_reset.argtypes = [vp]
     L.wbx_shard_set_host_output.argtypes = [vp, pp, u64]
     L.wbx_host_register.argtypes = [vp, C.c_size_t]
     L.wbx_host_unregister.argtypes = [vp]
@@ -367,6 +368,10 @@ class DeviceEngine:
 
     def shard_close(self):
         self._ck(self.L.wbx_shard_close(self.h))
+
+    def shard_reset(self):
+        """Recovery after a failed sharded mix: call on EVERY rank, then barrier on the host, then render again."""
+        self._ck(self.L.wbx_shard_reset(self.h))
 
     def shard_info(self):
         r, w = C.c_uint32(), C.c_uint32()

@@ -535,6 +535,7 @@ int wbx_sample_release(wbx_engine* e, uint32_t id) {
   for (int q = 0; q < 2; q++)
     if (e->samples[id].d_mip[q]) CU(e, cudaFree(e->samples[id].d_mip[q]));
   e->samples[id] = SampleRec();
+  e->submitted = e->mixed = false;  // the submitted span table may hold this sample's device pointer
   return WBX_OK;
 }
 
@@ -1033,7 +1034,11 @@ int wbx_mix(wbx_engine* e, uint32_t flags) {
 
 int wbx_mix_sharded_phase(wbx_engine* e, int phase) {
   if (!e) return WBX_ERR_INVALID;
-  if (phase == 1 || phase == 2) return shard_phase(e, phase);
+  if (phase == 1 || phase == 2) {
+    const int rc = shard_phase(e, phase);
+    if (rc && rc != WBX_ERR_INVALID) e->shard_phase = 0;  // a failed launch ends this collective (see wbx_shard_reset)
+    return rc;
+  }
   if (phase != 0) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded_phase: phase %d", phase);
   if (!e->submitted) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded before wbx_submit");
   const Shard& sh = e->shard;
@@ -1042,7 +1047,9 @@ int wbx_mix_sharded_phase(wbx_engine* e, int phase) {
   if (e->n_blocks > sh.max_blocks)
     return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded: %u callbacks > max_blocks %u of wbx_shard_init", e->n_blocks, sh.max_blocks);
   if (e->shard_phase != 0) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded: the previous sharded mix stopped in phase %d", e->shard_phase);
-  return do_mix(e, 0, true);
+  const int rc = do_mix(e, 0, true);
+  if (rc) e->shard_phase = 0;
+  return rc;
 }
 
 int wbx_mix_sharded(wbx_engine* e) {
@@ -1050,6 +1057,22 @@ int wbx_mix_sharded(wbx_engine* e) {
   if (!rc) rc = wbx_mix_sharded_phase(e, 1);
   if (!rc) rc = wbx_mix_sharded_phase(e, 2);
   return rc;
+}
+
+int wbx_shard_reset(wbx_engine* e) {
+  if (!e) return WBX_ERR_INVALID;
+  Shard& sh = e->shard;
+  if (!sh.on) return fail(e, WBX_ERR_INVALID, "wbx_shard_reset before wbx_shard_init");
+  CU(e, cudaSetDevice(e->device));
+  cudaStreamSynchronize(e->stream);  // a failed launch may have left a sticky-free error behind: drain, then clear
+  cudaGetLastError();
+  CU(e, cudaMemset(sh.block, 0, kShardHeaderBytes));  // this rank's arrival words
+  sh.epoch = 0;
+  if (sh.status) *sh.status = 0;
+  e->shard_phase = 0;
+  e->shard_result = false;
+  e->mixed = false;
+  return WBX_OK;
 }
 
 // the bus the last mix produced: the engine's own, or — after a sharded mix — the master bus (rank 0 only)
@@ -1061,6 +1084,7 @@ static float* result_bus(wbx_engine* e) {
 static int check_shard_status(wbx_engine* e) {
   if (e->shard.on && e->shard.status && *e->shard.status) {
     *e->shard.status = 0;
+    e->shard_phase = 0;
     return fail(e, WBX_ERR_CUDA, "sharded render: a peer rank did not reach the bus exchange within %.1f s",
                 (double)e->shard.timeout_ns * 1e-9);
   }
@@ -1205,8 +1229,10 @@ int wbx_render_levels(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, c
   bool direct = out_channels != nullptr && !sharded;
   float* dview[2] = {nullptr, nullptr};
   for (uint32_t c = 0; direct && c < e->C; c++) {
-    direct = out_channels[c] && is_pinned(out_channels[c]) &&
-             cudaHostGetDevicePointer((void**)&dview[c], out_channels[c], 0) == cudaSuccess && dview[c];
+    // the kernel stores bus tiles as float2: a channel that is only 4-byte aligned takes the copy path instead
+    direct = out_channels[c] && ((uintptr_t)out_channels[c] & 7u) == 0 && is_pinned(out_channels[c]) &&
+             cudaHostGetDevicePointer((void**)&dview[c], out_channels[c], 0) == cudaSuccess && dview[c] &&
+             ((uintptr_t)dview[c] & 7u) == 0;
     if (!direct) cudaGetLastError();
   }
   for (uint32_t c = 0; c < 2; c++) {
