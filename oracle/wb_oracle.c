@@ -74,6 +74,11 @@ typedef struct {
   int reverb_on;
   float* hist[2]; /* last n_taps - 1 chain outputs per channel (ring), zero at attach time */
   uint64_t hist_pos;
+  /* time-parallel form (fx_design_tables): per biquad the state-space input vector, A^m (m = 0..16) and A^(16*2^j)
+   * (j = 0..4), row-major 2x2; envelope follower constants and look-ahead slopes */
+  float B1[4], B2[4], P[4][17][4], S[4][5][4];
+  float a1m, r1m, sl[14]; /* sl: S1[2] | S2[3] | S3[4] | S4[5] */
+  int sel;                /* att <= rel: the branch of the follower is the larger candidate, else the smaller */
 } o_fx;
 
 typedef struct {
@@ -120,6 +125,8 @@ struct wbo_session {
 
 const char* wbo_kind(void) { return "port"; }
 static void fx_free(o_fx* f);
+static void fx_design_tables(o_fx* f);
+static void fx64_forget(const o_fx* f);
 
 static uint64_t g_ub_count = 0;
 /* port only: how many times a scenario drove the reference algorithm into undefined behaviour */
@@ -1084,6 +1091,7 @@ int wbo_set_impulse_response(wbo_session* s, const float* h, uint32_t n_taps) {
 int wbo_set_effects(wbo_session* s, int track, const wbo_effects* fx) {
   o_fx* f = &s->tracks[track]->fx;
   fx_free(f);
+  fx64_forget(f);
   memset(f, 0, sizeof(*f));
   if (!fx) return 0;
   f->reverb_on = fx->reverb_on != 0;
@@ -1098,6 +1106,7 @@ int wbo_set_effects(wbo_session* s, int track, const wbo_effects* fx) {
   f->makeup = (float)pow(10.0, (double)fx->comp_makeup_db / 20.0);
   f->att = (float)exp(-1.0 / ((double)fx->comp_attack_ms * 0.001 * (double)s->rate));
   f->rel = (float)exp(-1.0 / ((double)fx->comp_release_ms * 0.001 * (double)s->rate));
+  fx_design_tables(f);
   return 0;
 }
 
@@ -1120,8 +1129,10 @@ static void apply_reverb(wbo_session* s, o_fx* f, int c, float* buf, uint32_t n,
   free(x);
 }
 
-/* One channel, one callback, in place. Every operation is a single IEEE-754 rn op (fmaf = fused). */
-static void apply_effects(o_fx* f, int c, float* buf, uint32_t n) {
+/* The chain in its textbook sample-by-sample form (transposed direct form II biquads, branching peak follower): what
+ * apply_effects computes up to rounding. Kept as the accuracy yardstick of the time-parallel specification below
+ * (tests/test_oracle.py holds the two within 1e-5 of the block peak) and selectable with wbo_set_fx_textbook(1). */
+static void apply_effects_textbook(o_fx* f, int c, float* buf, uint32_t n) {
   for (uint32_t j = 0; j < n; j++) {
     float x = buf[j];
     if (f->eq_on) {
@@ -1151,6 +1162,257 @@ static void apply_effects(o_fx* f, int c, float* buf, uint32_t n) {
       x = (x * g) * f->makeup;
     }
     buf[j] = x;
+  }
+}
+
+
+/* The same chain with f64 state and arithmetic (coefficients as designed, i.e. the f32 values): ground truth for the
+ * accuracy of both f32 evaluations. State lives in a side table keyed by the o_fx address (test use only). */
+typedef struct {
+  double s1[2][4], s2[2][4], env[2];
+} o_fx64;
+static struct {
+  const o_fx* key;
+  o_fx64 st;
+} g_fx64[64];
+static o_fx64* fx64_state(const o_fx* f) {
+  for (int i = 0; i < 64; i++)
+    if (g_fx64[i].key == f) return &g_fx64[i].st;
+  for (int i = 0; i < 64; i++)
+    if (!g_fx64[i].key) {
+      g_fx64[i].key = f;
+      memset(&g_fx64[i].st, 0, sizeof(o_fx64));
+      return &g_fx64[i].st;
+    }
+  return NULL;
+}
+static void fx64_forget(const o_fx* f) {
+  for (int i = 0; i < 64; i++)
+    if (g_fx64[i].key == f) g_fx64[i].key = NULL;
+}
+static void apply_effects_f64(o_fx* f, int c, float* buf, uint32_t n) {
+  o_fx64* st = fx64_state(f);
+  if (!st) return;
+  for (uint32_t j = 0; j < n; j++) {
+    double x = (double)buf[j];
+    if (f->eq_on) {
+      for (int b = 0; b < 4; b++) {
+        const double y = (double)f->b0[b] * x + st->s1[c][b];
+        st->s1[c][b] = (double)f->b1[b] * x - (double)f->a1[b] * y + st->s2[c][b];
+        st->s2[c][b] = (double)f->b2[b] * x - (double)f->a2[b] * y;
+        x = y;
+      }
+    }
+    if (f->comp_on) {
+      const double xa = fabs(x);
+      double env = st->env[c];
+      env = xa > env ? (double)f->att * (env - xa) + xa : (double)f->rel * (env - xa) + xa;
+      st->env[c] = env;
+      double g = 1.0;
+      if (env > (double)f->thr) {
+        const double q = (double)f->thr / env;
+        switch (f->ratio_code) {
+          case 1: g = pow(q, 0.5); break;
+          case 2: g = pow(q, 0.75); break;
+          case 3: g = pow(q, 0.875); break;
+          default: g = q; break;
+        }
+      }
+      x = (x * g) * (double)f->makeup;
+    }
+    buf[j] = (float)x;
+  }
+}
+
+static int g_fx_textbook = 0; /* 0: the specification; 1: textbook f32; 2: textbook f64 */
+void wbo_set_fx_textbook(int mode) { g_fx_textbook = mode; }
+
+/* ---- the chain's SPECIFICATION: the same filters evaluated in a time-parallel association -------------------
+ * A biquad and the follower are recurrences in time; evaluated sample by sample a GPU is bound by the latency of the
+ * dependent operations. The specification therefore fixes a blocked evaluation order that exposes the parallelism —
+ * the CUDA kernel (wbx_kernels.cu fx_chain_kernel) performs exactly these IEEE operations, so CUDA == this bit for bit:
+ *  - a callback is processed in chunks of up to 512 frames = 32 segments ("lanes") of 16 frames;
+ *  - biquad b in state-space form s' = A s + B x, y = s1 + b0 x with A = [[-a1, 1], [-a2, 0]], B = [b1 - a1 b0,
+ *    b2 - a2 b0]: every segment is run from a ZERO state (y_zs, end state e), the 32 end states are combined into the
+ *    true state at every segment boundary by a Kogge-Stone scan with the matrices A^(16 * 2^j), and every frame gets
+ *    the zero-input response of its segment's true start state added: y[m] = y_zs[m] + (A^m)[0][.] . s_start;
+ *  - the peak follower env' = (|x| > env ? att : rel) * (env - |x|) + |x| equals mm(att * env + (1 - att)|x|,
+ *    rel * env + (1 - rel)|x|) with mm = max when att <= rel (min otherwise); mm-of-affine maps compose, so four steps
+ *    are env4 = mm_i(S4[i] * env0 + Q4[i]), i = number of attack steps taken, S4[i] = att^i rel^(4-i), with the
+ *    intercepts Q built by a small dynamic program from the inputs alone: only ONE fused multiply-add + mm per block
+ *    of 4 frames is serial in time; the envelope inside a block is the 1-, 2-, 3-step look-ahead from the block start;
+ *  - the gain computer and make-up gain are memoryless and unchanged.
+ * All tables are designed in f64 from the f32 coefficients and rounded once. */
+#define FX_SEG 16u
+#define FX_LANES 32u
+#define FX_CHUNK (FX_SEG * FX_LANES)
+
+static void mat2_mul(const double a[4], const double b[4], double out[4]) {
+  const double o0 = a[0] * b[0] + a[1] * b[2], o1 = a[0] * b[1] + a[1] * b[3];
+  const double o2 = a[2] * b[0] + a[3] * b[2], o3 = a[2] * b[1] + a[3] * b[3];
+  out[0] = o0, out[1] = o1, out[2] = o2, out[3] = o3;
+}
+
+static void fx_design_tables(o_fx* f) {
+  for (int b = 0; b < 4; b++) {
+    const double a1 = (double)f->a1[b], a2 = (double)f->a2[b], b0 = (double)f->b0[b];
+    f->B1[b] = (float)((double)f->b1[b] - a1 * b0);
+    f->B2[b] = (float)((double)f->b2[b] - a2 * b0);
+    const double A[4] = {-a1, 1.0, -a2, 0.0};
+    double pw[4] = {1.0, 0.0, 0.0, 1.0};
+    for (int m = 0; m <= 16; m++) {
+      for (int q = 0; q < 4; q++) f->P[b][m][q] = (float)pw[q];
+      if (m < 16) mat2_mul(pw, A, pw);
+    }
+    double sq[4] = {pw[0], pw[1], pw[2], pw[3]}; /* A^16 */
+    for (int j = 0; j < 5; j++) {
+      for (int q = 0; q < 4; q++) f->S[b][j][q] = (float)sq[q];
+      mat2_mul(sq, sq, sq);
+    }
+  }
+  const float a = f->att, r = f->rel;
+  f->sel = a <= r;
+  f->a1m = 1.0f - a;
+  f->r1m = 1.0f - r;
+  const float r2 = r * r, a2 = a * a, r3 = r2 * r, a3 = a2 * a;
+  float* sl = f->sl;
+  sl[0] = r, sl[1] = a;
+  sl[2] = r2, sl[3] = a * r, sl[4] = a2;
+  sl[5] = r3, sl[6] = a * r2, sl[7] = a2 * r, sl[8] = a3;
+  sl[9] = r2 * r2, sl[10] = a * r3, sl[11] = a2 * r2, sl[12] = a3 * r, sl[13] = a2 * a2;
+}
+
+static float fx_mm(int sel, float x, float y) { return sel ? fmaxf(x, y) : fminf(x, y); }
+
+/* one biquad over one chunk of n <= 512 frames, in place */
+static void fx_eq_stage(o_fx* f, int c, int b, float* x, uint32_t n) {
+  const float b0 = f->b0[b], na1 = -f->a1[b], na2 = -f->a2[b], B1 = f->B1[b], B2 = f->B2[b];
+  float e1[FX_LANES], e2[FX_LANES], v1[FX_LANES], v2[FX_LANES], yz[FX_CHUNK];
+  for (uint32_t l = 0; l < FX_LANES; l++) { /* zero-state pass of every segment */
+    const uint32_t f0 = l * FX_SEG;
+    const uint32_t len = f0 >= n ? 0u : (n - f0 < FX_SEG ? n - f0 : FX_SEG);
+    float s1 = 0.0f, s2 = 0.0f;
+    for (uint32_t m = 0; m < len; m++) {
+      const float xi = x[f0 + m];
+      yz[f0 + m] = fmaf(b0, xi, s1);
+      const float t = fmaf(B1, xi, s2);
+      s2 = fmaf(na2, s1, B2 * xi);
+      s1 = fmaf(na1, s1, t);
+    }
+    e1[l] = s1, e2[l] = s2;
+  }
+  const float in1 = f->s1[c][b], in2 = f->s2[c][b];
+  memcpy(v1, e1, sizeof(v1));
+  memcpy(v2, e2, sizeof(v2));
+  { /* the incoming state enters through segment 0 */
+    const float* S = f->S[b][0];
+    v1[0] = fmaf(S[0], in1, fmaf(S[1], in2, e1[0]));
+    v2[0] = fmaf(S[2], in1, fmaf(S[3], in2, e2[0]));
+  }
+  for (int j = 0; j < 5; j++) { /* Kogge-Stone: v[l] += A^(16 d) v[l - d] */
+    const uint32_t d = 1u << j;
+    const float* S = f->S[b][j];
+    float n1[FX_LANES], n2[FX_LANES];
+    for (uint32_t l = 0; l < FX_LANES; l++) {
+      if (l >= d) {
+        n1[l] = fmaf(S[0], v1[l - d], fmaf(S[1], v2[l - d], v1[l]));
+        n2[l] = fmaf(S[2], v1[l - d], fmaf(S[3], v2[l - d], v2[l]));
+      } else {
+        n1[l] = v1[l], n2[l] = v2[l];
+      }
+    }
+    memcpy(v1, n1, sizeof(v1));
+    memcpy(v2, n2, sizeof(v2));
+  }
+  for (uint32_t l = 0; l < FX_LANES; l++) { /* zero-input response of the segment's true start state */
+    const uint32_t f0 = l * FX_SEG;
+    if (f0 >= n) break;
+    const uint32_t len = n - f0 < FX_SEG ? n - f0 : FX_SEG;
+    const float st1 = l ? v1[l - 1] : in1, st2 = l ? v2[l - 1] : in2;
+    for (uint32_t m = 0; m < len; m++) x[f0 + m] = fmaf(f->P[b][m][1], st2, fmaf(f->P[b][m][0], st1, yz[f0 + m]));
+    if (f0 + len == n) { /* state after the chunk's last frame */
+      f->s1[c][b] = fmaf(f->P[b][len][0], st1, fmaf(f->P[b][len][1], st2, e1[l]));
+      f->s2[c][b] = fmaf(f->P[b][len][2], st1, fmaf(f->P[b][len][3], st2, e2[l]));
+    }
+  }
+}
+
+/* compressor over one chunk, in place */
+static void fx_comp_stage(o_fx* f, int c, float* x, uint32_t n) {
+  const float a = f->att, r = f->rel, a1m = f->a1m, r1m = f->r1m;
+  const float* sl = f->sl;
+  const int sel = f->sel;
+  float env[FX_CHUNK];
+  float e = f->env[c];
+  const uint32_t nb = n / 4;
+  for (uint32_t k = 0; k < nb; k++) {
+    float pa[4], pr[4];
+    for (int m = 0; m < 4; m++) {
+      const float xa = fabsf(x[4 * k + m]);
+      pa[m] = a1m * xa;
+      pr[m] = r1m * xa;
+    }
+    /* intercepts: Q_m[i] = best intercept after m steps of which i took the attack branch */
+    float q1[2], q2[3], q3[4], q4[5];
+    q1[0] = pr[0], q1[1] = pa[0];
+    q2[0] = fmaf(r, q1[0], pr[1]);
+    q2[1] = fx_mm(sel, fmaf(r, q1[1], pr[1]), fmaf(a, q1[0], pa[1]));
+    q2[2] = fmaf(a, q1[1], pa[1]);
+    q3[0] = fmaf(r, q2[0], pr[2]);
+    for (int i = 1; i < 3; i++) q3[i] = fx_mm(sel, fmaf(r, q2[i], pr[2]), fmaf(a, q2[i - 1], pa[2]));
+    q3[3] = fmaf(a, q2[2], pa[2]);
+    q4[0] = fmaf(r, q3[0], pr[3]);
+    for (int i = 1; i < 4; i++) q4[i] = fx_mm(sel, fmaf(r, q3[i], pr[3]), fmaf(a, q3[i - 1], pa[3]));
+    q4[4] = fmaf(a, q3[3], pa[3]);
+    float t = fmaf(sl[0], e, q1[0]);
+    env[4 * k] = fx_mm(sel, t, fmaf(sl[1], e, q1[1]));
+    t = fmaf(sl[2], e, q2[0]);
+    for (int i = 1; i < 3; i++) t = fx_mm(sel, t, fmaf(sl[2 + i], e, q2[i]));
+    env[4 * k + 1] = t;
+    t = fmaf(sl[5], e, q3[0]);
+    for (int i = 1; i < 4; i++) t = fx_mm(sel, t, fmaf(sl[5 + i], e, q3[i]));
+    env[4 * k + 2] = t;
+    t = fmaf(sl[9], e, q4[0]);
+    for (int i = 1; i < 5; i++) t = fx_mm(sel, t, fmaf(sl[9 + i], e, q4[i]));
+    env[4 * k + 3] = t;
+    e = t; /* the only step that is serial in time */
+  }
+  for (uint32_t j = 4 * nb; j < n; j++) { /* a chunk's last 1..3 frames: one step at a time */
+    const float xa = fabsf(x[j]);
+    e = fx_mm(sel, fmaf(r, e, r1m * xa), fmaf(a, e, a1m * xa));
+    env[j] = e;
+  }
+  f->env[c] = e;
+  for (uint32_t j = 0; j < n; j++) {
+    float g = 1.0f;
+    if (env[j] > f->thr) {
+      const float q = f->thr / env[j]; /* (thr/env)^(1 - 1/ratio) with divide and square roots only */
+      const float q2 = sqrtf(q);
+      switch (f->ratio_code) {
+        case 1: g = q2; break;                                  /* 2:1 -> q^(1/2) */
+        case 2: g = q2 * sqrtf(q2); break;                      /* 4:1 -> q^(3/4) */
+        case 3: g = (q2 * sqrtf(q2)) * sqrtf(sqrtf(q2)); break; /* 8:1 -> q^(7/8) */
+        default: g = q; break;                                  /* limiter */
+      }
+    }
+    x[j] = (x[j] * g) * f->makeup;
+  }
+}
+
+/* One channel, one callback, in place. */
+static void apply_effects(o_fx* f, int c, float* buf, uint32_t n) {
+  if (g_fx_textbook) {
+    if (g_fx_textbook == 2)
+      apply_effects_f64(f, c, buf, n);
+    else
+      apply_effects_textbook(f, c, buf, n);
+    return;
+  }
+  for (uint32_t off = 0; off < n; off += FX_CHUNK) {
+    const uint32_t len = n - off < FX_CHUNK ? n - off : FX_CHUNK;
+    if (f->eq_on)
+      for (int b = 0; b < 4; b++) fx_eq_stage(f, c, b, buf + off, len);
+    if (f->comp_on) fx_comp_stage(f, c, buf + off, len);
   }
 }
 

@@ -484,6 +484,41 @@ def effects(make_engine, fxp):
     return _collect(eng, outs, n)
 
 
+def effects_shapes(make_engine, fxp, n_tracks=24, block=512, n_blocks=5, out_channels=2, loud=True, chunks=None):
+    """EXTENSION scenario (parity unpinned w.r.t. whitebox): the chain's time-parallel evaluation at arbitrary shapes —
+    block sizes that leave partial segments / partial look-ahead blocks / several 512-frame chunks per callback, mono
+    bus, attack slower than release (the follower then takes the SMALLER candidate), EQ-only and compressor-only chains,
+    every ratio code, silent gaps between clips, signals well above the threshold."""
+    rng = np.random.RandomState(4242 + n_tracks + block)
+    eng = make_engine(out_channels, block, 48000, 120.0)
+    frames = (n_blocks + 3) * block + 64
+    eq_a = ((120.0, 4.0, 0.7), (800.0, -6.0, 1.2), (2500.0, 3.0, 2.0), (8000.0, 5.0, 0.7))
+    eq_b = ((60.0, 6.0, 1.1), (300.0, -9.0, 3.0), (6000.0, 4.0, 0.5), (15000.0, -5.0, 0.9))
+    spb = 48000 * 0.5
+    for t in range(n_tracks):
+        eng.add_track(-3.0 - (t % 9), -0.9 + 0.17 * (t % 11), False)
+        scale = 1 if not loud else max(1, n_tracks // 8)
+        sid = eng.add_sample(_src(rng, 2, frames, scale), 48000)
+        start = (t % 5) * 7 / spb if t % 4 == 1 else 0.0  # some clips start mid-block
+        end = (n_blocks - 1) * block / spb if t % 6 == 2 else 1e6  # some end before the render does
+        eng.add_clip(t, sid, start, end, float(t % 3), 1.0, 0.9)
+        kind = t % 6
+        if kind == 0:
+            eng.set_effects(t, fxp(eq=eq_a, threshold_db=-30.0, ratio_code=2, attack_ms=2.0, release_ms=60.0, makeup_db=3.0))
+        elif kind == 1:
+            eng.set_effects(t, fxp(eq=eq_b))
+        elif kind == 2:
+            eng.set_effects(t, fxp(threshold_db=-40.0, ratio_code=4, attack_ms=0.1, release_ms=5.0))
+        elif kind == 3:
+            eng.set_effects(t, fxp(eq=eq_b, threshold_db=-36.0, ratio_code=1, attack_ms=30.0, release_ms=3.0, makeup_db=-2.0))
+        elif kind == 4:
+            eng.set_effects(t, fxp(eq=eq_a, threshold_db=-33.0, ratio_code=3, attack_ms=1.0, release_ms=200.0))
+        # kind 5: no chain
+    eng.play()
+    outs = [eng.process(n) for n in (chunks or [n_blocks])]
+    return _collect(eng, outs, n_tracks)
+
+
 def reverb(make_engine, fxp, taps=777):
     """EXTENSION scenario (parity unpinned w.r.t. whitebox): BASELINE cfg 5 shape at test size — tracks whose chain
     ends in a convolution with a shared impulse response, history carried across renders."""

@@ -124,6 +124,36 @@ def test_effects_extension_vs_port(wb, batched):
     assert_exact(sc.effects(gpu_engine(wb, batched), wb.effect_params), ref, "effects")
 
 
+@pytest.mark.parametrize("shape", [
+    dict(n_tracks=24, block=512, n_blocks=5),                  # whole chunks
+    dict(n_tracks=12, block=256, n_blocks=7, chunks=[3, 1, 3]),  # half chunks, state carried across renders
+    dict(n_tracks=12, block=100, n_blocks=9),                  # partial segment (100 = 6 * 16 + 4)
+    dict(n_tracks=12, block=101, n_blocks=6),                  # odd block: partial look-ahead block, unaligned stores
+    dict(n_tracks=8, block=1, n_blocks=40),                    # one frame per callback: the one-step form only
+    dict(n_tracks=8, block=3, n_blocks=21),
+    dict(n_tracks=8, block=513, n_blocks=4),                   # a second chunk of one frame
+    dict(n_tracks=8, block=1030, n_blocks=3),                  # three chunks per callback, the last one ragged
+    dict(n_tracks=12, block=512, n_blocks=4, out_channels=1),  # mono bus
+    dict(n_tracks=12, block=512, n_blocks=4, loud=False),      # far above the threshold
+])
+def test_effects_time_parallel_shapes_vs_port(wb, shape):
+    """EXTENSION, parity unpinned: fx_chain_kernel == the C specification of the time-parallel chain (oracle/wb_oracle.c
+    apply_effects) bit for bit at every chunk shape."""
+    ref = sc.effects_shapes(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params, **shape)
+    assert_exact(sc.effects_shapes(gpu_engine(wb, True), wb.effect_params, **shape), ref, "effects %r" % (shape,))
+
+
+@pytest.mark.parametrize("n_tracks", [512, 4096])
+def test_effects_bench_shape_vs_port(wb, n_tracks):
+    """BASELINE cfg 4 at bench shape (512 tracks per GPU; 4096 = the whole session on one GPU): every track with the 4-band
+    EQ + compressor, CUDA == the C spec bit for bit (bus and VU peaks), and a per-callback render equals the batched one."""
+    shape = dict(n_tracks=n_tracks, block=512, n_blocks=4 if n_tracks <= 512 else 2)
+    ref = sc.effects_shapes(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params, **shape)
+    assert_exact(sc.effects_shapes(gpu_engine(wb, True), wb.effect_params, **shape), ref, "effects bench shape %d" % n_tracks)
+    if n_tracks <= 512:
+        assert_exact(sc.effects_shapes(gpu_engine(wb, False), wb.effect_params, **shape), ref, "effects per callback")
+
+
 @pytest.mark.parametrize("mode", ["direct", "tc"])
 @pytest.mark.parametrize("taps", [1, 2, 777, 2048])
 def test_reverb_extension_vs_port(wb, taps, mode, monkeypatch):

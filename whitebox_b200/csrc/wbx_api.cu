@@ -31,7 +31,7 @@ cudaError_t launch_mip_merge(const void* child, uint64_t child_mdc, void* parent
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
                            float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, const float* poly,
-                           cudaStream_t stream);
+                           uint32_t fx_flags, uint32_t* sm_arrivals, uint64_t tbs, cudaStream_t stream);
 cudaError_t launch_shard_signal(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch, cudaStream_t stream);
 cudaError_t launch_shard_wait(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch,
                               unsigned long long timeout_ns, uint32_t* status, cudaStream_t stream);
@@ -103,6 +103,8 @@ struct wbx_engine {
   uint32_t C = 2, B = 512, rate = 48000, n_tracks = 0;
   int sum_mode = WBX_SUM_AUTO;
   std::vector<SampleRec> samples;
+  DevBuf d_smarr;  // per-SM arrival counters of fx_chain_kernel (role rotation)
+  uint32_t fx_flags = 0;  // bit 0: some chain has an EQ or a compressor, bit 1: some chain is reverb-only
   DevBuf d_spans, d_cells, d_bus, d_zero, d_ws, d_conv, d_upload, d_fx, d_trackbuf, d_ir, d_firhist, d_firin, d_irtiles, d_firplanes, d_poly;
   HostBuf h_spans, h_bus, h_peaks, h_conv, h_levels, h_fx;
   // views into d_spans (the submitted table: spans | gains | cells of a one-callback render) and d_zero (the region one
@@ -248,8 +250,10 @@ void choose_shape(const wbx_engine* e, uint32_t n_blocks, int* fpl_out, uint32_t
   if (env && (atoi(env) == 4 || atoi(env) == 8 || atoi(env) == 16)) {
     fpl = atoi(env);
   } else {
-    // prefer big tiles (4 KiB bulk copies); split tiles only while exact-order items cannot fill the machine
-    while (fpl > 4 && items_for(fpl) < warps_for(fpl)) fpl >>= 1;
+    // prefer big tiles (4 KiB bulk copies): bulk-copy issue is a per-SM resource, so halving the tile costs more than
+    // idle warp slots do (measured, 1024 callbacks: 512-frame tiles on 43 % of the warp slots 0.75 ms, 128-frame tiles on
+    // all of them 1.8 ms). Split tiles only while the items cannot give every SM four busy warps.
+    while (fpl > 4 && items_for(fpl) < sm * 4) fpl >>= 1;
   }
   uint32_t groups = 1;
   const long items = items_for(fpl), warps = warps_for(fpl);
@@ -338,7 +342,7 @@ int wbx_destroy(wbx_engine* e) {
       for (int q = 0; q < 2; q++)
         if (s.d_mip[q]) cudaFree(s.d_mip[q]);
     }
-  for (DevBuf* b : {&e->d_spans, &e->d_cells, &e->d_bus, &e->d_zero, &e->d_ws, &e->d_conv,
+  for (DevBuf* b : {&e->d_smarr, &e->d_spans, &e->d_cells, &e->d_bus, &e->d_zero, &e->d_ws, &e->d_conv,
                     &e->d_upload, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin, &e->d_irtiles, &e->d_firplanes, &e->d_poly})
     if (b->p) cudaFree(b->p);
   for (HostBuf* b : {&e->h_spans, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
@@ -638,6 +642,42 @@ int wbx_set_track_effects(wbx_engine* e, uint32_t track, const wbx_effects* fx) 
   return WBX_OK;
 }
 
+// Tables of the chain's time-parallel form — the same f64 design as oracle/wb_oracle.c fx_design_tables (this file is
+// built with -ffp-contract=off: every product and sum below is separately rounded, as there).
+static void mat2_mul(const double a[4], const double b[4], double out[4]) {
+  const double o0 = a[0] * b[0] + a[1] * b[2], o1 = a[0] * b[1] + a[1] * b[3];
+  const double o2 = a[2] * b[0] + a[3] * b[2], o3 = a[2] * b[1] + a[3] * b[3];
+  out[0] = o0, out[1] = o1, out[2] = o2, out[3] = o3;
+}
+static void design_fx_tables(DFx& d) {
+  for (int b = 0; b < 4; b++) {
+    const double a1 = (double)d.a1[b], a2 = (double)d.a2[b], b0 = (double)d.b0[b];
+    d.B1[b] = (float)((double)d.b1[b] - a1 * b0);
+    d.B2[b] = (float)((double)d.b2[b] - a2 * b0);
+    const double A[4] = {-a1, 1.0, -a2, 0.0};
+    double pw[4] = {1.0, 0.0, 0.0, 1.0};
+    for (int m = 0; m <= 16; m++) {
+      for (int q = 0; q < 4; q++) d.P[b][m][q] = (float)pw[q];
+      if (m < 16) mat2_mul(pw, A, pw);
+    }
+    double sq[4] = {pw[0], pw[1], pw[2], pw[3]};  // A^16
+    for (int j = 0; j < 5; j++) {
+      for (int q = 0; q < 4; q++) d.S[b][j][q] = (float)sq[q];
+      mat2_mul(sq, sq, sq);
+    }
+  }
+  const float a = d.att, r = d.rel;
+  d.sel = a <= r ? 1u : 0u;
+  d.a1m = 1.0f - a;
+  d.r1m = 1.0f - r;
+  const float r2 = r * r, a2 = a * a, r3 = r2 * r, a3 = a2 * a;
+  float* sl = d.sl;
+  sl[0] = r, sl[1] = a;
+  sl[2] = r2, sl[3] = a * r, sl[4] = a2;
+  sl[5] = r3, sl[6] = a * r2, sl[7] = a2 * r, sl[8] = a3;
+  sl[9] = r2 * r2, sl[10] = a * r3, sl[11] = a2 * r2, sl[12] = a3 * r, sl[13] = a2 * a2;
+}
+
 // (re)build the compact device array of chains, keeping the running state of tracks whose chain did not change
 static int sync_effects(wbx_engine* e) {
   if (e->ir_taps > 1 && e->firhist_tracks != e->n_tracks && !e->fx_on.empty()) e->fx_dirty = true;
@@ -670,6 +710,7 @@ static int sync_effects(wbx_engine* e) {
     d.att = f.comp_attack;
     d.rel = f.comp_release;
     d.makeup = f.comp_makeup;
+    design_fx_tables(d);
     if (!e->fx_reset[t])
       for (const DFx& o : old)
         if (o.track == t) {
@@ -695,6 +736,12 @@ static int sync_effects(wbx_engine* e) {
   }
   std::fill(e->fx_reset.begin(), e->fx_reset.end(), 0);
   e->n_fx = (uint32_t)cur.size();
+  e->fx_flags = 0;
+  for (const DFx& d : cur) e->fx_flags |= (d.eq_on || d.comp_on) ? 1u : 2u;
+  {
+    int rc = dev_reserve(e, e->d_smarr, 1024 * sizeof(uint32_t));
+    if (rc) return rc;
+  }
   if (e->n_fx) {
     int rc = dev_reserve(e, e->d_fx, cur.size() * sizeof(DFx));
     if (rc) return rc;
@@ -813,13 +860,15 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
   if (n_fx) {
     // tracks with an effect chain are rendered to a per-track buffer (frame-interleaved stereo f32) that the mix
     // kernel then reads as one whole-block unity-speed call per callback with clip gain 1.0
-    const size_t tb_floats = (size_t)n_fx * n_blocks * B * 2;
+    // (per-track stride rounded up to an even number of frames: every track's buffer starts 16-byte aligned)
+    const size_t tbs = ((size_t)n_blocks * B + 1) & ~(size_t)1;
+    const size_t tb_floats = (size_t)n_fx * tbs * 2;
     if ((rc = dev_reserve(e, e->d_trackbuf, tb_floats * sizeof(float) + 256))) return rc;
     const DFx* hf = (const DFx*)e->h_fx.p;
     for (uint32_t i = 0; i < n_fx; i++) {
       DSpan& d = hs[n_segs + i];
       memset(&d, 0, sizeof(d));
-      d.base = (const float*)e->d_trackbuf.p + (size_t)i * n_blocks * B * 2;
+      d.base = (const float*)e->d_trackbuf.p + (size_t)i * tbs * 2;
       d.pos0 = 0.0;
       d.speed = 1.0;
       d.count = (uint64_t)n_blocks * B;
@@ -871,8 +920,9 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     CU(e, launch_effects((const DSpan*)e->d_spans.p, e->cells_ptr, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
                          n_segs, (float*)e->d_trackbuf.p, rv ? (const float*)e->d_ir.p : nullptr, rv ? e->ir_taps : 0,
                          (float*)e->d_firhist.p, (float*)e->d_firin.p, tc ? e->d_irtiles.p : nullptr,
-                         tc ? e->d_firplanes.p : nullptr, (const float*)e->d_poly.p, e->stream));
-    e->launches += rv ? (tc ? 7 : 6) : 3;
+                         tc ? e->d_firplanes.p : nullptr, (const float*)e->d_poly.p, e->fx_flags, (uint32_t*)e->d_smarr.p,
+                         (((uint64_t)n_blocks * B + 1) & ~(uint64_t)1), e->stream));
+    e->launches += (rv ? (tc ? 5 : 4) : 1) + ((e->fx_flags & 1u) ? 1 : 0) + ((e->fx_flags & 2u) ? 1 : 0);
   }
   e->n_blocks = n_blocks;
   e->n_spans = n_segs;

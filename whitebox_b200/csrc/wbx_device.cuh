@@ -153,9 +153,13 @@ struct DFx {
   float thr, att, rel, makeup;
   float s1[2][4], s2[2][4], env[2];  // state, persists across renders
   uint32_t reverb_on;
-  uint32_t pad;
+  uint32_t sel;  // att <= rel: the follower's branch is the larger candidate
+  // time-parallel form (oracle/wb_oracle.c fx_design_tables): state-space input vector, A^m (m = 0..16) and A^(16 * 2^j)
+  // (j = 0..4) per biquad, row-major 2x2; follower constants 1 - att, 1 - rel and look-ahead slopes S1 | S2 | S3 | S4
+  float B1[4], B2[4], P[4][17][4], S[4][5][4];
+  float a1m, r1m, sl[14];
 };
-static_assert(sizeof(DFx) == 16 + 80 + 16 + 72 + 8, "DFx layout");
+static_assert(sizeof(DFx) == 16 + 80 + 16 + 72 + 8 + 32 + 1088 + 320 + 64, "DFx layout");
 
 constexpr uint32_t kMaxPeers = 16;  // ranks of one sharded render (one NVSwitch box has 8)
 

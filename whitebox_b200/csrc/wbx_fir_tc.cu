@@ -92,7 +92,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {  // arrives on `bar`
 
 struct FirTcParams {
   const DFx* fx;
-  float* trackbuf;  // [n_fx][T][2]
+  float* trackbuf;  // [n_fx][tbs][2]
+  uint64_t tbs;     // frames per track in trackbuf (>= T, even)
   uint32_t C;       // bus channels: signal index = e * C + c
   uint32_t n_signals;
   uint64_t H, T;    // plane column of input time 0 (history rounded up to 8 columns), frames in this render
@@ -263,7 +264,7 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__
         const uint32_t sig = (uint32_t)(s0 + q);
         if (sig < p.n_signals) {
           const uint32_t e = sig / p.C, c = sig % p.C;
-          if (p.fx[e].reverb_on) p.trackbuf[((size_t)e * p.T + (size_t)n) * 2 + c] = acc[q];
+          if (p.fx[e].reverb_on) p.trackbuf[((size_t)e * p.tbs + (size_t)n) * 2 + c] = acc[q];
         }
       }
     }
@@ -322,7 +323,7 @@ cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, cuda
 
 // xin: f32 [n_signals][H + T]; planes: scratch for 3 x [n_signals][W] bf16
 cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T, uint32_t L, void* tiles,
-                          const float* xin, void* planes, float* trackbuf, cudaStream_t stream) {
+                          const float* xin, void* planes, float* trackbuf, uint64_t tbs, cudaStream_t stream) {
   const uint32_t S = n_fx * C;
   if (S == 0 || T == 0) return cudaSuccess;
   const uint64_t W = fir_tc_plane_width(H, T);
@@ -345,6 +346,7 @@ cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, 
   FirTcParams p;
   p.fx = fx;
   p.trackbuf = trackbuf;
+  p.tbs = tbs;
   p.C = C;
   p.n_signals = S;
   p.H = origin;  // the kernel only needs the plane column of input time 0

@@ -990,13 +990,14 @@ __device__ __forceinline__ float stream_value(const DSpan& sp, const DCell& cell
 // one warp per (effect track e, callback k): the track's mixing buffer before effects, frame-interleaved stereo
 __global__ void render_tracks_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells,
                                      const DFx* __restrict__ fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
-                                     uint32_t B, uint32_t C, const float* __restrict__ poly, float* __restrict__ trackbuf) {
+                                     uint32_t B, uint32_t C, const float* __restrict__ poly, float* __restrict__ trackbuf, uint64_t tbs) {
   const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (w >= (uint64_t)n_fx * K) return;
   const uint32_t e = (uint32_t)(w / K), k = (uint32_t)(w % K);
+  if (fx[e].eq_on || fx[e].comp_on) return;  // rendered inside fx_chain_kernel
   const uint32_t t = fx[e].track;
-  float2* out = reinterpret_cast<float2*>(trackbuf) + ((size_t)e * K + k) * B;
+  float2* out = reinterpret_cast<float2*>(trackbuf) + (size_t)e * tbs + (size_t)k * B;
   if (S == 1) {  // one Sampler::stream call per callback (the steady state): cell and span read once per warp
     const DCell cell = cells[(size_t)k * N + t];
     if (cell.span == kSilent) {
@@ -1047,45 +1048,8 @@ __global__ void render_tracks_kernel(const DSpan* __restrict__ spans, const DCel
   }
 }
 
-// The chain is a recurrence in time: one THREAD per (effect track, channel) carries the state in registers and
-// walks the whole render, 16 frames at a time so the loads of a chunk are in flight together. Same operations, same order as oracle/wb_oracle.c apply_effects (every op a single IEEE rn op;
-// __fmaf_rn = fmaf). Time-parallel (scan) evaluation of the biquads would re-associate and is left for later.
-struct FxChannel {
-  float s1[4], s2[4], env;
-};
-
-__device__ __forceinline__ float fx_sample(float x, FxChannel& st, const float (&b0)[4], const float (&b1)[4],
-                                           const float (&b2)[4], const float (&a1)[4], const float (&a2)[4], bool eq_on,
-                                           bool comp_on, float thr, float att, float rel, float makeup, uint32_t code) {
-  if (eq_on) {
-#pragma unroll
-    for (int b = 0; b < 4; b++) {  // transposed direct form II
-      const float y = __fmaf_rn(b0[b], x, st.s1[b]);
-      st.s1[b] = __fmaf_rn(b1[b], x, __fmaf_rn(-a1[b], y, st.s2[b]));
-      st.s2[b] = __fmaf_rn(b2[b], x, -__fmul_rn(a2[b], y));
-      x = y;
-    }
-  }
-  if (comp_on) {
-    const float xa = fabsf(x);
-    st.env = xa > st.env ? __fmaf_rn(att, __fsub_rn(st.env, xa), xa) : __fmaf_rn(rel, __fsub_rn(st.env, xa), xa);
-    float g = 1.0f;
-    if (st.env > thr) {
-      const float r = __fdiv_rn(thr, st.env);
-      const float r2 = __fsqrt_rn(r);
-      switch (code) {
-        case 1: g = r2; break;
-        case 2: g = __fmul_rn(r2, __fsqrt_rn(r2)); break;
-        case 3: g = __fmul_rn(__fmul_rn(r2, __fsqrt_rn(r2)), __fsqrt_rn(__fsqrt_rn(r2))); break;
-        default: g = r; break;
-      }
-    }
-    x = __fmul_rn(__fmul_rn(x, g), makeup);
-  }
-  return x;
-}
-
-// The memoryless part of the compressor: gain from the envelope, applied with the make-up gain.
+// The memoryless part of the compressor: gain from the envelope, applied with the make-up gain
+// (oracle/wb_oracle.c fx_comp_stage, last loop).
 __device__ __forceinline__ float fx_gain(float x, float env, float thr, float makeup, uint32_t code) {
   float g = 1.0f;
   if (env > thr) {
@@ -1101,325 +1065,534 @@ __device__ __forceinline__ float fx_gain(float x, float env, float thr, float ma
   return __fmul_rn(__fmul_rn(x, g), makeup);
 }
 
-// The chain is five recurrences in series (4 biquads, the envelope follower) and one memoryless map (gain computer).
-// A thread that walks them sample by sample is bound by the dependent-FMA latency of all five in a row while the GPU
-// idles. Here one WARP carries P (track, channel) pairs as a software pipeline over 32-frame chunks held in shared
-// memory: lane p*4+s runs biquad s of pair p on chunk i-s, lane p also runs pair p's envelope follower on chunk i-4 —
-// both recurrences sit in the same instruction stream, so their latencies overlap — and all 32 lanes then evaluate the
-// gain computer of chunk i-5 one frame per lane and store it. Every frame still sees exactly the operations of
-// fx_sample in the same order (a stage's input is the previous stage's rounded output either way): bit-identical to
-// the one-thread walk and to oracle/wb_oracle.c apply_effects.
-template <int P>
-struct FxLayout {
-  static constexpr int DEPTH = 4;                      // chunk slots per stage buffer (writer and readers 2 apart)
-  // 32 frames + pad. P <= 4: 36 — rows stay 16-B aligned for 128-bit accesses and the rows a quarter-warp touches
-  // start 4 banks apart (measured 16.0 -> 14.5 ms at 512 tracks). P = 8: 33 — with all 32 lanes active the 36-float
-  // stride is a 4-way bank conflict (measured 11.7 -> 13.2 ms at 4096 tracks), so that size keeps scalar accesses with
-  // one row per bank.
-  static constexpr int ROW = P <= 4 ? 36 : 33;
-  static constexpr bool VEC = ROW % 4 == 0;
-  static constexpr int ROWS = (5 * DEPTH) * P + DEPTH * P;  // X[0..4], E
-  static constexpr int WARP_FLOATS = ROWS * ROW;
-  __device__ static int x_row(int stage, int slot, int pair) { return (stage * DEPTH + slot) * P + pair; }
-  __device__ static int e_row(int slot, int pair) { return (5 * DEPTH + slot) * P + pair; }
-  static constexpr int IDLE = 0;  // row idle lanes point at (never dereferenced)
+// ---------------------------------------------------------------------------------------------------------
+// fx_chain_kernel — track render + 4-band EQ + compressor, TIME-PARALLEL (extension, BASELINE cfg 4)
+//
+// Specification: oracle/wb_oracle.c apply_effects (fx_eq_stage / fx_comp_stage) — the chain evaluated in a blocked
+// association chosen so that almost nothing is serial in time; this kernel performs exactly those IEEE operations
+// (explicit _rn intrinsics; packed f32x2 forms are per-component rn), so CUDA == the C spec bit for bit.
+//
+// One CTA carries TPC tracks (1, 2 or 4: enough to give every SM one CTA), software-pipelined over chunks of <= 512
+// frames of a callback, one __syncthreads per iteration:
+//   iteration i:   output warps       loads of the clips of chunk i in flight (Sampler::stream + clip gain), then
+//                                     chunk i-4: envelope inside each block of 4 frames (1/2/3-step look-ahead from the
+//                                     block start), gain computer, make-up, store to the track buffer the mix kernel
+//                                     reads; then chunk i -> X[i % 5]
+//                  EQ warps a / b     (per track) biquads 0, 1 of chunk i-1 / biquads 2, 3 of chunk i-2, in place: per
+//                                     biquad a zero-state pass over the lane's 16-frame segment, a Kogge-Stone scan of
+//                                     the 32 segment end states with A^(16 * 2^j), the zero-input correction; L and R
+//                                     share coefficients -> packed f32x2 math. Warp b then builds the intercepts Q4 of
+//                                     the follower's 4-step look-ahead per block.
+//                  serial warp        chunk i-3: env <- mm_i(S4[i] * env + Q4[i]) per block — the ONLY recurrence that
+//                                     is walked serially (5 independent FMAs + 2 three-input max per 4 frames); lane =
+//                                     (track, channel), so the TPC tracks of the CTA share one instruction stream
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FXC_SEG_STRIDE = 36;                // floats per 16-frame segment of packed (L, R) frames: 32 + 4 pad
+constexpr int FXC_XSLOT = 32 * FXC_SEG_STRIDE;    // one chunk of 512 frames
+constexpr int FXC_BLOCKS = 128;                   // 4-frame blocks per chunk
+constexpr int FXC_QPAIR = 5 * FXC_BLOCKS + 4;     // floats per (parity, pair) of intercepts [5][128]; +4: pairs 16 B apart mod 128
+constexpr int FXC_EPAIR = FXC_BLOCKS + 4;         // floats per (parity, pair) of block-end envelopes: [3] = incoming, [4 + g]
+
+struct FxcTrack {
+  float X[5][FXC_XSLOT];  // ring: render | EQ a | EQ b | (held) | output
+  float TP[2][2][3][2];  // tail frames of a chunk (n % 4): (pa, pr) per channel and frame, signed domain
+  float ET[2][2][4];     // envelope at the tail frames, signed domain
+  float P[4][17][4];     // A^m per biquad (row-major 2x2)
+  float S[4][5][4];      // A^(16 * 2^j)
+  float cf[4][8];        // b0, -a1, -a2, B1, B2 per biquad
+  float2 st[4][2];       // biquad states (s1, s2) as (L, R), carried from chunk to chunk
+};
+template <int TPC>
+struct FxcSmem {
+  FxcTrack tr[TPC];
+  float Q4[2][2 * TPC][FXC_QPAIR];  // [parity][pair = track * 2 + channel][candidate i][block], signed domain
+  float E[2][2 * TPC][FXC_EPAIR];   // envelope at the end of every block
 };
 
-// T > 1: the P pairs are carried by a TEAM of T warps on different schedulers, meeting at a named barrier once per chunk;
-// the chunk slots each role touches within an iteration are disjoint (same schedule as the one-warp form).
-//   T = 2: warp 0 runs the recurrences, warp 1 the input loads, the gain computer and the stores;
-//   T = 3: the envelope followers get their own warp (ptxas schedules the two recurrences of one warp mostly one after
-//          the other instead of interleaving them, and moving the followers to the I/O warp just moves the long pole).
-// Used while the session is too small to give every scheduler of the GPU a warp otherwise: the step is then bound by
-// per-warp latency, not by issue slots.
-template <int P, int T>
-__global__ void __launch_bounds__(T == 3 ? 192 : 128) effects_kernel(DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t frames,
-                                                       float* __restrict__ trackbuf) {
-  using L = FxLayout<P>;
-  extern __shared__ __align__(16) float fx_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool DUO = T > 1;  // (kept as a name for "several warps per team")
-  const int team = warp / T, role = warp % T;
-  const int teams_per_cta = (int)(blockDim.x >> 5) / T;
-  const bool do_rec = T == 1 || role == 0;                       // this warp runs the biquads
-  const bool do_io = T == 1 || role == 1;                        // this warp loads, computes gains and stores
-  const bool do_env = T == 1 || (T == 2 ? role == 0 : role == 2);  // this warp runs the envelope followers
-  float* sm = fx_smem + (size_t)team * L::WARP_FLOATS;
-  const uint32_t n_pairs = n_fx * C;
-  const uint32_t pair0 = (blockIdx.x * teams_per_cta + team) * P;
-  if (pair0 >= n_pairs) return;  // both warps of a team leave together
-  auto team_sync = [&]() {
-    if (DUO)
-      asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(32 * T) : "memory");
-    else
-      __syncwarp();
-  };
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 shfl_up2(float2 v, unsigned d) {
+  return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ float2 fmax2(float2 a, float2 b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+// smem address of frame f of a chunk slot (packed (L, R) float2)
+__device__ __forceinline__ int fxc_addr(int f) { return (f >> 4) * FXC_SEG_STRIDE + ((f & 15) << 1); }
 
-  // biquad role: lane = p*4 + s
-  const int bp = lane >> 2, bs = lane & 3;
-  const bool bq_lane = bp < P && pair0 + bp < n_pairs;
-  float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f, s1 = 0.f, s2 = 0.f;
-  bool eq_on = false;
-  if (bq_lane) {
-    const uint32_t g = pair0 + bp;
-    const DFx* f = fx + g / C;
-    const uint32_t c = g % C;
-    eq_on = f->eq_on != 0;
-    b0 = f->b0[bs], b1 = f->b1[bs], b2 = f->b2[bs], a1 = f->a1[bs], a2 = f->a2[bs];
-    s1 = f->s1[c][bs], s2 = f->s2[c][bs];
-  }
-  // envelope role: lane = p
-  bool env_lane = lane < P && pair0 + lane < n_pairs;
-  float env = 0.f, att = 0.f, rel = 0.f;
-  if (env_lane) {
-    const uint32_t g = pair0 + lane;
-    const DFx* f = fx + g / C;
-    env = f->env[g % C];
-    att = f->att, rel = f->rel;
-    env_lane = f->comp_on != 0;  // without a compressor the envelope state is left alone (fx_sample)
-  }
-  // gain role: every lane, pair r in turn — per-pair constants and the pair's channel in the interleaved track buffer
-  float thr[P], makeup[P];
-  uint32_t code[P];
-  bool comp_on[P];
-  float* buf[P];
-#pragma unroll
-  for (int r = 0; r < P; r++) {
-    const uint32_t g = pair0 + r < n_pairs ? pair0 + r : n_pairs - 1;
-    const DFx* f = fx + g / C;
-    thr[r] = f->thr, makeup[r] = f->makeup, code[r] = f->ratio_code, comp_on[r] = f->comp_on != 0;
-    buf[r] = trackbuf + (size_t)(g / C) * frames * 2 + (g % C);
-  }
-
-  // chunk counters are 32-bit: 2^32 chunks of 32 frames is 33 days of 48 kHz audio in one render
-  const uint32_t n_chunks = (uint32_t)((frames + 31) / 32);
-  const int last_len = (int)(frames - (uint64_t)(n_chunks ? n_chunks - 1 : 0) * 32);
-  auto chunk_len = [&](int32_t c) -> int {
-    if (c < 0 || (uint32_t)c >= n_chunks) return 0;
-    return (uint32_t)c + 1 == n_chunks ? last_len : 32;
-  };
-  // input chunk c (one frame per lane) of pair r; the track buffer is larger than L2, so every chunk is an HBM round trip
-  auto load_chunk = [&](uint32_t c, int r) -> float {
-    const uint64_t f = (uint64_t)c * 32 + lane;
-    return (do_io && pair0 + r < n_pairs && f < frames) ? buf[r][f * 2] : 0.0f;
-  };
-  // chunk 0 into X[0][0]; chunks 1 and 2 on their way (the loop keeps three chunks in flight in registers)
-  float nxt0[P], nxt1[P];
-  if (do_io) {
-#pragma unroll
-    for (int r = 0; r < P; r++)
-      if (pair0 + r < n_pairs && (uint64_t)lane < frames) sm[L::x_row(0, 0, r) * L::ROW + lane] = buf[r][(size_t)lane * 2];
-  }
-#pragma unroll
-  for (int r = 0; r < P; r++) {
-    nxt0[r] = load_chunk(1, r);
-    nxt1[r] = load_chunk(2, r);
-  }
-  team_sync();
-
-  for (uint32_t i = 0; i < n_chunks + 5; i++) {
-    // input of chunk i+3: issued now, stored into its slot two iterations from now — an HBM latency is longer than one
-    // iteration of the recurrences
-    float nxt2[P];
-#pragma unroll
-    for (int r = 0; r < P; r++) nxt2[r] = load_chunk(i + 3, r);
-
-    // ---- recurrences: biquad s on chunk i-s, envelope on chunk i-4 -------------------------------------------
-    const bool steady = i >= 5 && i + 1 < n_chunks;  // every role has a full chunk this iteration: no bounds work
-    const int32_t cb = (int32_t)i - bs, ce = (int32_t)i - 4;
-    const int nb = (bq_lane && do_rec) ? (steady ? 32 : chunk_len(cb)) : 0;
-    const int ne = (env_lane && do_env) ? (steady ? 32 : chunk_len(ce)) : 0;
-    const float* xin = sm + (nb ? L::x_row(bs, (int)(cb & 3), bp) : L::IDLE) * L::ROW;
-    float* xout = sm + (nb ? L::x_row(bs + 1, (int)(cb & 3), bp) : L::IDLE) * L::ROW;
-    const float* ein = sm + (ne ? L::x_row(4, (int)(ce & 3), lane) : L::IDLE) * L::ROW;
-    float* eout = sm + (ne ? L::e_row((int)(ce & 3), lane) : L::IDLE) * L::ROW;
-    // One steady-state pass over a full chunk for the roles this warp holds. Idle lanes run the same arithmetic on zeros
-    // (their state is never stored): only the shared-memory accesses are predicated on the lane's role, the recurrences
-    // carry no predicate. The chunk is staged in registers: a shared-memory load between dependent FMAs (the compiler
-    // cannot move it above the previous frame's store) would put its latency into every step of the recurrence.
-    auto steady_pass = [&](auto bq_tag, auto en_tag) {
-      constexpr bool BQ = decltype(bq_tag)::value, EN = decltype(en_tag)::value;
-      const bool bq = nb != 0, en = ne != 0;
-      float xv[BQ ? 32 : 1], ev[EN ? 32 : 1];
-      if constexpr (L::VEC) {
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {  // 128-bit shared-memory accesses: 8 loads instead of 32 per role
-          if constexpr (BQ) {
-            const float4 a = bq ? *reinterpret_cast<const float4*>(xin + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            xv[q] = a.x, xv[q + 1] = a.y, xv[q + 2] = a.z, xv[q + 3] = a.w;
-          }
-          if constexpr (EN) {
-            const float4 e4 = en ? *reinterpret_cast<const float4*>(ein + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            ev[q] = e4.x, ev[q + 1] = e4.y, ev[q + 2] = e4.z, ev[q + 3] = e4.w;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 32; q++) {
-          if constexpr (BQ) xv[q] = bq ? xin[q] : 0.0f;
-          if constexpr (EN) ev[q] = en ? ein[q] : 0.0f;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 32; q++) {
-        if constexpr (BQ) {
-          const float x = xv[q];
-          const float y = __fmaf_rn(b0, x, s1);  // transposed direct form II (fx_sample)
-          s1 = __fmaf_rn(b1, x, __fmaf_rn(-a1, y, s2));
-          s2 = __fmaf_rn(b2, x, -__fmul_rn(a2, y));
-          xv[q] = eq_on ? y : x;
-        }
-        if constexpr (EN) {
-          const float xa = fabsf(ev[q]);
-          const float d = __fsub_rn(env, xa);
-          env = xa > env ? __fmaf_rn(att, d, xa) : __fmaf_rn(rel, d, xa);
-          ev[q] = env;
-        }
-      }
-      if constexpr (L::VEC) {
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          if constexpr (BQ)
-            if (bq) *reinterpret_cast<float4*>(xout + q) = make_float4(xv[q], xv[q + 1], xv[q + 2], xv[q + 3]);
-          if constexpr (EN)
-            if (en) *reinterpret_cast<float4*>(eout + q) = make_float4(ev[q], ev[q + 1], ev[q + 2], ev[q + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 32; q++) {
-          if constexpr (BQ)
-            if (bq) xout[q] = xv[q];
-          if constexpr (EN)
-            if (en) eout[q] = ev[q];
-        }
-      }
-    };
-    if (steady) {
-      if (do_rec && do_env)
-        steady_pass(std::true_type{}, std::true_type{});
-      else if (do_rec)
-        steady_pass(std::true_type{}, std::false_type{});
-      else if (do_env)
-        steady_pass(std::false_type{}, std::true_type{});
-    } else {
-      for (int q = 0; q < 32; q++) {
-        if (q < nb) {
-          const float x = xin[q];
-          const float y = __fmaf_rn(b0, x, s1);
-          s1 = __fmaf_rn(b1, x, __fmaf_rn(-a1, y, s2));
-          s2 = __fmaf_rn(b2, x, -__fmul_rn(a2, y));
-          xout[q] = eq_on ? y : x;
-        }
-        if (q < ne) {
-          const float xa = fabsf(ein[q]);
-          const float d = __fsub_rn(env, xa);
-          env = xa > env ? __fmaf_rn(att, d, xa) : __fmaf_rn(rel, d, xa);
-          eout[q] = env;
-        }
-      }
+// what the clips of (callback k, track t) put at frame j of the cleared mixing buffer (generic path, from global)
+__device__ __noinline__ float2 fxc_render_frame(const DSpan* __restrict__ spans, const DCell* __restrict__ cells, uint32_t k,
+                                                uint32_t t, uint32_t N, uint32_t S, uint32_t j, uint32_t C,
+                                                const float* __restrict__ poly) {
+  float2 v = make_float2(0.0f, 0.0f);
+  for (uint32_t s = 0; s < S; s++) {
+    const DCell cell = cells[((size_t)k * N + t) * S + s];
+    if (cell.span == kSilent) continue;
+    const DSpan sp = spans[cell.span];
+    if (j >= sp.dst_off && j < sp.dst_off + cell.n_act) {
+      const int32_t jj = (int32_t)(j - sp.dst_off);
+      v.x = __fadd_rn(v.x, stream_value(sp, cell, jj, 0, k - sp.block0, poly, C == 2));  // dst += ... on a cleared buffer
+      if (C == 2) v.y = __fadd_rn(v.y, stream_value(sp, cell, jj, 1, k - sp.block0, poly, true));
     }
-    // ---- gain computer + store of chunk i-5, one frame per lane ------------------------------------------------
-    const int32_t cg = (int32_t)i - 5;
-    const int ng = do_io ? (steady ? 32 : chunk_len(cg)) : 0;
-    if (lane < ng) {
-#pragma unroll
-      for (int r = 0; r < P; r++) {
-        if (pair0 + r >= n_pairs) break;
-        const float x = sm[L::x_row(4, (int)(cg & 3), r) * L::ROW + lane];
-        const float e = sm[L::e_row((int)(cg & 3), r) * L::ROW + lane];
-        buf[r][((size_t)(uint32_t)cg * 32 + lane) * 2] = comp_on[r] ? fx_gain(x, e, thr[r], makeup[r], code[r]) : x;
-      }
-    }
-    // ---- stage the next input chunk -------------------------------------------------------------------------------
-    if (do_io) {
-#pragma unroll
-      for (int r = 0; r < P; r++) sm[L::x_row(0, (int)((i + 1) & 3), r) * L::ROW + lane] = nxt0[r];
-    }
-#pragma unroll
-    for (int r = 0; r < P; r++) {
-      nxt0[r] = nxt1[r];
-      nxt1[r] = nxt2[r];
-    }
-    team_sync();
   }
+  return v;
+}
 
-  if (do_rec && bq_lane && eq_on) {
-    const uint32_t g = pair0 + bp;
-    DFx* f = fx + g / C;
-    f->s1[g % C][bs] = s1;
-    f->s2[g % C][bs] = s2;
+// intercepts of the follower's look-ahead for one block of 4 frames, both channels packed; signed domain (negated when
+// the follower takes the smaller candidate, so that mm is always max). pa / pr = (1 - att)|x|, (1 - rel)|x|.
+struct FxcQ {
+  float2 q1[2], q2[3], q3[4], q4[5];
+};
+template <int DEPTH>
+__device__ __forceinline__ void fxc_intercepts(const float2 (&x)[4], float a, float r, float a1m_s, float r1m_s, FxcQ& q) {
+  float2 pa[4], pr[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const float2 xa = make_float2(fabsf(x[m].x), fabsf(x[m].y));
+    pa[m] = __fmul2_rn(f2(a1m_s), xa);
+    pr[m] = __fmul2_rn(f2(r1m_s), xa);
   }
-  if (do_env && env_lane) {
-    const uint32_t g = pair0 + lane;
-    fx[g / C].env[g % C] = env;
+  const float2 a2v = f2(a), r2v = f2(r);
+  q.q1[0] = pr[0], q.q1[1] = pa[0];
+  q.q2[0] = __ffma2_rn(r2v, q.q1[0], pr[1]);
+  q.q2[1] = fmax2(__ffma2_rn(r2v, q.q1[1], pr[1]), __ffma2_rn(a2v, q.q1[0], pa[1]));
+  q.q2[2] = __ffma2_rn(a2v, q.q1[1], pa[1]);
+  q.q3[0] = __ffma2_rn(r2v, q.q2[0], pr[2]);
+#pragma unroll
+  for (int i = 1; i < 3; i++) q.q3[i] = fmax2(__ffma2_rn(r2v, q.q2[i], pr[2]), __ffma2_rn(a2v, q.q2[i - 1], pa[2]));
+  q.q3[3] = __ffma2_rn(a2v, q.q2[2], pa[2]);
+  if (DEPTH >= 4) {
+    q.q4[0] = __ffma2_rn(r2v, q.q3[0], pr[3]);
+#pragma unroll
+    for (int i = 1; i < 4; i++) q.q4[i] = fmax2(__ffma2_rn(r2v, q.q3[i], pr[3]), __ffma2_rn(a2v, q.q3[i - 1], pa[3]));
+    q.q4[4] = __ffma2_rn(a2v, q.q3[3], pa[3]);
   }
 }
 
-template <int P, int T>
-static cudaError_t launch_effects_p(DFx* fx, uint32_t n_fx, uint32_t C, uint64_t frames, float* trackbuf, cudaStream_t stream) {
-  constexpr int TEAMS = T == 1 ? 4 : 2;  // teams (= shared-memory regions) per CTA
-  constexpr int WARPS = TEAMS * T;
-  const size_t smem = (size_t)FxLayout<P>::WARP_FLOATS * TEAMS * sizeof(float);
-  auto kfn = effects_kernel<P, T>;
+// one step of the serial recurrence: env after a block of 4 frames
+__device__ __forceinline__ float fxc_step(float ev, const float (&s4)[5], float q0, float q1, float q2, float q3, float q4) {
+  const float t0 = __fmaf_rn(s4[0], ev, q0), t1 = __fmaf_rn(s4[1], ev, q1), t2 = __fmaf_rn(s4[2], ev, q2);
+  const float t3 = __fmaf_rn(s4[3], ev, q3), t4 = __fmaf_rn(s4[4], ev, q4);
+  return fmaxf(fmaxf(fmaxf(t0, t1), t2), fmaxf(t3, t4));
+}
+
+template <int TPC>
+struct FxcShape {
+  static constexpr int OW = TPC == 4 ? 2 : 4;  // output warps per track
+  static constexpr int EQW = 1;                // EQ warps per track: 1 = all four biquads in one warp, 2 = a / b pipeline
+  static constexpr int WARPS = 1 + EQW * TPC + TPC * OW;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int OLANES = OW * 32;       // lanes rendering / finishing one track
+};
+
+template <int TPC>
+__global__ void __launch_bounds__(FxcShape<TPC>::THREADS, 1)
+fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells, DFx* __restrict__ fx, uint32_t n_fx, uint32_t N,
+                uint32_t S, uint32_t K, uint32_t B, uint32_t C, const float* __restrict__ poly, float* __restrict__ trackbuf,
+                uint64_t tbs) {
+  using SH = FxcShape<TPC>;
+  extern __shared__ __align__(16) unsigned char fxc_raw[];
+  FxcSmem<TPC>& sm = *reinterpret_cast<FxcSmem<TPC>*>(fxc_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // roles: warp 0 = the serial warp (lane = pair), warps 1..TPC = EQ a, TPC+1..2TPC = EQ b (one of each per track), the
+  // rest = output warps
+  const bool w_serial = warp == 0, w_eq = warp >= 1 && warp <= SH::EQW * TPC;
+  const bool w_eqb = SH::EQW == 1 ? w_eq : (w_eq && warp > TPC);  // the warp that finishes the EQ and builds the intercepts
+  const bool w_eqa = SH::EQW == 1 ? w_eq : (w_eq && warp <= TPC);
+  const int oidx = warp - 1 - SH::EQW * TPC;
+  const int tl = w_serial ? (lane >> 1) : (w_eq ? (warp - 1) % TPC : oidx / SH::OW);  // local track of this thread
+  const int ow = w_serial || w_eq ? 0 : oidx % SH::OW;
+  const uint32_t e = blockIdx.x * TPC + (uint32_t)(tl < TPC ? tl : 0);
+  const bool live_lane = tl < TPC && e < n_fx;
+  DFx* __restrict__ f = fx + (live_lane ? e : 0);
+  const bool eq_on = live_lane && f->eq_on != 0, comp_on = live_lane && f->comp_on != 0;
+  const bool active = eq_on || comp_on;  // reverb-only chains are rendered by render_tracks_kernel
+  const uint32_t t = f->track;
+  FxcTrack& tr = sm.tr[tl < TPC ? tl : 0];
+
+  // ---- tables and states into shared memory ----------------------------------------------------------------------
+  if (w_eqa && active) {
+    for (int i = lane; i < 4 * 17 * 4; i += 32) (&tr.P[0][0][0])[i] = (&f->P[0][0][0])[i];
+    for (int i = lane; i < 4 * 5 * 4; i += 32) (&tr.S[0][0][0])[i] = (&f->S[0][0][0])[i];
+    if (lane < 4) {
+      tr.cf[lane][0] = f->b0[lane];
+      tr.cf[lane][1] = -f->a1[lane];
+      tr.cf[lane][2] = -f->a2[lane];
+      tr.cf[lane][3] = f->B1[lane];
+      tr.cf[lane][4] = f->B2[lane];
+      tr.st[lane][0] = make_float2(f->s1[0][lane], f->s1[1][lane]);
+      tr.st[lane][1] = make_float2(f->s2[0][lane], f->s2[1][lane]);
+    }
+  }
+  __syncthreads();
+
+  const float att = f->att, rel = f->rel;
+  const bool sel = f->sel != 0;
+  const float sgn = sel ? 1.0f : -1.0f;
+  const float a1m_s = sel ? f->a1m : -f->a1m, r1m_s = sel ? f->r1m : -f->r1m;
+  const float thr = f->thr, makeup = f->makeup;
+  const uint32_t code = f->ratio_code;
+
+  const uint32_t spc = (B + 511u) / 512u;  // chunks per callback
+  const uint32_t NC = K * spc;
+  auto chunk_shape = [&](uint32_t i, uint32_t& k, uint32_t& f0, uint32_t& n) {
+    k = i / spc;
+    f0 = (i % spc) * 512u;
+    n = B - f0 < 512u ? B - f0 : 512u;
+  };
+  float2* const tb = reinterpret_cast<float2*>(trackbuf) + (size_t)e * tbs;
+  const bool tb_vec = (B & 1u) == 0;  // 4-frame groups of the track buffer are 16-byte aligned
+
+  const int pair = lane;  // serial warp: lane = track * 2 + channel
+  const bool ser_lane = w_serial && lane < 2 * TPC && comp_on;
+  float env_s = ser_lane ? sgn * f->env[lane & 1] : 0.0f;  // follower state, signed domain
+  float s4[5], s123[9];
+#pragma unroll
+  for (int i = 0; i < 5; i++) s4[i] = w_serial ? f->sl[9 + i] : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; i++) s123[i] = (!w_serial && !w_eq) ? f->sl[i] : 0.0f;
+
+  constexpr uint32_t LAG_S = SH::EQW + 1, LAG_O = SH::EQW + 2;  // chunks the serial / output warps run behind the render
+  for (uint32_t it = 0; it < NC + LAG_O; it++) {
+    if (w_eq) {
+      // ---- EQ: biquads 0, 1 of chunk it-1 (warp a) / biquads 2, 3 of chunk it-2, then the follower's intercepts (b) ----
+      const uint32_t lag = (SH::EQW == 2 && w_eqb) ? 2u : 1u;  // with one EQ warp the slot after it is simply held
+      if (active && it >= lag && it - lag < NC) {
+        uint32_t k, f0, n;
+        chunk_shape(it - lag, k, f0, n);
+        float* X = tr.X[(it - lag) % 5u];
+        const int par = (int)((it - lag) & 1);
+        if (eq_on) {
+          const int len = (int)n - 16 * lane < 0 ? 0 : ((int)n - 16 * lane > 16 ? 16 : (int)n - 16 * lane);
+          const int last = ((int)n - 1) >> 4;  // lane holding the chunk's last frame
+          float2 xs[16];
+          float* seg = X + lane * FXC_SEG_STRIDE;
+#pragma unroll
+          for (int m = 0; m < 16; m += 2) {
+            const float4 v = (m < len) ? *reinterpret_cast<const float4*>(seg + 2 * m) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xs[m] = make_float2(v.x, v.y);
+            xs[m + 1] = make_float2(v.z, v.w);
+          }
+#pragma unroll 1
+          for (int b = (SH::EQW == 2 && w_eqb) ? 2 : 0; b < ((SH::EQW == 2 && w_eqa) ? 2 : 4); b++) {
+            const float2 b0 = f2(tr.cf[b][0]), na1 = f2(tr.cf[b][1]), na2 = f2(tr.cf[b][2]), B1 = f2(tr.cf[b][3]), B2 = f2(tr.cf[b][4]);
+            float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+            if (n == 512u) {  // every segment is full: no per-frame guards
+#pragma unroll
+              for (int m = 0; m < 16; m++) {
+                const float2 xi = xs[m];
+                xs[m] = __ffma2_rn(b0, xi, s1);
+                const float2 tt = __ffma2_rn(B1, xi, s2);
+                s2 = __ffma2_rn(na2, s1, __fmul2_rn(B2, xi));
+                s1 = __ffma2_rn(na1, s1, tt);
+              }
+            } else {
+#pragma unroll
+              for (int m = 0; m < 16; m++) {
+                if (m < len) {
+                  const float2 xi = xs[m];
+                  xs[m] = __ffma2_rn(b0, xi, s1);
+                  const float2 tt = __ffma2_rn(B1, xi, s2);
+                  s2 = __ffma2_rn(na2, s1, __fmul2_rn(B2, xi));
+                  s1 = __ffma2_rn(na1, s1, tt);
+                }
+              }
+            }
+            const float2 e1 = s1, e2 = s2;
+            const float2 in1 = tr.st[b][0], in2 = tr.st[b][1];  // state entering the chunk (L, R)
+            float2 v1 = e1, v2 = e2;
+            if (lane == 0) {  // the incoming state enters through segment 0
+              v1 = __ffma2_rn(f2(tr.S[b][0][0]), in1, __ffma2_rn(f2(tr.S[b][0][1]), in2, e1));
+              v2 = __ffma2_rn(f2(tr.S[b][0][2]), in1, __ffma2_rn(f2(tr.S[b][0][3]), in2, e2));
+            }
+#pragma unroll
+            for (int j = 0; j < 5; j++) {  // Kogge-Stone: v[l] += A^(16 d) v[l - d]
+              const unsigned d = 1u << j;
+              const float2 u1 = shfl_up2(v1, d), u2 = shfl_up2(v2, d);
+              if (lane >= (int)d) {
+                const float4 sj = *reinterpret_cast<const float4*>(&tr.S[b][j][0]);
+                const float2 n1 = __ffma2_rn(f2(sj.x), u1, __ffma2_rn(f2(sj.y), u2, v1));
+                const float2 n2 = __ffma2_rn(f2(sj.z), u1, __ffma2_rn(f2(sj.w), u2, v2));
+                v1 = n1, v2 = n2;
+              }
+            }
+            float2 st1 = shfl_up2(v1, 1), st2 = shfl_up2(v2, 1);
+            if (lane == 0) st1 = in1, st2 = in2;
+            // zero-input response of the segment's true start state
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+              const float2 pm = *reinterpret_cast<const float2*>(&tr.P[b][m][0]);
+              xs[m] = __ffma2_rn(f2(pm.y), st2, __ffma2_rn(f2(pm.x), st1, xs[m]));
+            }
+            // state after the chunk's last frame, from the lane that holds it
+            __syncwarp();
+            if (lane == last) {
+              const float4 pl = *reinterpret_cast<const float4*>(&tr.P[b][len][0]);
+              tr.st[b][0] = __ffma2_rn(f2(pl.x), st1, __ffma2_rn(f2(pl.y), st2, e1));
+              tr.st[b][1] = __ffma2_rn(f2(pl.z), st1, __ffma2_rn(f2(pl.w), st2, e2));
+            }
+          }
+#pragma unroll
+          for (int m = 0; m < 16; m += 2)
+            if (m < len) *reinterpret_cast<float4*>(seg + 2 * m) = make_float4(xs[m].x, xs[m].y, xs[m + 1].x, xs[m + 1].y);
+          __syncwarp();
+        }
+        if (comp_on && w_eqb) {
+          const int nb = (int)n >> 2;
+          float* qL = sm.Q4[par][2 * tl];
+          float* qR = sm.Q4[par][2 * tl + 1];
+          for (int g = lane; g < nb; g += 32) {
+            const float* src = X + fxc_addr(4 * g);
+            const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+            const float2 x4[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)};
+            FxcQ q;
+            fxc_intercepts<4>(x4, att, rel, a1m_s, r1m_s, q);
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+              qL[i * FXC_BLOCKS + g] = q.q4[i].x;
+              qR[i * FXC_BLOCKS + g] = q.q4[i].y;
+            }
+          }
+          const int tail = (int)n & 3;
+          if (lane < tail) {  // the chunk's last 1..3 frames: (pa, pr) for the one-step form
+            const float2 xv = *reinterpret_cast<const float2*>(X + fxc_addr(4 * nb + lane));
+            tr.TP[par][0][lane][0] = __fmul_rn(a1m_s, fabsf(xv.x));
+            tr.TP[par][0][lane][1] = __fmul_rn(r1m_s, fabsf(xv.x));
+            tr.TP[par][1][lane][0] = __fmul_rn(a1m_s, fabsf(xv.y));
+            tr.TP[par][1][lane][1] = __fmul_rn(r1m_s, fabsf(xv.y));
+          }
+        }
+      }
+    } else if (w_serial) {
+      // ---- the follower's serial recurrence over chunk it-LAG_S: one step per block of 4 frames ---------------------
+      if (ser_lane && it >= LAG_S && it - LAG_S < NC) {
+        uint32_t k, f0, n;
+        chunk_shape(it - LAG_S, k, f0, n);
+        const int par = (int)((it - LAG_S) & 1);
+        const int nb = (int)n >> 2;
+        const float* Q = sm.Q4[par][pair];
+        float* E = sm.E[par][pair];
+        float ev = env_s;
+        E[3] = ev;  // the envelope entering the chunk
+        const int ng = nb >> 2;  // groups of 4 blocks: 5 x 128-bit loads, 1 x 128-bit store each
+        float4 qa[5], qb[5];
+        if (ng > 0) {
+#pragma unroll
+          for (int i = 0; i < 5; i++) qa[i] = *reinterpret_cast<const float4*>(Q + i * FXC_BLOCKS);
+        }
+        for (int j = 0; j < ng; j += 2) {
+          if (j + 1 < ng) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) qb[i] = *reinterpret_cast<const float4*>(Q + i * FXC_BLOCKS + 4 * (j + 1));
+          }
+          {
+            float4 o;
+            o.x = ev = fxc_step(ev, s4, qa[0].x, qa[1].x, qa[2].x, qa[3].x, qa[4].x);
+            o.y = ev = fxc_step(ev, s4, qa[0].y, qa[1].y, qa[2].y, qa[3].y, qa[4].y);
+            o.z = ev = fxc_step(ev, s4, qa[0].z, qa[1].z, qa[2].z, qa[3].z, qa[4].z);
+            o.w = ev = fxc_step(ev, s4, qa[0].w, qa[1].w, qa[2].w, qa[3].w, qa[4].w);
+            *reinterpret_cast<float4*>(E + 4 + 4 * j) = o;
+          }
+          if (j + 1 < ng) {
+            if (j + 2 < ng) {
+#pragma unroll
+              for (int i = 0; i < 5; i++) qa[i] = *reinterpret_cast<const float4*>(Q + i * FXC_BLOCKS + 4 * (j + 2));
+            }
+            float4 o;
+            o.x = ev = fxc_step(ev, s4, qb[0].x, qb[1].x, qb[2].x, qb[3].x, qb[4].x);
+            o.y = ev = fxc_step(ev, s4, qb[0].y, qb[1].y, qb[2].y, qb[3].y, qb[4].y);
+            o.z = ev = fxc_step(ev, s4, qb[0].z, qb[1].z, qb[2].z, qb[3].z, qb[4].z);
+            o.w = ev = fxc_step(ev, s4, qb[0].w, qb[1].w, qb[2].w, qb[3].w, qb[4].w);
+            *reinterpret_cast<float4*>(E + 4 + 4 * (j + 1)) = o;
+          }
+        }
+        for (int g = 4 * ng; g < nb; g++) {  // up to 3 blocks left over
+          ev = fxc_step(ev, s4, Q[g], Q[FXC_BLOCKS + g], Q[2 * FXC_BLOCKS + g], Q[3 * FXC_BLOCKS + g], Q[4 * FXC_BLOCKS + g]);
+          E[4 + g] = ev;
+        }
+        const int tail = (int)n & 3;
+        FxcTrack& mt = sm.tr[pair >> 1];
+        for (int j = 0; j < tail; j++) {
+          ev = fmaxf(__fmaf_rn(rel, ev, mt.TP[par][pair & 1][j][1]), __fmaf_rn(att, ev, mt.TP[par][pair & 1][j][0]));
+          mt.ET[par][pair & 1][j] = ev;
+        }
+        env_s = ev;
+      }
+    } else {
+      // ---- output warps: (1) loads of chunk `it` in flight, (2) output of chunk it-3, (3) chunk `it` -> X -----------
+      constexpr int RQ = 512 / SH::OLANES;  // frames per lane of a chunk
+      const int ol = ow * 32 + lane;        // lane among the track's output lanes
+      uint32_t rk = 0, rf0 = 0, rn = 0;
+      float2 rv[RQ];
+      int rmode = 0;  // 0 nothing, 1 scaled copy of rv, 2 generic per-frame path
+      uint32_t rlo = 0, rhi = 0;
+      float rgain = 0.0f;
+      if (active && it < NC) {
+        chunk_shape(it, rk, rf0, rn);
+        rmode = 2;
+        if (S == 1) {
+          const DCell cell = cells[(size_t)rk * N + t];
+          if (cell.span == kSilent) {
+            rmode = 1;  // rlo == rhi: zeros
+#pragma unroll
+            for (int q = 0; q < RQ; q++) rv[q] = make_float2(0.0f, 0.0f);
+          } else {
+            const DSpan* sp = spans + cell.span;
+            if (sp->fmt == F_F32 && sp->nch == 2 && sp->speed == 1.0 && sp->fade == 0 && C == 2) {
+              // unity-speed stereo f32 clip: a scaled copy (src * gain, then the add into the cleared buffer: 0 + m)
+              rmode = 1;
+              rlo = sp->dst_off, rhi = sp->dst_off + cell.n_act;
+              rgain = sp->gain;
+              const float2* src = reinterpret_cast<const float2*>(sp->base) + (int64_t)(uint32_t)(int64_t)cell.pos;
+#pragma unroll
+              for (int q = 0; q < RQ; q++) {
+                const uint32_t fr = q * SH::OLANES + ol, j = rf0 + fr;
+                rv[q] = (fr < rn && j >= rlo && j < rhi) ? __ldg(src + (j - rlo)) : make_float2(0.0f, 0.0f);
+              }
+            }
+          }
+        }
+      }
+      if (active && it >= LAG_O) {
+        uint32_t k, f0, n;
+        chunk_shape(it - LAG_O, k, f0, n);
+        const float* X = tr.X[(it - LAG_O) % 5u];
+        const int par = (int)((it - LAG_O) & 1);
+        const int nb = (int)n >> 2;
+        float2* dst = tb + (size_t)k * B + f0;
+        const float* EL = sm.E[par][2 * tl];
+        const float* ER = sm.E[par][2 * tl + 1];
+#pragma unroll
+        for (int u = 0; u < FXC_BLOCKS / SH::OLANES; u++) {
+          const int g = ol + u * SH::OLANES;  // block of 4 frames
+          if (g < nb) {
+            const float* src = X + fxc_addr(4 * g);
+            const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+            float2 y[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)};
+            if (comp_on) {
+              FxcQ q;
+              fxc_intercepts<3>(y, att, rel, a1m_s, r1m_s, q);
+              const float2 e0 = make_float2(EL[3 + g], ER[3 + g]);
+              float2 ev[4];
+              ev[0] = fmax2(__ffma2_rn(f2(s123[0]), e0, q.q1[0]), __ffma2_rn(f2(s123[1]), e0, q.q1[1]));
+              float2 tt = __ffma2_rn(f2(s123[2]), e0, q.q2[0]);
+#pragma unroll
+              for (int i = 1; i < 3; i++) tt = fmax2(tt, __ffma2_rn(f2(s123[2 + i]), e0, q.q2[i]));
+              ev[1] = tt;
+              tt = __ffma2_rn(f2(s123[5]), e0, q.q3[0]);
+#pragma unroll
+              for (int i = 1; i < 4; i++) tt = fmax2(tt, __ffma2_rn(f2(s123[5 + i]), e0, q.q3[i]));
+              ev[2] = tt;
+              ev[3] = make_float2(EL[4 + g], ER[4 + g]);
+              // the gain computer only does work above the threshold: one branch per block instead of one per sample
+              // (below it fx_gain is (x * 1) * makeup = x * makeup exactly)
+              bool hot = false;
+#pragma unroll
+              for (int m = 0; m < 4; m++) {
+                ev[m] = __fmul2_rn(f2(sgn), ev[m]);  // back from the signed domain (exact)
+                hot = hot || ev[m].x > thr || ev[m].y > thr;
+              }
+              if (hot) {
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                  y[m].x = fx_gain(y[m].x, ev[m].x, thr, makeup, code);
+                  y[m].y = fx_gain(y[m].y, ev[m].y, thr, makeup, code);
+                }
+              } else {
+#pragma unroll
+                for (int m = 0; m < 4; m++) y[m] = __fmul2_rn(y[m], f2(makeup));
+              }
+            }
+            if (tb_vec) {
+              reinterpret_cast<float4*>(dst + 4 * g)[0] = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
+              reinterpret_cast<float4*>(dst + 4 * g)[1] = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
+            } else {
+#pragma unroll
+              for (int m = 0; m < 4; m++) dst[4 * g + m] = y[m];
+            }
+          }
+        }
+        if (ol == 0) {  // the chunk's last 1..3 frames
+          const int tail = (int)n & 3;
+          for (int j = 0; j < tail; j++) {
+            float2 yv = *reinterpret_cast<const float2*>(X + fxc_addr(4 * nb + j));
+            if (comp_on) {
+              yv.x = fx_gain(yv.x, sgn * tr.ET[par][0][j], thr, makeup, code);
+              yv.y = fx_gain(yv.y, sgn * tr.ET[par][1][j], thr, makeup, code);
+            }
+            dst[4 * nb + j] = yv;
+          }
+        }
+      }
+      if (rmode) {
+        float* X = tr.X[it % 5u];
+#pragma unroll
+        for (int q = 0; q < RQ; q++) {
+          const uint32_t fr = q * SH::OLANES + ol, j = rf0 + fr;
+          if (fr < rn) {
+            float2 ov = make_float2(0.0f, 0.0f);
+            if (rmode == 1) {
+              if (j >= rlo && j < rhi) {
+                ov.x = __fadd_rn(0.0f, __fmul_rn(rv[q].x, rgain));
+                ov.y = __fadd_rn(0.0f, __fmul_rn(rv[q].y, rgain));
+              }
+            } else {
+              ov = fxc_render_frame(spans, cells, rk, t, N, S, j, C, poly);
+            }
+            *reinterpret_cast<float2*>(X + fxc_addr((int)fr)) = ov;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- state back ---------------------------------------------------------------------------------------------------
+  if (w_eq && eq_on && lane < 4) {
+    f->s1[0][lane] = tr.st[lane][0].x, f->s2[0][lane] = tr.st[lane][1].x;
+    if (C == 2) f->s1[1][lane] = tr.st[lane][0].y, f->s2[1][lane] = tr.st[lane][1].y;
+  }
+  if (ser_lane && (lane & 1) < (int)C) f->env[lane & 1] = sgn * env_s;
+}
+
+template <int TPC>
+static cudaError_t launch_effects_chain_t(const DSpan* spans, const DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S,
+                                          uint32_t K, uint32_t B, uint32_t C, const float* poly, float* trackbuf, uint64_t tbs,
+                                          cudaStream_t stream) {
+  auto kfn = fx_chain_kernel<TPC>;
+  const size_t smem = sizeof(FxcSmem<TPC>);
   cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  const uint32_t teams = (n_fx * C + P - 1) / P;
-  kfn<<<(teams + TEAMS - 1) / TEAMS, WARPS * 32, smem, stream>>>(fx, n_fx, C, frames, trackbuf);
+  kfn<<<(n_fx + TPC - 1) / TPC, FxcShape<TPC>::THREADS, smem, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs);
   return cudaGetLastError();
 }
 
-// Shape of the chain kernel. Small and medium sessions cannot fill the GPU's 4 schedulers per SM with one warp per P
-// pairs, and are bound by per-warp latency: they run as three-warp teams with the fewest pairs per team that keep the
-// total at ~1.5 warps per scheduler (measured at 512 tracks = 1024 pairs: P = 4 / 768 warps 11.3 ms, P = 2 / 1536 warps
-// 12.5 ms, P = 1 / 3072 warps 16.9 ms; single warps 17.2 ms). Large sessions are instruction-issue-bound: one warp per 8
-// pairs (measured at 4096 tracks: 10.0 ms, three-warp teams 13.1 ms).
-static cudaError_t launch_effects_chain(DFx* fx, uint32_t n_fx, uint32_t C, uint64_t frames, float* trackbuf, int n_sm,
-                                        cudaStream_t stream) {
-  const uint32_t pairs = n_fx * C;
-  const uint32_t slots = (uint32_t)n_sm * 4;  // warp schedulers of the GPU
-  auto teams = [&](uint32_t p) { return (pairs + p - 1) / p; };
-  int P = 4, T = 3;
-  if (3 * teams(1) <= slots + slots / 2) P = 1;
-  else if (3 * teams(2) <= slots + slots / 2) P = 2;
-  if (3 * teams(4) > 3 * slots) {  // even 4 pairs per team would put more than ~3 warps on every scheduler
-    T = 1;
-    P = pairs <= 4 * slots ? 4 : 8;
-  }
-  if (const char* env = getenv("WBX_FX_PAIRS")) {
+// Tracks per CTA: the serial warp walks one instruction stream for all pairs of its CTA, so a CTA should carry as many
+// tracks as it takes to give every SM one CTA (4 at most: shared memory); WBX_FX_TPC overrides.
+static cudaError_t launch_effects_chain(const DSpan* spans, const DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S,
+                                        uint32_t K, uint32_t B, uint32_t C, const float* poly, float* trackbuf,
+                                        uint64_t tbs, int n_sm, cudaStream_t stream) {
+  static_assert(sizeof(FxcSmem<4>) <= 227 * 1024, "fx_chain_kernel shared memory");
+  int tpc = n_fx <= (uint32_t)n_sm ? 1 : (n_fx <= 2u * (uint32_t)n_sm ? 2 : 4);
+  if (const char* env = getenv("WBX_FX_TPC")) {
     const int v = atoi(env);
-    if (v == 1 || v == 2 || v == 4 || v == 8) P = v;
+    if (v == 1 || v == 2 || v == 4) tpc = v;
   }
-  if (const char* env = getenv("WBX_FX_TEAM")) {
-    const int v = atoi(env);
-    if (v >= 1 && v <= 3) T = v;
+  switch (tpc) {
+    case 1: return launch_effects_chain_t<1>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, stream);
+    case 2: return launch_effects_chain_t<2>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, stream);
+    default: return launch_effects_chain_t<4>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, stream);
   }
-#define WBX_FX_CASE(PP)                                                                                \
-  case PP:                                                                                             \
-    return T == 3   ? launch_effects_p<PP, 3>(fx, n_fx, C, frames, trackbuf, stream)                   \
-           : T == 2 ? launch_effects_p<PP, 2>(fx, n_fx, C, frames, trackbuf, stream)                   \
-                    : launch_effects_p<PP, 1>(fx, n_fx, C, frames, trackbuf, stream);
-  switch (P) {
-    WBX_FX_CASE(1)
-    WBX_FX_CASE(2)
-    WBX_FX_CASE(4)
-    default: return T == 3   ? launch_effects_p<8, 3>(fx, n_fx, C, frames, trackbuf, stream)
-                    : T == 2 ? launch_effects_p<8, 2>(fx, n_fx, C, frames, trackbuf, stream)
-                             : launch_effects_p<8, 1>(fx, n_fx, C, frames, trackbuf, stream);
-  }
-#undef WBX_FX_CASE
 }
 
 // ---- convolution reverb (extension, cfg 5): direct form on the CUDA cores --------------------------------
 // xin  [n_fx][C][H + T] planar: H = taps - 1 history frames (oldest first) followed by this render's T chain outputs
 // hist [n_tracks][2][H] persists across renders (indexed by track, so it survives chain list rebuilds)
 __global__ void fir_gather_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T,
-                                  const float* __restrict__ hist, const float* __restrict__ trackbuf,
+                                  const float* __restrict__ hist, const float* __restrict__ trackbuf, uint64_t tbs,
                                   float* __restrict__ xin) {
   const uint32_t ec = blockIdx.y;
   const uint32_t e = ec / C, c = ec % C;
   if (!fx[e].reverb_on) return;
   const float* h = hist + ((size_t)fx[e].track * 2 + c) * H;
-  const float* tb = trackbuf + (size_t)e * T * 2 + c;
+  const float* tb = trackbuf + (size_t)e * tbs * 2 + c;
   float* x = xin + (size_t)ec * (H + T);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H + T; i += (uint64_t)gridDim.x * blockDim.x)
     x[i] = i < H ? h[i] : tb[(i - H) * 2];
@@ -1428,7 +1601,7 @@ __global__ void fir_gather_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uin
 // 256 consecutive outputs of one (track, channel) per CTA; taps in tiles of 256 staged in shared memory
 __global__ void __launch_bounds__(256) fir_kernel(const DFx* __restrict__ fx, uint32_t C, uint64_t H, uint64_t T,
                                                    const float* __restrict__ ir, uint32_t L,
-                                                   const float* __restrict__ xin, float* __restrict__ trackbuf) {
+                                                   const float* __restrict__ xin, float* __restrict__ trackbuf, uint64_t tbs) {
   __shared__ __align__(16) float hs[256];
   __shared__ float xs[512];
   const uint32_t ec = blockIdx.y;
@@ -1458,7 +1631,7 @@ __global__ void __launch_bounds__(256) fir_kernel(const DFx* __restrict__ fx, ui
     total += (double)part;
   }
   const int64_t n = n0 + tid;
-  if (n < (int64_t)T) trackbuf[((size_t)e * T + n) * 2 + c] = (float)total;
+  if (n < (int64_t)T) trackbuf[((size_t)e * tbs + n) * 2 + c] = (float)total;
 }
 
 __global__ void fir_save_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T,
@@ -1870,31 +2043,34 @@ cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, ui
 }
 
 cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T, uint32_t L, void* tiles,
-                          const float* xin, void* planes, float* trackbuf, cudaStream_t stream);  // wbx_fir_tc.cu
+                          const float* xin, void* planes, float* trackbuf, uint64_t tbs, cudaStream_t stream);  // wbx_fir_tc.cu
 
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
                            float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, const float* poly,
-                           cudaStream_t stream) {
+                           uint32_t fx_flags, uint32_t* sm_arrivals, uint64_t tbs, cudaStream_t stream) {
   if (n_fx == 0) return cudaSuccess;
   const uint64_t warps = (uint64_t)n_fx * K;
-  render_tracks_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf);
-  {
+  // chains with an EQ or a compressor: render + chain fused and time-parallel (fx_chain_kernel); chains that only end in
+  // the reverb: the plain render of the track
+  if (fx_flags & 2u)
+    render_tracks_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs);
+  if (fx_flags & 1u) {
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t err = launch_effects_chain(fx, n_fx, C, (uint64_t)K * B, trackbuf, n_sm, stream);
+    cudaError_t err = launch_effects_chain(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, n_sm, stream);
     if (err != cudaSuccess) return err;
   }
   if (L && ir && fir_hist && fir_in) {  // convolution reverb as the chain's last stage
     const uint64_t T = (uint64_t)K * B, H = L - 1;
     const dim3 gcopy((unsigned)(((H + T) + 255) / 256 < 4096 ? ((H + T) + 255) / 256 : 4096), n_fx * C);
-    fir_gather_kernel<<<gcopy, 256, 0, stream>>>(fx, n_fx, C, H, T, fir_hist, trackbuf, fir_in);
+    fir_gather_kernel<<<gcopy, 256, 0, stream>>>(fx, n_fx, C, H, T, fir_hist, trackbuf, tbs, fir_in);
     if (tc_tiles && tc_planes) {  // tensor-core path (wbx_fir_tc.cu)
-      cudaError_t err = launch_fir_tc(fx, n_fx, C, H, T, L, tc_tiles, fir_in, tc_planes, trackbuf, stream);
+      cudaError_t err = launch_fir_tc(fx, n_fx, C, H, T, L, tc_tiles, fir_in, tc_planes, trackbuf, tbs, stream);
       if (err != cudaSuccess) return err;
     } else {
-      fir_kernel<<<dim3((unsigned)((T + 255) / 256), n_fx * C), 256, 0, stream>>>(fx, C, H, T, ir, L, fir_in, trackbuf);
+      fir_kernel<<<dim3((unsigned)((T + 255) / 256), n_fx * C), 256, 0, stream>>>(fx, C, H, T, ir, L, fir_in, trackbuf, tbs);
     }
     if (H) fir_save_kernel<<<dim3((unsigned)((H + 255) / 256 < 1024 ? (H + 255) / 256 : 1024), n_fx * C), 256, 0, stream>>>(
         fx, n_fx, C, H, T, fir_in, fir_hist);
