@@ -67,7 +67,7 @@ int main(int argc, char** argv) {
     }
     for (int c = 0; c < 2; c++) realtime[c].insert(realtime[c].end(), output.channel_buffers[c], output.channel_buffers[c] + B);
   }
-  const float level0 = engine.tracks[0]->level[0];
+  const float level0 = engine.tracks[0]->level[0].peek();
 
   // offline bounce of the same range: one launch for all callbacks
   engine.stop();

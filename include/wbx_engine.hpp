@@ -8,14 +8,109 @@
 // (engine/audio_io_pulseaudio.cpp:411, engine/audio_io_wasapi.cpp:708) a wbx::Engine can be called with the
 // same wb::AudioBuffer<float> objects: process() is a template over any buffer type that exposes
 // `n_samples`, `n_channels` and `channel_buffers` (core/audio_buffer.h:19-23).
+//
+// Threading contract — the reference's, kept:
+//   * ONE audio thread calls process() / render(); it holds Engine::editor_lock — a yield-spinning lock
+//     (core/thread.h:11-35) — for the whole callback (engine/engine.cpp:1587,1651);
+//   * ONE UI thread edits: every Engine method that changes tracks, clips, transport or configuration takes the same
+//     lock (engine.h:89-94; e.g. engine.cpp:204-206, 301), so an edit lands between two callbacks;
+//   * Track::set_volume / set_pan / set_mute bypass the lock: they push a message into the track's lock-free
+//     single-producer / single-consumer ring (core/queue.h:142-196, capacity 64, engine/track.cpp:23) that the audio
+//     thread drains at the start of the next callback (track.cpp:773-779); a full ring makes the producer yield;
+//   * VU levels go back through std::atomic<float>: the audio thread raises them with a CAS-max, the UI takes them
+//     with exchange(0) (engine/vu_meter.h:17-40);
+//   * the load meter (core/timing.h:54-67, engine.cpp:1577,1653) is an atomic<double> EMA the UI may read at any time.
 #pragma once
+#include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "wbx.h"
 
 namespace wbx {
+
+// core/thread.h:11-35
+struct Spinlock {
+  std::atomic<bool> lock_{false};
+  bool try_lock() noexcept { return !lock_.load(std::memory_order_relaxed) && !lock_.exchange(true, std::memory_order_acquire); }
+  void lock() noexcept {
+    for (;;) {
+      if (!lock_.exchange(true, std::memory_order_acquire)) return;
+      while (lock_.load(std::memory_order_relaxed)) std::this_thread::yield();
+    }
+  }
+  void unlock() noexcept { lock_.store(false, std::memory_order_release); }
+};
+struct SpinGuard {
+  Spinlock& l;
+  explicit SpinGuard(Spinlock& lock) : l(lock) { l.lock(); }
+  ~SpinGuard() { l.unlock(); }
+  SpinGuard(const SpinGuard&) = delete;
+  SpinGuard& operator=(const SpinGuard&) = delete;
+};
+
+// core/queue.h:142-196 (ConcurrentRingBuffer): one producer thread, one consumer thread, no lock. One slot stays empty,
+// so CAP - 1 messages fit; push() yields while the ring is full, like the reference's.
+template <class T, uint32_t CAP>
+struct SpscRing {
+  static_assert(CAP >= 2, "capacity");
+  alignas(64) std::atomic<uint32_t> write_pos_{0};
+  alignas(64) std::atomic<uint32_t> read_pos_{0};
+  T data_[CAP];
+  bool try_push(const T& v) noexcept {
+    const uint32_t w = write_pos_.load(std::memory_order_relaxed);
+    const uint32_t r = read_pos_.load(std::memory_order_acquire);
+    const uint32_t nw = (w + 1) % CAP;
+    if (nw == r) return false;
+    data_[w] = v;
+    write_pos_.store(nw, std::memory_order_release);
+    return true;
+  }
+  void push(const T& v) noexcept {
+    while (!try_push(v)) std::this_thread::yield();
+  }
+  bool pop(T& v) noexcept {
+    const uint32_t w = write_pos_.load(std::memory_order_acquire);
+    const uint32_t r = read_pos_.load(std::memory_order_relaxed);
+    if (w == r) return false;
+    v = data_[r];
+    read_pos_.store((r + 1) % CAP, std::memory_order_release);
+    return true;
+  }
+  bool empty() const noexcept {  // consumer side
+    return write_pos_.load(std::memory_order_acquire) == read_pos_.load(std::memory_order_relaxed);
+  }
+};
+
+// engine/vu_meter.h:17-40: the level only rises until the UI takes it
+struct VULevel {
+  std::atomic<float> level{0.0f};
+  void push(float new_level) noexcept {  // audio thread
+    float old_level = level.load(std::memory_order_relaxed);
+    while (old_level < new_level &&
+           !level.compare_exchange_weak(old_level, new_level, std::memory_order_release, std::memory_order_relaxed)) {
+    }
+  }
+  float take() noexcept { return level.exchange(0.0f, std::memory_order_acq_rel); }  // UI thread (VUMeter::update)
+  float peek() const noexcept { return level.load(std::memory_order_acquire); }
+};
+
+// core/timing.h:54-67: EMA (alpha = 0.25) of callback time / buffer time, shown by the UI as the engine load
+struct PerformanceMeasurer {
+  std::atomic<double> usage{0.0};
+  void update(double duration, double target_duration) noexcept {
+    const double percentage = duration / target_duration;
+    const double old_usage = usage.load(std::memory_order_relaxed);
+    usage.store(old_usage + 0.25 * (percentage - old_usage), std::memory_order_release);
+  }
+  double get_usage() const noexcept {
+    const double u = usage.load(std::memory_order_acquire);
+    return u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+  }
+};
 
 // (mute ? 0 : volume) and pan law, engine/track.h:46-53
 struct TrackParameterState {
@@ -79,14 +174,22 @@ struct Track {
     uint32_t id;
     double value;
   };
-  std::vector<Msg> track_msg_queue;  // UI -> audio parameter messages (engine/track.h:131)
-  float level[2] = {0, 0};           // VUMeter::level (engine/vu_meter.h:17): max since last read
+  SpscRing<Msg, 64> track_msg_queue;  // UI -> audio parameter messages (engine/track.h:131, capacity track.cpp:23)
+  VULevel level[2];                   // VUMeter::level (engine/vu_meter.h:17): max since the UI last took it
   int32_t open_run = -1;             // index of this track's extendable run in the segment list
   // built-in effect chain (extension, see wbx.h): applied on the device between the clips and volume/pan
   wbx_effect_params effect_params{};
   bool effects_on = false, effects_dirty = false;
-  void set_effects(const wbx_effect_params* params);  // nullptr removes the chain
+  // nullptr removes the chain. Not a message: call it under Engine::edit_lock() (Engine::set_track_effects does).
+  void set_effects(const wbx_effect_params* params);
+  // A plugin in the track's slot (engine/track.h:124). In the reference Track::process then points its write buffer at
+  // the plugin's effect_buffer (track.cpp:600): the plugin runs BEFORE the clips are rendered, on an empty input, the
+  // clips are rendered into effect_buffer afterwards and never reach the mix (track.cpp:645-724) — a track with a plugin
+  // contributes only what the plugin itself writes. The slot here holds no third-party code: has_plugin reproduces the
+  // reference's behaviour for a plugin that outputs silence (the sampler state still advances, the clips are dropped).
+  bool has_plugin = false;
   ~Track();
+  // UI thread, lock-free: messages the audio thread applies at its next callback
   void set_volume(float db);  // engine/track.cpp:47-57
   void set_pan(float pan);    // :59-68
   void set_mute(bool mute);   // :70-79
@@ -102,6 +205,15 @@ class Engine {
   bool ok() const { return dev_ != nullptr; }
   const char* last_error() const;
 
+  // Held by the audio thread for a whole callback and by every edit below (engine.h:89-94); UI code that touches
+  // tracks / clips directly brackets it with edit_lock() / edit_unlock().
+  Spinlock editor_lock;
+  void edit_lock() { editor_lock.lock(); }
+  void edit_unlock() { editor_lock.unlock(); }
+  // engine load as the reference's control bar shows it (core/timing.h:54-67): callback time / buffer time, EMA
+  PerformanceMeasurer perf_measurer;
+  double cpu_usage() const { return perf_measurer.get_usage(); }
+
   // engine/engine.cpp:43-57, :24-30, :32-41
   int set_audio_channel_config(uint32_t input_channels, uint32_t output_channels, uint32_t buffer_size,
                                uint32_t sample_rate);
@@ -113,6 +225,10 @@ class Engine {
   // leaves, the bus summation order changes, every other track is muted / unmuted, a clip's gain changes (the playing
   // voice reads it every callback, track.cpp:676,716)
   int delete_track(uint32_t slot);
+  int set_track_effects(Track* track, const wbx_effect_params* params);  // Track::set_effects under the editor lock
+  // Engine::add_plugin_to_track / delete_plugin_from_track (engine.cpp:1466-1538) reduced to the slot's effect on the
+  // mix (see Track::has_plugin)
+  int set_track_plugin(Track* track, bool present);
   int move_track(uint32_t from_slot, uint32_t to_slot);
   int solo_track(uint32_t slot);
   int set_clip_gain(Track* track, uint32_t clip_id, float gain);
@@ -178,6 +294,8 @@ class Engine {
   void track_block(Track& t, uint32_t track_index, uint32_t block, double sample_rate, double beat_duration,
                    double start_time, double end_time, double block_sample_position, bool currently_playing);
   int prepare(uint32_t n_blocks, double sample_rate);
+  int schedule_locked(uint32_t n_blocks, double sample_rate);
+  void meter(std::chrono::steady_clock::time_point t0, uint32_t n_blocks);
   void reindex_effects();
   void merge_levels();
   uint32_t quiet_blocks(const Track& t, uint32_t k, uint32_t K) const;

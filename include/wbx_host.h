@@ -5,6 +5,9 @@
  *   Engine::add_audio_clip (engine.cpp:293), Engine::set_playhead_position (:32), play (:68), stop (:82),
  *   Engine::process (:1576) — here wbxh_render(n_blocks = 1) — and the batched n_blocks > 1 form.
  * All sample work runs in the CUDA engine (wbx.h); there is no CPU render path.
+ * Threads: one audio thread (wbxh_render*, wbxh_schedule) and one UI thread (everything else) may run concurrently —
+ * edits and renders serialise on the engine's editor lock, parameter setters and wbxh_level are lock-free
+ * (include/wbx_engine.hpp, "Threading contract").
  */
 #ifndef WBX_HOST_H
 #define WBX_HOST_H
@@ -26,9 +29,19 @@ const char* wbxh_last_error(wbxh_engine* h);
 wbx_engine* wbxh_device(wbxh_engine* h); /* the underlying device engine (wbx.h) */
 
 int wbxh_add_track(wbxh_engine* h, float volume_db, float pan, int mute); /* returns the track index */
-void wbxh_set_volume(wbxh_engine* h, int track, float db);
-void wbxh_set_pan(wbxh_engine* h, int track, float pan);
-void wbxh_set_mute(wbxh_engine* h, int track, int mute);
+/* Track::set_volume / set_pan / set_mute (engine/track.cpp:47-79): lock-free messages to the audio thread, may be called
+ * from the UI thread while another thread renders; WBX_ERR_INVALID for a bad track index. */
+int wbxh_set_volume(wbxh_engine* h, int track, float db);
+int wbxh_set_pan(wbxh_engine* h, int track, float pan);
+int wbxh_set_mute(wbxh_engine* h, int track, int mute);
+/* A plugin in the track's slot (engine/track.h:124): the reference then renders the clips into the plugin's effect buffer
+ * and never mixes them (track.cpp:600,645-724), so the track contributes only the plugin's own output — silence here. */
+int wbxh_set_plugin(wbxh_engine* h, int track, int present);
+/* Engine::set_audio_channel_config again (config.cpp:198-232: device change / removal): new block size / rate / channel
+ * count; tracks, clips, resident samples and the transport persist. */
+int wbxh_configure(wbxh_engine* h, uint32_t out_channels, uint32_t block_frames, uint32_t sample_rate);
+/* Engine load (core/timing.h:54-67): EMA of render wall time / rendered audio time, clamped to [0, 1]. */
+double wbxh_cpu_usage(wbxh_engine* h);
 /* returns the sample id (>= 0) or a negative wbx_status */
 int wbxh_add_sample(wbxh_engine* h, int format, uint32_t channels, uint64_t frames, uint32_t sample_rate,
                     const void* const* planar);

@@ -21,6 +21,7 @@ using namespace wb;
 
 namespace wb {
 void* wbref_buffer_memory(GPUBuffer* b);  // ref_stubs.cpp: host memory behind a buffer of the stand-in renderer
+void wbref_enable_null_plugin(bool on);   // ref_stubs.cpp: pm_open_plugin then returns a plugin that does nothing
 }
 
 struct wbo_session {
@@ -65,6 +66,29 @@ int wbo_add_track(wbo_session* s, float volume_db, float pan, int mute) {
 }
 
 void wbo_set_bpm(wbo_session* s, double bpm) { s->engine.set_bpm(bpm); }
+// Engine::add_plugin_to_track / delete_plugin_from_track (engine.cpp:1466-1551) with the no-op plugin of ref_stubs.cpp
+int wbo_set_plugin(wbo_session* s, int track, int present) {
+  Track* t = s->engine.tracks[track];
+  if (present) {
+    wbref_enable_null_plugin(true);
+    PluginUID uid = {};
+    PluginInterface* p = s->engine.add_plugin_to_track(t, uid);
+    wbref_enable_null_plugin(false);
+    return p ? 0 : -1;
+  }
+  s->engine.delete_plugin_from_track(t);
+  return 0;
+}
+// Engine::set_audio_channel_config again (config.cpp:198-232: the audio device changed under a running session)
+int wbo_reconfigure(wbo_session* s, uint32_t out_channels, uint32_t block, uint32_t rate) {
+  s->engine.set_audio_channel_config(0, out_channels, block, rate);
+  s->out_channels = out_channels;
+  s->block = block;
+  s->rate = rate;
+  s->out.resize(block);
+  s->out.resize_channel(out_channels);
+  return 0;
+}
 void wbo_set_volume(wbo_session* s, int track, float db) { s->engine.tracks[track]->set_volume(db); }
 void wbo_set_pan(wbo_session* s, int track, float pan) { s->engine.tracks[track]->set_pan(pan); }
 void wbo_set_mute(wbo_session* s, int track, int mute) { s->engine.tracks[track]->set_mute(mute != 0); }

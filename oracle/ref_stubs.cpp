@@ -97,8 +97,43 @@ GPURenderer* g_renderer = &g_host_renderer;
 void* wbref_buffer_memory(GPUBuffer* b) { return static_cast<HostBuffer*>(b)->mem; }
 
 // --- plughost / midi file stand-ins ----------------------------------------------------------------------
-PluginInterface* pm_open_plugin(PluginUID) { return nullptr; }
-void pm_close_plugin(PluginInterface*) {}
+// A plugin that is valid and does nothing: process() leaves the track's mixing buffer as Engine::process cleared it, which
+// is all it takes to pin what a plugin's PRESENCE does to the path (Track::process, track.cpp:600,645-724: the clips are
+// rendered into effect_buffer and never mixed). pm_open_plugin returns one once wbref_enable_null_plugin(1) was called.
+PluginInterface::PluginInterface(uint64_t module_hash, PluginFormat format) : module_hash(module_hash), format(format) {}
+PluginResult PluginInterface::render_ui() { return PluginResult::Ok; }
+namespace {
+struct NullPlugin final : PluginInterface {
+  NullPlugin() : PluginInterface(0, PluginFormat::Native) { is_plugin_valid = true; }
+  PluginResult init() override { return PluginResult::Ok; }
+  PluginResult shutdown() override { return PluginResult::Ok; }
+  uint32_t get_param_count() const override { return 0; }
+  uint32_t get_audio_bus_count(bool) const override { return 0; }
+  uint32_t get_event_bus_count(bool) const override { return 0; }
+  uint32_t get_latency_samples() const override { return 0; }
+  uint32_t get_tail_samples() const override { return 0; }
+  const char* get_name() const override { return "null"; }
+  PluginResult get_plugin_param_info(uint32_t, PluginParamInfo*) const override { return PluginResult::Unsupported; }
+  PluginResult get_audio_bus_info(bool, uint32_t, PluginAudioBusInfo*) const override { return PluginResult::Unsupported; }
+  PluginResult get_event_bus_info(bool, uint32_t, PluginEventBusInfo*) const override { return PluginResult::Unsupported; }
+  PluginResult activate_audio_bus(bool, uint32_t, bool) override { return PluginResult::Ok; }
+  PluginResult activate_event_bus(bool, uint32_t, bool) override { return PluginResult::Ok; }
+  PluginResult init_processing(PluginProcessingMode, uint32_t, double) override { return PluginResult::Ok; }
+  PluginResult start_processing() override { return PluginResult::Ok; }
+  PluginResult stop_processing() override { return PluginResult::Ok; }
+  void transfer_param(uint32_t, double) override {}
+  PluginResult process(PluginProcessInfo&) override { return PluginResult::Ok; }
+  bool has_view() const override { return false; }
+  bool has_window_attached() const override { return false; }
+  PluginResult get_view_size(uint32_t*, uint32_t*) const override { return PluginResult::Unsupported; }
+  PluginResult attach_window(SDL_Window*) override { return PluginResult::Unsupported; }
+  PluginResult detach_window() override { return PluginResult::Ok; }
+};
+bool g_null_plugin = false;
+}  // namespace
+void wbref_enable_null_plugin(bool on) { g_null_plugin = on; }
+PluginInterface* pm_open_plugin(PluginUID) { return g_null_plugin ? new NullPlugin() : nullptr; }
+void pm_close_plugin(PluginInterface* p) { delete p; }
 bool load_notes_from_file(MidiNoteBuffer&, const std::filesystem::path&) { return false; }
 
 }  // namespace wb

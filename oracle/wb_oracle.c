@@ -85,6 +85,7 @@ typedef struct {
   o_clip** clips;
   uint32_t n_clips, cap_clips;
   int ui_solo;        /* TrackParameterState::solo of ui_parameter_state (track.h:52, UI only) */
+  int has_plugin;     /* Track::plugin_instance != nullptr (track.h:124), for a plugin that writes nothing */
   o_clip** graveyard; /* clips trimmed away by later edits */
   uint32_t n_grave, cap_grave;
   o_fx fx;
@@ -176,6 +177,23 @@ wbo_session* wbo_create(uint32_t out_channels, uint32_t block_frames, uint32_t s
   s->mixing = alloc_planar(out_channels, block_frames);
   s->out = alloc_planar(out_channels, block_frames);
   return s;
+}
+
+/* Engine::set_audio_channel_config again (engine.cpp:43-57): only the buffer shapes and the numbers process() is called
+ * with change; tracks, clips, transport and the running voices' sampler state persist. */
+int wbo_reconfigure(wbo_session* s, uint32_t out_channels, uint32_t block_frames, uint32_t sample_rate) {
+  for (uint32_t c = 0; c < s->C; c++) {
+    free(s->mixing[c]);
+    free(s->out[c]);
+  }
+  free(s->mixing);
+  free(s->out);
+  s->C = out_channels;
+  s->B = block_frames;
+  s->rate = sample_rate;
+  s->mixing = alloc_planar(out_channels, block_frames);
+  s->out = alloc_planar(out_channels, block_frames);
+  return 0;
 }
 
 static void track_free(o_track* tr) {
@@ -478,6 +496,11 @@ static void add_to_cliplist(wbo_session* s, o_track* tr, o_clip* c) {
 }
 
 void wbo_set_bpm(wbo_session* s, double bpm) { s->beat_duration = 60.0 / bpm; } /* engine.cpp:24-30 */
+
+int wbo_set_plugin(wbo_session* s, int track, int present) { /* engine.cpp:1466-1551 */
+  s->tracks[track]->has_plugin = present != 0;
+  return 0;
+}
 
 /* Engine::set_clip_gain (engine.cpp:1460-1464) */
 int wbo_set_clip_gain(wbo_session* s, int track, int clip, float gain) {
@@ -1467,6 +1490,11 @@ static void track_process(wbo_session* s, o_track* tr, float** out, double sampl
       }
     }
   }
+
+  /* A plugin in the slot: write_buffer was effect_buffer (:600), i.e. the clips above never reach output_buffer, which
+   * holds what the plugin wrote (:645-662) — nothing, for the no-op plugin the reference is pinned with. */
+  if (tr->has_plugin)
+    for (uint32_t c = 0; c < s->C; c++) memset(out[c], 0, B * sizeof(float));
 
   /* dsp::apply_gain (dsp/dsp_ops.h:27-31) + VUMeter::push_samples (engine/vu_meter.h:20-30), :728-733.
    * pan_coeffs has two entries, so C <= 2 (track.h:50). */

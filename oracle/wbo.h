@@ -93,6 +93,14 @@ typedef struct wbo_effects {
   int reverb_on;       /* 1: convolve the chain's output with the session's impulse response (BASELINE cfg 5) */
 } wbo_effects;
 int wbo_set_effects(wbo_session*, int track, const wbo_effects* fx); /* port only; libwbref.so returns -1 */
+/* A plugin in the track's slot (Engine::add_plugin_to_track / delete_plugin_from_track, engine/engine.cpp:1466-1551).
+ * libwbref.so attaches a plugin that does nothing: what is pinned is the effect of a plugin's PRESENCE on the path —
+ * Track::process then renders the clips into effect_buffer and never mixes them (track.cpp:600,645-724). */
+int wbo_set_plugin(wbo_session*, int track, int present);
+/* Engine::set_audio_channel_config again on a live session (config.cpp:198-232: device change / removal). */
+int wbo_reconfigure(wbo_session*, uint32_t out_channels, uint32_t block_frames, uint32_t sample_rate);
+/* port only: 0 = the chain's specification (time-parallel association), 1 = textbook f32, 2 = textbook f64 */
+void wbo_set_fx_textbook(int mode);
 /* Convolution reverb — EXTENSION, PARITY UNPINNED: one impulse response h[0..n_taps) per session, applied as the
  * last stage of a track's chain: y[n] = (float) sum_k (double)h[k] * (double)x[n - k], k ascending, accumulated in
  * f64 (the ground truth a tensor-core or f32 implementation is held to within 1e-5 of the block peak); x before

@@ -53,6 +53,8 @@ def _load(path):
     lib.wbo_delete_region.argtypes = [vp, i32, dbl, dbl]
     lib.wbo_set_effects.argtypes = [vp, i32, vp]
     lib.wbo_set_resampler.argtypes = [vp, i32]
+    lib.wbo_set_plugin.argtypes = [vp, i32, i32]
+    lib.wbo_reconfigure.argtypes = [vp, u32, u32, u32]
     lib.wbo_set_impulse_response.argtypes = [vp, vp, u32]
     lib.wbo_set_playhead.argtypes = [vp, dbl]
     lib.wbo_play.argtypes = [vp]
@@ -188,6 +190,13 @@ class Session:
 
     def set_resampler(self, mode):
         self.lib.wbo_set_resampler(self.h, mode)
+
+    def set_plugin(self, track, present=True):
+        assert self.lib.wbo_set_plugin(self.h, track, int(present)) == 0
+
+    def configure(self, out_channels, block, rate):
+        assert self.lib.wbo_reconfigure(self.h, out_channels, block, rate) == 0
+        self.C, self.B, self.rate = out_channels, block, rate
 
     def set_playhead(self, beat):
         self.lib.wbo_set_playhead(self.h, beat)

@@ -738,5 +738,63 @@ def mip_source(fmt, frames, ch):
 
 EXT = dict(fades=fades, effects=effects, reverb=reverb, polyphase=polyphase)  # builder-specified extensions: checked against the C port only
 
+def plugin_silences(make_engine):
+    """SURVEY 8 a11: a plugin in a track's slot (engine/track.h:124). Track::process then renders the clips into the
+    plugin's effect_buffer, which is never mixed (track.cpp:600,645-724): the track contributes only what the plugin
+    writes — nothing for the no-op plugin the compiled reference is driven with — while its scheduler and sampler keep
+    running, so the clip is where it should be when the plugin is removed again."""
+    rng = np.random.RandomState(1111)
+    B, rate = 128, 48000
+    eng = make_engine(2, B, rate, 120.0)
+    spb = rate * 0.5
+    for t in range(5):
+        eng.add_track(-3.0 - t, -0.7 + 0.35 * t, False)
+        sid = eng.add_sample(_src(rng, 2, 5000, 3), 44100 if t == 3 else 48000, FMT_F32)
+        eng.add_clip(t, sid, (30.0 * t) / spb, 2600.0 / spb, 2.0 * t, 1.0, 0.6 + 0.1 * t)
+    eng.set_plugin(1, True)  # before playback starts
+    eng.play()
+    outs = [eng.process(4)]
+    eng.set_plugin(3, True)  # while its (resampled) clip plays
+    outs.append(eng.process(5))
+    eng.set_plugin(1, False)  # the clip resumes where the transport is, not where it stopped being heard
+    outs.append(eng.process(5))
+    eng.set_plugin(3, False)
+    eng.set_plugin(0, True)
+    outs.append(eng.process(8))  # past the clips' ends
+    return _collect(eng, outs, 5)
+
+
+def reconfigure(make_engine):
+    """SURVEY 5 / 8b: the audio device changes under a live session (config.cpp:198-232 -> Engine::set_audio_channel_config
+    again, app.cpp:263-264): new block size, then a new sample rate and channel count, with tracks, clips, resident
+    samples, the transport and playing voices persisting."""
+    rng = np.random.RandomState(2222)
+    eng = make_engine(2, 256, 48000, 120.0)
+    for t in range(6):
+        eng.add_track(-4.0 - t, -0.9 + 0.36 * t, False)
+        sid = eng.add_sample(_src(rng, 2 if t != 2 else 1, 30000, 4, FMT_I16 if t == 4 else FMT_F32),
+                             44100 if t % 3 == 1 else 48000, FMT_I16 if t == 4 else FMT_F32)
+        eng.add_clip(t, sid, 0.01 * t, 1.2 + 0.1 * t, float(t), 1.0, 0.8)
+    eng.play()
+    parts = [eng.process(5)]
+    eng.configure(2, 96, 48000)     # smaller block, mid-playback
+    parts.append(eng.process(9))
+    eng.configure(2, 512, 44100)    # new rate: running voices keep their speed until their next event (sampler.h:18-27)
+    parts.append(eng.process(4))
+    eng.stop()
+    eng.configure(1, 200, 96000)    # mono bus, stopped
+    eng.play()
+    parts.append(eng.process(6))
+    # block sizes differ between the parts: flatten each part's arrays instead of stacking them
+    res = {}
+    for i, (o, p) in enumerate(parts):
+        res["out%d" % i] = o
+        res["peaks%d" % i] = p
+    res["sampler_offsets"] = np.array([eng.sampler_offset(t) for t in range(6)], np.float64)
+    res["transport"] = np.array([eng.sample_position(), eng.playhead()], np.float64)
+    return res
+
+
 ALL = dict(kat=kat, cfg1=cfg1, cfg2_small=cfg2_small, cfg3_small=cfg3_small, int_formats=int_formats,
-           event_split=event_split, overlaps=overlaps, edits=edits, tempo=tempo, mixer=mixer, erase=erase, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty)
+           event_split=event_split, overlaps=overlaps, edits=edits, tempo=tempo, mixer=mixer, erase=erase, params=params, hot_clamp=hot_clamp, ragged=ragged, empty=empty,
+           plugin_silences=plugin_silences, reconfigure=reconfigure)

@@ -119,6 +119,10 @@ class ScheduleOnlyEngine:
         self.n_tracks -= 1
         return self.eng.delete_track(t)
 
+    def configure(self, C, B, rate):
+        self.eng.configure(C, B, rate)
+        self.C, self.B = C, B
+
     def __getattr__(self, name):
         return getattr(self.eng, name)
 

@@ -50,9 +50,9 @@ def assert_exact(res, ref, what):
 
 def assert_tree(res, ref, what):
     for k in ref:
-        if k == "out":
-            peak = np.abs(ref["out"]).max(axis=(1, 2), keepdims=True)
-            err = np.abs(res["out"].astype(np.float64) - ref["out"].astype(np.float64))
+        if k.startswith("out"):
+            peak = np.abs(ref[k]).max(axis=(1, 2), keepdims=True)
+            err = np.abs(res[k].astype(np.float64) - ref[k].astype(np.float64))
             assert np.all(err <= TREE_TOL * np.maximum(peak, 1e-30)), "%s: tree-mode bus error %.3g of block peak" % (
                 what, float((err / np.maximum(peak, 1e-30)).max()))
         else:
@@ -723,3 +723,62 @@ def test_cpp_sharded_demo(wb, tmp_path):
     r = subprocess.run([exe, "48", "12"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "sharded == single within tolerance" in r.stdout
+
+
+# ---- threading contract of the boundary (include/wbx_engine.hpp) ------------------------------------------------
+
+def test_ui_thread_edits_while_audio_thread_renders(wb):
+    """A UI thread hammers set_volume / set_pan / set_mute (lock-free SPSC ring) and add_clip (editor lock) through the C
+    exports while this thread renders callbacks on the GPU (ctypes drops the GIL inside both). Track 0 plays a DC source
+    at pan 0, so every callback's bus reveals the volume it used: it must be one the UI wrote, never an older one than
+    the callback before (some serialised schedule), and the run must not crash or deadlock."""
+    import threading
+    B = 128
+    eng = wb.Engine(2, B, 48000, 120.0, device=0, sum_mode=wb.SUM_EXACT)
+    n_tracks = 6
+    dc = np.full((2, 1 << 20), 0.25, np.float32)
+    noise = (np.random.RandomState(5).uniform(-1, 1, (2, 1 << 16)) * 1e-3).astype(np.float32)
+    for t in range(n_tracks):
+        eng.add_track(0.0, 0.0, t != 0)  # only track 0 is audible: the others are muted (and stay so: see ui())
+        sid = eng.add_sample(dc if t == 0 else noise, 48000)
+        eng.add_clip(t, sid, 0.0, 1e6, 0.0, 1.0, 1.0)
+    n_writes = 4000
+    dbs = (-40.0 + 40.0 * np.arange(n_writes) / n_writes).astype(np.float32)
+    vols = np.array([wb.db_to_linear(float(d)) for d in dbs], np.float32)
+    written = [0]
+    stop = threading.Event()
+
+    def ui():
+        i = 0
+        while not stop.is_set() and i + 1 < n_writes:
+            i += 1
+            eng.set_volume(0, float(dbs[i]))
+            written[0] = i
+            eng.set_pan(1 + i % (n_tracks - 1), -1.0 + (i % 50) / 25.0)
+            eng.set_mute(1 + i % (n_tracks - 1), True)
+            if i % 40 == 0:
+                eng.add_clip(1 + (i // 40) % (n_tracks - 1), 1, 2.0 + 0.01 * i, 2.2 + 0.01 * i, 0.0, 1.0, 0.5)
+                eng.level(0, 0, True)
+                eng.cpu_usage()
+
+    eng.play()
+    eng.render(1)  # consumes the constructor's messages
+    th = threading.Thread(target=ui)
+    th.start()
+    last = 0
+    try:
+        for k in range(1500):
+            out, _ = eng.render(1, want_peaks=False)
+            hi = written[0]
+            v = np.float32(out[0, 0] * np.float32(4.0))  # 0.25 * volume * 1.0, exact
+            assert np.all(out[0] == out[0, 0]) and np.all(out[1] == out[0, 0]), "callback %d: not one volume" % k
+            cand = np.nonzero(vols[last:min(hi + 2, n_writes)] == v)[0]
+            assert v == np.float32(1.0) and last == 0 or len(cand), "callback %d: volume %r was never written (%d..%d)" % (k, v, last, hi)
+            if len(cand):
+                last = last + int(cand[0])
+    finally:
+        stop.set()
+        th.join()
+    assert last > 0, "the audio thread never saw a UI write"
+    assert 0.0 <= eng.cpu_usage() <= 1.0
+    eng.close()

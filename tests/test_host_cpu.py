@@ -288,3 +288,38 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+# ---- threading contract of the host engine (include/wbx_engine.hpp) under the sanitizers ---------------------------
+
+def _build_stress(tmp_path, san):
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    exe = str(tmp_path / ("thread_stress_" + san.split(",")[0]))
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=" + san, "-ffp-contract=off", "-D__align__(n)=alignas(n)",
+           "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "thread_stress.cpp"),
+           os.path.join(root, "whitebox_b200", "csrc", "wbx_host.cpp"), "-o", exe, "-lpthread"]
+    if san != "thread":
+        cmd.insert(5, "-fno-sanitize-recover=undefined")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("sanitizer runtime not available: " + r.stderr[:200])
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+@pytest.mark.parametrize("san", ["thread", "address,undefined"])
+def test_threading_contract_under_sanitizers(tmp_path, san):
+    """SPSC parameter ring (core/queue.h:142-196), atomic VU levels (vu_meter.h:17-40), editor lock across callbacks and
+    edits (engine.cpp:1587,1651), load meter (timing.h:54-67): a UI thread hammering set_volume / set_pan / set_mute /
+    add_audio_clip / set_bpm / set_track_effects while the audio thread runs >= 10^4 callbacks is ThreadSanitizer-clean
+    (and ASan/UBSan-clean) on wbx_host.cpp, and every callback uses a volume of some serialised schedule."""
+    import subprocess
+    exe = _build_stress(tmp_path, san)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66", ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1")
+    r = subprocess.run([exe, "10000", "20000"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "errors 0" in r.stdout

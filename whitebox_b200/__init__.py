@@ -71,7 +71,8 @@ WBXH_SYMBOLS = [
     "wbxh_sample_position", "wbxh_playhead", "wbxh_level", "wbxh_panning_coefs", "wbxh_db_to_linear",
     "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_clip_range", "wbxh_set_bpm", "wbxh_delete_track", "wbxh_move_track", "wbxh_solo_track",
     "wbxh_set_clip_gain", "wbxh_move_clip",
-    "wbxh_resize_clip", "wbxh_delete_clip", "wbxh_duplicate_clip", "wbxh_delete_region",
+    "wbxh_resize_clip", "wbxh_delete_clip", "wbxh_duplicate_clip", "wbxh_delete_region", "wbxh_set_plugin", "wbxh_configure",
+    "wbxh_cpu_usage",
 ]
 
 _lib = None
@@ -147,9 +148,11 @@ def lib():
     L.wbxh_add_track.argtypes = [vp, flt, flt, i32]
     for f in ("wbxh_set_volume", "wbxh_set_pan"):
         getattr(L, f).argtypes = [vp, i32, flt]
-        getattr(L, f).restype = None
     L.wbxh_set_mute.argtypes = [vp, i32, i32]
-    L.wbxh_set_mute.restype = None
+    L.wbxh_set_plugin.argtypes = [vp, i32, i32]
+    L.wbxh_configure.argtypes = [vp, u32, u32, u32]
+    L.wbxh_cpu_usage.argtypes = [vp]
+    L.wbxh_cpu_usage.restype = dbl
     L.wbxh_add_sample.argtypes = [vp, i32, u32, u64, u32, pp]
     L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     L.wbxh_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
@@ -466,13 +469,27 @@ class Engine:
         return self.L.wbxh_add_track(self.h, volume_db, pan, int(mute))
 
     def set_volume(self, t, db):
-        self.L.wbxh_set_volume(self.h, t, db)
+        self._ck(self.L.wbxh_set_volume(self.h, t, db))
 
     def set_pan(self, t, pan):
-        self.L.wbxh_set_pan(self.h, t, pan)
+        self._ck(self.L.wbxh_set_pan(self.h, t, pan))
 
     def set_mute(self, t, m):
-        self.L.wbxh_set_mute(self.h, t, int(m))
+        self._ck(self.L.wbxh_set_mute(self.h, t, int(m)))
+
+    def set_plugin(self, t, present=True):
+        """A plugin in the track's slot: the reference then drops the track's clip audio (engine/track.cpp:600,645-724)."""
+        self._ck(self.L.wbxh_set_plugin(self.h, t, int(present)))
+
+    def configure(self, out_channels, block, rate):
+        """Engine::set_audio_channel_config again (device change): tracks, clips, samples and transport persist."""
+        self._ck(self.L.wbxh_configure(self.h, out_channels, block, rate))
+        self.C, self.B, self.rate = out_channels, block, rate
+        if self.dev is not None:
+            self.dev.C, self.dev.B = out_channels, block
+
+    def cpu_usage(self):
+        return self.L.wbxh_cpu_usage(self.h)
 
     def add_sample(self, data, rate, fmt=FMT_F32):
         data = np.ascontiguousarray(data, dtype=_NP[fmt])

@@ -50,11 +50,11 @@ Track::~Track() {
 void Track::set_volume(float db) {
   ui_parameter_state.volume_db = db;
   ui_parameter_state.volume = db_to_linear(db);
-  track_msg_queue.push_back({kParamVolume, (double)ui_parameter_state.volume});
+  track_msg_queue.push({kParamVolume, (double)ui_parameter_state.volume});
 }
 void Track::set_pan(float pan) {
   ui_parameter_state.pan = pan;
-  track_msg_queue.push_back({kParamPan, (double)pan});
+  track_msg_queue.push({kParamPan, (double)pan});
 }
 void Track::set_effects(const wbx_effect_params* params) {
   effects_on = params != nullptr;
@@ -63,7 +63,7 @@ void Track::set_effects(const wbx_effect_params* params) {
 }
 void Track::set_mute(bool mute) {
   ui_parameter_state.mute = mute;
-  track_msg_queue.push_back({kParamMute, (double)mute});
+  track_msg_queue.push({kParamMute, (double)mute});
 }
 
 // ---- clip lookup (Track::find_next_clip, engine/track.cpp:182-213, incl. find_lower_bound's n-1 start) ----
@@ -117,6 +117,7 @@ Engine::~Engine() {
 const char* Engine::last_error() const { return dev_ ? wbx_last_error(dev_) : err_.c_str(); }
 
 int Engine::set_audio_channel_config(uint32_t, uint32_t output_channels, uint32_t buffer_size, uint32_t sample_rate) {
+  SpinGuard edit(editor_lock);
   if (!dev_ && !host_only_) return WBX_ERR_NO_DEVICE;
   if (output_channels < 1 || output_channels > 2 || buffer_size == 0 || buffer_size > 65535) return WBX_ERR_INVALID;
   if (dev_) {
@@ -129,14 +130,33 @@ int Engine::set_audio_channel_config(uint32_t, uint32_t output_channels, uint32_
   return WBX_OK;
 }
 
-void Engine::set_bpm(double bpm) { beat_duration_ = 60.0 / bpm; }
+void Engine::set_bpm(double bpm) {  // engine.cpp:24-30 (an atomic store there; the same lock as every other edit here)
+  SpinGuard edit(editor_lock);
+  beat_duration_ = 60.0 / bpm;
+}
+
+int Engine::set_track_effects(Track* track, const wbx_effect_params* params) {
+  if (!track) return WBX_ERR_INVALID;
+  SpinGuard edit(editor_lock);
+  track->set_effects(params);
+  return WBX_OK;
+}
+
+int Engine::set_track_plugin(Track* track, bool present) {
+  if (!track) return WBX_ERR_INVALID;
+  SpinGuard edit(editor_lock);
+  track->has_plugin = present;
+  return WBX_OK;
+}
 
 void Engine::set_playhead_position(double beat) {
+  SpinGuard edit(editor_lock);
   playhead_start = beat;
   playhead = beat;
 }
 
 Track* Engine::add_track(const std::string& name) {
+  SpinGuard edit(editor_lock);
   Track* t = new Track();
   t->name = name;
   // Track::Track() queues the defaults first (engine/track.cpp:22-27)
@@ -149,6 +169,7 @@ Track* Engine::add_track(const std::string& name) {
 
 // Engine::delete_track (engine/engine.cpp:209-217)
 int Engine::delete_track(uint32_t slot) {
+  SpinGuard edit(editor_lock);
   if (slot >= tracks.size()) return WBX_ERR_INVALID;
   Track* t = tracks[slot];
   tracks.erase(tracks.begin() + slot);
@@ -165,6 +186,7 @@ void Engine::reindex_effects() {
 
 // Engine::move_track (engine/engine.cpp:228-243): the track order is the bus summation order
 int Engine::move_track(uint32_t from_slot, uint32_t to_slot) {
+  SpinGuard edit(editor_lock);
   if (from_slot >= tracks.size() || to_slot >= tracks.size()) return WBX_ERR_INVALID;
   if (from_slot == to_slot) return WBX_OK;
   Track* tmp = tracks[from_slot];
@@ -179,6 +201,7 @@ int Engine::move_track(uint32_t from_slot, uint32_t to_slot) {
 
 // Engine::solo_track (engine/engine.cpp:245-262): toggles the slot's solo flag and mutes / unmutes every other track
 int Engine::solo_track(uint32_t slot) {
+  SpinGuard edit(editor_lock);
   if (slot >= tracks.size()) return WBX_ERR_INVALID;
   bool mute = false;
   if (tracks[slot]->ui_parameter_state.solo) {
@@ -198,12 +221,14 @@ int Engine::solo_track(uint32_t slot) {
 
 // Engine::set_clip_gain (engine/engine.cpp:1460-1464)
 int Engine::set_clip_gain(Track* track, uint32_t clip_id, float gain) {
+  SpinGuard edit(editor_lock);
   if (!track || clip_id >= track->clips.size()) return WBX_ERR_INVALID;
   track->clips[clip_id]->gain = gain;
   return WBX_OK;
 }
 
 int Engine::add_sample(int format, uint32_t channels, uint64_t frames, uint32_t sample_rate, const void* const* planar) {
+  SpinGuard edit(editor_lock);
   if (!dev_ && !host_only_) return WBX_ERR_NO_DEVICE;
   uint32_t id = (uint32_t)samples_.size();
   if (dev_) {
@@ -343,6 +368,7 @@ void Engine::add_to_cliplist(Track* track, AudioClip* clip) {
 // Engine::add_audio_clip (engine/engine.cpp:293-309)
 int Engine::add_audio_clip(Track* track, double min_time, double max_time, double start_offset, uint32_t sample_id,
                            double speed, float gain, double fade_start, double fade_end) {
+  SpinGuard edit(editor_lock);
   if (!track || sample_id >= samples_.size() || !(max_time >= min_time)) return WBX_ERR_INVALID;
   AudioClip* clip = new AudioClip();
   clip->min_time = min_time;
@@ -364,6 +390,7 @@ static bool owns_clip(const Track* track, const AudioClip* clip) {
 
 // Engine::duplicate_clip (engine/engine.cpp:336-344)
 int Engine::duplicate_clip(Track* track, const AudioClip* clip_to_duplicate, double min_time, double max_time) {
+  SpinGuard edit(editor_lock);
   if (!owns_clip(track, clip_to_duplicate) || !(max_time >= min_time)) return WBX_ERR_INVALID;
   AudioClip* clip = new AudioClip(*clip_to_duplicate);
   clip->deleted = clip->internal_state_changed = false;  // Clip(const Clip&) does not copy them (clip.h:92-112)
@@ -376,6 +403,7 @@ int Engine::duplicate_clip(Track* track, const AudioClip* clip_to_duplicate, dou
 // Engine::move_clip (engine/engine.cpp:346-363) + calc_move_clip (engine/clip_edit.h:10-16). A clip moved while it plays
 // is stopped and restarted at its new content offset by the next callback (internal_state_changed, track.cpp:394-419).
 int Engine::move_clip(Track* track, AudioClip* clip, double relative_pos) {
+  SpinGuard edit(editor_lock);
   if (!owns_clip(track, clip)) return WBX_ERR_INVALID;
   if (relative_pos == 0.0) return WBX_OK;
   double new_pos = clip->min_time + relative_pos;
@@ -397,6 +425,7 @@ int Engine::move_clip(Track* track, AudioClip* clip, double relative_pos) {
 // changes the clip speed so that the same content fills the new length.
 int Engine::resize_clip(Track* track, AudioClip* clip, double relative_pos, double resize_limit, double min_length,
                         bool left_side, bool shift, bool stretch) {
+  SpinGuard edit(editor_lock);
   if (!owns_clip(track, clip)) return WBX_ERR_INVALID;
   if (relative_pos == 0.0) return WBX_OK;
   const double beat_duration = beat_duration_;
@@ -471,6 +500,7 @@ int Engine::resize_clip(Track* track, AudioClip* clip, double relative_pos, doub
 // Engine::delete_region(track, min, max) (engine/engine.cpp:463-473): erase a time range — the clips it touches are
 // trimmed, split or deleted.
 int Engine::delete_region(Track* track, double min, double max) {
+  SpinGuard edit(editor_lock);
   if (!track || !(max >= min)) return WBX_ERR_INVALID;
   uint32_t first = 0, last = 0;
   if (!query_clip_by_range(*track, min, max, &first, &last)) return WBX_OK;
@@ -482,6 +512,7 @@ int Engine::delete_region(Track* track, double min, double max) {
 
 // Engine::delete_clip (engine/engine.cpp:400-407). The clip is parked in the track's graveyard (see update_clip_ordering).
 int Engine::delete_clip(Track* track, AudioClip* clip) {
+  SpinGuard edit(editor_lock);
   if (!owns_clip(track, clip)) return WBX_ERR_INVALID;
   clip->deleted = true;
   update_clip_ordering(*track);
@@ -490,17 +521,20 @@ int Engine::delete_clip(Track* track, AudioClip* clip) {
 }
 
 int Engine::set_impulse_response(const float* h, uint32_t n_taps) {
+  SpinGuard edit(editor_lock);
   if (!dev_) return WBX_ERR_NO_DEVICE;
   return wbx_set_impulse_response(dev_, h, n_taps);
 }
 
 void Engine::play() {
+  SpinGuard edit(editor_lock);
   for (auto* t : tracks) reset_playback_state(*t, playhead_start, false);
   sample_position = 0;
   playing = true;
 }
 
 void Engine::stop() {
+  SpinGuard edit(editor_lock);
   playing = false;
   playhead = playhead_start;
   for (auto* t : tracks) {  // Track::stop, engine/track.cpp:248-256
@@ -630,7 +664,9 @@ void Engine::stream(Track& t, uint32_t track_index, uint32_t block, uint32_t num
   const uint64_t clip_frame = t.clip_frame;
   t.clip_frame += num_samples;  // the clip's own timeline advances whether or not the sample still has data
   if (t.sample_offset >= count) return;  // has finished streaming: position no longer advances
-  if (num_samples != 0) {
+  // a plugin in the slot: the clip is rendered into the plugin's effect_buffer and never mixed (track.cpp:600,645-724)
+  // — no segment reaches the device, the sampler's bookkeeping below runs all the same
+  if (num_samples != 0 && !t.has_plugin) {
     bool extended = false;
     if (t.open_run >= 0 && buffer_offset == 0 && num_samples == buffer_size_) {
       wbx_segment& r = segs_[t.open_run];
@@ -666,7 +702,8 @@ void Engine::track_block(Track& t, uint32_t track_index, uint32_t block, double 
   if (currently_playing)
     process_event(t, start_time, end_time, block_sample_position, beat_duration, sample_rate, buffer_size_);
 
-  for (const auto& m : t.track_msg_queue) {  // process_track_messages + parameter application, :618-643
+  Track::Msg m;
+  while (t.track_msg_queue.pop(m)) {  // process_track_messages + parameter application, :773-779, :618-643
     switch (m.id) {
       case kParamVolume: t.parameter_state.volume = (float)m.value; break;
       case kParamPan: {
@@ -679,7 +716,6 @@ void Engine::track_block(Track& t, uint32_t track_index, uint32_t block, double 
       case kParamMute: t.parameter_state.mute = m.value > 0.0; break;
     }
   }
-  t.track_msg_queue.clear();
 
   if (!currently_playing) {
     t.open_run = -1;
@@ -769,8 +805,8 @@ void Engine::stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t
   } else {
     streamed = advance_rounded(&off, adv, q, count);  // the reference's own recurrence, one rounding per callback
   }
-  bool extended = false;
-  if (t.open_run >= 0) {
+  bool extended = t.has_plugin || streamed == 0;  // (a plugin in the slot: nothing of the clip reaches the device)
+  if (!extended && t.open_run >= 0) {
     wbx_segment& r = segs_[t.open_run];
     if (r.block + r.n_blocks == block && r.length == B && r.dst_offset == 0) {
       r.n_blocks += streamed;
@@ -797,6 +833,11 @@ void Engine::stream_run(Track& t, uint32_t track_index, uint32_t block, uint32_t
 }
 
 int Engine::schedule(uint32_t n_blocks, double sample_rate) {
+  SpinGuard edit(editor_lock);
+  return schedule_locked(n_blocks, sample_rate);
+}
+
+int Engine::schedule_locked(uint32_t n_blocks, double sample_rate) {
   if (sample_rate == 0.0) sample_rate = (double)sample_rate_;
   cur_sample_rate_ = sample_rate;
   segs_.clear();
@@ -877,7 +918,7 @@ int Engine::prepare(uint32_t n_blocks, double sample_rate) {
     if (rc) return rc;
     t.effects_dirty = false;
   }
-  return schedule(n_blocks, sample_rate);
+  return schedule_locked(n_blocks, sample_rate);
 }
 
 // VUMeter::push_samples: level only rises until the UI reads it (vu_meter.h:25-29)
@@ -885,10 +926,19 @@ void Engine::merge_levels() {
   const uint32_t N = (uint32_t)tracks.size();
   for (uint32_t i = 0; i < N; i++)
     for (uint32_t c = 0; c < 2; c++)
-      if (tracks[i]->level[c] < levels_[2 * i + c]) tracks[i]->level[c] = levels_[2 * i + c];
+      tracks[i]->level[c].push(levels_[2 * i + c]);
+}
+
+// ScopedPerformanceCounter + perf_measurer.update (engine.cpp:1577,1653): wall time of the call against the audio it made
+void Engine::meter(std::chrono::steady_clock::time_point t0, uint32_t n_blocks) {
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  const double buffer_ms = 1000.0 * (double)buffer_size_ / cur_sample_rate_ * (double)n_blocks;
+  perf_measurer.update(ms, buffer_ms);
 }
 
 int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, double sample_rate) {
+  const auto t0 = std::chrono::steady_clock::now();
+  SpinGuard edit(editor_lock);  // held for the whole callback, like Engine::process (engine.cpp:1587,1651)
   int rc = prepare(n_blocks, sample_rate);
   if (rc) return rc;
   const uint32_t N = (uint32_t)tracks.size();
@@ -899,12 +949,14 @@ int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, 
                          N ? levels_.data() : nullptr);
   if (rc) return rc;
   merge_levels();
+  meter(t0, n_blocks);
   return WBX_OK;
 }
 
 // render() in two halves for a thread that drives several sharded engines (wbx_sharded.hpp): render_begin on every
 // engine, the phases of wbx_mix_sharded_phase on every engine's device(), render_end on every engine.
 int Engine::render_begin(uint32_t n_blocks, double sample_rate) {
+  SpinGuard edit(editor_lock);
   int rc = prepare(n_blocks, sample_rate);
   if (rc) return rc;
   return wbx_submit(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n_blocks);
@@ -912,6 +964,7 @@ int Engine::render_begin(uint32_t n_blocks, double sample_rate) {
 
 int Engine::render_end(float* const* out_channels, float* peaks) {
   if (!dev_) return WBX_ERR_NO_DEVICE;
+  SpinGuard edit(editor_lock);
   const uint32_t N = (uint32_t)tracks.size();
   int rc = wbx_fetch(dev_, out_channels, peaks);
   if (rc) return rc;
@@ -965,9 +1018,35 @@ int wbxh_add_track(wbxh_engine* h, float volume_db, float pan, int mute) {
   t->set_mute(mute != 0);
   return (int)h->eng.tracks.size() - 1;
 }
-void wbxh_set_volume(wbxh_engine* h, int track, float db) { h->eng.tracks[track]->set_volume(db); }
-void wbxh_set_pan(wbxh_engine* h, int track, float pan) { h->eng.tracks[track]->set_pan(pan); }
-void wbxh_set_mute(wbxh_engine* h, int track, int mute) { h->eng.tracks[track]->set_mute(mute != 0); }
+static wbx::Track* track_at(wbxh_engine* h, int track) {
+  return (!h || track < 0 || (size_t)track >= h->eng.tracks.size()) ? nullptr : h->eng.tracks[track];
+}
+int wbxh_set_volume(wbxh_engine* h, int track, float db) {
+  wbx::Track* t = track_at(h, track);
+  if (!t) return WBX_ERR_INVALID;
+  t->set_volume(db);
+  return WBX_OK;
+}
+int wbxh_set_pan(wbxh_engine* h, int track, float pan) {
+  wbx::Track* t = track_at(h, track);
+  if (!t) return WBX_ERR_INVALID;
+  t->set_pan(pan);
+  return WBX_OK;
+}
+int wbxh_set_mute(wbxh_engine* h, int track, int mute) {
+  wbx::Track* t = track_at(h, track);
+  if (!t) return WBX_ERR_INVALID;
+  t->set_mute(mute != 0);
+  return WBX_OK;
+}
+int wbxh_set_plugin(wbxh_engine* h, int track, int present) {
+  wbx::Track* t = track_at(h, track);
+  return t ? h->eng.set_track_plugin(t, present != 0) : WBX_ERR_INVALID;
+}
+int wbxh_configure(wbxh_engine* h, uint32_t out_channels, uint32_t block_frames, uint32_t sample_rate) {
+  return h ? h->eng.set_audio_channel_config(0, out_channels, block_frames, sample_rate) : WBX_ERR_INVALID;
+}
+double wbxh_cpu_usage(wbxh_engine* h) { return h ? h->eng.cpu_usage() : 0.0; }
 int wbxh_add_sample(wbxh_engine* h, int format, uint32_t channels, uint64_t frames, uint32_t sample_rate,
                     const void* const* planar) {
   return h->eng.add_sample(format, channels, frames, sample_rate, planar);
@@ -1034,8 +1113,7 @@ int wbxh_delete_region(wbxh_engine* h, int track, double min_beat, double max_be
 
 int wbxh_set_effects(wbxh_engine* h, int track, const wbx_effect_params* params) {
   if (track < 0 || (size_t)track >= h->eng.tracks.size()) return WBX_ERR_INVALID;
-  h->eng.tracks[track]->set_effects(params);
-  return WBX_OK;
+  return h->eng.set_track_effects(h->eng.tracks[track], params);
 }
 int wbxh_set_impulse_response(wbxh_engine* h, const float* ir, uint32_t n_taps) {
   return h->eng.set_impulse_response(ir, n_taps);
@@ -1063,13 +1141,16 @@ int wbxh_schedule(wbxh_engine* h, uint32_t n_blocks, const wbx_segment** segs, u
   return rc;
 }
 
-double wbxh_sampler_offset(wbxh_engine* h, int track) { return h->eng.tracks[track]->sample_offset; }
+double wbxh_sampler_offset(wbxh_engine* h, int track) {
+  wbx::Track* t = track_at(h, track);
+  return t ? t->sample_offset : 0.0;
+}
 double wbxh_sample_position(wbxh_engine* h) { return h->eng.sample_position; }
 double wbxh_playhead(wbxh_engine* h) { return h->eng.playhead; }
 float wbxh_level(wbxh_engine* h, int track, int channel, int reset) {
-  float v = h->eng.tracks[track]->level[channel];
-  if (reset) h->eng.tracks[track]->level[channel] = 0.0f;
-  return v;
+  wbx::Track* t = track_at(h, track);
+  if (!t || channel < 0 || channel > 1) return 0.0f;
+  return reset ? t->level[channel].take() : t->level[channel].peek();  // VUMeter::update's exchange(0) (vu_meter.h:32-40)
 }
 uint32_t wbxh_advance_rounded(double* off, double adv, uint32_t n, double limit) {
   return wbx::advance_rounded(off, adv, n, limit);

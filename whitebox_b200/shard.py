@@ -140,6 +140,23 @@ class ShardedEngine:
         e, i = self._track(t)
         e.set_clip_gain(i, clip, gain)
 
+    def set_plugin(self, t, present=True):
+        e, i = self._track(t)
+        e.set_plugin(i, present)
+
+    def configure(self, out_channels, block, rate):
+        """Engine::set_audio_channel_config again: every shard is reconfigured and the exchange (whose buffers are sized by
+        block and channel count) is set up anew; tracks, clips, resident samples and the transport persist."""
+        for e in self.shards:
+            e.dev.shard_close()
+            e.configure(out_channels, block, rate)
+        self.C, self.B, self.rate = out_channels, block, rate
+        for r, e in enumerate(self.shards):
+            e.dev.shard_init(r, self.W, self.max_blocks)
+        devs = [e.dev for e in self.shards]
+        for e in self.shards:
+            e.dev.shard_connect_local(devs)
+
     def delete_track(self, t):
         """Engine::delete_track: the track leaves its shard; later tracks of that shard move down one local slot."""
         s, i = self.tracks.pop(t)
