@@ -16,6 +16,9 @@
 #include "gfx/renderer.h"
 #include "gfx/waveform_visual.h"
 #include "wbo.h"
+#ifdef WBO_GPU
+#include "wbx_gpu_hooks.h"
+#endif
 
 using namespace wb;
 
@@ -38,7 +41,10 @@ static uint64_t g_next_uid = 1;
 
 extern "C" {
 
-const char* wbo_kind(void) { return "reference"; }
+#ifndef WBO_KIND
+#define WBO_KIND "reference"
+#endif
+const char* wbo_kind(void) { return WBO_KIND; }
 
 wbo_session* wbo_create(uint32_t out_channels, uint32_t block_frames, uint32_t sample_rate, double bpm) {
   auto* s = new wbo_session(out_channels, block_frames);
@@ -54,6 +60,9 @@ wbo_session* wbo_create(uint32_t out_channels, uint32_t block_frames, uint32_t s
 void wbo_destroy(wbo_session* s) {
   if (!s) return;
   s->engine.clear_all();  // deletes tracks -> clips release their SampleAsset refs
+#ifdef WBO_GPU
+  wbx_gpu::release(&s->engine);
+#endif
   delete s;
 }
 

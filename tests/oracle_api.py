@@ -13,6 +13,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libwbref.so")
 PORT_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+# the reference's engine with its sample loops replaced by the wbx C ABI (oracle/patch_ref_gpu.py)
+REF_GPU_SO = os.path.join(ROOT, "oracle", "_ref", "libwbref_gpu.so")
 
 FMT_I16, FMT_I24, FMT_I24_X8, FMT_I32, FMT_F32 = 3, 5, 6, 7, 9
 _NP = {FMT_I16: np.int16, FMT_I24: np.int32, FMT_I32: np.int32, FMT_F32: np.float32}
@@ -85,8 +87,12 @@ def have_port():
     return os.path.exists(PORT_SO)
 
 
+def have_ref_gpu():
+    return os.path.exists(REF_GPU_SO)
+
+
 def lib(kind):
-    return _load(REF_SO if kind == "reference" else PORT_SO)
+    return _load({"reference": REF_SO, "reference_gpu": REF_GPU_SO}.get(kind, PORT_SO))
 
 
 class Session:

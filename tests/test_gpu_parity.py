@@ -782,3 +782,21 @@ def test_ui_thread_edits_while_audio_thread_renders(wb):
     assert last > 0, "the audio thread never saw a UI write"
     assert 0.0 <= eng.cpu_usage() <= 1.0
     eng.close()
+
+
+# ---- INTEGRATION.md section A, compiled: the reference's own engine with its sample loops replaced by wbx ----------------
+
+@pytest.mark.parametrize("name", sorted(sc.ALL) + ["fuzz0", "fuzz1", "fuzz2", "fuzz3"])
+def test_reference_with_wbx_binding_equals_reference(wb, golden_dir, name):
+    """oracle/_ref/libwbref_gpu.so = the reference's engine.cpp / track.cpp with exactly the sample loops of the hot path
+    (Sampler::stream calls, apply_gain + VU loop, clear / mix / clamp) replaced by wbx_segment records and one
+    wbx_render_levels per callback (oracle/patch_ref_gpu.py, oracle/ref_gpu_hooks.cpp), every other line — transport,
+    editor lock, process_event, parameter queue, plugin slot — the reference's own. Driven through the reference's public
+    API it must reproduce the CPU reference's golden vectors bit for bit: the drop-in claim, executed."""
+    if not o.have_ref_gpu():
+        pytest.skip("oracle/_ref/libwbref_gpu.so was not built (needs /root/reference at build time)")
+    gold = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    mk = lambda C, B, r, bpm: o.Session("reference_gpu", C, B, r, bpm)  # noqa: E731
+    res = sc.fuzz(mk, int(name[4:])) if name.startswith("fuzz") else sc.ALL[name](mk)
+    assert o.lib("reference_gpu").wbo_kind() == b"reference+wbx"
+    assert_exact(res, gold, "reference+wbx " + name)
