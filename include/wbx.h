@@ -213,6 +213,16 @@ void wbx_host_free(void* p);
  * n_blocks*block_frames*out_channels elements. */
 int wbx_fetch_interleaved(wbx_engine* e, void* dst, int dst_format);
 
+/* Offline bounce (the export driver the reference's export dialog lacks, ui/export_audio_dlg.cpp:44-200,
+ * engine/export_prop.h:14-45): a long render is cut into chunks of callbacks; each chunk is converted to the device format
+ * on the engine's stream right after its mix and copied to page-locked host memory on a second stream, under the next
+ * chunk's submit + mix. Per chunk:  wbx_submit, wbx_mix, wbx_bounce_push;  wbx_bounce_pop hands out the oldest pushed
+ * chunk (frames * out_channels elements of dst_format, interleaved as wbx_fetch_interleaved) — the pointer stays valid
+ * until the next wbx_bounce_push reuses the slot, i.e. until the pop after next. At most two chunks are in flight. */
+int wbx_bounce_begin(wbx_engine* e, int dst_format);
+int wbx_bounce_push(wbx_engine* e);
+int wbx_bounce_pop(wbx_engine* e, const void** data, size_t* bytes);
+
 /* Device-side views of the last wbx_mix result (valid until the next wbx_submit):
  * bus [out_channels][n_blocks*block_frames] f32, peaks [n_blocks][n_tracks][2] f32. */
 int wbx_device_bus(wbx_engine* e, float** d_bus, uint64_t* n_floats);

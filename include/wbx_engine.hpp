@@ -263,6 +263,20 @@ class Engine {
   // receives n_blocks * buffer_size frames; peaks (optional) [n_blocks][n_tracks][2].
   int render(uint32_t n_blocks, float* const* out_channels, float* peaks, double sample_rate = 0.0);
 
+  // Offline bounce / export (the reference has the dialog, ui/export_audio_dlg.cpp:44-200, and the
+  // properties, engine/export_prop.h:14-45, but no driver): renders [start_beat, end_beat) from a stopped transport as
+  // Engine::process would — play() at start_beat, one callback after the other — in chunks of chunk_blocks callbacks,
+  // the clamped bus converted on the device to dst_format (core/audio_format_conv.cpp:5-106: WBX_FMT_I16 / I24_X8 / I32 /
+  // F32 interleaved) and handed to `sink` in order; chunk i's copy-out and sink.write overlap chunk i+1's mix. The last
+  // callback is cut at end_beat. Leaves the transport stopped at start_beat. Returns the frames written (>= 0) through
+  // frames_out.
+  struct BounceSink {
+    virtual ~BounceSink() {}
+    virtual int write(const void* data, size_t bytes) = 0;  // 0 or a negative wbx_status
+  };
+  int bounce(double start_beat, double end_beat, int dst_format, BounceSink& sink, uint32_t chunk_blocks = 256,
+             uint64_t* frames_out = nullptr);
+
   // render() in two halves, for one thread driving several engines of a sharded setup (include/wbx_sharded.hpp):
   // render_begin = host schedule + wbx_submit; the caller then runs wbx_mix_sharded_phase(device(), 0..2) in lock step
   // over all engines; render_end = bus (rank 0; others pass nullptr) / peaks / levels back.
@@ -278,6 +292,7 @@ class Engine {
   wbx_engine* device() const { return dev_; }
   uint32_t buffer_size() const { return buffer_size_; }
   uint32_t out_channels() const { return out_channels_; }
+  uint32_t sample_rate() const { return sample_rate_; }
   std::vector<Track*> tracks;
   double ppq = 96.0;
   double playhead = 0, playhead_start = 0, sample_position = 0;

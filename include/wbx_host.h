@@ -79,6 +79,15 @@ void wbxh_set_fast_forward(wbxh_engine* h, int on);
 /* n_blocks consecutive Engine::process callbacks: out_channels[c] -> n_blocks*block_frames f32 (clamped bus),
  * peaks (optional) [n_blocks][n_tracks][2]. */
 int wbxh_render(wbxh_engine* h, uint32_t n_blocks, float* const* out_channels, float* peaks);
+/* Offline bounce / export of [start_beat, end_beat) from a stopped transport (wbx::Engine::bounce, wbx_engine.hpp): the
+ * clamped bus in dst_format (WBX_FMT_I16 / I24_X8 / I32 / F32, interleaved as core/audio_format_conv.cpp writes them),
+ * rendered in chunks of chunk_blocks callbacks (0 = 256) whose copy-out overlaps the next chunk's mix. wbxh_bounce fills
+ * dst (cap_bytes; too small = WBX_ERR_INVALID); wbxh_bounce_wav writes a RIFF/WAVE file (I24_X8 becomes 24-bit PCM).
+ * *frames_out = frames delivered. */
+int wbxh_bounce(wbxh_engine* h, double start_beat, double end_beat, int dst_format, uint32_t chunk_blocks, void* dst,
+                uint64_t cap_bytes, uint64_t* frames_out);
+int wbxh_bounce_wav(wbxh_engine* h, double start_beat, double end_beat, int dst_format, uint32_t chunk_blocks, const char* path,
+                    uint64_t* frames_out);
 /* wbxh_render in two halves for one thread driving several engines of a sharded setup (wbx.h "sharded render"):
  * begin = host schedule + wbx_submit; then wbx_mix_sharded_phase(wbxh_device(h), 0..2) in lock step over all engines;
  * end = bus (rank 0 only, others pass NULL) / peaks / levels back. */

@@ -800,3 +800,56 @@ def test_reference_with_wbx_binding_equals_reference(wb, golden_dir, name):
     res = sc.fuzz(mk, int(name[4:])) if name.startswith("fuzz") else sc.ALL[name](mk)
     assert o.lib("reference_gpu").wbo_kind() == b"reference+wbx"
     assert_exact(res, gold, "reference+wbx " + name)
+
+
+# ---- offline bounce / export driver ----------------------------------------------------------------------
+
+def _bounce_session(make, n_tracks=24, B=256, rate=48000):
+    rng = np.random.RandomState(77)
+    eng = make(2, B, rate, 120.0)
+    spb = rate * 0.5
+    for t in range(n_tracks):
+        eng.add_track(-5.0 - (t % 6), -0.8 + 0.07 * t, False)
+        fmt = o.FMT_I16 if t % 7 == 3 else o.FMT_F32
+        sid = eng.add_sample(sc._src(rng, 2, 40000, 8, fmt), 44100 if t % 5 == 1 else 48000, fmt)
+        eng.add_clip(t, sid, (13 * t) / spb, (13 * t + 30000) / spb, float(t), 1.0, 0.7)
+        eng.add_clip(t, sid, (13 * t + 31000 + 5 * t) / spb, 1e6, 100.0, 1.0 if t % 3 else 0.75, 0.5)
+    return eng
+
+
+@pytest.mark.parametrize("fmt", ["I16", "I24_X8", "I32", "F32"])
+def test_bounce_equals_reference_process_loop(wb, fmt, tmp_path):
+    """wbx::Engine::bounce(start_beat, end_beat, format, sink): chunked render with the transport and sampler state carried
+    from chunk to chunk, conversion on the device, copy-out overlapped with the next chunk's mix. Byte-identical to the
+    reference's Engine::process loop from the same playhead followed by convert_f32_to_interleaved_* (core/
+    audio_format_conv.cpp:5-106), cut at end_beat; the WAV file holds the same samples."""
+    code = {"I16": o.FMT_I16, "I24_X8": o.FMT_I24_X8, "I32": o.FMT_I32, "F32": o.FMT_F32}[fmt]
+    B, rate = 256, 48000
+    start, end = 0.37, 3.21
+    total_frames = int(np.ceil((end - start) * 0.5 * rate))
+    n_blocks = (total_frames + B - 1) // B
+    kind = "reference" if o.have_ref() else "port"
+    ref = _bounce_session(lambda C, B_, r, bpm: o.Session(kind, C, B_, r, bpm))
+    ref.set_playhead(start)
+    ref.play()
+    out, _ = ref.process(n_blocks)
+    planar = np.ascontiguousarray(out.transpose(1, 0, 2).reshape(2, n_blocks * B))[:, :total_frames]
+    want = o.interleave(kind, planar, code)
+    eng = _bounce_session(gpu_engine(wb))
+    got = eng.bounce(start, end, code, chunk_blocks=7)  # 15 chunks, the last one partial
+    assert got.size == want.size and np.array_equal(got, want), "bounce %s differs from the reference's process loop" % fmt
+    again = eng.bounce(start, end, code, chunk_blocks=4096)  # one chunk; the transport was left stopped at `start`
+    assert np.array_equal(again, want)
+    path = tmp_path / ("bounce_%s.wav" % fmt)
+    frames = eng.bounce(start, end, code, chunk_blocks=16, path=path)
+    assert frames == total_frames
+    raw = np.fromfile(path, np.uint8)
+    assert raw[:4].tobytes() == b"RIFF" and raw[8:16].tobytes() == b"WAVEfmt " and raw[36:40].tobytes() == b"data"
+    data_len = int(np.frombuffer(raw[40:44].tobytes(), "<u4")[0])
+    body = raw[44:44 + data_len]
+    if fmt == "I24_X8":  # the file holds 24-bit PCM: the low three bytes of every I24_X8 word
+        assert data_len == total_frames * 2 * 3
+        assert np.array_equal(body.reshape(-1, 3), want.reshape(-1, 4)[:, :3])
+    else:
+        assert data_len == want.size and np.array_equal(body, want)
+    eng.close()

@@ -59,7 +59,7 @@ WBX_SYMBOLS = [
     "wbx_set_sum_mode", "wbx_set_stream", "wbx_sample_upload", "wbx_sample_release", "wbx_sample_update", "wbx_sample_mipmap", "wbx_render", "wbx_submit",
     "wbx_mix", "wbx_fetch", "wbx_fetch_levels", "wbx_host_alloc", "wbx_host_free", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
     "wbx_synchronize", "wbx_launch_count", "wbx_last_kernel", "wbx_effects_design", "wbx_set_track_effects",
-    "wbx_set_impulse_response", "wbx_render_levels", "wbx_shard_init", "wbx_shard_connect_ipc",
+    "wbx_set_impulse_response", "wbx_render_levels", "wbx_bounce_begin", "wbx_bounce_push", "wbx_bounce_pop", "wbx_shard_init", "wbx_shard_connect_ipc",
     "wbx_shard_connect_local", "wbx_mix_sharded", "wbx_mix_sharded_phase", "wbx_shard_reset", "wbx_shard_set_host_output", "wbx_host_register",
     "wbx_host_unregister", "wbx_shard_close", "wbx_shard_info",
 ]
@@ -72,7 +72,7 @@ WBXH_SYMBOLS = [
     "wbxh_advance_rounded", "wbxh_render_begin", "wbxh_render_end", "wbxh_clip_count", "wbxh_clip_range", "wbxh_set_bpm", "wbxh_delete_track", "wbxh_move_track", "wbxh_solo_track",
     "wbxh_set_clip_gain", "wbxh_move_clip",
     "wbxh_resize_clip", "wbxh_delete_clip", "wbxh_duplicate_clip", "wbxh_delete_region", "wbxh_set_plugin", "wbxh_configure",
-    "wbxh_cpu_usage",
+    "wbxh_cpu_usage", "wbxh_bounce", "wbxh_bounce_wav",
 ]
 
 _lib = None
@@ -153,6 +153,11 @@ def lib():
     L.wbxh_configure.argtypes = [vp, u32, u32, u32]
     L.wbxh_cpu_usage.argtypes = [vp]
     L.wbxh_cpu_usage.restype = dbl
+    L.wbxh_bounce.argtypes = [vp, dbl, dbl, i32, u32, vp, u64, C.POINTER(u64)]
+    L.wbxh_bounce_wav.argtypes = [vp, dbl, dbl, i32, u32, C.c_char_p, C.POINTER(u64)]
+    L.wbx_bounce_begin.argtypes = [vp, i32]
+    L.wbx_bounce_push.argtypes = [vp]
+    L.wbx_bounce_pop.argtypes = [vp, pp, C.POINTER(C.c_size_t)]
     L.wbxh_add_sample.argtypes = [vp, i32, u32, u64, u32, pp]
     L.wbxh_add_clip.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt]
     L.wbxh_add_clip_fade.argtypes = [vp, i32, i32, dbl, dbl, dbl, dbl, flt, dbl, dbl]
@@ -439,6 +444,7 @@ class Engine:
                            "(there is no CPU fallback)" % rc)
         self.h = h
         self.C, self.B, self.rate = out_channels, block, rate
+        self._bpm = bpm
         self.n_tracks = 0
         self.batched = batched
         self.dev = None
@@ -490,6 +496,20 @@ class Engine:
 
     def cpu_usage(self):
         return self.L.wbxh_cpu_usage(self.h)
+
+    def bounce(self, start_beat, end_beat, fmt=FMT_F32, chunk_blocks=256, path=None, out=None):
+        """Offline export of [start_beat, end_beat): -> interleaved bytes in device format `fmt` (np.uint8 array), or the
+        frame count when `path` names a WAV file to write. `out`: optional preallocated np.uint8 destination."""
+        frames = C.c_uint64()
+        if path is not None:
+            self._ck(self.L.wbxh_bounce_wav(self.h, start_beat, end_beat, fmt, chunk_blocks, str(path).encode(), C.byref(frames)))
+            return frames.value
+        size = {FMT_I16: 2, FMT_I24_X8: 4, FMT_I32: 4, FMT_F32: 4}[fmt]
+        if out is None:
+            bpm_frames = int(np.ceil((end_beat - start_beat) * 60.0 / self._bpm * self.rate)) + self.B
+            out = np.zeros(bpm_frames * self.C * size, np.uint8)
+        self._ck(self.L.wbxh_bounce(self.h, start_beat, end_beat, fmt, chunk_blocks, out.ctypes.data, out.nbytes, C.byref(frames)))
+        return out[:frames.value * self.C * size]
 
     def add_sample(self, data, rate, fmt=FMT_F32):
         data = np.ascontiguousarray(data, dtype=_NP[fmt])
@@ -563,6 +583,7 @@ class Engine:
         self.L.wbxh_set_resampler(self.h, mode)
 
     def set_bpm(self, bpm):
+        self._bpm = bpm
         self.L.wbxh_set_bpm(self.h, bpm)
 
     def set_playhead(self, beat):

@@ -140,6 +140,15 @@ struct wbx_engine {
   float* mirror[2] = {nullptr, nullptr};       // device view of page-locked caller channels the running render also writes
   float* mirror_host[2] = {nullptr, nullptr};  // ... and the caller's pointers they belong to (wbx_render)
   bool levels_queued = false;              // level reduce + copy into h_levels already enqueued for this mix
+  // offline bounce (wbx_bounce_*): two chunk slots, converted on the main stream, copied out on a second stream
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t bounce_ready[2] = {nullptr, nullptr}, bounce_done[2] = {nullptr, nullptr};
+  DevBuf d_bounce[2];
+  HostBuf h_bounce[2];
+  size_t bounce_bytes[2] = {0, 0};
+  int bounce_fmt = 0;
+  uint64_t bounce_pushed = 0, bounce_popped = 0;
+  bool bounce_on = false;
   Shard shard;
   bool shard_result = false;               // the last mix was sharded: the master bus is shard.block + bus_off (rank 0)
   int shard_phase = 0;                     // next phase of the running sharded mix (0 = none running)
@@ -348,6 +357,13 @@ int wbx_destroy(wbx_engine* e) {
   for (HostBuf* b : {&e->h_spans, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
     if (b->p) cudaFreeHost(b->p);
   if (e->staging_read) cudaEventDestroy(e->staging_read);
+  for (int i = 0; i < 2; i++) {
+    if (e->bounce_ready[i]) cudaEventDestroy(e->bounce_ready[i]);
+    if (e->bounce_done[i]) cudaEventDestroy(e->bounce_done[i]);
+    if (e->d_bounce[i].p) cudaFree(e->d_bounce[i].p);
+    if (e->h_bounce[i].p) cudaFreeHost(e->h_bounce[i].p);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   cudaStreamDestroy(e->own_stream);
   delete e;
   return WBX_OK;
@@ -1266,6 +1282,78 @@ int wbx_fetch_interleaved(wbx_engine* e, void* dst, int dst_format) {
   CU(e, cudaMemcpyAsync(e->h_conv.p, e->d_conv.p, bytes, cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaStreamSynchronize(e->stream));
   memcpy(dst, e->h_conv.p, bytes);
+  return WBX_OK;
+}
+
+// ---- offline bounce: chunks in the device format, their copy-out overlapping the next chunk's mix ---------------------
+static size_t conv_elem_size(int fmt) {
+  switch (fmt) {
+    case WBX_FMT_I16: return 2;
+    case WBX_FMT_I24: return 3;
+    case WBX_FMT_I24_X8:
+    case WBX_FMT_I32:
+    case WBX_FMT_F32: return 4;
+    default: return 0;
+  }
+}
+
+int wbx_bounce_begin(wbx_engine* e, int dst_format) {
+  if (!e) return WBX_ERR_INVALID;
+  if (!conv_elem_size(dst_format)) return fail(e, WBX_ERR_UNSUPPORTED, "device format %d", dst_format);
+  CU(e, cudaSetDevice(e->device));
+  if (!e->copy_stream) CU(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    if (!e->bounce_ready[i]) CU(e, cudaEventCreateWithFlags(&e->bounce_ready[i], cudaEventDisableTiming));
+    if (!e->bounce_done[i]) CU(e, cudaEventCreateWithFlags(&e->bounce_done[i], cudaEventDisableTiming));
+  }
+  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, cudaStreamSynchronize(e->copy_stream));
+  e->bounce_fmt = dst_format;
+  e->bounce_pushed = e->bounce_popped = 0;
+  e->bounce_on = true;
+  return WBX_OK;
+}
+
+int wbx_bounce_push(wbx_engine* e) {
+  if (!e) return WBX_ERR_INVALID;
+  if (!e->bounce_on) return fail(e, WBX_ERR_INVALID, "wbx_bounce_push before wbx_bounce_begin");
+  if (!e->mixed) return fail(e, WBX_ERR_INVALID, "wbx_bounce_push before wbx_mix");
+  if (e->bounce_pushed - e->bounce_popped >= 2) return fail(e, WBX_ERR_INVALID, "wbx_bounce_push: two chunks are already in flight, pop one");
+  CU(e, cudaSetDevice(e->device));
+  const float* bus = result_bus(e);
+  if (!bus) return fail(e, WBX_ERR_INVALID, "wbx_bounce_push: after a sharded mix only rank 0 holds the master bus");
+  const int slot = (int)(e->bounce_pushed & 1);
+  const uint64_t frames = (uint64_t)e->n_blocks * e->B;
+  const size_t bytes = e->bounce_fmt == WBX_FMT_I24 ? frames * 3 : frames * e->C * conv_elem_size(e->bounce_fmt);
+  if (bytes > e->d_bounce[slot].cap || bytes > e->h_bounce[slot].cap) {  // (re)size this slot: its previous copy-out is long popped
+    CU(e, cudaStreamSynchronize(e->copy_stream));
+    int rc;
+    if ((rc = dev_reserve(e, e->d_bounce[slot], bytes))) return rc;
+    if ((rc = host_reserve(e, e->h_bounce[slot], bytes))) return rc;
+  }
+  // the slot's previous copy-out (two chunks ago) must be over before the conversion overwrites the device buffer
+  if (e->bounce_pushed >= 2) CU(e, cudaStreamWaitEvent(e->stream, e->bounce_done[slot], 0));
+  CU(e, launch_interleave(bus, frames, e->C, e->bounce_fmt, e->d_bounce[slot].p, e->n_sm, e->stream));
+  e->launches++;
+  CU(e, cudaEventRecord(e->bounce_ready[slot], e->stream));
+  // ... and the copy to the host runs on the second stream, under the next chunk's submit + mix
+  CU(e, cudaStreamWaitEvent(e->copy_stream, e->bounce_ready[slot], 0));
+  CU(e, cudaMemcpyAsync(e->h_bounce[slot].p, e->d_bounce[slot].p, bytes, cudaMemcpyDeviceToHost, e->copy_stream));
+  CU(e, cudaEventRecord(e->bounce_done[slot], e->copy_stream));
+  e->bounce_bytes[slot] = bytes;
+  e->bounce_pushed++;
+  return WBX_OK;
+}
+
+int wbx_bounce_pop(wbx_engine* e, const void** data, size_t* bytes) {
+  if (!e || !data || !bytes) return WBX_ERR_INVALID;
+  if (!e->bounce_on || e->bounce_popped == e->bounce_pushed) return fail(e, WBX_ERR_INVALID, "wbx_bounce_pop: no chunk in flight");
+  CU(e, cudaSetDevice(e->device));
+  const int slot = (int)(e->bounce_popped & 1);
+  CU(e, cudaEventSynchronize(e->bounce_done[slot]));
+  *data = e->h_bounce[slot].p;
+  *bytes = e->bounce_bytes[slot];
+  e->bounce_popped++;
   return WBX_OK;
 }
 

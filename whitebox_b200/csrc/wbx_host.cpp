@@ -7,6 +7,7 @@
 // because event offsets come from truncating those doubles (engine/track.cpp:359-361,378-379,423-425).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 #include "../../include/wbx_engine.hpp"
@@ -953,6 +954,71 @@ int Engine::render(uint32_t n_blocks, float* const* out_channels, float* peaks, 
   return WBX_OK;
 }
 
+// Offline bounce: the batched render as an export driver. Chunk i's conversion runs right behind its mix, its copy to the
+// host on the device engine's second stream and the sink's write on this thread, all under chunk i+1's schedule + mix.
+int Engine::bounce(double start_beat, double end_beat, int dst_format, BounceSink& sink, uint32_t chunk_blocks,
+                   uint64_t* frames_out) {
+  if (frames_out) *frames_out = 0;
+  if (!dev_) return WBX_ERR_NO_DEVICE;
+  if (!(end_beat > start_beat) || chunk_blocks == 0) return WBX_ERR_INVALID;
+  size_t es;
+  switch (dst_format) {
+    case WBX_FMT_I16: es = 2; break;
+    case WBX_FMT_I24_X8:
+    case WBX_FMT_I32:
+    case WBX_FMT_F32: es = 4; break;
+    default: return WBX_ERR_UNSUPPORTED;  // (the reference's packed-I24 writer has no channel stride: not a file format)
+  }
+  stop();
+  set_playhead_position(start_beat);
+  play();
+  const auto t0 = std::chrono::steady_clock::now();
+  SpinGuard edit(editor_lock);  // an export owns the engine like a (long) callback does
+  const double total = std::ceil(beat_to_samples(end_beat - start_beat, (double)sample_rate_, beat_duration_));
+  const uint64_t total_frames = total > 0.0 ? (uint64_t)total : 0;
+  const uint64_t total_blocks = (total_frames + buffer_size_ - 1) / buffer_size_;
+  int rc = wbx_bounce_begin(dev_, dst_format);
+  uint64_t done_blocks = 0, in_flight = 0, written = 0;
+  auto pop_one = [&]() -> int {
+    const void* data = nullptr;
+    size_t bytes = 0;
+    int r = wbx_bounce_pop(dev_, &data, &bytes);
+    if (r) return r;
+    const size_t frame_bytes = es * out_channels_;
+    uint64_t frames = bytes / frame_bytes;
+    if (written + frames > total_frames) frames = total_frames - written;  // the last callback is cut at end_beat
+    written += frames;
+    in_flight--;
+    return frames ? sink.write(data, (size_t)frames * frame_bytes) : WBX_OK;
+  };
+  while (!rc && done_blocks < total_blocks) {
+    const uint32_t n = (uint32_t)std::min<uint64_t>(chunk_blocks, total_blocks - done_blocks);
+    if ((rc = prepare(n, 0.0))) break;
+    if ((rc = wbx_submit(dev_, segs_.data(), (uint32_t)segs_.size(), gains_.data(), n))) break;
+    if ((rc = wbx_mix(dev_, 0))) break;
+    if ((rc = wbx_bounce_push(dev_))) break;
+    in_flight++;
+    done_blocks += n;
+    if (in_flight == 2) rc = pop_one();  // the older chunk: its copy-out ran under the mix just enqueued
+  }
+  while (!rc && in_flight) rc = pop_one();
+  if (!rc && tracks.size()) {  // VU levels of the last chunk, as after any render
+    levels_.resize(tracks.size() * 2);
+    if (!(rc = wbx_fetch_levels(dev_, levels_.data()))) merge_levels();
+  }
+  if (!rc) rc = wbx_synchronize(dev_);
+  meter(t0, (uint32_t)std::min<uint64_t>(total_blocks, 0xFFFFFFFFu));
+  // Engine::stop (engine.cpp:82-92) without re-taking the lock
+  playing = false;
+  playhead = playhead_start;
+  for (Track* t : tracks) {
+    t->current_audio_event = AudioEvent();
+    t->audio_event_buffer.clear();
+  }
+  if (frames_out) *frames_out = written;
+  return rc;
+}
+
 // render() in two halves for a thread that drives several sharded engines (wbx_sharded.hpp): render_begin on every
 // engine, the phases of wbx_mix_sharded_phase on every engine's device(), render_end on every engine.
 int Engine::render_begin(uint32_t n_blocks, double sample_rate) {
@@ -1124,6 +1190,77 @@ void wbxh_set_playhead(wbxh_engine* h, double beat) { h->eng.set_playhead_positi
 void wbxh_play(wbxh_engine* h) { h->eng.play(); }
 void wbxh_stop(wbxh_engine* h) { h->eng.stop(); }
 void wbxh_set_fast_forward(wbxh_engine* h, int on) { h->eng.fast_forward = on != 0; }
+
+namespace {
+struct MemorySink final : Engine::BounceSink {
+  uint8_t* dst;
+  size_t cap, used = 0;
+  MemorySink(void* d, size_t c) : dst((uint8_t*)d), cap(c) {}
+  int write(const void* data, size_t bytes) override {
+    if (used + bytes > cap) return WBX_ERR_INVALID;
+    memcpy(dst + used, data, bytes);
+    used += bytes;
+    return WBX_OK;
+  }
+};
+// Minimal RIFF/WAVE writer: PCM 16 / 24 / 32 bit or IEEE float 32. 24-bit files are fed I24_X8 words (the 24-bit value in
+// the low three bytes, core/audio_format_conv.cpp:45-59) and packed to three bytes here.
+struct WavFileSink final : Engine::BounceSink {
+  FILE* f = nullptr;
+  int fmt;
+  uint32_t channels, rate;
+  uint64_t data_bytes = 0;
+  std::vector<uint8_t> pack;
+  WavFileSink(const char* path, int format, uint32_t ch, uint32_t sr) : fmt(format), channels(ch), rate(sr) {
+    f = fopen(path, "wb");
+    if (f) header();
+  }
+  ~WavFileSink() override { close(); }
+  void header() {
+    const uint32_t bits = fmt == WBX_FMT_I16 ? 16 : (fmt == WBX_FMT_I24_X8 ? 24 : 32);
+    const uint16_t tag = fmt == WBX_FMT_F32 ? 3 : 1, ch = (uint16_t)channels, align = (uint16_t)(channels * bits / 8), bps = (uint16_t)bits;
+    const uint32_t byte_rate = rate * align, fmt_len = 16, data_len = (uint32_t)data_bytes, riff_len = 36 + data_len;
+    fseek(f, 0, SEEK_SET);
+    fwrite("RIFF", 1, 4, f), fwrite(&riff_len, 4, 1, f), fwrite("WAVEfmt ", 1, 8, f), fwrite(&fmt_len, 4, 1, f);
+    fwrite(&tag, 2, 1, f), fwrite(&ch, 2, 1, f), fwrite(&rate, 4, 1, f), fwrite(&byte_rate, 4, 1, f), fwrite(&align, 2, 1, f);
+    fwrite(&bps, 2, 1, f), fwrite("data", 1, 4, f), fwrite(&data_len, 4, 1, f);
+  }
+  int write(const void* data, size_t bytes) override {
+    if (!f) return WBX_ERR_INVALID;
+    if (fmt == WBX_FMT_I24_X8) {
+      const size_t n = bytes / 4;
+      pack.resize(n * 3);
+      const uint8_t* s = (const uint8_t*)data;
+      for (size_t i = 0; i < n; i++) pack[3 * i] = s[4 * i], pack[3 * i + 1] = s[4 * i + 1], pack[3 * i + 2] = s[4 * i + 2];
+      data = pack.data();
+      bytes = n * 3;
+    }
+    if (fwrite(data, 1, bytes, f) != bytes) return WBX_ERR_INVALID;
+    data_bytes += bytes;
+    return WBX_OK;
+  }
+  void close() {
+    if (!f) return;
+    header();  // sizes are known now
+    fclose(f);
+    f = nullptr;
+  }
+};
+}  // namespace
+
+int wbxh_bounce(wbxh_engine* h, double start_beat, double end_beat, int dst_format, uint32_t chunk_blocks, void* dst,
+                uint64_t cap_bytes, uint64_t* frames_out) {
+  if (!h || !dst) return WBX_ERR_INVALID;
+  MemorySink sink(dst, (size_t)cap_bytes);
+  return h->eng.bounce(start_beat, end_beat, dst_format, sink, chunk_blocks ? chunk_blocks : 256, frames_out);
+}
+int wbxh_bounce_wav(wbxh_engine* h, double start_beat, double end_beat, int dst_format, uint32_t chunk_blocks, const char* path,
+                    uint64_t* frames_out) {
+  if (!h || !path) return WBX_ERR_INVALID;
+  WavFileSink sink(path, dst_format, h->eng.out_channels(), h->eng.sample_rate());
+  if (!sink.f) return WBX_ERR_INVALID;
+  return h->eng.bounce(start_beat, end_beat, dst_format, sink, chunk_blocks ? chunk_blocks : 256, frames_out);
+}
 
 int wbxh_render_begin(wbxh_engine* h, uint32_t n_blocks) { return h->eng.render_begin(n_blocks); }
 int wbxh_render_end(wbxh_engine* h, float* const* out_channels, float* peaks) { return h->eng.render_end(out_channels, peaks); }
