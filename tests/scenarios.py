@@ -542,6 +542,59 @@ def reverb(make_engine, fxp, taps=777):
     return _collect(eng, outs, n)
 
 
+def reverb_full_depth(make_engine, fxp, taps=65536, n_tracks=64, n_blocks=160, block=512, chunks=None, seed=5150):
+    """EXTENSION scenario (parity unpinned w.r.t. whitebox): BASELINE cfg 5 at FULL accumulation depth — more frames of
+    non-zero signal than the impulse response has taps (160 x 512 = 81920 > 65536) on >= 128 signals, so every tap chunk
+    of the tensor-core path multiplies real history and the accumulators see the whole chain. Returns the session's
+    arrays plus what an f64 evaluation needs (sources, gains, impulse response)."""
+    rng = np.random.RandomState(seed)
+    eng = make_engine(2, block, 48000, 120.0)
+    ir = (rng.standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 6.0)) * 0.01).astype(np.float32)
+    ir[0] = 1.0
+    eng.set_impulse_response(ir)
+    frames = (n_blocks + 2) * block
+    srcs, params = [], []
+    for t in range(n_tracks):
+        vol, pan, gain = -6.0 - (t % 7), -1.0 + 0.2 * (t % 11), float(np.float32(0.5 + 0.001 * (t % 512)))
+        eng.add_track(vol, pan, False)
+        x = _src(rng, 2, frames, n_tracks)
+        sid = eng.add_sample(x, 48000)
+        eng.add_clip(t, sid, 0.0, 1e6, 0.0, 1.0, gain)
+        eng.set_effects(t, fxp(reverb=True))
+        srcs.append(x)
+        params.append((vol, pan, gain))
+    eng.play()
+    outs = [eng.process(n) for n in (chunks or [n_blocks])]
+    res = _collect(eng, outs, n_tracks)
+    res["_ir"], res["_srcs"], res["_params"] = ir, srcs, params
+    return res
+
+
+def reverb_f64_expected(res, panning_coefs, db_to_linear, block=512):
+    """The specification of the convolution reverb (oracle/wb_oracle.c apply_reverb: y[n] = (float) sum_k h[k] x[n-k],
+    accumulated in f64) evaluated with an f64 FFT — the direct sum is ~1e15 multiply-adds at this size; the FFT evaluation
+    differs from it by ~1e-13 relative (tests/test_oracle.py pins that on a size the direct sum can do). -> the clamped
+    bus [K][2][B] and the per-callback VU peaks [K][N][2] the session should produce."""
+    ir, srcs, params = res["_ir"].astype(np.float64), res["_srcs"], res["_params"]
+    K = res["out"].shape[0]
+    n_out = K * block
+    nfft = 1 << int(np.ceil(np.log2(n_out + ir.size)))
+    H = np.fft.rfft(ir, nfft)
+    bus = np.zeros((2, n_out), np.float64)
+    peaks = np.zeros((K, len(srcs), 2), np.float32)
+    for t, (x, (vol, pan, gain)) in enumerate(zip(srcs, params)):
+        pl, pr = panning_coefs(pan)
+        v = np.float32(db_to_linear(vol))
+        for c, pc in ((0, pl), (1, pr)):
+            xin = (x[c][:n_out] * np.float32(gain)).astype(np.float32).astype(np.float64)  # Sampler::stream: src * clip gain
+            y = np.fft.irfft(np.fft.rfft(xin, nfft) * H, nfft)[:n_out].astype(np.float32)  # the chain's output
+            term = (y * np.float32(v * np.float32(pc))).astype(np.float32)                 # apply_gain: * (volume * pan)
+            peaks[:, t, c] = np.abs(term).reshape(K, block).max(axis=1)
+            bus[c] += term
+    out = np.clip(bus, -1.0, 1.0).astype(np.float32)
+    return np.ascontiguousarray(out.reshape(2, K, block).transpose(1, 0, 2)), peaks
+
+
 def polyphase(make_engine, fxp=None):
     """EXTENSION scenario (parity unpinned w.r.t. whitebox): BASELINE cfg 3 wording — 44.1 -> 48 kHz through the
     polyphase windowed-sinc resampler — plus other ratios, clip starts at frame 0 (taps reach before the sample),

@@ -181,6 +181,25 @@ def test_reverb_cfg5_tap_count_tensor_cores(wb, monkeypatch):
     assert np.all(err <= 1e-5 * peak), "reverb bus error %.3g of block peak" % float((err / peak).max())
 
 
+@pytest.mark.parametrize("chunks", [None, [64, 64, 32]])
+def test_reverb_cfg5_full_accumulation_depth(wb, chunks, monkeypatch):
+    """BASELINE cfg 5 on the tensor-core path at full depth: 64 stereo tracks (128 signals) x 160 callbacks x 512 frames
+    (81920 frames of signal > 65536 taps, in one render and carried across three), against the f64 specification; bus
+    and VU peaks within 1e-5 of the block / track peak. Every one of the 1027 tap chunks multiplies real history here
+    (the 777...65536-tap scenario above only ever fills 33 of them)."""
+    monkeypatch.setenv("WBX_FIR", "tc")
+    res = sc.reverb_full_depth(gpu_engine(wb, True), wb.effect_params, chunks=chunks)
+    want, want_peaks = sc.reverb_f64_expected(res, wb.panning_coefs, wb.db_to_linear)
+    peak = np.abs(want).max(axis=(1, 2), keepdims=True)
+    err = np.abs(res["out"].astype(np.float64) - want) / peak
+    assert float(err.max()) <= 1e-5, "reverb bus error %.3g of block peak (worst callback %d)" % (float(err.max()), int(err.max(axis=(1, 2)).argmax()))
+    # late callbacks (history longer than the response) are as good as early ones: no drift with accumulation depth
+    late = float(err[136:].max())
+    assert late <= 1e-5, "late-callback error %.3g" % late
+    pk = np.abs(want_peaks).max()
+    assert float(np.abs(res["peaks"].astype(np.float64) - want_peaks).max()) <= 1e-5 * pk
+
+
 def test_reverb_delta_is_identity(wb):
     """h = [1]: the convolution multiplies by exactly 1, so the render equals the chain-free one bit for bit."""
     def run(with_ir):

@@ -177,3 +177,17 @@ def test_effect_chain_spec_accuracy():
             assert err_spec <= 1e-5, "specification vs f64 chain: %.3g of block peak" % err_spec
         assert err_spec <= 2.0 * err_text + 1e-6, "specification %.3g vs textbook f32 %.3g of block peak" % (err_spec, err_text)
         assert err_text <= 2e-4 and err_spec <= 2e-4
+
+
+def test_reverb_f64_fft_evaluator_equals_direct_sum():
+    """The f64 FFT evaluation of the reverb specification that the full-depth GPU test and bench.py check against
+    (scenarios.reverb_f64_expected) equals the C port's direct f64 sum (oracle/wb_oracle.c apply_reverb) to ~1e-12 of the
+    block peak, at a size the direct sum can do."""
+    import whitebox_b200 as wb
+    mk = lambda C, B, r, bpm: o.Session("port", C, B, r, bpm)  # noqa: E731
+    res = sc.reverb_full_depth(mk, wb.effect_params, taps=3001, n_tracks=3, n_blocks=9, block=512)
+    want, want_peaks = sc.reverb_f64_expected(res, lambda p: o.panning_coefs("port", p), lambda d: o.db_to_linear("port", d))
+    peak = np.abs(want).max(axis=(1, 2), keepdims=True)
+    err = np.abs(res["out"].astype(np.float64) - want) / peak
+    assert float(err.max()) <= 2e-7, float(err.max())  # (both are rounded to f32 at the chain output: a few ulp)
+    assert float(np.abs(res["peaks"] - want_peaks).max()) <= 2e-7 * float(np.abs(want_peaks).max())
