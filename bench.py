@@ -786,7 +786,7 @@ def run_ours(args):
     ctx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
     ctx.rank = rank = int(os.environ.get("RANK", "0"))
     ctx.local = local = int(os.environ.get("LOCAL_RANK", "0"))
-    ctx.fir_split = int(os.environ.get("WBX_FIR_SPLIT", "6"))
+    ctx.fir_split = int(wb.lib().wbx_fir_split_factor())
     if args.gpus > 1 and world != args.gpus:
         raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)" % (args.gpus, args.gpus, world))
     torch.cuda.set_device(local)

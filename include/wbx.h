@@ -164,8 +164,8 @@ int wbx_effects_design(const wbx_effect_params* params, uint32_t sample_rate, wb
 /* Convolution reverb (extension, BASELINE cfg 5): one impulse response h[0..n_taps) per engine, applied as the last
  * stage of every chain with reverb_on: y[n] = sum_k h[k] * x[n-k] with the history carried across renders.
  * Specification = f64 accumulation (oracle/wb_oracle.c apply_reverb). Two implementations, both held to 1e-5 of the block
- * peak: responses of >= 1024 taps run on the tensor cores (the convolution as a Toeplitz GEMM, tcgen05.mma on a 3-term
- * bf16 split of both operands, f32 accumulation in TMEM drained periodically), shorter ones as a direct form on the CUDA
+ * peak: responses of >= 1024 taps run on the tensor cores (the convolution as a Toeplitz GEMM, tcgen05.mma on a 2-term
+ * fp16 split of both operands, f32 accumulation in TMEM drained periodically), shorter ones as a direct form on the CUDA
  * cores (f32 fused multiply-adds per 256-tap tile, tiles summed in f64). WBX_FIR=direct|tc overrides the threshold.
  * h == NULL or n_taps == 0 removes it. Changing it clears every track's reverb history. */
 int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps);
@@ -284,6 +284,9 @@ int wbx_shard_info(const wbx_engine* e, uint32_t* rank, uint32_t* world);
 /* ---- introspection --------------------------------------------------------------------------------- */
 /* Number of CUDA kernels this engine has launched since creation (bench.py's gpu_launches). */
 uint64_t wbx_launch_count(const wbx_engine* e);
+/* Reduced-precision tensor-core products issued per tap by the convolution reverb (split-precision factor; 3 = 2-term fp16
+ * split of both operands). */
+int wbx_fir_split_factor(void);
 /* Name of the mix kernel variant the last wbx_mix used ("exact/vec16", "tree/g8", ...). */
 const char* wbx_last_kernel(const wbx_engine* e);
 

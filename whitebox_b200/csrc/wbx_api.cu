@@ -43,7 +43,9 @@ cudaError_t launch_ingest(const void* host_table, void* table, size_t table_byte
 cudaError_t launch_levels_direct(const float* peaks, uint32_t K, uint32_t NC, float* levels_host, cudaStream_t stream);
 size_t fir_tc_tiles_bytes(uint32_t L);
 uint64_t fir_tc_plane_width(uint64_t H, uint64_t T);
-cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, cudaStream_t stream);
+cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, float h_scale, cudaStream_t stream);
+size_t fir_tc_scratch_bytes(uint64_t H, uint64_t T, uint32_t S);
+int fir_tc_split_factor();
 }  // namespace wbx
 
 using namespace wbx;
@@ -634,7 +636,16 @@ int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps) {
   e->fir_tc = mode ? (mode[0] == 't') : (n_taps >= 1024);
   if (e->fir_tc) {
     if ((rc = dev_reserve(e, e->d_irtiles, fir_tc_tiles_bytes(n_taps)))) return rc;
-    CU(e, launch_fir_tc_prepare((const float*)e->d_ir.p, n_taps, e->d_irtiles.p, e->stream));
+    // fp16 operands: scale the response so that its largest tap lands in [2^13, 2^14) (undone exactly in the epilogue)
+    float hmax = 0.0f;
+    for (uint32_t i = 0; i < n_taps; i++) hmax = std::fmax(hmax, std::fabs(h[i]));
+    float h_scale = 1.0f;
+    if (hmax > 0.0f && std::isfinite(hmax)) {
+      int ex;
+      std::frexp(hmax, &ex);
+      h_scale = std::ldexp(1.0f, 14 - ex);
+    }
+    CU(e, launch_fir_tc_prepare((const float*)e->d_ir.p, n_taps, e->d_irtiles.p, h_scale, e->stream));
     e->launches++;
   }
   CU(e, cudaStreamSynchronize(e->stream));
@@ -930,8 +941,7 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
     const bool rv = e->ir_taps > 0 && (reverb || e->ir_taps == 1);
     const bool tc = rv && e->fir_tc;
     if (tc) {
-      const uint64_t W = fir_tc_plane_width(e->ir_taps - 1, (uint64_t)n_blocks * B);
-      if ((rc = dev_reserve(e, e->d_firplanes, (size_t)3 * n_fx * C * W * 2 + 256))) return rc;
+      if ((rc = dev_reserve(e, e->d_firplanes, fir_tc_scratch_bytes(e->ir_taps - 1, (uint64_t)n_blocks * B, n_fx * C)))) return rc;
     }
     CU(e, launch_effects((const DSpan*)e->d_spans.p, e->cells_ptr, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
                          n_segs, (float*)e->d_trackbuf.p, rv ? (const float*)e->d_ir.p : nullptr, rv ? e->ir_taps : 0,
@@ -1587,6 +1597,7 @@ int wbx_synchronize(wbx_engine* e) {
 }
 
 uint64_t wbx_launch_count(const wbx_engine* e) { return e ? e->launches : 0; }
+int wbx_fir_split_factor(void) { return fir_tc_split_factor(); }
 const char* wbx_last_kernel(const wbx_engine* e) { return e ? e->kernel_name : ""; }
 
 }  // extern "C"

@@ -1587,15 +1587,23 @@ static cudaError_t launch_effects_chain(const DSpan* spans, const DCell* cells, 
 // hist [n_tracks][2][H] persists across renders (indexed by track, so it survives chain list rebuilds)
 __global__ void fir_gather_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T,
                                   const float* __restrict__ hist, const float* __restrict__ trackbuf, uint64_t tbs,
-                                  float* __restrict__ xin) {
+                                  float* __restrict__ xin, uint32_t* __restrict__ max_word) {
   const uint32_t ec = blockIdx.y;
   const uint32_t e = ec / C, c = ec % C;
   if (!fx[e].reverb_on) return;
   const float* h = hist + ((size_t)fx[e].track * 2 + c) * H;
   const float* tb = trackbuf + (size_t)e * tbs * 2 + c;
   float* x = xin + (size_t)ec * (H + T);
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H + T; i += (uint64_t)gridDim.x * blockDim.x)
-    x[i] = i < H ? h[i] : tb[(i - H) * 2];
+  float m = 0.0f;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H + T; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float v = i < H ? h[i] : tb[(i - H) * 2];
+    x[i] = v;
+    m = fmaxf(m, fabsf(v));
+  }
+  if (max_word) {  // the tensor-core path scales its fp16 operands by the largest input magnitude of the render
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(max_word, __float_as_uint(m));
+  }
 }
 
 // 256 consecutive outputs of one (track, channel) per CTA; taps in tiles of 256 staged in shared memory
@@ -2043,7 +2051,8 @@ cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, ui
 }
 
 cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T, uint32_t L, void* tiles,
-                          const float* xin, void* planes, float* trackbuf, uint64_t tbs, cudaStream_t stream);  // wbx_fir_tc.cu
+                          const float* xin, void* scratch, float* trackbuf, uint64_t tbs, int n_sm, cudaStream_t stream);  // wbx_fir_tc.cu
+uint32_t* fir_tc_max_word(void* scratch);
 
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
@@ -2065,9 +2074,18 @@ cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n
   if (L && ir && fir_hist && fir_in) {  // convolution reverb as the chain's last stage
     const uint64_t T = (uint64_t)K * B, H = L - 1;
     const dim3 gcopy((unsigned)(((H + T) + 255) / 256 < 4096 ? ((H + T) + 255) / 256 : 4096), n_fx * C);
-    fir_gather_kernel<<<gcopy, 256, 0, stream>>>(fx, n_fx, C, H, T, fir_hist, trackbuf, tbs, fir_in);
-    if (tc_tiles && tc_planes) {  // tensor-core path (wbx_fir_tc.cu)
-      cudaError_t err = launch_fir_tc(fx, n_fx, C, H, T, L, tc_tiles, fir_in, tc_planes, trackbuf, tbs, stream);
+    const bool tc = tc_tiles && tc_planes;
+    uint32_t* max_word = tc ? fir_tc_max_word(tc_planes) : nullptr;
+    if (max_word) {
+      cudaError_t err = cudaMemsetAsync(max_word, 0, sizeof(uint32_t), stream);
+      if (err != cudaSuccess) return err;
+    }
+    fir_gather_kernel<<<gcopy, 256, 0, stream>>>(fx, n_fx, C, H, T, fir_hist, trackbuf, tbs, fir_in, max_word);
+    if (tc) {  // tensor-core path (wbx_fir_tc.cu)
+      int dev = 0, n_sm = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      cudaError_t err = launch_fir_tc(fx, n_fx, C, H, T, L, tc_tiles, fir_in, tc_planes, trackbuf, tbs, n_sm, stream);
       if (err != cudaSuccess) return err;
     } else {
       fir_kernel<<<dim3((unsigned)((T + 255) / 256), n_fx * C), 256, 0, stream>>>(fx, C, H, T, ir, L, fir_in, trackbuf, tbs);
