@@ -260,7 +260,8 @@ int wbx_mix_sharded(wbx_engine* e);
 /* The same collective in its three phases, for ONE thread driving several engines (it must issue phase p on every
  * engine before phase p+1 on any, so that no engine's stream waits for work that has not been enqueued yet):
  *   0  mix into the owners' exchange buffers + arrival signal      1  wait, reduce own slice + clamp into the master
- *   bus, signal      2  wait. wbx_mix_sharded(e) = phases 0, 1, 2 back to back (one process or thread per GPU). */
+ *   bus, signal      2  wait. wbx_mix_sharded(e) (one process or thread per GPU) = phase 0's mix followed by the rest of the
+ *   exchange fused into ONE kernel launch (signal, wait, reduce + clamp, signal, wait); `phase` 3 selects that form. */
 int wbx_mix_sharded_phase(wbx_engine* e, int phase);
 /* Recovery. A phase that fails (a launch error, or a peer that never arrived: WBX_ERR_CUDA from the next synchronising
  * call) ends the running collective on this rank — the engine accepts a new wbx_mix_sharded afterwards — but the ranks'

@@ -40,6 +40,10 @@ cudaError_t launch_shard_reduce(const float* xchg, uint32_t W, uint32_t C, uint6
                                 cudaStream_t stream);
 cudaError_t launch_ingest(const void* host_table, void* table, size_t table_bytes, void* zero, size_t zero_bytes,
                           cudaStream_t stream);
+cudaError_t launch_shard_exchange(const float* xchg, uint32_t W, uint32_t C, uint64_t plane, uint64_t valid, const ShardPeers& peers,
+                                  uint64_t chan_stride, uint64_t dst_off, uint32_t rank, uint32_t epoch_arrive, uint32_t epoch_done,
+                                  unsigned long long timeout_ns, uint32_t* status, uint32_t* done_counter, int n_sm,
+                                  cudaStream_t stream);
 cudaError_t launch_levels_direct(const float* peaks, uint32_t K, uint32_t NC, float* levels_host, cudaStream_t stream);
 size_t fir_tc_tiles_bytes(uint32_t L);
 uint64_t fir_tc_plane_width(uint64_t H, uint64_t T);
@@ -93,6 +97,7 @@ struct Shard {
   float* host_out_host[2] = {nullptr, nullptr};  // ... and the host pointers they were given as
   uint64_t host_out_frames = 0;
   uint32_t* status = nullptr;  // page-locked host word raised by a barrier that timed out
+  uint32_t* done_counter = nullptr;  // device word: blocks of the fused exchange kernel that have finished their reduce
   unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
 };
 
@@ -972,7 +977,7 @@ static ShardPeers shard_peers(const Shard& sh) {
   return peers;
 }
 
-static int do_mix(wbx_engine* e, uint32_t flags, bool sharded) {
+static int do_mix(wbx_engine* e, uint32_t flags, bool sharded, bool defer_signal = false) {
   CU(e, cudaSetDevice(e->device));
   const uint32_t N = e->n_tracks, B = e->B, C = e->C, K = e->n_blocks;
   const size_t bus_floats = (size_t)C * K * B;
@@ -1065,9 +1070,11 @@ static int do_mix(wbx_engine* e, uint32_t flags, bool sharded) {
            sharded ? "/peer-reduce" : "");
   if (sharded) {
     // all of this rank's tiles are on their way into the owners' exchange buffers: tell every rank (phase 0 ends)
-    const ShardPeers peers = shard_peers(e->shard);
-    CU(e, launch_shard_signal(peers, sh.rank, sh.world, ++e->shard.epoch, e->stream));
-    e->launches++;
+    if (!defer_signal) {  // (the fused exchange kernel signals the arrival itself)
+      const ShardPeers peers = shard_peers(e->shard);
+      CU(e, launch_shard_signal(peers, sh.rank, sh.world, ++e->shard.epoch, e->stream));
+      e->launches++;
+    }
     e->shard_phase = 1;
     e->shard_result = true;
   }
@@ -1115,7 +1122,7 @@ int wbx_mix_sharded_phase(wbx_engine* e, int phase) {
     if (rc && rc != WBX_ERR_INVALID) e->shard_phase = 0;  // a failed launch ends this collective (see wbx_shard_reset)
     return rc;
   }
-  if (phase != 0) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded_phase: phase %d", phase);
+  if (phase != 0 && phase != 3) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded_phase: phase %d", phase);
   if (!e->submitted) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded before wbx_submit");
   const Shard& sh = e->shard;
   if (!sh.on || !sh.connected) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded: call wbx_shard_init and wbx_shard_connect_* first");
@@ -1123,16 +1130,38 @@ int wbx_mix_sharded_phase(wbx_engine* e, int phase) {
   if (e->n_blocks > sh.max_blocks)
     return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded: %u callbacks > max_blocks %u of wbx_shard_init", e->n_blocks, sh.max_blocks);
   if (e->shard_phase != 0) return fail(e, WBX_ERR_INVALID, "wbx_mix_sharded: the previous sharded mix stopped in phase %d", e->shard_phase);
-  const int rc = do_mix(e, 0, true);
+  int rc = do_mix(e, 0, true, phase == 3);
+  if (!rc && phase == 3) {  // phases 1 + 2 (and phase 0's signal) in one launch
+    Shard& s2 = e->shard;
+    ShardPeers peers = shard_peers(s2);
+    if ((uint64_t)e->n_blocks * e->B > s2.host_out_frames) peers.host_dst[0] = peers.host_dst[1] = nullptr;
+    const uint32_t K = e->n_blocks, B = e->B;
+    const uint32_t Ks = (K + s2.world - 1) / s2.world;
+    const uint64_t k0 = (uint64_t)s2.rank * Ks;
+    const uint64_t valid = k0 < K ? ((k0 + Ks < K ? Ks : K - k0) * (uint64_t)B) : 0;
+    const uint32_t e1 = ++s2.epoch, e2 = ++s2.epoch;
+    cudaError_t err = launch_shard_exchange((const float*)((uint8_t*)s2.block + s2.xchg_off), s2.world, e->C, (uint64_t)Ks * B, valid,
+                                            peers, (uint64_t)K * B, k0 * B, s2.rank, e1, e2, s2.timeout_ns, s2.status, s2.done_counter,
+                                            e->n_sm, e->stream);
+    if (err != cudaSuccess) rc = fail(e, WBX_ERR_CUDA, "shard exchange launch failed: %s", cudaGetErrorString(err));
+    e->launches++;
+    e->shard_phase = 0;
+  }
   if (rc) e->shard_phase = 0;
   return rc;
 }
 
+// One process or thread per GPU: the mix, then the WHOLE exchange (arrival signal, wait, owner reduce + clamp, completion
+// signal, wait) as one kernel launch. WBX_SHARD_FUSED=0 keeps the five separate launches of the phased form.
 int wbx_mix_sharded(wbx_engine* e) {
-  int rc = wbx_mix_sharded_phase(e, 0);
-  if (!rc) rc = wbx_mix_sharded_phase(e, 1);
-  if (!rc) rc = wbx_mix_sharded_phase(e, 2);
-  return rc;
+  static const bool fused = !(getenv("WBX_SHARD_FUSED") && atoi(getenv("WBX_SHARD_FUSED")) == 0);
+  if (!fused) {
+    int rc = wbx_mix_sharded_phase(e, 0);
+    if (!rc) rc = wbx_mix_sharded_phase(e, 1);
+    if (!rc) rc = wbx_mix_sharded_phase(e, 2);
+    return rc;
+  }
+  return wbx_mix_sharded_phase(e, 3);
 }
 
 int wbx_shard_reset(wbx_engine* e) {
@@ -1427,6 +1456,13 @@ int wbx_shard_init(wbx_engine* e, uint32_t rank, uint32_t world, uint32_t max_bl
     return fail(e, WBX_ERR_NOMEM, "cudaHostAlloc for the shard status word failed");
   }
   *sh.status = 0;
+  if (cudaMalloc((void**)&sh.done_counter, 256) != cudaSuccess || cudaMemset(sh.done_counter, 0, 256) != cudaSuccess) {
+    cudaFree(sh.block);
+    cudaFreeHost(sh.status);
+    sh.block = nullptr;
+    sh.status = nullptr;
+    return fail(e, WBX_ERR_NOMEM, "cudaMalloc for the shard exchange counter failed");
+  }
   if (const char* t = getenv("WBX_SHARD_TIMEOUT_MS"))
     if (atof(t) > 0) sh.timeout_ns = (unsigned long long)(atof(t) * 1e6);
   if (ipc_handle_out) {
@@ -1553,6 +1589,7 @@ int wbx_shard_close(wbx_engine* e) {
   }
   if (sh.block) cudaFree(sh.block);
   if (sh.status) cudaFreeHost(sh.status);
+  if (sh.done_counter) cudaFree(sh.done_counter);
   sh = Shard();
   e->shard_result = false;
   e->shard_phase = 0;

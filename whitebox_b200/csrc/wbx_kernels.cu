@@ -1760,6 +1760,88 @@ __global__ void shard_reduce_kernel(const float* __restrict__ xchg, uint32_t W, 
   }
 }
 
+// The whole exchange after a rank's mix in ONE launch (one process or thread per GPU: wbx_mix_sharded): signal this rank's
+// arrival, wait for every rank's, reduce this rank's slice of callbacks in rank order + clamp into the master bus (and the
+// host output), then — the last block to finish — signal completion and wait for every rank's. Five launches' worth of
+// latency become one. Blocks only ever spin on REMOTE flags, so no co-residency of the grid is assumed.
+template <int V>
+__global__ void __launch_bounds__(256)
+shard_exchange_kernel(const float* __restrict__ xchg, uint32_t W, uint32_t C, uint64_t plane, uint64_t valid, ShardPeers peers,
+                      uint64_t chan_stride, uint64_t dst_off, uint32_t rank, uint32_t epoch_arrive, uint32_t epoch_done,
+                      unsigned long long timeout_ns, volatile uint32_t* status, uint32_t* __restrict__ done_counter) {
+  __shared__ uint32_t is_last;
+  const uint32_t tid = threadIdx.x;
+  auto wait_all = [&](uint32_t epoch) {
+    if (tid < W) {
+      volatile uint32_t* mine = peers.flags[rank] + tid;
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while ((int32_t)(*mine - epoch) < 0) {
+        __nanosleep(64);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+          *status = 1u;
+          break;
+        }
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+  };
+  if (blockIdx.x == 0) {  // this rank's tiles are all on their way (the mix kernel before this launch has completed)
+    __threadfence_system();
+    if (tid < W) *(volatile uint32_t*)(peers.flags[tid] + rank) = epoch_arrive;
+  }
+  wait_all(epoch_arrive);
+  const uint64_t n = valid / V;
+  for (uint32_t c = 0; c < C; c++) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+      float acc[V];
+#pragma unroll
+      for (int q = 0; q < V; q++) acc[q] = 0.0f;
+      for (uint32_t s = 0; s < W; s++) {
+        const float* src = xchg + ((size_t)s * C + c) * plane;
+        float v[V];
+        if constexpr (V == 4) {
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(src) + i);
+          v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+        } else {
+          v[0] = __ldcg(src + i);
+        }
+#pragma unroll
+        for (int q = 0; q < V; q++) acc[q] = s == 0 ? v[q] : __fadd_rn(acc[q], v[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < V; q++) acc[q] = acc[q] > 1.0f ? 1.0f : (acc[q] < -1.0f ? -1.0f : acc[q]);  // NaN passes
+      for (uint32_t d = 0; d < peers.n_dst; d++) {
+        float* out = peers.dst[d] + (size_t)c * chan_stride + dst_off;
+        if constexpr (V == 4)
+          reinterpret_cast<float4*>(out)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else
+          out[i] = acc[0];
+      }
+      if (peers.host_dst[c]) {  // posted stores over this rank's own PCIe link
+        float* out = peers.host_dst[c] + dst_off;
+        if constexpr (V == 4)
+          reinterpret_cast<float4*>(out)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else
+          out[i] = acc[0];
+      }
+    }
+  }
+  // the last block to get here publishes this rank's completion and waits for everybody's
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (is_last) {
+    __threadfence_system();
+    if (tid < W) *(volatile uint32_t*)(peers.flags[tid] + rank) = epoch_done;
+    wait_all(epoch_done);
+    if (tid == 0) *done_counter = 0u;
+  }
+}
+
 // Realtime callback (one-callback render): the submitted table (spans | gains | cells) is pulled from page-locked host
 // memory by this kernel and the mix's zero region is cleared by it too, so the callback is kernels only — no hop between
 // the copy engine and the SMs (each costs several microseconds of the ~60 a callback takes).
@@ -2130,6 +2212,26 @@ cudaError_t launch_shard_reduce(const float* xchg, uint32_t W, uint32_t C, uint6
     shard_reduce_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(xchg, W, C, plane, valid, peers, chan_stride, dst_off);
   else
     shard_reduce_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(xchg, W, C, plane, valid, peers, chan_stride, dst_off);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_shard_exchange(const float* xchg, uint32_t W, uint32_t C, uint64_t plane, uint64_t valid, const ShardPeers& peers,
+                                  uint64_t chan_stride, uint64_t dst_off, uint32_t rank, uint32_t epoch_arrive, uint32_t epoch_done,
+                                  unsigned long long timeout_ns, uint32_t* status, uint32_t* done_counter, int n_sm,
+                                  cudaStream_t stream) {
+  bool v4 = (plane % 4 == 0) && (valid % 4 == 0) && (chan_stride % 4 == 0) && (dst_off % 4 == 0);
+  for (int c = 0; c < 2; c++)
+    if (peers.host_dst[c] && ((uintptr_t)peers.host_dst[c] & 15u)) v4 = false;
+  const uint64_t n = v4 ? valid / 4 : valid;
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > (uint64_t)n_sm * 4) blocks = (uint64_t)n_sm * 4;
+  if (blocks < 1) blocks = 1;
+  if (v4)
+    shard_exchange_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(xchg, W, C, plane, valid, peers, chan_stride, dst_off, rank,
+                                                                   epoch_arrive, epoch_done, timeout_ns, status, done_counter);
+  else
+    shard_exchange_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(xchg, W, C, plane, valid, peers, chan_stride, dst_off, rank,
+                                                                   epoch_arrive, epoch_done, timeout_ns, status, done_counter);
   return cudaGetLastError();
 }
 
