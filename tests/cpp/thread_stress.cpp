@@ -27,6 +27,11 @@ int wbx_render_levels(wbx_engine*, const wbx_segment*, uint32_t, const float*, u
 int wbx_submit(wbx_engine*, const wbx_segment*, uint32_t, const float*, uint32_t) { return WBX_ERR_NO_DEVICE; }
 int wbx_fetch(wbx_engine*, float* const*, float*) { return WBX_ERR_NO_DEVICE; }
 int wbx_fetch_levels(wbx_engine*, float*) { return WBX_ERR_NO_DEVICE; }
+int wbx_mix(wbx_engine*, uint32_t) { return WBX_ERR_NO_DEVICE; }
+int wbx_bounce_begin(wbx_engine*, int) { return WBX_ERR_NO_DEVICE; }
+int wbx_bounce_push(wbx_engine*) { return WBX_ERR_NO_DEVICE; }
+int wbx_bounce_pop(wbx_engine*, const void**, size_t*) { return WBX_ERR_NO_DEVICE; }
+int wbx_synchronize(wbx_engine*) { return WBX_ERR_NO_DEVICE; }
 }
 
 int main(int argc, char** argv) {
