@@ -288,6 +288,9 @@ uint64_t wbx_launch_count(const wbx_engine* e);
 /* Reduced-precision tensor-core products issued per tap by the convolution reverb (split-precision factor; 3 = 2-term fp16
  * split of both operands). */
 int wbx_fir_split_factor(void);
+/* The path the convolution reverb of this engine's impulse response takes: 0 direct form (CUDA cores), 1 direct form as a
+ * Toeplitz GEMM on the tensor cores, 2 partitioned FFT convolution. Chosen at wbx_set_impulse_response (>= 1024 taps: 2). */
+int wbx_fir_path(const wbx_engine* e);
 /* Name of the mix kernel variant the last wbx_mix used ("exact/vec16", "tree/g8", ...). */
 const char* wbx_last_kernel(const wbx_engine* e);
 

@@ -154,13 +154,29 @@ def test_effects_bench_shape_vs_port(wb, n_tracks):
         assert_exact(sc.effects_shapes(gpu_engine(wb, False), wb.effect_params, **shape), ref, "effects per callback")
 
 
-@pytest.mark.parametrize("mode", ["direct", "tc"])
+FX_SHAPES = ["1,4,1,1", "2,4,1,1", "4,2,1,1", "4,2,2,1", "2,2,1,2", "2,2,2,2", "1,2,1,4", "1,2,2,4", "1,4,2,2"]
+
+
+@pytest.mark.parametrize("fx_shape", FX_SHAPES)
+def test_effects_every_kernel_shape_vs_port(wb, fx_shape, monkeypatch):
+    """Every compiled instantiation of fx_chain_kernel (tracks per CTA, output warps, EQ warps, CTAs per SM — normally
+    chosen from the session size), forced with WBX_FX_SHAPE: whole chunks, a ragged multi-chunk block with state carried
+    across renders, and an odd block, each == the C spec bit for bit."""
+    monkeypatch.setenv("WBX_FX_SHAPE", fx_shape)
+    for shape in (dict(n_tracks=24, block=512, n_blocks=5), dict(n_tracks=10, block=1030, n_blocks=3, chunks=[1, 2]),
+                  dict(n_tracks=9, block=101, n_blocks=6)):
+        ref = sc.effects_shapes(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params, **shape)
+        assert_exact(sc.effects_shapes(gpu_engine(wb, True), wb.effect_params, **shape), ref, "effects %s %r" % (fx_shape, shape))
+
+
+@pytest.mark.parametrize("mode", ["direct", "tc", "fft", "fft512"])
 @pytest.mark.parametrize("taps", [1, 2, 777, 2048])
 def test_reverb_extension_vs_port(wb, taps, mode, monkeypatch):
     """EXTENSION, parity unpinned (BASELINE cfg 5 at test size): the convolution reverb — direct form on the CUDA
-    cores and the tcgen05 tensor-core Toeplitz GEMM (3-term bf16 split) — against the port's f64-accumulated
-    specification, within 1e-5 of the block peak (bus and VU peaks), history carried across renders."""
-    monkeypatch.setenv("WBX_FIR", mode)
+    cores, the tcgen05 tensor-core Toeplitz GEMM (2-term fp16 split) and the partitioned FFT convolution (2048- and
+    512-tap partitions) — against the port's f64-accumulated specification, within 1e-5 of the block peak (bus and VU
+    peaks), history carried across renders."""
+    _fir_mode(monkeypatch, mode)
     ref = sc.reverb(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params, taps)
     res = sc.reverb(gpu_engine(wb, True), wb.effect_params, taps)
     peak = np.abs(ref["out"]).max(axis=(1, 2), keepdims=True)
@@ -171,9 +187,16 @@ def test_reverb_extension_vs_port(wb, taps, mode, monkeypatch):
     assert same_bits(res["sampler_offsets"], ref["sampler_offsets"])
 
 
-def test_reverb_cfg5_tap_count_tensor_cores(wb, monkeypatch):
-    """BASELINE cfg 5's 65536-tap impulse response on the tensor-core path, against the f64 specification."""
-    monkeypatch.setenv("WBX_FIR", "tc")
+def _fir_mode(monkeypatch, mode):
+    """WBX_FIR picks the reverb path when an impulse response is set; "fft512" = the FFT path with 512-tap partitions."""
+    monkeypatch.setenv("WBX_FIR", "fft" if mode.startswith("fft") else mode)
+    monkeypatch.setenv("WBX_FFT_P", "512" if mode == "fft512" else "2048")
+
+
+@pytest.mark.parametrize("mode", ["tc", "fft", "fft512"])
+def test_reverb_cfg5_tap_count(wb, mode, monkeypatch):
+    """BASELINE cfg 5's 65536-tap impulse response on the tensor-core and FFT paths, against the f64 specification."""
+    _fir_mode(monkeypatch, mode)
     ref = sc.reverb(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params, 65536)
     res = sc.reverb(gpu_engine(wb, True), wb.effect_params, 65536)
     peak = np.abs(ref["out"]).max(axis=(1, 2), keepdims=True)
@@ -181,13 +204,14 @@ def test_reverb_cfg5_tap_count_tensor_cores(wb, monkeypatch):
     assert np.all(err <= 1e-5 * peak), "reverb bus error %.3g of block peak" % float((err / peak).max())
 
 
+@pytest.mark.parametrize("mode", ["tc", "fft", "fft512"])
 @pytest.mark.parametrize("chunks", [None, [64, 64, 32]])
-def test_reverb_cfg5_full_accumulation_depth(wb, chunks, monkeypatch):
-    """BASELINE cfg 5 on the tensor-core path at full depth: 64 stereo tracks (128 signals) x 160 callbacks x 512 frames
+def test_reverb_cfg5_full_accumulation_depth(wb, chunks, mode, monkeypatch):
+    """BASELINE cfg 5 on the tensor-core and FFT paths at full depth: 64 stereo tracks (128 signals) x 160 callbacks x 512 frames
     (81920 frames of signal > 65536 taps, in one render and carried across three), against the f64 specification; bus
     and VU peaks within 1e-5 of the block / track peak. Every one of the 1027 tap chunks multiplies real history here
     (the 777...65536-tap scenario above only ever fills 33 of them)."""
-    monkeypatch.setenv("WBX_FIR", "tc")
+    _fir_mode(monkeypatch, mode)
     res = sc.reverb_full_depth(gpu_engine(wb, True), wb.effect_params, chunks=chunks)
     want, want_peaks = sc.reverb_f64_expected(res, wb.panning_coefs, wb.db_to_linear)
     peak = np.abs(want).max(axis=(1, 2), keepdims=True)

@@ -175,31 +175,41 @@ def test_runs_are_merged(wb):
 def test_no_fma_contraction_in_mix_kernels(wb):
     """Parity depends on every multiply and add being separately rounded. nvcc -fmad=false covers scalar code,
     but ptxas (12.9) still contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 when the product has a single use,
-    so lint the SASS: inside mix_kernel the only fused ops allowed are the intended `a * -1 + b` (= b - a)."""
+    so lint the SASS: inside mix_kernel the only fused ops allowed are the intended `a * -1 + b` (= b - a) and
+    `prod * one + a` with a run-time 1.0f (= prod + a), one of each per lerp site."""
     import shutil
     import subprocess
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run(["cuobjdump", "-sass", wb.LIB_PATH], capture_output=True, text=True).stdout
     fn, bad, seen = None, [], 0
+    neg1, other, fmul2 = {}, {}, {}
     for line in sass.splitlines():
         if "Function :" in line:
             fn = line.split("Function :")[1].strip()
             continue
         if fn and "mix_kernel" in fn:
             seen += 1
-            body = line.split("/*")[1].split("*/")[-1] if line.count("/*") >= 2 else line
             # DFMA is not linted: the f64 path uses only __dadd_rn/__dmul_rn/__ddiv_rn and the correctly rounded
             # division itself expands to DFMA Newton steps (fade envelope, K_FADE)
-            for op in ("FFMA2", "FFMA"):
-                if (" " + op + " ") in line or (" " + op + ".") in line:
-                    if op == "FFMA2" and ", -1, " in line:
-                        continue
-                    if op == "FFMA" and "FFMA2" not in line:
-                        continue  # integer-division helpers (work-item decode) use scalar FFMA on non-audio values
-                    bad.append((fn[:40], line.strip()[:90]))
+            if " FMUL2 " in line or " FMUL2." in line:
+                fmul2[fn] = fmul2.get(fn, 0) + 1
+            if " FFMA2 " in line or " FFMA2." in line:
+                if ", -1, " in line:
+                    neg1[fn] = neg1.get(fn, 0) + 1  # b - a
+                else:
+                    other[fn] = other.get(fn, 0) + 1  # prod * one + a with the run-time 1.0f (consume_lin_t)
+            elif " FFMA " in line or " FFMA." in line:
+                pass  # integer-division helpers (work-item decode) use scalar FFMA on non-audio values
     assert seen > 1000, "mix_kernel SASS not found"
-    assert not bad, "fused multiply-adds on the audio path: %s" % bad[:5]
+    # every 2-tap lerp site holds exactly one `a * -1 + b`, one `prod * one + a` and three packed multiplies (fx * df,
+    # * clip gain, * track gain); a contraction anywhere (lerp, fast path, unity path) adds an FFMA2 or removes an FMUL2
+    for f in set(neg1) | set(other):
+        n = neg1.get(f, 0)
+        if other.get(f, 0) != n or fmul2.get(f, 0) < 3 * n:
+            bad.append((f[:50], n, other.get(f, 0), fmul2.get(f, 0)))
+    assert neg1, "lerp sites not found"
+    assert not bad, "fused multiply-adds on the audio path (function, b-a, other FFMA2, FMUL2): %s" % bad[:5]
 
 
 def build_dropin_demo(tmp):

@@ -58,7 +58,7 @@ WBX_SYMBOLS = [
     "wbx_abi_version", "wbx_create", "wbx_destroy", "wbx_last_error", "wbx_configure", "wbx_set_track_count",
     "wbx_set_sum_mode", "wbx_set_stream", "wbx_sample_upload", "wbx_sample_release", "wbx_sample_update", "wbx_sample_mipmap", "wbx_render", "wbx_submit",
     "wbx_mix", "wbx_fetch", "wbx_fetch_levels", "wbx_host_alloc", "wbx_host_free", "wbx_fetch_interleaved", "wbx_device_bus", "wbx_device_peaks", "wbx_clamp_device",
-    "wbx_synchronize", "wbx_launch_count", "wbx_fir_split_factor", "wbx_last_kernel", "wbx_effects_design", "wbx_set_track_effects",
+    "wbx_synchronize", "wbx_launch_count", "wbx_fir_split_factor", "wbx_fir_path", "wbx_last_kernel", "wbx_effects_design", "wbx_set_track_effects",
     "wbx_set_impulse_response", "wbx_render_levels", "wbx_bounce_begin", "wbx_bounce_push", "wbx_bounce_pop", "wbx_shard_init", "wbx_shard_connect_ipc",
     "wbx_shard_connect_local", "wbx_mix_sharded", "wbx_mix_sharded_phase", "wbx_shard_reset", "wbx_shard_set_host_output", "wbx_host_register",
     "wbx_host_unregister", "wbx_shard_close", "wbx_shard_info",

@@ -30,7 +30,7 @@ cudaError_t launch_mip_merge(const void* child, uint64_t child_mdc, void* parent
                              int n_sm, cudaStream_t stream);
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
-                           float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, const float* poly,
+                           float* fir_hist, float* fir_in, int fir_mode, void* fir_ir_aux, void* fir_scratch, const float* poly,
                            uint32_t fx_flags, uint32_t* sm_arrivals, uint64_t tbs, cudaStream_t stream);
 cudaError_t launch_shard_signal(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch, cudaStream_t stream);
 cudaError_t launch_shard_wait(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch,
@@ -50,6 +50,10 @@ uint64_t fir_tc_plane_width(uint64_t H, uint64_t T);
 cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, float h_scale, cudaStream_t stream);
 size_t fir_tc_scratch_bytes(uint64_t H, uint64_t T, uint32_t S);
 int fir_tc_split_factor();
+uint32_t fir_fft_partition();
+size_t fir_fft_ir_bytes(uint32_t L, uint32_t P);
+size_t fir_fft_scratch_bytes(uint64_t T, uint32_t L, uint32_t n_fx, uint32_t P);
+cudaError_t launch_fir_fft_prepare(const float* ir, uint32_t L, void* ir_spectra, uint32_t P, cudaStream_t stream);
 }  // namespace wbx
 
 using namespace wbx;
@@ -143,7 +147,9 @@ struct wbx_engine {
   uint32_t n_fx = 0;                 // chains resident in d_fx
   uint32_t ir_taps = 0;              // convolution reverb: taps of the impulse response in d_ir
   uint32_t firhist_tracks = 0;       // tracks d_firhist is sized (and zeroed) for
-  bool fir_tc = false;               // impulse response expanded for the tensor-core path (d_irtiles)
+  int fir_mode = 0;                  // reverb path: 0 direct form, 1 tensor cores (d_irtiles = Toeplitz tiles), 2 partitioned FFT
+                                     // (d_irtiles = twiddles + partition spectra)
+  uint32_t fir_fft_p = 0;            // partition size of the FFT path the spectra in d_irtiles were built for
   float* mirror[2] = {nullptr, nullptr};       // device view of page-locked caller channels the running render also writes
   float* mirror_host[2] = {nullptr, nullptr};  // ... and the caller's pointers they belong to (wbx_render)
   bool levels_queued = false;              // level reduce + copy into h_levels already enqueued for this mix
@@ -636,10 +642,11 @@ int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps) {
   int rc = dev_reserve(e, e->d_ir, (size_t)n_taps * sizeof(float));
   if (rc) return rc;
   CU(e, cudaMemcpyAsync(e->d_ir.p, h, (size_t)n_taps * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  // long responses run on the tensor cores (WBX_FIR=direct / tc overrides the 1024-tap threshold)
+  // long responses run as a partitioned FFT convolution, short ones in direct form; WBX_FIR=direct / tc / fft picks the path
+  // by hand (tc = the direct form as a Toeplitz GEMM on the tensor cores)
   const char* mode = getenv("WBX_FIR");
-  e->fir_tc = mode ? (mode[0] == 't') : (n_taps >= 1024);
-  if (e->fir_tc) {
+  e->fir_mode = mode ? (mode[0] == 't' ? 1 : (mode[0] == 'f' ? 2 : 0)) : (n_taps >= 1024 ? 2 : 0);
+  if (e->fir_mode == 1) {
     if ((rc = dev_reserve(e, e->d_irtiles, fir_tc_tiles_bytes(n_taps)))) return rc;
     // fp16 operands: scale the response so that its largest tap lands in [2^13, 2^14) (undone exactly in the epilogue)
     float hmax = 0.0f;
@@ -651,6 +658,11 @@ int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps) {
       h_scale = std::ldexp(1.0f, 14 - ex);
     }
     CU(e, launch_fir_tc_prepare((const float*)e->d_ir.p, n_taps, e->d_irtiles.p, h_scale, e->stream));
+    e->launches++;
+  } else if (e->fir_mode == 2) {
+    e->fir_fft_p = fir_fft_partition();
+    if ((rc = dev_reserve(e, e->d_irtiles, fir_fft_ir_bytes(n_taps, e->fir_fft_p)))) return rc;
+    CU(e, launch_fir_fft_prepare((const float*)e->d_ir.p, n_taps, e->d_irtiles.p, e->fir_fft_p, e->stream));
     e->launches++;
   }
   CU(e, cudaStreamSynchronize(e->stream));
@@ -944,16 +956,19 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
       if (H == 0 && (rc = dev_reserve(e, e->d_firhist, 256))) return rc;
     }
     const bool rv = e->ir_taps > 0 && (reverb || e->ir_taps == 1);
-    const bool tc = rv && e->fir_tc;
-    if (tc) {
+    const int fmode = rv ? e->fir_mode : 0;
+    if (fmode == 1) {
       if ((rc = dev_reserve(e, e->d_firplanes, fir_tc_scratch_bytes(e->ir_taps - 1, (uint64_t)n_blocks * B, n_fx * C)))) return rc;
+    } else if (fmode == 2) {
+      if ((rc = dev_reserve(e, e->d_firplanes, fir_fft_scratch_bytes((uint64_t)n_blocks * B, e->ir_taps, n_fx, e->fir_fft_p)))) return rc;
     }
     CU(e, launch_effects((const DSpan*)e->d_spans.p, e->cells_ptr, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
                          n_segs, (float*)e->d_trackbuf.p, rv ? (const float*)e->d_ir.p : nullptr, rv ? e->ir_taps : 0,
-                         (float*)e->d_firhist.p, (float*)e->d_firin.p, tc ? e->d_irtiles.p : nullptr,
-                         tc ? e->d_firplanes.p : nullptr, (const float*)e->d_poly.p, e->fx_flags, (uint32_t*)e->d_smarr.p,
+                         (float*)e->d_firhist.p, (float*)e->d_firin.p, fmode == 2 ? (int)(2u | (e->fir_fft_p << 8)) : fmode,
+                         fmode ? e->d_irtiles.p : nullptr,
+                         fmode ? e->d_firplanes.p : nullptr, (const float*)e->d_poly.p, e->fx_flags, (uint32_t*)e->d_smarr.p,
                          (((uint64_t)n_blocks * B + 1) & ~(uint64_t)1), e->stream));
-    e->launches += (rv ? (tc ? 5 : 4) : 1) + ((e->fx_flags & 1u) ? 1 : 0) + ((e->fx_flags & 2u) ? 1 : 0);
+    e->launches += (rv ? (fmode == 2 ? 6 : (fmode == 1 ? 5 : 4)) : 1) + ((e->fx_flags & 1u) ? 1 : 0) + ((e->fx_flags & 2u) ? 1 : 0);
   }
   e->n_blocks = n_blocks;
   e->n_spans = n_segs;
@@ -1048,6 +1063,7 @@ static int do_mix(wbx_engine* e, uint32_t flags, bool sharded, bool defer_signal
   p.n_items = K * n_tiles * groups;
   p.clamp = (flags & WBX_MIX_NO_CLAMP) ? 0u : 1u;
   p.ext = e->seg_flags ? 1u : 0u;
+  p.one = 1.0f;
   p.mirror[0] = e->mirror[0];
   p.mirror[1] = e->mirror[1];
   for (uint32_t j = 0; j < kMaxPeers; j++) p.xchg[j] = nullptr;
@@ -1635,6 +1651,8 @@ int wbx_synchronize(wbx_engine* e) {
 
 uint64_t wbx_launch_count(const wbx_engine* e) { return e ? e->launches : 0; }
 int wbx_fir_split_factor(void) { return fir_tc_split_factor(); }
+
+int wbx_fir_path(const wbx_engine* e) { return e ? e->fir_mode : WBX_ERR_INVALID; }
 const char* wbx_last_kernel(const wbx_engine* e) { return e ? e->kernel_name : ""; }
 
 }  // extern "C"

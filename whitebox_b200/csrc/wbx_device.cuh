@@ -180,6 +180,7 @@ struct MixParams {
   uint32_t n_items;     // n_blocks * n_tiles * groups
   uint32_t clamp;       // apply the [-1, 1] clamp
   uint32_t ext;         // some segment carries an extension flag (fade / polyphase): use the full kernel build
+  float one;            // 1.0f, opaque to ptxas (see consume_lin_t)
   // optional second destination of every bus tile: the caller's page-locked AudioBuffer channels, written from the
   // kernel over PCIe (posted stores) so no device-to-host copy follows the mix. nullptr = off.
   float* mirror[2];

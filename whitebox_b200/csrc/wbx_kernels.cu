@@ -21,6 +21,7 @@
 #include <type_traits>
 
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
 #include "wbx_device.cuh"
@@ -439,18 +440,29 @@ __device__ __forceinline__ void consume_uni(const Desc& d, const uint8_t* row, f
 // The position split avoids the slow f64<->int conversions: for 0 <= x < 2^31, t = x + 2^52 rounded TOWARDS
 // -INF is exactly floor(x) + 2^52 (the ulp there is 1), so its low mantissa word is (int64_t)x and
 // x - (t - 2^52) is x - (double)ix — both subtractions exact — as in sampler.cpp:51-52.
+// 64-bit shared-memory load by 32-bit shared address: keeps the per-frame address to one integer multiply-add
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+
+// `one` is 1.0f read from the kernel parameters — a value ptxas cannot see: fma(prod, one, a) is add_rn(prod, a)
+// exactly (prod * 1 is exact, one rounding), but unlike mul.rn.f32x2 + add.rn.f32x2 it cannot be contracted into a
+// fused multiply-add of the product's own factors (ptxas does that even under --fmad false when the product has a
+// single use; tests/test_host_cpu.py lints the SASS). It makes the lerp three packed instructions instead of five.
 template <int FPL, bool FULL>
 __device__ __forceinline__ void consume_lin_t(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
-                                              float& pkR, int lane) {
-  const float2* r2 = reinterpret_cast<const float2*>(row);
+                                              float& pkR, int lane, float one) {
   const int lo = d.lo, hi = d.hi;
-  const float2* rb = r2 - d.base;
+  const uint32_t rb = smem_u32(row) - (uint32_t)d.base * 8u;  // shared address of source frame 0 (wraps; only sums are used)
   const double pos = d.pos, speed = d.speed;
   const double M = 4503599627370496.0;  // 2^52
   const double jj0 = (double)(d.jrel0 + 2 * lane);
   const float2 g2 = make_float2(d.gain, d.gain);
   const float2 t2 = make_float2(d.tg[0], d.tg[1]);
   const float2 neg1 = make_float2(-1.0f, -1.0f);
+  const float2 one2 = make_float2(one, one);
 #pragma unroll
   for (int i = 0; i < FPL / 2; i++) {
     float2 term[2];
@@ -462,15 +474,13 @@ __device__ __forceinline__ void consume_lin_t(const Desc& d, const uint8_t* row,
         const double jj = __dadd_rn(jj0, (double)(64 * i + e));  // exact small integers == (double)j
         const double x = __dadd_rn(pos, __dmul_rn(jj, speed));   // sampler.cpp:50
         const double t = __dadd_rd(x, M);                        // floor(x) + 2^52
-        const int ix = __double2loint(t);                        // (int64_t)x, :51
+        const uint32_t ix = (uint32_t)__double2loint(t);         // (int64_t)x, :51
         const float fx = __double2float_rn(__dsub_rn(x, __dsub_rn(t, M)));  // (float)(x - (double)ix), :52
-        const float2 a = rb[ix], b = rb[ix + 1];
-        const float2 df = __ffma2_rn(a, neg1, b);  // b - a (a * -1 is exact: one rounding)
-        // a + fx * (b - a), :55 — scalar _rn ops on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
-        // FFMA2 when the product has no other use, even under --fmad false (tests/test_host_cpu.py lints SASS)
-        float2 sv;
-        sv.x = __fadd_rn(a.x, __fmul_rn(fx, df.x));
-        sv.y = __fadd_rn(a.y, __fmul_rn(fx, df.y));
+        const uint32_t addr = rb + ix * 8u;
+        const float2 a = lds_f2(addr), b = lds_f2(addr + 8u);
+        const float2 df = __ffma2_rn(a, neg1, b);                         // b - a (a * -1 is exact: one rounding)
+        const float2 pr = __fmul2_rn(make_float2(fx, fx), df);            // fx * (b - a)
+        const float2 sv = __ffma2_rn(pr, one2, a);                        // a + fx * (b - a), :55 (see `one` above)
         term[e] = __fmul2_rn(__fmul2_rn(sv, g2), t2);
         acc[i * 2 + e] = __fadd2_rn(acc[i * 2 + e], term[e]);
       }
@@ -482,11 +492,11 @@ __device__ __forceinline__ void consume_lin_t(const Desc& d, const uint8_t* row,
 
 template <int FPL>
 __device__ __forceinline__ void consume_lin(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
-                                            float& pkR, int lane) {
+                                            float& pkR, int lane, float one) {
   if (d.lo == 0 && d.hi == 32 * FPL)  // whole tile: no per-frame range checks
-    consume_lin_t<FPL, true>(d, row, acc, pkL, pkR, lane);
+    consume_lin_t<FPL, true>(d, row, acc, pkL, pkR, lane, one);
   else
-    consume_lin_t<FPL, false>(d, row, acc, pkL, pkR, lane);
+    consume_lin_t<FPL, false>(d, row, acc, pkL, pkR, lane, one);
 }
 
 // Stereo f32, polyphase windowed-sinc resample (extension) from the staged window: the lin path's position split,
@@ -765,7 +775,7 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
           } else if (kind == K_UNI) {
             consume_uni<FPL>(*dp, row, acc, pkL, pkR, lane);
           } else if (kind == K_LIN) {
-            consume_lin<FPL>(*dp, row, acc, pkL, pkR, lane);
+            consume_lin<FPL>(*dp, row, acc, pkL, pkR, lane, p.one);
           } else if (EXT && kind == K_POLY) {
             consume_poly<FPL>(*dp, row, p.poly, acc, pkL, pkR, lane);
           } else {
@@ -781,20 +791,17 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
         if (++slot_ctr == S) {
           slot_ctr = 0;
           if (active) {
-            // lanes 0-15 reduce L, lanes 16-31 reduce R: one exchange, then four butterfly steps
-            const float send = (lane < 16) ? pkR : pkL;
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-            float m = fmaxf((lane < 16) ? pkL : pkR, recv);
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            if ((lane & 15) == 0 && (lane == 0 || two)) {
-              float* dst = peaks_k + (size_t)cur_track * 2 + (lane >> 4);
+            // peaks are >= 0 and never NaN (fmaxf drops NaNs), so uint order == float order: one warp-wide integer
+            // max per channel (REDUX) instead of a five-step shuffle butterfly and its serial latency
+            const uint32_t mL = __reduce_max_sync(0xffffffffu, __float_as_uint(pkL));
+            const uint32_t mR = __reduce_max_sync(0xffffffffu, __float_as_uint(pkR));
+            if (lane < 2 && (lane == 0 || two)) {
+              const uint32_t m = lane ? mR : mL;
+              uint32_t* dst = reinterpret_cast<uint32_t*>(peaks_k + (size_t)cur_track * 2 + lane);
               if (p.n_tiles == 1)
                 *dst = m;
-              else if (m > 0.0f)
-                atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(m));  // m >= 0: uint order == float order
+              else if (m != 0u)
+                atomicMax(dst, m);
             }
             pkL = 0.0f;
             pkR = 0.0f;
@@ -1173,21 +1180,21 @@ __device__ __forceinline__ float fxc_step(float ev, const float (&s4)[5], float 
   return fmaxf(fmaxf(fmaxf(t0, t1), t2), fmaxf(t3, t4));
 }
 
-template <int TPC>
+template <int TPC, int OW_, int EQW_>
 struct FxcShape {
-  static constexpr int OW = TPC == 4 ? 2 : 4;  // output warps per track
-  static constexpr int EQW = 1;                // EQ warps per track: 1 = all four biquads in one warp, 2 = a / b pipeline
+  static constexpr int OW = OW_;    // output warps per track
+  static constexpr int EQW = EQW_;  // EQ warps per track: 1 = all four biquads in one warp, 2 = a / b pipeline
   static constexpr int WARPS = 1 + EQW * TPC + TPC * OW;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int OLANES = OW * 32;       // lanes rendering / finishing one track
 };
 
-template <int TPC>
-__global__ void __launch_bounds__(FxcShape<TPC>::THREADS, 1)
+template <int TPC, int OW_, int EQW_, int MINB>
+__global__ void __launch_bounds__((FxcShape<TPC, OW_, EQW_>::THREADS), MINB)
 fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells, DFx* __restrict__ fx, uint32_t n_fx, uint32_t N,
                 uint32_t S, uint32_t K, uint32_t B, uint32_t C, const float* __restrict__ poly, float* __restrict__ trackbuf,
                 uint64_t tbs) {
-  using SH = FxcShape<TPC>;
+  using SH = FxcShape<TPC, OW_, EQW_>;
   extern __shared__ __align__(16) unsigned char fxc_raw[];
   FxcSmem<TPC>& sm = *reinterpret_cast<FxcSmem<TPC>*>(fxc_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1552,34 +1559,48 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
   if (ser_lane && (lane & 1) < (int)C) f->env[lane & 1] = sgn * env_s;
 }
 
-template <int TPC>
+template <int TPC, int OW, int EQW, int MINB>
 static cudaError_t launch_effects_chain_t(const DSpan* spans, const DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S,
                                           uint32_t K, uint32_t B, uint32_t C, const float* poly, float* trackbuf, uint64_t tbs,
                                           cudaStream_t stream) {
-  auto kfn = fx_chain_kernel<TPC>;
+  auto kfn = fx_chain_kernel<TPC, OW, EQW, MINB>;
   const size_t smem = sizeof(FxcSmem<TPC>);
   cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  kfn<<<(n_fx + TPC - 1) / TPC, FxcShape<TPC>::THREADS, smem, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs);
+  kfn<<<(n_fx + TPC - 1) / TPC, FxcShape<TPC, OW, EQW>::THREADS, smem, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf,
+                                                                                 tbs);
   return cudaGetLastError();
 }
 
-// Tracks per CTA: the serial warp walks one instruction stream for all pairs of its CTA, so a CTA should carry as many
-// tracks as it takes to give every SM one CTA (4 at most: shared memory); WBX_FX_TPC overrides.
+// Shape = (tracks per CTA, output warps per track, EQ warps per track, CTAs per SM). The serial warp walks one instruction
+// stream for all pairs of its CTA, so a CTA should carry as many tracks as it takes to give every SM its share; several
+// small CTAs per SM decouple their per-chunk barriers. WBX_FX_SHAPE="tpc,ow,eqw,ctas" picks a compiled shape by hand.
 static cudaError_t launch_effects_chain(const DSpan* spans, const DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S,
                                         uint32_t K, uint32_t B, uint32_t C, const float* poly, float* trackbuf,
                                         uint64_t tbs, int n_sm, cudaStream_t stream) {
   static_assert(sizeof(FxcSmem<4>) <= 227 * 1024, "fx_chain_kernel shared memory");
-  int tpc = n_fx <= (uint32_t)n_sm ? 1 : (n_fx <= 2u * (uint32_t)n_sm ? 2 : 4);
-  if (const char* env = getenv("WBX_FX_TPC")) {
-    const int v = atoi(env);
-    if (v == 1 || v == 2 || v == 4) tpc = v;
+  static_assert(2 * sizeof(FxcSmem<2>) + 2048 <= 227 * 1024 && 4 * sizeof(FxcSmem<1>) + 4096 <= 227 * 1024, "CTAs per SM");
+  int shape = n_fx <= (uint32_t)n_sm ? 1410 : (n_fx <= 2u * (uint32_t)n_sm ? 2410 : 4210);
+  if (const char* env = getenv("WBX_FX_SHAPE")) {
+    int a = 0, b = 0, c = 0, d = 0;
+    if (sscanf(env, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) shape = a * 1000 + b * 100 + c * 10 + (d - 1);
   }
-  switch (tpc) {
-    case 1: return launch_effects_chain_t<1>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, stream);
-    case 2: return launch_effects_chain_t<2>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, stream);
-    default: return launch_effects_chain_t<4>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, stream);
+#define WBX_FX_CASE(TPC, OW, EQW, MINB) \
+  case TPC * 1000 + OW * 100 + EQW * 10 + (MINB - 1): \
+    return launch_effects_chain_t<TPC, OW, EQW, MINB>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, stream)
+  switch (shape) {
+    WBX_FX_CASE(1, 4, 1, 1);
+    WBX_FX_CASE(2, 4, 1, 1);
+    WBX_FX_CASE(4, 2, 1, 1);
+    WBX_FX_CASE(4, 2, 2, 1);
+    WBX_FX_CASE(2, 2, 1, 2);
+    WBX_FX_CASE(2, 2, 2, 2);
+    WBX_FX_CASE(1, 2, 1, 4);
+    WBX_FX_CASE(1, 2, 2, 4);
+    WBX_FX_CASE(1, 4, 2, 2);
+    default: return cudaErrorInvalidValue;
   }
+#undef WBX_FX_CASE
 }
 
 // ---- convolution reverb (extension, cfg 5): direct form on the CUDA cores --------------------------------
@@ -2135,10 +2156,13 @@ cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, ui
 cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T, uint32_t L, void* tiles,
                           const float* xin, void* scratch, float* trackbuf, uint64_t tbs, int n_sm, cudaStream_t stream);  // wbx_fir_tc.cu
 uint32_t* fir_tc_max_word(void* scratch);
+cudaError_t launch_fir_fft(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T, uint32_t L, const void* ir_spectra,
+                           const float* xin, void* scratch, float* trackbuf, uint64_t tbs, uint32_t P,
+                           cudaStream_t stream);  // wbx_fir_fft.cu
 
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
                            uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
-                           float* fir_hist, float* fir_in, void* tc_tiles, void* tc_planes, const float* poly,
+                           float* fir_hist, float* fir_in, int fir_mode, void* fir_ir_aux, void* fir_scratch, const float* poly,
                            uint32_t fx_flags, uint32_t* sm_arrivals, uint64_t tbs, cudaStream_t stream) {
   if (n_fx == 0) return cudaSuccess;
   const uint64_t warps = (uint64_t)n_fx * K;
@@ -2156,8 +2180,9 @@ cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n
   if (L && ir && fir_hist && fir_in) {  // convolution reverb as the chain's last stage
     const uint64_t T = (uint64_t)K * B, H = L - 1;
     const dim3 gcopy((unsigned)(((H + T) + 255) / 256 < 4096 ? ((H + T) + 255) / 256 : 4096), n_fx * C);
-    const bool tc = tc_tiles && tc_planes;
-    uint32_t* max_word = tc ? fir_tc_max_word(tc_planes) : nullptr;
+    const bool tc = fir_mode == 1 && fir_ir_aux && fir_scratch;
+    const bool fft = (fir_mode & 0xff) == 2 && fir_ir_aux && fir_scratch;  // bits 8.. = partition size
+    uint32_t* max_word = tc ? fir_tc_max_word(fir_scratch) : nullptr;
     if (max_word) {
       cudaError_t err = cudaMemsetAsync(max_word, 0, sizeof(uint32_t), stream);
       if (err != cudaSuccess) return err;
@@ -2167,7 +2192,10 @@ cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n
       int dev = 0, n_sm = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      cudaError_t err = launch_fir_tc(fx, n_fx, C, H, T, L, tc_tiles, fir_in, tc_planes, trackbuf, tbs, n_sm, stream);
+      cudaError_t err = launch_fir_tc(fx, n_fx, C, H, T, L, fir_ir_aux, fir_in, fir_scratch, trackbuf, tbs, n_sm, stream);
+      if (err != cudaSuccess) return err;
+    } else if (fft) {  // partitioned FFT convolution (wbx_fir_fft.cu)
+      cudaError_t err = launch_fir_fft(fx, n_fx, C, H, T, L, fir_ir_aux, fir_in, fir_scratch, trackbuf, tbs, (uint32_t)fir_mode >> 8, stream);
       if (err != cudaSuccess) return err;
     } else {
       fir_kernel<<<dim3((unsigned)((T + 255) / 256), n_fx * C), 256, 0, stream>>>(fx, C, H, T, ir, L, fir_in, trackbuf, tbs);
