@@ -169,7 +169,7 @@ def test_effects_every_kernel_shape_vs_port(wb, fx_shape, monkeypatch):
         assert_exact(sc.effects_shapes(gpu_engine(wb, True), wb.effect_params, **shape), ref, "effects %s %r" % (fx_shape, shape))
 
 
-@pytest.mark.parametrize("mode", ["direct", "tc", "fft", "fft512"])
+@pytest.mark.parametrize("mode", ["direct", "tc", "fft", "fft512", "fftauto"])
 @pytest.mark.parametrize("taps", [1, 2, 777, 2048])
 def test_reverb_extension_vs_port(wb, taps, mode, monkeypatch):
     """EXTENSION, parity unpinned (BASELINE cfg 5 at test size): the convolution reverb — direct form on the CUDA
@@ -190,7 +190,10 @@ def test_reverb_extension_vs_port(wb, taps, mode, monkeypatch):
 def _fir_mode(monkeypatch, mode):
     """WBX_FIR picks the reverb path when an impulse response is set; "fft512" = the FFT path with 512-tap partitions."""
     monkeypatch.setenv("WBX_FIR", "fft" if mode.startswith("fft") else mode)
-    monkeypatch.setenv("WBX_FFT_P", "512" if mode == "fft512" else "2048")
+    if mode == "fftauto":  # partition size chosen from the render length
+        monkeypatch.delenv("WBX_FFT_P", raising=False)
+    else:
+        monkeypatch.setenv("WBX_FFT_P", "512" if mode == "fft512" else "2048")
 
 
 @pytest.mark.parametrize("mode", ["tc", "fft", "fft512"])
@@ -222,6 +225,44 @@ def test_reverb_cfg5_full_accumulation_depth(wb, chunks, mode, monkeypatch):
     assert late <= 1e-5, "late-callback error %.3g" % late
     pk = np.abs(want_peaks).max()
     assert float(np.abs(res["peaks"].astype(np.float64) - want_peaks).max()) <= 1e-5 * pk
+
+
+@pytest.mark.parametrize("mode", ["fft", "fft512", "fftauto"])
+def test_reverb_fft_spectra_ring_warm_equals_cold(wb, mode, monkeypatch):
+    """FFT path: renders that are a whole number of partitions long reuse the previous render's window spectra (the ring
+    in wbx_fir_fft.cu); WBX_FFT_COLD rebuilds every window from the time-domain history instead — also across a render
+    that is NOT a whole number of partitions (5 callbacks) and a chain reset in the middle of the session (both fall back
+    to the rebuild). The two agree to rounding, not to the bit: a reused window may still hold frames older than the
+    taps - 1 frames the time-domain history keeps; they only meet zero-padded taps, but their rounding noise differs."""
+    def run(cold):
+        _fir_mode(monkeypatch, mode)
+        if cold:
+            monkeypatch.setenv("WBX_FFT_COLD", "1")
+        else:
+            monkeypatch.delenv("WBX_FFT_COLD", raising=False)
+        rng = np.random.RandomState(77)
+        eng = wb.Engine(2, 512, 48000, 120.0, device=0, sum_mode=wb.SUM_EXACT)
+        taps = 9000
+        ir = (rng.standard_normal(taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.02).astype(np.float32)
+        eng.set_impulse_response(ir)
+        for t in range(6):
+            eng.add_track(-5.0, 0.15 * t - 0.3, False)
+            sid = eng.add_sample(sc._src(rng, 2, 80 * 512, 6), 48000)
+            eng.add_clip(t, sid, 0.0, 1e6, 0.0, 1.0, 0.7)
+            if t != 4:
+                eng.set_effects(t, wb.effect_params(reverb=True))
+        eng.play()
+        outs = [eng.render(n) for n in (16, 16, 8, 5, 16, 16)]
+        eng.set_effects(2, wb.effect_params(reverb=True))  # re-attach: track 2 restarts from silence
+        outs += [eng.render(n) for n in (16, 16)]
+        return outs
+    warm, cold = run(False), run(True)
+    for i, ((a, pa), (b, pb)) in enumerate(zip(warm, cold)):
+        peak = float(np.abs(b).max())
+        assert peak > 1e-4
+        err = float(np.abs(a.astype(np.float64) - b).max()) / peak
+        assert err <= 2e-6, "render %d: warm vs cold differ by %.3g of the peak" % (i, err)
+        assert float(np.abs(pa.astype(np.float64) - pb).max()) <= 2e-6 * float(np.abs(pb).max())
 
 
 def test_reverb_delta_is_identity(wb):

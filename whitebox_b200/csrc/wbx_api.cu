@@ -29,8 +29,7 @@ cudaError_t launch_mip_level0(const void* base, uint32_t fmt, uint32_t nch, uint
 cudaError_t launch_mip_merge(const void* child, uint64_t child_mdc, void* parent, uint64_t parent_mdc, uint32_t nch, int high,
                              int n_sm, cudaStream_t stream);
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
-                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
-                           float* fir_hist, float* fir_in, int fir_mode, void* fir_ir_aux, void* fir_scratch, const float* poly,
+                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const FirLaunch& fir, const float* poly,
                            uint32_t fx_flags, uint32_t* sm_arrivals, uint64_t tbs, cudaStream_t stream);
 cudaError_t launch_shard_signal(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch, cudaStream_t stream);
 cudaError_t launch_shard_wait(const ShardPeers& peers, uint32_t rank, uint32_t world, uint32_t epoch,
@@ -50,9 +49,11 @@ uint64_t fir_tc_plane_width(uint64_t H, uint64_t T);
 cudaError_t launch_fir_tc_prepare(const float* ir, uint32_t L, void* tiles, float h_scale, cudaStream_t stream);
 size_t fir_tc_scratch_bytes(uint64_t H, uint64_t T, uint32_t S);
 int fir_tc_split_factor();
-uint32_t fir_fft_partition();
+uint32_t fir_fft_partition(uint64_t T);
 size_t fir_fft_ir_bytes(uint32_t L, uint32_t P);
-size_t fir_fft_scratch_bytes(uint64_t T, uint32_t L, uint32_t n_fx, uint32_t P);
+uint32_t fir_fft_windows(uint64_t T, uint32_t L, uint32_t P);
+size_t fir_fft_ring_bytes(uint32_t cap, uint32_t n_fx, uint32_t P);
+size_t fir_fft_scratch_bytes(uint64_t T, uint32_t n_fx, uint32_t P);
 cudaError_t launch_fir_fft_prepare(const float* ir, uint32_t L, void* ir_spectra, uint32_t P, cudaStream_t stream);
 }  // namespace wbx
 
@@ -116,7 +117,7 @@ struct wbx_engine {
   std::vector<SampleRec> samples;
   DevBuf d_smarr;  // per-SM arrival counters of fx_chain_kernel (role rotation)
   uint32_t fx_flags = 0;  // bit 0: some chain has an EQ or a compressor, bit 1: some chain is reverb-only
-  DevBuf d_spans, d_cells, d_bus, d_zero, d_ws, d_conv, d_upload, d_fx, d_trackbuf, d_ir, d_firhist, d_firin, d_irtiles, d_firplanes, d_poly;
+  DevBuf d_spans, d_cells, d_bus, d_zero, d_ws, d_conv, d_upload, d_fx, d_trackbuf, d_ir, d_firhist, d_firin, d_irtiles, d_firplanes, d_fftz, d_poly;
   HostBuf h_spans, h_bus, h_peaks, h_conv, h_levels, h_fx;
   // views into d_spans (the submitted table: spans | gains | cells of a one-callback render) and d_zero (the region one
   // memset clears before a mix: work counters | peaks | levels)
@@ -149,7 +150,13 @@ struct wbx_engine {
   uint32_t firhist_tracks = 0;       // tracks d_firhist is sized (and zeroed) for
   int fir_mode = 0;                  // reverb path: 0 direct form, 1 tensor cores (d_irtiles = Toeplitz tiles), 2 partitioned FFT
                                      // (d_irtiles = twiddles + partition spectra)
-  uint32_t fir_fft_p = 0;            // partition size of the FFT path the spectra in d_irtiles were built for
+  uint32_t fir_fft_p = 0;            // partition size of the FFT path the spectra in d_irtiles were built for (0: none yet)
+  uint64_t firhist_pos = 0;          // the history ring's origin: logical index i lives at (firhist_pos + i) mod (taps - 1)
+  uint64_t fx_gen = 0;               // bumped whenever the chain list in d_fx is rebuilt (or a chain's state reset)
+  // FFT path: the window spectra ring in d_fftz persists across renders (wbx_fir_fft.cu)
+  bool fftz_valid = false;
+  uint32_t fftz_cap = 0, fftz_base = 0, fftz_nfx = 0, fftz_p = 0;
+  uint64_t fftz_prev_frames = 0, fftz_gen = 0;
   float* mirror[2] = {nullptr, nullptr};       // device view of page-locked caller channels the running render also writes
   float* mirror_host[2] = {nullptr, nullptr};  // ... and the caller's pointers they belong to (wbx_render)
   bool levels_queued = false;              // level reduce + copy into h_levels already enqueued for this mix
@@ -365,7 +372,7 @@ int wbx_destroy(wbx_engine* e) {
         if (s.d_mip[q]) cudaFree(s.d_mip[q]);
     }
   for (DevBuf* b : {&e->d_smarr, &e->d_spans, &e->d_cells, &e->d_bus, &e->d_zero, &e->d_ws, &e->d_conv,
-                    &e->d_upload, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin, &e->d_irtiles, &e->d_firplanes, &e->d_poly})
+                    &e->d_upload, &e->d_fx, &e->d_trackbuf, &e->d_ir, &e->d_firhist, &e->d_firin, &e->d_irtiles, &e->d_firplanes, &e->d_fftz, &e->d_poly})
     if (b->p) cudaFree(b->p);
   for (HostBuf* b : {&e->h_spans, &e->h_bus, &e->h_peaks, &e->h_conv, &e->h_levels, &e->h_fx})
     if (b->p) cudaFreeHost(b->p);
@@ -638,6 +645,9 @@ int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps) {
   CU(e, cudaStreamSynchronize(e->stream));
   e->ir_taps = 0;
   e->firhist_tracks = 0;  // histories are re-created (zeroed) at the next submit
+  e->firhist_pos = 0;
+  e->fftz_valid = false;
+  e->fir_fft_p = 0;
   if (!h || n_taps == 0) return WBX_OK;
   int rc = dev_reserve(e, e->d_ir, (size_t)n_taps * sizeof(float));
   if (rc) return rc;
@@ -660,10 +670,7 @@ int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps) {
     CU(e, launch_fir_tc_prepare((const float*)e->d_ir.p, n_taps, e->d_irtiles.p, h_scale, e->stream));
     e->launches++;
   } else if (e->fir_mode == 2) {
-    e->fir_fft_p = fir_fft_partition();
-    if ((rc = dev_reserve(e, e->d_irtiles, fir_fft_ir_bytes(n_taps, e->fir_fft_p)))) return rc;
-    CU(e, launch_fir_fft_prepare((const float*)e->d_ir.p, n_taps, e->d_irtiles.p, e->fir_fft_p, e->stream));
-    e->launches++;
+    // the partition spectra depend on the partition size, which is chosen per render: built at the first submit
   }
   CU(e, cudaStreamSynchronize(e->stream));
   e->ir_taps = n_taps;
@@ -794,6 +801,7 @@ static int sync_effects(wbx_engine* e) {
     CU(e, cudaMemcpyAsync(e->d_fx.p, e->h_fx.p, cur.size() * sizeof(DFx), cudaMemcpyHostToDevice, e->stream));
   }
   e->fx_dirty = false;
+  e->fx_gen++;
   return WBX_OK;
 }
 
@@ -956,19 +964,64 @@ int wbx_submit(wbx_engine* e, const wbx_segment* segs, uint32_t n_segs, const fl
       if (H == 0 && (rc = dev_reserve(e, e->d_firhist, 256))) return rc;
     }
     const bool rv = e->ir_taps > 0 && (reverb || e->ir_taps == 1);
-    const int fmode = rv ? e->fir_mode : 0;
-    if (fmode == 1) {
-      if ((rc = dev_reserve(e, e->d_firplanes, fir_tc_scratch_bytes(e->ir_taps - 1, (uint64_t)n_blocks * B, n_fx * C)))) return rc;
-    } else if (fmode == 2) {
-      if ((rc = dev_reserve(e, e->d_firplanes, fir_fft_scratch_bytes((uint64_t)n_blocks * B, e->ir_taps, n_fx, e->fir_fft_p)))) return rc;
+    FirLaunch fir;
+    if (rv) {
+      const uint64_t T = (uint64_t)n_blocks * B, H = e->ir_taps - 1;
+      fir.ir = (const float*)e->d_ir.p;
+      fir.L = e->ir_taps;
+      fir.hist = (float*)e->d_firhist.p;
+      fir.hist_pos = e->firhist_pos;
+      fir.xin = (float*)e->d_firin.p;
+      fir.mode = e->fir_mode;
+      if (fir.mode == 1) {
+        if ((rc = dev_reserve(e, e->d_firplanes, fir_tc_scratch_bytes(H, T, n_fx * C)))) return rc;
+        fir.scratch = e->d_firplanes.p;
+      } else if (fir.mode == 2) {
+        const uint32_t P = fir_fft_partition(T);
+        if (P != e->fir_fft_p) {  // partition spectra of the response for this partition size
+          if ((rc = dev_reserve(e, e->d_irtiles, fir_fft_ir_bytes(e->ir_taps, P)))) return rc;
+          CU(e, launch_fir_fft_prepare(fir.ir, e->ir_taps, e->d_irtiles.p, P, e->stream));
+          e->launches++;
+          e->fir_fft_p = P;
+          e->fftz_valid = false;
+        }
+        if ((rc = dev_reserve(e, e->d_firplanes, fir_fft_scratch_bytes(T, n_fx, P)))) return rc;
+        const uint32_t NQ = fir_fft_windows(T, e->ir_taps, P), NP = (e->ir_taps + P - 1) / P;
+        // The previous render's windows are this render's history windows when it was a whole number of partitions long
+        // and nothing else changed; otherwise every window is rebuilt from the time-domain history.
+        bool warm = e->fftz_valid && e->fftz_p == P && e->fftz_nfx == n_fx && e->fftz_gen == e->fx_gen &&
+                    e->fftz_prev_frames % P == 0 && e->fftz_cap >= NQ && NP > 1 && !getenv("WBX_FFT_COLD");
+        if (!warm) {
+          const size_t need = fir_fft_ring_bytes(NQ, n_fx, P);
+          if (need > e->d_fftz.cap || e->fftz_nfx != n_fx || e->fftz_p != P || e->fftz_cap < NQ) {
+            if ((rc = dev_reserve(e, e->d_fftz, need))) return rc;
+            e->fftz_cap = NQ;
+          }
+          e->fftz_base = 0;
+          fir.fft_first_q = 0;
+        } else {
+          e->fftz_base = (uint32_t)((e->fftz_base + e->fftz_prev_frames / P) % e->fftz_cap);
+          fir.fft_first_q = NP - 1;
+        }
+        fir.scratch = e->d_firplanes.p;
+        fir.fft_ring = e->d_fftz.p;
+        fir.fft_ring_base = e->fftz_base;
+        fir.fft_ring_cap = e->fftz_cap;
+        fir.fft_p = P;
+        e->fftz_valid = true;
+        e->fftz_p = P;
+        e->fftz_nfx = n_fx;
+        e->fftz_gen = e->fx_gen;
+        e->fftz_prev_frames = T;
+      }
+      if (fir.mode != 2) e->fftz_valid = false;
+      fir.ir_aux = fir.mode ? e->d_irtiles.p : nullptr;
+      if (H) e->firhist_pos = (e->firhist_pos + T) % H;
     }
     CU(e, launch_effects((const DSpan*)e->d_spans.p, e->cells_ptr, (DFx*)e->d_fx.p, n_fx, N, slots, n_blocks, B, C,
-                         n_segs, (float*)e->d_trackbuf.p, rv ? (const float*)e->d_ir.p : nullptr, rv ? e->ir_taps : 0,
-                         (float*)e->d_firhist.p, (float*)e->d_firin.p, fmode == 2 ? (int)(2u | (e->fir_fft_p << 8)) : fmode,
-                         fmode ? e->d_irtiles.p : nullptr,
-                         fmode ? e->d_firplanes.p : nullptr, (const float*)e->d_poly.p, e->fx_flags, (uint32_t*)e->d_smarr.p,
+                         n_segs, (float*)e->d_trackbuf.p, fir, (const float*)e->d_poly.p, e->fx_flags, (uint32_t*)e->d_smarr.p,
                          (((uint64_t)n_blocks * B + 1) & ~(uint64_t)1), e->stream));
-    e->launches += (rv ? (fmode == 2 ? 6 : (fmode == 1 ? 5 : 4)) : 1) + ((e->fx_flags & 1u) ? 1 : 0) + ((e->fx_flags & 2u) ? 1 : 0);
+    e->launches += (rv ? (fir.mode == 1 ? 5 : 4) : 1) + ((e->fx_flags & 1u) ? 1 : 0) + ((e->fx_flags & 2u) ? 1 : 0);
   }
   e->n_blocks = n_blocks;
   e->n_spans = n_segs;

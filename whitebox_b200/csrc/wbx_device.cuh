@@ -191,6 +191,23 @@ struct MixParams {
   uint32_t shard_blocks, shard_rank;
 };
 
+// convolution reverb stage of launch_effects (extension, BASELINE cfg 5): the impulse response, the per-track time-domain
+// history ring and what the chosen path needs on top of it
+struct FirLaunch {
+  const float* ir = nullptr;  // [L] taps on the device; L == 0: no reverb stage
+  uint32_t L = 0;
+  float* hist = nullptr;      // [n_tracks][2][L - 1] ring: logical index i (oldest first) lives at (hist_pos + i) mod (L - 1)
+  uint64_t hist_pos = 0;
+  float* xin = nullptr;       // direct / tensor-core paths: gather buffer [n_fx * C][L - 1 + T]
+  int mode = 0;               // 0 direct form, 1 tensor cores, 2 partitioned FFT
+  void* ir_aux = nullptr;     // 1: Toeplitz tiles of the response; 2: twiddles + partition spectra
+  void* scratch = nullptr;    // 1: split-precision signal planes; 2: block spectra W
+  void* fft_ring = nullptr;   // 2: window spectra Z[cap][n_fx][2P], a ring over the window index
+  uint32_t fft_ring_base = 0, fft_ring_cap = 0;
+  uint32_t fft_first_q = 0;   // 2: windows below this index are already in the ring (previous render)
+  uint32_t fft_p = 0;         // 2: partition size (512 or 2048)
+};
+
 // ranks' views of one another for a sharded render (all pointers valid on this rank's device)
 struct ShardPeers {
   uint32_t* flags[kMaxPeers];  // flags[j] = rank j's arrival words [kMaxPeers]

@@ -1257,6 +1257,29 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
   for (int i = 0; i < 9; i++) s123[i] = (!w_serial && !w_eq) ? f->sl[i] : 0.0f;
 
   constexpr uint32_t LAG_S = SH::EQW + 1, LAG_O = SH::EQW + 2;  // chunks the serial / output warps run behind the render
+  // output warps, one slot per (callback, track): cell and span summary of the chunk about to be rendered, fetched one
+  // iteration ahead so that the cell -> span -> source chain of global round trips is off the per-chunk critical path
+  DCell pf_cell, nx_cell;
+  pf_cell.pos = 0.0, pf_cell.span = kSilent, pf_cell.n_act = 0;
+  nx_cell = pf_cell;
+  bool pf_fast = false;
+  uint32_t pf_dst_off = 0;
+  float pf_gain = 0.0f;
+  const float2* pf_base = nullptr;
+  auto span_summary = [&](const DCell& c) {
+    pf_fast = false;
+    if (c.span != kSilent) {
+      const DSpan* sp = spans + c.span;
+      pf_fast = sp->fmt == F_F32 && sp->nch == 2 && sp->speed == 1.0 && sp->fade == 0 && C == 2;
+      pf_dst_off = sp->dst_off;
+      pf_gain = sp->gain;
+      pf_base = reinterpret_cast<const float2*>(sp->base);
+    }
+  };
+  if (!w_serial && !w_eq && active && S == 1 && NC > 0) {
+    pf_cell = cells[t];  // chunk 0 = callback 0
+    span_summary(pf_cell);
+  }
   for (uint32_t it = 0; it < NC + LAG_O; it++) {
     if (w_eq) {
       // ---- EQ: biquads 0, 1 of chunk it-1 (warp a) / biquads 2, 3 of chunk it-2, then the follower's intercepts (b) ----
@@ -1435,25 +1458,28 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
         chunk_shape(it, rk, rf0, rn);
         rmode = 2;
         if (S == 1) {
-          const DCell cell = cells[(size_t)rk * N + t];
-          if (cell.span == kSilent) {
+          // the cell of this chunk and the summary of its span were fetched one iteration ago (pf_*): the source loads
+          // below depend on nothing that is still in flight
+          if (pf_cell.span == kSilent) {
             rmode = 1;  // rlo == rhi: zeros
 #pragma unroll
             for (int q = 0; q < RQ; q++) rv[q] = make_float2(0.0f, 0.0f);
-          } else {
-            const DSpan* sp = spans + cell.span;
-            if (sp->fmt == F_F32 && sp->nch == 2 && sp->speed == 1.0 && sp->fade == 0 && C == 2) {
-              // unity-speed stereo f32 clip: a scaled copy (src * gain, then the add into the cleared buffer: 0 + m)
-              rmode = 1;
-              rlo = sp->dst_off, rhi = sp->dst_off + cell.n_act;
-              rgain = sp->gain;
-              const float2* src = reinterpret_cast<const float2*>(sp->base) + (int64_t)(uint32_t)(int64_t)cell.pos;
+          } else if (pf_fast) {
+            // unity-speed stereo f32 clip: a scaled copy (src * gain, then the add into the cleared buffer: 0 + m)
+            rmode = 1;
+            rlo = pf_dst_off, rhi = pf_dst_off + pf_cell.n_act;
+            rgain = pf_gain;
+            const float2* src = pf_base + (int64_t)(uint32_t)(int64_t)pf_cell.pos;
 #pragma unroll
-              for (int q = 0; q < RQ; q++) {
-                const uint32_t fr = q * SH::OLANES + ol, j = rf0 + fr;
-                rv[q] = (fr < rn && j >= rlo && j < rhi) ? __ldg(src + (j - rlo)) : make_float2(0.0f, 0.0f);
-              }
+            for (int q = 0; q < RQ; q++) {
+              const uint32_t fr = q * SH::OLANES + ol, j = rf0 + fr;
+              rv[q] = (fr < rn && j >= rlo && j < rhi) ? __ldg(src + (j - rlo)) : make_float2(0.0f, 0.0f);
             }
+          }
+          if (it + 1 < NC) {  // next chunk's cell: in flight under the output stage below
+            uint32_t nk, nf0, nn;
+            chunk_shape(it + 1, nk, nf0, nn);
+            nx_cell = cells[(size_t)nk * N + t];
           }
         }
       }
@@ -1547,6 +1573,10 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
           }
         }
       }
+      if (active && S == 1 && it + 1 < NC) {
+        pf_cell = nx_cell;
+        span_summary(pf_cell);
+      }
     }
     __syncthreads();
   }
@@ -1607,8 +1637,8 @@ static cudaError_t launch_effects_chain(const DSpan* spans, const DCell* cells, 
 // xin  [n_fx][C][H + T] planar: H = taps - 1 history frames (oldest first) followed by this render's T chain outputs
 // hist [n_tracks][2][H] persists across renders (indexed by track, so it survives chain list rebuilds)
 __global__ void fir_gather_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T,
-                                  const float* __restrict__ hist, const float* __restrict__ trackbuf, uint64_t tbs,
-                                  float* __restrict__ xin, uint32_t* __restrict__ max_word) {
+                                  const float* __restrict__ hist, uint64_t hist_pos, const float* __restrict__ trackbuf,
+                                  uint64_t tbs, float* __restrict__ xin, uint32_t* __restrict__ max_word) {
   const uint32_t ec = blockIdx.y;
   const uint32_t e = ec / C, c = ec % C;
   if (!fx[e].reverb_on) return;
@@ -1617,7 +1647,14 @@ __global__ void fir_gather_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uin
   float* x = xin + (size_t)ec * (H + T);
   float m = 0.0f;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H + T; i += (uint64_t)gridDim.x * blockDim.x) {
-    const float v = i < H ? h[i] : tb[(i - H) * 2];
+    float v;
+    if (i < H) {  // the history is a ring: logical index i lives at (hist_pos + i) mod H
+      uint64_t r = hist_pos + i;
+      if (r >= H) r -= H;
+      v = h[r];
+    } else {
+      v = tb[(i - H) * 2];
+    }
     x[i] = v;
     m = fmaxf(m, fabsf(v));
   }
@@ -1663,14 +1700,21 @@ __global__ void __launch_bounds__(256) fir_kernel(const DFx* __restrict__ fx, ui
   if (n < (int64_t)T) trackbuf[((size_t)e * tbs + n) * 2 + c] = (float)total;
 }
 
+// the history ring takes the render's newest min(T, H) inputs (from the gather buffer: the outputs overwrote trackbuf):
+// logical index i in [H - n, H) of the NEW history lives at (new_pos + i) mod H
 __global__ void fir_save_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T,
-                                const float* __restrict__ xin, float* __restrict__ hist) {
+                                const float* __restrict__ xin, float* __restrict__ hist, uint64_t new_pos) {
   const uint32_t ec = blockIdx.y;
   const uint32_t e = ec / C, c = ec % C;
   if (!fx[e].reverb_on) return;
   float* h = hist + ((size_t)fx[e].track * 2 + c) * H;
-  const float* x = xin + (size_t)ec * (H + T) + T;  // the last H entries
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H; i += (uint64_t)gridDim.x * blockDim.x) h[i] = x[i];
+  const uint64_t n = T < H ? T : H;
+  const float* x = xin + (size_t)ec * (H + T) + (H + T - n);  // the last n entries
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = new_pos + (H - n + u);
+    if (r >= H) r -= H;
+    h[r] = x[u];
+  }
 }
 
 // point the cells of effect tracks at their processed buffer: one whole-block unity call per callback
@@ -2156,13 +2200,11 @@ cudaError_t launch_expand(const DSpan* spans, uint32_t n_spans, DCell* cells, ui
 cudaError_t launch_fir_tc(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T, uint32_t L, void* tiles,
                           const float* xin, void* scratch, float* trackbuf, uint64_t tbs, int n_sm, cudaStream_t stream);  // wbx_fir_tc.cu
 uint32_t* fir_tc_max_word(void* scratch);
-cudaError_t launch_fir_fft(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t H, uint64_t T, uint32_t L, const void* ir_spectra,
-                           const float* xin, void* scratch, float* trackbuf, uint64_t tbs, uint32_t P,
+cudaError_t launch_fir_fft(const DFx* fx, uint32_t n_fx, uint32_t C, uint64_t T, const FirLaunch& a, float* trackbuf, uint64_t tbs,
                            cudaStream_t stream);  // wbx_fir_fft.cu
 
 cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S, uint32_t K,
-                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const float* ir, uint32_t L,
-                           float* fir_hist, float* fir_in, int fir_mode, void* fir_ir_aux, void* fir_scratch, const float* poly,
+                           uint32_t B, uint32_t C, uint32_t first_fx_span, float* trackbuf, const FirLaunch& fir, const float* poly,
                            uint32_t fx_flags, uint32_t* sm_arrivals, uint64_t tbs, cudaStream_t stream) {
   if (n_fx == 0) return cudaSuccess;
   const uint64_t warps = (uint64_t)n_fx * K;
@@ -2177,31 +2219,36 @@ cudaError_t launch_effects(const DSpan* spans, DCell* cells, DFx* fx, uint32_t n
     cudaError_t err = launch_effects_chain(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, n_sm, stream);
     if (err != cudaSuccess) return err;
   }
-  if (L && ir && fir_hist && fir_in) {  // convolution reverb as the chain's last stage
+  const uint32_t L = fir.L;
+  if (L && fir.ir && fir.hist && fir.mode == 2 && fir.ir_aux && fir.scratch && fir.fft_ring) {
+    // convolution reverb as the chain's last stage: partitioned FFT convolution (wbx_fir_fft.cu), straight from the
+    // history ring and trackbuf
+    cudaError_t err = launch_fir_fft(fx, n_fx, C, (uint64_t)K * B, fir, trackbuf, tbs, stream);
+    if (err != cudaSuccess) return err;
+  } else if (L && fir.ir && fir.hist && fir.xin) {  // direct form: CUDA cores or tensor cores, from the gather buffer
     const uint64_t T = (uint64_t)K * B, H = L - 1;
     const dim3 gcopy((unsigned)(((H + T) + 255) / 256 < 4096 ? ((H + T) + 255) / 256 : 4096), n_fx * C);
-    const bool tc = fir_mode == 1 && fir_ir_aux && fir_scratch;
-    const bool fft = (fir_mode & 0xff) == 2 && fir_ir_aux && fir_scratch;  // bits 8.. = partition size
-    uint32_t* max_word = tc ? fir_tc_max_word(fir_scratch) : nullptr;
+    const bool tc = fir.mode == 1 && fir.ir_aux && fir.scratch;
+    uint32_t* max_word = tc ? fir_tc_max_word(fir.scratch) : nullptr;
     if (max_word) {
       cudaError_t err = cudaMemsetAsync(max_word, 0, sizeof(uint32_t), stream);
       if (err != cudaSuccess) return err;
     }
-    fir_gather_kernel<<<gcopy, 256, 0, stream>>>(fx, n_fx, C, H, T, fir_hist, trackbuf, tbs, fir_in, max_word);
+    fir_gather_kernel<<<gcopy, 256, 0, stream>>>(fx, n_fx, C, H, T, fir.hist, fir.hist_pos, trackbuf, tbs, fir.xin, max_word);
     if (tc) {  // tensor-core path (wbx_fir_tc.cu)
       int dev = 0, n_sm = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      cudaError_t err = launch_fir_tc(fx, n_fx, C, H, T, L, fir_ir_aux, fir_in, fir_scratch, trackbuf, tbs, n_sm, stream);
-      if (err != cudaSuccess) return err;
-    } else if (fft) {  // partitioned FFT convolution (wbx_fir_fft.cu)
-      cudaError_t err = launch_fir_fft(fx, n_fx, C, H, T, L, fir_ir_aux, fir_in, fir_scratch, trackbuf, tbs, (uint32_t)fir_mode >> 8, stream);
+      cudaError_t err = launch_fir_tc(fx, n_fx, C, H, T, L, fir.ir_aux, fir.xin, fir.scratch, trackbuf, tbs, n_sm, stream);
       if (err != cudaSuccess) return err;
     } else {
-      fir_kernel<<<dim3((unsigned)((T + 255) / 256), n_fx * C), 256, 0, stream>>>(fx, C, H, T, ir, L, fir_in, trackbuf, tbs);
+      fir_kernel<<<dim3((unsigned)((T + 255) / 256), n_fx * C), 256, 0, stream>>>(fx, C, H, T, fir.ir, L, fir.xin, trackbuf, tbs);
     }
-    if (H) fir_save_kernel<<<dim3((unsigned)((H + 255) / 256 < 1024 ? (H + 255) / 256 : 1024), n_fx * C), 256, 0, stream>>>(
-        fx, n_fx, C, H, T, fir_in, fir_hist);
+    if (H) {
+      const uint64_t n = T < H ? T : H;
+      fir_save_kernel<<<dim3((unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), n_fx * C), 256, 0, stream>>>(
+          fx, n_fx, C, H, T, fir.xin, fir.hist, (fir.hist_pos + T) % H);
+    }
   }
   patch_fx_cells_kernel<<<(unsigned)((warps + 127) / 128), 128, 0, stream>>>(fx, n_fx, N, S, K, B, first_fx_span, cells);
   return cudaGetLastError();
