@@ -192,17 +192,18 @@ def make_sources(n_tracks, n_blocks, seed, src_rate=RATE):
         yield t, [pool[o:o + frames] for o in offs]
 
 
-NCU_MIX_CAPTURES = ["r02_ncu_full_mix_fpl16_K4096.txt", "r01b_ncu_full_mix_fpl16_K4096.txt",
-                    "r01_ncu_full_mix_fpl16_K4096.txt"]  # newest first
+# `ncu --set full` captures of the mix kernel at the bench shape (1024 tracks x 4096 callbacks), newest first
+NCU_MIX_CAPTURES = {"cfg2": ["r02_ncu_full_mix_cfg2.txt", "r01b_ncu_full_mix_fpl16_K4096.txt", "r01_ncu_full_mix_fpl16_K4096.txt"],
+                    "cfg3": ["r02_ncu_full_mix_cfg3.txt"]}
 
 
-def ncu_traffic(n_tracks, n_blocks):
+def ncu_traffic(wl, n_tracks, n_blocks):
     """(dram__bytes_read.sum + dram__bytes_write.sum of one mix-kernel launch, file) from the newest committed
     `ncu --set full` capture of this exact shape (profiles/), or (None, None) when no capture of the shape exists."""
     if (n_tracks, n_blocks) != (1024, 4096):
         return None, None
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-    for name in NCU_MIX_CAPTURES:
+    for name in NCU_MIX_CAPTURES.get(wl, []):
         try:
             rd = wr = None
             for ln in open(os.path.join(ROOT, "profiles", name)):
@@ -707,7 +708,7 @@ def run_workload(ctx, wl, N, K, steps, warmup, min_seconds, main, args):
         value = world * track_frames_per_step / (ms_per_step * 1e-3)
         alg_bytes = track_frames_per_step * ALG_BYTES_PER_TRACK_FRAME * src_rate / RATE  # each source sample read once
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(N, K) if wl == "cfg2" else (None, None)
+        traffic, traffic_src = ncu_traffic(wl, N, K)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms,
                     "traffic_source": (traffic_src + " (ncu --set full, bytes per launch)") if traffic else None,

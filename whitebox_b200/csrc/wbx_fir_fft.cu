@@ -41,7 +41,6 @@ namespace wbx {
 
 namespace {
 
-constexpr int MAC_BG = 16;  // output blocks per thread of the partition sum (sliding window length)
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
@@ -248,8 +247,10 @@ __global__ void __launch_bounds__(FftShape<N>::THREADS) fft_ir_kernel(const floa
 // partition p, the window ending at (b - p + 1) P, which is window q = b - p + NP - 1.
 // Thread = (f, e, group of MAC_BG blocks): at step p it needs q = Q0 - p + j for its blocks j = 0 .. MAC_BG-1 — a window
 // that slides down by one per step, kept in registers (slot (p - j) mod MAC_BG, static under the unroll).
-template <int N>
-__global__ void __launch_bounds__(128, 5) fft_mac_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t NP, uint32_t NB,
+// MAC_BG = output blocks per thread (the sliding window's length): 16 for long renders, 4 / 1 for renders of a few blocks
+// (a realtime callback is one block: a longer window would only multiply zeros)
+template <int N, int MAC_BG>
+__global__ void __launch_bounds__(128, MAC_BG == 16 ? 5 : 8) fft_mac_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t NP, uint32_t NB,
                                                       const float2* __restrict__ Hs, const float2* __restrict__ Z, FftRing ring,
                                                       float2* __restrict__ W) {
   const uint32_t e = blockIdx.y;
@@ -276,9 +277,10 @@ __global__ void __launch_bounds__(128, 5) fft_mac_kernel(const DFx* __restrict__
   // takes its eight loads from two base pointers with fixed strides, all in flight together.
   const int64_t S0 = (int64_t)ring.slot((uint32_t)Q0);
   const float2* hp0 = Hs + f;
-  for (uint32_t p0 = 0; p0 < NP; p0 += MAC_BG) {
+  constexpr int UNR = MAC_BG < 4 ? 4 : MAC_BG;  // steps per unrolled loop body (a multiple of the window length)
+  for (uint32_t p0 = 0; p0 < NP; p0 += UNR) {
 #pragma unroll
-    for (int g = 0; g < MAC_BG / 4; g++) {
+    for (int g = 0; g < UNR / 4; g++) {
       const uint32_t pg = p0 + 4 * g;
       if (pg >= NP) break;
       int64_t s = S0 - (int64_t)pg;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(128, 5) fft_mac_kernel(const DFx* __restrict__
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int pp = 4 * g + u;
+        const int pp = (4 * g + u) % MAC_BG;
         win[pp] = zv[u];
 #pragma unroll
         for (int j = 0; j < MAC_BG; j++) cmac(acc[j], hv[u], win[(pp - j + MAC_BG) % MAC_BG]);
@@ -467,7 +469,12 @@ static cudaError_t launch_fir_fft_t(const DFx* fx, uint32_t n_fx, uint32_t C, ui
     fft_save_kernel<<<dim3((unsigned)((n + 255) / 256 < 256 ? (n + 255) / 256 : 256), n_fx), 256, 0, stream>>>(fx, C, H, T, trackbuf,
                                                                                                              tbs, a.hist, new_pos);
   }
-  fft_mac_kernel<N><<<dim3(N / 128, n_fx, (NB + MAC_BG - 1) / MAC_BG), 128, 0, stream>>>(fx, n_fx, NP, NB, Hs, Z, ring, W);
+  if (NB > 4)
+    fft_mac_kernel<N, 16><<<dim3(N / 128, n_fx, (NB + 15) / 16), 128, 0, stream>>>(fx, n_fx, NP, NB, Hs, Z, ring, W);
+  else if (NB > 1)
+    fft_mac_kernel<N, 4><<<dim3(N / 128, n_fx, 1), 128, 0, stream>>>(fx, n_fx, NP, NB, Hs, Z, ring, W);
+  else
+    fft_mac_kernel<N, 1><<<dim3(N / 128, n_fx, 1), 128, 0, stream>>>(fx, n_fx, NP, NB, Hs, Z, ring, W);
   ifft_blocks_kernel<N><<<dim3(NB, n_fx), SH::THREADS, SH::SMEM, stream>>>(fx, n_fx, C, T, W, tw, trackbuf, tbs);
   return cudaGetLastError();
 }
