@@ -519,12 +519,12 @@ def effects_shapes(make_engine, fxp, n_tracks=24, block=512, n_blocks=5, out_cha
     return _collect(eng, outs, n_tracks)
 
 
-def reverb(make_engine, fxp, taps=777):
+def reverb(make_engine, fxp, taps=777, B=256, out_channels=2):
     """EXTENSION scenario (parity unpinned w.r.t. whitebox): BASELINE cfg 5 shape at test size — tracks whose chain
     ends in a convolution with a shared impulse response, history carried across renders."""
     rng = np.random.RandomState(909)
-    B, rate = 256, 48000
-    eng = make_engine(2, B, rate, 120.0)
+    rate = 48000
+    eng = make_engine(out_channels, B, rate, 120.0)
     ir = (rng.uniform(-1, 1, taps) * np.exp(-np.arange(taps) / (taps / 5.0)) * 0.2).astype(np.float32)
     ir[0] = 1.0
     eng.set_impulse_response(ir)

@@ -187,6 +187,22 @@ def test_reverb_extension_vs_port(wb, taps, mode, monkeypatch):
     assert same_bits(res["sampler_offsets"], ref["sampler_offsets"])
 
 
+@pytest.mark.parametrize("mode", ["direct", "tc", "fft", "fft512"])
+@pytest.mark.parametrize("shape", [dict(B=101, out_channels=2), dict(B=256, out_channels=1), dict(B=77, out_channels=1),
+                                   dict(B=1000, out_channels=2)])
+def test_reverb_odd_blocks_and_mono_bus(wb, shape, mode, monkeypatch):
+    """The reverb paths on odd block sizes (renders that are no whole number of partitions, unaligned track buffers) and
+    on a mono bus (the FFT path then carries a real signal through its complex transforms), 3000 taps, vs the f64 spec."""
+    _fir_mode(monkeypatch, mode)
+    ref = sc.reverb(lambda C, B, r, bpm: o.Session("port", C, B, r, bpm), wb.effect_params, 3000, **shape)
+    res = sc.reverb(gpu_engine(wb, True), wb.effect_params, 3000, **shape)
+    peak = np.abs(ref["out"]).max(axis=(1, 2), keepdims=True)
+    err = np.abs(res["out"].astype(np.float64) - ref["out"])
+    assert np.all(err <= 1e-5 * peak), "reverb bus error %.3g of block peak" % float((err / peak).max())
+    pk = np.abs(ref["peaks"]).max()
+    assert np.all(np.abs(res["peaks"].astype(np.float64) - ref["peaks"]) <= 1e-5 * pk)
+
+
 def _fir_mode(monkeypatch, mode):
     """WBX_FIR picks the reverb path when an impulse response is set; "fft512" = the FFT path with 512-tap partitions."""
     monkeypatch.setenv("WBX_FIR", "fft" if mode.startswith("fft") else mode)
