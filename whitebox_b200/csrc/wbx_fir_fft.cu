@@ -176,7 +176,7 @@ struct FftRing {  // spectra ring over the window index q: slot(q) = (base + q) 
 // render): history frames from the time-domain ring hist[track][2][H] (logical index i -> (hist_pos + i) mod H, oldest
 // first), frames >= 0 from trackbuf; frames outside [-H, T) are zero.
 template <int N>
-__global__ void __launch_bounds__(FftShape<N>::THREADS) fft_windows_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t C,
+__global__ void __launch_bounds__(FftShape<N>::THREADS, N == 4096 ? 4 : 16) fft_windows_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t C,
                                                                            uint64_t H, uint64_t T, uint32_t NP, uint32_t q0,
                                                                            const float* __restrict__ hist, uint64_t hist_pos,
                                                                            const float* __restrict__ trackbuf, uint64_t tbs,
@@ -248,7 +248,10 @@ __global__ void __launch_bounds__(FftShape<N>::THREADS) fft_ir_kernel(const floa
 // Thread = (f, e, group of MAC_BG blocks): at step p it needs q = Q0 - p + j for its blocks j = 0 .. MAC_BG-1 — a window
 // that slides down by one per step, kept in registers (slot (p - j) mod MAC_BG, static under the unroll).
 // MAC_BG = output blocks per thread (the sliding window's length): 16 for long renders, 4 / 1 for renders of a few blocks
-// (a realtime callback is one block: a longer window would only multiply zeros)
+// (a realtime callback is one block: a longer window would only multiply zeros).
+// (Measured and dropped: the same sum with H and Z staged through a shared-memory ring by 1 KiB cp.async.bulk copies —
+// 186 us against 174 us for this version at cfg 5: two bulk copies per step per CTA run into the TMA issue rate of
+// small copies, ~88 cycles each per SM, the same limit the mix kernel met with 2 KiB windows in round 1.)
 template <int N, int MAC_BG>
 __global__ void __launch_bounds__(128, MAC_BG == 16 ? 5 : 8) fft_mac_kernel(const DFx* __restrict__ fx, uint32_t n_fx, uint32_t NP, uint32_t NB,
                                                       const float2* __restrict__ Hs, const float2* __restrict__ Z, FftRing ring,

@@ -705,7 +705,9 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
     uint32_t cur_track = 0;
     uint32_t slot_ctr = 0;  // position of the current cell within its track's `slots` cells
 
-    // descriptors of the first batch (lanes >= BATCH idle)
+    // descriptors of the first batch (lanes >= BATCH idle); the barrier orders the previous item's last descriptor reads
+    // before these writes (the shuffle above synchronises execution, not memory)
+    __syncwarp();
     if (lane < BATCH) {
       const DCell c0 = load_cell(cells, lane, n_cells);
       const DSpan s0 = load_span(p.spans, c0);
@@ -750,6 +752,7 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
         if (ci >= n_cells) break;
         if (more && i == BATCH / 4 && lane < BATCH) sN = load_span(p.spans, cN);
         if (more && i == BATCH / 2) {
+          __syncwarp();  // every lane is done reading the ring half written next (the previous batch's descriptors)
           if (lane < BATCH)
             resolve_store<L::STAGE_BYTES, L::T>(cN, sN, p.gains, f0, tile_len, two, k, &ring[((b + 1) & 1) * BATCH + lane]);
           __syncwarp();
