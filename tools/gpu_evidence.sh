@@ -1,6 +1,6 @@
-# Round-2 evidence run on one B200 (everything lands in gpurun_out/r02i; summaries are copied to profiles/ by hand).
+# Round-2 evidence run on one B200 (everything lands in gpurun_out/evidence; summaries are copied to profiles/ by hand).
 set -x
-O=gpurun_out/r02i
+O=gpurun_out/evidence
 mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 tail -4 $O/pytest_gpu.log

@@ -1,5 +1,6 @@
+# compute-sanitizer (racecheck, memcheck) over the parity tests of the kernels new in round 2 + the golden / fuzz / sharded sessions; then an ncu launch list of the cfg 5 chain stage.   gpurun -- bash tools/gpu_sanitizer.sh
 set -x
-O=gpurun_out/r02k
+O=gpurun_out/sanitizer
 mkdir -p $O
 SEL="effects_every_kernel_shape or effects_time_parallel or reverb_extension or reverb_odd or warm_equals_cold or sharded_engines_on_one or golden_sharded or fused or tree or golden_scenario or fuzz"
 timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "$SEL" > $O/compute_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" >> $O/compute_sanitizer_racecheck.log
