@@ -48,6 +48,7 @@ PARITY_TOL = 1e-5              # north_star: 1e-5 relative, stated on the block 
 WORKLOAD_TEXT = {
     "cfg2": "cfg2: %d stereo tracks/GPU, 48 kHz f32, gain/pan + bus sum (fade=0: the reference has none), 512-frame block",
     "cfg3": "cfg3: %d stereo tracks/GPU, 44.1 kHz f32 sources resampled to 48 kHz (2-tap linear, the reference's resampler) + mix, 512-frame block",
+    "cfg3p": "cfg3p: %d stereo tracks/GPU, 44.1 kHz f32 sources resampled to 48 kHz with the 128-phase x 16-tap polyphase windowed sinc (BASELINE cfg 3's wording; extension, parity unpinned: the reference only has the linear resampler) + mix, 512-frame block",
     "cfg4": "cfg4: %d stereo tracks/GPU, 48 kHz f32, 4-band biquad EQ + compressor chain on every track (extension, parity unpinned) + mix; a step = chains (wbx_submit) + mix",
     "cfg5": "cfg5: %d stereo tracks/GPU, 48 kHz f32, %d-tap convolution reverb on every track (tensor-core path; extension, parity unpinned) + mix; a step = chains (wbx_submit) + mix",
 }
@@ -98,7 +99,7 @@ def hbm_peak():
 def workload_config(wl, n_per_gpu, world, blocks, taps):
     """The static description of a workload: identical in our arm and in the reference arm."""
     text = WORKLOAD_TEXT[wl] % ((n_per_gpu, taps) if wl == "cfg5" else (n_per_gpu,))
-    src_rate = 44100 if wl == "cfg3" else RATE
+    src_rate = 44100 if wl in ("cfg3", "cfg3p") else RATE
     gib = n_per_gpu * blocks * BLOCK * ALG_BYTES_PER_TRACK_FRAME * src_rate / RATE / 2**30
     return {"workload": text, "tracks_per_gpu": n_per_gpu, "total_tracks": n_per_gpu * world, "block_frames": BLOCK,
             "blocks_per_step": blocks, "sample_rate": RATE,
@@ -316,7 +317,7 @@ def run_reference(args):
     n_per_gpu = args.tracks or 1024
     K = args.blocks or 4096
     n_tracks = n_per_gpu * args.gpus
-    src_rate = 44100 if wl == "cfg3" else RATE
+    src_rate = 44100 if wl in ("cfg3", "cfg3p") else RATE
     blocks = max(64, args.ref_blocks // args.gpus)  # the bounded sample; keeps the host-memory footprint in check
     vals = []
     engines = CpuEngines(kind, n_tracks, blocks, threads, src_rate=src_rate)
@@ -378,11 +379,13 @@ def parity_expected(ctx, wl, N, Kp, src_rate, taps, src_blocks):
                     bus[c] += (y * np.float32(np.float32(vol_lin) * np.float32(pc))).astype(np.float32)
         out = np.clip(bus, -1.0, 1.0).astype(np.float32)
         return np.ascontiguousarray(out.reshape(2, Kp, BLOCK).transpose(1, 0, 2)), "f64 FFT statement of the C spec (apply_reverb)"
-    kind = "port" if wl == "cfg4" else oracle_kind()
+    kind = "port" if wl in ("cfg4", "cfg3p") else oracle_kind()
     if kind == "port" and not o.have_port():
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
     s = o.Session(kind, 2, BLOCK, RATE, 120.0)
     fxp = cfg4_params(wb) if wl == "cfg4" else None
+    if wl == "cfg3p":
+        s.set_resampler(1)
     g = 0
     for r in range(world):
         for t, x in make_sources(N, src_blocks, 1234 + r, src_rate):
@@ -413,9 +416,9 @@ def run_workload(ctx, wl, N, K, steps, warmup, min_seconds, main, args):
     torch, dist, wb, shard = ctx.torch, ctx.dist, ctx.wb, ctx.shard
     world, rank, local = ctx.world, ctx.rank, ctx.local
     taps = args.taps
-    src_rate = 44100 if wl == "cfg3" else RATE
+    src_rate = 44100 if wl in ("cfg3", "cfg3p") else RATE
     resubmit = wl in ("cfg4", "cfg5")  # the effect chains run at submit: a step is submit + mix
-    Kp = {"cfg2": 4, "cfg3": 4, "cfg4": 4, "cfg5": 160 if taps > 8192 else 16}[wl]  # callbacks of the parity render
+    Kp = {"cfg2": 4, "cfg3": 4, "cfg3p": 4, "cfg4": 4, "cfg5": 160 if taps > 8192 else 16}[wl]  # callbacks of the parity render
     Kp = max(1, min(Kp, args.parity_blocks)) if args.parity_blocks else Kp
     Kmax = max(K, Kp)
     peak_gbs, peak_src = hbm_peak()
@@ -436,6 +439,8 @@ def run_workload(ctx, wl, N, K, steps, warmup, min_seconds, main, args):
                     sum_mode=wb.SUM_EXACT if (args.exact and wl != "cfg5") else wb.SUM_AUTO)
     stream = ctx.stream
     eng.dev.set_stream(stream.cuda_stream)
+    if wl == "cfg3p":
+        eng.set_resampler(1)  # polyphase quality mode (extension)
     host_sources = []
     for t, x in make_sources(N, Kmax, 1234 + rank, src_rate):
         vol, pan, gain = track_params(rank * N + t)
@@ -713,6 +718,10 @@ def run_workload(ctx, wl, N, K, steps, warmup, min_seconds, main, args):
                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms,
                     "traffic_source": (traffic_src + " (ncu --set full, bytes per launch)") if traffic else None,
                     "algorithmic_bytes_per_launch": alg_bytes}
+        if wl == "cfg3p":
+            roofline["note"] = ("quality mode, not the reference's resampler: 16 taps x 2 channels per frame with a per-frame gather of "
+                                "the phase's coefficient row; bound by shared-memory wavefronts (ncu: profiles/"
+                                "r02_ncu_full_mix_cfg3_polyphase.txt), not HBM")
         if wl == "cfg4":
             roofline["note"] = ("kernel_ms = the whole step (track render + effect chains + mix); algorithmic bytes = 8 B per "
                                 "track-frame (SURVEY.md 8d)")
@@ -816,7 +825,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx.stream = torch.cuda.Stream()
 
-    defaults = {"cfg2": (1024, 4096), "cfg3": (1024, 4096), "cfg4": (512, 1024), "cfg5": (max(1, 256 // world), 64)}
+    defaults = {"cfg2": (1024, 4096), "cfg3": (1024, 4096), "cfg3p": (1024, 4096), "cfg4": (512, 1024), "cfg5": (max(1, 256 // world), 64)}
     wl = args.workload
     N = args.tracks if args.tracks else defaults[wl][0]
     K = args.blocks if args.blocks else defaults[wl][1]
@@ -824,8 +833,8 @@ def run_ours(args):
     if wl == "cfg2" and args.sub:
         # the other BASELINE configs as short runs on the same box (same harness, fewer steps)
         sub = {}
-        sub_shape = {"cfg3": (1024, 4096), "cfg4": (512, 1024), "cfg5": (max(1, 256 // world), 64)}
-        for swl in ("cfg3", "cfg4", "cfg5"):
+        sub_shape = {"cfg3": (1024, 4096), "cfg3p": (1024, 4096), "cfg4": (512, 1024), "cfg5": (max(1, 256 // world), 64)}
+        for swl in ("cfg3", "cfg3p", "cfg4", "cfg5"):
             try:
                 r = run_workload(ctx, swl, sub_shape[swl][0], sub_shape[swl][1], args.sub_steps, 3, args.sub_seconds, False, args)
             except Exception as ex:  # a failing sub-run must not take the contract line with it
@@ -851,7 +860,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg3p", "cfg4", "cfg5"],
                     help="BASELINE.json configs[1] (the contract line, default) or configs[2..4] alone")
     ap.add_argument("--tracks", type=int, default=0, help="stereo tracks per GPU (0: 1024; cfg4 512; cfg5 256 / gpus = strong scaling)")
     ap.add_argument("--blocks", type=int, default=0, help="512-frame callbacks per step (0: 4096; cfg4 1024; cfg5 64)")

@@ -54,10 +54,13 @@ def main():
     total_frames = int(np.ceil(end_beat * 0.5 * rate))
     size = {wb.FMT_I16: 2, wb.FMT_I24_X8: 4, wb.FMT_I32: 4, wb.FMT_F32: 4}[code]
     out = np.zeros((total_frames + B) * 2 * size, np.uint8)
+    out.fill(1)  # touch every page of the destination: the timed runs should not pay first-touch page faults
     eng.bounce(0.0, 8.0, code, chunk_blocks=args.chunk, out=out)  # warm-up (buffers, kernels)
-    t0 = time.perf_counter()
-    got = eng.bounce(0.0, end_beat, code, chunk_blocks=args.chunk, out=out)
-    t_bounce = time.perf_counter() - t0
+    t_bounce = 1e9
+    for _ in range(3):  # best of three: a single 80 ms run is at the mercy of the host's memory system
+        t0 = time.perf_counter()
+        got = eng.bounce(0.0, end_beat, code, chunk_blocks=args.chunk, out=out)
+        t_bounce = min(t_bounce, time.perf_counter() - t0)
     assert got.size == total_frames * 2 * size
     # the same audio through the plain batched render (bus back as planar f32, no conversion), chunk by chunk
     n_blocks = (total_frames + B - 1) // B
@@ -66,16 +69,18 @@ def main():
     eng.set_playhead(0.0)
     eng.play()
     eng.render(min(args.chunk, n_blocks), want_peaks=False, out=pinned.array[:, :min(args.chunk, n_blocks) * B])
-    eng.stop()
-    eng.set_playhead(0.0)
-    eng.play()
-    t0 = time.perf_counter()
-    done = 0
-    while done < n_blocks:
-        n = min(args.chunk, n_blocks - done)
-        eng.render(n, want_peaks=False, out=pinned.array[:, :n * B])
-        done += n
-    t_render = time.perf_counter() - t0
+    t_render = 1e9
+    for _ in range(3):
+        eng.stop()
+        eng.set_playhead(0.0)
+        eng.play()
+        t0 = time.perf_counter()
+        done = 0
+        while done < n_blocks:
+            n = min(args.chunk, n_blocks - done)
+            eng.render(n, want_peaks=False, out=pinned.array[:, :n * B])
+            done += n
+        t_render = min(t_render, time.perf_counter() - t0)
     eng.stop()
     # parity spot check: the first callbacks of the export against the reference's process loop + convert_f32_to_interleaved_*
     ref.play()
@@ -85,6 +90,7 @@ def main():
     same = bool(np.array_equal(got[:want.size], want))
     tf = N * total_frames
     print("bounce: %d tracks x %.1f min -> %s, chunks of %d callbacks" % (N, args.minutes, args.fmt, args.chunk))
+    print("  (best of 3 runs each; the bounce copies every chunk from its page-locked slot into a pageable %d MB destination)" % (out.size >> 20))
     print("  bounce  %.3f s  %.3e track-frames/s  (%.0fx realtime)" % (t_bounce, tf / t_bounce, args.minutes * 60.0 / t_bounce))
     print("  render  %.3f s  %.3e track-frames/s  (same audio, planar f32 bus into page-locked channels)" % (t_render, tf / t_render))
     print("  bounce / render rate = %.3f" % (t_render / t_bounce))

@@ -261,6 +261,33 @@ __device__ __forceinline__ float2 poly_frame(const float* __restrict__ table, co
   return acc;
 }
 
+// The mix kernel's copy of the same evaluation: the coefficient table staged in shared memory (rows padded to
+// POLY_ROW floats: 32 lanes gather 32 different rows per tap group, which through L1 costs one tag lookup per lane and
+// bounded the first version at 5.6e10 track-frames/s), (L, R) accumulated as one packed FFMA2 per tap (per-component rn:
+// the same bits as the two scalar fused multiply-adds of the specification).
+constexpr int POLY_ROW = 20;                       // floats per phase row in shared memory (16 taps + 4 pad: 80 B, 16-B aligned)
+constexpr int POLY_SMEM_BYTES = 128 * POLY_ROW * 4;
+__device__ __forceinline__ float2 poly_frame_s(const float* tab_s, uint32_t rb_s, uint32_t ix, double fd) {
+  const int ph = __double2int_rz(__dmul_rn(fd, 128.0));
+  const float4* h4 = reinterpret_cast<const float4*>(tab_s + ph * POLY_ROW);
+  float2 acc = make_float2(0.0f, 0.0f);
+  const uint32_t a0 = rb_s + (ix - 7u) * 8u;  // shared address of source frame ix - 7
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const float4 h = h4[q];
+    float2 s0, s1, s2, s3;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(s0.x), "=f"(s0.y) : "r"(a0 + (4 * q + 0) * 8u));
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(s1.x), "=f"(s1.y) : "r"(a0 + (4 * q + 1) * 8u));
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(s2.x), "=f"(s2.y) : "r"(a0 + (4 * q + 2) * 8u));
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(s3.x), "=f"(s3.y) : "r"(a0 + (4 * q + 3) * 8u));
+    acc = __ffma2_rn(make_float2(h.x, h.x), s0, acc);
+    acc = __ffma2_rn(make_float2(h.y, h.y), s1, acc);
+    acc = __ffma2_rn(make_float2(h.z, h.z), s2, acc);
+    acc = __ffma2_rn(make_float2(h.w, h.w), s3, acc);
+  }
+  return acc;
+}
+
 // Fade extension (include/wbx.h): envelope of clip-relative output frame n.
 struct FadeEnv {
   double n0;  // clip frame of segment-relative frame 0
@@ -502,9 +529,9 @@ __device__ __forceinline__ void consume_lin(const Desc& d, const uint8_t* row, f
 // Stereo f32, polyphase windowed-sinc resample (extension) from the staged window: the lin path's position split,
 // then 16 taps per frame.
 template <int FPL>
-__device__ __forceinline__ void consume_poly(const Desc& d, const uint8_t* row, const float* __restrict__ poly,
-                                             float2 (&acc)[FPL], float& pkL, float& pkR, int lane) {
-  const float2* rb = reinterpret_cast<const float2*>(row) - d.base;
+__device__ __forceinline__ void consume_poly(const Desc& d, const uint8_t* row, const float* tab_s, float2 (&acc)[FPL], float& pkL,
+                                             float& pkR, int lane) {
+  const uint32_t rb_s = smem_u32(row) - (uint32_t)d.base * 8u;  // shared address of source frame 0 (wraps; only sums are used)
   const int lo = d.lo, hi = d.hi;
   const double pos = d.pos, speed = d.speed;
   const double M = 4503599627370496.0;  // 2^52
@@ -520,9 +547,9 @@ __device__ __forceinline__ void consume_poly(const Desc& d, const uint8_t* row, 
         const double jj = __dadd_rn(jj0, (double)(64 * i + e));
         const double x = __dadd_rn(pos, __dmul_rn(jj, speed));
         const double t = __dadd_rd(x, M);  // floor(x) + 2^52 (x >= 0)
-        const int ix = __double2loint(t);
+        const uint32_t ix = (uint32_t)__double2loint(t);
         const double fd = __dsub_rn(x, __dsub_rn(t, M));
-        const float2 sv = poly_frame(poly, rb, (int64_t)ix, fd);
+        const float2 sv = poly_frame_s(tab_s, rb_s, ix, fd);
         accumulate2(sv, g2, t2, acc[i * 2 + e], pkL, pkR);
       }
     }
@@ -677,6 +704,15 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
   }
   __syncwarp();
 
+  // EXT build: the polyphase coefficient table behind the warps' regions (launch_mix_e sizes the allocation)
+  const float* poly_s = nullptr;
+  if (EXT && p.poly != nullptr) {
+    float* tab = reinterpret_cast<float*>(smem + (size_t)(blockDim.x >> 5) * L::WARP_BYTES);
+    for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) tab[(i >> 4) * POLY_ROW + (i & 15)] = __ldg(p.poly + i);
+    poly_s = tab;
+    __syncthreads();
+  }
+
   const bool two = (p.C == 2);
   const uint32_t N = p.n_tracks, S = p.slots;
   uint32_t n_issued = 0, n_consumed = 0;  // staged items, monotonic over the kernel: stage = n % STAGES
@@ -780,7 +816,7 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
           } else if (kind == K_LIN) {
             consume_lin<FPL>(*dp, row, acc, pkL, pkR, lane, p.one);
           } else if (EXT && kind == K_POLY) {
-            consume_poly<FPL>(*dp, row, p.poly, acc, pkL, pkR, lane);
+            consume_poly<FPL>(*dp, row, poly_s, acc, pkL, pkR, lane);
           } else {
             const Desc d = *dp;
             consume_gen<FPL, EXT>(d, staged ? (const void*)row : d.src, acc, pkL, pkR, lane, two, p.spans, p.poly);
@@ -2106,7 +2142,8 @@ template <int FPL, int STAGES, int WARPS, bool EXT>
 static cudaError_t launch_mix_e(const MixParams& p, int n_sm, cudaStream_t stream, int* ctas_out) {
   using L = MixLayout<FPL, STAGES>;
   auto kfn = mix_kernel<FPL, STAGES, WARPS, EXT>;
-  const int smem = L::WARP_BYTES * WARPS;
+  const int extra = EXT ? POLY_SMEM_BYTES : 0;  // the polyphase table behind the warps' regions
+  const int smem = L::WARP_BYTES * WARPS + extra;
   // attribute + occupancy are properties of the instantiation (per device of the same kind): queried once, not on the
   // realtime callback's path
   static int per_sm_cached[64] = {0};
@@ -2135,7 +2172,7 @@ static cudaError_t launch_mix_e(const MixParams& p, int n_sm, cudaStream_t strea
   if (ctas > need) ctas = need;
   if (ctas < 1) ctas = 1;
   if (ctas_out) *ctas_out = (int)ctas;
-  kfn<<<(unsigned)ctas, wpc * 32, (size_t)L::WARP_BYTES * wpc, stream>>>(p);
+  kfn<<<(unsigned)ctas, wpc * 32, (size_t)L::WARP_BYTES * wpc + extra, stream>>>(p);
   return cudaGetLastError();
 }
 
