@@ -1279,9 +1279,13 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
   const uint32_t spc = (B + 511u) / 512u;  // chunks per callback
   const uint32_t NC = K * spc;
   auto chunk_shape = [&](uint32_t i, uint32_t& k, uint32_t& f0, uint32_t& n) {
-    k = i / spc;
-    f0 = (i % spc) * 512u;
-    n = B - f0 < 512u ? B - f0 : 512u;
+    if (spc == 1u) {  // the usual case (block <= 512 frames): no integer divisions on the per-chunk path
+      k = i, f0 = 0u, n = B;
+    } else {
+      k = i / spc;
+      f0 = (i % spc) * 512u;
+      n = B - f0 < 512u ? B - f0 : 512u;
+    }
   };
   float2* const tb = reinterpret_cast<float2*>(trackbuf) + (size_t)e * tbs;
   const bool tb_vec = (B & 1u) == 0;  // 4-frame groups of the track buffer are 16-byte aligned
@@ -1295,29 +1299,22 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
 #pragma unroll
   for (int i = 0; i < 9; i++) s123[i] = (!w_serial && !w_eq) ? f->sl[i] : 0.0f;
 
-  constexpr uint32_t LAG_S = SH::EQW + 1, LAG_O = SH::EQW + 2;  // chunks the serial / output warps run behind the render
-  // output warps, one slot per (callback, track): cell and span summary of the chunk about to be rendered, fetched one
-  // iteration ahead so that the cell -> span -> source chain of global round trips is off the per-chunk critical path
-  DCell pf_cell, nx_cell;
-  pf_cell.pos = 0.0, pf_cell.span = kSilent, pf_cell.n_act = 0;
-  nx_cell = pf_cell;
-  bool pf_fast = false;
-  uint32_t pf_dst_off = 0;
-  float pf_gain = 0.0f;
-  const float2* pf_base = nullptr;
-  auto span_summary = [&](const DCell& c) {
-    pf_fast = false;
-    if (c.span != kSilent) {
-      const DSpan* sp = spans + c.span;
-      pf_fast = sp->fmt == F_F32 && sp->nch == 2 && sp->speed == 1.0 && sp->fade == 0 && C == 2;
-      pf_dst_off = sp->dst_off;
-      pf_gain = sp->gain;
-      pf_base = reinterpret_cast<const float2*>(sp->base);
+  // chunks behind the render: EQ 1 (2 for the second EQ warp), the follower's intercepts 2 (built by the second EQ warp, or —
+  // with one EQ warp per track — by the track's output warps, which have the slack), the serial warp 3, the output 4
+  constexpr uint32_t LAG_Q = 2, LAG_S = 3, LAG_O = 4;
+  // output warps, one slot per (callback, track): the cell of a chunk is pulled into L1 two iterations before it is read
+  // (a prefetch instruction holds no register across the output stage; an early LOAD did, was spilled, and the spill store
+  // waited for the data — 12 % of the kernel's stall samples), so the cell -> span -> source chain starts from an L1 hit
+  auto prefetch_cell = [&](uint32_t chunk) {
+    if (chunk < NC) {
+      uint32_t pk, pf0, pn;
+      chunk_shape(chunk, pk, pf0, pn);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cells + (size_t)pk * N + t));
     }
   };
-  if (!w_serial && !w_eq && active && S == 1 && NC > 0) {
-    pf_cell = cells[t];  // chunk 0 = callback 0
-    span_summary(pf_cell);
+  if (!w_serial && !w_eq && active && S == 1 && lane == 0 && ow == 0) {
+    prefetch_cell(0);
+    prefetch_cell(1);
   }
   for (uint32_t it = 0; it < NC + LAG_O; it++) {
     if (w_eq) {
@@ -1403,7 +1400,7 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
             if (m < len) *reinterpret_cast<float4*>(seg + 2 * m) = make_float4(xs[m].x, xs[m].y, xs[m + 1].x, xs[m + 1].y);
           __syncwarp();
         }
-        if (comp_on && w_eqb) {
+        if (SH::EQW == 2 && comp_on && w_eqb) {
           const int nb = (int)n >> 2;
           float* qL = sm.Q4[par][2 * tl];
           float* qR = sm.Q4[par][2 * tl + 1];
@@ -1490,36 +1487,71 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
       const int ol = ow * 32 + lane;        // lane among the track's output lanes
       uint32_t rk = 0, rf0 = 0, rn = 0;
       float2 rv[RQ];
-      int rmode = 0;  // 0 nothing, 1 scaled copy of rv, 2 generic per-frame path
+      int rmode = 0;  // 0 nothing, 1 scaled copy of rv, 2 generic per-frame path, 3 scaled copy of a whole chunk
       uint32_t rlo = 0, rhi = 0;
       float rgain = 0.0f;
       if (active && it < NC) {
         chunk_shape(it, rk, rf0, rn);
         rmode = 2;
         if (S == 1) {
-          // the cell of this chunk and the summary of its span were fetched one iteration ago (pf_*): the source loads
-          // below depend on nothing that is still in flight
-          if (pf_cell.span == kSilent) {
+          if (lane == 0 && ow == 0) prefetch_cell(it + 2);
+          const DCell cell = cells[(size_t)rk * N + t];  // in L1 since two iterations ago
+          if (cell.span == kSilent) {
             rmode = 1;  // rlo == rhi: zeros
 #pragma unroll
             for (int q = 0; q < RQ; q++) rv[q] = make_float2(0.0f, 0.0f);
-          } else if (pf_fast) {
-            // unity-speed stereo f32 clip: a scaled copy (src * gain, then the add into the cleared buffer: 0 + m)
-            rmode = 1;
-            rlo = pf_dst_off, rhi = pf_dst_off + pf_cell.n_act;
-            rgain = pf_gain;
-            const float2* src = pf_base + (int64_t)(uint32_t)(int64_t)pf_cell.pos;
+          } else {
+            const DSpan* sp = spans + cell.span;
+            if (sp->fmt == F_F32 && sp->nch == 2 && sp->speed == 1.0 && sp->fade == 0 && C == 2) {
+              // unity-speed stereo f32 clip: a scaled copy (src * gain, then the add into the cleared buffer: 0 + m)
+              rmode = 1;
+              rlo = sp->dst_off, rhi = sp->dst_off + cell.n_act;
+              rgain = sp->gain;
+              const float2* src = reinterpret_cast<const float2*>(sp->base) + (int64_t)(uint32_t)(int64_t)cell.pos;
+              if (rn == 512u && rlo <= rf0 && rhi >= rf0 + 512u) {  // a whole chunk inside the clip: no per-frame range checks
+                rmode = 3;
+                const float2* s0 = src + (rf0 - rlo) + ol;
 #pragma unroll
-            for (int q = 0; q < RQ; q++) {
-              const uint32_t fr = q * SH::OLANES + ol, j = rf0 + fr;
-              rv[q] = (fr < rn && j >= rlo && j < rhi) ? __ldg(src + (j - rlo)) : make_float2(0.0f, 0.0f);
+                for (int q = 0; q < RQ; q++) rv[q] = __ldg(s0 + q * SH::OLANES);
+              } else {
+#pragma unroll
+                for (int q = 0; q < RQ; q++) {
+                  const uint32_t fr = q * SH::OLANES + ol, j = rf0 + fr;
+                  rv[q] = (fr < rn && j >= rlo && j < rhi) ? __ldg(src + (j - rlo)) : make_float2(0.0f, 0.0f);
+                }
+              }
             }
           }
-          if (it + 1 < NC) {  // next chunk's cell: in flight under the output stage below
-            uint32_t nk, nf0, nn;
-            chunk_shape(it + 1, nk, nf0, nn);
-            nx_cell = cells[(size_t)nk * N + t];
+        }
+      }
+      if (SH::EQW == 1 && comp_on && it >= LAG_Q && it - LAG_Q < NC) {
+        // the follower's intercepts of chunk it-2 (its EQ finished last iteration): Q4 per block of 4 frames
+        uint32_t k, f0, n;
+        chunk_shape(it - LAG_Q, k, f0, n);
+        const float* X = tr.X[(it - LAG_Q) % 5u];
+        const int par = (int)((it - LAG_Q) & 1);
+        const int nb = (int)n >> 2;
+        float* qL = sm.Q4[par][2 * tl];
+        float* qR = sm.Q4[par][2 * tl + 1];
+        for (int g = ol; g < nb; g += SH::OLANES) {
+          const float* src = X + fxc_addr(4 * g);
+          const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+          const float2 x4[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)};
+          FxcQ q;
+          fxc_intercepts<4>(x4, att, rel, a1m_s, r1m_s, q);
+#pragma unroll
+          for (int i = 0; i < 5; i++) {
+            qL[i * FXC_BLOCKS + g] = q.q4[i].x;
+            qR[i * FXC_BLOCKS + g] = q.q4[i].y;
           }
+        }
+        const int tail = (int)n & 3;
+        if (ol < tail) {  // the chunk's last 1..3 frames: (pa, pr) for the one-step form
+          const float2 xv = *reinterpret_cast<const float2*>(X + fxc_addr(4 * nb + ol));
+          tr.TP[par][0][ol][0] = __fmul_rn(a1m_s, fabsf(xv.x));
+          tr.TP[par][0][ol][1] = __fmul_rn(r1m_s, fabsf(xv.x));
+          tr.TP[par][1][ol][0] = __fmul_rn(a1m_s, fabsf(xv.y));
+          tr.TP[par][1][ol][1] = __fmul_rn(r1m_s, fabsf(xv.y));
         }
       }
       if (active && it >= LAG_O) {
@@ -1593,7 +1625,16 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
           }
         }
       }
-      if (rmode) {
+      if (rmode == 3) {
+        float* X = tr.X[it % 5u] + fxc_addr(ol);  // frame q * OLANES + ol sits q * (OLANES / 16) segments further on
+#pragma unroll
+        for (int q = 0; q < RQ; q++) {
+          float2 ov;
+          ov.x = __fadd_rn(0.0f, __fmul_rn(rv[q].x, rgain));
+          ov.y = __fadd_rn(0.0f, __fmul_rn(rv[q].y, rgain));
+          *reinterpret_cast<float2*>(X + q * (SH::OLANES / 16) * FXC_SEG_STRIDE) = ov;
+        }
+      } else if (rmode) {
         float* X = tr.X[it % 5u];
 #pragma unroll
         for (int q = 0; q < RQ; q++) {
@@ -1611,10 +1652,6 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
             *reinterpret_cast<float2*>(X + fxc_addr((int)fr)) = ov;
           }
         }
-      }
-      if (active && S == 1 && it + 1 < NC) {
-        pf_cell = nx_cell;
-        span_summary(pf_cell);
       }
     }
     __syncthreads();
