@@ -1119,16 +1119,18 @@ __device__ __forceinline__ float fx_gain(float x, float env, float thr, float ma
 // (explicit _rn intrinsics; packed f32x2 forms are per-component rn), so CUDA == the C spec bit for bit.
 //
 // One CTA carries TPC tracks (1, 2 or 4: enough to give every SM one CTA), software-pipelined over chunks of <= 512
-// frames of a callback, one __syncthreads per iteration:
-//   iteration i:   output warps       loads of the clips of chunk i in flight (Sampler::stream + clip gain), then
+// frames of a callback, one __syncthreads per iteration, chunk c living in ring slot X[c % 5]:
+//   iteration i:   output warps       loads of the clips of chunk i in flight (Sampler::stream + clip gain; the chunk's cell
+//                                     was pulled into L1 two iterations earlier), then
+//                                     chunk i-2: the intercepts Q4 of the follower's 4-step look-ahead per block of 4 frames
+//                                     (with two EQ warps per track the second one builds them instead),
 //                                     chunk i-4: envelope inside each block of 4 frames (1/2/3-step look-ahead from the
 //                                     block start), gain computer, make-up, store to the track buffer the mix kernel
 //                                     reads; then chunk i -> X[i % 5]
-//                  EQ warps a / b     (per track) biquads 0, 1 of chunk i-1 / biquads 2, 3 of chunk i-2, in place: per
-//                                     biquad a zero-state pass over the lane's 16-frame segment, a Kogge-Stone scan of
-//                                     the 32 segment end states with A^(16 * 2^j), the zero-input correction; L and R
-//                                     share coefficients -> packed f32x2 math. Warp b then builds the intercepts Q4 of
-//                                     the follower's 4-step look-ahead per block.
+//                  EQ warp            (per track) the four biquads of chunk i-1 in place: per biquad a zero-state pass
+//                                     over the lane's 16-frame segment, a Kogge-Stone scan of the 32 segment end states
+//                                     with A^(16 * 2^j), the zero-input correction; L and R share coefficients -> packed
+//                                     f32x2 math
 //                  serial warp        chunk i-3: env <- mm_i(S4[i] * env + Q4[i]) per block — the ONLY recurrence that
 //                                     is walked serially (5 independent FMAs + 2 three-input max per 4 frames); lane =
 //                                     (track, channel), so the TPC tracks of the CTA share one instruction stream
@@ -1140,7 +1142,7 @@ constexpr int FXC_QPAIR = 5 * FXC_BLOCKS + 4;     // floats per (parity, pair) o
 constexpr int FXC_EPAIR = FXC_BLOCKS + 4;         // floats per (parity, pair) of block-end envelopes: [3] = incoming, [4 + g]
 
 struct FxcTrack {
-  float X[5][FXC_XSLOT];  // ring: render | EQ a | EQ b | (held) | output
+  float X[5][FXC_XSLOT];  // ring: render | EQ | intercepts | (held while the serial warp runs) | output
   float TP[2][2][3][2];  // tail frames of a chunk (n % 4): (pa, pr) per channel and frame, signed domain
   float ET[2][2][4];     // envelope at the tail frames, signed domain
   float P[4][17][4];     // A^m per biquad (row-major 2x2)
