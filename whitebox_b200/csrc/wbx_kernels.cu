@@ -231,9 +231,12 @@ __device__ __forceinline__ void accumulate(float s, float gain, float tg, float&
   pk = fmaxf(pk, fabsf(term));                           // vu_meter.h:24
 }
 
-// Lane <-> frame mapping of a tile of T = 32*FPL frames: lane owns frame pairs (2q, 2q+1), q = lane + 32*i,
-// i < FPL/2 — for an interleaved stereo f32 window that pair is exactly one 16-byte shared-memory word.
-// acc[i*2+e] is the (L, R) bus accumulator of frame 2*(lane+32*i)+e.
+// Lane <-> frame mapping of a tile of T = 32*FPL frames: lane owns the frames lane + 32*m, m < FPL; acc[m] is the
+// (L, R) bus accumulator of frame lane + 32*m. Consecutive lanes read consecutive source frames: an interleaved stereo
+// f32 frame is one 8-byte shared-memory word, so a warp-wide load of one frame per lane is conflict-free at unity speed
+// and stays within two 128-byte rows for resampled clips (round 1 gave a lane the frame PAIR (2q, 2q+1) for 128-bit
+// loads on the unity path; the resampled paths then read every other word and paid two wavefronts per load).
+// The loops below still run (i, e) with m = 2*i + e.
 
 // Generic per-frame path: any format, unity or linear, staged window (shared) or direct (global) rows.
 // `row` points at window frame 0 (frame-interleaved, NCH channels); d.base is that frame's sample index.
@@ -320,7 +323,7 @@ __device__ __forceinline__ void consume_gen_t(const Desc& d, const void* row, fl
   for (int i = 0; i < FPL / 2; i++) {
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const int fr = 2 * (lane + 32 * i) + e;
+      const int fr = lane + 32 * (2 * i + e);
       if (fr >= (int)d.lo && fr < (int)d.hi) {
         const int32_t jj = fr + d.jrel0;
         float sL, sR = 0.0f;
@@ -404,23 +407,23 @@ __device__ __forceinline__ void consume_gen(const Desc& d, const void* row, floa
   }
 }
 
-// Fast path: stereo f32, unity speed, the whole tile, 16-B aligned window. One 128-bit shared load = two
-// (L, R) frames; gain, pan and the bus add run as packed f32x2 (each component separately rounded, rn).
+// Fast path: stereo f32, unity speed, the whole tile. One 64-bit shared load = one (L, R) frame; gain, pan and the bus
+// add run as packed f32x2 (each component separately rounded, rn).
 template <int FPL>
 __device__ __forceinline__ void consume_fast(const uint8_t* row, float gain, float tgL, float tgR,
                                              float2 (&acc)[FPL], float& pkL, float& pkR, int lane) {
-  const float4* r4 = reinterpret_cast<const float4*>(row);
+  const float2* r2 = reinterpret_cast<const float2*>(row);
   const float2 g2 = make_float2(gain, gain);
   const float2 t2 = make_float2(tgL, tgR);
-  float4 v[FPL / 2];
+  float2 v[FPL];
 #pragma unroll
-  for (int i = 0; i < FPL / 2; i++) v[i] = r4[lane + 32 * i];
+  for (int m = 0; m < FPL; m++) v[m] = r2[lane + 32 * m];
 #pragma unroll
-  for (int i = 0; i < FPL / 2; i++) {
-    const float2 a = __fmul2_rn(__fmul2_rn(make_float2(v[i].x, v[i].y), g2), t2);  // frame 2q:   (L, R)
-    const float2 b = __fmul2_rn(__fmul2_rn(make_float2(v[i].z, v[i].w), g2), t2);  // frame 2q+1: (L, R)
-    acc[i * 2 + 0] = __fadd2_rn(acc[i * 2 + 0], a);
-    acc[i * 2 + 1] = __fadd2_rn(acc[i * 2 + 1], b);
+  for (int m = 0; m < FPL; m += 2) {
+    const float2 a = __fmul2_rn(__fmul2_rn(v[m], g2), t2);      // frame lane + 32 m:       (L, R)
+    const float2 b = __fmul2_rn(__fmul2_rn(v[m + 1], g2), t2);  // frame lane + 32 (m + 1): (L, R)
+    acc[m] = __fadd2_rn(acc[m], a);
+    acc[m + 1] = __fadd2_rn(acc[m + 1], b);
     pkL = fmaxf(fmaxf(pkL, fabsf(a.x)), fabsf(b.x));
     pkR = fmaxf(fmaxf(pkR, fabsf(a.y)), fabsf(b.y));
   }
@@ -448,7 +451,7 @@ __device__ __forceinline__ void consume_uni_t(const Desc& d, const uint8_t* row,
   for (int i = 0; i < FPL / 2; i++) {
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const int fr = 2 * (lane + 32 * i) + e;
+      const int fr = lane + 32 * (2 * i + e);
       if (FULL || (fr >= lo && fr < hi)) accumulate2(r2[fr + shift], g2, t2, acc[i * 2 + e], pkL, pkR);
     }
   }
@@ -485,7 +488,7 @@ __device__ __forceinline__ void consume_lin_t(const Desc& d, const uint8_t* row,
   const uint32_t rb = smem_u32(row) - (uint32_t)d.base * 8u;  // shared address of source frame 0 (wraps; only sums are used)
   const double pos = d.pos, speed = d.speed;
   const double M = 4503599627370496.0;  // 2^52
-  const double jj0 = (double)(d.jrel0 + 2 * lane);
+  const double jj0 = (double)(d.jrel0 + lane);
   const float2 g2 = make_float2(d.gain, d.gain);
   const float2 t2 = make_float2(d.tg[0], d.tg[1]);
   const float2 neg1 = make_float2(-1.0f, -1.0f);
@@ -495,10 +498,10 @@ __device__ __forceinline__ void consume_lin_t(const Desc& d, const uint8_t* row,
     float2 term[2];
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const int fr = 2 * (lane + 32 * i) + e;
+      const int fr = lane + 32 * (2 * i + e);
       term[e] = make_float2(0.0f, 0.0f);
       if (FULL || (fr >= lo && fr < hi)) {
-        const double jj = __dadd_rn(jj0, (double)(64 * i + e));  // exact small integers == (double)j
+        const double jj = __dadd_rn(jj0, (double)(32 * (2 * i + e)));  // exact small integers == (double)j
         const double x = __dadd_rn(pos, __dmul_rn(jj, speed));   // sampler.cpp:50
         const double t = __dadd_rd(x, M);                        // floor(x) + 2^52
         const uint32_t ix = (uint32_t)__double2loint(t);         // (int64_t)x, :51
@@ -535,16 +538,16 @@ __device__ __forceinline__ void consume_poly(const Desc& d, const uint8_t* row, 
   const int lo = d.lo, hi = d.hi;
   const double pos = d.pos, speed = d.speed;
   const double M = 4503599627370496.0;  // 2^52
-  const double jj0 = (double)(d.jrel0 + 2 * lane);
+  const double jj0 = (double)(d.jrel0 + lane);
   const float2 g2 = make_float2(d.gain, d.gain);
   const float2 t2 = make_float2(d.tg[0], d.tg[1]);
 #pragma unroll
   for (int i = 0; i < FPL / 2; i++) {
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const int fr = 2 * (lane + 32 * i) + e;
+      const int fr = lane + 32 * (2 * i + e);
       if (fr >= lo && fr < hi) {
-        const double jj = __dadd_rn(jj0, (double)(64 * i + e));
+        const double jj = __dadd_rn(jj0, (double)(32 * (2 * i + e)));
         const double x = __dadd_rn(pos, __dmul_rn(jj, speed));
         const double t = __dadd_rd(x, M);  // floor(x) + 2^52 (x >= 0)
         const uint32_t ix = (uint32_t)__double2loint(t);
@@ -686,7 +689,7 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
 }
 
 template <int FPL, int STAGES, int WARPS, bool EXT>
-__global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
+__global__ void __launch_bounds__(WARPS * 32, 2) mix_kernel(const MixParams p) {
   using L = MixLayout<FPL, STAGES>;
   constexpr int BATCH = L::BATCH;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -866,44 +869,30 @@ __global__ void __launch_bounds__(WARPS * 32) mix_kernel(const MixParams p) {
       outp[1] = outp[0] + chan_stride;
     }
     const size_t out_off = (size_t)k * p.B + f0;
-    const bool vec_ok = (p.B & 1u) == 0;  // frame pairs are 8-byte aligned in the planar bus
+    const bool vec_ok = (p.B & 1u) == 0;  // frame pairs are 8-byte aligned in the planar bus (tree mode's final stores)
     if (p.groups == 1) {
 #pragma unroll
-      for (int i = 0; i < FPL / 2; i++) {
-        const int fr = 2 * (lane + 32 * i);
-        float v[2][2] = {{acc[i * 2].x, acc[i * 2 + 1].x}, {acc[i * 2].y, acc[i * 2 + 1].y}};
+      for (int m = 0; m < FPL; m++) {
+        const int fr = lane + 32 * m;  // one frame per lane: every store is one contiguous 128-byte run per warp
+        if (fr < tile_len) {
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-          if (c == 1 && !two) break;
-          float* out = outp[c];
-          float x0 = v[c][0], x1 = v[c][1];
-          if (p.clamp) {  // engine.cpp:1627-1636 (NaN passes)
-            x0 = x0 > 1.0f ? 1.0f : (x0 < -1.0f ? -1.0f : x0);
-            x1 = x1 > 1.0f ? 1.0f : (x1 < -1.0f ? -1.0f : x1);
-          }
-          float* mir = p.mirror[c] ? p.mirror[c] + out_off : nullptr;
-          if (vec_ok && fr + 1 < tile_len) {
-            *reinterpret_cast<float2*>(out + fr) = make_float2(x0, x1);
-            if (mir) *reinterpret_cast<float2*>(mir + fr) = make_float2(x0, x1);
-          } else {
-            if (fr < tile_len) out[fr] = x0;
-            if (fr + 1 < tile_len) out[fr + 1] = x1;
-            if (mir) {
-              if (fr < tile_len) mir[fr] = x0;
-              if (fr + 1 < tile_len) mir[fr + 1] = x1;
-            }
+          for (int c = 0; c < 2; c++) {
+            if (c == 1 && !two) break;
+            float x0 = c ? acc[m].y : acc[m].x;
+            if (p.clamp) x0 = x0 > 1.0f ? 1.0f : (x0 < -1.0f ? -1.0f : x0);  // engine.cpp:1627-1636 (NaN passes)
+            outp[c][fr] = x0;
+            if (p.mirror[c]) p.mirror[c][out_off + fr] = x0;
           }
         }
       }
     } else {
       // tree mode: publish this group's partial, the last group to arrive adds them in group order
       const uint32_t tile_id = k * p.n_tiles + f;
-      float2* part = reinterpret_cast<float2*>(p.ws) + ((size_t)tile_id * p.groups + g) * 2 * (L::T / 2);
+      float* part = p.ws + ((size_t)tile_id * p.groups + g) * 2 * L::T;  // [channel][T] planar
 #pragma unroll
-      for (int i = 0; i < FPL / 2; i++) {
-        const int q = lane + 32 * i;
-        part[q] = make_float2(acc[i * 2].x, acc[i * 2 + 1].x);               // channel 0, frames 2q, 2q+1
-        part[(L::T / 2) + q] = make_float2(acc[i * 2].y, acc[i * 2 + 1].y);  // channel 1
+      for (int m = 0; m < FPL; m++) {
+        part[lane + 32 * m] = acc[m].x;         // channel 0
+        part[L::T + lane + 32 * m] = acc[m].y;  // channel 1
       }
       __threadfence();
       __syncwarp();
