@@ -1,10 +1,7 @@
 set -x
-O=gpurun_out/r02o
+O=gpurun_out/r02p
 mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -5 $O/pytest_gpu.log
-python tools/kbench.py --tracks 1024 --blocks 4096 --fpl 16 --iters 5 > $O/kbench.log 2>&1
-python tools/kbench.py --tracks 1024 --blocks 4096 --rate 44100 --fpl 16 --iters 5 >> $O/kbench.log 2>&1
-python tools/kbench.py --tracks 1024 --blocks 1024 --rate 44100 --poly 1 --fpl 16 --iters 5 >> $O/kbench.log 2>&1
-python tools/kbench.py --tracks 1024 --blocks 4096 --offset 1 --fpl 16 --iters 5 >> $O/kbench.log 2>&1
-cat $O/kbench.log
-for n in 64 1024; do python tools/latency.py --tracks $n --mode auto >> $O/latency.log 2>&1; done; cat $O/latency.log
+NCU="ncu --set full --clock-control none --import-source on -c 1"
+timeout 400 $NCU -k regex:mix_kernel --launch-skip 2 -o $O/mix_cfg2 python tools/kbench.py --tracks 1024 --blocks 4096 --fpl 16 --iters 1 > $O/ncu_mix_cfg2.out 2>&1
+timeout 400 $NCU -k regex:mix_kernel --launch-skip 2 -o $O/mix_cfg3 python tools/kbench.py --tracks 1024 --blocks 4096 --rate 44100 --fpl 16 --iters 1 > $O/ncu_mix_cfg3.out 2>&1
+timeout 400 $NCU -k regex:mix_kernel --launch-skip 2 -o $O/mix_poly python tools/kbench.py --tracks 1024 --blocks 1024 --rate 44100 --poly 1 --fpl 16 --iters 1 > $O/ncu_poly.out 2>&1

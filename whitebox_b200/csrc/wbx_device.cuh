@@ -117,14 +117,16 @@ static_assert(sizeof(DCell) == 16, "DCell layout");
 // item kinds after resolve (per cell and frame tile)
 enum : uint32_t {
   K_SILENT = 0,
-  K_FAST = 1,    // stereo f32, unity speed, whole tile, 16-B aligned window: 128-bit loads + packed f32x2 math
+  K_FAST = 1,    // stereo f32, unity speed, whole tile, window starting on tile frame 0: packed f32x2 math, no index math
   K_GEN = 2,     // anything else whose window fits a stage: per-frame path on the staged window
   K_DIRECT = 3,  // window larger than a stage (speed well above 1): per-frame path straight from global
-  K_UNI = 4,     // stereo f32, unity speed, odd start frame or partial tile: 64-bit loads + packed math
+  K_UNI = 4,     // stereo f32, unity speed, odd start frame (whole tile): 64-bit loads + packed math
   K_LIN = 5,     // stereo f32, 2-tap linear resample from the staged window, conversion-free position split
   K_FADE = 6,        // a fade ramp overlaps this tile: per-frame path times the envelope (staged window)
   K_DIRECT_FADE = 7, // K_DIRECT with a fade ramp
-  K_POLY = 8         // stereo f32, polyphase windowed-sinc resample (extension) from the staged window
+  K_POLY = 8,        // stereo f32, polyphase windowed-sinc resample (extension) from the staged window
+  K_UNI_P = 9,       // K_UNI / K_LIN on a partial tile (per-frame range checks); the plain kinds cover the whole tile
+  K_LIN_P = 10
 };
 
 // Resolved per-(cell, tile) descriptor, lives in shared memory (64 B).

@@ -457,14 +457,6 @@ __device__ __forceinline__ void consume_uni_t(const Desc& d, const uint8_t* row,
   }
 }
 
-template <int FPL>
-__device__ __forceinline__ void consume_uni(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
-                                            float& pkR, int lane) {
-  if (d.lo == 0 && d.hi == 32 * FPL)  // whole tile: no per-frame range checks
-    consume_uni_t<FPL, true>(d, row, acc, pkL, pkR, lane);
-  else
-    consume_uni_t<FPL, false>(d, row, acc, pkL, pkR, lane);
-}
 
 // Stereo f32, 2-tap linear resample (sample_linear<float, F32>, dsp/sampler.cpp:34-59) from the staged window.
 // The position split avoids the slow f64<->int conversions: for 0 <= x < 2^31, t = x + 2^52 rounded TOWARDS
@@ -520,14 +512,6 @@ __device__ __forceinline__ void consume_lin_t(const Desc& d, const uint8_t* row,
   }
 }
 
-template <int FPL>
-__device__ __forceinline__ void consume_lin(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
-                                            float& pkR, int lane, float one) {
-  if (d.lo == 0 && d.hi == 32 * FPL)  // whole tile: no per-frame range checks
-    consume_lin_t<FPL, true>(d, row, acc, pkL, pkR, lane, one);
-  else
-    consume_lin_t<FPL, false>(d, row, acc, pkL, pkR, lane, one);
-}
 
 // Stereo f32, polyphase windowed-sinc resample (extension) from the staged window: the lin path's position split,
 // then 16 taps per frame.
@@ -669,9 +653,9 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
         else if (poly)
           d.kind = K_POLY;
         else if (st32 && unity)
-          d.kind = (lo == 0 && hi == T && first == a) ? K_FAST : K_UNI;
+          d.kind = (lo == 0 && hi == T) ? (first == a ? K_FAST : K_UNI) : K_UNI_P;
         else if (st32 && last < (int64_t)0x3fffffff)
-          d.kind = K_LIN;
+          d.kind = (lo == 0 && hi == T) ? K_LIN : K_LIN_P;
         else
           d.kind = K_GEN;
       } else {  // window larger than a stage (speed well above 1): read the source straight from global
@@ -734,7 +718,6 @@ __global__ void __launch_bounds__(WARPS * 32, 2) mix_kernel(const MixParams p) {
     const DCell* cells = p.cells + ((size_t)k * N + tb) * S;
     const int f0 = (int)(f * L::T);
     const int tile_len = ((int)p.B - f0 < L::T) ? (int)p.B - f0 : L::T;
-    float* peaks_k = p.peaks + (size_t)k * N * 2;
 
     float2 acc[FPL];
 #pragma unroll
@@ -767,12 +750,11 @@ __global__ void __launch_bounds__(WARPS * 32, 2) mix_kernel(const MixParams p) {
       const uint32_t lim = limit < n_cells ? limit : n_cells;
       while (ip < lim && (n_issued - n_consumed) < (uint32_t)STAGES) {
         const Desc* dd = &ring[ip & (L::RING - 1)];
-        const uint32_t kind = dd->kind;
-        if (kind != K_SILENT && kind != K_DIRECT && kind != K_DIRECT_FADE) {
+        const uint32_t bytes = dd->bytes;  // non-zero exactly for the kinds that stage a window
+        if (bytes) {
           if (lane == 0) {
             const uint32_t st = n_issued % STAGES;
             const uint32_t bar = bars_s + 8 * st;
-            const uint32_t bytes = dd->bytes;
             mbar_expect_tx(bar, bytes);
             bulk_g2s(rows_s + st * L::STAGE_BYTES, dd->src, bytes, bar);
           }
@@ -814,10 +796,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) mix_kernel(const MixParams p) {
           const uint8_t* row = wbase + (size_t)st * L::STAGE_BYTES;
           if (kind == K_FAST) {
             consume_fast<FPL>(row, dp->gain, dp->tg[0], dp->tg[1], acc, pkL, pkR, lane);
-          } else if (kind == K_UNI) {
-            consume_uni<FPL>(*dp, row, acc, pkL, pkR, lane);
           } else if (kind == K_LIN) {
-            consume_lin<FPL>(*dp, row, acc, pkL, pkR, lane, p.one);
+            consume_lin_t<FPL, true>(*dp, row, acc, pkL, pkR, lane, p.one);
+          } else if (kind == K_UNI) {
+            consume_uni_t<FPL, true>(*dp, row, acc, pkL, pkR, lane);
+          } else if (kind == K_LIN_P) {
+            consume_lin_t<FPL, false>(*dp, row, acc, pkL, pkR, lane, p.one);
+          } else if (kind == K_UNI_P) {
+            consume_uni_t<FPL, false>(*dp, row, acc, pkL, pkR, lane);
           } else if (EXT && kind == K_POLY) {
             consume_poly<FPL>(*dp, row, poly_s, acc, pkL, pkR, lane);
           } else {
@@ -839,7 +825,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) mix_kernel(const MixParams p) {
             const uint32_t mR = __reduce_max_sync(0xffffffffu, __float_as_uint(pkR));
             if (lane < 2 && (lane == 0 || two)) {
               const uint32_t m = lane ? mR : mL;
-              uint32_t* dst = reinterpret_cast<uint32_t*>(peaks_k + (size_t)cur_track * 2 + lane);
+              uint32_t* dst = reinterpret_cast<uint32_t*>(p.peaks) + ((k * N + cur_track) * 2u + (uint32_t)lane);  // < 2^32 (launch_mix)
               if (p.n_tiles == 1)
                 *dst = m;
               else if (m != 0u)
@@ -2219,6 +2205,7 @@ static int variant_b() {
 }
 
 cudaError_t launch_mix(const MixParams& p, int fpl, int n_sm, cudaStream_t stream, int* ctas_out) {
+  if ((uint64_t)p.n_blocks * p.n_tracks * 2u >= (1ull << 32)) return cudaErrorInvalidValue;  // the kernel indexes peaks in 32 bits
   if (fpl == 16 && variant_b()) return launch_mix_t<16, 2, 8>(p, n_sm, stream, ctas_out);
   switch (fpl) {
     case 16: return launch_mix_t<16, 3, 7>(p, n_sm, stream, ctas_out);
