@@ -163,10 +163,13 @@ typedef struct wbx_effects { /* designed coefficients */
 int wbx_effects_design(const wbx_effect_params* params, uint32_t sample_rate, wbx_effects* out);
 /* Convolution reverb (extension, BASELINE cfg 5): one impulse response h[0..n_taps) per engine, applied as the last
  * stage of every chain with reverb_on: y[n] = sum_k h[k] * x[n-k] with the history carried across renders.
- * Specification = f64 accumulation (oracle/wb_oracle.c apply_reverb). Two implementations, both held to 1e-5 of the block
- * peak: responses of >= 1024 taps run on the tensor cores (the convolution as a Toeplitz GEMM, tcgen05.mma on a 2-term
- * fp16 split of both operands, f32 accumulation in TMEM drained periodically), shorter ones as a direct form on the CUDA
- * cores (f32 fused multiply-adds per 256-tap tile, tiles summed in f64). WBX_FIR=direct|tc overrides the threshold.
+ * Specification = f64 accumulation (oracle/wb_oracle.c apply_reverb). Three implementations, all held to 1e-5 of the block
+ * peak: responses of >= 1024 taps run as a uniformly partitioned FFT convolution (overlap-save, f32, a track's two channels
+ * as one complex signal; partitions of 2048 taps for long renders, 512 for short ones; the window spectra persist across
+ * renders), shorter ones as a direct form on the CUDA cores (f32 fused multiply-adds per 256-tap tile, tiles summed in
+ * f64); the direct form on the tensor cores (the convolution as a Toeplitz GEMM, tcgen05.mma on a 2-term fp16 split of
+ * both operands, f32 accumulation in TMEM drained periodically) is kept selectable. WBX_FIR=direct|tc|fft picks by hand
+ * (read here); wbx_fir_path tells which one an engine uses.
  * h == NULL or n_taps == 0 removes it. Changing it clears every track's reverb history. */
 int wbx_set_impulse_response(wbx_engine* e, const float* h, uint32_t n_taps);
 /* Attach (fx != NULL) or remove (NULL) a track's chain and clear its state. Tracks without a chain take the
