@@ -610,6 +610,15 @@ def test_render_into_page_locked_channels(wb, K, B, mode):
     plain = np.zeros((2, K * B), np.float32)
     assert dev.L.wbx_render_levels(dev.h, segs.ctypes.data, N, gains.ctypes.data, K, wb._chan_ptrs(plain), None, None) == 0
     assert same_bits(plain, out)
+    # ... and the same pageable allocation page-locked in place (wbx_host_register): the kernel writes it directly
+    plain[:] = 3.0
+    assert dev.L.wbx_host_register(plain.ctypes.data, plain.nbytes) == 0
+    try:
+        assert dev.L.wbx_render_levels(dev.h, segs.ctypes.data, N, gains.ctypes.data, K, wb._chan_ptrs(plain), None, None) == 0
+        assert same_bits(plain, out)
+    finally:
+        dev.synchronize()
+        assert dev.L.wbx_host_unregister(plain.ctypes.data) == 0
 
 
 def _sharded_setup(wb, world, N, K, B, C=2, seed=11, empty_rank=None):
