@@ -36,9 +36,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -50,11 +47,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// global -> shared bulk copy, 16-B aligned addresses, size a multiple of 16; completes `bytes` on `bar`.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+// global -> shared bulk copy (16-B aligned addresses, size a multiple of 16; completes `bytes` on `bar`):
+// one elected lane of a CONVERGED warp announces `bytes` on `bar` and issues the bulk copy. Written as one predicated
+// block around elect.sync: ptxas then knows a single lane is active and moves the operands to uniform registers with
+// plain R2UR — an `if (lane == 0)` around the same two instructions compiles to a divergent branch plus a
+// first-active-lane loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) around UBLKCP, ~20 more instructions per copy.
+__device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -587,8 +592,8 @@ __device__ __forceinline__ DSpan load_span(const DSpan* spans, const DCell& c) {
 
 // Turn (cell, span) into the per-tile descriptor: which frames, which source window, which code path.
 template <int STAGE_BYTES, int T>
-__device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, const float* __restrict__ gains,
-                                              int f0, int tile_len, bool two, uint32_t k, Desc* out) {
+__device__ __forceinline__ uint32_t resolve_store(const DCell& c, const DSpan& s, const float* __restrict__ gains,
+                                                  int f0, int tile_len, bool two, uint32_t k, Desc* out) {
   Desc d;
   d.src = nullptr;
   d.pos = c.pos;
@@ -670,6 +675,17 @@ __device__ __forceinline__ void resolve_store(const DCell& c, const DSpan& s, co
   o[1] = q[1];
   o[2] = q[2];
   o[3] = q[3];
+  return d.kind;
+}
+
+// A batch of descriptors is LEAN when its BATCH cells all resolved to the same whole-tile stereo-f32 kind (the shape of
+// BASELINE cfg 2 / cfg 3: every track plays one clip across the tile). Such a batch runs through a loop that knows the
+// kind, knows every cell stages a window and (one slot per track) ends a track: no per-cell dispatch, no `bytes` test in
+// front of the bulk copy, no slot / activity bookkeeping. Returns the kind, 0 when the batch is mixed. All lanes call.
+__device__ __forceinline__ uint32_t lean_batch_kind(uint32_t my_kind, int lane, int batch) {
+  const uint32_t k0 = __shfl_sync(0xffffffffu, my_kind, 0);
+  const bool same = __all_sync(0xffffffffu, lane >= batch || my_kind == k0);
+  return (same && (k0 == K_FAST || k0 == K_LIN || k0 == K_UNI)) ? k0 : 0u;
 }
 
 template <int FPL, int STAGES, int WARPS, bool EXT>
@@ -730,12 +746,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) mix_kernel(const MixParams p) {
     // descriptors of the first batch (lanes >= BATCH idle); the barrier orders the previous item's last descriptor reads
     // before these writes (the shuffle above synchronises execution, not memory)
     __syncwarp();
+    uint32_t mk0 = K_SILENT;
     if (lane < BATCH) {
       const DCell c0 = load_cell(cells, lane, n_cells);
       const DSpan s0 = load_span(p.spans, c0);
-      resolve_store<L::STAGE_BYTES, L::T>(c0, s0, p.gains, f0, tile_len, two, k, &ring[lane]);
+      mk0 = resolve_store<L::STAGE_BYTES, L::T>(c0, s0, p.gains, f0, tile_len, two, k, &ring[lane]);
     }
     __syncwarp();
+    uint32_t lean = (S == 1u) ? lean_batch_kind(mk0, lane, BATCH) : 0u;  // kind of the current batch when it is lean
     uint32_t limit = BATCH;  // cells [0, limit) have descriptors
     uint32_t ip = 0;         // next cell to consider for staging
     const uint32_t nb = (n_cells + BATCH - 1) / BATCH;
@@ -752,33 +770,134 @@ __global__ void __launch_bounds__(WARPS * 32, 2) mix_kernel(const MixParams p) {
         const Desc* dd = &ring[ip & (L::RING - 1)];
         const uint32_t bytes = dd->bytes;  // non-zero exactly for the kinds that stage a window
         if (bytes) {
-          if (lane == 0) {
-            const uint32_t st = n_issued % STAGES;
-            const uint32_t bar = bars_s + 8 * st;
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(rows_s + st * L::STAGE_BYTES, dd->src, bytes, bar);
-          }
+          const uint32_t st = n_issued % STAGES;
+          bulk_g2s_elect(rows_s + st * L::STAGE_BYTES, dd->src, bytes, bars_s + 8 * st);
           n_issued++;
         }
         ip++;
       }
     };
+    // VU block peak of a finished track (vu_meter.h:20-30). Peaks are >= 0 and never NaN (fmaxf drops NaNs), so uint
+    // order == float order: one warp-wide integer max per channel (REDUX) instead of a five-step shuffle butterfly
+    auto flush_peaks = [&](uint32_t track) {
+      const uint32_t mL = __reduce_max_sync(0xffffffffu, __float_as_uint(pkL));
+      const uint32_t mR = __reduce_max_sync(0xffffffffu, __float_as_uint(pkR));
+      if (lane < 2 && (lane == 0 || two)) {
+        const uint32_t m = lane ? mR : mL;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(p.peaks) + ((k * N + track) * 2u + (uint32_t)lane);  // < 2^32 (launch_mix)
+        if (p.n_tiles == 1)
+          *dst = m;
+        else if (m != 0u)
+          atomicMax(dst, m);
+      }
+      pkL = 0.0f;
+      pkR = 0.0f;
+    };
 
     for (uint32_t b = 0; b < nb; b++) {
       const bool more = (b + 1 < nb);
       if (more && lane < BATCH) cN = load_cell(cells, (b + 1) * BATCH + lane, n_cells);
+      uint32_t lean_next = 0u;
+      // descriptors of the next batch, half a batch ahead
+      auto resolve_next = [&]() {
+        __syncwarp();  // every lane is done reading the ring half written next (the previous batch's descriptors)
+        uint32_t mk = K_SILENT;
+        if (lane < BATCH)
+          mk = resolve_store<L::STAGE_BYTES, L::T>(cN, sN, p.gains, f0, tile_len, two, k, &ring[((b + 1) & 1) * BATCH + lane]);
+        __syncwarp();
+        limit += BATCH;
+        if (S == 1u) lean_next = lean_batch_kind(mk, lane, BATCH);
+      };
+      // ---- lean batch: BATCH whole-tile cells of one kind, each staging a window and ending its track ------------------
+      // The pipeline is brought to depth STAGES - 1 up front, so the producer is at most one step per cell (a mixed batch
+      // before this one may have left it full: the depth test stays); descriptors are walked by byte offset; the 16 block
+      // peaks are parked in lanes 0..15 and stored once per batch (tracks of a batch are neighbours: one 128-byte run).
+      auto lean_batch = [&](auto kind_c) {
+        constexpr uint32_t KIND = decltype(kind_c)::value;
+        constexpr uint32_t RING_BYTES = L::RING * (uint32_t)sizeof(Desc);
+        uint32_t stage_lim = (b + 1) * BATCH;  // cells below it are known to stage a window
+        const uint8_t* ring_b = reinterpret_cast<const uint8_t*>(ring);
+        auto stage_one = [&]() {
+          const Desc* dd = reinterpret_cast<const Desc*>(ring_b + (ip * (uint32_t)sizeof(Desc)) % RING_BYTES);
+          const uint32_t st = n_issued % STAGES;
+          bulk_g2s_elect(rows_s + st * L::STAGE_BYTES, dd->src, dd->bytes, bars_s + 8 * st);
+          n_issued++;
+          ip++;
+        };
+        while (ip < stage_lim && (n_issued - n_consumed) < (uint32_t)(STAGES - 1)) stage_one();
+        uint32_t keepL = 0u, keepR = 0u;  // lane i: block peaks of the batch's cell i
+        uint32_t doff = (b & 1u) * BATCH * (uint32_t)sizeof(Desc);
+        int cib = 0;  // cell within the batch
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+          if (more) {
+            if (q == 1 && lane < BATCH) sN = load_span(p.spans, cN);
+            if (q == 2) {
+              resolve_next();
+              if (lean_next) stage_lim += BATCH;
+            }
+          }
+#pragma unroll 1
+          for (int j = 0; j < 4; j++) {
+            if (ip < stage_lim && (n_issued - n_consumed) < (uint32_t)STAGES) stage_one();
+            const Desc* dp = reinterpret_cast<const Desc*>(ring_b + doff);
+            const uint32_t st = n_consumed % STAGES;
+            const uint32_t par = (n_consumed / STAGES) & 1u;
+            while (!mbar_try_wait(bars_s + 8 * st, par)) {
+            }
+            const uint8_t* row = wbase + (size_t)st * L::STAGE_BYTES;
+            if (KIND == K_FAST)
+              consume_fast<FPL>(row, dp->gain, dp->tg[0], dp->tg[1], acc, pkL, pkR, lane);
+            else if (KIND == K_LIN)
+              consume_lin_t<FPL, true>(*dp, row, acc, pkL, pkR, lane, p.one);
+            else
+              consume_uni_t<FPL, true>(*dp, row, acc, pkL, pkR, lane);
+            __syncwarp();  // every lane is done reading the stage before the elected lane may refill it
+            n_consumed++;
+            const uint32_t mL = __reduce_max_sync(0xffffffffu, __float_as_uint(pkL));
+            const uint32_t mR = __reduce_max_sync(0xffffffffu, __float_as_uint(pkR));
+            if (lane == cib) keepL = mL, keepR = mR;
+            pkL = 0.0f;
+            pkR = 0.0f;
+            cib++;
+            doff += (uint32_t)sizeof(Desc);
+          }
+        }
+        if (lane < BATCH) {  // VU block peaks of the batch (vu_meter.h:20-30), as flush_peaks stores them
+          const uint32_t track = ring[(b & 1u) * BATCH + lane].track;
+          uint32_t* dst = reinterpret_cast<uint32_t*>(p.peaks) + (k * N + track) * 2u;  // < 2^32 (launch_mix)
+          if (p.n_tiles == 1) {
+            if (two)
+              *reinterpret_cast<uint2*>(dst) = make_uint2(keepL, keepR);
+            else
+              dst[0] = keepL;
+          } else {
+            if (keepL != 0u) atomicMax(dst, keepL);
+            if (two && keepR != 0u) atomicMax(dst + 1, keepR);
+          }
+        }
+      };
+      if (lean == K_LIN) {
+        lean_batch(std::integral_constant<uint32_t, K_LIN>());
+        lean = lean_next;
+        continue;
+      }
+      if (lean == K_FAST) {
+        lean_batch(std::integral_constant<uint32_t, K_FAST>());
+        lean = lean_next;
+        continue;
+      }
+      if (lean == K_UNI) {
+        lean_batch(std::integral_constant<uint32_t, K_UNI>());
+        lean = lean_next;
+        continue;
+      }
 #pragma unroll 1
       for (int i = 0; i < BATCH; i++) {
         const uint32_t ci = b * BATCH + i;
         if (ci >= n_cells) break;
         if (more && i == BATCH / 4 && lane < BATCH) sN = load_span(p.spans, cN);
-        if (more && i == BATCH / 2) {
-          __syncwarp();  // every lane is done reading the ring half written next (the previous batch's descriptors)
-          if (lane < BATCH)
-            resolve_store<L::STAGE_BYTES, L::T>(cN, sN, p.gains, f0, tile_len, two, k, &ring[((b + 1) & 1) * BATCH + lane]);
-          __syncwarp();
-          limit += BATCH;
-        }
+        if (more && i == BATCH / 2) resolve_next();
         produce();
         // ---- consumer role ------------------------------------------------------------------------------
         const Desc* dp = &ring[ci & (L::RING - 1)];
@@ -819,24 +938,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2) mix_kernel(const MixParams p) {
         if (++slot_ctr == S) {
           slot_ctr = 0;
           if (active) {
-            // peaks are >= 0 and never NaN (fmaxf drops NaNs), so uint order == float order: one warp-wide integer
-            // max per channel (REDUX) instead of a five-step shuffle butterfly and its serial latency
-            const uint32_t mL = __reduce_max_sync(0xffffffffu, __float_as_uint(pkL));
-            const uint32_t mR = __reduce_max_sync(0xffffffffu, __float_as_uint(pkR));
-            if (lane < 2 && (lane == 0 || two)) {
-              const uint32_t m = lane ? mR : mL;
-              uint32_t* dst = reinterpret_cast<uint32_t*>(p.peaks) + ((k * N + cur_track) * 2u + (uint32_t)lane);  // < 2^32 (launch_mix)
-              if (p.n_tiles == 1)
-                *dst = m;
-              else if (m != 0u)
-                atomicMax(dst, m);
-            }
-            pkL = 0.0f;
-            pkR = 0.0f;
+            flush_peaks(cur_track);
             active = false;
           }
         }
       }
+      lean = lean_next;
     }
 
     // ---- bus write ------------------------------------------------------------------------------------
