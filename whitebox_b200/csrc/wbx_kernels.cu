@@ -478,9 +478,16 @@ __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
 // exactly (prod * 1 is exact, one rounding), but unlike mul.rn.f32x2 + add.rn.f32x2 it cannot be contracted into a
 // fused multiply-add of the product's own factors (ptxas does that even under --fmad false when the product has a
 // single use; tests/test_host_cpu.py lints the SASS). It makes the lerp three packed instructions instead of five.
+#ifndef WBX_LIN_GROUP
+#define WBX_LIN_GROUP 8
+#endif
+// Frames are taken WBX_LIN_GROUP at a time in three phases — the f64 position chains of the group, its shared-memory
+// loads, the packed lerp / gain / bus add — so that several dependent chains (7 f64-pipe operations deep each) are in
+// flight per warp; every frame has its own accumulator, so the grouping does not touch the arithmetic.
 template <int FPL, bool FULL>
 __device__ __forceinline__ void consume_lin_t(const Desc& d, const uint8_t* row, float2 (&acc)[FPL], float& pkL,
                                               float& pkR, int lane, float one) {
+  constexpr int G = (FULL && FPL % WBX_LIN_GROUP == 0) ? WBX_LIN_GROUP : 2;
   const int lo = d.lo, hi = d.hi;
   const uint32_t rb = smem_u32(row) - (uint32_t)d.base * 8u;  // shared address of source frame 0 (wraps; only sums are used)
   const double pos = d.pos, speed = d.speed;
@@ -491,29 +498,48 @@ __device__ __forceinline__ void consume_lin_t(const Desc& d, const uint8_t* row,
   const float2 neg1 = make_float2(-1.0f, -1.0f);
   const float2 one2 = make_float2(one, one);
 #pragma unroll
-  for (int i = 0; i < FPL / 2; i++) {
-    float2 term[2];
+  for (int m0 = 0; m0 < FPL; m0 += G) {
+    uint32_t addr[G];
+    float fx[G];
+    bool on[G];
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const int fr = lane + 32 * (2 * i + e);
-      term[e] = make_float2(0.0f, 0.0f);
-      if (FULL || (fr >= lo && fr < hi)) {
-        const double jj = __dadd_rn(jj0, (double)(32 * (2 * i + e)));  // exact small integers == (double)j
-        const double x = __dadd_rn(pos, __dmul_rn(jj, speed));   // sampler.cpp:50
-        const double t = __dadd_rd(x, M);                        // floor(x) + 2^52
-        const uint32_t ix = (uint32_t)__double2loint(t);         // (int64_t)x, :51
-        const float fx = __double2float_rn(__dsub_rn(x, __dsub_rn(t, M)));  // (float)(x - (double)ix), :52
-        const uint32_t addr = rb + ix * 8u;
-        const float2 a = lds_f2(addr), b = lds_f2(addr + 8u);
-        const float2 df = __ffma2_rn(a, neg1, b);                         // b - a (a * -1 is exact: one rounding)
-        const float2 pr = __fmul2_rn(make_float2(fx, fx), df);            // fx * (b - a)
-        const float2 sv = __ffma2_rn(pr, one2, a);                        // a + fx * (b - a), :55 (see `one` above)
-        term[e] = __fmul2_rn(__fmul2_rn(sv, g2), t2);
-        acc[i * 2 + e] = __fadd2_rn(acc[i * 2 + e], term[e]);
+    for (int u = 0; u < G; u++) {
+      const int fr = lane + 32 * (m0 + u);
+      on[u] = FULL || (fr >= lo && fr < hi);
+      addr[u] = 0u;
+      fx[u] = 0.0f;
+      if (on[u]) {
+        const double jj = __dadd_rn(jj0, (double)(32 * (m0 + u)));  // exact small integers == (double)j
+        const double x = __dadd_rn(pos, __dmul_rn(jj, speed));    // sampler.cpp:50
+        const double t = __dadd_rd(x, M);                         // floor(x) + 2^52
+        const uint32_t ix = (uint32_t)__double2loint(t);          // (int64_t)x, :51
+        fx[u] = __double2float_rn(__dsub_rn(x, __dsub_rn(t, M)));  // (float)(x - (double)ix), :52
+        addr[u] = rb + ix * 8u;
       }
     }
-    pkL = fmaxf(fmaxf(pkL, fabsf(term[0].x)), fabsf(term[1].x));
-    pkR = fmaxf(fmaxf(pkR, fabsf(term[0].y)), fabsf(term[1].y));
+    float2 a[G], b[G];
+#pragma unroll
+    for (int u = 0; u < G; u++) {
+      a[u] = make_float2(0.0f, 0.0f), b[u] = a[u];
+      if (on[u]) a[u] = lds_f2(addr[u]), b[u] = lds_f2(addr[u] + 8u);
+    }
+    float2 term[G];
+#pragma unroll
+    for (int u = 0; u < G; u++) {
+      term[u] = make_float2(0.0f, 0.0f);
+      if (on[u]) {
+        const float2 df = __ffma2_rn(a[u], neg1, b[u]);               // b - a (a * -1 is exact: one rounding)
+        const float2 pr = __fmul2_rn(make_float2(fx[u], fx[u]), df);  // fx * (b - a)
+        const float2 sv = __ffma2_rn(pr, one2, a[u]);                 // a + fx * (b - a), :55 (see `one` above)
+        term[u] = __fmul2_rn(__fmul2_rn(sv, g2), t2);
+        acc[m0 + u] = __fadd2_rn(acc[m0 + u], term[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < G; u += 2) {
+      pkL = fmaxf(fmaxf(pkL, fabsf(term[u].x)), fabsf(term[u + 1].x));
+      pkR = fmaxf(fmaxf(pkR, fabsf(term[u].y)), fabsf(term[u + 1].y));
+    }
   }
 }
 
