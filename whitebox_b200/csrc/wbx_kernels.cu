@@ -1334,26 +1334,41 @@ struct FxcShape {
   static constexpr int OW = OW_;    // output warps per track
   static constexpr int EQW = EQW_;  // EQ warps per track: 1 = all four biquads in one warp, 2 = a / b pipeline
   static constexpr int WARPS = 1 + EQW * TPC + TPC * OW;
-  static constexpr int THREADS = WARPS * 32;
+  // warp slots of the CTA; the 4-track shape gets three unused ones so that its roles can be placed per sub-partition
+  // (registers are allocated four warps at a time: 13 warps already cost 16)
+  static constexpr int SLOTS = (TPC == 4 && OW_ == 2 && EQW_ == 1) ? 16 : WARPS;
+  static constexpr int THREADS = SLOTS * 32;
   static constexpr int OLANES = OW * 32;       // lanes rendering / finishing one track
+};
+
+// Which role the warp in each slot of the CTA plays. A warp runs on sub-partition (slot % 4) of its SM, and the roles are
+// very different instruction streams — the serial warp and the EQ warps are dependent chains that need an issue slot the
+// cycle they become ready, the output warps are long independent streams — so WHERE a role sits decides how long it takes:
+// with the slots simply in role order (serial, EQ..., output...) the serial warp of the 4-track CTA shared a sub-partition
+// with an EQ warp and two output warps and took 86 % of the iteration (45 cycles per step of a 12-cycle chain), the EQ warp
+// next to it 83 % against 63 % for its three siblings (per-role clock64 counters, profiles/r02c_fx_roles.log).
+// code: 0 = serial warp, 1 + tl = EQ warp a of track tl, 9 + tl = EQ warp b, 32 + tl * OW + ow = output warp, 255 = unused
+struct FxcRoles {
+  uint8_t code[32];
 };
 
 template <int TPC, int OW_, int EQW_, int MINB>
 __global__ void __launch_bounds__((FxcShape<TPC, OW_, EQW_>::THREADS), MINB)
 fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells, DFx* __restrict__ fx, uint32_t n_fx, uint32_t N,
                 uint32_t S, uint32_t K, uint32_t B, uint32_t C, const float* __restrict__ poly, float* __restrict__ trackbuf,
-                uint64_t tbs) {
+                uint64_t tbs, const FxcRoles roles) {
   using SH = FxcShape<TPC, OW_, EQW_>;
   extern __shared__ __align__(16) unsigned char fxc_raw[];
   FxcSmem<TPC>& sm = *reinterpret_cast<FxcSmem<TPC>*>(fxc_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // roles: warp 0 = the serial warp (lane = pair), warps 1..TPC = EQ a, TPC+1..2TPC = EQ b (one of each per track), the
-  // rest = output warps
-  const bool w_serial = warp == 0, w_eq = warp >= 1 && warp <= SH::EQW * TPC;
-  const bool w_eqb = SH::EQW == 1 ? w_eq : (w_eq && warp > TPC);  // the warp that finishes the EQ and builds the intercepts
-  const bool w_eqa = SH::EQW == 1 ? w_eq : (w_eq && warp <= TPC);
-  const int oidx = warp - 1 - SH::EQW * TPC;
-  const int tl = w_serial ? (lane >> 1) : (w_eq ? (warp - 1) % TPC : oidx / SH::OW);  // local track of this thread
+  // roles by slot (FxcRoles): the serial warp (lane = pair), EQ a / EQ b (one of each per track), output warps
+  const int rc = roles.code[warp & 31];
+  if (rc == 255) return;  // unused slot: the CTA's barriers count the live warps only
+  const bool w_serial = rc == 0, w_eq = rc >= 1 && rc < 32;
+  const bool w_eqb = SH::EQW == 1 ? w_eq : (w_eq && rc >= 9);  // the warp that finishes the EQ and builds the intercepts
+  const bool w_eqa = SH::EQW == 1 ? w_eq : (w_eq && rc < 9);
+  const int oidx = rc - 32;
+  const int tl = w_serial ? (lane >> 1) : (w_eq ? (rc - 1) & 7 : oidx / SH::OW);  // local track of this thread
   const int ow = w_serial || w_eq ? 0 : oidx % SH::OW;
   const uint32_t e = blockIdx.x * TPC + (uint32_t)(tl < TPC ? tl : 0);
   const bool live_lane = tl < TPC && e < n_fx;
@@ -1449,6 +1464,14 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
 #pragma unroll 1
           for (int b = (SH::EQW == 2 && w_eqb) ? 2 : 0; b < ((SH::EQW == 2 && w_eqa) ? 2 : 4); b++) {
             const float2 b0 = f2(tr.cf[b][0]), na1 = f2(tr.cf[b][1]), na2 = f2(tr.cf[b][2]), B1 = f2(tr.cf[b][3]), B2 = f2(tr.cf[b][4]);
+            // everything the scan and the state update read from shared memory is fetched HERE, under the zero-state pass:
+            // inside the scan each of these loads sat on the critical path (load -> 2 dependent FMAs -> shuffle), and the
+            // EQ warp is the long pole of the CTA's pipeline. The scan steps are selects, not branches, for the same reason.
+            float4 sj[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) sj[j] = *reinterpret_cast<const float4*>(&tr.S[b][j][0]);  // A^(16 * 2^j)
+            const float2 in1 = tr.st[b][0], in2 = tr.st[b][1];  // state entering the chunk (L, R)
+            const float4 pl = *reinterpret_cast<const float4*>(&tr.P[b][len][0]);
             float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
             if (n == 512u) {  // every segment is full: no per-frame guards
 #pragma unroll
@@ -1472,22 +1495,19 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
               }
             }
             const float2 e1 = s1, e2 = s2;
-            const float2 in1 = tr.st[b][0], in2 = tr.st[b][1];  // state entering the chunk (L, R)
             float2 v1 = e1, v2 = e2;
-            if (lane == 0) {  // the incoming state enters through segment 0
-              v1 = __ffma2_rn(f2(tr.S[b][0][0]), in1, __ffma2_rn(f2(tr.S[b][0][1]), in2, e1));
-              v2 = __ffma2_rn(f2(tr.S[b][0][2]), in1, __ffma2_rn(f2(tr.S[b][0][3]), in2, e2));
+            {  // the incoming state enters through segment 0
+              const float2 w1 = __ffma2_rn(f2(sj[0].x), in1, __ffma2_rn(f2(sj[0].y), in2, e1));
+              const float2 w2 = __ffma2_rn(f2(sj[0].z), in1, __ffma2_rn(f2(sj[0].w), in2, e2));
+              if (lane == 0) v1 = w1, v2 = w2;
             }
 #pragma unroll
             for (int j = 0; j < 5; j++) {  // Kogge-Stone: v[l] += A^(16 d) v[l - d]
               const unsigned d = 1u << j;
               const float2 u1 = shfl_up2(v1, d), u2 = shfl_up2(v2, d);
-              if (lane >= (int)d) {
-                const float4 sj = *reinterpret_cast<const float4*>(&tr.S[b][j][0]);
-                const float2 n1 = __ffma2_rn(f2(sj.x), u1, __ffma2_rn(f2(sj.y), u2, v1));
-                const float2 n2 = __ffma2_rn(f2(sj.z), u1, __ffma2_rn(f2(sj.w), u2, v2));
-                v1 = n1, v2 = n2;
-              }
+              const float2 n1 = __ffma2_rn(f2(sj[j].x), u1, __ffma2_rn(f2(sj[j].y), u2, v1));
+              const float2 n2 = __ffma2_rn(f2(sj[j].z), u1, __ffma2_rn(f2(sj[j].w), u2, v2));
+              if (lane >= (int)d) v1 = n1, v2 = n2;  // lanes below d computed on their own values: dropped
             }
             float2 st1 = shfl_up2(v1, 1), st2 = shfl_up2(v2, 1);
             if (lane == 0) st1 = in1, st2 = in2;
@@ -1497,12 +1517,13 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
               const float2 pm = *reinterpret_cast<const float2*>(&tr.P[b][m][0]);
               xs[m] = __ffma2_rn(f2(pm.y), st2, __ffma2_rn(f2(pm.x), st1, xs[m]));
             }
-            // state after the chunk's last frame, from the lane that holds it
+            // state after the chunk's last frame, from the lane that holds it (every lane evaluates it, one stores)
+            const float2 ns1 = __ffma2_rn(f2(pl.x), st1, __ffma2_rn(f2(pl.y), st2, e1));
+            const float2 ns2 = __ffma2_rn(f2(pl.z), st1, __ffma2_rn(f2(pl.w), st2, e2));
             __syncwarp();
             if (lane == last) {
-              const float4 pl = *reinterpret_cast<const float4*>(&tr.P[b][len][0]);
-              tr.st[b][0] = __ffma2_rn(f2(pl.x), st1, __ffma2_rn(f2(pl.y), st2, e1));
-              tr.st[b][1] = __ffma2_rn(f2(pl.z), st1, __ffma2_rn(f2(pl.w), st2, e2));
+              tr.st[b][0] = ns1;
+              tr.st[b][1] = ns2;
             }
           }
 #pragma unroll
@@ -1779,12 +1800,49 @@ template <int TPC, int OW, int EQW, int MINB>
 static cudaError_t launch_effects_chain_t(const DSpan* spans, const DCell* cells, DFx* fx, uint32_t n_fx, uint32_t N, uint32_t S,
                                           uint32_t K, uint32_t B, uint32_t C, const float* poly, float* trackbuf, uint64_t tbs,
                                           cudaStream_t stream) {
+  using SH = FxcShape<TPC, OW, EQW>;
   auto kfn = fx_chain_kernel<TPC, OW, EQW, MINB>;
   const size_t smem = sizeof(FxcSmem<TPC>);
   cudaError_t err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  kfn<<<(n_fx + TPC - 1) / TPC, FxcShape<TPC, OW, EQW>::THREADS, smem, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf,
-                                                                                 tbs);
+  // slots in role order: serial, EQ a per track, EQ b per track, output warps
+  FxcRoles roles;
+  for (int i = 0; i < 32; i++) roles.code[i] = 255;
+  uint8_t want[32];  // every role of the shape, in role order: serial, EQ a per track, EQ b per track, output warps
+  int nw = 0;
+  want[nw++] = 0;
+  for (int t = 0; t < TPC; t++) want[nw++] = (uint8_t)(1 + t);
+  if (EQW == 2)
+    for (int t = 0; t < TPC; t++) want[nw++] = (uint8_t)(9 + t);
+  for (int o = 0; o < TPC * OW; o++) want[nw++] = (uint8_t)(32 + o);
+  for (int i = 0; i < nw; i++) roles.code[i] = want[i];
+  if (SH::SLOTS == 16 && nw == 13) {
+    // the 4-track CTA (13 warps in 16 slots) over the four sub-partitions (slot % 4): the serial warp next to two output
+    // warps (which spend much of an iteration waiting for memory), the EQ warps in pairs with one output warp, the other
+    // output warps pooled. Measured against role order and three other placements: profiles/r02c_fx_roles.log.
+    //   0: serial out out -   1: EQ0 EQ1 out -   2: EQ2 EQ3 out -   3: out out out out
+    static const uint8_t bal[16] = {0, 1, 3, 32, 33, 2, 4, 34, 35, 36, 37, 38, 255, 255, 255, 39};
+    for (int i = 0; i < 16; i++) roles.code[i] = bal[i];
+    if (const char* env = getenv("WBX_FX_LAYOUT")) {  // experiments: 16 comma-separated codes, every role exactly once
+      int v[16], got = 0;
+      for (const char* q = env; got < 16 && *q;) {
+        v[got++] = atoi(q);
+        while (*q && *q != ',') q++;
+        if (*q == ',') q++;
+      }
+      bool ok = got == 16;
+      for (int j = 0; j < nw && ok; j++) {
+        int c = 0;
+        for (int i = 0; i < 16; i++) c += v[i] == want[j];
+        ok = c == 1;
+      }
+      int live = 0;
+      for (int i = 0; i < 16 && ok; i++) live += v[i] != 255;
+      if (!ok || live != nw) return cudaErrorInvalidValue;
+      for (int i = 0; i < 16; i++) roles.code[i] = (uint8_t)v[i];
+    }
+  }
+  kfn<<<(n_fx + TPC - 1) / TPC, SH::THREADS, smem, stream>>>(spans, cells, fx, n_fx, N, S, K, B, C, poly, trackbuf, tbs, roles);
   return cudaGetLastError();
 }
 
