@@ -430,6 +430,42 @@ def test_unaligned_offsets_and_speeds(wb):
     assert_exact(run(gpu_engine(wb)), run(cpu_engine()), "unaligned/speeds")
 
 
+def test_lean_and_general_batches_alternate(wb):
+    """The mix kernel resolves 16 cells at a time and runs a batch whose cells all resolved to the same whole-tile
+    stereo-f32 kind through a lean loop, anything else through the general one; both share the staging counters and the
+    stage parities. 112 tracks = seven batches of every flavour in one tile — unity (K_FAST), a batch with silent and
+    late-starting tracks, linear resample (K_LIN), odd start offsets (K_UNI), int16 sources, a batch whose LAST cells are
+    silent in front of a lean batch (the general loop then leaves the pipeline full), unity again — over callbacks in
+    which the late clips start mid-block (partial tiles turn a lean batch into a general one for that callback only)."""
+    def run(mk):
+        rng = np.random.RandomState(77)
+        eng = mk(2, 512, 48000, 120.0)
+        n = 112
+        for t in range(n):
+            b = t // 16
+            eng.add_track(-4.0 - (t % 5), -0.8 + 0.1 * (t % 17), False)
+            fmt = sc.FMT_I16 if b == 4 else sc.FMT_F32
+            rate = 44100 if b == 2 else 48000
+            sid = eng.add_sample(sc._src(rng, 2, 40000, n, fmt), rate, fmt)
+            start = 0.0
+            if b == 1 and t % 3 == 0:
+                continue  # a silent track inside batch 1
+            if b == 1 and t % 3 == 1:
+                start = 0.011 * (t % 7 + 1)  # starts mid-block in a later callback
+            if b == 5 and t % 16 >= 13:
+                continue  # the batch's last cells are silent
+            if b == 6 and t % 16 == 2:
+                start = 0.037  # one late clip: batch 6 is general for one callback, lean afterwards
+            off = float(1 + t % 5) if b == 3 else 0.0
+            eng.add_clip(t, sid, start, 64.0, off, 1.0, 0.08 + 0.001 * (t % 9))  # the bus stays inside the clamp
+        eng.play()
+        return sc._collect(eng, [eng.process(6), eng.process(1), eng.process(3)], n)
+    ref = run(cpu_engine())
+    assert_exact(run(gpu_engine(wb)), ref, "lean/general batches")
+    assert_exact(run(gpu_engine(wb, False)), ref, "lean/general batches, per callback")
+    assert_tree(run(gpu_engine(wb, True, wb.SUM_TREE)), ref, "lean/general batches, tree order")
+
+
 def test_cfg2_full_track_count_vs_cpu(wb):
     """BASELINE cfg 2 at its full 1024 tracks, 4 callbacks: direct bit-exact comparison."""
     ref = sc.standard(cpu_engine(), 1024, 2, 48000, 4)
