@@ -18,6 +18,7 @@
 // x86-64 build (no FMA contraction); the arithmetic that decides parity also uses explicit _rn intrinsics.
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <type_traits>
 
 #include <cstdint>
@@ -1632,13 +1633,26 @@ fx_chain_kernel(const DSpan* __restrict__ spans, const DCell* __restrict__ cells
 #pragma unroll
             for (int q = 0; q < RQ; q++) rv[q] = make_float2(0.0f, 0.0f);
           } else {
-            const DSpan* sp = spans + cell.span;
-            if (sp->fmt == F_F32 && sp->nch == 2 && sp->speed == 1.0 && sp->fade == 0 && C == 2) {
+            // the fields of the span that decide the path, fetched together (four independent 16-byte loads, one round trip):
+            // tested one after the other through the pointer, each && was a dependent load + branch on the path that
+            // issues this chunk's clip loads
+            static_assert(offsetof(DSpan, base) == 0 && offsetof(DSpan, speed) == 16 && offsetof(DSpan, gain) == 32 &&
+                              offsetof(DSpan, dst_off) == 48 && offsetof(DSpan, fmt) == 56 && offsetof(DSpan, nch) == 64 &&
+                              offsetof(DSpan, fade) == 68,
+                          "DSpan layout");
+            const int4* spq = reinterpret_cast<const int4*>(spans + cell.span);
+            const int4 q0 = __ldg(spq), q1 = __ldg(spq + 1), q2 = __ldg(spq + 2), q3 = __ldg(spq + 3);
+            const int4 q4 = __ldg(spq + 4);
+            const void* sp_base = reinterpret_cast<const void*>(((uint64_t)(uint32_t)q0.y << 32) | (uint32_t)q0.x);
+            const double sp_speed = __hiloint2double(q1.y, q1.x);
+            const float sp_gain = __int_as_float(q2.x);
+            const uint32_t sp_dst_off = (uint32_t)q3.x, sp_fmt = (uint32_t)q3.z, sp_nch = (uint32_t)q4.x, sp_fade = (uint32_t)q4.y;
+            if (sp_fmt == F_F32 && sp_nch == 2 && sp_speed == 1.0 && sp_fade == 0 && C == 2) {
               // unity-speed stereo f32 clip: a scaled copy (src * gain, then the add into the cleared buffer: 0 + m)
               rmode = 1;
-              rlo = sp->dst_off, rhi = sp->dst_off + cell.n_act;
-              rgain = sp->gain;
-              const float2* src = reinterpret_cast<const float2*>(sp->base) + (int64_t)(uint32_t)(int64_t)cell.pos;
+              rlo = sp_dst_off, rhi = sp_dst_off + cell.n_act;
+              rgain = sp_gain;
+              const float2* src = reinterpret_cast<const float2*>(sp_base) + (int64_t)(uint32_t)(int64_t)cell.pos;
               if (rn == 512u && rlo <= rf0 && rhi >= rf0 + 512u) {  // a whole chunk inside the clip: no per-frame range checks
                 rmode = 3;
                 const float2* s0 = src + (rf0 - rlo) + ol;
